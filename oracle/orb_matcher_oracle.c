@@ -1,0 +1,266 @@
+/*
+ * orb_matcher_oracle.c -- CPU oracle (TEST INFRASTRUCTURE, see orb_oracle.h) for the
+ * ORBmatcher Hamming search: DescriptorDistance, SearchForInitialization and
+ * SearchByProjection(Frame&, vector<MapPoint*>&, th), plus the Frame grid they query.
+ *
+ * S/ = /root/reference/oRB_SLAM2_Android/src/main/jni/ORB_SLAM2/src/.  The pointer graph
+ * (Frame / MapPoint objects) is flattened to arrays; the loop structure, comparison
+ * operators, float types and iteration orders follow the cited lines.
+ */
+#include "orb_oracle.h"
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define GRID_COLS 64   /* I/Frame.h:41 */
+#define GRID_ROWS 48   /* I/Frame.h:40 */
+#define TH_HIGH 100    /* S/ORBmatcher.cc:37 */
+#define TH_LOW 50      /* S/ORBmatcher.cc:38 */
+#define HISTO_LENGTH 30
+
+/* S/ORBmatcher.cc:1651-1667: eight 32-bit words, SWAR population count of the XOR. */
+int orc_descriptor_distance(const uint8_t *a, const uint8_t *b)
+{
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t wa, wb;
+        memcpy(&wa, a + 4 * i, 4);
+        memcpy(&wb, b + 4 * i, 4);
+        uint32_t v = wa ^ wb;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0x0F0F0F0Fu) * 0x01010101u) >> 24);
+    }
+    return dist;
+}
+
+/* Frame::ComputeImageBounds with zero distortion (S/Frame.cc:582-588) and the inverse cell
+ * sizes of S/Frame.cc:317-318. */
+void orc_grid_bounds(orc_grid *g, int img_w, int img_h)
+{
+    g->min_x = 0.0f; g->max_x = (float)img_w;
+    g->min_y = 0.0f; g->max_y = (float)img_h;
+    g->inv_w = (float)GRID_COLS / (g->max_x - g->min_x);
+    g->inv_h = (float)GRID_ROWS / (g->max_y - g->min_y);
+}
+
+/* Frame::PosInGrid (S/Frame.cc:505-517): round-half-away (roundf), reject out of range. */
+static int pos_in_grid(const orc_grid *g, float x, float y, int *px, int *py)
+{
+    *px = (int)roundf((x - g->min_x) * g->inv_w);
+    *py = (int)roundf((y - g->min_y) * g->inv_h);
+    return !(*px < 0 || *px >= GRID_COLS || *py < 0 || *py >= GRID_ROWS);
+}
+
+/* Frame::AssignFeaturesToGrid (S/Frame.cc:336-357): cells keep keypoint indices in
+ * increasing index order.  Stored as CSR with cell = ix*GRID_ROWS + iy. */
+void orc_grid_assign(orc_grid *g, int n, const float *kx, const float *ky, const int32_t *octave,
+                     int32_t *items_storage)
+{
+    g->n = n; g->kx = kx; g->ky = ky; g->octave = octave; g->cell_items = items_storage;
+    int *cnt = (int *)calloc(GRID_COLS * GRID_ROWS, sizeof(int));
+    int *cell = (int *)malloc(sizeof(int) * (n + 1));
+    for (int i = 0; i < n; i++) {
+        int px, py;
+        cell[i] = pos_in_grid(g, kx[i], ky[i], &px, &py) ? px * GRID_ROWS + py : -1;
+        if (cell[i] >= 0) cnt[cell[i]]++;
+    }
+    g->cell_start[0] = 0;
+    for (int c = 0; c < GRID_COLS * GRID_ROWS; c++) g->cell_start[c + 1] = g->cell_start[c] + cnt[c];
+    memset(cnt, 0, sizeof(int) * GRID_COLS * GRID_ROWS);
+    for (int i = 0; i < n; i++)
+        if (cell[i] >= 0) items_storage[g->cell_start[cell[i]] + cnt[cell[i]]++] = i;
+    free(cnt); free(cell);
+}
+
+/* Frame::GetFeaturesInArea (S/Frame.cc:447-502). */
+int orc_features_in_area(const orc_grid *g, float x, float y, float r, int minLevel, int maxLevel,
+                         int32_t *out, int cap)
+{
+    int n = 0;
+    int minCX = (int)floorf((x - g->min_x - r) * g->inv_w);
+    if (minCX < 0) minCX = 0;
+    if (minCX >= GRID_COLS) return 0;
+    int maxCX = (int)ceilf((x - g->min_x + r) * g->inv_w);
+    if (maxCX > GRID_COLS - 1) maxCX = GRID_COLS - 1;
+    if (maxCX < 0) return 0;
+    int minCY = (int)floorf((y - g->min_y - r) * g->inv_h);
+    if (minCY < 0) minCY = 0;
+    if (minCY >= GRID_ROWS) return 0;
+    int maxCY = (int)ceilf((y - g->min_y + r) * g->inv_h);
+    if (maxCY > GRID_ROWS - 1) maxCY = GRID_ROWS - 1;
+    if (maxCY < 0) return 0;
+    const int check = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = minCX; ix <= maxCX; ix++)
+        for (int iy = minCY; iy <= maxCY; iy++) {
+            int c = ix * GRID_ROWS + iy;
+            for (int j = g->cell_start[c]; j < g->cell_start[c + 1]; j++) {
+                int idx = g->cell_items[j];
+                if (check) {
+                    if (g->octave[idx] < minLevel) continue;
+                    if (maxLevel >= 0 && g->octave[idx] > maxLevel) continue;
+                }
+                float dx = g->kx[idx] - x, dy = g->ky[idx] - y;
+                if (fabsf(dx) < r && fabsf(dy) < r) {
+                    if (n < cap) out[n] = idx;
+                    n++;
+                }
+            }
+        }
+    return n;
+}
+
+/* ORBmatcher::ComputeThreeMaxima (S/ORBmatcher.cc:1605-1646) on bin sizes. */
+static void three_maxima(const int *sizes, int L, int *i1, int *i2, int *i3)
+{
+    int m1 = 0, m2 = 0, m3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = sizes[i];
+        if (s > m1) { m3 = m2; m2 = m1; m1 = s; *i3 = *i2; *i2 = *i1; *i1 = i; }
+        else if (s > m2) { m3 = m2; m2 = s; *i3 = *i2; *i2 = i; }
+        else if (s > m3) { m3 = s; *i3 = i; }
+    }
+    if (m2 < 0.1f * (float)m1) { *i2 = -1; *i3 = -1; }
+    else if (m3 < 0.1f * (float)m1) { *i3 = -1; }
+}
+
+/* S/ORBmatcher.cc:409-524 */
+int orc_search_for_initialization(
+    int n1, const float *k1x, const float *k1y, const int32_t *k1oct, const float *k1ang, const uint8_t *d1,
+    int n2, const float *k2x, const float *k2y, const int32_t *k2oct, const float *k2ang, const uint8_t *d2,
+    int img_w, int img_h, float nnratio, int check_orientation, int window_size,
+    float *prev_matched, int32_t *matches12)
+{
+    (void)k1x; (void)k1y;
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+
+    orc_grid g;
+    int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n2 + 1));
+    orc_grid_bounds(&g, img_w, img_h);
+    orc_grid_assign(&g, n2, k2x, k2y, k2oct, items);
+
+    int *hist_bin = (int *)malloc(sizeof(int) * (n1 + 1));   /* bin of i1 in insertion order */
+    int *hist_i1 = (int *)malloc(sizeof(int) * (n1 + 1));
+    int nhist = 0;
+    const float factor = 1.0f / HISTO_LENGTH;                /* sic: the reference's bin width (:417) */
+
+    int *matched_dist = (int *)malloc(sizeof(int) * (n2 + 1));
+    int *matches21 = (int *)malloc(sizeof(int) * (n2 + 1));
+    for (int i = 0; i < n2; i++) { matched_dist[i] = INT_MAX; matches21[i] = -1; }
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n2 + 1));
+
+    for (int i1 = 0; i1 < n1; i1++) {
+        int level1 = k1oct[i1];
+        if (level1 > 0) continue;
+        int nc = orc_features_in_area(&g, prev_matched[2 * i1], prev_matched[2 * i1 + 1],
+                                      (float)window_size, level1, level1, cand, n2);
+        if (nc == 0) continue;
+        const uint8_t *da = d1 + 32 * (size_t)i1;
+        int best = INT_MAX, best2 = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            int i2 = cand[c];
+            int dist = orc_descriptor_distance(da, d2 + 32 * (size_t)i2);
+            if (matched_dist[i2] <= dist) continue;
+            if (dist < best) { best2 = best; best = dist; bestIdx2 = i2; }
+            else if (dist < best2) best2 = dist;
+        }
+        if (best <= TH_LOW) {
+            if ((float)best < (float)best2 * nnratio) {
+                if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2;
+                matches21[bestIdx2] = i1;
+                matched_dist[bestIdx2] = best;
+                nmatches++;
+                if (check_orientation) {
+                    float rot = k1ang[i1] - k2ang[bestIdx2];
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    hist_bin[nhist] = bin; hist_i1[nhist] = i1; nhist++;
+                }
+            }
+        }
+    }
+
+    if (check_orientation) {
+        int sizes[HISTO_LENGTH] = {0};
+        for (int k = 0; k < nhist; k++) sizes[hist_bin[k]]++;
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            int b = hist_bin[k];
+            if (b == ind1 || b == ind2 || b == ind3) continue;
+            if (matches12[hist_i1[k]] >= 0) { matches12[hist_i1[k]] = -1; nmatches--; }
+        }
+    }
+
+    for (int i1 = 0; i1 < n1; i1++)
+        if (matches12[i1] >= 0) {
+            prev_matched[2 * i1] = k2x[matches12[i1]];
+            prev_matched[2 * i1 + 1] = k2y[matches12[i1]];
+        }
+
+    free(cand); free(matches21); free(matched_dist); free(hist_i1); free(hist_bin); free(items);
+    return nmatches;
+}
+
+/* S/ORBmatcher.cc:47-139 */
+int orc_search_by_projection(
+    int nmp, const uint8_t *mp_in_view, const uint8_t *mp_bad, const float *mp_x, const float *mp_y,
+    const float *mp_xr, const int32_t *mp_level, const float *mp_viewcos, const uint8_t *mp_desc,
+    const int32_t *mp_obs,
+    int n, const float *kx, const float *ky, const int32_t *koct, const float *kuright, const uint8_t *kdesc,
+    int32_t *kp_mp, const int32_t *kp_mp_obs,
+    int nlevels, const float *scale_factors, int img_w, int img_h, float nnratio, float th)
+{
+    (void)nlevels;
+    int nmatches = 0;
+    const int bFactor = th != 1.0;
+    orc_grid g;
+    int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    orc_grid_bounds(&g, img_w, img_h);
+    orc_grid_assign(&g, n, kx, ky, koct, items);
+
+    for (int i = 0; i < nmp; i++) {
+        if (!mp_in_view[i]) continue;
+        if (mp_bad[i]) continue;
+        const int lvl = mp_level[i];
+        float r = ((double)mp_viewcos[i] > 0.998) ? 2.5f : 4.0f;     /* RadiusByViewingCos (:133-139) */
+        if (bFactor) r *= th;
+        const float rs = r * scale_factors[lvl];
+        int nc = orc_features_in_area(&g, mp_x[i], mp_y[i], rs, lvl - 1, lvl, cand, n);
+        if (nc == 0) continue;
+        const uint8_t *dm = mp_desc + 32 * (size_t)i;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            if (kp_mp[idx] != -1) {
+                int obs = kp_mp[idx] >= 0 ? mp_obs[kp_mp[idx]] : kp_mp_obs[idx];
+                if (obs > 0) continue;
+            }
+            if (kuright[idx] > 0) {
+                const float er = fabsf(mp_xr[i] - kuright[idx]);
+                if (er > rs) continue;
+            }
+            const int dist = orc_descriptor_distance(dm, kdesc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = koct[idx];
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = koct[idx];
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+            kp_mp[bestIdx] = i;
+            nmatches++;
+        }
+    }
+    free(cand); free(items);
+    return nmatches;
+}

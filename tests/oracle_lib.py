@@ -1,0 +1,260 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+import this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def build_oracle():
+    so = os.path.join(ORACLE_DIR, "liborb_oracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.c", "orb_matcher_oracle.c", "orb_oracle.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liborb_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build_oracle())
+        L.orc_round.argtypes = [C.c_float]; L.orc_round.restype = C.c_int
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]; L.orc_fast_atan2.restype = C.c_float
+        L.orc_sincosf.argtypes = [C.c_float, _f32p, _f32p]
+        L.orc_resize_linear_u8.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_copy_make_border_reflect101.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+        L.orc_fast9_16.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast9_16.restype = C.c_int
+        L.orc_gaussian_blur7.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_create.restype = C.c_void_p
+        L.orc_extractor_destroy.argtypes = [C.c_void_p]
+        L.orc_extractor_set_blur_variant.argtypes = [C.c_void_p, C.c_int]
+        for name in ("orc_scale_factors", "orc_inv_scale_factors", "orc_level_sigma2", "orc_inv_level_sigma2"):
+            getattr(L, name).argtypes = [C.c_void_p]; getattr(L, name).restype = _f32p
+        for name in ("orc_features_per_level", "orc_umax"):
+            getattr(L, name).argtypes = [C.c_void_p]; getattr(L, name).restype = C.POINTER(C.c_int)
+        L.orc_pattern.restype = C.POINTER(C.c_int8)
+        L.orc_extract.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p, C.c_int]
+        L.orc_extract.restype = C.c_int
+        for name in ("orc_level_width", "orc_level_height"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int]; getattr(L, name).restype = C.c_int
+        for name in ("orc_level_pixels", "orc_level_blurred"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int]; getattr(L, name).restype = C.c_void_p
+        for name in ("orc_level_candidates", "orc_level_keypoints"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+            getattr(L, name).restype = C.c_int
+        L.orc_distribute_octree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_void_p, C.c_int]
+        L.orc_distribute_octree.restype = C.c_int
+        L.orc_descriptor_distance.argtypes = [_u8p, _u8p]; L.orc_descriptor_distance.restype = C.c_int
+        L.orc_search_for_initialization.argtypes = (
+            [C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p] * 2 +
+            [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _f32p, _i32p])
+        L.orc_search_for_initialization.restype = C.c_int
+        L.orc_search_by_projection.argtypes = [
+            C.c_int, _u8p, _u8p, _f32p, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p,
+            C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p, _i32p,
+            C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.orc_search_by_projection.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+# ---- primitives -------------------------------------------------------------------------
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_ptr(src, _u8p), src.shape[1], src.shape[0], src.strides[0],
+                               _ptr(dst, _u8p), dw, dh, dw)
+    return dst
+
+
+def copy_make_border(src, border):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h + 2 * border, w + 2 * border), np.uint8)
+    lib().orc_copy_make_border_reflect101(_ptr(src, _u8p), w, h, src.strides[0], _ptr(dst, _u8p),
+                                          dst.strides[0], border)
+    return dst
+
+
+def fast(img, threshold, nms=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = (w // 2 + 2) * (h // 2 + 2) if nms else w * h
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_fast9_16(_ptr(img, _u8p), w, h, img.strides[0], threshold, int(nms), out.ctypes.data, cap)
+    assert n <= cap
+    return out[:n]
+
+
+def gaussian_blur7(img, variant=0):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    dst = np.empty_like(img)
+    lib().orc_gaussian_blur7(_ptr(img, _u8p), w, h, img.strides[0], _ptr(dst, _u8p), dst.strides[0], variant)
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def sincosf(a):
+    s = C.c_float(); c = C.c_float()
+    lib().orc_sincosf(float(a), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def distribute_octree(cands, minX, maxX, minY, maxY, N, tie_break=0):
+    cands = np.ascontiguousarray(cands, KP_DTYPE)
+    cap = N + 4 * 64 + 16
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_distribute_octree(cands.ctypes.data, len(cands), minX, maxX, minY, maxY, N, tie_break,
+                                    out.ctypes.data, cap)
+    assert n >= 0, n
+    return out[:n]
+
+
+# ---- extractor ---------------------------------------------------------------------------
+class OracleExtractor:
+    """Mirror of ORB_SLAM2::ORBextractor (I/ORBextractor.h:45-111) backed by the C oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, blur_variant=0):
+        self.L = lib()
+        self.h = self.L.orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        assert self.h
+        self.L.orc_extractor_set_blur_variant(self.h, blur_variant)
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+
+    def __del__(self):
+        try:
+            self.L.orc_extractor_destroy(self.h)
+        except Exception:
+            pass
+
+    def _farr(self, fn, n):
+        return np.ctypeslib.as_array(getattr(self.L, fn)(self.h), (n,)).copy()
+
+    @property
+    def scale_factors(self): return self._farr("orc_scale_factors", self.nlevels)
+    @property
+    def inv_scale_factors(self): return self._farr("orc_inv_scale_factors", self.nlevels)
+    @property
+    def level_sigma2(self): return self._farr("orc_level_sigma2", self.nlevels)
+    @property
+    def inv_level_sigma2(self): return self._farr("orc_inv_level_sigma2", self.nlevels)
+    @property
+    def features_per_level(self): return self._farr("orc_features_per_level", self.nlevels)
+    @property
+    def umax(self): return self._farr("orc_umax", 16)
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        cap = self.nfeatures + 8 * self.nlevels + 4 * 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_extract(self.h, _ptr(img, _u8p), w, h, img.strides[0], kps.ctypes.data,
+                               _ptr(desc, _u8p), cap)
+        if n < 0:
+            raise ValueError("oracle extract failed: %d" % n)
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_shape(self, l):
+        return self.L.orc_level_height(self.h, l), self.L.orc_level_width(self.h, l)
+
+    def level_pixels(self, l):
+        h, w = self.level_shape(l)
+        p = self.L.orc_level_pixels(self.h, l)
+        return np.ctypeslib.as_array(C.cast(p, _u8p), (h, w)).copy()
+
+    def level_blurred(self, l):
+        h, w = self.level_shape(l)
+        p = self.L.orc_level_blurred(self.h, l)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(C.cast(p, _u8p), (h, w)).copy()
+
+    def _kparr(self, fn, l):
+        p = C.c_void_p()
+        n = getattr(self.L, fn)(self.h, l, C.byref(p))
+        if n == 0:
+            return np.zeros(0, KP_DTYPE)
+        buf = (C.c_char * (n * 28)).from_address(p.value)
+        return np.frombuffer(buf, KP_DTYPE, n).copy()
+
+    def level_candidates(self, l): return self._kparr("orc_level_candidates", l)
+    def level_keypoints(self, l): return self._kparr("orc_level_keypoints", l)
+
+
+# ---- matcher -----------------------------------------------------------------------------
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_ptr(a, _u8p), _ptr(b, _u8p))
+
+
+def _f(a): return np.ascontiguousarray(a, np.float32)
+def _i(a): return np.ascontiguousarray(a, np.int32)
+def _b(a): return np.ascontiguousarray(a, np.uint8)
+
+
+def search_for_initialization(k1, d1, k2, d2, prev_matched, img_w, img_h, nnratio=0.9, check_ori=True, window=100):
+    """k1/k2: KP_DTYPE arrays (mvKeysUn); prev_matched: (n1,2) float32, updated copy returned."""
+    n1, n2 = len(k1), len(k2)
+    k1x, k1y, k1o, k1a = _f(k1["x"]), _f(k1["y"]), _i(k1["octave"]), _f(k1["angle"])
+    k2x, k2y, k2o, k2a = _f(k2["x"]), _f(k2["y"]), _i(k2["octave"]), _f(k2["angle"])
+    d1 = _b(d1); d2 = _b(d2)
+    pm = _f(prev_matched).copy()
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    n = lib().orc_search_for_initialization(
+        n1, _ptr(k1x, _f32p), _ptr(k1y, _f32p), _ptr(k1o, _i32p), _ptr(k1a, _f32p), _ptr(d1, _u8p),
+        n2, _ptr(k2x, _f32p), _ptr(k2y, _f32p), _ptr(k2o, _i32p), _ptr(k2a, _f32p), _ptr(d2, _u8p),
+        img_w, img_h, nnratio, int(check_ori), window, _ptr(pm, _f32p), _ptr(m12, _i32p))
+    return n, m12[:n1], pm
+
+
+def search_by_projection(mp, kp, kdesc, scale_factors, img_w, img_h, nnratio=0.8, th=1.0,
+                         kp_mp=None, kp_mp_obs=None):
+    """mp: dict of arrays (in_view,bad,x,y,xr,level,viewcos,desc,obs); kp: KP_DTYPE (mvKeysUn)."""
+    nmp, n = len(mp["x"]), len(kp)
+    kx, ky, ko = _f(kp["x"]), _f(kp["y"]), _i(kp["octave"])
+    kur = _f(mp.get("kuright", np.full(n, -1.0, np.float32)))
+    kdesc = _b(kdesc)
+    kp_mp = np.full(max(n, 1), -1, np.int32) if kp_mp is None else _i(kp_mp).copy()
+    kp_mp_obs = np.zeros(max(n, 1), np.int32) if kp_mp_obs is None else _i(kp_mp_obs)
+    a = {k: v for k, v in mp.items()}
+    iv, bad = _b(a["in_view"]), _b(a["bad"])
+    x, y, xr, lv, vc = _f(a["x"]), _f(a["y"]), _f(a["xr"]), _i(a["level"]), _f(a["viewcos"])
+    de, ob = _b(a["desc"]), _i(a["obs"])
+    sf = _f(scale_factors)
+    cnt = lib().orc_search_by_projection(
+        nmp, _ptr(iv, _u8p), _ptr(bad, _u8p), _ptr(x, _f32p), _ptr(y, _f32p), _ptr(xr, _f32p),
+        _ptr(lv, _i32p), _ptr(vc, _f32p), _ptr(de, _u8p), _ptr(ob, _i32p),
+        n, _ptr(kx, _f32p), _ptr(ky, _f32p), _ptr(ko, _i32p), _ptr(kur, _f32p), _ptr(kdesc, _u8p),
+        _ptr(kp_mp, _i32p), _ptr(kp_mp_obs, _i32p),
+        len(sf), _ptr(sf, _f32p), img_w, img_h, nnratio, th)
+    return cnt, kp_mp[:n]

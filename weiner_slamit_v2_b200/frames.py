@@ -1,0 +1,71 @@
+"""Seeded synthetic textured frames -- pure numpy, so the CPU oracle,
+the GPU path, the tests and the bench all see byte-identical inputs on every machine.
+
+frame(i) = 128 + three octaves of cubic-upsampled Gaussian noise (grid pitch 64/16/4 px,
+amplitude 40/30/20), clipped to uint8, then W*H/600 random filled grey rectangles.  The
+rectangles give FAST plenty of corners at every pyramid level; the noise gives the descriptors
+texture.
+"""
+import numpy as np
+
+
+def _cubic_matrix(n_out, n_in):
+    """(n_out x n_in) Catmull-Rom interpolation matrix sampling n_in knots over n_out pixels."""
+    pos = (np.arange(n_out) + 0.5) * (n_in - 1) / n_out
+    i0 = np.floor(pos).astype(np.int64)
+    t = pos - i0
+    w = np.stack([((-t + 2) * t - 1) * t / 2, ((3 * t - 5) * t * t + 2) / 2,
+                  ((-3 * t + 4) * t + 1) * t / 2, (t - 1) * t * t / 2], axis=1)
+    m = np.zeros((n_out, n_in))
+    for k in range(4):
+        idx = np.clip(i0 + k - 1, 0, n_in - 1)
+        np.add.at(m, (np.arange(n_out), idx), w[:, k])
+    return m
+
+
+_MATS = {}
+
+
+def _mat(n_out, n_in):
+    key = (n_out, n_in)
+    if key not in _MATS:
+        _MATS[key] = _cubic_matrix(n_out, n_in)
+    return _MATS[key]
+
+
+def synthetic_frame(index, width=640, height=480, seed_base=1000):
+    rng = np.random.default_rng(seed_base + int(index))
+    img = np.full((height, width), 128.0)
+    for pitch, amp in ((64, 40.0), (16, 30.0), (4, 20.0)):
+        gh, gw = height // pitch + 3, width // pitch + 3
+        g = rng.standard_normal((gh, gw))
+        img += amp * (_mat(height, gh) @ g @ _mat(width, gw).T)
+    img = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    nrect = width * height // 600
+    xs = rng.integers(0, width, nrect); ys = rng.integers(0, height, nrect)
+    ws = rng.integers(4, 60, nrect); hs = rng.integers(4, 60, nrect)
+    gs = rng.integers(0, 256, nrect)
+    for x, y, w, h, g in zip(xs, ys, ws, hs, gs):
+        img[y:y + h, x:x + w] = g
+    return img
+
+
+def synthetic_batch(first, count, width=640, height=480, seed_base=1000):
+    return np.stack([synthetic_frame(first + i, width, height, seed_base) for i in range(count)])
+
+
+def low_contrast_frame(index, width=640, height=480):
+    """Exercises the minThFAST retry: corners whose contrast sits between 7 and 20 grey levels."""
+    rng = np.random.default_rng(5000 + int(index))
+    img = np.full((height, width), 100, np.uint8)
+    n = width * height // 900
+    xs = rng.integers(0, width, n); ys = rng.integers(0, height, n)
+    ws = rng.integers(6, 50, n); hs = rng.integers(6, 50, n)
+    gs = rng.integers(100, 116, n)
+    for x, y, w, h, g in zip(xs, ys, ws, hs, gs):
+        img[y:y + h, x:x + w] = g
+    # a few strong corners so both thresholds are in play
+    for k in range(12):
+        x, y = rng.integers(30, width - 60), rng.integers(30, height - 60)
+        img[y:y + 25, x:x + 25] = 220
+    return img
