@@ -1,0 +1,173 @@
+/*
+ * orb_b200.h -- C ABI of liborb_b200.so: the B200 (sm_100a) implementation of the ORB-SLAM2
+ * front-end hot path of serviceberry3/weiner_slamit_v2.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer for this path: the seam is
+ * the two C++ classes ORB_SLAM2::ORBextractor (I/ORBextractor.h:45-111) and
+ * ORB_SLAM2::ORBmatcher (I/ORBmatcher.h:37-102), I/ = oRB_SLAM2_Android/src/main/jni/
+ * ORB_SLAM2/include/.  weiner_slamit_v2_b200/shim/ re-implements those two classes with
+ * unchanged signatures on top of the functions below (INTEGRATION.md shows the build line).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative ORBB200_E* code (orbb200_last_error() gives the text, per thread); nothing
+ * throws; a handle owns all device memory and one CUDA stream and is NOT re-entrant (same
+ * rule as an ORBextractor instance, S/Frame.cc:93-96 uses two instances from two threads);
+ * different handles may be used from different threads / on different GPUs.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBB200_OK            0
+#define ORBB200_EINVAL       -1   /* bad argument (null pointer, size out of range, ...) */
+#define ORBB200_ECUDA        -2   /* a CUDA runtime call or kernel failed */
+#define ORBB200_ECAPACITY    -3   /* an output buffer is smaller than the result */
+#define ORBB200_EGEOMETRY    -4   /* image geometry the reference algorithm is undefined on */
+#define ORBB200_ENODEVICE    -5   /* no CUDA device / wrong architecture */
+
+const char *orbb200_last_error(void);
+int orbb200_device_count(void);           /* number of visible CUDA devices (0 if none) */
+const char *orbb200_version(void);
+
+/* cv::KeyPoint, field for field (28 bytes). */
+typedef struct {
+    float x, y;       /* pt, in level-0 pixel units */
+    float size;       /* 31 * scale[octave], truncated to an integer value */
+    float angle;      /* degrees, [0,360] */
+    float response;   /* FAST corner score */
+    int32_t octave;
+    int32_t class_id; /* always -1 */
+} orbb200_keypoint;
+
+/* ------------------------------------------------------------------------------------- */
+/* ORBextractor                                                                          */
+/* ------------------------------------------------------------------------------------- */
+typedef struct orbb200_extractor orbb200_extractor;
+
+/* Replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (S/ORBextractor.cc:415-482).  width/height fix the frame geometry of this handle,
+ * max_batch the largest batch one call may carry, device the CUDA ordinal.
+ * blur_taps: 0 = OpenCV >= 3.x fixed-point Gaussian {18,34,48,56,48,34,18}/256,
+ *            1 = OpenCV 2.4.9 {18,34,49,55,49,34,18}/256 (what the Android build linked). */
+int orbb200_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                             int width, int height, int max_batch, int device, int blur_taps,
+                             orbb200_extractor **out);
+void orbb200_extractor_destroy(orbb200_extractor *h);
+
+/* Replaces the getters of I/ORBextractor.h:63-83 and the protected tables. Arrays have
+ * nlevels entries (umax: 16). Any pointer may be NULL. */
+int orbb200_extractor_tables(const orbb200_extractor *h, float *scale, float *inv_scale, float *sigma2,
+                             float *inv_sigma2, int *features_per_level, int *umax16);
+int orbb200_extractor_levels(const orbb200_extractor *h);
+/* Upper bound on keypoints per frame (sum over levels of quota+3): size output buffers with it. */
+int orbb200_extractor_max_keypoints(const orbb200_extractor *h);
+int orbb200_extractor_level_size(const orbb200_extractor *h, int level, int *w, int *hgt);
+
+/* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors)
+ * (S/ORBextractor.cc:1064-1136) for `batch` frames in HOST memory.  Frame f starts at
+ * images + f*frame_stride, rows are `stride` bytes apart.  keypoints: batch x cap entries,
+ * descriptors: batch x cap x 32 bytes, counts: batch ints; frame f's results start at index
+ * f*cap, in the reference's order (level-major, quadtree list order inside a level).
+ * cap must be >= orbb200_extractor_max_keypoints(). */
+int orbb200_extract_host(orbb200_extractor *h, const uint8_t *images, int batch, size_t stride, size_t frame_stride,
+                         orbb200_keypoint *keypoints, uint8_t *descriptors, int32_t *counts, int cap);
+
+/* Same, for frames already in DEVICE memory; outputs stay on the device.  Asynchronous on
+ * the handle's stream; orbb200_extractor_sync() waits.  d_keypoints/d_descriptors/d_counts
+ * may be NULL to use handle-owned buffers (fetch them with orbb200_extractor_outputs). */
+int orbb200_extract_device(orbb200_extractor *h, const uint8_t *d_images, int batch, size_t stride, size_t frame_stride,
+                           orbb200_keypoint *d_keypoints, uint8_t *d_descriptors, int32_t *d_counts, int cap);
+int orbb200_extractor_sync(orbb200_extractor *h);
+int orbb200_extractor_outputs(orbb200_extractor *h, orbb200_keypoint **d_keypoints, uint8_t **d_descriptors,
+                              int32_t **d_counts, int *cap);
+/* CUDA stream the handle launches on (a cudaStream_t), for event timing by the caller. */
+void *orbb200_extractor_stream(orbb200_extractor *h);
+/* Number of kernel launches the last extract call issued. */
+int orbb200_extractor_last_launches(const orbb200_extractor *h);
+
+/* Stage read-back of the most recent extract call (parity tests; also backs the public
+ * member mvImagePyramid of I/ORBextractor.h:85).  All copy into HOST buffers. */
+int orbb200_extractor_get_level(orbb200_extractor *h, int frame, int level, int blurred, uint8_t *dst, size_t dst_stride);
+/* FAST candidates of one level before the quadtree (S/ORBextractor.cc:805-849): x,y relative
+ * to the 16-px border, score; returned sorted into the reference's cell-row-major order. */
+int orbb200_extractor_get_candidates(orbb200_extractor *h, int frame, int level, int32_t *x, int32_t *y, int32_t *score,
+                                     int cap, int *n);
+/* keypoints of one level after DistributeOctTree (level coordinates, border included). */
+int orbb200_extractor_get_level_keypoints(orbb200_extractor *h, int frame, int level, int32_t *x, int32_t *y,
+                                          int32_t *score, int cap, int *n);
+
+/* ------------------------------------------------------------------------------------- */
+/* ORBmatcher                                                                            */
+/* ------------------------------------------------------------------------------------- */
+typedef struct orbb200_matcher orbb200_matcher;
+
+/* Scratch owner for the matching entry points (the reference's ORBmatcher is stateless,
+ * I/ORBmatcher.h:37-102; the handle only holds device buffers + a stream).
+ * max_items = largest number of frame pairs / frames per call, max_points = largest number
+ * of keypoints (or map points) per side. */
+int orbb200_matcher_create(int max_items, int max_points, int device, orbb200_matcher **out);
+void orbb200_matcher_destroy(orbb200_matcher *m);
+void *orbb200_matcher_stream(orbb200_matcher *m);
+int orbb200_matcher_sync(orbb200_matcher *m);
+int orbb200_matcher_last_launches(const orbb200_matcher *m);
+
+/* Replaces ORBmatcher::DescriptorDistance (S/ORBmatcher.cc:1651-1667) for n independent
+ * descriptor pairs a[i], b[i] (32 bytes each, HOST memory); dist[i] in 0..256. */
+int orbb200_descriptor_distance(orbb200_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *dist);
+
+/* One side of a frame for the search functions: SoA view of Frame::mvKeysUn / mDescriptors
+ * (I/Frame.h).  Arrays are `items` x `stride` entries; n[i] keypoints are valid in item i. */
+typedef struct {
+    const int32_t *n;        /* items */
+    const float *x, *y;      /* items x stride */
+    const int32_t *octave;   /* items x stride */
+    const float *angle;      /* items x stride (may be NULL where unused) */
+    const uint8_t *desc;     /* items x stride x 32 */
+    int stride;
+} orbb200_frame_view;
+
+/* Replaces ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+ * (S/ORBmatcher.cc:409-524) for `items` independent frame pairs.  img_w/img_h give the
+ * undistorted image bounds (Frame::mnMinX.. with zero distortion, S/Frame.cc:582-588).
+ * prev_matched: items x f1.stride x 2 floats, in/out.  matches12: items x f1.stride ints.
+ * nmatches: items ints.  All pointers are HOST pointers unless `on_device` is non-zero, in
+ * which case every pointer (including those inside the views) is a device pointer and the
+ * call is asynchronous on the matcher's stream. */
+int orbb200_search_for_initialization(orbb200_matcher *m, int items, const orbb200_frame_view *f1,
+                                      const orbb200_frame_view *f2, int img_w, int img_h, float nnratio,
+                                      int check_orientation, int window_size, float *prev_matched,
+                                      int32_t *matches12, int32_t *nmatches, int on_device);
+
+/* Map points flattened from vector<MapPoint*> (the "variables used by the tracking",
+ * I/MapPoint.h:96-104, plus GetDescriptor()/isBad()/Observations()). items x stride. */
+typedef struct {
+    const int32_t *n;
+    const uint8_t *in_view, *bad;          /* mbTrackInView, isBad() */
+    const float *proj_x, *proj_y, *proj_xr; /* mTrackProjX/Y/XR */
+    const int32_t *level;                   /* mnTrackScaleLevel */
+    const float *view_cos;                  /* mTrackViewCos */
+    const uint8_t *desc;                    /* GetDescriptor(), x32 */
+    const int32_t *obs;                     /* Observations() */
+    int stride;
+} orbb200_mappoint_view;
+
+/* Replaces ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)
+ * (S/ORBmatcher.cc:47-131) for `items` independent frames.  u_right: items x f.stride
+ * (Frame::mvuRight; NULL = monocular, all -1).  kp_mp: items x f.stride, in/out: index of
+ * the map point each keypoint holds (Frame::mvpMapPoints): -1 none, -2 a map point that is
+ * not in `mp` whose Observations() is in kp_mp_obs (may be NULL when no -2 is used).
+ * scale_factors: nlevels floats (Frame::mvScaleFactors). nmatches: items ints. */
+int orbb200_search_by_projection(orbb200_matcher *m, int items, const orbb200_frame_view *f,
+                                 const float *u_right, const orbb200_mappoint_view *mp, int32_t *kp_mp,
+                                 const int32_t *kp_mp_obs, const float *scale_factors, int nlevels, int img_w,
+                                 int img_h, float nnratio, float th, int32_t *nmatches, int on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,106 @@
+"""GPU parity: the CUDA ORBextractor (through the C ABI) against the CPU oracle, stage by stage
+and end to end, bit-exact.  Oracle = oracle/liborb_oracle.so (pinned against cv2 and against the
+reference's own compiled ORBextractor.cc, see test_oracle_*.py)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from weiner_slamit_v2_b200 import ORBextractor
+from weiner_slamit_v2_b200.frames import low_contrast_frame, synthetic_frame
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = (1000, 1.2, 8, 20, 7)
+
+
+def _cand_sorted(c):
+    return c["x"].astype(np.int32), c["y"].astype(np.int32), c["response"].astype(np.int32)
+
+
+def _compare_frame(ex, orc, frames, f, check_stages=True):
+    img = frames[f]
+    ko, do = orc(img)
+    if check_stages:
+        for l in range(ex.nlevels):
+            assert np.array_equal(ex.get_level(f, l), orc.level_pixels(l)), "pyramid level %d" % l
+            cx, cy, cs = ex.get_candidates(f, l)
+            ox, oy, os_ = _cand_sorted(orc.level_candidates(l))
+            assert np.array_equal(cx, ox) and np.array_equal(cy, oy) and np.array_equal(cs, os_), "FAST candidates level %d" % l
+            kx, ky, ks = ex.get_level_keypoints(f, l)
+            lk = orc.level_keypoints(l)
+            assert np.array_equal(kx, lk["x"].astype(np.int32)) and np.array_equal(ky, lk["y"].astype(np.int32)), "quadtree level %d" % l
+            assert np.array_equal(ks, lk["response"].astype(np.int32))
+            ob = orc.level_blurred(l)
+            if ob is not None:
+                assert np.array_equal(ex.get_level(f, l, blurred=True), ob), "blur level %d" % l
+    return ko, do
+
+
+@pytest.mark.parametrize("size", [(640, 480), (752, 480)])
+def test_stages_and_output_bit_exact(size):
+    w, h = size
+    frames = np.stack([synthetic_frame(i, w, h) for i in range(4)])
+    ex = ORBextractor(*PARAMS, width=w, height=h, max_batch=4)
+    orc = O.OracleExtractor(*PARAMS)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(4):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        n = counts[f]
+        assert n == len(ko)
+        assert kps[f, :n].tobytes() == ko.tobytes(), "keypoints differ"
+        assert np.array_equal(desc[f, :n], do), "descriptors differ"
+
+
+def test_single_frame_call_matches_batch():
+    img = synthetic_frame(7)
+    ex = ORBextractor(*PARAMS, max_batch=2)
+    k1, d1 = ex(img)
+    kb, db, cb = ex.extract_batch(np.stack([synthetic_frame(8), img]))
+    assert k1.tobytes() == kb[1, :cb[1]].tobytes() and np.array_equal(d1, db[1, :cb[1]])
+
+
+def test_low_contrast_retry_and_constant_image():
+    frames = np.stack([low_contrast_frame(0), np.full((480, 640), 77, np.uint8), low_contrast_frame(1)])
+    ex = ORBextractor(*PARAMS, max_batch=3)
+    orc = O.OracleExtractor(*PARAMS)
+    kps, desc, counts = ex.extract_batch(frames)
+    assert counts[1] == 0                                    # constant image: no keypoints, descriptors released
+    for f in (0, 2):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], do)
+
+
+def test_noise_image_many_candidates():
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (2, 480, 640)).astype(np.uint8)
+    ex = ORBextractor(*PARAMS, max_batch=2)
+    orc = O.OracleExtractor(*PARAMS)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(2):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], do)
+
+
+def test_other_parameters_1280x720_2000():
+    frames = np.stack([synthetic_frame(i, 1280, 720) for i in range(2)])
+    p = (2000, 1.2, 8, 20, 7)
+    ex = ORBextractor(*p, width=1280, height=720, max_batch=2)
+    orc = O.OracleExtractor(*p)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(2):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], do)
+
+
+def test_tables_match_oracle():
+    ex = ORBextractor(*PARAMS)
+    orc = O.OracleExtractor(*PARAMS)
+    assert np.array_equal(ex.GetScaleFactors(), orc.scale_factors)
+    assert np.array_equal(ex.GetInverseScaleFactors(), orc.inv_scale_factors)
+    assert np.array_equal(ex.GetScaleSigmaSquares(), orc.level_sigma2)
+    assert np.array_equal(ex.GetInverseScaleSigmaSquares(), orc.inv_level_sigma2)
+    assert np.array_equal(ex.mnFeaturesPerLevel, orc.features_per_level)
+    assert np.array_equal(ex.umax, orc.umax)

@@ -1,0 +1,1182 @@
+// orb_extractor.cu -- ORBextractor::operator() for batches of frames on B200 (sm_100a).
+//
+// Reference path: S/ORBextractor.cc (S/ = oRB_SLAM2_Android/src/main/jni/ORB_SLAM2/src/):
+//   ComputePyramid :1138-1168, ComputeKeyPointsOctTree :778-873, DistributeOctTree :552-776,
+//   IC_Angle :82-109, GaussianBlur call :1117, computeOrbDescriptor :113-152, operator() :1064-1136.
+// Everything here is integer / byte streaming work (HBM- and issue-bound): no tensor cores.
+//
+// Kernel map (one launch each per batch unless noted):
+//   k_resize     x (nlevels-1)  pyramid level l from level l-1, 11-bit fixed-point bilinear
+//   k_fast       one CTA per 30-px detection cell: FAST-9/16 score map in shared memory, 3x3 NMS,
+//                iniThFAST -> minThFAST retry decided per cell, candidates appended per (frame,level)
+//   k_quadtree   one CTA per (frame,level): DistributeOctTree as parallel rounds over a node table
+//   k_blur       7x7 fixed-point separable Gaussian, shared-memory tiles
+//   k_describe   one warp per keypoint: IC_Angle moments (warp reduction) + steered BRIEF + output
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+
+namespace orbb200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+constexpr int MAXL = 16;             // pyramid levels supported per handle
+constexpr int EDGE = 19;             // EDGE_THRESHOLD (S/ORBextractor.cc:79)
+constexpr int BORDER = EDGE - 3;     // minBorderX/Y (:789)
+constexpr int HALF_PATCH = 15;       // HALF_PATCH_SIZE (:78)
+constexpr int MAX_DIM = 4095;        // coordinates are packed into 12 bits
+
+struct LevelGeo {
+    int w, h, pitch;                 // level size; row pitch inside the pyramid / blur slabs
+    int nCols, nRows, wCell, hCell;  // FAST cell grid (:797-803)
+    int cellStart;                   // first CTA index of this level in k_fast's grid
+    int maxBX, maxBY;                // maxBorderX/Y (:791-792)
+    int N, nIni;                     // quadtree quota and number of root nodes (:556)
+    int candOff, candCap;            // slice of the per-frame candidate slab (u32 entries)
+    int kpOff, kpCap;                // slice of the per-frame level-keypoint slab
+    int xtabOff, ytabOff;            // resize tables (short4 entries) for producing this level
+    int blurTileStart, blurTilesX;   // k_blur tile table
+    float hX;                        // root node width (:558)
+    float scale, kpSize;             // mvScaleFactor[l]; (int)(PATCH_SIZE*scale) (:855)
+    long long pyrOff, blurOff;       // byte offsets inside a frame's slab
+};
+
+struct ExtractParams {
+    int nlevels, iniTh, minTh, batch;
+    const uint8_t* in;               // level 0 = the caller's frames
+    long long inFrameStride;
+    int inPitch;
+    uint8_t* pyr;                    // levels 1.. of every frame
+    long long pyrFrameBytes;
+    uint8_t* blur;                   // blurred levels 0.. of every frame
+    long long blurFrameBytes;
+    const short4* tabs;              // resize tables
+    uint32_t* cand;                  // FAST candidates: x | y<<12 | score<<24 (x,y relative to the 16-px border)
+    int* candCount;                  // batch x nlevels
+    int candFrameCap;
+    uint32_t* lkp;                   // per-level keypoints after the quadtree, same packing
+    int* lkpCount;                   // batch x nlevels
+    int kpFrameCap;
+    uint16_t* qtScratch;             // node slot per candidate, used only when a tree does not fit in smem
+    orbb200_keypoint* outKp;
+    uint8_t* outDesc;
+    int* outCount;
+    int outCap;
+    int* status;                     // device error bits
+    int blurVariant;
+    // k_fast shared-memory geometry
+    int fastTP, fastTH, fastSP, fastQCap, fastKCap;
+    // k_quadtree shared-memory geometry
+    int qtNC, qtPC;
+    LevelGeo lv[MAXL];
+};
+
+__device__ __forceinline__ const uint8_t* level_ptr(const ExtractParams& P, int l, int frame, int& pitch)
+{
+    if (l == 0) { pitch = P.inPitch; return P.in + (long long)frame * P.inFrameStride; }
+    pitch = P.lv[l].pitch;
+    return P.pyr + (long long)frame * P.pyrFrameBytes + P.lv[l].pyrOff;
+}
+
+enum { STATUS_QT_RUNAWAY = 1, STATUS_CAND_OVERFLOW = 2, STATUS_KP_OVERFLOW = 4 };
+
+// ======================================================================================
+// K1: pyramid level from the previous level (cv::resize INTER_LINEAR, 8UC1; :1157)
+// ======================================================================================
+// xtab[x] = (sx, alpha0, alpha1, sx+1 clamped), ytab[y] = (sy0, sy1, beta0, beta1), both computed on
+// the host with the reference's float/double arithmetic.  Each thread produces 4 adjacent pixels
+// and stores them as one 32-bit word (row pitch is a multiple of 16).
+__global__ void __launch_bounds__(256) k_resize(const ExtractParams P, int l)
+{
+    const LevelGeo& g = P.lv[l];
+    const int frame = blockIdx.z;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (y >= g.h || x0 >= g.w) return;
+    int sp;
+    const uint8_t* src = level_ptr(P, l - 1, frame, sp);
+    uint8_t* dst = P.pyr + (long long)frame * P.pyrFrameBytes + g.pyrOff;
+    const short4* xt = P.tabs + g.xtabOff;
+    const short4 yt = __ldg(P.tabs + g.ytabOff + y);
+    const uint8_t* s0 = src + (long long)yt.x * sp;
+    const uint8_t* s1 = src + (long long)yt.y * sp;
+    const int b0 = yt.z, b1 = yt.w;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = x0 + i;
+        if (x < g.w) {
+            const short4 t = __ldg(xt + x);
+            const int r0 = (int)__ldg(s0 + t.x) * t.y + (int)__ldg(s0 + t.w) * t.z;
+            const int r1 = (int)__ldg(s1 + t.x) * t.y + (int)__ldg(s1 + t.w) * t.z;
+            int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            out |= (uint32_t)v << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(dst + (long long)y * g.pitch + x0) = out;
+}
+
+// ======================================================================================
+// K2: per-cell FAST-9/16 + NMS + threshold retry (:805-849)
+// ======================================================================================
+// Bresenham ring of radius 3 (the order is cyclic, which is all the arc test needs).
+__constant__ int c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+__constant__ int c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+// Corner score of the pixel at c (shared-memory tile, pitch tp): the largest t such that 9
+// contiguous ring pixels are all > v+t or all < v-t, i.e. max over arcs of min |diff|, minus 1
+// (cv::cornerScore<16>).  Returns 0 when the pixel is not a corner at threshold t.
+__device__ __forceinline__ int fast_score(const uint8_t* c, int tp, int t)
+{
+    const int v = c[0];
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = (int)c[c_ring_dy[k] * tp + c_ring_dx[k]] - v;
+    // sliding minimum / maximum over windows of 9 on the circular 16-ring, by doubling
+    int lo2[16], hi2[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
+    int lo4[16], hi4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
+    int bright = -256, dark = 256;   // max over arcs of min(d); min over arcs of max(d)
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+        bright = max(bright, lo9);
+        dark = min(dark, hi9);
+    }
+    const int m = max(bright, -dark);
+    return m > t ? m - 1 : 0;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fast(const ExtractParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_nq, s_nk, s_nini, s_base, s_pos;
+
+    const int frame = blockIdx.y;
+    int l = 0;
+    while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].cellStart) l++;
+    const LevelGeo& g = P.lv[l];
+    const int c = blockIdx.x - g.cellStart;
+    const int ci = c / g.nCols, cj = c - ci * g.nCols;
+    const int iniY = BORDER + ci * g.hCell, iniX = BORDER + cj * g.wCell;
+    if (iniY >= g.maxBY - 3 || iniX >= g.maxBX - 6) return;            // :810, :819
+    const int maxY = min(iniY + g.hCell + 6, g.maxBY), maxX = min(iniX + g.wCell + 6, g.maxBX);
+    const int ww = maxX - iniX, wh = maxY - iniY;
+    if (ww < 7 || wh < 7) return;                                       // cv::FAST finds nothing in < 7 px
+    const int dw = ww - 6, dh = wh - 6;                                 // detection area (3-px FAST margin)
+
+    const int TP = P.fastTP, SP = P.fastSP;
+    uint8_t* tile = smem;                                               // [fastTH][TP]
+    uint8_t* score = tile + P.fastTH * TP;                              // [(dh+2)][SP], zero border
+    uint16_t* queue = reinterpret_cast<uint16_t*>(score + (P.fastTH - 4) * SP);
+    uint32_t* klist = reinterpret_cast<uint32_t*>(queue + P.fastQCap);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int pitch;
+    const uint8_t* img = level_ptr(P, l, frame, pitch);
+    img += (long long)iniY * pitch + iniX;
+
+    if (tid == 0) { s_nq = 0; s_nk = 0; s_nini = 0; s_pos = 0; }
+    for (int r = warp; r < wh; r += THREADS / 32)
+        for (int x = lane; x < ww; x += 32) tile[r * TP + x] = __ldg(img + (long long)r * pitch + x);
+    for (int i = tid; i < (dh + 2) * SP; i += THREADS) score[i] = 0;
+    __syncthreads();
+
+    const int tlow = min(P.iniTh, P.minTh);
+    // pass 1: cheap reject on two opposite ring pairs -- a 9-arc of one polarity contains at least
+    // one pixel of every opposite pair -- survivors are queued so pass 2 runs on dense warps.
+    for (int r = warp; r < dh; r += THREADS / 32)
+        for (int x = lane; x < dw; x += 32) {
+            const uint8_t* cpx = tile + (r + 3) * TP + x + 3;
+            const int v = cpx[0], hi = v + tlow, lo = v - tlow;
+            const int a = cpx[3 * TP], b = cpx[-3 * TP], e = cpx[3], f = cpx[-3];
+            const bool br = (a > hi || b > hi) && (e > hi || f > hi);
+            const bool dk = (a < lo || b < lo) && (e < lo || f < lo);
+            if (br || dk) queue[atomicAdd(&s_nq, 1)] = (uint16_t)(r * 64 + x);
+        }
+    __syncthreads();
+    const int nq = s_nq;
+    for (int i = tid; i < nq; i += THREADS) {
+        const int r = queue[i] >> 6, x = queue[i] & 63;
+        const int s = fast_score(tile + (r + 3) * TP + x + 3, TP, tlow);
+        if (s > 0) score[(r + 1) * SP + x + 1] = (uint8_t)s;
+        else queue[i] = 0xffff;
+    }
+    __syncthreads();
+    // pass 3: 3x3 non-max suppression (strictly greater than all 8 neighbours, others count 0)
+    for (int i = tid; i < nq; i += THREADS) {
+        if (queue[i] == 0xffff) continue;
+        const int r = queue[i] >> 6, x = queue[i] & 63;
+        const uint8_t* sp = score + (r + 1) * SP + x + 1;
+        const int s = sp[0];
+        if (s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
+            s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1]) {
+            const int xr = x + 3 + cj * g.wCell, yr = r + 3 + ci * g.hCell;   // relative to the border (:840-841)
+            klist[atomicAdd(&s_nk, 1)] = (uint32_t)xr | ((uint32_t)yr << 12) | ((uint32_t)s << 24);
+            if (s >= P.iniTh) atomicAdd(&s_nini, 1);
+        }
+    }
+    __syncthreads();
+    // threshold retry (:829-833): keypoints at iniThFAST if the cell has any, else those at minThFAST
+    const int nk = s_nk;
+    const bool useIni = s_nini > 0;
+    const int thr = useIni ? P.iniTh : P.minTh;
+    // (if iniTh < minTh and nothing reached iniTh, nothing reaches minTh either)
+    const int total = useIni ? s_nini : (P.minTh <= P.iniTh ? nk : 0);
+    if (total == 0) return;
+    if (tid == 0) s_base = atomicAdd(&P.candCount[frame * P.nlevels + l], total);
+    __syncthreads();
+    const int base = s_base;
+    uint32_t* out = P.cand + (long long)frame * P.candFrameCap + g.candOff;
+    for (int i = tid; i < nk; i += THREADS) {
+        const uint32_t e = klist[i];
+        if ((int)(e >> 24) >= thr) {
+            const int p = base + atomicAdd(&s_pos, 1);
+            if (p < g.candCap) out[p] = e;
+            else atomicOr(P.status, STATUS_CAND_OVERFLOW);
+        }
+    }
+}
+
+// ======================================================================================
+// K3: DistributeOctTree (:552-776) as parallel rounds
+// ======================================================================================
+// The reference keeps a std::list of nodes, always inserts at the front and erases split parents,
+// so the list is ordered by DESCENDING creation number at all times; the output order is that
+// order.  A breadth pass (:613-678) splits every node with > 1 point in list order; once
+// size + 3*expandable > N (:686) nodes are split largest-first -- std::sort on (count, node address)
+// read backwards (:694-699), where address order is creation order under a monotonic allocator
+// (the canonical tie-break) -- stopping as soon as the list has N nodes (:743).
+// Inside one round all splits are independent; the only sequential coupling is (a) the creation
+// numbers of the children and (b) where the N-cut falls, and both are prefix sums over the
+// processing order.  Nodes live in a slot table: the first non-empty child re-uses its parent's
+// slot, so the table never needs more than max-list-size + nIni entries.
+constexpr int QT_THREADS = 256;
+
+struct QtShared {
+    int size, nslots, nextseq, E, phase, finish, cut, rounds;
+    int warpsum[40];
+};
+
+__device__ __forceinline__ int qt_block_excl_scan(int* data, int n, int* warpsum)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += QT_THREADS) {
+        const int i = base + tid;
+        const int v = i < n ? data[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warpsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = lane < QT_THREADS / 32 ? warpsum[lane] : 0;
+            int s = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += y;
+            }
+            if (lane < QT_THREADS / 32) warpsum[lane] = s - w;
+            if (lane == 31) warpsum[32] = s;
+        }
+        __syncthreads();
+        if (i < n) data[i] = x - v + warpsum[warp] + carry;
+        carry += warpsum[32];
+        __syncthreads();
+    }
+    return carry;
+}
+
+__device__ __forceinline__ int qt_quadrant(uint32_t p, int2 mid)
+{
+    const int x = p & 0xfff, y = (p >> 12) & 0xfff;
+    return (x < mid.x ? 0 : 1) + (y < mid.y ? 0 : 2);
+}
+
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ QtShared S;
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.y, l = blockIdx.x;
+    const LevelGeo& g = P.lv[l];
+    const int N = g.N, NC = P.qtNC, PC = P.qtPC;
+    const int n = min(P.candCount[frame * P.nlevels + l], g.candCap);
+    const uint32_t* cand = P.cand + (long long)frame * P.candFrameCap + g.candOff;
+    uint32_t* lkp = P.lkp + (long long)frame * P.kpFrameCap + g.kpOff;
+
+    // shared-memory carve-up (sizes in units of NC / PC, see extractor_create)
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(smem);     // NC
+    int2* emid = reinterpret_cast<int2*>(best + NC);                             // NC
+    short4* nrect = reinterpret_cast<short4*>(emid + NC);                        // NC (x0,x1,y0,y1)
+    int* ncnt = reinterpret_cast<int*>(nrect + NC);                              // NC
+    int* nseq = ncnt + NC;                                                       // NC
+    int* erank = nseq + NC;                                                      // NC
+    int* elist = erank + NC;                                                     // NC
+    int* elist2 = elist + NC;                                                    // NC
+    int* scanC = elist2 + NC;                                                    // NC
+    int* scanG = scanC + NC;                                                     // NC
+    int* ccnt = scanG + NC;                                                      // 4*NC
+    int* cslot = ccnt + 4 * NC;                                                  // 4*NC
+    uint32_t* spts = reinterpret_cast<uint32_t*>(cslot + 4 * NC);                // PC
+    uint16_t* sslot = reinterpret_cast<uint16_t*>(spts + PC);                    // PC
+
+    const uint32_t* pts;
+    uint16_t* pslot;
+    if (n <= PC) {
+        for (int p = tid; p < n; p += QT_THREADS) spts[p] = cand[p];
+        pts = spts; pslot = sslot;
+    } else {   // oversized tree: run the same code out of global memory
+        pts = cand;
+        pslot = P.qtScratch + (long long)frame * P.candFrameCap + g.candOff;
+    }
+    for (int s = tid; s < NC; s += QT_THREADS) { ncnt[s] = 0; erank[s] = -1; }
+    __syncthreads();
+
+    // root nodes and initial assignment (:564-598)
+    const int nIni = g.nIni;
+    for (int i = tid; i < nIni; i += QT_THREADS) {
+        nrect[i] = make_short4((short)(int)(g.hX * (float)i), (short)(int)(g.hX * (float)(i + 1)), 0,
+                               (short)(g.maxBY - BORDER));
+        nseq[i] = nIni - 1 - i;
+    }
+    for (int p = tid; p < n; p += QT_THREADS) {
+        int r = (int)__fdiv_rn((float)(pts[p] & 0xfff), g.hX);
+        r = min(max(r, 0), nIni - 1);
+        pslot[p] = (uint16_t)r;
+        atomicAdd(&ncnt[r], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int size = 0, E = 0;
+        for (int i = 0; i < nIni; i++) {
+            if (ncnt[i] > 0) size++;
+            if (ncnt[i] > 1) elist[E++] = i;
+        }
+        S.size = size; S.nslots = nIni; S.nextseq = nIni; S.E = E; S.phase = 1; S.finish = 0; S.rounds = 0;
+    }
+    __syncthreads();
+
+    while (!S.finish) {
+        const int E = S.E, size = S.size, nslots = S.nslots, nextseq = S.nextseq, phase = S.phase;
+        // A: rank the nodes to split, remember their split point
+        for (int k = tid; k < E; k += QT_THREADS) {
+            const int s = elist[k];
+            erank[s] = k;
+            const short4 r = nrect[s];
+            emid[k] = make_int2(r.x + (r.y - r.x + 1) / 2, r.z + (r.w - r.z + 1) / 2);   // DivideNode :496-497
+            ccnt[4 * k] = ccnt[4 * k + 1] = ccnt[4 * k + 2] = ccnt[4 * k + 3] = 0;
+        }
+        if (tid == 0) S.cut = E;
+        __syncthreads();
+        // B: count the points of each child
+        for (int p = tid; p < n; p += QT_THREADS) {
+            const int k = erank[pslot[p]];
+            if (k >= 0) atomicAdd(&ccnt[4 * k + qt_quadrant(pts[p], emid[k])], 1);
+        }
+        __syncthreads();
+        // C: children per node, prefix sums in processing order, N-cut
+        for (int k = tid; k < E; k += QT_THREADS) {
+            const int c = (ccnt[4 * k] > 0) + (ccnt[4 * k + 1] > 0) + (ccnt[4 * k + 2] > 0) + (ccnt[4 * k + 3] > 0);
+            scanC[k] = c;
+            scanG[k] = c - 1;
+        }
+        __syncthreads();
+        const int totalC = qt_block_excl_scan(scanC, E, S.warpsum);
+        const int totalG = qt_block_excl_scan(scanG, E, S.warpsum);
+        if (phase == 2) {
+            for (int k = tid; k < E; k += QT_THREADS) {
+                const int gk = (k + 1 < E ? scanG[k + 1] : totalG) - scanG[k];
+                if (size + scanG[k] + gk >= N) atomicMin(&S.cut, k);        // break at :743
+            }
+            __syncthreads();
+        }
+        const int Ecut = S.cut < E ? S.cut + 1 : E;
+        const int grow = Ecut < E ? scanG[Ecut] : totalG;
+        const int made = Ecut < E ? scanC[Ecut] : totalC;
+        // D: create the children (n1..n4 order = quadrant order)
+        for (int k = tid; k < Ecut; k += QT_THREADS) {
+            const int s = elist[k];
+            const short4 r = nrect[s];
+            const int2 m = emid[k];
+            int j = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int cnt = ccnt[4 * k + q];
+                int slot = -1;
+                if (cnt > 0) {
+                    slot = j == 0 ? s : nslots + scanG[k] + j - 1;
+                    nrect[slot] = make_short4((q & 1) ? (short)m.x : r.x, (q & 1) ? r.y : (short)m.x,
+                                              (q & 2) ? (short)m.y : r.z, (q & 2) ? r.w : (short)m.y);
+                    ncnt[slot] = cnt;
+                    nseq[slot] = nextseq + scanC[k] + j;
+                    j++;
+                }
+                cslot[4 * k + q] = slot;
+            }
+        }
+        __syncthreads();
+        // E: move the points into their child
+        for (int p = tid; p < n; p += QT_THREADS) {
+            const int k = erank[pslot[p]];
+            if (k >= 0 && k < Ecut) pslot[p] = (uint16_t)cslot[4 * k + qt_quadrant(pts[p], emid[k])];
+        }
+        __syncthreads();
+        // F/G: clear ranks, collect the children that can still be split (creation order)
+        for (int k = tid; k < E; k += QT_THREADS) erank[elist[k]] = -1;
+        for (int i = tid; i < 4 * Ecut; i += QT_THREADS) ccnt[i] = ccnt[i] > 1 ? 1 : 0;
+        __syncthreads();
+        const int newE = qt_block_excl_scan(ccnt, 4 * Ecut, S.warpsum);
+        for (int i = tid; i < 4 * Ecut; i += QT_THREADS) {
+            const int s = cslot[i];
+            if (s >= 0 && ncnt[s] > 1) elist2[ccnt[i]] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int nsize = size + grow;
+            int fin = 0, nphase = phase;
+            if (nsize >= N || nsize == size) fin = 1;                        // :682 / :747
+            else if (phase == 1 && nsize + 3 * newE > N) nphase = 2;         // :686
+            if (++S.rounds > 4096) { fin = 1; atomicOr(P.status, STATUS_QT_RUNAWAY); }
+            if (nslots + grow > NC) { fin = 1; atomicOr(P.status, STATUS_KP_OVERFLOW); }
+            S.size = nsize; S.nslots = nslots + grow; S.nextseq = nextseq + made; S.E = newE;
+            S.phase = nphase; S.finish = fin;
+        }
+        __syncthreads();
+        if (!S.finish) {
+            if (S.phase == 1) {
+                // next breadth pass walks the list front to back = newest child first
+                for (int k = tid; k < newE; k += QT_THREADS) elist[k] = elist2[newE - 1 - k];
+            } else {
+                // largest first; equal counts: later-created node first
+                for (int k = tid; k < newE; k += QT_THREADS) {
+                    const int s = elist2[k], c = ncnt[s], q = nseq[s];
+                    int pos = 0;
+                    for (int j = 0; j < newE; j++) {
+                        const int t = elist2[j];
+                        const int ct = ncnt[t];
+                        pos += (ct > c) || (ct == c && nseq[t] > q);
+                    }
+                    elist[pos] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // best response per leaf; ties go to the earlier candidate in the reference's order
+    // (cells row-major, row-major inside a cell), recovered from the coordinates (:755-773)
+    const int nslots = S.nslots;
+    for (int s = tid; s < nslots; s += QT_THREADS) best[s] = 0ull;
+    __syncthreads();
+    for (int p = tid; p < n; p += QT_THREADS) {
+        const uint32_t e = pts[p];
+        const int x = e & 0xfff, y = (e >> 12) & 0xfff;
+        const unsigned long long ord = ((unsigned long long)((y - 3) / g.hCell) << 32) |
+                                       ((unsigned long long)((x - 3) / g.wCell) << 24) | ((unsigned long long)y << 12) | x;
+        const unsigned long long key = ((unsigned long long)(e >> 24) << 40) | (0xffffffffffull - ord);
+        atomicMax(&best[pslot[p]], key);
+    }
+    __syncthreads();
+    // list order = descending creation number
+    for (int s = tid; s < nslots; s += QT_THREADS) {
+        if (ncnt[s] <= 0) continue;
+        const int q = nseq[s];
+        int pos = 0;
+        for (int t = 0; t < nslots; t++) pos += (ncnt[t] > 0 && nseq[t] > q);
+        const unsigned long long key = best[s];
+        const unsigned long long ord = 0xffffffffffull - (key & 0xffffffffffull);
+        if (pos < g.kpCap) lkp[pos] = (uint32_t)(ord & 0xffffff) | ((uint32_t)(key >> 40) << 24);
+        else atomicOr(P.status, STATUS_KP_OVERFLOW);
+    }
+    if (tid == 0) P.lkpCount[frame * P.nlevels + l] = min(S.size, g.kpCap);
+}
+
+// ======================================================================================
+// K5: GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (:1117), 8.8 fixed point like OpenCV
+// ======================================================================================
+constexpr int BL_TW = 128, BL_TH = 32, BL_THREADS = 256;
+
+__device__ __forceinline__ int reflect101(int p, int n)
+{
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(BL_THREADS) k_blur(const ExtractParams P)
+{
+    __shared__ __align__(16) uint8_t tile[BL_TH + 6][BL_TW + 8];
+    __shared__ __align__(16) uint16_t hsum[BL_TH + 6][BL_TW];
+    const int frame = blockIdx.y;
+    int l = 0;
+    while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].blurTileStart) l++;
+    const LevelGeo& g = P.lv[l];
+    if (P.lkpCount[frame * P.nlevels + l] == 0) return;       // the reference skips empty levels (:1112)
+    const int t = blockIdx.x - g.blurTileStart;
+    const int ty = t / g.blurTilesX, tx = t - ty * g.blurTilesX;
+    const int x0 = tx * BL_TW, y0 = ty * BL_TH;
+    int pitch;
+    const uint8_t* img = level_ptr(P, l, frame, pitch);
+    const int k0 = 18, k1 = 34, k2 = P.blurVariant ? 49 : 48, k3 = P.blurVariant ? 55 : 56;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < (BL_TH + 6) * (BL_TW + 6); i += BL_THREADS) {
+        const int r = i / (BL_TW + 6), c = i - r * (BL_TW + 6);
+        const int sy = reflect101(min(y0 + r - 3, g.h + 2), g.h), sx = reflect101(min(x0 + c - 3, g.w + 2), g.w);
+        tile[r][c] = __ldg(img + (long long)sy * pitch + sx);
+    }
+    __syncthreads();
+    for (int i = tid; i < (BL_TH + 6) * BL_TW; i += BL_THREADS) {
+        const int r = i / BL_TW, c = i - r * BL_TW;
+        const uint8_t* p = &tile[r][c];
+        hsum[r][c] = (uint16_t)(k0 * (p[0] + p[6]) + k1 * (p[1] + p[5]) + k2 * (p[2] + p[4]) + k3 * p[3]);
+    }
+    __syncthreads();
+    uint8_t* dst = P.blur + (long long)frame * P.blurFrameBytes + g.blurOff;
+    for (int i = tid; i < BL_TH * (BL_TW / 4); i += BL_THREADS) {
+        const int r = i / (BL_TW / 4), c4 = (i - r * (BL_TW / 4)) * 4;
+        const int y = y0 + r, x = x0 + c4;
+        if (y >= g.h || x >= g.w) continue;
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t acc = (uint32_t)k0 * (hsum[r][c4 + j] + hsum[r + 6][c4 + j]) +
+                                 (uint32_t)k1 * (hsum[r + 1][c4 + j] + hsum[r + 5][c4 + j]) +
+                                 (uint32_t)k2 * (hsum[r + 2][c4 + j] + hsum[r + 4][c4 + j]) +
+                                 (uint32_t)k3 * hsum[r + 3][c4 + j];
+            const uint32_t v = min((acc + 32768u) >> 16, 255u);
+            out |= v << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (long long)y * g.pitch + x) = out;
+    }
+}
+
+// ======================================================================================
+// K4+K6: IC_Angle (:82-109) and computeOrbDescriptor (:113-152), one warp per keypoint
+// ======================================================================================
+__constant__ int c_umax[HALF_PATCH + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+__constant__ signed char c_pattern[1024] = {
+#include "../../include/orb_b200_pattern.inc"
+};
+
+// cv::fastAtan2: every step is a separately rounded fp32 operation (no FMA contraction).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = 2.2204460492503131e-16f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// glibc sinf/cosf (ARM optimized-routines sincosf): pi/2 reduction and polynomial in double,
+// one rounding to float.  Bit-identical to libm on every float in [0, 2*pi] (tested exhaustively
+// on the host restatement, oracle/orb_oracle.c:orc_sincosf).
+__device__ __forceinline__ float sc_poly(double x, double x2, int n, bool negcos)
+{
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+                 C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0) {
+        const double x3 = __dmul_rn(x, x2);
+        const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+        const double x7 = __dmul_rn(x3, x2);
+        const double s = __dadd_rn(x, __dmul_rn(x3, S1));
+        return __double2float_rn(__dadd_rn(s, __dmul_rn(x7, s1)));
+    }
+    const double sg = negcos ? -1.0 : 1.0;
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __dadd_rn(sg * C3, __dmul_rn(x2, sg * C4));
+    const double c1 = __dadd_rn(sg * C0, __dmul_rn(x2, sg * C1));
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __dadd_rn(c1, __dmul_rn(x4, sg * C2));
+    return __double2float_rn(__dadd_rn(c, __dmul_rn(x6, c2)));
+}
+
+__device__ __forceinline__ void libm_sincosf(float y, float& s, float& c)
+{
+    const double HPI_INV = 0x1.45F306DC9C883p+23, HPI = 0x1.921FB54442D18p0;
+    double x = (double)y;
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ff;
+    if (top < 0x3f4) {
+        if (top < 0x398) { s = y; c = 1.0f; return; }
+        const double x2 = __dmul_rn(x, x);
+        s = sc_poly(x, x2, 0, false);
+        c = sc_poly(x, x2, 1, false);
+        return;
+    }
+    const double r = __dmul_rn(x, HPI_INV);
+    const int n = ((int)r + 0x800000) >> 24;
+    x = __dsub_rn(x, __dmul_rn((double)n, HPI));
+    const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    const bool neg = (n & 2) != 0;
+    const double xs = __dmul_rn(x, sgn), x2 = __dmul_rn(x, x);
+    s = sc_poly(xs, x2, n, neg);
+    c = sc_poly(xs, x2, n ^ 1, neg);
+}
+
+constexpr int DESC_WARPS = 8;
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParams P)
+{
+    __shared__ short s_pat[16 * 32];     // [k][byte]: point 16*byte+k as x | y<<8 (bank-conflict free per k)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 512; i += DESC_WARPS * 32) {
+        const int byte = i >> 4, k = i & 15;
+        s_pat[k * 32 + byte] = (short)((c_pattern[2 * i] & 0xff) | ((int)c_pattern[2 * i + 1] << 8));
+    }
+    __syncthreads();
+    const int frame = blockIdx.y;
+    const int idx = blockIdx.x * DESC_WARPS + warp;        // slot in the frame's level-keypoint slab
+    if (idx >= P.kpFrameCap) return;
+    int l = 0;
+    while (l + 1 < P.nlevels && idx >= P.lv[l + 1].kpOff) l++;
+    const LevelGeo& g = P.lv[l];
+    const int i = idx - g.kpOff;
+    const int* counts = P.lkpCount + frame * P.nlevels;
+    if (i >= counts[l]) {
+        if (idx == 0 && lane == 0) {            // level 0 empty: this warp still publishes the frame total
+            int tot = 0;
+            for (int q = 0; q < P.nlevels; q++) tot += counts[q];
+            P.outCount[frame] = tot;
+        }
+        return;
+    }
+    int off = 0;
+    for (int q = 0; q < l; q++) off += counts[q];
+    if (idx == 0 && lane == 0) {
+        int tot = 0;
+        for (int q = 0; q < P.nlevels; q++) tot += counts[q];
+        P.outCount[frame] = tot;
+    }
+    const int o = off + i;
+    if (o >= P.outCap) { if (lane == 0) atomicOr(P.status, STATUS_KP_OVERFLOW); return; }
+
+    const uint32_t e = P.lkp[(long long)frame * P.kpFrameCap + idx];
+    const int x = (e & 0xfff) + BORDER, y = ((e >> 12) & 0xfff) + BORDER, score = e >> 24;   // :857-858
+
+    // ---- orientation: intensity centroid over the radius-15 disc of the UNBLURRED level ----
+    int pitch;
+    const uint8_t* c = level_ptr(P, l, frame, pitch);
+    c += (long long)y * pitch + x;
+    const int u = lane - HALF_PATCH;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+#pragma unroll 1
+        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
+            if (abs(u) <= c_umax[abs(v)]) {
+                const int val = __ldg(c + v * pitch + u);
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, d);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- descriptor on the BLURRED level: lane b produces byte b (pairs 8b..8b+7) ----
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+    float a, b;
+    libm_sincosf(__fmul_rn(angle, factorPI), b, a);
+    const uint8_t* cb = P.blur + (long long)frame * P.blurFrameBytes + g.blurOff + (long long)y * g.pitch + x;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int t[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int pk = s_pat[(2 * k + s) * 32 + lane];
+            const float px = (float)(signed char)(pk & 0xff), py = (float)(pk >> 8);
+            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            t[s] = __ldg(cb + ry * g.pitch + rx);
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    P.outDesc[((long long)frame * P.outCap + o) * 32 + lane] = (uint8_t)val;
+
+    // ---- keypoint record (cv::KeyPoint layout), coordinates scaled to level 0 (:1126-1132) ----
+    if (lane < 7) {
+        float fx = (float)x, fy = (float)y;
+        if (l != 0) { fx = __fmul_rn(fx, g.scale); fy = __fmul_rn(fy, g.scale); }
+        uint32_t w;
+        switch (lane) {
+            case 0: w = __float_as_uint(fx); break;
+            case 1: w = __float_as_uint(fy); break;
+            case 2: w = __float_as_uint(g.kpSize); break;
+            case 3: w = __float_as_uint(angle); break;
+            case 4: w = __float_as_uint((float)score); break;
+            case 5: w = (uint32_t)l; break;
+            default: w = 0xffffffffu; break;
+        }
+        reinterpret_cast<uint32_t*>(P.outKp + (long long)frame * P.outCap + o)[lane] = w;
+    }
+}
+
+}  // namespace orbb200
+
+// ======================================================================================
+// host side: handle, geometry, launches, C ABI
+// ======================================================================================
+using namespace orbb200;
+
+struct orbb200_extractor {
+    int nfeatures, nlevels, iniTh, minTh, width, height, maxBatch, device, blurTaps;
+    double scaleFactorD;
+    float scale[MAXL], invScale[MAXL], sigma2[MAXL], invSigma2[MAXL];
+    int perLevel[MAXL];
+    ExtractParams P;           // device pointers + geometry (in / batch patched per call)
+    cudaStream_t stream;
+    uint8_t* dIn;              // staging for host frames (level 0)
+    size_t inPitch;
+    int totalCells, totalBlurTiles, maxKp;
+    size_t fastSmem, qtSmem;
+    int lastLaunches, lastBatch;
+    const uint8_t* lastIn; long long lastInFrameStride; int lastInPitch;
+    orbb200_keypoint* dOutKp; uint8_t* dOutDesc; int* dOutCount;
+    void* pinned; size_t pinnedBytes;
+    std::vector<void*> allocs;
+};
+
+static int round_half_even(float v) { return (int)lrintf(v); }
+
+static short coef11(float c)
+{
+    int v = round_half_even(c * 2048.f);
+    return (short)std::min(std::max(v, -32768), 32767);
+}
+
+// cv::resize INTER_LINEAR coefficient tables for sw x sh -> dw x dh (see oracle/orb_oracle.c)
+static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<short4>& xt, std::vector<short4>& yt)
+{
+    const double scale_x = 1. / ((double)dw / sw), scale_y = 1. / ((double)dh / sh);
+    xt.resize(dw); yt.resize(dh);
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)floorf(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xt[dx] = make_short4((short)sx, coef11(1.f - fx), coef11(fx), (short)std::min(sx + 1, sw - 1));
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)floorf(fy);
+        fy -= sy;
+        const int y0 = std::min(std::max(sy, 0), sh - 1), y1 = std::min(std::max(sy + 1, 0), sh - 1);
+        yt[dy] = make_short4((short)y0, (short)y1, coef11(1.f - fy), coef11(fy));
+    }
+}
+
+template <typename T>
+static int dev_alloc(orbb200_extractor* h, T** p, size_t count)
+{
+    void* q = nullptr;
+    ORB_CUDA(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 256)));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return ORBB200_OK;
+}
+
+extern "C" const char* orbb200_last_error(void) { return g_err; }
+extern "C" const char* orbb200_version(void) { return "orb_b200 0.1 (sm_100a)"; }
+extern "C" int orbb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                                        int width, int height, int max_batch, int device, int blur_taps,
+                                        orbb200_extractor** out)
+{
+    if (!out) { set_error("out is NULL"); return ORBB200_EINVAL; }
+    *out = nullptr;
+    if (nlevels < 1 || nlevels > MAXL || nfeatures < 0 || max_batch < 1 || !(scaleFactor > 1.0f) ||
+        width < 1 || height < 1 || width > MAX_DIM || height > MAX_DIM || iniThFAST < 0 || minThFAST < 0 ||
+        iniThFAST > 255 || minThFAST > 255) {
+        set_error("invalid extractor parameters");
+        return ORBB200_EINVAL;
+    }
+    int ndev = orbb200_device_count();
+    if (device < 0 || device >= ndev) { set_error("CUDA device %d not available (%d visible)", device, ndev); return ORBB200_ENODEVICE; }
+    ORB_CUDA(cudaSetDevice(device));
+
+    orbb200_extractor* h = new orbb200_extractor();
+    h->nfeatures = nfeatures; h->nlevels = nlevels; h->iniTh = iniThFAST; h->minTh = minThFAST;
+    h->width = width; h->height = height; h->maxBatch = max_batch; h->device = device; h->blurTaps = blur_taps ? 1 : 0;
+    h->pinned = nullptr; h->pinnedBytes = 0; h->lastLaunches = 0; h->lastBatch = 0; h->lastIn = nullptr;
+    // ---- constructor tables (S/ORBextractor.cc:421-455); scaleFactor is held in a double (I/ORBextractor.h:98)
+    h->scaleFactorD = (double)scaleFactor;
+    h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        h->scale[i] = (float)((double)h->scale[i - 1] * h->scaleFactorD);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) { h->invScale[i] = 1.0f / h->scale[i]; h->invSigma2[i] = 1.0f / h->sigma2[i]; }
+    {
+        const float factor = (float)(1.0 / h->scaleFactorD);
+        float desired = (float)nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+        int sum = 0;
+        for (int l = 0; l < nlevels - 1; l++) {
+            h->perLevel[l] = round_half_even(desired);
+            sum += h->perLevel[l];
+            desired *= factor;
+        }
+        h->perLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
+    }
+
+    // ---- per-level geometry
+    ExtractParams& P = h->P;
+    memset(&P, 0, sizeof(P));
+    P.nlevels = nlevels; P.iniTh = iniThFAST; P.minTh = minThFAST; P.blurVariant = h->blurTaps;
+    std::vector<short4> tabs;
+    long long pyrOff = 0, blurOff = 0;
+    int cells = 0, candOff = 0, kpOff = 0, tiles = 0, maxWCell = 0, maxHCell = 0, maxKpCap = 0;
+    for (int l = 0; l < nlevels; l++) {
+        LevelGeo& g = P.lv[l];
+        g.w = round_half_even((float)width * h->invScale[l]);      // :1145
+        g.h = round_half_even((float)height * h->invScale[l]);
+        g.pitch = (int)align_up(g.w, 16);
+        g.maxBX = g.w - EDGE + 3; g.maxBY = g.h - EDGE + 3;
+        const float fw = (float)(g.maxBX - BORDER), fh = (float)(g.maxBY - BORDER);
+        if (fw < 30.f || fh < 30.f) {
+            set_error("level %d is %dx%d: narrower than one 30-px FAST cell plus borders; the reference divides by zero here", l, g.w, g.h);
+            delete h; return ORBB200_EGEOMETRY;
+        }
+        g.nCols = (int)(fw / 30.f); g.nRows = (int)(fh / 30.f);                    // :797-798
+        g.wCell = (int)ceilf(fw / g.nCols); g.hCell = (int)ceilf(fh / g.nRows);    // :799-800
+        g.cellStart = cells; cells += g.nCols * g.nRows;
+        maxWCell = std::max(maxWCell, g.wCell); maxHCell = std::max(maxHCell, g.hCell);
+        g.N = h->perLevel[l];
+        g.nIni = (int)roundf((float)(g.maxBX - BORDER) / (g.maxBY - BORDER));      // :556
+        if (g.nIni < 1) {
+            set_error("level %d aspect ratio %d:%d rounds to zero quadtree roots; the reference divides by zero here", l, g.w, g.h);
+            delete h; return ORBB200_EGEOMETRY;
+        }
+        g.hX = (float)(g.maxBX - BORDER) / g.nIni;                                  // :558
+        // NMS keeps at most one corner per 2x2 block of the detection area
+        g.candCap = ((g.maxBX - BORDER) / 2 + 2) * ((g.maxBY - BORDER) / 2 + 2);
+        g.candOff = candOff; candOff += (int)align_up(g.candCap, 64);
+        g.kpCap = std::max(g.N + 3, 4 * g.nIni);
+        g.kpOff = kpOff; kpOff += g.kpCap;
+        maxKpCap = std::max(maxKpCap, g.kpCap + g.nIni);
+        g.scale = h->scale[l];
+        g.kpSize = (float)(int)(31 * h->scale[l]);                                   // :855
+        g.blurOff = blurOff; blurOff += (long long)align_up((size_t)g.pitch * g.h, 256);
+        if (l > 0) {
+            g.pyrOff = pyrOff; pyrOff += (long long)align_up((size_t)g.pitch * g.h, 256);
+            std::vector<short4> xt, yt;
+            build_resize_tables(P.lv[l - 1].w, P.lv[l - 1].h, g.w, g.h, xt, yt);
+            g.xtabOff = (int)tabs.size(); tabs.insert(tabs.end(), xt.begin(), xt.end());
+            g.ytabOff = (int)tabs.size(); tabs.insert(tabs.end(), yt.begin(), yt.end());
+        }
+        g.blurTilesX = (g.w + BL_TW - 1) / BL_TW;
+        g.blurTileStart = tiles; tiles += g.blurTilesX * ((g.h + BL_TH - 1) / BL_TH);
+    }
+    h->totalCells = cells; h->totalBlurTiles = tiles; h->maxKp = kpOff;
+    P.pyrFrameBytes = std::max<long long>(pyrOff, 256); P.blurFrameBytes = blurOff;
+    P.candFrameCap = candOff; P.kpFrameCap = kpOff; P.outCap = kpOff;
+
+    // k_fast shared memory: window tile, score map with a zero ring, candidate queue, kept list
+    if (maxWCell > 63 - 6 || maxHCell > 63 - 6) { set_error("FAST cell larger than 57 px"); delete h; return ORBB200_EGEOMETRY; }
+    P.fastTP = (int)align_up(maxWCell + 6, 4); P.fastTH = maxHCell + 6;
+    P.fastSP = (int)align_up(maxWCell + 2, 4);
+    P.fastQCap = (int)align_up((size_t)maxWCell * maxHCell, 8);
+    P.fastKCap = ((maxWCell + 1) / 2) * ((maxHCell + 1) / 2) + 8;
+    h->fastSmem = (size_t)P.fastTH * P.fastTP + (size_t)(P.fastTH - 4) * P.fastSP + 2 * (size_t)P.fastQCap + 4 * (size_t)P.fastKCap;
+    h->fastSmem = align_up(h->fastSmem, 16);
+    // k_quadtree shared memory: 88 bytes per node slot + 6 bytes per candidate held on chip
+    P.qtNC = (int)align_up(maxKpCap + 8, 8);
+    const size_t perNode = 8 + 8 + 8 + 4 * 7 + 16 + 16;
+    const size_t budget = 200 * 1024;
+    if (perNode * P.qtNC + 6 * 1024 > budget) { set_error("nfeatures too large for the on-chip quadtree (%d node slots)", P.qtNC); delete h; return ORBB200_EINVAL; }
+    P.qtPC = (int)std::min<size_t>(8192, (budget - perNode * P.qtNC) / 6) & ~7;
+    h->qtSmem = perNode * P.qtNC + 6 * (size_t)P.qtPC;
+
+    // ---- device memory
+    h->inPitch = align_up(width, 16);
+    int rc;
+#define TRY(x) do { rc = (x); if (rc != ORBB200_OK) { orbb200_extractor_destroy(h); return rc; } } while (0)
+    short4* dTabs = nullptr;
+    TRY(dev_alloc(h, &h->dIn, h->inPitch * height * (size_t)max_batch));
+    TRY(dev_alloc(h, &P.pyr, (size_t)P.pyrFrameBytes * max_batch));
+    TRY(dev_alloc(h, &P.blur, (size_t)P.blurFrameBytes * max_batch));
+    TRY(dev_alloc(h, &dTabs, tabs.size() + 1));
+    TRY(dev_alloc(h, &P.cand, (size_t)P.candFrameCap * max_batch));
+    TRY(dev_alloc(h, &P.qtScratch, (size_t)P.candFrameCap * max_batch));
+    TRY(dev_alloc(h, &P.candCount, (size_t)nlevels * max_batch));
+    TRY(dev_alloc(h, &P.lkp, (size_t)P.kpFrameCap * max_batch));
+    TRY(dev_alloc(h, &P.lkpCount, (size_t)nlevels * max_batch));
+    TRY(dev_alloc(h, &h->dOutKp, (size_t)P.outCap * max_batch));
+    TRY(dev_alloc(h, &h->dOutDesc, (size_t)P.outCap * max_batch * 32));
+    TRY(dev_alloc(h, &h->dOutCount, (size_t)max_batch));
+    TRY(dev_alloc(h, &P.status, 1));
+#undef TRY
+    P.tabs = dTabs;
+    cudaError_t e = cudaSuccess;
+    if (!tabs.empty()) e = cudaMemcpy(dTabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(P.status, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qtSmem);
+    if (e != cudaSuccess) {
+        set_error("extractor_create: %s", cudaGetErrorString(e));
+        orbb200_extractor_destroy(h);
+        return ORBB200_ECUDA;
+    }
+    *out = h;
+    return ORBB200_OK;
+}
+
+extern "C" void orbb200_extractor_destroy(orbb200_extractor* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+}
+
+extern "C" int orbb200_extractor_tables(const orbb200_extractor* h, float* scale, float* inv_scale, float* sigma2,
+                                        float* inv_sigma2, int* features_per_level, int* umax16)
+{
+    if (!h) { set_error("null handle"); return ORBB200_EINVAL; }
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    for (int i = 0; i < h->nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->invScale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->invSigma2[i];
+        if (features_per_level) features_per_level[i] = h->perLevel[i];
+    }
+    if (umax16) memcpy(umax16, umax, sizeof(umax));
+    return ORBB200_OK;
+}
+extern "C" int orbb200_extractor_levels(const orbb200_extractor* h) { return h ? h->nlevels : ORBB200_EINVAL; }
+extern "C" int orbb200_extractor_max_keypoints(const orbb200_extractor* h) { return h ? h->maxKp : ORBB200_EINVAL; }
+extern "C" int orbb200_extractor_level_size(const orbb200_extractor* h, int level, int* w, int* hgt)
+{
+    if (!h || level < 0 || level >= h->nlevels) { set_error("bad level"); return ORBB200_EINVAL; }
+    if (w) *w = h->P.lv[level].w;
+    if (hgt) *hgt = h->P.lv[level].h;
+    return ORBB200_OK;
+}
+extern "C" void* orbb200_extractor_stream(orbb200_extractor* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int orbb200_extractor_last_launches(const orbb200_extractor* h) { return h ? h->lastLaunches : 0; }
+
+// enqueue the whole pipeline for `batch` frames whose level 0 is at d_images
+static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, size_t stride, size_t frame_stride,
+                   orbb200_keypoint* d_kp, uint8_t* d_desc, int32_t* d_counts, int cap)
+{
+    ExtractParams P = h->P;
+    P.batch = batch; P.in = d_images; P.inPitch = (int)stride; P.inFrameStride = (long long)frame_stride;
+    P.outKp = d_kp; P.outDesc = d_desc; P.outCount = d_counts; P.outCap = cap;
+    cudaStream_t st = h->stream;
+    int launches = 0;
+    ORB_CUDA(cudaMemsetAsync(P.candCount, 0, sizeof(int) * P.nlevels * batch, st));
+    for (int l = 1; l < P.nlevels; l++) {
+        const LevelGeo& g = P.lv[l];
+        dim3 grid((g.w + 127) / 128, (g.h + 7) / 8, batch), block(32, 8);
+        k_resize<<<grid, block, 0, st>>>(P, l);
+        ORB_CHECK_LAUNCH("k_resize"); launches++;
+    }
+    k_fast<128><<<dim3(h->totalCells, batch), 128, h->fastSmem, st>>>(P);
+    ORB_CHECK_LAUNCH("k_fast"); launches++;
+    k_quadtree<<<dim3(P.nlevels, batch), QT_THREADS, h->qtSmem, st>>>(P);
+    ORB_CHECK_LAUNCH("k_quadtree"); launches++;
+    k_blur<<<dim3(h->totalBlurTiles, batch), BL_THREADS, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_blur"); launches++;
+    k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_describe"); launches++;
+    h->lastLaunches = launches; h->lastBatch = batch;
+    h->lastIn = d_images; h->lastInPitch = (int)stride; h->lastInFrameStride = (long long)frame_stride;
+    return ORBB200_OK;
+}
+
+static int check_status(orbb200_extractor* h)
+{
+    int st = 0;
+    ORB_CUDA(cudaMemcpyAsync(&st, h->P.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ORB_CUDA(cudaStreamSynchronize(h->stream));
+    if (st) {
+        cudaMemsetAsync(h->P.status, 0, sizeof(int), h->stream);
+        set_error("device-side failure bits 0x%x (1=quadtree runaway, 2=candidate overflow, 4=keypoint overflow)", st);
+        return ORBB200_ECUDA;
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_extract_device(orbb200_extractor* h, const uint8_t* d_images, int batch, size_t stride,
+                                      size_t frame_stride, orbb200_keypoint* d_keypoints, uint8_t* d_descriptors,
+                                      int32_t* d_counts, int cap)
+{
+    if (!h || !d_images) { set_error("null handle or image pointer"); return ORBB200_EINVAL; }
+    if (batch < 1 || batch > h->maxBatch) { set_error("batch %d outside 1..%d", batch, h->maxBatch); return ORBB200_EINVAL; }
+    if (stride < (size_t)h->width) { set_error("stride smaller than the frame width"); return ORBB200_EINVAL; }
+    if (!d_keypoints && !d_descriptors && !d_counts) { d_keypoints = h->dOutKp; d_descriptors = h->dOutDesc; d_counts = h->dOutCount; cap = h->maxKp; }
+    if (!d_keypoints || !d_descriptors || !d_counts) { set_error("output pointers must be all set or all NULL"); return ORBB200_EINVAL; }
+    if (cap < h->maxKp) { set_error("cap %d < orbb200_extractor_max_keypoints() = %d", cap, h->maxKp); return ORBB200_ECAPACITY; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    return enqueue(h, d_images, batch, stride, frame_stride, d_keypoints, d_descriptors, d_counts, cap);
+}
+
+extern "C" int orbb200_extractor_sync(orbb200_extractor* h)
+{
+    if (!h) { set_error("null handle"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    return check_status(h);
+}
+
+extern "C" int orbb200_extractor_outputs(orbb200_extractor* h, orbb200_keypoint** d_keypoints, uint8_t** d_descriptors,
+                                         int32_t** d_counts, int* cap)
+{
+    if (!h) { set_error("null handle"); return ORBB200_EINVAL; }
+    if (d_keypoints) *d_keypoints = h->dOutKp;
+    if (d_descriptors) *d_descriptors = h->dOutDesc;
+    if (d_counts) *d_counts = h->dOutCount;
+    if (cap) *cap = h->maxKp;
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images, int batch, size_t stride,
+                                    size_t frame_stride, orbb200_keypoint* keypoints, uint8_t* descriptors,
+                                    int32_t* counts, int cap)
+{
+    if (!h || !images || !keypoints || !descriptors || !counts) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (batch < 1 || batch > h->maxBatch) { set_error("batch %d outside 1..%d", batch, h->maxBatch); return ORBB200_EINVAL; }
+    if (stride < (size_t)h->width) { set_error("stride smaller than the frame width"); return ORBB200_EINVAL; }
+    if (cap < h->maxKp) { set_error("cap %d < orbb200_extractor_max_keypoints() = %d", cap, h->maxKp); return ORBB200_ECAPACITY; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (frame_stride == stride * (size_t)h->height) {
+        ORB_CUDA(cudaMemcpy2DAsync(h->dIn, h->inPitch, images, stride, h->width, (size_t)h->height * batch,
+                                   cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < batch; f++)
+            ORB_CUDA(cudaMemcpy2DAsync(h->dIn + (size_t)f * h->inPitch * h->height, h->inPitch, images + f * frame_stride,
+                                       stride, h->width, h->height, cudaMemcpyHostToDevice, st));
+    }
+    int rc = enqueue(h, h->dIn, batch, h->inPitch, h->inPitch * (size_t)h->height, h->dOutKp, h->dOutDesc, h->dOutCount, h->maxKp);
+    if (rc != ORBB200_OK) return rc;
+    // results: one contiguous D2H per array when the caller's cap equals ours, else per-frame rows
+    const int mk = h->maxKp;
+    ORB_CUDA(cudaMemcpyAsync(counts, h->dOutCount, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpy2DAsync(keypoints, (size_t)cap * sizeof(orbb200_keypoint), h->dOutKp, (size_t)mk * sizeof(orbb200_keypoint),
+                               (size_t)mk * sizeof(orbb200_keypoint), batch, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpy2DAsync(descriptors, (size_t)cap * 32, h->dOutDesc, (size_t)mk * 32, (size_t)mk * 32, batch,
+                               cudaMemcpyDeviceToHost, st));
+    return check_status(h);
+}
+
+// ---- stage read-back -------------------------------------------------------------------
+extern "C" int orbb200_extractor_get_level(orbb200_extractor* h, int frame, int level, int blurred, uint8_t* dst, size_t dst_stride)
+{
+    if (!h || !dst || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastBatch) { set_error("bad argument"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    const LevelGeo& g = h->P.lv[level];
+    const uint8_t* src; size_t sp;
+    if (blurred) { src = h->P.blur + (size_t)frame * h->P.blurFrameBytes + g.blurOff; sp = g.pitch; }
+    else if (level == 0) { src = h->lastIn + (size_t)frame * h->lastInFrameStride; sp = h->lastInPitch; }
+    else { src = h->P.pyr + (size_t)frame * h->P.pyrFrameBytes + g.pyrOff; sp = g.pitch; }
+    ORB_CUDA(cudaStreamSynchronize(h->stream));
+    ORB_CUDA(cudaMemcpy2D(dst, dst_stride, src, sp, g.w, g.h, cudaMemcpyDeviceToHost));
+    return ORBB200_OK;
+}
+
+static int fetch_packed(orbb200_extractor* h, const uint32_t* dsrc, const int* dcount, int maxn, std::vector<uint32_t>& v)
+{
+    int n = 0;
+    ORB_CUDA(cudaStreamSynchronize(h->stream));
+    ORB_CUDA(cudaMemcpy(&n, dcount, sizeof(int), cudaMemcpyDeviceToHost));
+    n = std::min(n, maxn);
+    v.resize(n);
+    if (n) ORB_CUDA(cudaMemcpy(v.data(), dsrc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_extractor_get_candidates(orbb200_extractor* h, int frame, int level, int32_t* x, int32_t* y,
+                                                int32_t* score, int cap, int* n)
+{
+    if (!h || !n || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastBatch) { set_error("bad argument"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    const LevelGeo& g = h->P.lv[level];
+    std::vector<uint32_t> v;
+    int rc = fetch_packed(h, h->P.cand + (size_t)frame * h->P.candFrameCap + g.candOff, h->P.candCount + frame * h->nlevels + level, g.candCap, v);
+    if (rc) return rc;
+    // the device list is unordered; restore the reference's order: cells row-major, then row-major in the cell
+    auto key = [&](uint32_t e) {
+        const uint64_t px = e & 0xfff, py = (e >> 12) & 0xfff;
+        return ((uint64_t)((py - 3) / g.hCell) << 40) | ((uint64_t)((px - 3) / g.wCell) << 28) | (py << 12) | px;
+    };
+    std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    *n = (int)v.size();
+    if ((int)v.size() > cap) { set_error("candidate buffer too small (%zu)", v.size()); return ORBB200_ECAPACITY; }
+    for (size_t i = 0; i < v.size(); i++) {
+        if (x) x[i] = v[i] & 0xfff;
+        if (y) y[i] = (v[i] >> 12) & 0xfff;
+        if (score) score[i] = v[i] >> 24;
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_extractor_get_level_keypoints(orbb200_extractor* h, int frame, int level, int32_t* x, int32_t* y,
+                                                     int32_t* score, int cap, int* n)
+{
+    if (!h || !n || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->lastBatch) { set_error("bad argument"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    const LevelGeo& g = h->P.lv[level];
+    std::vector<uint32_t> v;
+    int rc = fetch_packed(h, h->P.lkp + (size_t)frame * h->P.kpFrameCap + g.kpOff, h->P.lkpCount + frame * h->nlevels + level, g.kpCap, v);
+    if (rc) return rc;
+    *n = (int)v.size();
+    if ((int)v.size() > cap) { set_error("keypoint buffer too small (%zu)", v.size()); return ORBB200_ECAPACITY; }
+    for (size_t i = 0; i < v.size(); i++) {
+        if (x) x[i] = (v[i] & 0xfff) + BORDER;
+        if (y) y[i] = ((v[i] >> 12) & 0xfff) + BORDER;
+        if (score) score[i] = v[i] >> 24;
+    }
+    return ORBB200_OK;
+}
