@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- ORB frames/s on B200 (BASELINE.json: 640x480, 1000 kp, 8 levels; configs[1]:
+batched extraction of 256 synthetic frames on a single B200).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N ...            the reference's own CPU implementation (oracle/_ref)
+
+A step = one pass of ORBextractor::operator() over one batch of 256 frames per GPU.  `value` is
+frames/s with the frames already resident in HBM (device time, CUDA events, max over ranks);
+`e2e` is the same metric through the host-buffer C-ABI call (H2D + kernels + D2H inside the timed
+region).  Frames are independent, so N GPUs = N shards, no collective on the data path (weak scaling);
+the only cross-rank traffic is the max-reduction of the elapsed time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
+BATCH = 256                       # frames per GPU per step (configs[1])
+DISTINCT = 32                     # distinct synthetic frames generated per rank (tiled to BATCH)
+
+# Algorithmic HBM bytes per frame and per kernel (DESIGN.md "Roofline model"):
+# every stage reads its input once and writes its output once.
+ALG_BYTES = {
+    "pyramid": 926546 + 643332,
+    "fast": 950532 + 80000,
+    "quadtree": 80000 + 16000,
+    "blur": 950532 + 950532,
+    "describe": 749000 + 512000 + 60000,
+}
+STAGES = ["pyramid", "fast", "quadtree", "blur", "describe"]
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def _frames(rank, count):
+    import numpy as np
+    from weiner_slamit_v2_b200.frames import synthetic_frame
+    base = [synthetic_frame(rank * 100000 + i, WIDTH, HEIGHT) for i in range(min(DISTINCT, count))]
+    reps = (count + len(base) - 1) // len(base)
+    return np.stack((base * reps)[:count])
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own ORBextractor.cc (oracle/_ref) on the host cores
+# --------------------------------------------------------------------------------------------
+def _cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _load_ref():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_lib
+    if ref_lib.available():
+        return ref_lib, "reference"
+    return None, "port"
+
+
+def cpu_extract_fps(frames, threads):
+    """frames/s of the CPU implementation over `frames` with `threads` host threads."""
+    import numpy as np
+    ref_lib, kind = _load_ref()
+    t0 = time.perf_counter()
+    if ref_lib is not None:
+        counts = ref_lib.extract_batch_mt(frames, threads, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    else:  # oracle port, single instance per thread via a thread pool (ctypes releases the GIL)
+        import oracle_lib
+        from concurrent.futures import ThreadPoolExecutor
+        def work(chunk):
+            o = oracle_lib.OracleExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+            return [len(o(f)[0]) for f in chunk]
+        chunks = [frames[i::threads] for i in range(threads)]
+        with ThreadPoolExecutor(threads) as ex:
+            counts = np.concatenate([np.asarray(c) for c in ex.map(work, chunks)])
+    dt = time.perf_counter() - t0
+    return len(frames) / dt, kind, int(np.sum(counts))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = _cpu_threads()
+    sample = BATCH                                   # one full step: 256 frames (~20 s of CPU work)
+    frames = _frames(0, sample)
+    for _ in range(args.warmup):
+        cpu_extract_fps(frames[: max(threads, 8)], threads)
+    total_t, kind = 0.0, "port"
+    for _ in range(args.steps):
+        fps, kind, _ = cpu_extract_fps(frames, threads)
+        total_t += sample / fps
+    value = sample * args.steps / total_t
+    line = {
+        "impl": "reference", "metric": "ORB frames/s (640x480, 1000 kp, 8 lvl)", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_t / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "batched ORB extraction, 256 synthetic 640x480 frames, 1000 kp/8 levels (configs[1])",
+                   "frames_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": "%d of the 256 frames of one step, %d host threads, one ORBextractor each" % (sample, threads)},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from weiner_slamit_v2_b200 import ORBextractor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the extractor has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=WIDTH, height=HEIGHT, max_batch=BATCH, device=local)
+    ex.set_profiling(True)
+    frames = _frames(rank, BATCH)
+    pinned = torch.empty((BATCH, HEIGHT, WIDTH), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = frames
+    d_frames = pinned.cuda()
+    stream = torch.cuda.ExternalStream(ex.stream, device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ex.extract_device(d_frames, BATCH, WIDTH, WIDTH * HEIGHT)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ex.sync()
+
+    # ---- device-resident throughput: K steps, L2 flushed before each, CUDA events on the launch stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms = np.zeros(5)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            flush.fill_(k & 0xff)
+            ev[k][0].record()
+            step()
+            ev[k][1].record()
+            stage_ms += ex.stage_ms()          # waits for this step's last stage event
+    ex.sync()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ex.last_launches * args.steps
+
+    # ---- end to end through the host-buffer C-ABI call: H2D + kernels + D2H inside the timed region
+    host_in = pinned.numpy()
+    cap = ex.max_keypoints
+    out_k = torch.empty((BATCH, cap, 28), dtype=torch.uint8, pin_memory=True)
+    out_d = torch.empty((BATCH, cap, 32), dtype=torch.uint8, pin_memory=True)
+    out_c = torch.empty((BATCH,), dtype=torch.int32, pin_memory=True)
+    from weiner_slamit_v2_b200._lib import check
+
+    def e2e_step():
+        check(ex._L.orbb200_extract_host(ex._h, host_in.ctypes.data, BATCH, WIDTH, WIDTH * HEIGHT,
+                                         out_k.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), cap))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()                              # synchronous: returns after the D2H copies
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    nkp = int(out_c.sum())
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(nkp)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks (device-timed)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)    # the path's only "collective": a count gather
+    dev_ms_max, e2e_ms_max = t.tolist()
+
+    if rank == 0:
+        frames_total = BATCH * world * args.steps
+        value = frames_total / (dev_ms_max * 1e-3)
+        e2e = frames_total / (e2e_ms_max * 1e-3)
+        peak, which = _peaks()
+        per_stage = stage_ms / args.steps
+        dom = int(np.argmax(per_stage))
+        ach = ALG_BYTES[STAGES[dom]] * BATCH / (per_stage[dom] * 1e-3) / 1e9
+        line = {
+            "metric": "ORB frames/s (640x480, 1000 kp, 8 lvl)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "batched ORB extraction, 256 synthetic 640x480 frames per GPU, 1000 kp/8 levels, "
+                                   "FAST 20/7 (configs[1])",
+                       "frames_per_step_per_gpu": BATCH, "l2": "256 MiB flush buffer written before every timed step",
+                       "parallelism": "frames sharded by batch, no data-path collective"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * WIDTH * HEIGHT,
+                    "d2h_bytes_per_step": BATCH * (4 + cap * 60), "keypoints_per_step": nkp / world},
+            "gpu_launches": launches,
+            "kernel_ms_per_step": {s: float(per_stage[i]) for i, s in enumerate(STAGES)},
+            "roofline": {"bound": "hbm", "kernel": STAGES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": _traffic(STAGES[dom]), "peak_source": which,
+                         "all": {s: ALG_BYTES[s] * BATCH / (per_stage[i] * 1e-3) / 1e9 / peak for i, s in enumerate(STAGES)}},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = _cpu_threads()
+            sample = BATCH
+            fps, kind, _ = cpu_extract_fps(frames[:sample], threads)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                                    "sample": "%d of the 256 frames of one step, %d host threads" % (sample, threads)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _traffic(stage):
+    """dram bytes per launch from the committed ncu --set full capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(stage)
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,12 @@ void *orbb200_extractor_stream(orbb200_extractor *h);
 /* Number of kernel launches the last extract call issued. */
 int orbb200_extractor_last_launches(const orbb200_extractor *h);
 
+/* Per-stage device time of the most recent call, from CUDA events recorded on the handle's stream
+ * between the kernels: ms5 = {pyramid (all resize launches), FAST, quadtree, blur, orientation+descriptor}.
+ * Off by default; the bench harness turns it on to compute per-kernel roofline fractions. */
+int orbb200_extractor_set_profiling(orbb200_extractor *h, int on);
+int orbb200_extractor_stage_ms(orbb200_extractor *h, float *ms5);
+
 /* Stage read-back of the most recent extract call (parity tests; also backs the public
  * member mvImagePyramid of I/ORBextractor.h:85).  All copy into HOST buffers. */
 int orbb200_extractor_get_level(orbb200_extractor *h, int frame, int level, int blurred, uint8_t *dst, size_t dst_stride);

@@ -1,0 +1,106 @@
+"""Pins the C oracle against the reference's OWN code: oracle/_ref = ORB_SLAM2/src/ORBextractor.cc
+compiled unmodified for x86 (built here by `make -C oracle ref`; prebuilt file on the GPU box), and
+against the golden vectors that build produced (tests/golden/, tools/gen_golden.py)."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import ref_lib as R
+from weiner_slamit_v2_b200 import frames as F
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_extract_*.npz")))
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_reproduces_reference_golden_vectors(path):
+    g = np.load(path)
+    p = g["params"]
+    params = (int(p[0]), float(p[1]), int(p[2]), int(p[3]), int(p[4]))
+    meta = [str(m) for m in g["meta"]]
+    gen = getattr(F, meta[0])
+    w, h = int(meta[1]), int(meta[2])
+    orc = O.OracleExtractor(*params)
+    for i, idx in enumerate(meta[3:]):
+        img = gen(int(idx), w, h)
+        assert np.array_equal(_sha(img), g["frame_sha_%d" % i]), "frame generator changed"
+        k, d = orc(img)
+        assert k.tobytes() == g["kps_%d" % i].tobytes()
+        assert np.array_equal(d, g["desc_%d" % i])
+        for l in range(params[2]):
+            assert np.array_equal(_sha(orc.level_pixels(l)), g["pyr_sha_%d" % i][l])
+
+
+def test_golden_vectors_exist():
+    assert len(GOLDEN) >= 4
+
+
+@needs_ref
+def test_constructor_tables_match_reference():
+    for params in ((1000, 1.2, 8, 20, 7), (2000, 1.2, 8, 20, 7), (500, 1.5, 5, 25, 9), (1500, 1.1, 12, 20, 7)):
+        t = R.RefExtractor(*params).tables()
+        o = O.OracleExtractor(*params)
+        assert np.array_equal(t["scale"], o.scale_factors) and np.array_equal(t["inv_scale"], o.inv_scale_factors)
+        assert np.array_equal(t["sigma2"], o.level_sigma2) and np.array_equal(t["inv_sigma2"], o.inv_level_sigma2)
+        assert np.array_equal(t["per_level"], o.features_per_level) and np.array_equal(t["umax"], o.umax)
+        assert np.array_equal(t["pattern"], np.ctypeslib.as_array(O.lib().orc_pattern(), (1024,)))
+
+
+@needs_ref
+def test_full_extractor_matches_reference_fresh_frames():
+    o, r = O.OracleExtractor(), R.RefExtractor()
+    for i in (11, 12, 13):
+        img = F.synthetic_frame(i)
+        ko, do = o(img)
+        kr, dr = r(img)
+        assert ko.tobytes() == kr.tobytes() and np.array_equal(do, dr)
+        for l in range(8):
+            assert np.array_equal(o.level_pixels(l), r.level_pixels(l))
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (480, 640)).astype(np.uint8)      # far more candidates than the quota
+    ko, do = o(img); kr, dr = r(img)
+    assert ko.tobytes() == kr.tobytes() and np.array_equal(do, dr)
+    assert len(o(np.full((480, 640), 9, np.uint8))[0]) == len(r(np.full((480, 640), 9, np.uint8))[0]) == 0
+
+
+@needs_ref
+def test_pyramid_border_matches_reference():
+    r = R.RefExtractor(); o = O.OracleExtractor()
+    img = F.synthetic_frame(5)
+    r(img); o(img)
+    for l in range(8):
+        assert np.array_equal(r.level_pixels(l, with_border=True), O.copy_make_border(o.level_pixels(l), 19))
+
+
+@needs_ref
+def test_distribute_octree_matches_reference_under_monotonic_allocator():
+    """The quadtree's (count, node address) tie-break (S/ORBextractor.cc:694-698) is fixed by the bump
+    allocator in oracle/ref_harness.cc; the oracle uses creation order, which must agree."""
+    r = R.RefExtractor()
+    rng = np.random.default_rng(21)
+    for trial in range(40):
+        w, h = int(rng.integers(120, 1300)), int(rng.integers(100, 700))
+        if round(w / h) < 1:
+            continue
+        n = int(rng.integers(0, 3000))
+        N = int(rng.integers(1, 500))
+        pts = set()
+        while len(pts) < n:
+            pts.add((int(rng.integers(3, w - 3)), int(rng.integers(3, h - 3))))
+        c = np.zeros(len(pts), O.KP_DTYPE)
+        arr = np.array(sorted(pts, key=lambda p: (p[1], p[0])), np.float32).reshape(-1, 2)
+        if len(arr):
+            c["x"], c["y"] = arr[:, 0], arr[:, 1]
+        c["response"] = rng.integers(7, 60, len(c)).astype(np.float32)   # many response ties
+        c["size"] = 7; c["angle"] = -1; c["class_id"] = -1
+        a = O.distribute_octree(c, 16, 16 + w, 16, 16 + h, N)
+        b = r.distribute_octree(c, 16, 16 + w, 16, 16 + h, N)
+        assert a.tobytes() == b.tobytes(), (trial, w, h, n, N, len(a), len(b))

@@ -51,6 +51,8 @@ SIGNATURES = {
     "orbb200_extractor_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int)]),
     "orbb200_extractor_stream": (vp, [vp]),
     "orbb200_extractor_last_launches": (C.c_int, [vp]),
+    "orbb200_extractor_set_profiling": (C.c_int, [vp, C.c_int]),
+    "orbb200_extractor_stage_ms": (C.c_int, [vp, vp]),
     "orbb200_extractor_get_level": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]),
     "orbb200_extractor_get_candidates": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]),
     "orbb200_extractor_get_level_keypoints": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]),

@@ -775,6 +775,7 @@ struct orbb200_extractor {
     const uint8_t* lastIn; long long lastInFrameStride; int lastInPitch;
     orbb200_keypoint* dOutKp; uint8_t* dOutDesc; int* dOutCount;
     void* pinned; size_t pinnedBytes;
+    bool profiling; cudaEvent_t ev[6];   // stage boundaries of the last call: resize | fast | quadtree | blur | describe
     std::vector<void*> allocs;
 };
 
@@ -847,6 +848,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     h->nfeatures = nfeatures; h->nlevels = nlevels; h->iniTh = iniThFAST; h->minTh = minThFAST;
     h->width = width; h->height = height; h->maxBatch = max_batch; h->device = device; h->blurTaps = blur_taps ? 1 : 0;
     h->pinned = nullptr; h->pinnedBytes = 0; h->lastLaunches = 0; h->lastBatch = 0; h->lastIn = nullptr;
+    h->profiling = false;
+    for (int i = 0; i < 6; i++) h->ev[i] = nullptr;
     // ---- constructor tables (S/ORBextractor.cc:421-455); scaleFactor is held in a double (I/ORBextractor.h:98)
     h->scaleFactorD = (double)scaleFactor;
     h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
@@ -975,6 +978,7 @@ extern "C" void orbb200_extractor_destroy(orbb200_extractor* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (void* p : h->allocs) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h;
@@ -1007,6 +1011,24 @@ extern "C" int orbb200_extractor_level_size(const orbb200_extractor* h, int leve
 extern "C" void* orbb200_extractor_stream(orbb200_extractor* h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int orbb200_extractor_last_launches(const orbb200_extractor* h) { return h ? h->lastLaunches : 0; }
 
+extern "C" int orbb200_extractor_set_profiling(orbb200_extractor* h, int on)
+{
+    if (!h) { set_error("null handle"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    if (on) for (int i = 0; i < 6; i++) if (!h->ev[i]) ORB_CUDA(cudaEventCreate(&h->ev[i]));
+    h->profiling = on != 0;
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_extractor_stage_ms(orbb200_extractor* h, float* ms5)
+{
+    if (!h || !ms5 || !h->profiling) { set_error("profiling is off"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(h->device));
+    ORB_CUDA(cudaEventSynchronize(h->ev[5]));
+    for (int i = 0; i < 5; i++) ORB_CUDA(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]));
+    return ORBB200_OK;
+}
+
 // enqueue the whole pipeline for `batch` frames whose level 0 is at d_images
 static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, size_t stride, size_t frame_stride,
                    orbb200_keypoint* d_kp, uint8_t* d_desc, int32_t* d_counts, int cap)
@@ -1017,20 +1039,28 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
     cudaStream_t st = h->stream;
     int launches = 0;
     ORB_CUDA(cudaMemsetAsync(P.candCount, 0, sizeof(int) * P.nlevels * batch, st));
+#define STAGE_MARK(i) do { if (h->profiling) ORB_CUDA(cudaEventRecord(h->ev[i], st)); } while (0)
+    STAGE_MARK(0);
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeo& g = P.lv[l];
         dim3 grid((g.w + 127) / 128, (g.h + 7) / 8, batch), block(32, 8);
         k_resize<<<grid, block, 0, st>>>(P, l);
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
+    STAGE_MARK(1);
     k_fast<128><<<dim3(h->totalCells, batch), 128, h->fastSmem, st>>>(P);
     ORB_CHECK_LAUNCH("k_fast"); launches++;
+    STAGE_MARK(2);
     k_quadtree<<<dim3(P.nlevels, batch), QT_THREADS, h->qtSmem, st>>>(P);
     ORB_CHECK_LAUNCH("k_quadtree"); launches++;
+    STAGE_MARK(3);
     k_blur<<<dim3(h->totalBlurTiles, batch), BL_THREADS, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_blur"); launches++;
+    STAGE_MARK(4);
     k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_describe"); launches++;
+    STAGE_MARK(5);
+#undef STAGE_MARK
     h->lastLaunches = launches; h->lastBatch = batch;
     h->lastIn = d_images; h->lastInPitch = (int)stride; h->lastInFrameStride = (long long)frame_stride;
     return ORBB200_OK;

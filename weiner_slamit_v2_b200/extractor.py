@@ -103,6 +103,15 @@ class ORBextractor:
     @property
     def last_launches(self): return self._L.orbb200_extractor_last_launches(self._h)
 
+    def set_profiling(self, on=True):
+        check(self._L.orbb200_extractor_set_profiling(self._h, int(on)))
+
+    def stage_ms(self):
+        """Device ms of the last call per stage: pyramid, fast, quadtree, blur, describe."""
+        ms = np.zeros(5, np.float32)
+        check(self._L.orbb200_extractor_stage_ms(self._h, ms.ctypes.data))
+        return ms
+
     # ---- stage read-back (parity tests; mvImagePyramid) ----
     def level_size(self, level):
         w, h = C.c_int(), C.c_int()
