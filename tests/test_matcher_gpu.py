@@ -1,0 +1,106 @@
+"""GPU parity: ORBmatcher's three in-scope entry points through the C ABI against the CPU oracle
+(oracle/orb_matcher_oracle.c), bit-exact on match indices, counts, distances and vbPrevMatched."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from weiner_slamit_v2_b200.matcher import Frame, MapPoints, ORBmatcher
+from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def test_descriptor_distance_matches_oracle():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (5000, 32)).astype(np.uint8)
+    b = rng.integers(0, 256, (5000, 32)).astype(np.uint8)
+    b[:10] = a[:10]; b[10:20] = ~a[10:20]
+    m = ORBmatcher()
+    d = m.DescriptorDistance(a, b)
+    ref = np.array([O.descriptor_distance(a[i], b[i]) for i in range(len(a))])
+    assert np.array_equal(d, ref) and d[:10].max() == 0 and d[10:20].min() == 256
+    assert m.DescriptorDistance(a[0], b[0]) == ref[0]
+    assert np.array_equal(d, np.unpackbits(a ^ b, axis=1).sum(1))       # property: popcount of the XOR
+
+
+@pytest.mark.parametrize("brute,window,n", [(False, 100, 1000), (True, 1000, 1000), (False, 10, 700), (True, 40, 333)])
+def test_search_for_initialization_matches_oracle(brute, window, n):
+    items = 6
+    pairs = [init_pair(i, n=n, brute_force=brute) for i in range(items)]
+    m = ORBmatcher(0.9, True, max_items=items, max_points=n)
+    F1 = [Frame(p[0], p[1], 640, 480) for p in pairs]
+    F2 = [Frame(p[2], p[3], 640, 480) for p in pairs]
+    nm, m12, pm = m.search_for_initialization_batch(F1, F2, [p[4] for p in pairs], window)
+    total = 0
+    for i, p in enumerate(pairs):
+        on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], 640, 480, 0.9, True, window)
+        assert nm[i] == on, (i, nm[i], on)
+        assert np.array_equal(m12[i], om12)
+        assert np.array_equal(pm[i], opm)
+        total += on
+    assert total > 0
+
+
+def test_search_for_initialization_no_orientation_and_second_round():
+    p = init_pair(11, n=800)
+    m = ORBmatcher(0.9, False)
+    F1, F2 = Frame(p[0], p[1], 640, 480), Frame(p[2], p[3], 640, 480)
+    prev = p[4].copy()
+    n1, m12 = m.SearchForInitialization(F1, F2, prev, None, 100)
+    on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], 640, 480, 0.9, False, 100)
+    assert n1 == on and np.array_equal(m12, om12) and np.array_equal(prev, opm)
+    # second call with the updated vbPrevMatched (what MonocularInitialization does frame after frame)
+    n2, m12b = m.SearchForInitialization(F1, F2, prev, None, 100)
+    on2, om12b, opm2 = O.search_for_initialization(p[0], p[1], p[2], p[3], opm, 640, 480, 0.9, False, 100)
+    assert n2 == on2 and np.array_equal(m12b, om12b) and np.array_equal(prev, opm2)
+
+
+def test_search_for_initialization_empty_and_ragged():
+    m = ORBmatcher(0.9, True, max_items=3, max_points=64)
+    p = init_pair(3, n=50)
+    empty = np.zeros(0, p[0].dtype)
+    F1 = [Frame(p[0], p[1], 640, 480), Frame(empty, np.zeros((0, 32), np.uint8), 640, 480), Frame(p[0][:7], p[1][:7], 640, 480)]
+    F2 = [Frame(empty, np.zeros((0, 32), np.uint8), 640, 480), Frame(p[2], p[3], 640, 480), Frame(p[2], p[3], 640, 480)]
+    prevs = [p[4], np.zeros((0, 2), np.float32), p[4][:7]]
+    nm, m12, pm = m.search_for_initialization_batch(F1, F2, prevs, 100)
+    assert nm[0] == 0 and nm[1] == 0 and (m12[0] == -1).all()
+    on, om12, opm = O.search_for_initialization(p[0][:7], p[1][:7], p[2], p[3], p[4][:7], 640, 480, 0.9, True, 100)
+    assert nm[2] == on and np.array_equal(m12[2], om12) and np.array_equal(pm[2], opm)
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0])
+def test_search_by_projection_matches_oracle(th):
+    items = 4
+    data = [projection_frame(i, n_kp=2000, n_mp=3000) for i in range(items)]
+    m = ORBmatcher(0.8, True, max_items=items, max_points=3000)
+    frames = [Frame(kp, kd, 1280, 720, SCALE_FACTORS_8) for kp, kd, _ in data]
+    # some keypoints already hold a foreign map point (with and without observations)
+    rng = np.random.default_rng(5)
+    for f in frames:
+        idx = rng.choice(f.N, 100, replace=False)
+        f.mvpMapPoints[idx] = -2
+        f.mvpMapPointObs[idx] = rng.integers(0, 3, 100)
+    pre = [(f.mvpMapPoints.copy(), f.mvpMapPointObs.copy()) for f in frames]
+    mps = [MapPoints(mp["x"], mp["y"], mp["level"], mp["viewcos"], mp["desc"], mp["in_view"], mp["bad"], mp["xr"], mp["obs"])
+           for _, _, mp in data]
+    nm = m.search_by_projection_batch(frames, mps, th)
+    tot = 0
+    for i, (kp, kd, mp) in enumerate(data):
+        cnt, kpmp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, 1280, 720, 0.8, th, pre[i][0], pre[i][1])
+        assert nm[i] == cnt, (i, nm[i], cnt)
+        assert np.array_equal(frames[i].mvpMapPoints, kpmp)
+        tot += cnt
+    assert tot > 100
+
+
+def test_search_by_projection_stereo_and_zero_observation_points():
+    kp, kd, mp = projection_frame(42, n_kp=500, n_mp=1500, width=640, height=480)
+    rng = np.random.default_rng(1)
+    ur = np.where(rng.random(500) < 0.5, kp["x"] - rng.uniform(0, 30, 500), -1).astype(np.float32)
+    mp["xr"] = (mp["x"] - rng.uniform(0, 30, 1500)).astype(np.float32)
+    mp["kuright"] = ur
+    f = Frame(kp, kd, 640, 480, SCALE_FACTORS_8, u_right=ur)
+    m = ORBmatcher(0.8)
+    n = m.SearchByProjection(f, MapPoints(mp["x"], mp["y"], mp["level"], mp["viewcos"], mp["desc"], mp["in_view"], mp["bad"], mp["xr"], mp["obs"]), 3.0)
+    cnt, kpmp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, 640, 480, 0.8, 3.0)
+    assert n == cnt and np.array_equal(f.mvpMapPoints, kpmp)

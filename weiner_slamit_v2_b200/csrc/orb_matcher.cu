@@ -1,14 +1,642 @@
-// orb_matcher.cu -- ORBmatcher Hamming search on B200 (placeholder until the kernels land: every
-// entry point fails loudly, there is no fallback).
+// orb_matcher.cu -- ORBmatcher's Hamming search for batches of frame pairs / frames on B200.
+//
+// Reference path (S/ = oRB_SLAM2_Android/src/main/jni/ORB_SLAM2/src/):
+//   DescriptorDistance S/ORBmatcher.cc:1651-1667, SearchForInitialization :409-524,
+//   SearchByProjection(Frame&, vector<MapPoint*>&, th) :47-131, ComputeThreeMaxima :1605-1646,
+//   Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid S/Frame.cc:336-357, 447-517.
+//
+// Both searches are greedy and order dependent inside one frame (pair): an accepted match changes
+// what later queries may take (vMatchedDistance :448, mvpMapPoints :89-91,:125).  Items (pairs /
+// frames) are independent, so the device mapping is: items in parallel, one warp per item walking
+// its queries in the reference's order, the 32 lanes sharing each query's candidate scan
+// (XOR + __popc on 256-bit descriptors) and a warp-shuffle best / second-best reduction whose
+// tie-break reproduces "first candidate in GetFeaturesInArea order wins" (candidates are visited
+// in CSR order = ix, iy, insertion order; ties go to the lower CSR position).
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstring>
+#include <vector>
 #include "common.cuh"
+
+namespace orbb200 {
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;   // I/Frame.h:40-41
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;                          // S/ORBmatcher.cc:37-39
+
+struct FrameDev {           // device-side orbb200_frame_view
+    const int* n;
+    const float *x, *y;
+    const int* octave;
+    const float* angle;
+    const uint8_t* desc;
+    int stride;
+};
+
+struct GridGeo { float minX, minY, invW, invH; };
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1)
+{
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---- DescriptorDistance for n independent pairs ------------------------------------------
+__global__ void k_distance(const uint4* a, const uint4* b, int n, int* dist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dist[i] = hamming256(__ldg(a + 2 * i), __ldg(a + 2 * i + 1), __ldg(b + 2 * i), __ldg(b + 2 * i + 1));
+}
+
+// ---- Frame::AssignFeaturesToGrid as CSR (one CTA per frame) --------------------------------
+// cell = ix*48+iy with ix,iy = roundf((pt - min) * inv) (PosInGrid, S/Frame.cc:505-517); points whose
+// cell falls outside the 64x48 grid are not indexed.  Inside a cell, indices ascend (push_back order).
+__global__ void __launch_bounds__(256) k_build_grid(FrameDev f, GridGeo g, int* cellStart, int* cellItems)
+{
+    __shared__ int cnt[GRID_CELLS + 1];
+    __shared__ int wsum[9];
+    const int item = blockIdx.x, tid = threadIdx.x;
+    const int n = min(f.n[item], f.stride);
+    const float* kx = f.x + (size_t)item * f.stride;
+    const float* ky = f.y + (size_t)item * f.stride;
+    int* cs = cellStart + (size_t)item * (GRID_CELLS + 1);
+    int* ci = cellItems + (size_t)item * f.stride;
+    for (int c = tid; c <= GRID_CELLS; c += 256) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kx[i], g.minX), g.invW));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(ky[i], g.minY), g.invH));
+        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) atomicAdd(&cnt[px * GRID_ROWS + py], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counts: 12 per thread
+    int local[12], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) { local[j] = cnt[tid * 12 + j]; sum += local[j]; }
+    int x = sum;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (tid == 0) { int a = 0; for (int w = 0; w < 8; w++) { const int t = wsum[w]; wsum[w] = a; a += t; } wsum[8] = a; }
+    __syncthreads();
+    int run = x - sum + wsum[warp];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { cnt[tid * 12 + j] = run; cs[tid * 12 + j] = run; run += local[j]; }
+    if (tid == 255) { cs[GRID_CELLS] = run; }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kx[i], g.minX), g.invW));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(ky[i], g.minY), g.invH));
+        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) ci[atomicAdd(&cnt[px * GRID_ROWS + py], 1)] = i;
+    }
+    __syncthreads();
+    // restore insertion (ascending index) order inside every cell
+    for (int c = tid; c < GRID_CELLS; c += 256) {
+        const int s = cs[c], e = cnt[c];
+        for (int a = s + 1; a < e; a++) {
+            const int v = ci[a];
+            int b = a - 1;
+            while (b >= s && ci[b] > v) { ci[b + 1] = ci[b]; b--; }
+            ci[b + 1] = v;
+        }
+    }
+}
+
+// Cell range of GetFeaturesInArea (S/Frame.cc:452-466); false when the query misses the grid.
+__device__ __forceinline__ bool cell_range(const GridGeo& g, float x, float y, float r, int& c0, int& c1, int& r0, int& r1)
+{
+    c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.minX), r), g.invW)));
+    if (c0 >= GRID_COLS) return false;
+    c1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.minX), r), g.invW)));
+    if (c1 < 0) return false;
+    r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.minY), r), g.invH)));
+    if (r0 >= GRID_ROWS) return false;
+    r1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.minY), r), g.invH)));
+    if (r1 < 0) return false;
+    return true;
+}
+
+// Best / second-best exactly as the reference's scan computes them.  The sequential update
+//   if (d < best) { second = best; best = d; } else if (d < second) second = d;
+// leaves best = smallest and second = second smallest element under the lexicographic key
+// (distance, visiting position) -- including which element supplies the "level" payload -- so the
+// pair can be reduced associatively across lanes.
+struct Top2 { int b, bp, ba, s, sp, sa; };     // best: dist, pos, payload; second: dist, pos, payload
+__device__ __forceinline__ void top2_push(Top2& t, int d, int pos, int payload)
+{
+    if (d < t.b) { t.s = t.b; t.sp = t.bp; t.sa = t.ba; t.b = d; t.bp = pos; t.ba = payload; }
+    else if (d < t.s) { t.s = d; t.sp = pos; t.sa = payload; }
+}
+__device__ __forceinline__ bool key_lt(int d0, int p0, int d1, int p1) { return d0 < d1 || (d0 == d1 && p0 < p1); }
+__device__ __forceinline__ Top2 top2_merge(const Top2& a, const Top2& o)
+{
+    Top2 r;
+    if (key_lt(a.b, a.bp, o.b, o.bp)) {
+        r.b = a.b; r.bp = a.bp; r.ba = a.ba;
+        if (key_lt(a.s, a.sp, o.b, o.bp)) { r.s = a.s; r.sp = a.sp; r.sa = a.sa; } else { r.s = o.b; r.sp = o.bp; r.sa = o.ba; }
+    } else {
+        r.b = o.b; r.bp = o.bp; r.ba = o.ba;
+        if (key_lt(o.s, o.sp, a.b, a.bp)) { r.s = o.s; r.sp = o.sp; r.sa = o.sa; } else { r.s = a.b; r.sp = a.bp; r.sa = a.ba; }
+    }
+    return r;
+}
+__device__ __forceinline__ Top2 top2_warp_reduce(Top2 t)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        Top2 o;
+        o.b = __shfl_xor_sync(0xffffffffu, t.b, d); o.bp = __shfl_xor_sync(0xffffffffu, t.bp, d);
+        o.ba = __shfl_xor_sync(0xffffffffu, t.ba, d); o.s = __shfl_xor_sync(0xffffffffu, t.s, d);
+        o.sp = __shfl_xor_sync(0xffffffffu, t.sp, d); o.sa = __shfl_xor_sync(0xffffffffu, t.sa, d);
+        t = top2_merge(t, o);
+    }
+    return t;
+}
+
+// ---- SearchForInitialization: one warp per frame pair (S/ORBmatcher.cc:409-524) -------------
+struct InitParams {
+    FrameDev f1, f2;
+    GridGeo g;
+    const int* cellStart;     // items x (GRID_CELLS+1), F2 grid
+    const int* cellItems;     // items x f2.stride
+    int* matchedDist;         // items x f2.stride scratch (vMatchedDistance)
+    int* matches21;           // items x f2.stride scratch (vnMatches21)
+    int* histBin;             // items x f1.stride scratch: rotation bin of i1 when it was accepted, else -1
+    float* prevMatched;       // items x f1.stride x 2, in/out
+    int* matches12;           // items x f1.stride
+    int* nmatches;            // items
+    int items, window, checkOri;
+    float nnratio;
+};
+
+__global__ void __launch_bounds__(128) k_search_init(const InitParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= P.items) return;
+    const int n1 = min(P.f1.n[item], P.f1.stride), n2 = min(P.f2.n[item], P.f2.stride);
+    const int* oct1 = P.f1.octave + (size_t)item * P.f1.stride;
+    const float* ang1 = P.f1.angle + (size_t)item * P.f1.stride;
+    const uint4* d1 = reinterpret_cast<const uint4*>(P.f1.desc + (size_t)item * P.f1.stride * 32);
+    const float* k2x = P.f2.x + (size_t)item * P.f2.stride;
+    const float* k2y = P.f2.y + (size_t)item * P.f2.stride;
+    const int* oct2 = P.f2.octave + (size_t)item * P.f2.stride;
+    const float* ang2 = P.f2.angle + (size_t)item * P.f2.stride;
+    const uint4* d2 = reinterpret_cast<const uint4*>(P.f2.desc + (size_t)item * P.f2.stride * 32);
+    const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+    const int* ci = P.cellItems + (size_t)item * P.f2.stride;
+    int* vmd = P.matchedDist + (size_t)item * P.f2.stride;
+    int* m21 = P.matches21 + (size_t)item * P.f2.stride;
+    int* hbin = P.histBin + (size_t)item * P.f1.stride;
+    float* prev = P.prevMatched + (size_t)item * P.f1.stride * 2;
+    int* m12 = P.matches12 + (size_t)item * P.f1.stride;
+
+    for (int i = lane; i < n2; i += 32) { vmd[i] = INT_MAX; m21[i] = -1; }
+    for (int i = lane; i < n1; i += 32) { m12[i] = -1; hbin[i] = -1; }
+    __syncwarp();
+
+    const float r = (float)P.window;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = oct1[i1];
+        if (level1 > 0) continue;                                               // :425-427
+        int c0, c1, r0, r1;
+        if (!cell_range(P.g, prev[2 * i1], prev[2 * i1 + 1], r, c0, c1, r0, r1)) continue;
+        const float qx = prev[2 * i1], qy = prev[2 * i1 + 1];
+        const uint4 a0 = __ldg(d1 + 2 * i1), a1 = __ldg(d1 + 2 * i1 + 1);
+        Top2 t = {INT_MAX, INT_MAX, -1, INT_MAX, INT_MAX, -1};
+        const bool fullRows = (r0 == 0 && r1 == GRID_ROWS - 1);
+        const int ncol = fullRows ? 1 : (c1 - c0 + 1);
+        for (int c = 0; c < ncol; c++) {
+            const int s = fullRows ? cs[c0 * GRID_ROWS] : cs[(c0 + c) * GRID_ROWS + r0];
+            const int e = fullRows ? cs[(c1 + 1) * GRID_ROWS] : cs[(c0 + c) * GRID_ROWS + r1 + 1];
+            for (int p = s + lane; p < e; p += 32) {
+                const int i2 = ci[p];
+                // level filter: minLevel = maxLevel = level1 (:429, Frame.cc:468-485)
+                const int o2 = oct2[i2];
+                if (o2 < level1 || (level1 >= 0 && o2 > level1)) continue;
+                if (!(fabsf(__fsub_rn(k2x[i2], qx)) < r && fabsf(__fsub_rn(k2y[i2], qy)) < r)) continue;
+                const int dist = hamming256(a0, a1, __ldg(d2 + 2 * i2), __ldg(d2 + 2 * i2 + 1));
+                if (vmd[i2] <= dist) continue;                                     // :448
+                top2_push(t, dist, p, 0);
+            }
+        }
+        t = top2_warp_reduce(t);
+        if (t.b <= TH_LOW && (float)t.b < __fmul_rn((float)t.s, P.nnratio)) {     // :463-465
+            if (lane == 0) {
+                const int best2 = ci[t.bp];
+                const int old = m21[best2];
+                if (old >= 0) m12[old] = -1;                                         // :467-471
+                m12[i1] = best2;
+                m21[best2] = i1;
+                vmd[best2] = t.b;
+                if (P.checkOri) {
+                    float rot = __fsub_rn(ang1[i1], ang2[best2]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));       // sic (:417,:482)
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    hbin[i1] = bin;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // The running count (nmatches++ / nmatches-- at :470,:475) equals the number of live entries of
+    // vnMatches12 at this point; recount instead of tracking the decrements.
+    __syncwarp();
+    int live = 0;
+    for (int i = lane; i < n1; i += 32) live += m12[i] >= 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) live += __shfl_xor_sync(0xffffffffu, live, d);
+    int nmatches = live;
+
+    if (P.checkOri) {
+        // histogram sizes count every acceptance, including matches stolen later (:479-486)
+        int sizes = 0;     // lane b holds the size of bin b (30 bins)
+        for (int i = 0; i < n1; i += 32) {
+            const int b = (i + lane < n1) ? hbin[i + lane] : -1;
+            for (int q = 0; q < HISTO_LENGTH; q++) {
+                const unsigned m = __ballot_sync(0xffffffffu, b == q);
+                if (lane == q) sizes += __popc(m);
+            }
+        }
+        // ComputeThreeMaxima (:1605-1646), evaluated redundantly by every lane
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int q = 0; q < HISTO_LENGTH; q++) {
+            const int s = __shfl_sync(0xffffffffu, sizes, q);
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = q; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = q; }
+            else if (s > max3) { max3 = s; ind3 = q; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+        int removed = 0;
+        for (int i = lane; i < n1; i += 32) {
+            const int b = hbin[i];
+            if (b >= 0 && b != ind1 && b != ind2 && b != ind3 && m12[i] >= 0) { m12[i] = -1; removed++; }   // :493-516
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, d);
+        nmatches -= removed;
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32)                                                    // :519-521
+        if (m12[i] >= 0) { prev[2 * i] = k2x[m12[i]]; prev[2 * i + 1] = k2y[m12[i]]; }
+    if (lane == 0) P.nmatches[item] = nmatches;
+}
+
+// ---- SearchByProjection: one warp per frame (S/ORBmatcher.cc:47-131) ------------------------
+struct ProjParams {
+    FrameDev f;
+    const float* uRight;       // items x f.stride or NULL
+    GridGeo g;
+    const int* cellStart;
+    const int* cellItems;
+    const int* mpN;
+    const uint8_t *mpInView, *mpBad;
+    const float *mpX, *mpY, *mpXR;
+    const int* mpLevel;
+    const float* mpViewCos;
+    const uint8_t* mpDesc;
+    const int* mpObs;
+    int mpStride;
+    int* kpMp;                 // items x f.stride, in/out
+    const int* kpMpObs;        // items x f.stride or NULL
+    const float* scaleFactors;
+    int nlevels;
+    int* nmatches;
+    int items;
+    float nnratio, th;
+};
+
+__global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= P.items) return;
+    const int n = min(P.f.n[item], P.f.stride), nmp = min(P.mpN[item], P.mpStride);
+    const float* kx = P.f.x + (size_t)item * P.f.stride;
+    const float* ky = P.f.y + (size_t)item * P.f.stride;
+    const int* koct = P.f.octave + (size_t)item * P.f.stride;
+    const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
+    const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
+    const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+    const int* ci = P.cellItems + (size_t)item * P.f.stride;
+    int* kpmp = P.kpMp + (size_t)item * P.f.stride;
+    const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
+    const size_t mo = (size_t)item * P.mpStride;
+    const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + mo * 32);
+    (void)n;
+
+    int nmatches = 0;
+    const bool bFactor = P.th != 1.0f;
+    for (int i = 0; i < nmp; i++) {
+        if (!P.mpInView[mo + i]) continue;                                        // :56-60
+        if (P.mpBad[mo + i]) continue;
+        const int lvl = P.mpLevel[mo + i];
+        float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
+        if (bFactor) r = __fmul_rn(r, P.th);
+        const float rs = __fmul_rn(r, P.scaleFactors[lvl]);
+        const float qx = P.mpX[mo + i], qy = P.mpY[mo + i];
+        int c0, c1, r0, r1;
+        if (!cell_range(P.g, qx, qy, rs, c0, c1, r0, r1)) continue;
+        const int minLevel = lvl - 1, maxLevel = lvl;
+        const bool check = (minLevel > 0) || (maxLevel >= 0);
+        const uint4 a0 = __ldg(md + 2 * i), a1 = __ldg(md + 2 * i + 1);
+        const float qxr = P.mpXR[mo + i];
+        Top2 t = {256, INT_MAX, -1, 256, INT_MAX, -1};
+        for (int c = c0; c <= c1; c++) {
+            const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
+            for (int p = s + lane; p < e; p += 32) {
+                const int idx = ci[p];
+                const int o = koct[idx];
+                if (check) {
+                    if (o < minLevel) continue;
+                    if (maxLevel >= 0 && o > maxLevel) continue;
+                }
+                if (!(fabsf(__fsub_rn(kx[idx], qx)) < rs && fabsf(__fsub_rn(ky[idx], qy)) < rs)) continue;
+                const int held = kpmp[idx];                                          // :89-91
+                if (held != -1) {
+                    const int obs = held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0);
+                    if (obs > 0) continue;
+                }
+                if (ur && ur[idx] > 0) {                                            // :93-98
+                    const float er = fabsf(__fsub_rn(qxr, ur[idx]));
+                    if (er > rs) continue;
+                }
+                const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                top2_push(t, dist, p, o);
+            }
+        }
+        t = top2_warp_reduce(t);
+        if (t.b <= TH_HIGH && !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s))) {   // :120-127
+            if (lane == 0) kpmp[ci[t.bp]] = i;
+            nmatches++;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) P.nmatches[item] = nmatches;
+}
+
+}  // namespace orbb200
+
+// =========================================================================================
+// host side
+// =========================================================================================
 using namespace orbb200;
-struct orbb200_matcher { int dummy; };
-#define NOT_YET(name) do { set_error(name ": not implemented yet"); return ORBB200_EINVAL; } while (0)
-extern "C" int orbb200_matcher_create(int, int, int, orbb200_matcher**) { NOT_YET("orbb200_matcher_create"); }
-extern "C" void orbb200_matcher_destroy(orbb200_matcher*) {}
-extern "C" void* orbb200_matcher_stream(orbb200_matcher*) { return nullptr; }
-extern "C" int orbb200_matcher_sync(orbb200_matcher*) { NOT_YET("orbb200_matcher_sync"); }
-extern "C" int orbb200_matcher_last_launches(const orbb200_matcher*) { return 0; }
-extern "C" int orbb200_descriptor_distance(orbb200_matcher*, const uint8_t*, const uint8_t*, int, int32_t*) { NOT_YET("orbb200_descriptor_distance"); }
-extern "C" int orbb200_search_for_initialization(orbb200_matcher*, int, const orbb200_frame_view*, const orbb200_frame_view*, int, int, float, int, int, float*, int32_t*, int32_t*, int) { NOT_YET("orbb200_search_for_initialization"); }
-extern "C" int orbb200_search_by_projection(orbb200_matcher*, int, const orbb200_frame_view*, const float*, const orbb200_mappoint_view*, int32_t*, const int32_t*, const float*, int, int, int, float, float, int32_t*, int) { NOT_YET("orbb200_search_by_projection"); }
+
+struct orbb200_matcher {
+    int maxItems, maxPoints, device, lastLaunches;
+    cudaStream_t stream;
+    int *cellStart, *cellItems, *scratchA, *scratchB, *scratchC;
+    std::vector<void*> allocs;
+    // staging for host-pointer calls
+    uint8_t* stage; size_t stageBytes;
+};
+
+static int m_alloc(orbb200_matcher* m, void** p, size_t bytes)
+{
+    ORB_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 256)));
+    m->allocs.push_back(*p);
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_matcher_create(int max_items, int max_points, int device, orbb200_matcher** out)
+{
+    if (!out || max_items < 1 || max_points < 1) { set_error("invalid matcher parameters"); return ORBB200_EINVAL; }
+    *out = nullptr;
+    int ndev = orbb200_device_count();
+    if (device < 0 || device >= ndev) { set_error("CUDA device %d not available (%d visible)", device, ndev); return ORBB200_ENODEVICE; }
+    ORB_CUDA(cudaSetDevice(device));
+    orbb200_matcher* m = new orbb200_matcher();
+    m->maxItems = max_items; m->maxPoints = max_points; m->device = device; m->lastLaunches = 0;
+    m->stage = nullptr; m->stageBytes = 0; m->stream = nullptr;
+    int rc = ORBB200_OK;
+    const size_t np = (size_t)max_items * max_points;
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->cellStart, sizeof(int) * (size_t)max_items * (GRID_CELLS + 1));
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->cellItems, sizeof(int) * np);
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchA, sizeof(int) * np);
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchB, sizeof(int) * np);
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchC, sizeof(int) * np);
+    if (rc == ORBB200_OK && cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed"); rc = ORBB200_ECUDA;
+    }
+    if (rc != ORBB200_OK) { orbb200_matcher_destroy(m); return rc; }
+    *out = m;
+    return ORBB200_OK;
+}
+
+extern "C" void orbb200_matcher_destroy(orbb200_matcher* m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->stage) cudaFree(m->stage);
+    delete m;
+}
+extern "C" void* orbb200_matcher_stream(orbb200_matcher* m) { return m ? (void*)m->stream : nullptr; }
+extern "C" int orbb200_matcher_last_launches(const orbb200_matcher* m) { return m ? m->lastLaunches : 0; }
+extern "C" int orbb200_matcher_sync(orbb200_matcher* m)
+{
+    if (!m) { set_error("null handle"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    ORB_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBB200_OK;
+}
+
+// bump allocator over one device staging block for host-pointer calls
+struct Stager {
+    orbb200_matcher* m; size_t off; cudaStream_t st;
+    int reserve(size_t bytes)
+    {
+        if (bytes > m->stageBytes) {
+            if (m->stage) cudaFree(m->stage);
+            m->stage = nullptr; m->stageBytes = 0;
+            ORB_CUDA(cudaMalloc((void**)&m->stage, bytes));
+            m->stageBytes = bytes;
+        }
+        off = 0;
+        return ORBB200_OK;
+    }
+    template <typename T> int up(const T* host, size_t count, const T** dev)
+    {
+        if (!host) { *dev = nullptr; return ORBB200_OK; }
+        T* d = reinterpret_cast<T*>(m->stage + off);
+        off += align_up(count * sizeof(T), 256);
+        ORB_CUDA(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+        *dev = d;
+        return ORBB200_OK;
+    }
+    template <typename T> T* out(size_t count)
+    {
+        T* d = reinterpret_cast<T*>(m->stage + off);
+        off += align_up(count * sizeof(T), 256);
+        return d;
+    }
+};
+static size_t pad(size_t b) { return align_up(b, 256); }
+
+extern "C" int orbb200_descriptor_distance(orbb200_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist)
+{
+    if (!m || !a || !b || !dist || n < 0) { set_error("bad argument"); return ORBB200_EINVAL; }
+    if (n == 0) return ORBB200_OK;
+    ORB_CUDA(cudaSetDevice(m->device));
+    Stager s{m, 0, m->stream};
+    int rc = s.reserve(2 * pad((size_t)n * 32) + pad((size_t)n * 4));
+    if (rc) return rc;
+    const uint8_t *da, *db;
+    if ((rc = s.up(a, (size_t)n * 32, &da)) || (rc = s.up(b, (size_t)n * 32, &db))) return rc;
+    int* dd = s.out<int>(n);
+    k_distance<<<(n + 255) / 256, 256, 0, m->stream>>>(reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(db), n, dd);
+    ORB_CHECK_LAUNCH("k_distance");
+    m->lastLaunches = 1;
+    ORB_CUDA(cudaMemcpyAsync(dist, dd, sizeof(int) * n, cudaMemcpyDeviceToHost, m->stream));
+    ORB_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBB200_OK;
+}
+
+static GridGeo grid_geo(int img_w, int img_h)
+{
+    GridGeo g;
+    g.minX = 0.0f; g.minY = 0.0f;                                   // ComputeImageBounds, no distortion (S/Frame.cc:582-588)
+    g.invW = (float)GRID_COLS / ((float)img_w - g.minX);             // S/Frame.cc:317-318
+    g.invH = (float)GRID_ROWS / ((float)img_h - g.minY);
+    return g;
+}
+
+static int check_view(const orbb200_matcher* m, int items, int stride, const char* what)
+{
+    if (items < 1 || items > m->maxItems) { set_error("%s: items %d outside 1..%d", what, items, m->maxItems); return ORBB200_EINVAL; }
+    if (stride < 1 || stride > m->maxPoints) { set_error("%s: stride %d outside 1..%d", what, stride, m->maxPoints); return ORBB200_EINVAL; }
+    return ORBB200_OK;
+}
+
+static int upload_frame(Stager& s, const orbb200_frame_view* v, int items, FrameDev* d, bool needAngle)
+{
+    const size_t np = (size_t)items * v->stride;
+    int rc;
+    d->stride = v->stride;
+    if ((rc = s.up(v->n, items, &d->n))) return rc;
+    if ((rc = s.up(v->x, np, &d->x))) return rc;
+    if ((rc = s.up(v->y, np, &d->y))) return rc;
+    if ((rc = s.up(v->octave, np, &d->octave))) return rc;
+    if ((rc = s.up(needAngle ? v->angle : nullptr, np, &d->angle))) return rc;
+    if ((rc = s.up(v->desc, np * 32, &d->desc))) return rc;
+    return ORBB200_OK;
+}
+static size_t frame_bytes(const orbb200_frame_view* v, int items)
+{
+    const size_t np = (size_t)items * v->stride;
+    return pad(items * 4) + 4 * pad(np * 4) + pad(np * 32);
+}
+static FrameDev as_dev(const orbb200_frame_view* v)
+{
+    FrameDev d;
+    d.n = v->n; d.x = v->x; d.y = v->y; d.octave = v->octave; d.angle = v->angle; d.desc = v->desc; d.stride = v->stride;
+    return d;
+}
+
+extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, const orbb200_frame_view* f1,
+                                                 const orbb200_frame_view* f2, int img_w, int img_h, float nnratio,
+                                                 int check_orientation, int window_size, float* prev_matched,
+                                                 int32_t* matches12, int32_t* nmatches, int on_device)
+{
+    if (!m || !f1 || !f2 || !prev_matched || !matches12 || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (!f1->n || !f1->octave || !f1->desc || !f2->n || !f2->x || !f2->y || !f2->octave || !f2->desc ||
+        (check_orientation && (!f1->angle || !f2->angle))) { set_error("incomplete frame view"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, f1->stride, "f1")) || (rc = check_view(m, items, f2->stride, "f2"))) return rc;
+    if (img_w < 1 || img_h < 1) { set_error("bad image bounds"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    InitParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t np1 = (size_t)items * f1->stride;
+    float* dPrev; int *dM12, *dN;
+    Stager s{m, 0, st};
+    if (on_device) {
+        P.f1 = as_dev(f1); P.f2 = as_dev(f2);
+        dPrev = prev_matched; dM12 = matches12; dN = nmatches;
+    } else {
+        if ((rc = s.reserve(frame_bytes(f1, items) + frame_bytes(f2, items) + pad(np1 * 8) + pad(np1 * 4) + pad(items * 4)))) return rc;
+        if ((rc = upload_frame(s, f1, items, &P.f1, check_orientation != 0)) || (rc = upload_frame(s, f2, items, &P.f2, check_orientation != 0))) return rc;
+        const float* dp;
+        if ((rc = s.up(prev_matched, np1 * 2, &dp))) return rc;
+        dPrev = const_cast<float*>(dp);
+        dM12 = s.out<int>(np1); dN = s.out<int>(items);
+    }
+    P.g = grid_geo(img_w, img_h);
+    P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.matchedDist = m->scratchA; P.matches21 = m->scratchB; P.histBin = m->scratchC;
+    P.prevMatched = dPrev; P.matches12 = dM12; P.nmatches = dN;
+    P.items = items; P.window = window_size; P.checkOri = check_orientation; P.nnratio = nnratio;
+    // scratch strides follow the views
+    k_build_grid<<<items, 256, 0, st>>>(P.f2, P.g, m->cellStart, m->cellItems);
+    ORB_CHECK_LAUNCH("k_build_grid");
+    k_search_init<<<(items + 3) / 4, 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_search_init");
+    m->lastLaunches = 2;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(prev_matched, dPrev, np1 * 8, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(matches12, dM12, np1 * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const orbb200_frame_view* f,
+                                            const float* u_right, const orbb200_mappoint_view* mp, int32_t* kp_mp,
+                                            const int32_t* kp_mp_obs, const float* scale_factors, int nlevels, int img_w,
+                                            int img_h, float nnratio, float th, int32_t* nmatches, int on_device)
+{
+    if (!m || !f || !mp || !kp_mp || !scale_factors || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (!f->n || !f->x || !f->y || !f->octave || !f->desc || !mp->n || !mp->in_view || !mp->bad || !mp->proj_x ||
+        !mp->proj_y || !mp->proj_xr || !mp->level || !mp->view_cos || !mp->desc || !mp->obs) { set_error("incomplete view"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, f->stride, "frame")) || (rc = check_view(m, items, mp->stride, "map points"))) return rc;
+    if (nlevels < 1 || img_w < 1 || img_h < 1) { set_error("bad geometry"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    ProjParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t np = (size_t)items * f->stride, nm = (size_t)items * mp->stride;
+    Stager s{m, 0, st};
+    int* dN;
+    if (on_device) {
+        P.f = as_dev(f); P.uRight = u_right;
+        P.mpN = mp->n; P.mpInView = mp->in_view; P.mpBad = mp->bad; P.mpX = mp->proj_x; P.mpY = mp->proj_y; P.mpXR = mp->proj_xr;
+        P.mpLevel = mp->level; P.mpViewCos = mp->view_cos; P.mpDesc = mp->desc; P.mpObs = mp->obs;
+        P.kpMp = kp_mp; P.kpMpObs = kp_mp_obs; P.scaleFactors = scale_factors; dN = nmatches;
+    } else {
+        const size_t bytes = frame_bytes(f, items) + 3 * pad(np * 4) + pad(items * 4) + 2 * pad(nm) + 6 * pad(nm * 4) + pad(nm * 32) +
+                             pad((size_t)nlevels * 4) + pad(items * 4);
+        if ((rc = s.reserve(bytes))) return rc;
+        if ((rc = upload_frame(s, f, items, &P.f, false))) return rc;
+        const int* kpmp;
+        if ((rc = s.up(u_right, np, &P.uRight)) || (rc = s.up(kp_mp, np, &kpmp)) || (rc = s.up(kp_mp_obs, np, &P.kpMpObs)) ||
+            (rc = s.up(mp->n, items, &P.mpN)) || (rc = s.up(mp->in_view, nm, &P.mpInView)) || (rc = s.up(mp->bad, nm, &P.mpBad)) ||
+            (rc = s.up(mp->proj_x, nm, &P.mpX)) || (rc = s.up(mp->proj_y, nm, &P.mpY)) || (rc = s.up(mp->proj_xr, nm, &P.mpXR)) ||
+            (rc = s.up(mp->level, nm, &P.mpLevel)) || (rc = s.up(mp->view_cos, nm, &P.mpViewCos)) ||
+            (rc = s.up(mp->desc, nm * 32, &P.mpDesc)) || (rc = s.up(mp->obs, nm, &P.mpObs)) ||
+            (rc = s.up(scale_factors, (size_t)nlevels, &P.scaleFactors))) return rc;
+        P.kpMp = const_cast<int*>(kpmp);
+        dN = s.out<int>(items);
+    }
+    P.mpStride = mp->stride; P.g = grid_geo(img_w, img_h); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.nlevels = nlevels; P.nmatches = dN; P.items = items; P.nnratio = nnratio; P.th = th;
+    k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
+    ORB_CHECK_LAUNCH("k_build_grid");
+    k_search_proj<<<(items + 3) / 4, 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_search_proj");
+    m->lastLaunches = 2;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(kp_mp, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}

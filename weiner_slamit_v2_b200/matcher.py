@@ -1,0 +1,193 @@
+"""Host-side mirror of ORB_SLAM2::ORBmatcher (I/ORBmatcher.h:37-102) over the C ABI, for the three
+in-scope entry points: DescriptorDistance, SearchForInitialization, SearchByProjection(Frame&,
+vector<MapPoint*>&, th).  Frame / MapPoint pointer graphs are flattened to structure-of-arrays
+views exactly as a C++ maintainer's shim would; results are written back into the
+same fields the reference mutates (vnMatches12, vbPrevMatched, Frame::mvpMapPoints)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FrameView, KP_DTYPE, MapPointView, check
+
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30       # S/ORBmatcher.cc:37-39
+
+
+class Frame:
+    """The fields of ORB_SLAM2::Frame the matcher reads (I/Frame.h): mvKeysUn, mDescriptors, mvuRight,
+    mvpMapPoints (as indices into the map-point list, -1 = none), mvScaleFactors, image bounds."""
+
+    def __init__(self, keys_un, descriptors, width, height, scale_factors=None, u_right=None):
+        self.mvKeysUn = np.ascontiguousarray(keys_un, KP_DTYPE)
+        self.mDescriptors = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        assert len(self.mvKeysUn) == len(self.mDescriptors)
+        self.N = len(self.mvKeysUn)
+        self.width, self.height = int(width), int(height)
+        self.mvScaleFactors = None if scale_factors is None else np.ascontiguousarray(scale_factors, np.float32)
+        self.mvuRight = np.full(self.N, -1.0, np.float32) if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        self.mvpMapPoints = np.full(self.N, -1, np.int32)
+        self.mvpMapPointObs = np.zeros(self.N, np.int32)     # Observations() of foreign map points (-2 entries)
+
+
+class MapPoints:
+    """vector<MapPoint*> flattened: the 'variables used by the tracking' (I/MapPoint.h:96-104) plus
+    GetDescriptor(), isBad(), Observations()."""
+
+    def __init__(self, proj_x, proj_y, level, view_cos, desc, in_view=None, bad=None, proj_xr=None, obs=None):
+        n = len(proj_x)
+        self.n = n
+        self.mTrackProjX = np.ascontiguousarray(proj_x, np.float32)
+        self.mTrackProjY = np.ascontiguousarray(proj_y, np.float32)
+        self.mTrackProjXR = np.zeros(n, np.float32) if proj_xr is None else np.ascontiguousarray(proj_xr, np.float32)
+        self.mnTrackScaleLevel = np.ascontiguousarray(level, np.int32)
+        self.mTrackViewCos = np.ascontiguousarray(view_cos, np.float32)
+        self.descriptor = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.mbTrackInView = np.ones(n, np.uint8) if in_view is None else np.ascontiguousarray(in_view, np.uint8)
+        self.bad = np.zeros(n, np.uint8) if bad is None else np.ascontiguousarray(bad, np.uint8)
+        self.observations = np.ones(n, np.int32) if obs is None else np.ascontiguousarray(obs, np.int32)
+
+
+def _pack(arrs, stride, dtype, tail=()):
+    out = np.zeros((len(arrs), stride) + tuple(tail), dtype)
+    for i, a in enumerate(arrs):
+        out[i, :len(a)] = a
+    return out
+
+
+def _frame_view(frames, keep):
+    """Pack a list of Frame into padded SoA arrays + the ctypes view (arrays kept alive in `keep`)."""
+    stride = max(1, max(f.N for f in frames))
+    n = np.array([f.N for f in frames], np.int32)
+    x = _pack([f.mvKeysUn["x"] for f in frames], stride, np.float32)
+    y = _pack([f.mvKeysUn["y"] for f in frames], stride, np.float32)
+    o = _pack([f.mvKeysUn["octave"] for f in frames], stride, np.int32)
+    a = _pack([f.mvKeysUn["angle"] for f in frames], stride, np.float32)
+    d = _pack([f.mDescriptors for f in frames], stride, np.uint8, (32,))
+    keep += [n, x, y, o, a, d]
+    return FrameView(n.ctypes.data, x.ctypes.data, y.ctypes.data, o.ctypes.data, a.ctypes.data, d.ctypes.data, stride), stride
+
+
+class ORBmatcher:
+    TH_HIGH, TH_LOW, HISTO_LENGTH = TH_HIGH, TH_LOW, HISTO_LENGTH
+    _shared = {}
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0, max_items=1, max_points=4096):
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self._L = _lib.load()
+        self._h = _lib.vp()
+        self.device, self.max_items, self.max_points = device, max_items, max_points
+        check(self._L.orbb200_matcher_create(max_items, max_points, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orbb200_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ensure(self, items, points):
+        if items > self.max_items or points > self.max_points:
+            self.close()
+            self.max_items, self.max_points = max(items, self.max_items), max(points, self.max_points)
+            self._h = _lib.vp()
+            check(self._L.orbb200_matcher_create(self.max_items, self.max_points, self.device, C.byref(self._h)))
+
+    @property
+    def stream(self): return self._L.orbb200_matcher_stream(self._h)
+    @property
+    def last_launches(self): return self._L.orbb200_matcher_last_launches(self._h)
+    def sync(self): check(self._L.orbb200_matcher_sync(self._h))
+
+    # ---- DescriptorDistance (static in the reference; S/ORBmatcher.cc:1651-1667) ----
+    def DescriptorDistance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.zeros(len(a), np.int32)
+        check(self._L.orbb200_descriptor_distance(self._h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return int(out[0]) if len(out) == 1 else out
+
+    # ---- SearchForInitialization (S/ORBmatcher.cc:409-524) ----
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, vnMatches12=None, windowSize=10):
+        """Returns nmatches; vbPrevMatched ((n1,2) float32) is updated in place; vnMatches12 is returned
+        through the list/array argument when given, and always as the second return value."""
+        n, m12, pm = self.search_for_initialization_batch([F1], [F2], [vbPrevMatched], windowSize)
+        vbPrevMatched[...] = pm[0]
+        if vnMatches12 is not None:
+            vnMatches12[:] = m12[0].tolist() if isinstance(vnMatches12, list) else m12[0]
+        return int(n[0]), m12[0]
+
+    def search_for_initialization_batch(self, F1s, F2s, prev_matched, windowSize=10):
+        items = len(F1s)
+        keep = []
+        v1, s1 = _frame_view(F1s, keep)
+        v2, s2 = _frame_view(F2s, keep)
+        self._ensure(items, max(s1, s2))
+        w, h = F2s[0].width, F2s[0].height
+        assert all(f.width == w and f.height == h for f in F2s), "one image geometry per call"
+        pm = _pack([np.asarray(p, np.float32).reshape(-1, 2) for p in prev_matched], s1, np.float32, (2,))
+        m12 = np.full((items, s1), -1, np.int32)
+        nm = np.zeros(items, np.int32)
+        check(self._L.orbb200_search_for_initialization(self._h, items, C.byref(v1), C.byref(v2), w, h, self.mfNNratio,
+                                                        int(self.mbCheckOrientation), int(windowSize), pm.ctypes.data,
+                                                        m12.ctypes.data, nm.ctypes.data, 0))
+        return nm, [m12[i, :F1s[i].N] for i in range(items)], [pm[i, :F1s[i].N] for i in range(items)]
+
+    # ---- SearchByProjection(Frame&, vector<MapPoint*>&, th) (S/ORBmatcher.cc:47-131) ----
+    def SearchByProjection(self, F, vpMapPoints, th=3.0):
+        n = self.search_by_projection_batch([F], [vpMapPoints], th)
+        return int(n[0])
+
+    def search_by_projection_batch(self, frames, mappoints, th=3.0):
+        """Assignments are written into each frame's mvpMapPoints (index of the map point, like
+        F.mvpMapPoints[bestIdx] = pMP)."""
+        items = len(frames)
+        keep = []
+        fv, s = _frame_view(frames, keep)
+        ms = max(1, max(m.n for m in mappoints))
+        self._ensure(items, max(s, ms))
+        w, h = frames[0].width, frames[0].height
+        sf = frames[0].mvScaleFactors
+        assert sf is not None, "Frame.mvScaleFactors is required"
+        ur = _pack([f.mvuRight for f in frames], s, np.float32)
+        kpmp = _pack([f.mvpMapPoints for f in frames], s, np.int32)
+        kpobs = _pack([f.mvpMapPointObs for f in frames], s, np.int32)
+        mn = np.array([m.n for m in mappoints], np.int32)
+        a = dict(
+            iv=_pack([m.mbTrackInView for m in mappoints], ms, np.uint8), bad=_pack([m.bad for m in mappoints], ms, np.uint8),
+            x=_pack([m.mTrackProjX for m in mappoints], ms, np.float32), y=_pack([m.mTrackProjY for m in mappoints], ms, np.float32),
+            xr=_pack([m.mTrackProjXR for m in mappoints], ms, np.float32), lv=_pack([m.mnTrackScaleLevel for m in mappoints], ms, np.int32),
+            vc=_pack([m.mTrackViewCos for m in mappoints], ms, np.float32), de=_pack([m.descriptor for m in mappoints], ms, np.uint8, (32,)),
+            ob=_pack([m.observations for m in mappoints], ms, np.int32))
+        mv = MapPointView(mn.ctypes.data, a["iv"].ctypes.data, a["bad"].ctypes.data, a["x"].ctypes.data, a["y"].ctypes.data,
+                          a["xr"].ctypes.data, a["lv"].ctypes.data, a["vc"].ctypes.data, a["de"].ctypes.data,
+                          a["ob"].ctypes.data, ms)
+        nm = np.zeros(items, np.int32)
+        check(self._L.orbb200_search_by_projection(self._h, items, C.byref(fv), ur.ctypes.data, C.byref(mv), kpmp.ctypes.data,
+                                                   kpobs.ctypes.data, sf.ctypes.data, len(sf), w, h, self.mfNNratio,
+                                                   float(th), nm.ctypes.data, 0))
+        for i, f in enumerate(frames):
+            f.mvpMapPoints[:] = kpmp[i, :f.N]
+        return nm
+
+
+def smoke(kps, desc, counts):
+    """Tiny matcher run on cuda:0 checked against the oracle (called from __graft_entry__.smoke)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import oracle_lib as O
+    n0, n1 = int(counts[0]), int(counts[1])
+    F1 = Frame(kps[0, :n0], desc[0, :n0], 640, 480)
+    F2 = Frame(kps[0, :n0], desc[0, :n0], 640, 480)            # same frame: every level-0 point matches itself
+    prev = np.stack([F1.mvKeysUn["x"], F1.mvKeysUn["y"]], 1).astype(np.float32)
+    m = ORBmatcher(0.9, True)
+    n, m12 = m.SearchForInitialization(F1, F2, prev.copy(), None, 100)
+    on, om12, _ = O.search_for_initialization(F1.mvKeysUn, F1.mDescriptors, F2.mvKeysUn, F2.mDescriptors, prev, 640, 480, 0.9, True, 100)
+    assert n == on and np.array_equal(m12, om12), "SearchForInitialization differs from the oracle"
+    d = m.DescriptorDistance(desc[0, :n0], desc[1, :n0] if n1 >= n0 else desc[0, :n0][::-1])
+    print("smoke: matcher OK (%d initialization matches, bit-exact vs oracle; %d distances)" % (n, len(np.atleast_1d(d))))

@@ -1,0 +1,74 @@
+"""Seeded synthetic matching workloads: keypoint sets, descriptor
+pairs with controlled bit noise, projected map points.  Pure numpy so oracle and GPU see the same bytes."""
+import numpy as np
+
+from ._lib import KP_DTYPE
+
+SCALE_FACTORS_8 = np.array([1.0, 1.2, 1.44, 1.728, 2.0736, 2.48832, 2.985984, 3.5831808], np.float32)
+
+
+def flip_bits(desc, nbits, rng):
+    """Flip nbits[i] random distinct bits of each 256-bit descriptor."""
+    out = desc.copy()
+    for i, k in enumerate(nbits):
+        if k:
+            pos = rng.choice(256, size=int(k), replace=False)
+            np.bitwise_xor.at(out[i], pos >> 3, (1 << (pos & 7)).astype(np.uint8))
+    return out
+
+
+def random_keypoints(n, width, height, rng, nlevels=8, level0_only=False):
+    k = np.zeros(n, KP_DTYPE)
+    if level0_only:
+        octv = np.zeros(n, np.int32)
+    else:   # geometric split like the extractor's per-level quota
+        p = 1.0 / SCALE_FACTORS_8[:nlevels] ** 1
+        octv = np.sort(rng.choice(nlevels, size=n, p=p / p.sum())).astype(np.int32)
+    sc = SCALE_FACTORS_8[octv]
+    k["x"] = (rng.integers(19, np.maximum(20, (width / sc).astype(int) - 19)) * sc).astype(np.float32)
+    k["y"] = (rng.integers(19, np.maximum(20, (height / sc).astype(int) - 19)) * sc).astype(np.float32)
+    k["octave"] = octv
+    k["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    k["size"] = (31 * sc).astype(np.int32)
+    k["response"] = rng.integers(7, 120, n)
+    k["class_id"] = -1
+    return k
+
+
+def init_pair(index, n=1000, width=640, height=480, brute_force=False):
+    """A frame pair for SearchForInitialization: F2 = F1's keypoints moved by a few pixels, rotated by
+    a common angle (so the rotation histogram has a dominant bin), descriptors with 0..60 flipped bits,
+    shuffled order.  brute_force: all keypoints on octave 0 (every F1 point is a query)."""
+    rng = np.random.default_rng(70000 + index)
+    k1 = random_keypoints(n, width, height, rng, level0_only=brute_force)
+    d1 = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+    perm = rng.permutation(n)
+    k2 = k1[perm].copy()
+    k2["x"] += rng.normal(0, 3, n).astype(np.float32)
+    k2["y"] += rng.normal(0, 3, n).astype(np.float32)
+    k2["x"] = np.clip(k2["x"], 0, width - 1); k2["y"] = np.clip(k2["y"], 0, height - 1)
+    rot = rng.uniform(0, 30)
+    k2["angle"] = np.mod(k2["angle"] - rot + rng.normal(0, 4, n), 360).astype(np.float32)
+    d2 = flip_bits(d1[perm], rng.integers(0, 61, n), rng)
+    # a few exact duplicates so distance ties and match stealing occur
+    dup = rng.choice(n, size=n // 20, replace=False)
+    d2[dup] = d2[np.roll(dup, 1)]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    return k1, d1, k2, d2, prev
+
+
+def projection_frame(index, n_kp=2000, n_mp=10000, width=1280, height=720, nlevels=8):
+    """One frame for SearchByProjection: keypoints + map points that project near them (config 5)."""
+    rng = np.random.default_rng(90000 + index)
+    kp = random_keypoints(n_kp, width, height, rng, nlevels)
+    kd = rng.integers(0, 256, (n_kp, 32)).astype(np.uint8)
+    src = rng.integers(0, n_kp, n_mp)
+    desc = flip_bits(kd[src], rng.integers(0, 41, n_mp), rng)
+    x = (kp["x"][src] + rng.normal(0, 2, n_mp)).astype(np.float32)
+    y = (kp["y"][src] + rng.normal(0, 2, n_mp)).astype(np.float32)
+    level = np.minimum(kp["octave"][src] + (rng.random(n_mp) < 0.5), nlevels - 1).astype(np.int32)
+    mp = dict(x=x, y=y, xr=np.zeros(n_mp, np.float32), level=level,
+              viewcos=rng.uniform(0.9, 1.0, n_mp).astype(np.float32), desc=desc,
+              in_view=(rng.random(n_mp) < 0.97).astype(np.uint8), bad=(rng.random(n_mp) < 0.02).astype(np.uint8),
+              obs=(rng.random(n_mp) < 0.95).astype(np.int32) * rng.integers(1, 9, n_mp).astype(np.int32))
+    return kp, kd, mp
