@@ -58,7 +58,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -280,6 +280,8 @@ def run_ours(args):
                          "all": {s: ALG_BYTES[s] * BATCH / (per_stage[i] * 1e-3) / 1e9 / peak for i, s in enumerate(STAGES)}},
             "clocks": clocks,
         }
+        if world == 1 and not args.no_matching:
+            line["matching"] = run_matching(local, max(2, min(args.steps, 5)))
         if world == 1 and not args.no_cpu_baseline:
             threads = _cpu_threads()
             sample = BATCH
@@ -289,6 +291,101 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_matching(local, steps):
+    """configs[2] and configs[4]: SearchForInitialization on 4096 brute-force-shaped pairs (1000 x 1000
+    descriptors, ratio 0.9) and SearchByProjection on 512 frames (10k map points vs 2000 keypoints), data
+    resident in HBM, CUDA events on the matcher's stream."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from weiner_slamit_v2_b200 import _lib
+    from weiner_slamit_v2_b200._lib import FrameView, MapPointView, check
+    from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
+
+    L = _lib.load()
+    dev = torch.device("cuda", local)
+    out = {}
+
+    def up(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def tile(a, items):
+        reps = (items + len(a) - 1) // len(a)
+        return np.concatenate([a] * reps)[:items]
+
+    def timed(stream, fn, steps):
+        st = torch.cuda.ExternalStream(stream, device=local)
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    # ---- configs[2]
+    items, n, distinct = 4096, 1000, 32
+    pairs = [init_pair(i, n=n, brute_force=True) for i in range(distinct)]
+    def fv(idx_k, idx_d):
+        t = dict(n=up(np.full(items, n, np.int32)),
+                 x=up(tile(np.stack([p[idx_k]["x"] for p in pairs]), items)), y=up(tile(np.stack([p[idx_k]["y"] for p in pairs]), items)),
+                 o=up(tile(np.stack([p[idx_k]["octave"] for p in pairs]), items)), a=up(tile(np.stack([p[idx_k]["angle"] for p in pairs]), items)),
+                 d=up(tile(np.stack([p[idx_d] for p in pairs]), items)))
+        return t, FrameView(t["n"].data_ptr(), t["x"].data_ptr(), t["y"].data_ptr(), t["o"].data_ptr(), t["a"].data_ptr(), t["d"].data_ptr(), n)
+    t1, v1 = fv(0, 1)
+    t2, v2 = fv(2, 3)
+    prev0 = up(tile(np.stack([p[4] for p in pairs]), items))
+    prev = prev0.clone()
+    m12 = torch.empty((items, n), dtype=torch.int32, device=dev)
+    nm = torch.empty(items, dtype=torch.int32, device=dev)
+    h = _lib.vp()
+    check(L.orbb200_matcher_create(items, 10000, local, C.byref(h)))
+    bounds = np.array([0, 0, 640, 480], np.float32)
+    def init_step():
+        prev.copy_(prev0)
+        check(L.orbb200_search_for_initialization(h, items, C.byref(v1), C.byref(v2), bounds.ctypes.data, 0.9, 1, 1000,
+                                                  prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 1))
+    ms = timed(L.orbb200_matcher_stream(h), init_step, steps)
+    acc = int(nm.sum())
+    out["search_for_initialization"] = {
+        "workload": "4096 frame pairs, 1000 x 1000 descriptors per pair (all octave 0, window > image), ratio 0.9, checkOri",
+        "ms_per_step": ms, "pairs_per_s": items / ms * 1e3, "distance_evals_per_s": items * n * n / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    del t1, t2, prev, prev0, m12
+
+    # ---- configs[4]
+    items, nk, nmp, distinct = 512, 2000, 10000, 16
+    fr = [projection_frame(i, nk, nmp) for i in range(distinct)]
+    tk = dict(n=up(np.full(items, nk, np.int32)), x=up(tile(np.stack([f[0]["x"] for f in fr]), items)),
+              y=up(tile(np.stack([f[0]["y"] for f in fr]), items)), o=up(tile(np.stack([f[0]["octave"] for f in fr]), items)),
+              d=up(tile(np.stack([f[1] for f in fr]), items)))
+    kv = FrameView(tk["n"].data_ptr(), tk["x"].data_ptr(), tk["y"].data_ptr(), tk["o"].data_ptr(), None, tk["d"].data_ptr(), nk)
+    keys = ["in_view", "bad", "x", "y", "xr", "level", "viewcos", "desc", "obs"]
+    tm = {k: up(tile(np.stack([f[2][k] for f in fr]), items)) for k in keys}
+    tm["n"] = up(np.full(items, nmp, np.int32))
+    mv = MapPointView(tm["n"].data_ptr(), *[tm[k].data_ptr() for k in keys], nmp)
+    kpmp = torch.empty((items, nk), dtype=torch.int32, device=dev)
+    nm2 = torch.empty(items, dtype=torch.int32, device=dev)
+    sf = up(SCALE_FACTORS_8)
+    b2 = np.array([0, 0, 1280, 720], np.float32)
+    def proj_step():
+        kpmp.fill_(-1)
+        check(L.orbb200_search_by_projection(h, items, C.byref(kv), None, C.byref(mv), kpmp.data_ptr(), None, sf.data_ptr(), 8,
+                                             b2.ctypes.data, 0.8, 1.0, nm2.data_ptr(), 1))
+    ms = timed(L.orbb200_matcher_stream(h), proj_step, steps)
+    acc = int(nm2.sum())
+    out["search_by_projection"] = {
+        "workload": "512 frames, 10000 projected map points vs 2000 keypoints per frame, th=1, ratio 0.8",
+        "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "map_points_per_s": items * nmp / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    L.orbb200_matcher_destroy(h)
+    return out
 
 
 def _traffic(stage):
@@ -307,6 +404,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-matching", action="store_true", help="skip the Hamming-matching configs (configs[2], configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

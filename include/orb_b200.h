@@ -138,14 +138,14 @@ typedef struct {
 } orbb200_frame_view;
 
 /* Replaces ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
- * (S/ORBmatcher.cc:409-524) for `items` independent frame pairs.  img_w/img_h give the
- * undistorted image bounds (Frame::mnMinX.. with zero distortion, S/Frame.cc:582-588).
+ * (S/ORBmatcher.cc:409-524) for `items` independent frame pairs.  bounds = {mnMinX, mnMinY, mnMaxX,
+ * mnMaxY} of the Frame class (S/Frame.cc:561-589; {0,0,cols,rows} without lens distortion).
  * prev_matched: items x f1.stride x 2 floats, in/out.  matches12: items x f1.stride ints.
  * nmatches: items ints.  All pointers are HOST pointers unless `on_device` is non-zero, in
  * which case every pointer (including those inside the views) is a device pointer and the
  * call is asynchronous on the matcher's stream. */
 int orbb200_search_for_initialization(orbb200_matcher *m, int items, const orbb200_frame_view *f1,
-                                      const orbb200_frame_view *f2, int img_w, int img_h, float nnratio,
+                                      const orbb200_frame_view *f2, const float bounds[4], float nnratio,
                                       int check_orientation, int window_size, float *prev_matched,
                                       int32_t *matches12, int32_t *nmatches, int on_device);
 
@@ -170,8 +170,8 @@ typedef struct {
  * scale_factors: nlevels floats (Frame::mvScaleFactors). nmatches: items ints. */
 int orbb200_search_by_projection(orbb200_matcher *m, int items, const orbb200_frame_view *f,
                                  const float *u_right, const orbb200_mappoint_view *mp, int32_t *kp_mp,
-                                 const int32_t *kp_mp_obs, const float *scale_factors, int nlevels, int img_w,
-                                 int img_h, float nnratio, float th, int32_t *nmatches, int on_device);
+                                 const int32_t *kp_mp_obs, const float *scale_factors, int nlevels,
+                                 const float bounds[4], float nnratio, float th, int32_t *nmatches, int on_device);
 
 #ifdef __cplusplus
 }

@@ -35,12 +35,12 @@ int orc_descriptor_distance(const uint8_t *a, const uint8_t *b)
     return dist;
 }
 
-/* Frame::ComputeImageBounds with zero distortion (S/Frame.cc:582-588) and the inverse cell
- * sizes of S/Frame.cc:317-318. */
-void orc_grid_bounds(orc_grid *g, int img_w, int img_h)
+/* Image bounds as Frame::ComputeImageBounds leaves them (S/Frame.cc:561-589; {0,0,cols,rows} when
+ * there is no lens distortion) and the inverse cell sizes of S/Frame.cc:317-318. */
+void orc_grid_bounds(orc_grid *g, const float bounds[4])
 {
-    g->min_x = 0.0f; g->max_x = (float)img_w;
-    g->min_y = 0.0f; g->max_y = (float)img_h;
+    g->min_x = bounds[0]; g->max_x = bounds[2];
+    g->min_y = bounds[1]; g->max_y = bounds[3];
     g->inv_w = (float)GRID_COLS / (g->max_x - g->min_x);
     g->inv_h = (float)GRID_ROWS / (g->max_y - g->min_y);
 }
@@ -129,7 +129,7 @@ static void three_maxima(const int *sizes, int L, int *i1, int *i2, int *i3)
 int orc_search_for_initialization(
     int n1, const float *k1x, const float *k1y, const int32_t *k1oct, const float *k1ang, const uint8_t *d1,
     int n2, const float *k2x, const float *k2y, const int32_t *k2oct, const float *k2ang, const uint8_t *d2,
-    int img_w, int img_h, float nnratio, int check_orientation, int window_size,
+    const float bounds[4], float nnratio, int check_orientation, int window_size,
     float *prev_matched, int32_t *matches12)
 {
     (void)k1x; (void)k1y;
@@ -138,7 +138,7 @@ int orc_search_for_initialization(
 
     orc_grid g;
     int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n2 + 1));
-    orc_grid_bounds(&g, img_w, img_h);
+    orc_grid_bounds(&g, bounds);
     orc_grid_assign(&g, n2, k2x, k2y, k2oct, items);
 
     int *hist_bin = (int *)malloc(sizeof(int) * (n1 + 1));   /* bin of i1 in insertion order */
@@ -213,7 +213,7 @@ int orc_search_by_projection(
     const int32_t *mp_obs,
     int n, const float *kx, const float *ky, const int32_t *koct, const float *kuright, const uint8_t *kdesc,
     int32_t *kp_mp, const int32_t *kp_mp_obs,
-    int nlevels, const float *scale_factors, int img_w, int img_h, float nnratio, float th)
+    int nlevels, const float *scale_factors, const float bounds[4], float nnratio, float th)
 {
     (void)nlevels;
     int nmatches = 0;
@@ -221,7 +221,7 @@ int orc_search_by_projection(
     orc_grid g;
     int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
     int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
-    orc_grid_bounds(&g, img_w, img_h);
+    orc_grid_bounds(&g, bounds);
     orc_grid_assign(&g, n, kx, ky, koct, items);
 
     for (int i = 0; i < nmp; i++) {

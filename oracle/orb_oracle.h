@@ -94,7 +94,7 @@ typedef struct {
     int32_t cell_start[64 * 48 + 1];    /* cell = ix*48+iy */
     int32_t *cell_items;                /* n entries */
 } orc_grid;
-void orc_grid_bounds(orc_grid *g, int img_w, int img_h);           /* undistorted-free camera: Frame.cc:582-588,317-318 */
+void orc_grid_bounds(orc_grid *g, const float bounds[4]);         /* {mnMinX,mnMinY,mnMaxX,mnMaxY}: Frame.cc:561-589,317-318 */
 void orc_grid_assign(orc_grid *g, int n, const float *kx, const float *ky, const int32_t *octave,
                      int32_t *items_storage);                      /* AssignFeaturesToGrid */
 int  orc_features_in_area(const orc_grid *g, float x, float y, float r, int minLevel, int maxLevel,
@@ -104,7 +104,7 @@ int  orc_features_in_area(const orc_grid *g, float x, float y, float r, int minL
 int orc_search_for_initialization(
     int n1, const float *k1x, const float *k1y, const int32_t *k1oct, const float *k1ang, const uint8_t *d1,
     int n2, const float *k2x, const float *k2y, const int32_t *k2oct, const float *k2ang, const uint8_t *d2,
-    int img_w, int img_h, float nnratio, int check_orientation, int window_size,
+    const float bounds[4], float nnratio, int check_orientation, int window_size,
     float *prev_matched, int32_t *matches12);
 
 /* SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:47-131), flattened:
@@ -118,7 +118,7 @@ int orc_search_by_projection(
     const int32_t *mp_obs,
     int n, const float *kx, const float *ky, const int32_t *koct, const float *kuright, const uint8_t *kdesc,
     int32_t *kp_mp, const int32_t *kp_mp_obs,
-    int nlevels, const float *scale_factors, int img_w, int img_h, float nnratio, float th);
+    int nlevels, const float *scale_factors, const float bounds[4], float nnratio, float th);
 
 #ifdef __cplusplus
 }

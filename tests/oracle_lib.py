@@ -72,12 +72,12 @@ def lib():
         L.orc_descriptor_distance.argtypes = [_u8p, _u8p]; L.orc_descriptor_distance.restype = C.c_int
         L.orc_search_for_initialization.argtypes = (
             [C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p] * 2 +
-            [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _f32p, _i32p])
+            [_f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p])
         L.orc_search_for_initialization.restype = C.c_int
         L.orc_search_by_projection.argtypes = [
             C.c_int, _u8p, _u8p, _f32p, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p,
             C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p, _i32p,
-            C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_float]
+            C.c_int, _f32p, _f32p, C.c_float, C.c_float]
         L.orc_search_by_projection.restype = C.c_int
         _lib = L
     return _lib
@@ -222,8 +222,14 @@ def _i(a): return np.ascontiguousarray(a, np.int32)
 def _b(a): return np.ascontiguousarray(a, np.uint8)
 
 
-def search_for_initialization(k1, d1, k2, d2, prev_matched, img_w, img_h, nnratio=0.9, check_ori=True, window=100):
-    """k1/k2: KP_DTYPE arrays (mvKeysUn); prev_matched: (n1,2) float32, updated copy returned."""
+def _bounds(b):
+    return np.ascontiguousarray(b, np.float32).reshape(4)
+
+
+def search_for_initialization(k1, d1, k2, d2, prev_matched, bounds, nnratio=0.9, check_ori=True, window=100):
+    """k1/k2: KP_DTYPE arrays (mvKeysUn); prev_matched: (n1,2) float32, updated copy returned;
+    bounds = (mnMinX, mnMinY, mnMaxX, mnMaxY)."""
+    bnd = _bounds(bounds)
     n1, n2 = len(k1), len(k2)
     k1x, k1y, k1o, k1a = _f(k1["x"]), _f(k1["y"]), _i(k1["octave"]), _f(k1["angle"])
     k2x, k2y, k2o, k2a = _f(k2["x"]), _f(k2["y"]), _i(k2["octave"]), _f(k2["angle"])
@@ -233,11 +239,11 @@ def search_for_initialization(k1, d1, k2, d2, prev_matched, img_w, img_h, nnrati
     n = lib().orc_search_for_initialization(
         n1, _ptr(k1x, _f32p), _ptr(k1y, _f32p), _ptr(k1o, _i32p), _ptr(k1a, _f32p), _ptr(d1, _u8p),
         n2, _ptr(k2x, _f32p), _ptr(k2y, _f32p), _ptr(k2o, _i32p), _ptr(k2a, _f32p), _ptr(d2, _u8p),
-        img_w, img_h, nnratio, int(check_ori), window, _ptr(pm, _f32p), _ptr(m12, _i32p))
+        _ptr(bnd, _f32p), nnratio, int(check_ori), window, _ptr(pm, _f32p), _ptr(m12, _i32p))
     return n, m12[:n1], pm
 
 
-def search_by_projection(mp, kp, kdesc, scale_factors, img_w, img_h, nnratio=0.8, th=1.0,
+def search_by_projection(mp, kp, kdesc, scale_factors, bounds, nnratio=0.8, th=1.0,
                          kp_mp=None, kp_mp_obs=None):
     """mp: dict of arrays (in_view,bad,x,y,xr,level,viewcos,desc,obs); kp: KP_DTYPE (mvKeysUn)."""
     nmp, n = len(mp["x"]), len(kp)
@@ -251,10 +257,11 @@ def search_by_projection(mp, kp, kdesc, scale_factors, img_w, img_h, nnratio=0.8
     x, y, xr, lv, vc = _f(a["x"]), _f(a["y"]), _f(a["xr"]), _i(a["level"]), _f(a["viewcos"])
     de, ob = _b(a["desc"]), _i(a["obs"])
     sf = _f(scale_factors)
+    bnd = _bounds(bounds)
     cnt = lib().orc_search_by_projection(
         nmp, _ptr(iv, _u8p), _ptr(bad, _u8p), _ptr(x, _f32p), _ptr(y, _f32p), _ptr(xr, _f32p),
         _ptr(lv, _i32p), _ptr(vc, _f32p), _ptr(de, _u8p), _ptr(ob, _i32p),
         n, _ptr(kx, _f32p), _ptr(ky, _f32p), _ptr(ko, _i32p), _ptr(kur, _f32p), _ptr(kdesc, _u8p),
         _ptr(kp_mp, _i32p), _ptr(kp_mp_obs, _i32p),
-        len(sf), _ptr(sf, _f32p), img_w, img_h, nnratio, th)
+        len(sf), _ptr(sf, _f32p), _ptr(bnd, _f32p), nnratio, th)
     return cnt, kp_mp[:n]

@@ -33,7 +33,7 @@ def test_search_for_initialization_matches_oracle(brute, window, n):
     nm, m12, pm = m.search_for_initialization_batch(F1, F2, [p[4] for p in pairs], window)
     total = 0
     for i, p in enumerate(pairs):
-        on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], 640, 480, 0.9, True, window)
+        on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], (0, 0, 640, 480), 0.9, True, window)
         assert nm[i] == on, (i, nm[i], on)
         assert np.array_equal(m12[i], om12)
         assert np.array_equal(pm[i], opm)
@@ -47,11 +47,11 @@ def test_search_for_initialization_no_orientation_and_second_round():
     F1, F2 = Frame(p[0], p[1], 640, 480), Frame(p[2], p[3], 640, 480)
     prev = p[4].copy()
     n1, m12 = m.SearchForInitialization(F1, F2, prev, None, 100)
-    on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], 640, 480, 0.9, False, 100)
+    on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], (0, 0, 640, 480), 0.9, False, 100)
     assert n1 == on and np.array_equal(m12, om12) and np.array_equal(prev, opm)
     # second call with the updated vbPrevMatched (what MonocularInitialization does frame after frame)
     n2, m12b = m.SearchForInitialization(F1, F2, prev, None, 100)
-    on2, om12b, opm2 = O.search_for_initialization(p[0], p[1], p[2], p[3], opm, 640, 480, 0.9, False, 100)
+    on2, om12b, opm2 = O.search_for_initialization(p[0], p[1], p[2], p[3], opm, (0, 0, 640, 480), 0.9, False, 100)
     assert n2 == on2 and np.array_equal(m12b, om12b) and np.array_equal(prev, opm2)
 
 
@@ -64,7 +64,7 @@ def test_search_for_initialization_empty_and_ragged():
     prevs = [p[4], np.zeros((0, 2), np.float32), p[4][:7]]
     nm, m12, pm = m.search_for_initialization_batch(F1, F2, prevs, 100)
     assert nm[0] == 0 and nm[1] == 0 and (m12[0] == -1).all()
-    on, om12, opm = O.search_for_initialization(p[0][:7], p[1][:7], p[2], p[3], p[4][:7], 640, 480, 0.9, True, 100)
+    on, om12, opm = O.search_for_initialization(p[0][:7], p[1][:7], p[2], p[3], p[4][:7], (0, 0, 640, 480), 0.9, True, 100)
     assert nm[2] == on and np.array_equal(m12[2], om12) and np.array_equal(pm[2], opm)
 
 
@@ -86,7 +86,7 @@ def test_search_by_projection_matches_oracle(th):
     nm = m.search_by_projection_batch(frames, mps, th)
     tot = 0
     for i, (kp, kd, mp) in enumerate(data):
-        cnt, kpmp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, 1280, 720, 0.8, th, pre[i][0], pre[i][1])
+        cnt, kpmp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, (0, 0, 1280, 720), 0.8, th, pre[i][0], pre[i][1])
         assert nm[i] == cnt, (i, nm[i], cnt)
         assert np.array_equal(frames[i].mvpMapPoints, kpmp)
         tot += cnt
@@ -102,5 +102,22 @@ def test_search_by_projection_stereo_and_zero_observation_points():
     f = Frame(kp, kd, 640, 480, SCALE_FACTORS_8, u_right=ur)
     m = ORBmatcher(0.8)
     n = m.SearchByProjection(f, MapPoints(mp["x"], mp["y"], mp["level"], mp["viewcos"], mp["desc"], mp["in_view"], mp["bad"], mp["xr"], mp["obs"]), 3.0)
-    cnt, kpmp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, 640, 480, 0.8, 3.0)
+    cnt, kpmp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, (0, 0, 640, 480), 0.8, 3.0)
     assert n == cnt and np.array_equal(f.mvpMapPoints, kpmp)
+
+
+def test_distorted_image_bounds_shift_the_grid():
+    """With lens distortion Frame::mnMinX.. are not the image rectangle (S/Frame.cc:561-580)."""
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    p = init_pair(21, n=600)
+    m = ORBmatcher(0.9, True)
+    F1, F2 = Frame(p[0], p[1], 640, 480, bounds=bounds), Frame(p[2], p[3], 640, 480, bounds=bounds)
+    prev = p[4].copy()
+    n, m12 = m.SearchForInitialization(F1, F2, prev, None, 60)
+    on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], bounds, 0.9, True, 60)
+    assert n == on and np.array_equal(m12, om12) and np.array_equal(prev, opm)
+    kp, kd, mp = projection_frame(7, n_kp=800, n_mp=2000, width=640, height=480)
+    f = Frame(kp, kd, 640, 480, SCALE_FACTORS_8, bounds=bounds)
+    cnt = m.SearchByProjection(f, MapPoints(mp["x"], mp["y"], mp["level"], mp["viewcos"], mp["desc"], mp["in_view"], mp["bad"], mp["xr"], mp["obs"]), 5.0)
+    ocnt, okp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, bounds, 0.8, 5.0)
+    assert cnt == ocnt and np.array_equal(f.mvpMapPoints, okp)

@@ -62,10 +62,10 @@ SIGNATURES = {
     "orbb200_matcher_sync": (C.c_int, [vp]),
     "orbb200_matcher_last_launches": (C.c_int, [vp]),
     "orbb200_descriptor_distance": (C.c_int, [vp, vp, vp, C.c_int, vp]),
-    "orbb200_search_for_initialization": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), C.c_int,
-                                                    C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int]),
+    "orbb200_search_for_initialization": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), vp,
+                                                    C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int]),
     "orbb200_search_by_projection": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), vp, C.POINTER(MapPointView), vp, vp,
-                                               vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, C.c_int]),
+                                               vp, C.c_int, vp, C.c_float, C.c_float, vp, C.c_int]),
 }
 
 _lib = None

@@ -498,12 +498,12 @@ extern "C" int orbb200_descriptor_distance(orbb200_matcher* m, const uint8_t* a,
     return ORBB200_OK;
 }
 
-static GridGeo grid_geo(int img_w, int img_h)
+static GridGeo grid_geo(const float* bounds)
 {
     GridGeo g;
-    g.minX = 0.0f; g.minY = 0.0f;                                   // ComputeImageBounds, no distortion (S/Frame.cc:582-588)
-    g.invW = (float)GRID_COLS / ((float)img_w - g.minX);             // S/Frame.cc:317-318
-    g.invH = (float)GRID_ROWS / ((float)img_h - g.minY);
+    g.minX = bounds[0]; g.minY = bounds[1];                           // Frame::mnMinX/Y (S/Frame.cc:561-589)
+    g.invW = (float)GRID_COLS / (bounds[2] - bounds[0]);               // mfGridElementWidthInv (S/Frame.cc:317-318)
+    g.invH = (float)GRID_ROWS / (bounds[3] - bounds[1]);
     return g;
 }
 
@@ -540,7 +540,7 @@ static FrameDev as_dev(const orbb200_frame_view* v)
 }
 
 extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, const orbb200_frame_view* f1,
-                                                 const orbb200_frame_view* f2, int img_w, int img_h, float nnratio,
+                                                 const orbb200_frame_view* f2, const float* bounds, float nnratio,
                                                  int check_orientation, int window_size, float* prev_matched,
                                                  int32_t* matches12, int32_t* nmatches, int on_device)
 {
@@ -549,7 +549,7 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
         (check_orientation && (!f1->angle || !f2->angle))) { set_error("incomplete frame view"); return ORBB200_EINVAL; }
     int rc;
     if ((rc = check_view(m, items, f1->stride, "f1")) || (rc = check_view(m, items, f2->stride, "f2"))) return rc;
-    if (img_w < 1 || img_h < 1) { set_error("bad image bounds"); return ORBB200_EINVAL; }
+    if (!bounds || !(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1])) { set_error("bad image bounds"); return ORBB200_EINVAL; }
     ORB_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = m->stream;
     InitParams P;
@@ -568,7 +568,7 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
         dPrev = const_cast<float*>(dp);
         dM12 = s.out<int>(np1); dN = s.out<int>(items);
     }
-    P.g = grid_geo(img_w, img_h);
+    P.g = grid_geo(bounds);
     P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.matchedDist = m->scratchA; P.matches21 = m->scratchB; P.histBin = m->scratchC;
     P.prevMatched = dPrev; P.matches12 = dM12; P.nmatches = dN;
@@ -590,15 +590,15 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
 
 extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const orbb200_frame_view* f,
                                             const float* u_right, const orbb200_mappoint_view* mp, int32_t* kp_mp,
-                                            const int32_t* kp_mp_obs, const float* scale_factors, int nlevels, int img_w,
-                                            int img_h, float nnratio, float th, int32_t* nmatches, int on_device)
+                                            const int32_t* kp_mp_obs, const float* scale_factors, int nlevels,
+                                            const float* bounds, float nnratio, float th, int32_t* nmatches, int on_device)
 {
     if (!m || !f || !mp || !kp_mp || !scale_factors || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
     if (!f->n || !f->x || !f->y || !f->octave || !f->desc || !mp->n || !mp->in_view || !mp->bad || !mp->proj_x ||
         !mp->proj_y || !mp->proj_xr || !mp->level || !mp->view_cos || !mp->desc || !mp->obs) { set_error("incomplete view"); return ORBB200_EINVAL; }
     int rc;
     if ((rc = check_view(m, items, f->stride, "frame")) || (rc = check_view(m, items, mp->stride, "map points"))) return rc;
-    if (nlevels < 1 || img_w < 1 || img_h < 1) { set_error("bad geometry"); return ORBB200_EINVAL; }
+    if (nlevels < 1 || !bounds || !(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1])) { set_error("bad geometry"); return ORBB200_EINVAL; }
     ORB_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = m->stream;
     ProjParams P;
@@ -626,7 +626,7 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
         P.kpMp = const_cast<int*>(kpmp);
         dN = s.out<int>(items);
     }
-    P.mpStride = mp->stride; P.g = grid_geo(img_w, img_h); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.mpStride = mp->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.nlevels = nlevels; P.nmatches = dN; P.items = items; P.nnratio = nnratio; P.th = th;
     k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");

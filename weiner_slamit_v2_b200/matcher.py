@@ -17,12 +17,14 @@ class Frame:
     """The fields of ORB_SLAM2::Frame the matcher reads (I/Frame.h): mvKeysUn, mDescriptors, mvuRight,
     mvpMapPoints (as indices into the map-point list, -1 = none), mvScaleFactors, image bounds."""
 
-    def __init__(self, keys_un, descriptors, width, height, scale_factors=None, u_right=None):
+    def __init__(self, keys_un, descriptors, width, height, scale_factors=None, u_right=None, bounds=None):
         self.mvKeysUn = np.ascontiguousarray(keys_un, KP_DTYPE)
         self.mDescriptors = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
         assert len(self.mvKeysUn) == len(self.mDescriptors)
         self.N = len(self.mvKeysUn)
         self.width, self.height = int(width), int(height)
+        # mnMinX, mnMinY, mnMaxX, mnMaxY (S/Frame.cc:561-589): the image rectangle unless lens distortion moves it
+        self.bounds = np.array([0, 0, width, height] if bounds is None else bounds, np.float32)
         self.mvScaleFactors = None if scale_factors is None else np.ascontiguousarray(scale_factors, np.float32)
         self.mvuRight = np.full(self.N, -1.0, np.float32) if u_right is None else np.ascontiguousarray(u_right, np.float32)
         self.mvpMapPoints = np.full(self.N, -1, np.int32)
@@ -128,12 +130,12 @@ class ORBmatcher:
         v1, s1 = _frame_view(F1s, keep)
         v2, s2 = _frame_view(F2s, keep)
         self._ensure(items, max(s1, s2))
-        w, h = F2s[0].width, F2s[0].height
-        assert all(f.width == w and f.height == h for f in F2s), "one image geometry per call"
+        bnd = F2s[0].bounds
+        assert all(np.array_equal(f.bounds, bnd) for f in F2s), "one image geometry per call"
         pm = _pack([np.asarray(p, np.float32).reshape(-1, 2) for p in prev_matched], s1, np.float32, (2,))
         m12 = np.full((items, s1), -1, np.int32)
         nm = np.zeros(items, np.int32)
-        check(self._L.orbb200_search_for_initialization(self._h, items, C.byref(v1), C.byref(v2), w, h, self.mfNNratio,
+        check(self._L.orbb200_search_for_initialization(self._h, items, C.byref(v1), C.byref(v2), bnd.ctypes.data, self.mfNNratio,
                                                         int(self.mbCheckOrientation), int(windowSize), pm.ctypes.data,
                                                         m12.ctypes.data, nm.ctypes.data, 0))
         return nm, [m12[i, :F1s[i].N] for i in range(items)], [pm[i, :F1s[i].N] for i in range(items)]
@@ -151,7 +153,7 @@ class ORBmatcher:
         fv, s = _frame_view(frames, keep)
         ms = max(1, max(m.n for m in mappoints))
         self._ensure(items, max(s, ms))
-        w, h = frames[0].width, frames[0].height
+        bnd = frames[0].bounds
         sf = frames[0].mvScaleFactors
         assert sf is not None, "Frame.mvScaleFactors is required"
         ur = _pack([f.mvuRight for f in frames], s, np.float32)
@@ -169,7 +171,7 @@ class ORBmatcher:
                           a["ob"].ctypes.data, ms)
         nm = np.zeros(items, np.int32)
         check(self._L.orbb200_search_by_projection(self._h, items, C.byref(fv), ur.ctypes.data, C.byref(mv), kpmp.ctypes.data,
-                                                   kpobs.ctypes.data, sf.ctypes.data, len(sf), w, h, self.mfNNratio,
+                                                   kpobs.ctypes.data, sf.ctypes.data, len(sf), bnd.ctypes.data, self.mfNNratio,
                                                    float(th), nm.ctypes.data, 0))
         for i, f in enumerate(frames):
             f.mvpMapPoints[:] = kpmp[i, :f.N]
@@ -187,7 +189,7 @@ def smoke(kps, desc, counts):
     prev = np.stack([F1.mvKeysUn["x"], F1.mvKeysUn["y"]], 1).astype(np.float32)
     m = ORBmatcher(0.9, True)
     n, m12 = m.SearchForInitialization(F1, F2, prev.copy(), None, 100)
-    on, om12, _ = O.search_for_initialization(F1.mvKeysUn, F1.mDescriptors, F2.mvKeysUn, F2.mDescriptors, prev, 640, 480, 0.9, True, 100)
+    on, om12, _ = O.search_for_initialization(F1.mvKeysUn, F1.mDescriptors, F2.mvKeysUn, F2.mDescriptors, prev, (0, 0, 640, 480), 0.9, True, 100)
     assert n == on and np.array_equal(m12, om12), "SearchForInitialization differs from the oracle"
     d = m.DescriptorDistance(desc[0, :n0], desc[1, :n0] if n1 >= n0 else desc[0, :n0][::-1])
     print("smoke: matcher OK (%d initialization matches, bit-exact vs oracle; %d distances)" % (n, len(np.atleast_1d(d))))

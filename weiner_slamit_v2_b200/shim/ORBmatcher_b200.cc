@@ -1,0 +1,166 @@
+// ORBmatcher_b200.cc -- B200 bodies for the three in-scope methods of ORB_SLAM2::ORBmatcher:
+//   DescriptorDistance                                   (replaces S/ORBmatcher.cc:1651-1667)
+//   SearchForInitialization                              (replaces S/ORBmatcher.cc:409-524)
+//   SearchByProjection(Frame&, vector<MapPoint*>&, th)   (replaces S/ORBmatcher.cc:47-131)
+// It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
+// so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
+// their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
+// replaced bodies with #ifndef ORB_B200_MATCHER.
+// The pointer graph is flattened to structure-of-arrays on the host, the search runs in CUDA
+// through include/orb_b200.h, and the results are written back into the fields the reference
+// mutates.  No CPU search path exists here; on a device error the call logs and reports 0 matches.
+#include "ORBmatcher.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "orb_b200.h"
+
+namespace ORB_SLAM2
+{
+
+namespace
+{
+// One device scratch handle per host thread: ORBmatcher is stateless and is used concurrently from
+// the Tracking, LocalMapping and LoopClosing threads (S/System.cc:156,160).
+struct ThreadMatcher {
+    orbb200_matcher* h; int items, points;
+    ThreadMatcher() : h(0), items(0), points(0) {}
+    ~ThreadMatcher() { if (h) orbb200_matcher_destroy(h); }
+    orbb200_matcher* get(int needPoints)
+    {
+        if (h && needPoints <= points) return h;
+        if (h) orbb200_matcher_destroy(h);
+        h = 0;
+        points = needPoints < 4096 ? 4096 : needPoints;
+        if (orbb200_matcher_create(1, points, 0, &h) != ORBB200_OK) {
+            std::fprintf(stderr, "ORBmatcher(B200): %s\n", orbb200_last_error());
+            h = 0; points = 0;
+        }
+        return h;
+    }
+};
+thread_local ThreadMatcher tlsMatcher;
+
+struct FrameSoA {
+    int32_t n;
+    std::vector<float> x, y, angle;
+    std::vector<int32_t> octave;
+    std::vector<unsigned char> desc;
+    orbb200_frame_view view;
+    explicit FrameSoA(const Frame& F)
+    {
+        n = (int32_t)F.mvKeysUn.size();
+        const int s = n > 0 ? n : 1;
+        x.resize(s); y.resize(s); angle.resize(s); octave.resize(s); desc.resize((size_t)s * 32);
+        for (int i = 0; i < n; i++) {
+            const cv::KeyPoint& kp = F.mvKeysUn[i];
+            x[i] = kp.pt.x; y[i] = kp.pt.y; angle[i] = kp.angle; octave[i] = kp.octave;
+            std::memcpy(&desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+        }
+        view.n = &n; view.x = &x[0]; view.y = &y[0]; view.octave = &octave[0]; view.angle = &angle[0];
+        view.desc = &desc[0]; view.stride = s;
+    }
+};
+
+void FrameBounds(float b[4])
+{
+    b[0] = Frame::mnMinX; b[1] = Frame::mnMinY; b[2] = Frame::mnMaxX; b[3] = Frame::mnMaxY;
+}
+}  // namespace
+
+int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b)
+{
+    orbb200_matcher* h = tlsMatcher.get(1);
+    int32_t dist = 0;
+    if (!h || orbb200_descriptor_distance(h, a.ptr<unsigned char>(), b.ptr<unsigned char>(), 1, &dist) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::DescriptorDistance: %s\n", orbb200_last_error());
+        return 256;
+    }
+    return dist;
+}
+
+int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                                        std::vector<int>& vnMatches12, int windowSize)
+{
+    vnMatches12 = std::vector<int>(F1.mvKeysUn.size(), -1);
+    FrameSoA s1(F1), s2(F2);
+    orbb200_matcher* h = tlsMatcher.get(s1.n > s2.n ? s1.n : s2.n);
+    if (!h) return 0;
+    std::vector<float> prev((size_t)s1.view.stride * 2, 0.f);
+    for (int i = 0; i < s1.n; i++) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    std::vector<int32_t> m12(s1.view.stride, -1);
+    int32_t nmatches = 0;
+    float bounds[4];
+    FrameBounds(bounds);
+    if (orbb200_search_for_initialization(h, 1, &s1.view, &s2.view, bounds, mfNNratio, mbCheckOrientation ? 1 : 0,
+                                          windowSize, &prev[0], &m12[0], &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchForInitialization: %s\n", orbb200_last_error());
+        return 0;
+    }
+    for (int i = 0; i < s1.n; i++) {
+        vnMatches12[i] = m12[i];
+        vbPrevMatched[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);
+    }
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th)
+{
+    const int nmp = (int)vpMapPoints.size();
+    FrameSoA s(F);
+    orbb200_matcher* h = tlsMatcher.get(s.n > nmp ? s.n : nmp);
+    if (!h || nmp == 0) return 0;
+
+    // map points -> SoA (the "variables used by the tracking", I/MapPoint.h:96-104)
+    const int ms = nmp;
+    int32_t mn = nmp;
+    std::vector<unsigned char> inView(ms), bad(ms), desc((size_t)ms * 32);
+    std::vector<float> px(ms), py(ms), pxr(ms), vcos(ms);
+    std::vector<int32_t> level(ms), obs(ms);
+    std::map<const MapPoint*, int> indexOf;
+    for (int i = 0; i < nmp; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        indexOf[pMP] = i;
+        inView[i] = pMP->mbTrackInView ? 1 : 0;
+        bad[i] = pMP->isBad() ? 1 : 0;
+        px[i] = pMP->mTrackProjX; py[i] = pMP->mTrackProjY; pxr[i] = pMP->mTrackProjXR;
+        level[i] = pMP->mnTrackScaleLevel; vcos[i] = pMP->mTrackViewCos;
+        obs[i] = pMP->Observations();
+        const cv::Mat d = pMP->GetDescriptor();
+        if (!d.empty()) std::memcpy(&desc[(size_t)i * 32], d.ptr<unsigned char>(), 32);
+    }
+    orbb200_mappoint_view mv;
+    mv.n = &mn; mv.in_view = &inView[0]; mv.bad = &bad[0]; mv.proj_x = &px[0]; mv.proj_y = &py[0]; mv.proj_xr = &pxr[0];
+    mv.level = &level[0]; mv.view_cos = &vcos[0]; mv.desc = &desc[0]; mv.obs = &obs[0]; mv.stride = ms;
+
+    // keypoint occupancy (Frame::mvpMapPoints): index into vpMapPoints, or -2 + Observations() for others
+    std::vector<int32_t> kpMp(s.view.stride, -1), kpObs(s.view.stride, 0);
+    std::vector<float> uRight(s.view.stride, -1.f);
+    for (int i = 0; i < s.n; i++) {
+        uRight[i] = F.mvuRight[i];
+        MapPoint* held = F.mvpMapPoints[i];
+        if (!held) continue;
+        std::map<const MapPoint*, int>::const_iterator it = indexOf.find(held);
+        if (it != indexOf.end()) kpMp[i] = it->second;
+        else { kpMp[i] = -2; kpObs[i] = held->Observations(); }
+    }
+    const std::vector<int32_t> before(kpMp);
+
+    float bounds[4];
+    FrameBounds(bounds);
+    int32_t nmatches = 0;
+    if (orbb200_search_by_projection(h, 1, &s.view, &uRight[0], &mv, &kpMp[0], &kpObs[0], &F.mvScaleFactors[0],
+                                     (int)F.mvScaleFactors.size(), bounds, mfNNratio, th, &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchByProjection: %s\n", orbb200_last_error());
+        return 0;
+    }
+    for (int i = 0; i < s.n; i++)
+        if (kpMp[i] != before[i] && kpMp[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[kpMp[i]];   // :125
+    return nmatches;
+}
+
+}  // namespace ORB_SLAM2
