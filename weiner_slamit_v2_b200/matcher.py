@@ -177,19 +177,3 @@ class ORBmatcher:
             f.mvpMapPoints[:] = kpmp[i, :f.N]
         return nm
 
-
-def smoke(kps, desc, counts):
-    """Tiny matcher run on cuda:0 checked against the oracle (called from __graft_entry__.smoke)."""
-    import os, sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-    import oracle_lib as O
-    n0, n1 = int(counts[0]), int(counts[1])
-    F1 = Frame(kps[0, :n0], desc[0, :n0], 640, 480)
-    F2 = Frame(kps[0, :n0], desc[0, :n0], 640, 480)            # same frame: every level-0 point matches itself
-    prev = np.stack([F1.mvKeysUn["x"], F1.mvKeysUn["y"]], 1).astype(np.float32)
-    m = ORBmatcher(0.9, True)
-    n, m12 = m.SearchForInitialization(F1, F2, prev.copy(), None, 100)
-    on, om12, _ = O.search_for_initialization(F1.mvKeysUn, F1.mDescriptors, F2.mvKeysUn, F2.mDescriptors, prev, (0, 0, 640, 480), 0.9, True, 100)
-    assert n == on and np.array_equal(m12, om12), "SearchForInitialization differs from the oracle"
-    d = m.DescriptorDistance(desc[0, :n0], desc[1, :n0] if n1 >= n0 else desc[0, :n0][::-1])
-    print("smoke: matcher OK (%d initialization matches, bit-exact vs oracle; %d distances)" % (n, len(np.atleast_1d(d))))
