@@ -36,8 +36,13 @@ for f in range(min(B, 4)):
 # device-resident timing
 d = torch.from_numpy(frames).cuda()
 st = torch.cuda.ExternalStream(ex.stream)
+ex.set_profiling(True)
 for it in range(3):
     ex.extract_device(d, B, 640, 640 * 480); ex.sync()
+acc = np.zeros(5)
+for it in range(5):
+    ex.extract_device(d, B, 640, 640 * 480); acc += ex.stage_ms()
+print("stage ms (pyramid, fast, quadtree, blur, describe):", np.round(acc / 5, 4))
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 with torch.cuda.stream(st):
     e0.record()

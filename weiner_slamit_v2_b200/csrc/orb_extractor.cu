@@ -76,7 +76,7 @@ struct ExtractParams {
     int* status;                     // device error bits
     int blurVariant;
     // k_fast shared-memory geometry
-    int fastTP, fastTH, fastSP, fastQCap, fastKCap;
+    int fastLarge, totalCells;       // fastLarge: cells exceed 37 x 34 px -> the <36,64> instantiation
     // k_quadtree shared-memory geometry
     int qtNC, qtPC;
     LevelGeo lv[MAXL];
@@ -131,49 +131,58 @@ __global__ void __launch_bounds__(256) k_resize(const ExtractParams P, int l)
 // ======================================================================================
 // K2: per-cell FAST-9/16 + NMS + threshold retry (:805-849)
 // ======================================================================================
-// Bresenham ring of radius 3 (the order is cyclic, which is all the arc test needs).
-__constant__ int c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__constant__ int c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+// The kernel is instruction-issue bound (ncu: issue slots ~80 % busy, DRAM < 2 %), so the design
+// minimises instructions per pixel rather than bytes:
+//  * the cell window (+3-px halo) is staged in shared memory EXPANDED to 16 bits per pixel, twice:
+//    copy A holds pixel pairs (2j, 2j+1) per 32-bit word, copy B pairs (2j+1, 2j+2).  Any two
+//    horizontally adjacent pixels are then ONE aligned LDS.32 away, already zero-extended;
+//  * a thread works on two adjacent centre pixels at once in the two 16-bit halves of a register:
+//    the 16 ring differences, biased by +256 so they stay positive, go through a sliding
+//    min-of-9 / max-of-9 network built from 3-input packed VIMNMX3.U16x2 (min3 of min3) --
+//    80 packed min/max for both pixels and both polarities;
+//  * pass 1 rejects pairs with two opposite ring pairs (a 9-arc of one polarity contains a pixel
+//    of every opposite pair) and queues the survivors, so the full network runs on dense warps.
 
-// Corner score of the pixel at c (shared-memory tile, pitch tp): the largest t such that 9
-// contiguous ring pixels are all > v+t or all < v-t, i.e. max over arcs of min |diff|, minus 1
-// (cv::cornerScore<16>).  Returns 0 when the pixel is not a corner at threshold t.
-__device__ __forceinline__ int fast_score(const uint8_t* c, int tp, int t)
-{
-    const int v = c[0];
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = (int)c[c_ring_dy[k] * tp + c_ring_dx[k]] - v;
-    // sliding minimum / maximum over windows of 9 on the circular 16-ring, by doubling
-    int lo2[16], hi2[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
-    int lo4[16], hi4[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-    int bright = -256, dark = 256;   // max over arcs of min(d); min over arcs of max(d)
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-        bright = max(bright, lo9);
-        dark = min(dark, hi9);
-    }
-    const int m = max(bright, -dark);
-    return m > t ? m - 1 : 0;
-}
+// FAST_TPW / FAST_TH are compile-time so that every ring load is `base + immediate`:
+//   <24,42> covers cells up to 39 x 36 px (every level of the 640x480 ... 1920x1080 pyramids),
+//   <36,64> covers the largest possible cell (57 x 57).
+constexpr int FAST_WARPS = 2;     // cells per CTA; the warps of a CTA never synchronise with each other
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_fast(const ExtractParams P)
+template <int TPW, int TH>
+struct FastGeo {
+    static constexpr int BOFF = TH * TPW;                 // copy B follows copy A (32-bit words)
+    static constexpr int SP = TPW * 2 - 4;                // score-map pitch in bytes, >= widest cell + 2, multiple of 4
+    static constexpr int QCAP = (TPW - 4) * (TH - 6);     // pixel pairs per cell, upper bound
+    static constexpr int QBYTES = 2 * QCAP + 128;         // the queue region later holds the NMS survivors (u32, <= QCAP/2 + 32)
+    static constexpr int CCAP = 2 * QCAP;                 // corner pixels per cell, upper bound
+    static constexpr int WARP_BYTES = ((2 * BOFF * 4 + (TH - 4) * SP + QBYTES + 2 * CCAP + 15) / 16) * 16;
+    // largest cell this instantiation can stage: window (cell + 6) plus up to 3 + 3 px of alignment slack
+    static constexpr bool fits(int wCell, int hCell) { return ((wCell + 12) >> 2) * 2 <= TPW && hCell + 6 <= TH; }
+};
+
+template <int TPW, int TH>
+__global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
 {
+    using G = FastGeo<TPW, TH>;
+    constexpr int BOFF = G::BOFF, SP = G::SP;
+    // Bresenham ring of radius 3 (the order is cyclic, which is all the arc test needs)
+    constexpr int RING_DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr int RING_DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    // word offset of ring pair k relative to the centre pair (which sits at an even tile column):
+    // even dx -> copy A, odd dx -> copy B (pairs starting at odd columns)
+#define RING_OFF(k) (RING_DY[k] * TPW + ((RING_DX[k] & 1) ? BOFF + (RING_DX[k] - 1) / 2 : RING_DX[k] / 2))
+    static_assert((-3 - 1) / 2 == -2 && (-1 - 1) / 2 == -1, "odd negative dx map to the pair starting one column left");
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_nq, s_nk, s_nini, s_base, s_pos;
+    constexpr unsigned FULL = 0xffffffffu;
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cell = blockIdx.x * FAST_WARPS + warp;
+    if (cell >= P.totalCells) return;
     const int frame = blockIdx.y;
     int l = 0;
-    while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].cellStart) l++;
+    while (l + 1 < P.nlevels && cell >= P.lv[l + 1].cellStart) l++;
     const LevelGeo& g = P.lv[l];
-    const int c = blockIdx.x - g.cellStart;
+    const int c = cell - g.cellStart;
     const int ci = c / g.nCols, cj = c - ci * g.nCols;
     const int iniY = BORDER + ci * g.hCell, iniX = BORDER + cj * g.wCell;
     if (iniY >= g.maxBY - 3 || iniX >= g.maxBX - 6) return;            // :810, :819
@@ -182,77 +191,194 @@ __global__ void __launch_bounds__(THREADS) k_fast(const ExtractParams P)
     if (ww < 7 || wh < 7) return;                                       // cv::FAST finds nothing in < 7 px
     const int dw = ww - 6, dh = wh - 6;                                 // detection area (3-px FAST margin)
 
-    const int TP = P.fastTP, SP = P.fastSP;
-    uint8_t* tile = smem;                                               // [fastTH][TP]
-    uint8_t* score = tile + P.fastTH * TP;                              // [(dh+2)][SP], zero border
-    uint16_t* queue = reinterpret_cast<uint16_t*>(score + (P.fastTH - 4) * SP);
-    uint32_t* klist = reinterpret_cast<uint32_t*>(queue + P.fastQCap);
+    uint32_t* tw = reinterpret_cast<uint32_t*>(smem + (size_t)warp * G::WARP_BYTES);   // [2][TH][TPW]
+    uint8_t* score = reinterpret_cast<uint8_t*>(tw + 2 * BOFF);         // [(dh+2)][SP], zero ring
+    uint16_t* queue = reinterpret_cast<uint16_t*>(score + (TH - 4) * SP);
+    uint16_t* clist = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(queue) + G::QBYTES);
+    uint32_t* klist = reinterpret_cast<uint32_t*>(queue);               // the queue is dead by then
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int pitch;
     const uint8_t* img = level_ptr(P, l, frame, pitch);
-    img += (long long)iniY * pitch + iniX;
+    // 4-byte aligned load origin: tile column 0 is image column ax, the window starts at column `shift`
+    // (1..4: at least one spare column on the left, because pairs start one pixel early when par = 1)
+    const int ax = (iniX - 1) & ~3, shift = iniX - ax;
+    const int nwords = (shift + ww + 3) >> 2;                           // <= TPW / 2
+    const uint8_t* rowp = img + (long long)iniY * pitch + ax;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3) == 0;
 
-    if (tid == 0) { s_nq = 0; s_nk = 0; s_nini = 0; s_pos = 0; }
-    for (int r = warp; r < wh; r += THREADS / 32)
-        for (int x = lane; x < ww; x += 32) tile[r * TP + x] = __ldg(img + (long long)r * pitch + x);
-    for (int i = tid; i < (dh + 2) * SP; i += THREADS) score[i] = 0;
-    __syncthreads();
+    {   // stage the window (expanded to 16 bit): two rows per step when a row needs <= 16 words,
+        // four independent loads in flight per lane
+        const int lpr = nwords <= 16 ? 16 : 32, rpi = 32 / lpr;
+        const int wl = lane & (lpr - 1), sub = lane / lpr;
+        const bool colAct = wl < nwords;
+        const uint8_t* q = rowp + (long long)sub * pitch + 4 * wl;
+        const long long qstep = (long long)rpi * pitch;
+        uint32_t* a = tw + sub * TPW + 2 * wl;
+        for (int rb = 0; rb < wh; rb += 4 * rpi) {          // warp-uniform trip count (full-mask shuffle inside)
+            const int r0 = rb + sub;
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                v[u] = 0;
+                if (colAct && r0 + u * rpi < wh) {
+                    const uint8_t* qq = q + u * qstep;
+                    if (aligned) v[u] = __ldg(reinterpret_cast<const uint32_t*>(qq));
+                    else v[u] = (uint32_t)__ldg(qq) | ((uint32_t)__ldg(qq + 1) << 8) | ((uint32_t)__ldg(qq + 2) << 16) | ((uint32_t)__ldg(qq + 3) << 24);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t nx = __shfl_down_sync(FULL, v[u], 1);
+                if (colAct && r0 + u * rpi < wh) {
+                    uint32_t* aa = a + u * rpi * TPW;
+                    *reinterpret_cast<uint2*>(aa) = make_uint2(__byte_perm(v[u], 0, 0x4140), __byte_perm(v[u], 0, 0x4342));
+                    *reinterpret_cast<uint2*>(aa + BOFF) = make_uint2(__byte_perm(v[u], 0, 0x4241), __byte_perm(v[u], nx, 0x4433) & 0x00ff00ffu);
+                }
+            }
+            q += 4 * qstep;
+            a += 4 * rpi * TPW;
+        }
+        uint4* sz = reinterpret_cast<uint4*>(score);
+        for (int i = lane; i < ((dh + 2) * SP + 15) / 16; i += 32) sz[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
 
+    // Pixel pairs start at EVEN tile columns: pair i covers detection x = 2i - par and 2i - par + 1
+    // (when par = 1 the first pair's left pixel is outside the area and is masked).
+    const int par = (shift + 3) & 1;
+    const uint32_t* tbase = tw + 3 * TPW + ((shift + 3 - par) >> 1);     // centre pair of (row 0, pair 0)
     const int tlow = min(P.iniTh, P.minTh);
-    // pass 1: cheap reject on two opposite ring pairs -- a 9-arc of one polarity contains at least
-    // one pixel of every opposite pair -- survivors are queued so pass 2 runs on dense warps.
-    for (int r = warp; r < dh; r += THREADS / 32)
-        for (int x = lane; x < dw; x += 32) {
-            const uint8_t* cpx = tile + (r + 3) * TP + x + 3;
-            const int v = cpx[0], hi = v + tlow, lo = v - tlow;
-            const int a = cpx[3 * TP], b = cpx[-3 * TP], e = cpx[3], f = cpx[-3];
-            const bool br = (a > hi || b > hi) && (e > hi || f > hi);
-            const bool dk = (a < lo || b < lo) && (e < lo || f < lo);
-            if (br || dk) queue[atomicAdd(&s_nq, 1)] = (uint16_t)(r * 64 + x);
+    const uint32_t T2 = (uint32_t)tlow * 0x00010001u;
+    const int npair = (dw + par + 1) >> 1, total = npair * dh;
+    const unsigned ltmask = (1u << lane) - 1;
+
+    // pass 1: cheap reject on the four opposite ring pairs (0,8) (4,12) (2,10) (6,14): a 9-arc of one
+    // polarity contains a pixel of every opposite pair.  Both centre pixels at once; survivors queued.
+    int nq = 0;
+    {
+        int r = lane / npair, i = lane - r * npair;
+        const int stepR = 32 / npair, stepI = 32 - stepR * npair;
+        for (int idx = lane; idx - lane < total; idx += 32) {
+            bool pass = false;
+            if (idx < total) {
+                const uint32_t* b = tbase + r * TPW + i;
+                const uint32_t V = b[0];
+                const uint32_t R0 = b[RING_OFF(0)], R8 = b[RING_OFF(8)], R4 = b[RING_OFF(4)], R12 = b[RING_OFF(12)];
+                const uint32_t R2 = b[RING_OFF(2)], R10 = b[RING_OFF(10)], R6 = b[RING_OFF(6)], R14 = b[RING_OFF(14)];
+                const uint32_t mb = __vminu2(__vminu2(__vmaxu2(R0, R8), __vmaxu2(R4, R12)), __vminu2(__vmaxu2(R2, R10), __vmaxu2(R6, R14)));
+                const uint32_t md = __vmaxu2(__vmaxu2(__vminu2(R0, R8), __vminu2(R4, R12)), __vmaxu2(__vminu2(R2, R10), __vminu2(R6, R14)));
+                const uint32_t hiV = V + T2;
+                pass = __vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, V) != V;
+            }
+            const unsigned bal = __ballot_sync(FULL, pass);
+            if (pass) queue[nq + __popc(bal & ltmask)] = (uint16_t)(r * 32 + i);
+            nq += __popc(bal);
+            r += stepR; i += stepI;
+            if (i >= npair) { i -= npair; r++; }
         }
-    __syncthreads();
-    const int nq = s_nq;
-    for (int i = tid; i < nq; i += THREADS) {
-        const int r = queue[i] >> 6, x = queue[i] & 63;
-        const int s = fast_score(tile + (r + 3) * TP + x + 3, TP, tlow);
-        if (s > 0) score[(r + 1) * SP + x + 1] = (uint8_t)s;
-        else queue[i] = 0xffff;
     }
-    __syncthreads();
-    // pass 3: 3x3 non-max suppression (strictly greater than all 8 neighbours, others count 0)
-    for (int i = tid; i < nq; i += THREADS) {
-        if (queue[i] == 0xffff) continue;
-        const int r = queue[i] >> 6, x = queue[i] & 63;
-        const uint8_t* sp = score + (r + 1) * SP + x + 1;
-        const int s = sp[0];
-        if (s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
-            s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1]) {
+    __syncwarp();
+    // pass 2: exact corner score = max over the 16 arcs of 9 of min|centre - ring|, minus 1
+    // (cv::cornerScore<16>), for both pixels and both polarities with packed 16-bit min/max.
+    // Corner pixels are compacted into clist for the NMS pass.
+    int ncorner = 0;
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int q = q0 + lane;
+        bool c0 = false, c1 = false;
+        int r = 0, x0 = 0;
+        if (q < nq) {
+            const int e = queue[q];
+            r = e >> 5;
+            const int i = e & 31;
+            const uint32_t* b = tbase + r * TPW + i;
+            const uint32_t Cm = 0x01000100u - b[0];                  // 256 - v per half: ring + Cm = 256 + (ring - v)
+            uint32_t D[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) D[k] = b[RING_OFF(k)] + Cm;
+            uint32_t lo3[16], hi3[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                lo3[k] = __vimin3_u16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
+                hi3[k] = __vimax3_u16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
+            }
+            uint32_t lo9[16], hi9[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                lo9[k] = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+                hi9[k] = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+            }
+            uint32_t bright = __vimax3_u16x2(lo9[0], lo9[1], lo9[2]), dark = __vimin3_u16x2(hi9[0], hi9[1], hi9[2]);
+#pragma unroll
+            for (int k = 3; k < 15; k += 2) {
+                bright = __vimax3_u16x2(bright, lo9[k], lo9[k + 1]);
+                dark = __vimin3_u16x2(dark, hi9[k], hi9[k + 1]);
+            }
+            bright = __vmaxu2(bright, lo9[15]);
+            dark = __vminu2(dark, hi9[15]);
+            // bright = 256 + max-arc-min(ring - v); dark = 256 + min-arc-max(ring - v); m = max(bright-256, 256-dark)
+            const uint32_t m2 = __vmaxu2(bright, 0x02000200u - dark);    // 256 + m per half
+            const int m0 = (int)(m2 & 0xffffu) - 256, m1 = (int)(m2 >> 16) - 256;
+            x0 = 2 * i - par;
+            uint8_t* sp = score + (r + 1) * SP + x0 + 1;
+            c0 = (m0 > tlow) && (x0 >= 0);
+            c1 = (m1 > tlow) && (x0 + 1 < dw);
+            if (c0) sp[0] = (uint8_t)(m0 - 1);
+            if (c1) sp[1] = (uint8_t)(m1 - 1);
+        }
+        const unsigned b0 = __ballot_sync(FULL, c0), b1 = __ballot_sync(FULL, c1);
+        if (c0) clist[ncorner + __popc(b0 & ltmask)] = (uint16_t)(r * 64 + x0);
+        ncorner += __popc(b0);
+        if (c1) clist[ncorner + __popc(b1 & ltmask)] = (uint16_t)(r * 64 + x0 + 1);
+        ncorner += __popc(b1);
+    }
+    __syncwarp();
+    // pass 3: 3x3 non-max suppression (strictly greater than all 8 neighbours, non-corners count 0)
+    int nk = 0, nini = 0;
+    for (int q0 = 0; q0 < ncorner; q0 += 32) {
+        const int q = q0 + lane;
+        bool keep = false;
+        int s = 0, r = 0, x = 0;
+        if (q < ncorner) {
+            const int e = clist[q];
+            r = e >> 6; x = e & 63;
+            const uint8_t* sp = score + (r + 1) * SP + x + 1;
+            s = sp[0];
+            const int nb = max(max(max((int)sp[-1], (int)sp[1]), max((int)sp[-SP - 1], (int)sp[-SP])),
+                               max(max((int)sp[-SP + 1], (int)sp[SP - 1]), max((int)sp[SP], (int)sp[SP + 1])));
+            keep = s > nb;
+        }
+        const unsigned bal = __ballot_sync(FULL, keep);
+        if (keep) {
             const int xr = x + 3 + cj * g.wCell, yr = r + 3 + ci * g.hCell;   // relative to the border (:840-841)
-            klist[atomicAdd(&s_nk, 1)] = (uint32_t)xr | ((uint32_t)yr << 12) | ((uint32_t)s << 24);
-            if (s >= P.iniTh) atomicAdd(&s_nini, 1);
+            klist[nk + __popc(bal & ltmask)] = (uint32_t)xr | ((uint32_t)yr << 12) | ((uint32_t)s << 24);
         }
+        nk += __popc(bal);
+        nini += __popc(__ballot_sync(FULL, keep && s >= P.iniTh));
     }
-    __syncthreads();
+    __syncwarp();
     // threshold retry (:829-833): keypoints at iniThFAST if the cell has any, else those at minThFAST
-    const int nk = s_nk;
-    const bool useIni = s_nini > 0;
-    const int thr = useIni ? P.iniTh : P.minTh;
     // (if iniTh < minTh and nothing reached iniTh, nothing reaches minTh either)
-    const int total = useIni ? s_nini : (P.minTh <= P.iniTh ? nk : 0);
-    if (total == 0) return;
-    if (tid == 0) s_base = atomicAdd(&P.candCount[frame * P.nlevels + l], total);
-    __syncthreads();
-    const int base = s_base;
+    const bool useIni = nini > 0;
+    const int thr = useIni ? P.iniTh : P.minTh;
+    const int ntotal = useIni ? nini : (P.minTh <= P.iniTh ? nk : 0);
+    if (ntotal == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&P.candCount[frame * P.nlevels + l], ntotal);
+    base = __shfl_sync(FULL, base, 0);
     uint32_t* out = P.cand + (long long)frame * P.candFrameCap + g.candOff;
-    for (int i = tid; i < nk; i += THREADS) {
-        const uint32_t e = klist[i];
-        if ((int)(e >> 24) >= thr) {
-            const int p = base + atomicAdd(&s_pos, 1);
+    for (int i0 = 0; i0 < nk; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t e = i < nk ? klist[i] : 0;
+        const bool take = i < nk && (int)(e >> 24) >= thr;
+        const unsigned bal = __ballot_sync(FULL, take);
+        if (take) {
+            const int p = base + __popc(bal & ltmask);
             if (p < g.candCap) out[p] = e;
             else atomicOr(P.status, STATUS_CAND_OVERFLOW);
         }
+        base += __popc(bal);
     }
+#undef RING_OFF
 }
 
 // ======================================================================================
@@ -922,14 +1048,12 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     P.pyrFrameBytes = std::max<long long>(pyrOff, 256); P.blurFrameBytes = blurOff;
     P.candFrameCap = candOff; P.kpFrameCap = kpOff; P.outCap = kpOff;
 
-    // k_fast shared memory: window tile, score map with a zero ring, candidate queue, kept list
-    if (maxWCell > 63 - 6 || maxHCell > 63 - 6) { set_error("FAST cell larger than 57 px"); delete h; return ORBB200_EGEOMETRY; }
-    P.fastTP = (int)align_up(maxWCell + 6, 4); P.fastTH = maxHCell + 6;
-    P.fastSP = (int)align_up(maxWCell + 2, 4);
-    P.fastQCap = (int)align_up((size_t)maxWCell * maxHCell, 8);
-    P.fastKCap = ((maxWCell + 1) / 2) * ((maxHCell + 1) / 2) + 8;
-    h->fastSmem = (size_t)P.fastTH * P.fastTP + (size_t)(P.fastTH - 4) * P.fastSP + 2 * (size_t)P.fastQCap + 4 * (size_t)P.fastKCap;
-    h->fastSmem = align_up(h->fastSmem, 16);
+    // k_fast: pick the tile instantiation that holds the largest cell (+6 halo, +6 alignment slack)
+    if (maxWCell > 57 || maxHCell > 57) { set_error("FAST cell larger than 57 px"); delete h; return ORBB200_EGEOMETRY; }
+    P.fastLarge = FastGeo<24, 42>::fits(maxWCell, maxHCell) ? 0 : 1;
+    if (P.fastLarge && !FastGeo<36, 64>::fits(maxWCell, maxHCell)) { set_error("FAST cell does not fit the staging tile"); delete h; return ORBB200_EGEOMETRY; }
+    P.totalCells = cells;
+    h->fastSmem = (size_t)FAST_WARPS * (P.fastLarge ? FastGeo<36, 64>::WARP_BYTES : FastGeo<24, 42>::WARP_BYTES);
     // k_quadtree shared memory: 88 bytes per node slot + 6 bytes per candidate held on chip
     P.qtNC = (int)align_up(maxKpCap + 8, 8);
     const size_t perNode = 8 + 8 + 8 + 4 * 7 + 16 + 16;
@@ -962,7 +1086,9 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     if (!tabs.empty()) e = cudaMemcpy(dTabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(P.status, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
+    if (e == cudaSuccess) e = P.fastLarge
+        ? cudaFuncSetAttribute(k_fast<36, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem)
+        : cudaFuncSetAttribute(k_fast<24, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qtSmem);
     if (e != cudaSuccess) {
         set_error("extractor_create: %s", cudaGetErrorString(e));
@@ -1048,7 +1174,11 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
     STAGE_MARK(1);
-    k_fast<128><<<dim3(h->totalCells, batch), 128, h->fastSmem, st>>>(P);
+    {
+        const dim3 grid((h->totalCells + FAST_WARPS - 1) / FAST_WARPS, batch);
+        if (P.fastLarge) k_fast<36, 64><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
+        else k_fast<24, 42><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
+    }
     ORB_CHECK_LAUNCH("k_fast"); launches++;
     STAGE_MARK(2);
     k_quadtree<<<dim3(P.nlevels, batch), QT_THREADS, h->qtSmem, st>>>(P);
