@@ -76,7 +76,7 @@ struct ExtractParams {
     int* status;                     // device error bits
     int blurVariant;
     // k_fast shared-memory geometry
-    int fastLarge, totalCells;       // fastLarge: cells exceed 37 x 34 px -> the <36,64> instantiation
+    int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <36,64> instantiation
     // k_quadtree shared-memory geometry
     int qtNC, qtPC;
     LevelGeo lv[MAXL];
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_resize(const ExtractParams P, int l)
     const int frame = blockIdx.z;
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 8 + threadIdx.y;
-    if (y >= g.h || x0 >= g.w) return;
+    if (y >= g.h || x0 >= g.w + 4) return;        // columns w..w+3: REFLECT_101 continuation for k_blur
     int sp;
     const uint8_t* src = level_ptr(P, l - 1, frame, sp);
     uint8_t* dst = P.pyr + (long long)frame * P.pyrFrameBytes + g.pyrOff;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_resize(const ExtractParams P, int l)
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int x = x0 + i;
-        if (x < g.w) {
+        if (x < g.w + 4) {
             const short4 t = __ldg(xt + x);
             const int r0 = (int)__ldg(s0 + t.x) * t.y + (int)__ldg(s0 + t.w) * t.z;
             const int r1 = (int)__ldg(s1 + t.x) * t.y + (int)__ldg(s1 + t.w) * t.z;
@@ -643,7 +643,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
 // ======================================================================================
 // K5: GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (:1117), 8.8 fixed point like OpenCV
 // ======================================================================================
-constexpr int BL_TW = 128, BL_TH = 32, BL_THREADS = 256;
+// Issue-bound, so built for few instructions per pixel: a thread owns 4 adjacent columns (one 32-bit
+// word) and walks down BL_ROWS rows.  Horizontal pass on packed bytes: two IDP.4A per pixel on byte
+// windows cut out of three aligned words with PRMT.  Vertical pass: a 7-row register window of the
+// 16-bit row sums (the loop is unrolled by 7 so the window rotates by renaming), symmetric taps
+// folded (3 adds + 4 multiply-adds per pixel).  out = (sum + 2^15) >> 16 is byte 2 of the accumulator.
+// Columns w..w+3 of levels >= 1 hold the REFLECT_101 continuation (k_resize writes them), so only the
+// left edge and the level-0 right edge need a fix-up, both a single PRMT.
+constexpr int BL_ROWS = 36, BL_WARPS = 4;     // 36 output rows + 6 halo rows = 6 groups of 7 input rows
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
@@ -652,51 +659,85 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
-__global__ void __launch_bounds__(BL_THREADS) k_blur(const ExtractParams P)
+__device__ __forceinline__ void blur_load_words(const uint8_t* row, int x0, int w, bool fast, bool left, bool rightFix,
+                                                uint32_t& w0, uint32_t& w1, uint32_t& w2)
 {
-    __shared__ __align__(16) uint8_t tile[BL_TH + 6][BL_TW + 8];
-    __shared__ __align__(16) uint16_t hsum[BL_TH + 6][BL_TW];
+    if (fast) {
+        w1 = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
+        w0 = left ? 0u : __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 4));
+        w2 = rightFix ? 0u : __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 4));
+        if (left) w0 = __byte_perm(w1, w2, 0x1234);          // p[-4..-1] = p[4], p[3], p[2], p[1]
+        if (rightFix) w2 = __byte_perm(w0, w1, 0x3456);      // p[w..w+3] = p[w-2], p[w-3], p[w-4], p[w-5]
+    } else {                                                 // unaligned or odd-width level 0: byte gathers
+        uint32_t v[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            v[j] = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int x = reflect101(min(x0 - 4 + 4 * j + b, w + 3), w);
+                v[j] |= (uint32_t)__ldg(row + x) << (8 * b);
+            }
+        }
+        w0 = v[0]; w1 = v[1]; w2 = v[2];
+    }
+}
+
+__global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * BL_WARPS + warp;
+    if (tile >= P.totalBlurTiles) return;
     const int frame = blockIdx.y;
     int l = 0;
-    while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].blurTileStart) l++;
+    while (l + 1 < P.nlevels && tile >= P.lv[l + 1].blurTileStart) l++;
     const LevelGeo& g = P.lv[l];
     if (P.lkpCount[frame * P.nlevels + l] == 0) return;       // the reference skips empty levels (:1112)
-    const int t = blockIdx.x - g.blurTileStart;
+    const int t = tile - g.blurTileStart;
     const int ty = t / g.blurTilesX, tx = t - ty * g.blurTilesX;
-    const int x0 = tx * BL_TW, y0 = ty * BL_TH;
+    const int x0 = tx * 128 + 4 * lane, y0 = ty * BL_ROWS;
+    if (x0 >= g.w) return;
     int pitch;
     const uint8_t* img = level_ptr(P, l, frame, pitch);
-    const int k0 = 18, k1 = 34, k2 = P.blurVariant ? 49 : 48, k3 = P.blurVariant ? 55 : 56;
-    const int tid = threadIdx.x;
-
-    for (int i = tid; i < (BL_TH + 6) * (BL_TW + 6); i += BL_THREADS) {
-        const int r = i / (BL_TW + 6), c = i - r * (BL_TW + 6);
-        const int sy = reflect101(min(y0 + r - 3, g.h + 2), g.h), sx = reflect101(min(x0 + c - 3, g.w + 2), g.w);
-        tile[r][c] = __ldg(img + (long long)sy * pitch + sx);
-    }
-    __syncthreads();
-    for (int i = tid; i < (BL_TH + 6) * BL_TW; i += BL_THREADS) {
-        const int r = i / BL_TW, c = i - r * BL_TW;
-        const uint8_t* p = &tile[r][c];
-        hsum[r][c] = (uint16_t)(k0 * (p[0] + p[6]) + k1 * (p[1] + p[5]) + k2 * (p[2] + p[4]) + k3 * p[3]);
-    }
-    __syncthreads();
     uint8_t* dst = P.blur + (long long)frame * P.blurFrameBytes + g.blurOff;
-    for (int i = tid; i < BL_TH * (BL_TW / 4); i += BL_THREADS) {
-        const int r = i / (BL_TW / 4), c4 = (i - r * (BL_TW / 4)) * 4;
-        const int y = y0 + r, x = x0 + c4;
-        if (y >= g.h || x >= g.w) continue;
-        uint32_t out = 0;
+
+    const bool alignedSrc = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3) == 0;
+    // level 0 is the caller's buffer: nothing beyond column w-1 may be read; levels >= 1 carry 4 reflected columns
+    const bool fast = alignedSrc && (l > 0 || (g.w & 3) == 0 || x0 + 8 <= g.w);
+    const bool left = x0 == 0, rightFix = (l == 0) && (x0 + 4 >= g.w);
+    const uint32_t k0 = 18, k1 = 34, k2 = P.blurVariant ? 49 : 48, k3 = P.blurVariant ? 55 : 56;
+    const uint32_t kA = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);     // taps for p[x-3..x]
+    const uint32_t kB = k2 | (k1 << 8) | (k0 << 16);                  // taps for p[x+1..x+3]
+    const int yEnd = min(y0 + BL_ROWS, g.h);
+
+    int H[7][4];
+#pragma unroll 1
+    for (int grp = 0; grp < (BL_ROWS + 6) / 7; grp++) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t acc = (uint32_t)k0 * (hsum[r][c4 + j] + hsum[r + 6][c4 + j]) +
-                                 (uint32_t)k1 * (hsum[r + 1][c4 + j] + hsum[r + 5][c4 + j]) +
-                                 (uint32_t)k2 * (hsum[r + 2][c4 + j] + hsum[r + 4][c4 + j]) +
-                                 (uint32_t)k3 * hsum[r + 3][c4 + j];
-            const uint32_t v = min((acc + 32768u) >> 16, 255u);
-            out |= v << (8 * j);
+        for (int u = 0; u < 7; u++) {
+            const int ir = grp * 7 + u;
+            const int oy = y0 + ir - 6;                        // output row completed by this input row
+            if (oy >= yEnd) break;
+            const int iy = reflect101(y0 - 3 + ir, g.h);
+            uint32_t w0, w1, w2;
+            blur_load_words(img + (long long)iy * pitch, x0, g.w, fast, left, rightFix, w0, w1, w2);
+            H[u][0] = __dp4a(__byte_perm(w0, w1, 0x4321), kA, __dp4a(__byte_perm(w1, w2, 0x4321), kB, 0u));
+            H[u][1] = __dp4a(__byte_perm(w0, w1, 0x5432), kA, __dp4a(__byte_perm(w1, w2, 0x5432), kB, 0u));
+            H[u][2] = __dp4a(__byte_perm(w0, w1, 0x6543), kA, __dp4a(__byte_perm(w1, w2, 0x6543), kB, 0u));
+            H[u][3] = __dp4a(w1, kA, __dp4a(w2, kB, 0u));
+            if (oy >= y0) {
+                uint32_t acc[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // window rows: oldest = slot (u+1)%7 ... newest = slot u
+                    acc[j] = 32768u + k0 * (uint32_t)(H[(u + 1) % 7][j] + H[u][j]) + k1 * (uint32_t)(H[(u + 2) % 7][j] + H[(u + 6) % 7][j]) +
+                             k2 * (uint32_t)(H[(u + 3) % 7][j] + H[(u + 5) % 7][j]) + k3 * (uint32_t)H[(u + 4) % 7][j];
+                    if (P.blurVariant) acc[j] = min(acc[j], 0x00ffffffu);    // taps sum to 257: saturate like OpenCV
+                }
+                const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
+                *reinterpret_cast<uint32_t*>(dst + (long long)oy * g.pitch + x0) = __byte_perm(lo, hi, 0x5410);
+            }
         }
-        *reinterpret_cast<uint32_t*>(dst + (long long)y * g.pitch + x) = out;
     }
 }
 
@@ -824,8 +865,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParam
     const int u = lane - HALF_PATCH;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-#pragma unroll 1
-        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
+#pragma unroll
+        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {         // 31 independent loads in flight
             if (abs(u) <= c_umax[abs(v)]) {
                 const int val = __ldg(c + v * pitch + u);
                 m10 += u * val;
@@ -917,7 +958,7 @@ static short coef11(float c)
 static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<short4>& xt, std::vector<short4>& yt)
 {
     const double scale_x = 1. / ((double)dw / sw), scale_y = 1. / ((double)dh / sh);
-    xt.resize(dw); yt.resize(dh);
+    xt.resize(dw + 4); yt.resize(dh);
     for (int dx = 0; dx < dw; dx++) {
         float fx = (float)((dx + 0.5) * scale_x - 0.5);
         int sx = (int)floorf(fx);
@@ -926,6 +967,7 @@ static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<shor
         if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
         xt[dx] = make_short4((short)sx, coef11(1.f - fx), coef11(fx), (short)std::min(sx + 1, sw - 1));
     }
+    for (int i = 0; i < 4; i++) xt[dw + i] = xt[dw - 2 - i];    // columns dw..dw+3 mirror dw-2..dw-5 (REFLECT_101)
     for (int dy = 0; dy < dh; dy++) {
         float fy = (float)((dy + 0.5) * scale_y - 0.5);
         int sy = (int)floorf(fy);
@@ -1007,7 +1049,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         LevelGeo& g = P.lv[l];
         g.w = round_half_even((float)width * h->invScale[l]);      // :1145
         g.h = round_half_even((float)height * h->invScale[l]);
-        g.pitch = (int)align_up(g.w, 16);
+        g.pitch = (int)align_up(g.w + 4, 16);       // >= 4 spare columns: k_resize stores the REFLECT_101 continuation there
         g.maxBX = g.w - EDGE + 3; g.maxBY = g.h - EDGE + 3;
         const float fw = (float)(g.maxBX - BORDER), fh = (float)(g.maxBY - BORDER);
         if (fw < 30.f || fh < 30.f) {
@@ -1041,10 +1083,11 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
             g.xtabOff = (int)tabs.size(); tabs.insert(tabs.end(), xt.begin(), xt.end());
             g.ytabOff = (int)tabs.size(); tabs.insert(tabs.end(), yt.begin(), yt.end());
         }
-        g.blurTilesX = (g.w + BL_TW - 1) / BL_TW;
-        g.blurTileStart = tiles; tiles += g.blurTilesX * ((g.h + BL_TH - 1) / BL_TH);
+        g.blurTilesX = (g.w + 127) / 128;
+        g.blurTileStart = tiles; tiles += g.blurTilesX * ((g.h + BL_ROWS - 1) / BL_ROWS);
     }
     h->totalCells = cells; h->totalBlurTiles = tiles; h->maxKp = kpOff;
+    P.totalBlurTiles = tiles;
     P.pyrFrameBytes = std::max<long long>(pyrOff, 256); P.blurFrameBytes = blurOff;
     P.candFrameCap = candOff; P.kpFrameCap = kpOff; P.outCap = kpOff;
 
@@ -1169,7 +1212,7 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
     STAGE_MARK(0);
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeo& g = P.lv[l];
-        dim3 grid((g.w + 127) / 128, (g.h + 7) / 8, batch), block(32, 8);
+        dim3 grid((g.w + 4 + 127) / 128, (g.h + 7) / 8, batch), block(32, 8);
         k_resize<<<grid, block, 0, st>>>(P, l);
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
@@ -1184,7 +1227,7 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
     k_quadtree<<<dim3(P.nlevels, batch), QT_THREADS, h->qtSmem, st>>>(P);
     ORB_CHECK_LAUNCH("k_quadtree"); launches++;
     STAGE_MARK(3);
-    k_blur<<<dim3(h->totalBlurTiles, batch), BL_THREADS, 0, st>>>(P);
+    k_blur<<<dim3((h->totalBlurTiles + BL_WARPS - 1) / BL_WARPS, batch), BL_WARPS * 32, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_blur"); launches++;
     STAGE_MARK(4);
     k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
