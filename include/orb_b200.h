@@ -50,7 +50,7 @@ typedef struct {
 typedef struct orbb200_extractor orbb200_extractor;
 
 /* Replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
- * (S/ORBextractor.cc:415-482).  width/height fix the frame geometry of this handle,
+ * (S/ORBextractor.cc:415-482; 1 < scaleFactor <= 2).  width/height fix the frame geometry of this handle,
  * max_batch the largest batch one call may carry, device the CUDA ordinal.
  * blur_taps: 0 = OpenCV >= 3.x fixed-point Gaussian {18,34,48,56,48,34,18}/256,
  *            1 = OpenCV 2.4.9 {18,34,49,55,49,34,18}/256 (what the Android build linked). */

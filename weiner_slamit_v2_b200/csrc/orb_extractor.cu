@@ -56,7 +56,7 @@ struct ExtractParams {
     int nlevels, iniTh, minTh, batch;
     const uint8_t* in;               // level 0 = the caller's frames
     long long inFrameStride;
-    int inPitch;
+    int inPitch, inRowBytes;         // inRowBytes: bytes of a level-0 row that may be read as whole aligned words
     uint8_t* pyr;                    // levels 1.. of every frame
     long long pyrFrameBytes;
     uint8_t* blur;                   // blurred levels 0.. of every frame
@@ -95,37 +95,83 @@ enum { STATUS_QT_RUNAWAY = 1, STATUS_CAND_OVERFLOW = 2, STATUS_KP_OVERFLOW = 4 }
 // K1: pyramid level from the previous level (cv::resize INTER_LINEAR, 8UC1; :1157)
 // ======================================================================================
 // xtab[x] = (sx, alpha0, alpha1, sx+1 clamped), ytab[y] = (sy0, sy1, beta0, beta1), both computed on
-// the host with the reference's float/double arithmetic.  Each thread produces 4 adjacent pixels
-// and stores them as one 32-bit word (row pitch is a multiple of 16).
-__global__ void __launch_bounds__(256) k_resize(const ExtractParams P, int l)
+// the host with the reference's float/double arithmetic (11-bit coefficients).
+// Issue-bound, so: a thread owns 4 adjacent destination columns and walks down RZ_ROWS rows.  The
+// column geometry (byte selectors, packed coefficients) is set up once; per source row the thread
+// loads three aligned words, funnel-shifts them with two PRMT, and each column's horizontal blend
+// S[sx]*a0 + S[sx+1]*a1 is one PRMT + one IDP.2A (coefficients in the 16-bit lanes, pixels in the
+// byte lanes).  A source row shared by two consecutive destination rows is computed once.  The
+// vertical blend ((b*(r>>4))>>16 twice, +2, >>2) is two IMAD.HI per pixel.
+// Columns w..w+3 are written too: they hold the REFLECT_101 continuation that k_blur reads.
+constexpr int RZ_ROWS = 16, RZ_WARPS = 4;
+
+__device__ __forceinline__ void resize_hrow(const uint8_t* row, int a, bool ld1, bool ld2, uint32_t selShift,
+                                            const uint32_t (&sel)[4], const uint32_t (&coef)[4], uint32_t (&r)[4])
+{
+    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(row + a));
+    const uint32_t w1 = ld1 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 4)) : 0u;
+    const uint32_t w2 = ld2 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 8)) : 0u;
+    const uint32_t lo = __byte_perm(w0, w1, selShift), hi = __byte_perm(w1, w2, selShift);
+#pragma unroll
+    for (int j = 0; j < 4; j++) r[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;
+}
+
+__global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P, int l)
 {
     const LevelGeo& g = P.lv[l];
     const int frame = blockIdx.z;
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (y >= g.h || x0 >= g.w + 4) return;        // columns w..w+3: REFLECT_101 continuation for k_blur
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int yBeg = (blockIdx.y * RZ_WARPS + (threadIdx.x >> 5)) * RZ_ROWS;
+    if (x0 >= g.w + 4 || yBeg >= g.h) return;
     int sp;
     const uint8_t* src = level_ptr(P, l - 1, frame, sp);
+    const int rowBytes = (l - 1 == 0) ? P.inRowBytes : sp;    // level 0 may be the caller's buffer: never read past its pixels
     uint8_t* dst = P.pyr + (long long)frame * P.pyrFrameBytes + g.pyrOff;
     const short4* xt = P.tabs + g.xtabOff;
-    const short4 yt = __ldg(P.tabs + g.ytabOff + y);
-    const uint8_t* s0 = src + (long long)yt.x * sp;
-    const uint8_t* s1 = src + (long long)yt.y * sp;
-    const int b0 = yt.z, b1 = yt.w;
-    uint32_t out = 0;
+
+    // column geometry, once per thread
+    short4 t[4];
+    int bmin = 1 << 30;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int x = x0 + i;
-        if (x < g.w + 4) {
-            const short4 t = __ldg(xt + x);
-            const int r0 = (int)__ldg(s0 + t.x) * t.y + (int)__ldg(s0 + t.w) * t.z;
-            const int r1 = (int)__ldg(s1 + t.x) * t.y + (int)__ldg(s1 + t.w) * t.z;
-            int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-            out |= (uint32_t)v << (8 * i);
-        }
+    for (int j = 0; j < 4; j++) {
+        t[j] = __ldg(xt + min(x0 + j, g.w + 3));
+        bmin = min(bmin, (int)t[j].x);
     }
-    *reinterpret_cast<uint32_t*>(dst + (long long)y * g.pitch + x0) = out;
+    const int a = bmin & ~3;
+    const uint32_t selShift = 0x3210u + 0x1111u * (uint32_t)(bmin - a);
+    uint32_t sel[4], coef[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        sel[j] = (uint32_t)(t[j].x - bmin) | ((uint32_t)(t[j].w - bmin) << 4);    // bytes S[sx], S[sx+1] -> byte lanes 0,1
+        coef[j] = (uint32_t)(uint16_t)t[j].y | ((uint32_t)(uint16_t)t[j].z << 16);
+    }
+    const bool ld1 = a + 4 < rowBytes, ld2 = a + 8 < rowBytes;
+
+    const short4* yt = P.tabs + g.ytabOff;
+    const int yEnd = min(yBeg + RZ_ROWS, g.h);
+    uint32_t r0[4], r1[4];
+    int cur1 = -1;                                            // source row held in r1
+    for (int y = yBeg; y < yEnd; y++) {
+        const short4 ty = __ldg(yt + y);
+        if (ty.x == cur1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) r0[j] = r1[j];
+        } else {
+            resize_hrow(src + (long long)ty.x * sp, a, ld1, ld2, selShift, sel, coef, r0);
+        }
+        if (ty.y == ty.x) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) r1[j] = r0[j];
+        } else {
+            resize_hrow(src + (long long)ty.y * sp, a, ld1, ld2, selShift, sel, coef, r1);
+        }
+        cur1 = ty.y;
+        const uint32_t B0 = (uint32_t)ty.z << 16, B1 = (uint32_t)ty.w << 16;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = min((__umulhi(B0, r0[j]) + __umulhi(B1, r1[j]) + 2u) >> 2, 255u);
+        *reinterpret_cast<uint32_t*>(dst + (long long)y * g.pitch + x0) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+    }
 }
 
 // ======================================================================================
@@ -981,7 +1027,7 @@ template <typename T>
 static int dev_alloc(orbb200_extractor* h, T** p, size_t count)
 {
     void* q = nullptr;
-    ORB_CUDA(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 256)));
+    ORB_CUDA(cudaMalloc(&q, count * sizeof(T) + 256));      // slack: kernels read whole aligned words near row ends
     h->allocs.push_back(q);
     *p = (T*)q;
     return ORBB200_OK;
@@ -1002,7 +1048,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
 {
     if (!out) { set_error("out is NULL"); return ORBB200_EINVAL; }
     *out = nullptr;
-    if (nlevels < 1 || nlevels > MAXL || nfeatures < 0 || max_batch < 1 || !(scaleFactor > 1.0f) ||
+    if (nlevels < 1 || nlevels > MAXL || nfeatures < 0 || max_batch < 1 || !(scaleFactor > 1.0f) || scaleFactor > 2.0f ||
         width < 1 || height < 1 || width > MAX_DIM || height > MAX_DIM || iniThFAST < 0 || minThFAST < 0 ||
         iniThFAST > 255 || minThFAST > 255) {
         set_error("invalid extractor parameters");
@@ -1080,6 +1126,11 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
             g.pyrOff = pyrOff; pyrOff += (long long)align_up((size_t)g.pitch * g.h, 256);
             std::vector<short4> xt, yt;
             build_resize_tables(P.lv[l - 1].w, P.lv[l - 1].h, g.w, g.h, xt, yt);
+            for (int x0 = 0; x0 < g.w + 4; x0 += 4) {      // k_resize cuts 4 columns out of one 8-byte window
+                int lo = 1 << 30, hi = 0;
+                for (int j = 0; j < 4; j++) { const short4 e = xt[std::min(x0 + j, g.w + 3)]; lo = std::min(lo, (int)e.x); hi = std::max(hi, (int)e.w); }
+                if (hi - lo > 7) { set_error("scale factor too large for the resize kernel (column span %d)", hi - lo); delete h; return ORBB200_EGEOMETRY; }
+            }
             g.xtabOff = (int)tabs.size(); tabs.insert(tabs.end(), xt.begin(), xt.end());
             g.ytabOff = (int)tabs.size(); tabs.insert(tabs.end(), yt.begin(), yt.end());
         }
@@ -1203,17 +1254,34 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
                    orbb200_keypoint* d_kp, uint8_t* d_desc, int32_t* d_counts, int cap)
 {
     ExtractParams P = h->P;
+    cudaStream_t st = h->stream;
+    // The kernels read level 0 as aligned 32-bit words.  A caller buffer qualifies when base and strides are
+    // 4-byte aligned and the width is a multiple of 4 (then no word straddles the end of a row); anything
+    // else is first copied into the handle's padded staging slab.
+    if (d_images != h->dIn) {
+        const bool canonical = ((reinterpret_cast<uintptr_t>(d_images) | stride | frame_stride | (size_t)h->width) & 3) == 0;
+        if (canonical) {
+            P.inRowBytes = h->width;
+        } else {
+            for (int f = 0; f < batch; f++)
+                ORB_CUDA(cudaMemcpy2DAsync(h->dIn + (size_t)f * h->inPitch * h->height, h->inPitch, d_images + f * frame_stride,
+                                           stride, h->width, h->height, cudaMemcpyDeviceToDevice, st));
+            d_images = h->dIn; stride = h->inPitch; frame_stride = h->inPitch * (size_t)h->height;
+            P.inRowBytes = (int)h->inPitch;
+        }
+    } else {
+        P.inRowBytes = (int)h->inPitch;
+    }
     P.batch = batch; P.in = d_images; P.inPitch = (int)stride; P.inFrameStride = (long long)frame_stride;
     P.outKp = d_kp; P.outDesc = d_desc; P.outCount = d_counts; P.outCap = cap;
-    cudaStream_t st = h->stream;
     int launches = 0;
     ORB_CUDA(cudaMemsetAsync(P.candCount, 0, sizeof(int) * P.nlevels * batch, st));
 #define STAGE_MARK(i) do { if (h->profiling) ORB_CUDA(cudaEventRecord(h->ev[i], st)); } while (0)
     STAGE_MARK(0);
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeo& g = P.lv[l];
-        dim3 grid((g.w + 4 + 127) / 128, (g.h + 7) / 8, batch), block(32, 8);
-        k_resize<<<grid, block, 0, st>>>(P, l);
+        dim3 grid((g.w + 4 + 127) / 128, (g.h + RZ_ROWS * RZ_WARPS - 1) / (RZ_ROWS * RZ_WARPS), batch);
+        k_resize<<<grid, RZ_WARPS * 32, 0, st>>>(P, l);
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
     STAGE_MARK(1);
