@@ -791,9 +791,24 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
 // K4+K6: IC_Angle (:82-109) and computeOrbDescriptor (:113-152), one warp per keypoint
 // ======================================================================================
 __constant__ int c_umax[HALF_PATCH + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-__constant__ signed char c_pattern[1024] = {
+// The 512 pattern points, transposed and packed at compile time: entry [k*32 + b] is point 16*b + k as
+// x | y << 8.  Lane b of a warp needs point 16*b + k at step k -- 32 different addresses per access, which
+// the constant cache would serialise 32-way -- so the table lives in global memory and is read through the
+// read-only path (__ldg): one coalesced 64-byte L1 line per step.
+struct PatternTable { short v[512]; };
+constexpr signed char PATTERN_SRC[1024] = {
 #include "../../include/orb_b200_pattern.inc"
 };
+constexpr PatternTable make_pattern_table()
+{
+    PatternTable t{};
+    for (int i = 0; i < 512; i++) {
+        const int byte = i >> 4, k = i & 15;
+        t.v[k * 32 + byte] = (short)((PATTERN_SRC[2 * i] & 0xff) | ((int)PATTERN_SRC[2 * i + 1] * 256));
+    }
+    return t;
+}
+__device__ const PatternTable d_pattern = make_pattern_table();
 
 // cv::fastAtan2: every step is a separately rounded fp32 operation (no FMA contraction).
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
@@ -868,13 +883,7 @@ constexpr int DESC_WARPS = 8;
 
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParams P)
 {
-    __shared__ short s_pat[16 * 32];     // [k][byte]: point 16*byte+k as x | y<<8 (bank-conflict free per k)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 512; i += DESC_WARPS * 32) {
-        const int byte = i >> 4, k = i & 15;
-        s_pat[k * 32 + byte] = (short)((c_pattern[2 * i] & 0xff) | ((int)c_pattern[2 * i + 1] << 8));
-    }
-    __syncthreads();
     const int frame = blockIdx.y;
     const int idx = blockIdx.x * DESC_WARPS + warp;        // slot in the frame's level-keypoint slab
     if (idx >= P.kpFrameCap) return;
@@ -938,7 +947,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParam
         int t[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const int pk = s_pat[(2 * k + s) * 32 + lane];
+            const int pk = __ldg(&d_pattern.v[(2 * k + s) * 32 + lane]);
             const float px = (float)(signed char)(pk & 0xff), py = (float)(pk >> 8);
             const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
