@@ -177,47 +177,43 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
 // ======================================================================================
 // K2: per-cell FAST-9/16 + NMS + threshold retry (:805-849)
 // ======================================================================================
-// The kernel is instruction-issue bound (ncu: issue slots ~80 % busy, DRAM < 2 %), so the design
-// minimises instructions per pixel rather than bytes:
-//  * the cell window (+3-px halo) is staged in shared memory EXPANDED to 16 bits per pixel, twice:
-//    copy A holds pixel pairs (2j, 2j+1) per 32-bit word, copy B pairs (2j+1, 2j+2).  Any two
-//    horizontally adjacent pixels are then ONE aligned LDS.32 away, already zero-extended;
-//  * a thread works on two adjacent centre pixels at once in the two 16-bit halves of a register:
-//    the 16 ring differences, biased by +256 so they stay positive, go through a sliding
-//    min-of-9 / max-of-9 network built from 3-input packed VIMNMX3.U16x2 (min3 of min3) --
-//    80 packed min/max for both pixels and both polarities;
-//  * pass 1 rejects pairs with two opposite ring pairs (a 9-arc of one polarity contains a pixel
-//    of every opposite pair) and queues the survivors, so the full network runs on dense warps.
-
-// FAST_TPW / FAST_TH are compile-time so that every ring load is `base + immediate`:
+// One WARP per 30-px cell.  The kernel was issue-bound and then latency-bound at low occupancy, so it
+// is built for few instructions per pixel AND a small shared-memory footprint (~7 KB per warp):
+//  * the cell window (+3-px halo) is staged in shared memory expanded to 16 bits per pixel, two pixels
+//    per 32-bit word.  A thread works on two adjacent centre pixels at once (the two 16-bit halves of
+//    a register); centre pairs sit at even tile columns, so a ring pair at an even dx is one aligned
+//    LDS.32 and one at an odd dx is cut out of two neighbouring words with a single PRMT;
+//  * pass 1 rejects pairs using the four opposite ring pairs (a 9-arc of one polarity contains a pixel
+//    of every opposite pair) and queues the survivors by ballot, so the full test runs on dense warps;
+//  * pass 2: the 16 ring differences, biased by +256 to stay positive, go through a sliding
+//    min-of-9 / max-of-9 network of 3-input packed VIMNMX3.U16x2 (min3 of min3): 80 packed min/max
+//    give the exact cv::cornerScore of both pixels for both polarities;
+//  * pass 3: 3x3 NMS on the byte score map; the iniThFAST -> minThFAST retry is a per-cell count
+//    (a corner at threshold t is exactly "score >= t", so one score map serves both thresholds).
+// FAST_TPW / FAST_TH are compile-time so every ring load is `base + immediate`:
 //   <24,42> covers cells up to 39 x 36 px (every level of the 640x480 ... 1920x1080 pyramids),
 //   <36,64> covers the largest possible cell (57 x 57).
-constexpr int FAST_WARPS = 2;     // cells per CTA; the warps of a CTA never synchronise with each other
+constexpr int FAST_WARPS = 4;     // cells per CTA; the warps of a CTA never synchronise with each other
 
 template <int TPW, int TH>
 struct FastGeo {
-    static constexpr int BOFF = TH * TPW;                 // copy B follows copy A (32-bit words)
     static constexpr int SP = TPW * 2 - 4;                // score-map pitch in bytes, >= widest cell + 2, multiple of 4
     static constexpr int QCAP = (TPW - 4) * (TH - 6);     // pixel pairs per cell, upper bound
-    static constexpr int QBYTES = 2 * QCAP + 128;         // the queue region later holds the NMS survivors (u32, <= QCAP/2 + 32)
-    static constexpr int CCAP = 2 * QCAP;                 // corner pixels per cell, upper bound
-    static constexpr int WARP_BYTES = ((2 * BOFF * 4 + (TH - 4) * SP + QBYTES + 2 * CCAP + 15) / 16) * 16;
-    // largest cell this instantiation can stage: window (cell + 6) plus up to 3 + 3 px of alignment slack
-    static constexpr bool fits(int wCell, int hCell) { return ((wCell + 12) >> 2) * 2 <= TPW && hCell + 6 <= TH; }
+    static constexpr int QBYTES = 2 * QCAP + 64;
+    static constexpr int TILE_BYTES = TH * TPW * 4 + 64;  // (+ slack: the last pair's right neighbour word)
+    static constexpr int WARP_BYTES = ((TILE_BYTES + (TH - 4) * SP + QBYTES + 15) / 16) * 16;
+    // largest cell this instantiation can stage: window (cell + 6) plus up to 4 + 3 px of alignment slack
+    static constexpr bool fits(int wCell, int hCell) { return ((wCell + 13) >> 2) * 2 <= TPW && hCell + 6 <= TH; }
+    static_assert(TH * TPW * 4 >= 4 * (QCAP / 2 + 64), "NMS survivors are written over the dead tile");
 };
+
+#define FAST_PAIR(a, b) __byte_perm(a, b, 0x5432)     // pixels (2j+1, 2j+2) out of words j and j+1
 
 template <int TPW, int TH>
 __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
 {
     using G = FastGeo<TPW, TH>;
-    constexpr int BOFF = G::BOFF, SP = G::SP;
-    // Bresenham ring of radius 3 (the order is cyclic, which is all the arc test needs)
-    constexpr int RING_DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-    constexpr int RING_DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-    // word offset of ring pair k relative to the centre pair (which sits at an even tile column):
-    // even dx -> copy A, odd dx -> copy B (pairs starting at odd columns)
-#define RING_OFF(k) (RING_DY[k] * TPW + ((RING_DX[k] & 1) ? BOFF + (RING_DX[k] - 1) / 2 : RING_DX[k] / 2))
-    static_assert((-3 - 1) / 2 == -2 && (-1 - 1) / 2 == -1, "odd negative dx map to the pair starting one column left");
+    constexpr int SP = G::SP;
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -237,11 +233,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     if (ww < 7 || wh < 7) return;                                       // cv::FAST finds nothing in < 7 px
     const int dw = ww - 6, dh = wh - 6;                                 // detection area (3-px FAST margin)
 
-    uint32_t* tw = reinterpret_cast<uint32_t*>(smem + (size_t)warp * G::WARP_BYTES);   // [2][TH][TPW]
-    uint8_t* score = reinterpret_cast<uint8_t*>(tw + 2 * BOFF);         // [(dh+2)][SP], zero ring
+    uint32_t* tw = reinterpret_cast<uint32_t*>(smem + (size_t)warp * G::WARP_BYTES);   // [TH][TPW], 2 px per word
+    uint8_t* score = reinterpret_cast<uint8_t*>(tw) + G::TILE_BYTES;    // [(dh+2)][SP], zero ring
     uint16_t* queue = reinterpret_cast<uint16_t*>(score + (TH - 4) * SP);
-    uint16_t* clist = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(queue) + G::QBYTES);
-    uint32_t* klist = reinterpret_cast<uint32_t*>(queue);               // the queue is dead by then
+    uint32_t* klist = tw;                                               // the tile is dead by then
 
     int pitch;
     const uint8_t* img = level_ptr(P, l, frame, pitch);
@@ -260,7 +255,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
         const uint8_t* q = rowp + (long long)sub * pitch + 4 * wl;
         const long long qstep = (long long)rpi * pitch;
         uint32_t* a = tw + sub * TPW + 2 * wl;
-        for (int rb = 0; rb < wh; rb += 4 * rpi) {          // warp-uniform trip count (full-mask shuffle inside)
+        for (int rb = 0; rb < wh; rb += 4 * rpi) {
             const int r0 = rb + sub;
             uint32_t v[4];
 #pragma unroll
@@ -273,14 +268,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t nx = __shfl_down_sync(FULL, v[u], 1);
-                if (colAct && r0 + u * rpi < wh) {
-                    uint32_t* aa = a + u * rpi * TPW;
-                    *reinterpret_cast<uint2*>(aa) = make_uint2(__byte_perm(v[u], 0, 0x4140), __byte_perm(v[u], 0, 0x4342));
-                    *reinterpret_cast<uint2*>(aa + BOFF) = make_uint2(__byte_perm(v[u], 0, 0x4241), __byte_perm(v[u], nx, 0x4433) & 0x00ff00ffu);
-                }
-            }
+            for (int u = 0; u < 4; u++)
+                if (colAct && r0 + u * rpi < wh)
+                    *reinterpret_cast<uint2*>(a + u * rpi * TPW) = make_uint2(__byte_perm(v[u], 0, 0x4140), __byte_perm(v[u], 0, 0x4342));
             q += 4 * qstep;
             a += 4 * rpi * TPW;
         }
@@ -298,8 +288,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     const int npair = (dw + par + 1) >> 1, total = npair * dh;
     const unsigned ltmask = (1u << lane) - 1;
 
-    // pass 1: cheap reject on the four opposite ring pairs (0,8) (4,12) (2,10) (6,14): a 9-arc of one
-    // polarity contains a pixel of every opposite pair.  Both centre pixels at once; survivors queued.
+    // pass 1: cheap reject on the ring pairs (0,8) (4,12) (2,10) (6,14), both centre pixels at once
     int nq = 0;
     {
         int r = lane / npair, i = lane - r * npair;
@@ -309,8 +298,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
             if (idx < total) {
                 const uint32_t* b = tbase + r * TPW + i;
                 const uint32_t V = b[0];
-                const uint32_t R0 = b[RING_OFF(0)], R8 = b[RING_OFF(8)], R4 = b[RING_OFF(4)], R12 = b[RING_OFF(12)];
-                const uint32_t R2 = b[RING_OFF(2)], R10 = b[RING_OFF(10)], R6 = b[RING_OFF(6)], R14 = b[RING_OFF(14)];
+                const uint32_t R0 = b[3 * TPW], R8 = b[-3 * TPW];
+                const uint32_t R4 = FAST_PAIR(b[1], b[2]), R12 = FAST_PAIR(b[-2], b[-1]);
+                const uint32_t R2 = b[2 * TPW + 1], R14 = b[2 * TPW - 1], R6 = b[-2 * TPW + 1], R10 = b[-2 * TPW - 1];
                 const uint32_t mb = __vminu2(__vminu2(__vmaxu2(R0, R8), __vmaxu2(R4, R12)), __vminu2(__vmaxu2(R2, R10), __vmaxu2(R6, R14)));
                 const uint32_t md = __vmaxu2(__vmaxu2(__vminu2(R0, R8), __vminu2(R4, R12)), __vmaxu2(__vminu2(R2, R10), __vminu2(R6, R14)));
                 const uint32_t hiV = V + T2;
@@ -325,22 +315,30 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     }
     __syncwarp();
     // pass 2: exact corner score = max over the 16 arcs of 9 of min|centre - ring|, minus 1
-    // (cv::cornerScore<16>), for both pixels and both polarities with packed 16-bit min/max.
-    // Corner pixels are compacted into clist for the NMS pass.
-    int ncorner = 0;
+    // (cv::cornerScore<16>).  Pairs with a corner are compacted in place (write index <= read index)
+    // with two flag bits saying which half is a corner.
+    int ncp = 0;
     for (int q0 = 0; q0 < nq; q0 += 32) {
         const int q = q0 + lane;
         bool c0 = false, c1 = false;
-        int r = 0, x0 = 0;
+        int e = 0;
         if (q < nq) {
-            const int e = queue[q];
-            r = e >> 5;
-            const int i = e & 31;
+            e = queue[q];
+            const int r = e >> 5, i = e & 31;
             const uint32_t* b = tbase + r * TPW + i;
             const uint32_t Cm = 0x01000100u - b[0];                  // 256 - v per half: ring + Cm = 256 + (ring - v)
             uint32_t D[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) D[k] = b[RING_OFF(k)] + Cm;
+            {
+                const uint32_t a0 = b[3 * TPW - 1], a1 = b[3 * TPW], a2 = b[3 * TPW + 1];
+                D[15] = FAST_PAIR(a0, a1) + Cm; D[0] = a1 + Cm; D[1] = FAST_PAIR(a1, a2) + Cm;
+                const uint32_t z0 = b[-3 * TPW - 1], z1 = b[-3 * TPW], z2 = b[-3 * TPW + 1];
+                D[9] = FAST_PAIR(z0, z1) + Cm; D[8] = z1 + Cm; D[7] = FAST_PAIR(z1, z2) + Cm;
+                D[14] = b[2 * TPW - 1] + Cm; D[2] = b[2 * TPW + 1] + Cm;
+                D[10] = b[-2 * TPW - 1] + Cm; D[6] = b[-2 * TPW + 1] + Cm;
+                D[13] = FAST_PAIR(b[TPW - 2], b[TPW - 1]) + Cm; D[3] = FAST_PAIR(b[TPW + 1], b[TPW + 2]) + Cm;
+                D[12] = FAST_PAIR(b[-2], b[-1]) + Cm; D[4] = FAST_PAIR(b[1], b[2]) + Cm;
+                D[11] = FAST_PAIR(b[-TPW - 2], b[-TPW - 1]) + Cm; D[5] = FAST_PAIR(b[-TPW + 1], b[-TPW + 2]) + Cm;
+            }
             uint32_t lo3[16], hi3[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
@@ -364,42 +362,45 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
             // bright = 256 + max-arc-min(ring - v); dark = 256 + min-arc-max(ring - v); m = max(bright-256, 256-dark)
             const uint32_t m2 = __vmaxu2(bright, 0x02000200u - dark);    // 256 + m per half
             const int m0 = (int)(m2 & 0xffffu) - 256, m1 = (int)(m2 >> 16) - 256;
-            x0 = 2 * i - par;
+            const int x0 = 2 * i - par;
             uint8_t* sp = score + (r + 1) * SP + x0 + 1;
             c0 = (m0 > tlow) && (x0 >= 0);
             c1 = (m1 > tlow) && (x0 + 1 < dw);
             if (c0) sp[0] = (uint8_t)(m0 - 1);
             if (c1) sp[1] = (uint8_t)(m1 - 1);
         }
-        const unsigned b0 = __ballot_sync(FULL, c0), b1 = __ballot_sync(FULL, c1);
-        if (c0) clist[ncorner + __popc(b0 & ltmask)] = (uint16_t)(r * 64 + x0);
-        ncorner += __popc(b0);
-        if (c1) clist[ncorner + __popc(b1 & ltmask)] = (uint16_t)(r * 64 + x0 + 1);
-        ncorner += __popc(b1);
+        const unsigned bal = __ballot_sync(FULL, c0 || c1);
+        if (c0 || c1) queue[ncp + __popc(bal & ltmask)] = (uint16_t)(e | (c0 ? 0x4000 : 0) | (c1 ? 0x8000 : 0));
+        ncp += __popc(bal);
     }
     __syncwarp();
-    // pass 3: 3x3 non-max suppression (strictly greater than all 8 neighbours, non-corners count 0)
+    // pass 3: 3x3 non-max suppression (strictly greater than all 8 neighbours, non-corners count 0);
+    // survivors go to klist, which re-uses the tile
     int nk = 0, nini = 0;
-    for (int q0 = 0; q0 < ncorner; q0 += 32) {
+    for (int q0 = 0; q0 < ncp; q0 += 32) {
         const int q = q0 + lane;
-        bool keep = false;
-        int s = 0, r = 0, x = 0;
-        if (q < ncorner) {
-            const int e = clist[q];
-            r = e >> 6; x = e & 63;
-            const uint8_t* sp = score + (r + 1) * SP + x + 1;
-            s = sp[0];
-            const int nb = max(max(max((int)sp[-1], (int)sp[1]), max((int)sp[-SP - 1], (int)sp[-SP])),
-                               max(max((int)sp[-SP + 1], (int)sp[SP - 1]), max((int)sp[SP], (int)sp[SP + 1])));
-            keep = s > nb;
+        const int e = q < ncp ? queue[q] : 0;
+        const int r = (e >> 5) & 0x1ff, x0 = 2 * (e & 31) - par;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            bool keep = false;
+            int s = 0;
+            const int x = x0 + j;
+            if (e & (0x4000 << j)) {
+                const uint8_t* sp = score + (r + 1) * SP + x + 1;
+                s = sp[0];
+                const int nb = max(max(max((int)sp[-1], (int)sp[1]), max((int)sp[-SP - 1], (int)sp[-SP])),
+                                   max(max((int)sp[-SP + 1], (int)sp[SP - 1]), max((int)sp[SP], (int)sp[SP + 1])));
+                keep = s > nb;
+            }
+            const unsigned bal = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int xr = x + 3 + cj * g.wCell, yr = r + 3 + ci * g.hCell;   // relative to the border (:840-841)
+                klist[nk + __popc(bal & ltmask)] = (uint32_t)xr | ((uint32_t)yr << 12) | ((uint32_t)s << 24);
+            }
+            nk += __popc(bal);
+            nini += __popc(__ballot_sync(FULL, keep && s >= P.iniTh));
         }
-        const unsigned bal = __ballot_sync(FULL, keep);
-        if (keep) {
-            const int xr = x + 3 + cj * g.wCell, yr = r + 3 + ci * g.hCell;   // relative to the border (:840-841)
-            klist[nk + __popc(bal & ltmask)] = (uint32_t)xr | ((uint32_t)yr << 12) | ((uint32_t)s << 24);
-        }
-        nk += __popc(bal);
-        nini += __popc(__ballot_sync(FULL, keep && s >= P.iniTh));
     }
     __syncwarp();
     // threshold retry (:829-833): keypoints at iniThFAST if the cell has any, else those at minThFAST
@@ -424,8 +425,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
         }
         base += __popc(bal);
     }
-#undef RING_OFF
 }
+#undef FAST_PAIR
 
 // ======================================================================================
 // K3: DistributeOctTree (:552-776) as parallel rounds
