@@ -999,6 +999,8 @@ struct orbb200_extractor {
     orbb200_keypoint* dOutKp; uint8_t* dOutDesc; int* dOutCount;
     void* pinned; size_t pinnedBytes;
     bool profiling; cudaEvent_t ev[6];   // stage boundaries of the last call: resize | fast | quadtree | blur | describe
+    cudaStream_t copyIn, copyOut;        // host path: H2D and D2H run beside the kernels, chunk by chunk
+    cudaEvent_t evIn[8], evDone[8];
     std::vector<void*> allocs;
 };
 
@@ -1074,6 +1076,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     h->pinned = nullptr; h->pinnedBytes = 0; h->lastLaunches = 0; h->lastBatch = 0; h->lastIn = nullptr;
     h->profiling = false;
     for (int i = 0; i < 6; i++) h->ev[i] = nullptr;
+    h->copyIn = h->copyOut = nullptr;
+    for (int i = 0; i < 8; i++) h->evIn[i] = h->evDone[i] = nullptr;
     // ---- constructor tables (S/ORBextractor.cc:421-455); scaleFactor is held in a double (I/ORBextractor.h:98)
     h->scaleFactorD = (double)scaleFactor;
     h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
@@ -1190,6 +1194,12 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     if (!tabs.empty()) e = cudaMemcpy(dTabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(P.status, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copyIn, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copyOut, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = P.fastLarge
         ? cudaFuncSetAttribute(k_fast<36, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem)
         : cudaFuncSetAttribute(k_fast<24, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
@@ -1209,6 +1219,9 @@ extern "C" void orbb200_extractor_destroy(orbb200_extractor* h)
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 8; i++) { if (h->evIn[i]) cudaEventDestroy(h->evIn[i]); if (h->evDone[i]) cudaEventDestroy(h->evDone[i]); }
+    if (h->copyIn) cudaStreamDestroy(h->copyIn);
+    if (h->copyOut) cudaStreamDestroy(h->copyOut);
     for (void* p : h->allocs) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h;
@@ -1260,23 +1273,30 @@ extern "C" int orbb200_extractor_stage_ms(orbb200_extractor* h, float* ms5)
 }
 
 // enqueue the whole pipeline for `batch` frames whose level 0 is at d_images
+// `first` = index of the scratch slabs (pyramid, candidates, ...) the batch's frame 0 uses, so that several
+// chunks of one host call can be in flight in disjoint parts of the handle's buffers.
 static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, size_t stride, size_t frame_stride,
-                   orbb200_keypoint* d_kp, uint8_t* d_desc, int32_t* d_counts, int cap)
+                   orbb200_keypoint* d_kp, uint8_t* d_desc, int32_t* d_counts, int cap, int first = 0)
 {
     ExtractParams P = h->P;
     cudaStream_t st = h->stream;
+    P.pyr += (size_t)first * P.pyrFrameBytes; P.blur += (size_t)first * P.blurFrameBytes;
+    P.cand += (size_t)first * P.candFrameCap; P.qtScratch += (size_t)first * P.candFrameCap;
+    P.candCount += (size_t)first * P.nlevels; P.lkp += (size_t)first * P.kpFrameCap; P.lkpCount += (size_t)first * P.nlevels;
+    const size_t inFrameBytes = h->inPitch * (size_t)h->height;
+    const bool staged = d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch;
     // The kernels read level 0 as aligned 32-bit words.  A caller buffer qualifies when base and strides are
     // 4-byte aligned and the width is a multiple of 4 (then no word straddles the end of a row); anything
     // else is first copied into the handle's padded staging slab.
-    if (d_images != h->dIn) {
+    if (!staged) {
         const bool canonical = ((reinterpret_cast<uintptr_t>(d_images) | stride | frame_stride | (size_t)h->width) & 3) == 0;
         if (canonical) {
             P.inRowBytes = h->width;
         } else {
             for (int f = 0; f < batch; f++)
-                ORB_CUDA(cudaMemcpy2DAsync(h->dIn + (size_t)f * h->inPitch * h->height, h->inPitch, d_images + f * frame_stride,
+                ORB_CUDA(cudaMemcpy2DAsync(h->dIn + (size_t)(first + f) * inFrameBytes, h->inPitch, d_images + f * frame_stride,
                                            stride, h->width, h->height, cudaMemcpyDeviceToDevice, st));
-            d_images = h->dIn; stride = h->inPitch; frame_stride = h->inPitch * (size_t)h->height;
+            d_images = h->dIn + (size_t)first * inFrameBytes; stride = h->inPitch; frame_stride = inFrameBytes;
             P.inRowBytes = (int)h->inPitch;
         }
     } else {
@@ -1371,24 +1391,41 @@ extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images,
     if (stride < (size_t)h->width) { set_error("stride smaller than the frame width"); return ORBB200_EINVAL; }
     if (cap < h->maxKp) { set_error("cap %d < orbb200_extractor_max_keypoints() = %d", cap, h->maxKp); return ORBB200_ECAPACITY; }
     ORB_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    if (frame_stride == stride * (size_t)h->height) {
-        ORB_CUDA(cudaMemcpy2DAsync(h->dIn, h->inPitch, images, stride, h->width, (size_t)h->height * batch,
-                                   cudaMemcpyHostToDevice, st));
-    } else {
-        for (int f = 0; f < batch; f++)
-            ORB_CUDA(cudaMemcpy2DAsync(h->dIn + (size_t)f * h->inPitch * h->height, h->inPitch, images + f * frame_stride,
-                                       stride, h->width, h->height, cudaMemcpyHostToDevice, st));
-    }
-    int rc = enqueue(h, h->dIn, batch, h->inPitch, h->inPitch * (size_t)h->height, h->dOutKp, h->dOutDesc, h->dOutCount, h->maxKp);
-    if (rc != ORBB200_OK) return rc;
-    // results: one contiguous D2H per array when the caller's cap equals ours, else per-frame rows
+    // Chunked pipeline: while chunk c is in the kernels, chunk c+1 is on its way up and chunk c-1 on its way
+    // down (three streams, events between them).  Small batches go through in one piece.
+    const int nchunk = batch >= 64 ? 4 : (batch >= 16 ? 2 : 1);
+    const int cs = (batch + nchunk - 1) / nchunk;
     const int mk = h->maxKp;
-    ORB_CUDA(cudaMemcpyAsync(counts, h->dOutCount, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpy2DAsync(keypoints, (size_t)cap * sizeof(orbb200_keypoint), h->dOutKp, (size_t)mk * sizeof(orbb200_keypoint),
-                               (size_t)mk * sizeof(orbb200_keypoint), batch, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpy2DAsync(descriptors, (size_t)cap * 32, h->dOutDesc, (size_t)mk * 32, (size_t)mk * 32, batch,
-                               cudaMemcpyDeviceToHost, st));
+    const size_t inFrameBytes = h->inPitch * (size_t)h->height;
+    for (int c = 0; c < nchunk; c++) {
+        const int f0 = c * cs, n = std::min(cs, batch - f0);
+        if (n <= 0) break;
+        const uint8_t* src = images + (size_t)f0 * frame_stride;
+        uint8_t* dIn = h->dIn + (size_t)f0 * inFrameBytes;
+        if (frame_stride == stride * (size_t)h->height) {
+            ORB_CUDA(cudaMemcpy2DAsync(dIn, h->inPitch, src, stride, h->width, (size_t)h->height * n, cudaMemcpyHostToDevice, h->copyIn));
+        } else {
+            for (int f = 0; f < n; f++)
+                ORB_CUDA(cudaMemcpy2DAsync(dIn + (size_t)f * inFrameBytes, h->inPitch, src + f * frame_stride, stride, h->width,
+                                           h->height, cudaMemcpyHostToDevice, h->copyIn));
+        }
+        ORB_CUDA(cudaEventRecord(h->evIn[c], h->copyIn));
+        ORB_CUDA(cudaStreamWaitEvent(h->stream, h->evIn[c], 0));
+        int rc = enqueue(h, dIn, n, h->inPitch, inFrameBytes, h->dOutKp + (size_t)f0 * mk, h->dOutDesc + (size_t)f0 * mk * 32,
+                         h->dOutCount + f0, mk, f0);
+        if (rc != ORBB200_OK) return rc;
+        ORB_CUDA(cudaEventRecord(h->evDone[c], h->stream));
+        ORB_CUDA(cudaStreamWaitEvent(h->copyOut, h->evDone[c], 0));
+        ORB_CUDA(cudaMemcpyAsync(counts + f0, h->dOutCount + f0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->copyOut));
+        ORB_CUDA(cudaMemcpy2DAsync(keypoints + (size_t)f0 * cap, (size_t)cap * sizeof(orbb200_keypoint), h->dOutKp + (size_t)f0 * mk,
+                                   (size_t)mk * sizeof(orbb200_keypoint), (size_t)mk * sizeof(orbb200_keypoint), n,
+                                   cudaMemcpyDeviceToHost, h->copyOut));
+        ORB_CUDA(cudaMemcpy2DAsync(descriptors + (size_t)f0 * cap * 32, (size_t)cap * 32, h->dOutDesc + (size_t)f0 * mk * 32, (size_t)mk * 32,
+                                   (size_t)mk * 32, n, cudaMemcpyDeviceToHost, h->copyOut));
+    }
+    h->lastBatch = batch; h->lastIn = h->dIn; h->lastInPitch = (int)h->inPitch; h->lastInFrameStride = (long long)inFrameBytes;
+    h->lastLaunches *= nchunk;
+    ORB_CUDA(cudaStreamSynchronize(h->copyOut));
     return check_status(h);
 }
 
