@@ -345,7 +345,7 @@ def run_matching(local, steps):
     m12 = torch.empty((items, n), dtype=torch.int32, device=dev)
     nm = torch.empty(items, dtype=torch.int32, device=dev)
     h = _lib.vp()
-    check(L.orbb200_matcher_create(items, 10000, local, C.byref(h)))
+    check(L.orbb200_matcher_create(items, n, local, C.byref(h)))
     bounds = np.array([0, 0, 640, 480], np.float32)
     def init_step():
         prev.copy_(prev0)
@@ -358,9 +358,12 @@ def run_matching(local, steps):
         "ms_per_step": ms, "pairs_per_s": items / ms * 1e3, "distance_evals_per_s": items * n * n / ms * 1e3,
         "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
     del t1, t2, prev, prev0, m12
+    L.orbb200_matcher_destroy(h)
 
     # ---- configs[4]
     items, nk, nmp, distinct = 512, 2000, 10000, 16
+    h = _lib.vp()
+    check(L.orbb200_matcher_create(items, nmp, local, C.byref(h)))
     fr = [projection_frame(i, nk, nmp) for i in range(distinct)]
     tk = dict(n=up(np.full(items, nk, np.int32)), x=up(tile(np.stack([f[0]["x"] for f in fr]), items)),
               y=up(tile(np.stack([f[0]["y"] for f in fr]), items)), o=up(tile(np.stack([f[0]["octave"] for f in fr]), items)),

@@ -193,35 +193,32 @@ static const int RING_DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1,
  * time), minus 1.  Returns 0 if the pixel is not a corner at `threshold`. */
 static int fast_score(const uint8_t *p, const int *off, int threshold)
 {
-    int v = p[0];
-    int d[16];
-    unsigned bright = 0, dark = 0;
+    const int v = p[0];
+    int d[16], lo2[16], hi2[16], lo4[16], hi4[16];
+    for (int k = 0; k < 16; k++) d[k] = (int)p[off[k]] - v;
+    /* sliding minimum / maximum over the windows of 9 of the circular ring, by doubling: 2, 4, 8, +1 */
     for (int k = 0; k < 16; k++) {
-        d[k] = (int)p[off[k]] - v;
-        if (d[k] > threshold) bright |= 1u << k;
-        if (d[k] < -threshold) dark |= 1u << k;
+        const int e = d[(k + 1) & 15];
+        lo2[k] = d[k] < e ? d[k] : e;
+        hi2[k] = d[k] > e ? d[k] : e;
     }
-    int best = 0;
-    for (int pol = 0; pol < 2; pol++) {
-        unsigned m = pol ? dark : bright;
-        unsigned mm = m | (m << 16);
-        /* any run of 9 set bits? */
-        unsigned a = mm & (mm >> 1);
-        a &= a >> 2;
-        a &= a >> 4;
-        a &= mm >> 8;
-        if (!(a & 0xffffu)) continue;
-        for (int s = 0; s < 16; s++) {
-            int mn = 1 << 30;
-            for (int j = 0; j < 9; j++) {
-                int q = d[(s + j) & 15];
-                if (pol) q = -q;
-                if (q < mn) mn = q;
-            }
-            if (mn > best) best = mn;
-        }
+    for (int k = 0; k < 16; k++) {
+        const int a = lo2[(k + 2) & 15], b = hi2[(k + 2) & 15];
+        lo4[k] = lo2[k] < a ? lo2[k] : a;
+        hi4[k] = hi2[k] > b ? hi2[k] : b;
     }
-    return best > 0 ? best - 1 : 0;   /* best > threshold >= 0 whenever a run exists */
+    int bright = -256, dark = 256;      /* max over arcs of min(d);  min over arcs of max(d) */
+    for (int k = 0; k < 16; k++) {
+        int lo = lo4[k] < lo4[(k + 4) & 15] ? lo4[k] : lo4[(k + 4) & 15];
+        int hi = hi4[k] > hi4[(k + 4) & 15] ? hi4[k] : hi4[(k + 4) & 15];
+        const int e = d[(k + 8) & 15];
+        if (e < lo) lo = e;
+        if (e > hi) hi = e;
+        if (lo > bright) bright = lo;
+        if (hi < dark) dark = hi;
+    }
+    const int m = bright > -dark ? bright : -dark;
+    return m > threshold ? m - 1 : 0;
 }
 
 int orc_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, int nms,
@@ -233,26 +230,38 @@ int orc_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, in
     if (threshold > 255) threshold = 255;
     int off[16];
     for (int k = 0; k < 16; k++) off[k] = RING_DY[k] * stride + RING_DX[k];
-    /* score map over the whole window; 0 = not a corner (also outside the 3-px margin) */
-    uint8_t *score = (uint8_t *)calloc((size_t)w * h, 1);
-    uint8_t *is_corner = (uint8_t *)calloc((size_t)w * h, 1);
-    for (int y = 3; y < h - 3; y++)
+    /* classification table: 1 = darker than centre - t, 2 = brighter than centre + t */
+    uint8_t tab[512];
+    for (int i = -255; i <= 255; i++) tab[i + 255] = (uint8_t)(i < -threshold ? 1 : (i > threshold ? 2 : 0));
+    /* score map over the whole window; 0 = not a corner (also outside the 3-px margin).
+     * Cell-sized windows (the extractor's case) use a stack buffer. */
+    uint8_t stackbuf[72 * 72 * 2];
+    const size_t npx = (size_t)w * h;
+    uint8_t *score = npx * 2 <= sizeof(stackbuf) ? stackbuf : (uint8_t *)malloc(npx * 2);
+    uint8_t *is_corner = score + npx;
+    memset(score, 0, npx * 2);
+    for (int y = 3; y < h - 3; y++) {
+        const uint8_t *row = img + (size_t)y * stride;
         for (int x = 3; x < w - 3; x++) {
-            const uint8_t *p = img + (size_t)y * stride + x;
-            /* cheap reject: a 9-arc always contains two adjacent compass points */
-            int v = p[0], nb = 0, nd = 0;
-            for (int k = 0; k < 16; k += 4) {
-                int q = (int)p[off[k]] - v;
-                nb += q > threshold;
-                nd += q < -threshold;
-            }
-            if (nb < 2 && nd < 2) continue;
-            /* corner test proper */
+            const uint8_t *p = row + x;
+            const uint8_t *tb = tab + 255 - p[0];
+            /* a 9-arc of one polarity contains a pixel of every opposite pair: AND the pair classes */
+            int d = tb[p[off[0]]] | tb[p[off[8]]];
+            if (!d) continue;
+            d &= tb[p[off[4]]] | tb[p[off[12]]];
+            d &= tb[p[off[2]]] | tb[p[off[10]]];
+            d &= tb[p[off[6]]] | tb[p[off[14]]];
+            if (!d) continue;
+            d &= tb[p[off[1]]] | tb[p[off[9]]];
+            d &= tb[p[off[3]]] | tb[p[off[11]]];
+            d &= tb[p[off[5]]] | tb[p[off[13]]];
+            d &= tb[p[off[7]]] | tb[p[off[15]]];
+            if (!d) continue;
             unsigned bright = 0, dark = 0;
             for (int k = 0; k < 16; k++) {
-                int q = (int)p[off[k]] - v;
-                if (q > threshold) bright |= 1u << k;
-                if (q < -threshold) dark |= 1u << k;
+                const int cls = tb[p[off[k]]];
+                bright |= (unsigned)(cls >> 1) << k;
+                dark |= (unsigned)(cls & 1) << k;
             }
             int corner = 0;
             for (int pol = 0; pol < 2 && !corner; pol++) {
@@ -265,8 +274,9 @@ int orc_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, in
             }
             if (!corner) continue;
             is_corner[(size_t)y * w + x] = 1;
-            score[(size_t)y * w + x] = (uint8_t)fast_score(p, off, threshold);
+            score[(size_t)y * w + x] = nms ? (uint8_t)fast_score(p, off, threshold) : 0;
         }
+    }
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x < w - 3; x++) {
             size_t i = (size_t)y * w + x;
@@ -285,8 +295,7 @@ int orc_fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, in
             }
             n++;
         }
-    free(score);
-    free(is_corner);
+    if (score != stackbuf) free(score);
     return n;
 }
 
@@ -298,26 +307,33 @@ void orc_gaussian_blur7(const uint8_t *src, int w, int h, int sstride,
 {
     static const int TAPS[2][7] = {{18, 34, 48, 56, 48, 34, 18}, {18, 34, 49, 55, 49, 34, 18}};
     const int *k = TAPS[variant ? 1 : 0];
-    uint32_t *tmp = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)w * h);
+    /* horizontal pass into 8.8 fixed point; each row is first copied into a buffer padded with its
+     * REFLECT_101 continuation so the inner loop needs no border logic */
+    uint16_t *tmp = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)w * h);
+    uint8_t *pad = (uint8_t *)malloc((size_t)w + 6);
     for (int y = 0; y < h; y++) {
         const uint8_t *s = src + (size_t)y * sstride;
+        for (int i = 0; i < 3; i++) { pad[i] = s[reflect101(i - 3, w)]; pad[w + 3 + i] = s[reflect101(w + i, w)]; }
+        memcpy(pad + 3, s, w);
+        uint16_t *t = tmp + (size_t)y * w;
         for (int x = 0; x < w; x++) {
-            uint32_t acc = 0;
-            for (int i = -3; i <= 3; i++) acc += (uint32_t)k[i + 3] * s[reflect101(x + i, w)];
-            tmp[(size_t)y * w + x] = acc;           /* 8.8 fixed point */
+            const uint8_t *q = pad + x;
+            t[x] = (uint16_t)(k[0] * (q[0] + q[6]) + k[1] * (q[1] + q[5]) + k[2] * (q[2] + q[4]) + k[3] * q[3]);
         }
     }
-    uint8_t *outbuf = (uint8_t *)malloc((size_t)w * h);
-    for (int y = 0; y < h; y++)
+    /* vertical pass; rows are picked through the same reflection; dst may alias src (tmp holds the input) */
+    for (int y = 0; y < h; y++) {
+        const uint16_t *r[7];
+        for (int j = 0; j < 7; j++) r[j] = tmp + (size_t)reflect101(y + j - 3, h) * w;
+        uint8_t *d = dst + (size_t)y * dstride;
         for (int x = 0; x < w; x++) {
-            uint32_t acc = 0;
-            for (int j = -3; j <= 3; j++)
-                acc += (uint32_t)k[j + 3] * tmp[(size_t)reflect101(y + j, h) * w + x];
+            uint32_t acc = (uint32_t)k[0] * (r[0][x] + r[6][x]) + (uint32_t)k[1] * (r[1][x] + r[5][x]) +
+                           (uint32_t)k[2] * (r[2][x] + r[4][x]) + (uint32_t)k[3] * r[3][x];
             uint32_t v = (acc + 32768u) >> 16;      /* 16.16 -> u8, round half up, saturate */
-            outbuf[(size_t)y * w + x] = (uint8_t)(v > 255 ? 255 : v);
+            d[x] = (uint8_t)(v > 255 ? 255 : v);
         }
-    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * dstride, outbuf + (size_t)y * w, w);
-    free(outbuf);
+    }
+    free(pad);
     free(tmp);
 }
 

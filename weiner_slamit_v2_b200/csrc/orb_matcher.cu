@@ -168,10 +168,96 @@ struct InitParams {
     float* prevMatched;       // items x f1.stride x 2, in/out
     int* matches12;           // items x f1.stride
     int* nmatches;            // items
+    uint4* topk;              // items x f1.stride: the 4 best candidates of every query, key = dist << 20 | CSR position
+    int* topkCount;           // items x f1.stride: number of candidates that passed the static tests
     int items, window, checkOri;
     float nnratio;
 };
 
+// Sorted insertion of a key into a 4-entry ascending list (keys are unique: they embed the position).
+__device__ __forceinline__ void top4_insert(uint4& t, uint32_t k)
+{
+    uint32_t m;
+    m = min(t.x, k); k = max(t.x, k); t.x = m;
+    m = min(t.y, k); k = max(t.y, k); t.y = m;
+    m = min(t.z, k); k = max(t.z, k); t.z = m;
+    t.w = min(t.w, k);
+}
+
+// ---- SearchForInitialization, phase A: everything that does not depend on the greedy state ----
+// One THREAD per F1 keypoint (query); the F2 keypoints are streamed through shared memory in CSR order
+// (= GetFeaturesInArea visiting order) and every lane tests the same candidate at the same time, so the
+// candidate's descriptor is one broadcast load.  A candidate that passes the static tests of
+// GetFeaturesInArea (cell range, level, window) costs 8 XOR + 8 POPC; the 4 smallest keys
+// (distance, visiting position) and the candidate count are kept per query.
+constexpr int TOPK_CHUNK = 1024;
+struct CandMeta { float x, y; int meta; };     // meta = octave | cx << 16 | cy << 24
+
+__global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
+{
+    __shared__ __align__(16) uint4 s_desc[TOPK_CHUNK * 2];
+    __shared__ CandMeta s_meta[TOPK_CHUNK];
+    const int item = blockIdx.y, tid = threadIdx.x;
+    const int n1 = min(P.f1.n[item], P.f1.stride), n2 = min(P.f2.n[item], P.f2.stride);
+    if ((int)blockIdx.x * 128 >= n1) return;
+    const int q = blockIdx.x * 128 + tid;
+    const float* k2x = P.f2.x + (size_t)item * P.f2.stride;
+    const float* k2y = P.f2.y + (size_t)item * P.f2.stride;
+    const int* oct2 = P.f2.octave + (size_t)item * P.f2.stride;
+    const uint4* d2 = reinterpret_cast<const uint4*>(P.f2.desc + (size_t)item * P.f2.stride * 32);
+    const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+    const int* ci = P.cellItems + (size_t)item * P.f2.stride;
+    const int ngrid = cs[GRID_CELLS];                          // keypoints that are in the grid at all
+
+    bool active = q < n1;
+    int level1 = 0, c0 = 0, c1 = -1, r0 = 0, r1 = -1;
+    float qx = 0.f, qy = 0.f;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    const float r = (float)P.window;
+    if (active) {
+        level1 = P.f1.octave[(size_t)item * P.f1.stride + q];
+        const float* prev = P.prevMatched + ((size_t)item * P.f1.stride + q) * 2;
+        qx = prev[0]; qy = prev[1];
+        active = level1 <= 0 && cell_range(P.g, qx, qy, r, c0, c1, r0, r1);
+        const uint4* d1 = reinterpret_cast<const uint4*>(P.f1.desc + ((size_t)item * P.f1.stride + q) * 32);
+        a0 = __ldg(d1); a1 = __ldg(d1 + 1);
+    }
+    uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    int count = 0;
+    for (int base = 0; base < ngrid; base += TOPK_CHUNK) {
+        const int nc = min(TOPK_CHUNK, ngrid - base);
+        __syncthreads();
+        for (int c = tid; c < nc; c += 128) {
+            const int i2 = ci[base + c];
+            const float x = k2x[i2], y = k2y[i2];
+            const int cx = (int)roundf(__fmul_rn(__fsub_rn(x, P.g.minX), P.g.invW));
+            const int cy = (int)roundf(__fmul_rn(__fsub_rn(y, P.g.minY), P.g.invH));
+            s_meta[c].x = x; s_meta[c].y = y;
+            s_meta[c].meta = (oct2[i2] & 0xffff) | (cx << 16) | (cy << 24);
+            s_desc[2 * c] = __ldg(d2 + 2 * i2);
+            s_desc[2 * c + 1] = __ldg(d2 + 2 * i2 + 1);
+        }
+        __syncthreads();
+        if (active) {
+            for (int c = 0; c < nc; c++) {
+                const CandMeta m = s_meta[c];
+                const int o2 = (short)(m.meta & 0xffff), cx = (m.meta >> 16) & 0xff, cy = (m.meta >> 24) & 0xff;
+                if (cx < c0 || cx > c1 || cy < r0 || cy > r1) continue;
+                if (o2 < level1 || (level1 >= 0 && o2 > level1)) continue;             // Frame.cc:468-485
+                if (!(fabsf(__fsub_rn(m.x, qx)) < r && fabsf(__fsub_rn(m.y, qy)) < r)) continue;
+                const int dist = hamming256(a0, a1, s_desc[2 * c], s_desc[2 * c + 1]);
+                top4_insert(best, ((uint32_t)dist << 20) | (uint32_t)(base + c));
+                count++;
+            }
+        }
+    }
+    if (q < n1) {
+        P.topk[(size_t)item * P.f1.stride + q] = best;
+        P.topkCount[(size_t)item * P.f1.stride + q] = active ? count : -1;
+    }
+}
+
+// ---- SearchForInitialization, phase B: the greedy pass, one warp per frame pair ----------------
 __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
 {
     const int lane = threadIdx.x & 31;
@@ -199,31 +285,64 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
     __syncwarp();
 
     const float r = (float)P.window;
+    const uint4* topk = P.topk + (size_t)item * P.f1.stride;
+    const int* topkCount = P.topkCount + (size_t)item * P.f1.stride;
     for (int i1 = 0; i1 < n1; i1++) {
+        const int cnt = topkCount[i1];
+        if (cnt <= 0) continue;            // octave > 0 (:425-427), query outside the grid, or no candidate (:431)
         const int level1 = oct1[i1];
-        if (level1 > 0) continue;                                               // :425-427
-        int c0, c1, r0, r1;
-        if (!cell_range(P.g, prev[2 * i1], prev[2 * i1 + 1], r, c0, c1, r0, r1)) continue;
-        const float qx = prev[2 * i1], qy = prev[2 * i1 + 1];
-        const uint4 a0 = __ldg(d1 + 2 * i1), a1 = __ldg(d1 + 2 * i1 + 1);
         Top2 t = {INT_MAX, INT_MAX, -1, INT_MAX, INT_MAX, -1};
-        const bool fullRows = (r0 == 0 && r1 == GRID_ROWS - 1);
-        const int ncol = fullRows ? 1 : (c1 - c0 + 1);
-        for (int c = 0; c < ncol; c++) {
-            const int s = fullRows ? cs[c0 * GRID_ROWS] : cs[(c0 + c) * GRID_ROWS + r0];
-            const int e = fullRows ? cs[(c1 + 1) * GRID_ROWS] : cs[(c0 + c) * GRID_ROWS + r1 + 1];
-            for (int p = s + lane; p < e; p += 32) {
-                const int i2 = ci[p];
-                // level filter: minLevel = maxLevel = level1 (:429, Frame.cc:468-485)
-                const int o2 = oct2[i2];
-                if (o2 < level1 || (level1 >= 0 && o2 > level1)) continue;
-                if (!(fabsf(__fsub_rn(k2x[i2], qx)) < r && fabsf(__fsub_rn(k2y[i2], qy)) < r)) continue;
-                const int dist = hamming256(a0, a1, __ldg(d2 + 2 * i2), __ldg(d2 + 2 * i2 + 1));
-                if (vmd[i2] <= dist) continue;                                     // :448
-                top2_push(t, dist, p, 0);
+        // Fast path (every lane redundantly): walk the query's 4 best static candidates in visiting order and
+        // drop those a previous query already holds at a distance <= ours (:448).  The first two survivors are
+        // best / second-best.  That is conclusive when two survive, when the list holds every candidate, or
+        // when the best survivor already fails TH_LOW; otherwise fall back to the full scan below.
+        bool resolved;
+        {
+            const uint4 kk = topk[i1];
+            const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+            int found = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (found < 2 && j < cnt) {
+                    const int dist = (int)(key[j] >> 20), pos = (int)(key[j] & 0xfffffu);
+                    if (!(vmd[ci[pos]] <= dist)) {
+                        if (found == 0) { t.b = dist; t.bp = pos; } else { t.s = dist; t.sp = pos; }
+                        found++;
+                    }
+                }
+            }
+            // every candidate beyond the list is at least as far as its last entry (d3)
+            const int d3 = (int)(key[3] >> 20);
+            resolved = found == 2 || cnt <= 4 || (found == 1 && t.b > TH_LOW) || (found == 0 && d3 > TH_LOW);
+            if (!resolved && found == 1 && (float)t.b < __fmul_rn((float)d3, P.nnratio)) {
+                t.s = d3;                  // the true second-best is >= d3: the ratio test passes either way
+                resolved = true;
             }
         }
-        t = top2_warp_reduce(t);
+        if (!resolved) {
+            t = Top2{INT_MAX, INT_MAX, -1, INT_MAX, INT_MAX, -1};
+            int c0, c1, r0, r1;
+            cell_range(P.g, prev[2 * i1], prev[2 * i1 + 1], r, c0, c1, r0, r1);
+            const float qx = prev[2 * i1], qy = prev[2 * i1 + 1];
+            const uint4 a0 = __ldg(d1 + 2 * i1), a1 = __ldg(d1 + 2 * i1 + 1);
+            const bool fullRows = (r0 == 0 && r1 == GRID_ROWS - 1);
+            const int ncol = fullRows ? 1 : (c1 - c0 + 1);
+            for (int c = 0; c < ncol; c++) {
+                const int s = fullRows ? cs[c0 * GRID_ROWS] : cs[(c0 + c) * GRID_ROWS + r0];
+                const int e = fullRows ? cs[(c1 + 1) * GRID_ROWS] : cs[(c0 + c) * GRID_ROWS + r1 + 1];
+                for (int p = s + lane; p < e; p += 32) {
+                    const int i2 = ci[p];
+                    // level filter: minLevel = maxLevel = level1 (:429, Frame.cc:468-485)
+                    const int o2 = oct2[i2];
+                    if (o2 < level1 || (level1 >= 0 && o2 > level1)) continue;
+                    if (!(fabsf(__fsub_rn(k2x[i2], qx)) < r && fabsf(__fsub_rn(k2y[i2], qy)) < r)) continue;
+                    const int dist = hamming256(a0, a1, __ldg(d2 + 2 * i2), __ldg(d2 + 2 * i2 + 1));
+                    if (vmd[i2] <= dist) continue;                                     // :448
+                    top2_push(t, dist, p, 0);
+                }
+            }
+            t = top2_warp_reduce(t);
+        }
         if (t.b <= TH_LOW && (float)t.b < __fmul_rn((float)t.s, P.nnratio)) {     // :463-465
             if (lane == 0) {
                 const int best2 = ci[t.bp];
@@ -307,10 +426,78 @@ struct ProjParams {
     const float* scaleFactors;
     int nlevels;
     int* nmatches;
+    uint4* topk;               // items x mpStride: 4 best static candidates, key = dist << 23 | CSR position << 5 | octave
+    int* topkCount;            // items x mpStride
     int items;
     float nnratio, th;
 };
 
+// ---- SearchByProjection, phase A: one THREAD per map point, everything that does not depend on the
+// assignments made during the call: grid window, level and stereo tests, keypoints that hold a map
+// point with observations from the start (those are never re-assigned), Hamming distance; the 4
+// smallest keys (distance, visiting position) and the candidate count are kept per map point.
+__global__ void __launch_bounds__(128) k_proj_topk(const ProjParams P)
+{
+    const int item = blockIdx.y;
+    const int nmp = min(P.mpN[item], P.mpStride);
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= nmp) return;
+    const size_t mo = (size_t)item * P.mpStride;
+    uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    int count = -1;
+    if (P.mpInView[mo + i] && !P.mpBad[mo + i]) {                                    // :56-60
+        const float* kx = P.f.x + (size_t)item * P.f.stride;
+        const float* ky = P.f.y + (size_t)item * P.f.stride;
+        const int* koct = P.f.octave + (size_t)item * P.f.stride;
+        const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
+        const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
+        const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+        const int* ci = P.cellItems + (size_t)item * P.f.stride;
+        const int* kpmp = P.kpMp + (size_t)item * P.f.stride;
+        const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
+        const int lvl = P.mpLevel[mo + i];
+        float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
+        if (P.th != 1.0f) r = __fmul_rn(r, P.th);
+        const float rs = __fmul_rn(r, P.scaleFactors[lvl]);
+        const float qx = P.mpX[mo + i], qy = P.mpY[mo + i], qxr = P.mpXR[mo + i];
+        int c0, c1, r0, r1;
+        if (cell_range(P.g, qx, qy, rs, c0, c1, r0, r1)) {
+            count = 0;
+            const int minLevel = lvl - 1, maxLevel = lvl;
+            const bool check = (minLevel > 0) || (maxLevel >= 0);
+            const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + (mo + i) * 32);
+            const uint4 a0 = __ldg(md), a1 = __ldg(md + 1);
+            for (int c = c0; c <= c1; c++) {
+                const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
+                for (int p = s; p < e; p++) {
+                    const int idx = ci[p];
+                    const int o = koct[idx];
+                    if (check) {
+                        if (o < minLevel) continue;
+                        if (maxLevel >= 0 && o > maxLevel) continue;
+                    }
+                    if (!(fabsf(__fsub_rn(kx[idx], qx)) < rs && fabsf(__fsub_rn(ky[idx], qy)) < rs)) continue;
+                    const int held = kpmp[idx];                                      // :89-91, initial state
+                    if (held != -1) {
+                        const int obs = held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0);
+                        if (obs > 0) continue;
+                    }
+                    if (ur && ur[idx] > 0) {                                        // :93-98
+                        const float er = fabsf(__fsub_rn(qxr, ur[idx]));
+                        if (er > rs) continue;
+                    }
+                    const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                    top4_insert(best, ((uint32_t)dist << 23) | ((uint32_t)p << 5) | (uint32_t)(o & 31));
+                    count++;
+                }
+            }
+        }
+    }
+    P.topk[mo + i] = best;
+    P.topkCount[mo + i] = count;
+}
+
+// ---- SearchByProjection, phase B: the greedy pass, one warp per frame --------------------------
 __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
 {
     const int lane = threadIdx.x & 31;
@@ -332,45 +519,74 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
 
     int nmatches = 0;
     const bool bFactor = P.th != 1.0f;
+    const uint4* topk = P.topk + mo;
+    const int* topkCount = P.topkCount + mo;
     for (int i = 0; i < nmp; i++) {
-        if (!P.mpInView[mo + i]) continue;                                        // :56-60
-        if (P.mpBad[mo + i]) continue;
-        const int lvl = P.mpLevel[mo + i];
-        float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
-        if (bFactor) r = __fmul_rn(r, P.th);
-        const float rs = __fmul_rn(r, P.scaleFactors[lvl]);
-        const float qx = P.mpX[mo + i], qy = P.mpY[mo + i];
-        int c0, c1, r0, r1;
-        if (!cell_range(P.g, qx, qy, rs, c0, c1, r0, r1)) continue;
-        const int minLevel = lvl - 1, maxLevel = lvl;
-        const bool check = (minLevel > 0) || (maxLevel >= 0);
-        const uint4 a0 = __ldg(md + 2 * i), a1 = __ldg(md + 2 * i + 1);
-        const float qxr = P.mpXR[mo + i];
+        const int cnt = topkCount[i];
+        if (cnt <= 0) continue;          // not in view / bad (:56-60), outside the grid, or no candidate (:73)
         Top2 t = {256, INT_MAX, -1, 256, INT_MAX, -1};
-        for (int c = c0; c <= c1; c++) {
-            const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
-            for (int p = s + lane; p < e; p += 32) {
-                const int idx = ci[p];
-                const int o = koct[idx];
-                if (check) {
-                    if (o < minLevel) continue;
-                    if (maxLevel >= 0 && o > maxLevel) continue;
+        // Fast path (every lane redundantly): the map point's 4 best static candidates in visiting order,
+        // minus the keypoints that were taken since (:89-91).  Conclusive when two survive, when the list
+        // holds every candidate, or when nothing within TH_HIGH can survive; otherwise the full scan below.
+        bool resolved;
+        {
+            const uint4 kk = topk[i];
+            const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+            int found = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (found < 2 && j < cnt) {
+                    const int dist = (int)(key[j] >> 23), pos = (int)((key[j] >> 5) & 0x3ffffu), o = (int)(key[j] & 31u);
+                    bool taken = false;
+                    const int held = kpmp[ci[pos]];
+                    if (held != -1) taken = (held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[ci[pos]] : 0)) > 0;
+                    if (!taken && dist < 256) {
+                        if (found == 0) { t.b = dist; t.bp = pos; t.ba = o; } else { t.s = dist; t.sp = pos; t.sa = o; }
+                        found++;
+                    }
                 }
-                if (!(fabsf(__fsub_rn(kx[idx], qx)) < rs && fabsf(__fsub_rn(ky[idx], qy)) < rs)) continue;
-                const int held = kpmp[idx];                                          // :89-91
-                if (held != -1) {
-                    const int obs = held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0);
-                    if (obs > 0) continue;
-                }
-                if (ur && ur[idx] > 0) {                                            // :93-98
-                    const float er = fabsf(__fsub_rn(qxr, ur[idx]));
-                    if (er > rs) continue;
-                }
-                const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
-                top2_push(t, dist, p, o);
             }
+            const int d3 = (int)(key[3] >> 23);
+            resolved = found == 2 || cnt <= 4 || (found == 1 && t.b > TH_HIGH) || (found == 0 && d3 > TH_HIGH);
         }
-        t = top2_warp_reduce(t);
+        if (!resolved) {
+            t = Top2{256, INT_MAX, -1, 256, INT_MAX, -1};
+            const int lvl = P.mpLevel[mo + i];
+            float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
+            if (bFactor) r = __fmul_rn(r, P.th);
+            const float rs = __fmul_rn(r, P.scaleFactors[lvl]);
+            const float qx = P.mpX[mo + i], qy = P.mpY[mo + i];
+            int c0, c1, r0, r1;
+            cell_range(P.g, qx, qy, rs, c0, c1, r0, r1);
+            const int minLevel = lvl - 1, maxLevel = lvl;
+            const bool check = (minLevel > 0) || (maxLevel >= 0);
+            const uint4 a0 = __ldg(md + 2 * i), a1 = __ldg(md + 2 * i + 1);
+            const float qxr = P.mpXR[mo + i];
+            for (int c = c0; c <= c1; c++) {
+                const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
+                for (int p = s + lane; p < e; p += 32) {
+                    const int idx = ci[p];
+                    const int o = koct[idx];
+                    if (check) {
+                        if (o < minLevel) continue;
+                        if (maxLevel >= 0 && o > maxLevel) continue;
+                    }
+                    if (!(fabsf(__fsub_rn(kx[idx], qx)) < rs && fabsf(__fsub_rn(ky[idx], qy)) < rs)) continue;
+                    const int held = kpmp[idx];                                          // :89-91
+                    if (held != -1) {
+                        const int obs = held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0);
+                        if (obs > 0) continue;
+                    }
+                    if (ur && ur[idx] > 0) {                                            // :93-98
+                        const float er = fabsf(__fsub_rn(qxr, ur[idx]));
+                        if (er > rs) continue;
+                    }
+                    const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                    top2_push(t, dist, p, o);
+                }
+            }
+            t = top2_warp_reduce(t);
+        }
         if (t.b <= TH_HIGH && !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s))) {   // :120-127
             if (lane == 0) kpmp[ci[t.bp]] = i;
             nmatches++;
@@ -390,7 +606,8 @@ using namespace orbb200;
 struct orbb200_matcher {
     int maxItems, maxPoints, device, lastLaunches;
     cudaStream_t stream;
-    int *cellStart, *cellItems, *scratchA, *scratchB, *scratchC;
+    int *cellStart, *cellItems, *scratchA, *scratchB, *scratchC, *topkCount;
+    uint4* topk;
     std::vector<void*> allocs;
     // staging for host-pointer calls
     uint8_t* stage; size_t stageBytes;
@@ -420,6 +637,8 @@ extern "C" int orbb200_matcher_create(int max_items, int max_points, int device,
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchA, sizeof(int) * np);
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchB, sizeof(int) * np);
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchC, sizeof(int) * np);
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->topk, sizeof(uint4) * np);
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->topkCount, sizeof(int) * np);
     if (rc == ORBB200_OK && cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed"); rc = ORBB200_ECUDA;
     }
@@ -511,6 +730,7 @@ static int check_view(const orbb200_matcher* m, int items, int stride, const cha
 {
     if (items < 1 || items > m->maxItems) { set_error("%s: items %d outside 1..%d", what, items, m->maxItems); return ORBB200_EINVAL; }
     if (stride < 1 || stride > m->maxPoints) { set_error("%s: stride %d outside 1..%d", what, stride, m->maxPoints); return ORBB200_EINVAL; }
+    if (stride >= (1 << 18)) { set_error("%s: more than 262143 points per item", what); return ORBB200_EINVAL; }
     return ORBB200_OK;
 }
 
@@ -572,13 +792,16 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.matchedDist = m->scratchA; P.matches21 = m->scratchB; P.histBin = m->scratchC;
     P.prevMatched = dPrev; P.matches12 = dM12; P.nmatches = dN;
+    P.topk = m->topk; P.topkCount = m->topkCount;
     P.items = items; P.window = window_size; P.checkOri = check_orientation; P.nnratio = nnratio;
     // scratch strides follow the views
     k_build_grid<<<items, 256, 0, st>>>(P.f2, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");
+    k_init_topk<<<dim3((f1->stride + 127) / 128, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_init_topk");
     k_search_init<<<(items + 3) / 4, 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_search_init");
-    m->lastLaunches = 2;
+    m->lastLaunches = 3;
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(prev_matched, dPrev, np1 * 8, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaMemcpyAsync(matches12, dM12, np1 * 4, cudaMemcpyDeviceToHost, st));
@@ -598,6 +821,7 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
         !mp->proj_y || !mp->proj_xr || !mp->level || !mp->view_cos || !mp->desc || !mp->obs) { set_error("incomplete view"); return ORBB200_EINVAL; }
     int rc;
     if ((rc = check_view(m, items, f->stride, "frame")) || (rc = check_view(m, items, mp->stride, "map points"))) return rc;
+    if (nlevels > 32) { set_error("more than 32 pyramid levels"); return ORBB200_EINVAL; }
     if (nlevels < 1 || !bounds || !(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1])) { set_error("bad geometry"); return ORBB200_EINVAL; }
     ORB_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = m->stream;
@@ -628,11 +852,14 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
     }
     P.mpStride = mp->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.nlevels = nlevels; P.nmatches = dN; P.items = items; P.nnratio = nnratio; P.th = th;
+    P.topk = m->topk; P.topkCount = m->topkCount;
     k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");
+    k_proj_topk<<<dim3((mp->stride + 127) / 128, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_proj_topk");
     k_search_proj<<<(items + 3) / 4, 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_search_proj");
-    m->lastLaunches = 2;
+    m->lastLaunches = 3;
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(kp_mp, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
