@@ -690,14 +690,21 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
 // ======================================================================================
 // K5: GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (:1117), 8.8 fixed point like OpenCV
 // ======================================================================================
-// Issue-bound, so built for few instructions per pixel: a thread owns 4 adjacent columns (one 32-bit
-// word) and walks down BL_ROWS rows.  Horizontal pass on packed bytes: two IDP.4A per pixel on byte
-// windows cut out of three aligned words with PRMT.  Vertical pass: a 7-row register window of the
-// 16-bit row sums (the loop is unrolled by 7 so the window rotates by renaming), symmetric taps
-// folded (3 adds + 4 multiply-adds per pixel).  out = (sum + 2^15) >> 16 is byte 2 of the accumulator.
-// Columns w..w+3 of levels >= 1 hold the REFLECT_101 continuation (k_resize writes them), so only the
-// left edge and the level-0 right edge need a fix-up, both a single PRMT.
+// A warp owns a 128 x 36 output tile.  The 42 input rows it needs are fetched by the TMA unit as 1-D
+// bulk copies (cp.async.bulk, one per row, completion counted on an mbarrier) into a two-stage ring in
+// shared memory, so the loads of tile t+1 fly while tile t is being filtered and no load latency sits
+// on the critical path.  REFLECT_101 in y is a choice of source row per copy; in x it is one PRMT at the
+// left edge and (level 0 only) at the right edge -- levels >= 1 carry their reflected continuation in
+// columns w..w+3 (written by k_resize).
+// Arithmetic, per thread = 4 adjacent pixels: horizontal pass on packed bytes, two IDP.4A per pixel on
+// byte windows cut out of three words with PRMT; vertical pass over a 7-row register window of 16-bit
+// row sums (loop unrolled by 7 so the window rotates by renaming), symmetric taps folded;
+// out = (sum + 2^15) >> 16 is byte 2 of the accumulator.
 constexpr int BL_ROWS = 36, BL_WARPS = 4;     // 36 output rows + 6 halo rows = 6 groups of 7 input rows
+constexpr int BL_IN_ROWS = BL_ROWS + 6;
+constexpr int BL_ROW_BYTES = 160;             // image columns x0-16 .. x0+143 (16-byte aligned window around 128 px)
+constexpr int BL_STAGE_BYTES = BL_IN_ROWS * BL_ROW_BYTES;
+constexpr int BL_WARP_BYTES = 2 * BL_STAGE_BYTES + 16;
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
@@ -706,85 +713,129 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
-__device__ __forceinline__ void blur_load_words(const uint8_t* row, int x0, int w, bool fast, bool left, bool rightFix,
-                                                uint32_t& w0, uint32_t& w1, uint32_t& w2)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    if (fast) {
-        w1 = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
-        w0 = left ? 0u : __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 4));
-        w2 = rightFix ? 0u : __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 4));
-        if (left) w0 = __byte_perm(w1, w2, 0x1234);          // p[-4..-1] = p[4], p[3], p[2], p[1]
-        if (rightFix) w2 = __byte_perm(w0, w1, 0x3456);      // p[w..w+3] = p[w-2], p[w-3], p[w-4], p[w-5]
-    } else {                                                 // unaligned or odd-width level 0: byte gathers
-        uint32_t v[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            v[j] = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int x = reflect101(min(x0 - 4 + 4 * j + b, w + 3), w);
-                v[j] |= (uint32_t)__ldg(row + x) << (8 * b);
-            }
-        }
-        w0 = v[0]; w1 = v[1]; w2 = v[2];
-    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+struct BlurTile { int l, frame, x0, y0; };
+
+// tile index -> (frame, level, position); false when the level has no keypoints (skipped like :1112)
+__device__ __forceinline__ bool blur_tile(const ExtractParams& P, long long t, BlurTile& bt)
+{
+    const int frame = (int)(t / P.totalBlurTiles), tile = (int)(t - (long long)frame * P.totalBlurTiles);
+    int l = 0;
+    while (l + 1 < P.nlevels && tile >= P.lv[l + 1].blurTileStart) l++;
+    const LevelGeo& g = P.lv[l];
+    const int q = tile - g.blurTileStart;
+    const int ty = q / g.blurTilesX, tx = q - ty * g.blurTilesX;
+    bt.l = l; bt.frame = frame; bt.x0 = tx * 128; bt.y0 = ty * BL_ROWS;
+    return P.lkpCount[frame * P.nlevels + l] != 0;
 }
 
 __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
 {
+    extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x * BL_WARPS + warp;
-    if (tile >= P.totalBlurTiles) return;
-    const int frame = blockIdx.y;
-    int l = 0;
-    while (l + 1 < P.nlevels && tile >= P.lv[l + 1].blurTileStart) l++;
-    const LevelGeo& g = P.lv[l];
-    if (P.lkpCount[frame * P.nlevels + l] == 0) return;       // the reference skips empty levels (:1112)
-    const int t = tile - g.blurTileStart;
-    const int ty = t / g.blurTilesX, tx = t - ty * g.blurTilesX;
-    const int x0 = tx * 128 + 4 * lane, y0 = ty * BL_ROWS;
-    if (x0 >= g.w) return;
-    int pitch;
-    const uint8_t* img = level_ptr(P, l, frame, pitch);
-    uint8_t* dst = P.blur + (long long)frame * P.blurFrameBytes + g.blurOff;
+    uint8_t* ring = smem + (size_t)warp * BL_WARP_BYTES;
+    const uint32_t bar0 = smem_u32(ring + 2 * BL_STAGE_BYTES);          // two 8-byte mbarriers
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
-    const bool alignedSrc = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3) == 0;
-    // level 0 is the caller's buffer: nothing beyond column w-1 may be read; levels >= 1 carry 4 reflected columns
-    const bool fast = alignedSrc && (l > 0 || (g.w & 3) == 0 || x0 + 8 <= g.w);
-    const bool left = x0 == 0, rightFix = (l == 0) && (x0 + 4 >= g.w);
+    const long long nTiles = (long long)P.totalBlurTiles * P.batch;
+    const long long stride = (long long)gridDim.x * BL_WARPS;
     const uint32_t k0 = 18, k1 = 34, k2 = P.blurVariant ? 49 : 48, k3 = P.blurVariant ? 55 : 56;
     const uint32_t kA = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);     // taps for p[x-3..x]
     const uint32_t kB = k2 | (k1 << 8) | (k0 << 16);                  // taps for p[x+1..x+3]
-    const int yEnd = min(y0 + BL_ROWS, g.h);
 
-    int H[7][4];
+    // issue the 42 row copies of tile bt into ring stage s
+    auto issue = [&](const BlurTile& bt, int s) {
+        const LevelGeo& g = P.lv[bt.l];
+        int pitch;
+        const uint8_t* img = level_ptr(P, bt.l, bt.frame, pitch);
+        const int rowLimit = bt.l == 0 ? P.inRowBytes : pitch;          // bytes of a row that may be read (multiple of 16)
+        const int xs = max(bt.x0 - 16, 0), xe = min(bt.x0 + 144, rowLimit);
+        const uint32_t nbytes = (uint32_t)(xe - xs);
+        const uint32_t bar = bar0 + 8 * s;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage are done
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbytes * BL_IN_ROWS) : "memory");
+        __syncwarp();
+        for (int ir = lane; ir < BL_IN_ROWS; ir += 32) {
+            const int iy = reflect101(min(bt.y0 - 3 + ir, g.h + 2), g.h);
+            const uint8_t* src = img + (long long)iy * pitch + xs;
+            const uint32_t dst = smem_u32(ring + s * BL_STAGE_BYTES + ir * BL_ROW_BYTES + (xs - (bt.x0 - 16)));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(nbytes), "r"(bar) : "memory");
+        }
+    };
+
+    long long t = (long long)blockIdx.x * BL_WARPS + warp;
+    BlurTile cur, nxt;
+    while (t < nTiles && !blur_tile(P, t, cur)) t += stride;
+    if (t >= nTiles) return;
+    issue(cur, 0);
+    int stage = 0;
+    uint32_t phase0 = 0, phase1 = 0;
+    while (t < nTiles) {
+        long long tn = t + stride;
+        while (tn < nTiles && !blur_tile(P, tn, nxt)) tn += stride;
+        if (tn < nTiles) issue(nxt, stage ^ 1);
+        if (stage == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; } else { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
+
+        const LevelGeo& g = P.lv[cur.l];
+        const int x0 = cur.x0 + 4 * lane;
+        if (x0 < g.w) {
+            uint8_t* dst = P.blur + (long long)cur.frame * P.blurFrameBytes + g.blurOff;
+            const bool left = x0 == 0, rightFix = (cur.l == 0) && (x0 + 4 >= g.w);
+            const int yEnd = min(cur.y0 + BL_ROWS, g.h);
+            const uint8_t* sb = ring + stage * BL_STAGE_BYTES + 12 + 4 * lane;      // word holding columns x0-4..x0-1
+            int H[7][4];
 #pragma unroll 1
-    for (int grp = 0; grp < (BL_ROWS + 6) / 7; grp++) {
+            for (int grp = 0; grp < BL_IN_ROWS / 7; grp++) {
 #pragma unroll
-        for (int u = 0; u < 7; u++) {
-            const int ir = grp * 7 + u;
-            const int oy = y0 + ir - 6;                        // output row completed by this input row
-            if (oy >= yEnd) break;
-            const int iy = reflect101(y0 - 3 + ir, g.h);
-            uint32_t w0, w1, w2;
-            blur_load_words(img + (long long)iy * pitch, x0, g.w, fast, left, rightFix, w0, w1, w2);
-            H[u][0] = __dp4a(__byte_perm(w0, w1, 0x4321), kA, __dp4a(__byte_perm(w1, w2, 0x4321), kB, 0u));
-            H[u][1] = __dp4a(__byte_perm(w0, w1, 0x5432), kA, __dp4a(__byte_perm(w1, w2, 0x5432), kB, 0u));
-            H[u][2] = __dp4a(__byte_perm(w0, w1, 0x6543), kA, __dp4a(__byte_perm(w1, w2, 0x6543), kB, 0u));
-            H[u][3] = __dp4a(w1, kA, __dp4a(w2, kB, 0u));
-            if (oy >= y0) {
-                uint32_t acc[4];
+                for (int u = 0; u < 7; u++) {
+                    const int ir = grp * 7 + u;
+                    const int oy = cur.y0 + ir - 6;                    // output row completed by this input row
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(sb + ir * BL_ROW_BYTES);
+                    uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                    if (left) w0 = __byte_perm(w1, w2, 0x1234);        // p[-4..-1] = p[4], p[3], p[2], p[1]
+                    if (rightFix) w2 = __byte_perm(w0, w1, 0x3456);    // p[w..w+3] = p[w-2], p[w-3], p[w-4], p[w-5]
+                    H[u][0] = __dp4a(__byte_perm(w0, w1, 0x4321), kA, __dp4a(__byte_perm(w1, w2, 0x4321), kB, 0u));
+                    H[u][1] = __dp4a(__byte_perm(w0, w1, 0x5432), kA, __dp4a(__byte_perm(w1, w2, 0x5432), kB, 0u));
+                    H[u][2] = __dp4a(__byte_perm(w0, w1, 0x6543), kA, __dp4a(__byte_perm(w1, w2, 0x6543), kB, 0u));
+                    H[u][3] = __dp4a(w1, kA, __dp4a(w2, kB, 0u));
+                    if (oy >= cur.y0 && oy < yEnd) {
+                        uint32_t acc[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    // window rows: oldest = slot (u+1)%7 ... newest = slot u
-                    acc[j] = 32768u + k0 * (uint32_t)(H[(u + 1) % 7][j] + H[u][j]) + k1 * (uint32_t)(H[(u + 2) % 7][j] + H[(u + 6) % 7][j]) +
-                             k2 * (uint32_t)(H[(u + 3) % 7][j] + H[(u + 5) % 7][j]) + k3 * (uint32_t)H[(u + 4) % 7][j];
-                    if (P.blurVariant) acc[j] = min(acc[j], 0x00ffffffu);    // taps sum to 257: saturate like OpenCV
+                        for (int j = 0; j < 4; j++) {
+                            // window rows: oldest = slot (u+1)%7 ... newest = slot u
+                            acc[j] = 32768u + k0 * (uint32_t)(H[(u + 1) % 7][j] + H[u][j]) + k1 * (uint32_t)(H[(u + 2) % 7][j] + H[(u + 6) % 7][j]) +
+                                     k2 * (uint32_t)(H[(u + 3) % 7][j] + H[(u + 5) % 7][j]) + k3 * (uint32_t)H[(u + 4) % 7][j];
+                            if (P.blurVariant) acc[j] = min(acc[j], 0x00ffffffu);    // taps sum to 257: saturate like OpenCV
+                        }
+                        const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
+                        *reinterpret_cast<uint32_t*>(dst + (long long)oy * g.pitch + x0) = __byte_perm(lo, hi, 0x5410);
+                    }
                 }
-                const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
-                *reinterpret_cast<uint32_t*>(dst + (long long)oy * g.pitch + x0) = __byte_perm(lo, hi, 0x5410);
             }
         }
+        __syncwarp();
+        t = tn; cur = nxt; stage ^= 1;
     }
 }
 
@@ -992,7 +1043,7 @@ struct orbb200_extractor {
     cudaStream_t stream;
     uint8_t* dIn;              // staging for host frames (level 0)
     size_t inPitch;
-    int totalCells, totalBlurTiles, maxKp;
+    int totalCells, totalBlurTiles, maxKp, numSMs;
     size_t fastSmem, qtSmem;
     int lastLaunches, lastBatch;
     const uint8_t* lastIn; long long lastInFrameStride; int lastInPitch;
@@ -1171,7 +1222,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     h->qtSmem = perNode * P.qtNC + 6 * (size_t)P.qtPC;
 
     // ---- device memory
-    h->inPitch = align_up(width, 16);
+    h->inPitch = align_up(width + 4, 16);
     int rc;
 #define TRY(x) do { rc = (x); if (rc != ORBB200_OK) { orbb200_extractor_destroy(h); return rc; } } while (0)
     short4* dTabs = nullptr;
@@ -1204,6 +1255,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         ? cudaFuncSetAttribute(k_fast<36, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem)
         : cudaFuncSetAttribute(k_fast<24, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qtSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
         set_error("extractor_create: %s", cudaGetErrorString(e));
         orbb200_extractor_destroy(h);
@@ -1285,11 +1338,11 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
     P.candCount += (size_t)first * P.nlevels; P.lkp += (size_t)first * P.kpFrameCap; P.lkpCount += (size_t)first * P.nlevels;
     const size_t inFrameBytes = h->inPitch * (size_t)h->height;
     const bool staged = d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch;
-    // The kernels read level 0 as aligned 32-bit words.  A caller buffer qualifies when base and strides are
-    // 4-byte aligned and the width is a multiple of 4 (then no word straddles the end of a row); anything
-    // else is first copied into the handle's padded staging slab.
+    // The kernels read level 0 as aligned words and 16-byte TMA bulk rows.  A caller buffer qualifies when base,
+    // strides and width are multiples of 16 (then no chunk straddles the end of a row); anything else is
+    // first copied into the handle's padded staging slab.
     if (!staged) {
-        const bool canonical = ((reinterpret_cast<uintptr_t>(d_images) | stride | frame_stride | (size_t)h->width) & 3) == 0;
+        const bool canonical = ((reinterpret_cast<uintptr_t>(d_images) | stride | frame_stride | (size_t)h->width) & 15) == 0;
         if (canonical) {
             P.inRowBytes = h->width;
         } else {
@@ -1325,7 +1378,11 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
     k_quadtree<<<dim3(P.nlevels, batch), QT_THREADS, h->qtSmem, st>>>(P);
     ORB_CHECK_LAUNCH("k_quadtree"); launches++;
     STAGE_MARK(3);
-    k_blur<<<dim3((h->totalBlurTiles + BL_WARPS - 1) / BL_WARPS, batch), BL_WARPS * 32, 0, st>>>(P);
+    {   // persistent warps: a few CTAs per SM walk the (frame, level, tile) list
+        const long long tiles = (long long)h->totalBlurTiles * batch;
+        const int ctas = (int)std::min<long long>((tiles + BL_WARPS - 1) / BL_WARPS, (long long)h->numSMs * 4);
+        k_blur<<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, st>>>(P);
+    }
     ORB_CHECK_LAUNCH("k_blur"); launches++;
     STAGE_MARK(4);
     k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
