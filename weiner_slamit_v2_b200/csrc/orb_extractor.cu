@@ -1222,7 +1222,9 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     h->qtSmem = perNode * P.qtNC + 6 * (size_t)P.qtPC;
 
     // ---- device memory
-    h->inPitch = align_up(width + 4, 16);
+    // staging slab for host frames / non-canonical device frames: tight rows when the width allows 16-byte
+    // chunks (host copies are then linear, which is what PCIe DMA likes), padded rows otherwise
+    h->inPitch = (width % 16 == 0) ? (size_t)width : align_up(width + 4, 16);
     int rc;
 #define TRY(x) do { rc = (x); if (rc != ORBB200_OK) { orbb200_extractor_destroy(h); return rc; } } while (0)
     short4* dTabs = nullptr;
@@ -1450,7 +1452,8 @@ extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images,
     ORB_CUDA(cudaSetDevice(h->device));
     // Chunked pipeline: while chunk c is in the kernels, chunk c+1 is on its way up and chunk c-1 on its way
     // down (three streams, events between them).  Small batches go through in one piece.
-    const int nchunk = batch >= 64 ? 4 : (batch >= 16 ? 2 : 1);
+    int nchunk = batch >= 96 ? 3 : (batch >= 32 ? 2 : 1);       // measured on B200 + PCIe gen5: 2-3 chunks are best at batch 256
+    if (const char* e = getenv("ORBB200_CHUNKS")) nchunk = std::max(1, std::min(8, std::min(batch, atoi(e))));   // tuning knob
     const int cs = (batch + nchunk - 1) / nchunk;
     const int mk = h->maxKp;
     const size_t inFrameBytes = h->inPitch * (size_t)h->height;
@@ -1459,7 +1462,9 @@ extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images,
         if (n <= 0) break;
         const uint8_t* src = images + (size_t)f0 * frame_stride;
         uint8_t* dIn = h->dIn + (size_t)f0 * inFrameBytes;
-        if (frame_stride == stride * (size_t)h->height) {
+        if (frame_stride == stride * (size_t)h->height && stride == h->inPitch) {
+            ORB_CUDA(cudaMemcpyAsync(dIn, src, inFrameBytes * n, cudaMemcpyHostToDevice, h->copyIn));       // one linear DMA
+        } else if (frame_stride == stride * (size_t)h->height) {
             ORB_CUDA(cudaMemcpy2DAsync(dIn, h->inPitch, src, stride, h->width, (size_t)h->height * n, cudaMemcpyHostToDevice, h->copyIn));
         } else {
             for (int f = 0; f < n; f++)
@@ -1474,11 +1479,18 @@ extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images,
         ORB_CUDA(cudaEventRecord(h->evDone[c], h->stream));
         ORB_CUDA(cudaStreamWaitEvent(h->copyOut, h->evDone[c], 0));
         ORB_CUDA(cudaMemcpyAsync(counts + f0, h->dOutCount + f0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->copyOut));
-        ORB_CUDA(cudaMemcpy2DAsync(keypoints + (size_t)f0 * cap, (size_t)cap * sizeof(orbb200_keypoint), h->dOutKp + (size_t)f0 * mk,
-                                   (size_t)mk * sizeof(orbb200_keypoint), (size_t)mk * sizeof(orbb200_keypoint), n,
-                                   cudaMemcpyDeviceToHost, h->copyOut));
-        ORB_CUDA(cudaMemcpy2DAsync(descriptors + (size_t)f0 * cap * 32, (size_t)cap * 32, h->dOutDesc + (size_t)f0 * mk * 32, (size_t)mk * 32,
-                                   (size_t)mk * 32, n, cudaMemcpyDeviceToHost, h->copyOut));
+        if (cap == mk) {
+            ORB_CUDA(cudaMemcpyAsync(keypoints + (size_t)f0 * cap, h->dOutKp + (size_t)f0 * mk, (size_t)n * mk * sizeof(orbb200_keypoint),
+                                     cudaMemcpyDeviceToHost, h->copyOut));
+            ORB_CUDA(cudaMemcpyAsync(descriptors + (size_t)f0 * cap * 32, h->dOutDesc + (size_t)f0 * mk * 32, (size_t)n * mk * 32,
+                                     cudaMemcpyDeviceToHost, h->copyOut));
+        } else {
+            ORB_CUDA(cudaMemcpy2DAsync(keypoints + (size_t)f0 * cap, (size_t)cap * sizeof(orbb200_keypoint), h->dOutKp + (size_t)f0 * mk,
+                                       (size_t)mk * sizeof(orbb200_keypoint), (size_t)mk * sizeof(orbb200_keypoint), n,
+                                       cudaMemcpyDeviceToHost, h->copyOut));
+            ORB_CUDA(cudaMemcpy2DAsync(descriptors + (size_t)f0 * cap * 32, (size_t)cap * 32, h->dOutDesc + (size_t)f0 * mk * 32, (size_t)mk * 32,
+                                       (size_t)mk * 32, n, cudaMemcpyDeviceToHost, h->copyOut));
+        }
     }
     h->lastBatch = batch; h->lastIn = h->dIn; h->lastInPitch = (int)h->inPitch; h->lastInFrameStride = (long long)inFrameBytes;
     h->lastLaunches *= nchunk;
