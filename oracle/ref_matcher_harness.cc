@@ -1,0 +1,126 @@
+// ref_matcher_harness.cc -- TEST INFRASTRUCTURE.  C entry points that run the reference's OWN, unmodified
+// ORBmatcher.cc (with Frame.cc and MapPoint.cc) on flattened inputs: the harness builds ORB_SLAM2::Frame and
+// ORB_SLAM2::MapPoint objects, calls ORBmatcher::SearchForInitialization / SearchByProjection /
+// DescriptorDistance, and copies the results back.  Private members are reached by re-declaring the access
+// specifiers for the reference headers only (the standard headers are included first, untouched).
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <list>
+#include <map>
+#include <mutex>
+#include <new>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include <numeric>
+#include <limits>
+#include <unordered_map>
+#include <opencv2/opencv.hpp>
+#include <opencv2/core/core.hpp>
+#include <opencv2/features2d/features2d.hpp>
+#include <Eigen/Core>
+#include <Eigen/Dense>
+
+#define private public
+#define protected public
+#include "ORBmatcher.h"
+#undef private
+#undef protected
+
+using namespace ORB_SLAM2;
+
+namespace {
+void fill_frame(Frame& F, int n, const float* x, const float* y, const int32_t* oct, const float* ang,
+                const uint8_t* desc, const float* bounds)
+{
+    F.N = n;
+    F.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) {
+        cv::KeyPoint& k = F.mvKeysUn[i];
+        k.pt.x = x[i]; k.pt.y = y[i]; k.octave = oct[i]; k.angle = ang ? ang[i] : -1.f; k.size = 31.f; k.response = 0; k.class_id = -1;
+    }
+    F.mvKeys = F.mvKeysUn;
+    F.mDescriptors = cv::Mat(n > 0 ? n : 1, 32, CV_8U, (void*)desc);
+    F.mvuRight = std::vector<float>(n, -1.f);
+    F.mvDepth = std::vector<float>(n, -1.f);
+    F.mvpMapPoints = std::vector<MapPoint*>(n, static_cast<MapPoint*>(NULL));
+    Frame::mnMinX = bounds[0]; Frame::mnMinY = bounds[1]; Frame::mnMaxX = bounds[2]; Frame::mnMaxY = bounds[3];
+    // as in the Frame constructor (Frame.cc:317-318)
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+    F.AssignFeaturesToGrid();
+}
+}  // namespace
+
+extern "C" {
+
+int refm_descriptor_distance(const uint8_t* a, const uint8_t* b)
+{
+    cv::Mat A(1, 32, CV_8U, (void*)a), B(1, 32, CV_8U, (void*)b);
+    return ORBmatcher::DescriptorDistance(A, B);
+}
+
+int refm_search_for_initialization(
+    int n1, const float* k1x, const float* k1y, const int32_t* k1oct, const float* k1ang, const uint8_t* d1,
+    int n2, const float* k2x, const float* k2y, const int32_t* k2oct, const float* k2ang, const uint8_t* d2,
+    const float* bounds, float nnratio, int check_orientation, int window_size, float* prev_matched, int32_t* matches12)
+{
+    Frame F1, F2;
+    fill_frame(F1, n1, k1x, k1y, k1oct, k1ang, d1, bounds);
+    fill_frame(F2, n2, k2x, k2y, k2oct, k2ang, d2, bounds);
+    std::vector<cv::Point2f> prev(n1);
+    for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+    std::vector<int> m12;
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    const int n = matcher.SearchForInitialization(F1, F2, prev, m12, window_size);
+    for (int i = 0; i < n1; i++) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
+int refm_search_by_projection(
+    int nmp, const uint8_t* mp_in_view, const uint8_t* mp_bad, const float* mp_x, const float* mp_y,
+    const float* mp_xr, const int32_t* mp_level, const float* mp_viewcos, const uint8_t* mp_desc, const int32_t* mp_obs,
+    int n, const float* kx, const float* ky, const int32_t* koct, const float* kuright, const uint8_t* kdesc,
+    int32_t* kp_mp, const int32_t* kp_mp_obs,
+    int nlevels, const float* scale_factors, const float* bounds, float nnratio, float th)
+{
+    Frame F;
+    fill_frame(F, n, kx, ky, koct, NULL, kdesc, bounds);
+    for (int i = 0; i < n; i++) F.mvuRight[i] = kuright[i];
+    F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+    // MapPoint has no default constructor and its real ones need a Map and a KeyFrame: use zeroed storage
+    // and construct only what the three methods touch (descriptor Mat; the mutexes are valid when zeroed).
+    MapPoint* mps = (MapPoint*)std::calloc(nmp > 0 ? nmp : 1, sizeof(MapPoint));
+    MapPoint* foreign = (MapPoint*)std::calloc(n > 0 ? n : 1, sizeof(MapPoint));
+    std::vector<MapPoint*> vp(nmp);
+    for (int i = 0; i < nmp; i++) {
+        MapPoint* p = &mps[i];
+        new (&p->mDescriptor) cv::Mat(1, 32, CV_8U, (void*)(mp_desc + 32 * (size_t)i));
+        p->mbTrackInView = mp_in_view[i] != 0; p->mbBad = mp_bad[i] != 0;
+        p->mTrackProjX = mp_x[i]; p->mTrackProjY = mp_y[i]; p->mTrackProjXR = mp_xr[i];
+        p->mnTrackScaleLevel = mp_level[i]; p->mTrackViewCos = mp_viewcos[i]; p->nObs = mp_obs[i];
+        vp[i] = p;
+    }
+    for (int i = 0; i < n; i++) {
+        if (kp_mp[i] >= 0) F.mvpMapPoints[i] = &mps[kp_mp[i]];
+        else if (kp_mp[i] == -2) { foreign[i].nObs = kp_mp_obs[i]; F.mvpMapPoints[i] = &foreign[i]; }
+    }
+    ORBmatcher matcher(nnratio, true);
+    const int cnt = matcher.SearchByProjection(F, vp, th);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = F.mvpMapPoints[i];
+        if (!p) kp_mp[i] = -1;
+        else if (p >= mps && p < mps + nmp) kp_mp[i] = (int32_t)(p - mps);
+        else kp_mp[i] = -2;
+    }
+    for (int i = 0; i < nmp; i++) mps[i].mDescriptor.~Mat();
+    std::free(mps); std::free(foreign);
+    return cnt;
+}
+}

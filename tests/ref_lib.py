@@ -88,3 +88,75 @@ def extract_batch_mt(frames, threads, nfeatures=1000, scale_factor=1.2, nlevels=
     lib().ref_extract_batch_mt(nfeatures, scale_factor, nlevels, ini_th, min_th, frames.ctypes.data_as(_u8p),
                                n, w, h, threads, counts.ctypes.data_as(C.POINTER(C.c_int)))
     return counts
+
+
+# ---- the reference's own ORBmatcher.cc (+ Frame.cc, MapPoint.cc): oracle/_ref/libref_matcher.so -------------
+REFM_SO = os.path.join(ORACLE_DIR, "_ref", "libref_matcher.so")
+_mlib = None
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+
+
+def matcher_available():
+    return os.path.exists(REFM_SO)
+
+
+def mlib():
+    global _mlib
+    if _mlib is None:
+        L = C.CDLL(REFM_SO)
+        L.refm_descriptor_distance.argtypes = [_u8p, _u8p]
+        L.refm_search_for_initialization.argtypes = ([C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p] * 2 +
+                                                     [_f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p])
+        L.refm_search_by_projection.argtypes = [
+            C.c_int, _u8p, _u8p, _f32p, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p,
+            C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p, _i32p,
+            C.c_int, _f32p, _f32p, C.c_float, C.c_float]
+        _mlib = L
+    return _mlib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _f(a): return np.ascontiguousarray(a, np.float32)
+def _i(a): return np.ascontiguousarray(a, np.int32)
+def _b(a): return np.ascontiguousarray(a, np.uint8)
+
+
+def ref_descriptor_distance(a, b):
+    a, b = _b(a), _b(b)
+    return mlib().refm_descriptor_distance(_p(a, _u8p), _p(b, _u8p))
+
+
+def ref_search_for_initialization(k1, d1, k2, d2, prev_matched, bounds, nnratio=0.9, check_ori=True, window=100):
+    n1, n2 = len(k1), len(k2)
+    a = [_f(k1["x"]), _f(k1["y"]), _i(k1["octave"]), _f(k1["angle"]), _b(d1) if n1 else np.zeros((1, 32), np.uint8)]
+    b = [_f(k2["x"]), _f(k2["y"]), _i(k2["octave"]), _f(k2["angle"]), _b(d2) if n2 else np.zeros((1, 32), np.uint8)]
+    bnd = _f(bounds).reshape(4)
+    pm = _f(prev_matched).copy().reshape(-1, 2) if n1 else np.zeros((1, 2), np.float32)
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    n = mlib().refm_search_for_initialization(
+        n1, _p(a[0], _f32p), _p(a[1], _f32p), _p(a[2], _i32p), _p(a[3], _f32p), _p(a[4], _u8p),
+        n2, _p(b[0], _f32p), _p(b[1], _f32p), _p(b[2], _i32p), _p(b[3], _f32p), _p(b[4], _u8p),
+        _p(bnd, _f32p), nnratio, int(check_ori), window, _p(pm, _f32p), _p(m12, _i32p))
+    return n, m12[:n1], pm[:n1]
+
+
+def ref_search_by_projection(mp, kp, kdesc, scale_factors, bounds, nnratio=0.8, th=1.0, kp_mp=None, kp_mp_obs=None):
+    nmp, n = len(mp["x"]), len(kp)
+    kx, ky, ko = _f(kp["x"]), _f(kp["y"]), _i(kp["octave"])
+    kur = _f(mp.get("kuright", np.full(n, -1.0, np.float32)))
+    kdesc = _b(kdesc)
+    kp_mp = np.full(max(n, 1), -1, np.int32) if kp_mp is None else _i(kp_mp).copy()
+    kp_mp_obs = np.zeros(max(n, 1), np.int32) if kp_mp_obs is None else _i(kp_mp_obs)
+    iv, bad = _b(mp["in_view"]), _b(mp["bad"])
+    x, y, xr, lv, vc = _f(mp["x"]), _f(mp["y"]), _f(mp["xr"]), _i(mp["level"]), _f(mp["viewcos"])
+    de, ob = _b(mp["desc"]), _i(mp["obs"])
+    sf, bnd = _f(scale_factors), _f(bounds).reshape(4)
+    cnt = mlib().refm_search_by_projection(
+        nmp, _p(iv, _u8p), _p(bad, _u8p), _p(x, _f32p), _p(y, _f32p), _p(xr, _f32p), _p(lv, _i32p), _p(vc, _f32p),
+        _p(de, _u8p), _p(ob, _i32p), n, _p(kx, _f32p), _p(ky, _f32p), _p(ko, _i32p), _p(kur, _f32p), _p(kdesc, _u8p),
+        _p(kp_mp, _i32p), _p(kp_mp_obs, _i32p), len(sf), _p(sf, _f32p), _p(bnd, _f32p), nnratio, th)
+    return cnt, kp_mp[:n]

@@ -104,3 +104,80 @@ def test_distribute_octree_matches_reference_under_monotonic_allocator():
         a = O.distribute_octree(c, 16, 16 + w, 16, 16 + h, N)
         b = r.distribute_octree(c, 16, 16 + w, 16, 16 + h, N)
         assert a.tobytes() == b.tobytes(), (trial, w, h, n, N, len(a), len(b))
+
+
+# ---- matcher: oracle/_ref/libref_matcher.so = the reference's own ORBmatcher.cc + Frame.cc + MapPoint.cc ------
+needs_refm = pytest.mark.skipif(not R.matcher_available(), reason="oracle/_ref/libref_matcher.so not built")
+MGOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_match_*.npz")))
+
+
+@needs_refm
+def test_descriptor_distance_matches_reference():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (500, 32)).astype(np.uint8)
+    b = rng.integers(0, 256, (500, 32)).astype(np.uint8)
+    b[:5] = a[:5]; b[5:10] = ~a[5:10]
+    for i in range(500):
+        assert O.descriptor_distance(a[i], b[i]) == R.ref_descriptor_distance(a[i], b[i])
+
+
+@needs_refm
+@pytest.mark.parametrize("brute,window,n,ori", [(False, 100, 1000, True), (True, 1000, 1000, True), (False, 10, 700, True),
+                                                 (True, 40, 333, False), (False, 100, 1, True), (False, 60, 0, True)])
+def test_search_for_initialization_matches_reference(brute, window, n, ori):
+    from weiner_slamit_v2_b200.workloads import init_pair
+    for idx in range(3):
+        p = init_pair(200 + idx, n=max(n, 1), brute_force=brute)
+        if n == 0:
+            p = tuple(x[:0] for x in p)
+        for bounds in ((0, 0, 640, 480), (-13.7, -9.2, 661.3, 492.8)):
+            a = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], bounds, 0.9, ori, window)
+            b = R.ref_search_for_initialization(p[0], p[1], p[2], p[3], p[4], bounds, 0.9, ori, window)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+            # second round from the updated vbPrevMatched, as MonocularInitialization does
+            a2 = O.search_for_initialization(p[0], p[1], p[2], p[3], a[2], bounds, 0.9, ori, window)
+            b2 = R.ref_search_for_initialization(p[0], p[1], p[2], p[3], b[2], bounds, 0.9, ori, window)
+            assert a2[0] == b2[0] and np.array_equal(a2[1], b2[1]) and np.array_equal(a2[2], b2[2])
+
+
+@needs_refm
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0])
+def test_search_by_projection_matches_reference(th):
+    from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, projection_frame
+    for idx, (w, h) in enumerate(((1280, 720), (640, 480))):
+        kp, kd, mp = projection_frame(300 + idx, 2000, 4000, w, h)
+        rng = np.random.default_rng(idx)
+        pre = np.full(2000, -1, np.int32); obs = np.zeros(2000, np.int32)
+        ii = rng.choice(2000, 150, replace=False)
+        pre[ii] = -2; obs[ii] = rng.integers(0, 3, 150)
+        pre[rng.choice(2000, 50, replace=False)] = rng.integers(0, 4000, 50)     # some already hold listed map points
+        ur = np.where(rng.random(2000) < 0.3, kp["x"] - rng.uniform(0, 30, 2000), -1).astype(np.float32)
+        mp["kuright"] = ur
+        mp["xr"] = (mp["x"] - rng.uniform(0, 30, 4000)).astype(np.float32)
+        a = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, (0, 0, w, h), 0.8, th, pre, obs)
+        b = R.ref_search_by_projection(mp, kp, kd, SCALE_FACTORS_8, (0, 0, w, h), 0.8, th, pre, obs)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("path", MGOLDEN, ids=[os.path.basename(p) for p in MGOLDEN])
+def test_matcher_oracle_reproduces_reference_golden_vectors(path):
+    """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
+    from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
+    g = np.load(path)
+    if "init" in os.path.basename(path):
+        for i in range(int(g["count"])):
+            idx, n, brute, window = (int(v) for v in g["cfg_%d" % i])
+            p = init_pair(idx, n=n, brute_force=bool(brute))
+            a = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], (0, 0, 640, 480), 0.9, True, window)
+            assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["m12_%d" % i]) and np.array_equal(a[2], g["prev_%d" % i])
+    else:
+        for i in range(int(g["count"])):
+            idx, nk, nmp = (int(v) for v in g["cfg_%d" % i][:3])
+            th = float(g["cfg_%d" % i][3])
+            kp, kd, mp = projection_frame(idx, nk, nmp)
+            a = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, (0, 0, 1280, 720), 0.8, th)
+            assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["kpmp_%d" % i])
+
+
+def test_matcher_golden_vectors_exist():
+    assert len(MGOLDEN) >= 2

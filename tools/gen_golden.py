@@ -45,3 +45,27 @@ dump("ref_extract_lowcontrast.npz", (1000, 1.2, 8, 20, 7), [low_contrast_frame(i
      ["low_contrast_frame", "640", "480", "0", "1"])
 dump("ref_extract_752x480_n500_s1.5_l5.npz", (500, 1.5, 5, 25, 9), [synthetic_frame(40 + i, 752, 480) for i in range(2)],
      ["synthetic_frame", "752", "480", "40", "41"])
+
+# ---- matcher vectors from the reference's own ORBmatcher.cc (oracle/_ref/libref_matcher.so) ----
+assert R.matcher_available(), "build oracle/_ref/libref_matcher.so first (make -C oracle refm)"
+from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame  # noqa: E402
+
+out = {}
+cfgs = [(400, 1000, 0, 100), (401, 1000, 1, 1000), (402, 600, 0, 30), (403, 250, 1, 50)]
+for i, (idx, n, brute, window) in enumerate(cfgs):
+    p = init_pair(idx, n=n, brute_force=bool(brute))
+    r = R.ref_search_for_initialization(p[0], p[1], p[2], p[3], p[4], (0, 0, 640, 480), 0.9, True, window)
+    out["cfg_%d" % i] = np.array([idx, n, brute, window]); out["n_%d" % i] = r[0]; out["m12_%d" % i] = r[1]; out["prev_%d" % i] = r[2]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_init.npz"), **out)
+print("ref_match_init.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+cfgs = [(500, 2000, 10000, 1.0), (501, 2000, 6000, 3.0), (502, 800, 3000, 5.0)]
+for i, (idx, nk, nmp, th) in enumerate(cfgs):
+    kp, kd, mp = projection_frame(idx, nk, nmp)
+    r = R.ref_search_by_projection(mp, kp, kd, SCALE_FACTORS_8, (0, 0, 1280, 720), 0.8, th)
+    out["cfg_%d" % i] = np.array([idx, nk, nmp, th]); out["n_%d" % i] = r[0]; out["kpmp_%d" % i] = r[1]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_proj.npz"), **out)
+print("ref_match_proj.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
