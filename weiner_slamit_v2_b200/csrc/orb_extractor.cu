@@ -103,7 +103,7 @@ enum { STATUS_QT_RUNAWAY = 1, STATUS_CAND_OVERFLOW = 2, STATUS_KP_OVERFLOW = 4 }
 // byte lanes).  A source row shared by two consecutive destination rows is computed once.  The
 // vertical blend ((b*(r>>4))>>16 twice, +2, >>2) is two IMAD.HI per pixel.
 // Columns w..w+3 are written too: they hold the REFLECT_101 continuation that k_blur reads.
-constexpr int RZ_ROWS = 16, RZ_WARPS = 4;
+constexpr int RZ_ROWS = 8, RZ_WARPS = 4;
 
 __device__ __forceinline__ void resize_hrow(const uint8_t* row, int a, bool ld1, bool ld2, uint32_t selShift,
                                             const uint32_t (&sel)[4], const uint32_t (&coef)[4], uint32_t (&r)[4])
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
 // FAST_TPW / FAST_TH are compile-time so every ring load is `base + immediate`:
 //   <24,42> covers cells up to 39 x 36 px (every level of the 640x480 ... 1920x1080 pyramids),
 //   <36,64> covers the largest possible cell (57 x 57).
-constexpr int FAST_WARPS = 4;     // cells per CTA; the warps of a CTA never synchronise with each other
+constexpr int FAST_WARPS = 2;     // cells per CTA; the warps of a CTA never synchronise with each other
 
 template <int TPW, int TH>
 struct FastGeo {
