@@ -170,6 +170,7 @@ struct InitParams {
     int* nmatches;            // items
     uint4* topk;              // items x f1.stride: the 4 best candidates of every query, key = dist << 20 | CSR position
     int* topkCount;           // items x f1.stride: number of candidates that passed the static tests
+    uint4* topkIdx;           // items x f1.stride: F2 keypoint index of each of the 4 entries
     int items, window, checkOri;
     float nnratio;
 };
@@ -254,6 +255,13 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
     if (q < n1) {
         P.topk[(size_t)item * P.f1.stride + q] = best;
         P.topkCount[(size_t)item * P.f1.stride + q] = active ? count : -1;
+        if (active && count > 0) {
+            const uint32_t k[4] = {best.x, best.y, best.z, best.w};
+            uint32_t id[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) id[j] = j < count ? (uint32_t)ci[k[j] & 0xfffffu] : 0u;
+            P.topkIdx[(size_t)item * P.f1.stride + q] = make_uint4(id[0], id[1], id[2], id[3]);
+        }
     }
 }
 
@@ -274,22 +282,38 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
     const uint4* d2 = reinterpret_cast<const uint4*>(P.f2.desc + (size_t)item * P.f2.stride * 32);
     const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
     const int* ci = P.cellItems + (size_t)item * P.f2.stride;
-    int* vmd = P.matchedDist + (size_t)item * P.f2.stride;
     int* m21 = P.matches21 + (size_t)item * P.f2.stride;
     int* hbin = P.histBin + (size_t)item * P.f1.stride;
     float* prev = P.prevMatched + (size_t)item * P.f1.stride * 2;
     int* m12 = P.matches12 + (size_t)item * P.f1.stride;
 
-    for (int i = lane; i < n2; i += 32) { vmd[i] = INT_MAX; m21[i] = -1; }
+    // vMatchedDistance (:419) lives in shared memory as 16 bits (0xffff = INT_MAX; real values are <= TH_LOW)
+    extern __shared__ uint16_t s_vmd_all[];
+    uint16_t* vmd = s_vmd_all + (size_t)(threadIdx.x >> 5) * ((P.f2.stride + 7) & ~7);
+    for (int i = lane; i < n2; i += 32) { vmd[i] = 0xffff; m21[i] = -1; }
     for (int i = lane; i < n1; i += 32) { m12[i] = -1; hbin[i] = -1; }
     __syncwarp();
 
     const float r = (float)P.window;
     const uint4* topk = P.topk + (size_t)item * P.f1.stride;
+    const uint4* topkIdx = P.topkIdx + (size_t)item * P.f1.stride;
     const int* topkCount = P.topkCount + (size_t)item * P.f1.stride;
-    for (int i1 = 0; i1 < n1; i1++) {
-        const int cnt = topkCount[i1];
+    // lane j loads the list of query base + j (coalesced, one latency per 32 queries); the warp then walks the
+    // queries in order, broadcasting each list by shuffle
+    for (int base = 0; base < n1; base += 32) {
+      const int mine = base + lane;
+      int cntL = -1;
+      uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
+      if (mine < n1) { cntL = topkCount[mine]; kkL = topk[mine]; idL = topkIdx[mine]; }
+      const int jEnd = min(32, n1 - base);
+      for (int jq = 0; jq < jEnd; jq++) {
+        const int i1 = base + jq;
+        const int cnt = __shfl_sync(0xffffffffu, cntL, jq);
         if (cnt <= 0) continue;            // octave > 0 (:425-427), query outside the grid, or no candidate (:431)
+        const uint4 kk = make_uint4(__shfl_sync(0xffffffffu, kkL.x, jq), __shfl_sync(0xffffffffu, kkL.y, jq),
+                                    __shfl_sync(0xffffffffu, kkL.z, jq), __shfl_sync(0xffffffffu, kkL.w, jq));
+        const uint4 idv = make_uint4(__shfl_sync(0xffffffffu, idL.x, jq), __shfl_sync(0xffffffffu, idL.y, jq),
+                                     __shfl_sync(0xffffffffu, idL.z, jq), __shfl_sync(0xffffffffu, idL.w, jq));
         const int level1 = oct1[i1];
         Top2 t = {INT_MAX, INT_MAX, -1, INT_MAX, INT_MAX, -1};
         // Fast path (every lane redundantly): walk the query's 4 best static candidates in visiting order and
@@ -298,14 +322,14 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
         // when the best survivor already fails TH_LOW; otherwise fall back to the full scan below.
         bool resolved;
         {
-            const uint4 kk = topk[i1];
             const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+            const uint32_t kid[4] = {idv.x, idv.y, idv.z, idv.w};
             int found = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (found < 2 && j < cnt) {
                     const int dist = (int)(key[j] >> 20), pos = (int)(key[j] & 0xfffffu);
-                    if (!(vmd[ci[pos]] <= dist)) {
+                    if (!((int)vmd[kid[j]] <= dist)) {
                         if (found == 0) { t.b = dist; t.bp = pos; } else { t.s = dist; t.sp = pos; }
                         found++;
                     }
@@ -337,7 +361,7 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
                     if (o2 < level1 || (level1 >= 0 && o2 > level1)) continue;
                     if (!(fabsf(__fsub_rn(k2x[i2], qx)) < r && fabsf(__fsub_rn(k2y[i2], qy)) < r)) continue;
                     const int dist = hamming256(a0, a1, __ldg(d2 + 2 * i2), __ldg(d2 + 2 * i2 + 1));
-                    if (vmd[i2] <= dist) continue;                                     // :448
+                    if ((int)vmd[i2] <= dist) continue;                                // :448
                     top2_push(t, dist, p, 0);
                 }
             }
@@ -350,7 +374,7 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
                 if (old >= 0) m12[old] = -1;                                         // :467-471
                 m12[i1] = best2;
                 m21[best2] = i1;
-                vmd[best2] = t.b;
+                vmd[best2] = (uint16_t)t.b;
                 if (P.checkOri) {
                     float rot = __fsub_rn(ang1[i1], ang2[best2]);
                     if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
@@ -361,6 +385,7 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
             }
         }
         __syncwarp();
+      }
     }
     // The running count (nmatches++ / nmatches-- at :470,:475) equals the number of live entries of
     // vnMatches12 at this point; recount instead of tracking the decrements.
@@ -428,6 +453,7 @@ struct ProjParams {
     int* nmatches;
     uint4* topk;               // items x mpStride: 4 best static candidates, key = dist << 23 | CSR position << 5 | octave
     int* topkCount;            // items x mpStride
+    uint4* topkIdx;            // items x mpStride: keypoint index of each of the 4 entries (saves the cellItems hop in phase B)
     int items;
     float nnratio, th;
 };
@@ -444,6 +470,7 @@ __global__ void __launch_bounds__(128) k_proj_topk(const ProjParams P)
     if (i >= nmp) return;
     const size_t mo = (size_t)item * P.mpStride;
     uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    const int* ciw = P.cellItems + (size_t)item * P.f.stride;
     int count = -1;
     if (P.mpInView[mo + i] && !P.mpBad[mo + i]) {                                    // :56-60
         const float* kx = P.f.x + (size_t)item * P.f.stride;
@@ -495,6 +522,13 @@ __global__ void __launch_bounds__(128) k_proj_topk(const ProjParams P)
     }
     P.topk[mo + i] = best;
     P.topkCount[mo + i] = count;
+    if (count > 0) {
+        const uint32_t k[4] = {best.x, best.y, best.z, best.w};
+        uint32_t id[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) id[j] = j < count ? (uint32_t)ciw[(k[j] >> 5) & 0x3ffffu] : 0u;
+        P.topkIdx[mo + i] = make_uint4(id[0], id[1], id[2], id[3]);
+    }
 }
 
 // ---- SearchByProjection, phase B: the greedy pass, one warp per frame --------------------------
@@ -515,31 +549,52 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
     const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
     const size_t mo = (size_t)item * P.mpStride;
     const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + mo * 32);
-    (void)n;
+    // occupancy of every keypoint (holds a map point with observations -> skipped, :89-91) as one byte in shared
+    // memory: the greedy state is read several times per map point and must not cost a global round trip
+    extern __shared__ uint8_t s_occ_all[];
+    uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * ((P.f.stride + 15) & ~15);
+    for (int idx = lane; idx < n; idx += 32) {
+        const int held = kpmp[idx];
+        occ[idx] = held != -1 && (held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0)) > 0;
+    }
+    __syncwarp();
 
     int nmatches = 0;
     const bool bFactor = P.th != 1.0f;
     const uint4* topk = P.topk + mo;
+    const uint4* topkIdx = P.topkIdx + mo;
     const int* topkCount = P.topkCount + mo;
-    for (int i = 0; i < nmp; i++) {
-        const int cnt = topkCount[i];
+    // The per-map-point lists do not depend on the greedy state: lane j loads the list of map point base + j
+    // (coalesced, one memory latency per 32 map points) and the warp walks them in order by shuffle.
+    for (int base = 0; base < nmp; base += 32) {
+      const int mine = base + lane;
+      int cntL = -1, obsL = 0;
+      uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
+      if (mine < nmp) { cntL = topkCount[mine]; kkL = topk[mine]; idL = topkIdx[mine]; obsL = P.mpObs[mo + mine]; }
+      const int jEnd = min(32, nmp - base);
+      for (int j = 0; j < jEnd; j++) {
+        const int i = base + j;
+        const int cnt = __shfl_sync(0xffffffffu, cntL, j);
         if (cnt <= 0) continue;          // not in view / bad (:56-60), outside the grid, or no candidate (:73)
+        const uint4 kk = make_uint4(__shfl_sync(0xffffffffu, kkL.x, j), __shfl_sync(0xffffffffu, kkL.y, j),
+                                    __shfl_sync(0xffffffffu, kkL.z, j), __shfl_sync(0xffffffffu, kkL.w, j));
+        const uint4 idv = make_uint4(__shfl_sync(0xffffffffu, idL.x, j), __shfl_sync(0xffffffffu, idL.y, j),
+                                     __shfl_sync(0xffffffffu, idL.z, j), __shfl_sync(0xffffffffu, idL.w, j));
+        const int obsI = __shfl_sync(0xffffffffu, obsL, j);
         Top2 t = {256, INT_MAX, -1, 256, INT_MAX, -1};
         // Fast path (every lane redundantly): the map point's 4 best static candidates in visiting order,
         // minus the keypoints that were taken since (:89-91).  Conclusive when two survive, when the list
         // holds every candidate, or when nothing within TH_HIGH can survive; otherwise the full scan below.
         bool resolved;
         {
-            const uint4 kk = topk[i];
             const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+            const uint32_t kid[4] = {idv.x, idv.y, idv.z, idv.w};
             int found = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (found < 2 && j < cnt) {
                     const int dist = (int)(key[j] >> 23), pos = (int)((key[j] >> 5) & 0x3ffffu), o = (int)(key[j] & 31u);
-                    bool taken = false;
-                    const int held = kpmp[ci[pos]];
-                    if (held != -1) taken = (held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[ci[pos]] : 0)) > 0;
+                    const bool taken = occ[kid[j]] != 0;
                     if (!taken && dist < 256) {
                         if (found == 0) { t.b = dist; t.bp = pos; t.ba = o; } else { t.s = dist; t.sp = pos; t.sa = o; }
                         found++;
@@ -572,11 +627,7 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
                         if (maxLevel >= 0 && o > maxLevel) continue;
                     }
                     if (!(fabsf(__fsub_rn(kx[idx], qx)) < rs && fabsf(__fsub_rn(ky[idx], qy)) < rs)) continue;
-                    const int held = kpmp[idx];                                          // :89-91
-                    if (held != -1) {
-                        const int obs = held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0);
-                        if (obs > 0) continue;
-                    }
+                    if (occ[idx]) continue;                                              // :89-91
                     if (ur && ur[idx] > 0) {                                            // :93-98
                         const float er = fabsf(__fsub_rn(qxr, ur[idx]));
                         if (er > rs) continue;
@@ -588,10 +639,15 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
             t = top2_warp_reduce(t);
         }
         if (t.b <= TH_HIGH && !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s))) {   // :120-127
-            if (lane == 0) kpmp[ci[t.bp]] = i;
+            if (lane == 0) {
+                const int bestIdx = ci[t.bp];
+                kpmp[bestIdx] = i;                                                   // :125
+                occ[bestIdx] = obsI > 0;
+            }
             nmatches++;
         }
         __syncwarp();
+      }
     }
     if (lane == 0) P.nmatches[item] = nmatches;
 }
@@ -607,7 +663,7 @@ struct orbb200_matcher {
     int maxItems, maxPoints, device, lastLaunches;
     cudaStream_t stream;
     int *cellStart, *cellItems, *scratchA, *scratchB, *scratchC, *topkCount;
-    uint4* topk;
+    uint4 *topk, *topkIdx;
     std::vector<void*> allocs;
     // staging for host-pointer calls
     uint8_t* stage; size_t stageBytes;
@@ -639,6 +695,7 @@ extern "C" int orbb200_matcher_create(int max_items, int max_points, int device,
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchC, sizeof(int) * np);
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->topk, sizeof(uint4) * np);
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->topkCount, sizeof(int) * np);
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->topkIdx, sizeof(uint4) * np);
     if (rc == ORBB200_OK && cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed"); rc = ORBB200_ECUDA;
     }
@@ -792,14 +849,19 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.matchedDist = m->scratchA; P.matches21 = m->scratchB; P.histBin = m->scratchC;
     P.prevMatched = dPrev; P.matches12 = dM12; P.nmatches = dN;
-    P.topk = m->topk; P.topkCount = m->topkCount;
+    P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx;
     P.items = items; P.window = window_size; P.checkOri = check_orientation; P.nnratio = nnratio;
     // scratch strides follow the views
     k_build_grid<<<items, 256, 0, st>>>(P.f2, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");
     k_init_topk<<<dim3((f1->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_init_topk");
-    k_search_init<<<(items + 3) / 4, 128, 0, st>>>(P);
+    {
+        const size_t sm = 4 * sizeof(uint16_t) * (size_t)((f2->stride + 7) & ~7);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
+        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_search_init<<<(items + 3) / 4, 128, sm, st>>>(P);
+    }
     ORB_CHECK_LAUNCH("k_search_init");
     m->lastLaunches = 3;
     if (!on_device) {
@@ -852,12 +914,17 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
     }
     P.mpStride = mp->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.nlevels = nlevels; P.nmatches = dN; P.items = items; P.nnratio = nnratio; P.th = th;
-    P.topk = m->topk; P.topkCount = m->topkCount;
+    P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx;
     k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");
     k_proj_topk<<<dim3((mp->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_proj_topk");
-    k_search_proj<<<(items + 3) / 4, 128, 0, st>>>(P);
+    {
+        const size_t sm = 4 * (size_t)((f->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_search_proj<<<(items + 3) / 4, 128, sm, st>>>(P);
+    }
     ORB_CHECK_LAUNCH("k_search_proj");
     m->lastLaunches = 3;
     if (!on_device) {
