@@ -173,6 +173,27 @@ int orbb200_search_by_projection(orbb200_matcher *m, int items, const orbb200_fr
                                  const int32_t *kp_mp_obs, const float *scale_factors, int nlevels,
                                  const float bounds[4], float nnratio, float th, int32_t *nmatches, int on_device);
 
+/* ------------------------------------------------------------------------------------- */
+/* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
+/* ------------------------------------------------------------------------------------- */
+/* K = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2, k3} (Frame::mK, Frame::mDistCoef as float).
+ * All three run on the matcher handle's stream. */
+
+/* Replaces Frame::UndistortKeyPoints (S/Frame.cc:529-559) for a batch that is still on the DEVICE: reads the
+ * extractor's cv::KeyPoint records (items x cap, counts per item) and writes the undistorted keypoints as
+ * structure-of-arrays (items x cap each) -- exactly the arrays an orbb200_frame_view with stride = cap wants;
+ * the descriptors are the extractor's descriptor output as is.  Asynchronous. */
+int orbb200_frames_from_keypoints(orbb200_matcher *m, const orbb200_keypoint *d_keypoints, const int32_t *d_counts,
+                                  int items, int cap, const float K[4], const float dist[5], float *d_x, float *d_y,
+                                  int32_t *d_octave, float *d_angle);
+/* cv::undistortPoints(src, dst, K, dist, Mat(), K) for n points in HOST memory (xy interleaved). */
+int orbb200_undistort_points(orbb200_matcher *m, const float *xy_in, float *xy_out, int n, const float K[4], const float dist[5]);
+/* Replaces Frame::ComputeImageBounds (S/Frame.cc:561-589): bounds = {mnMinX, mnMinY, mnMaxX, mnMaxY}. */
+int orbb200_image_bounds(orbb200_matcher *m, int cols, int rows, const float K[4], const float dist[5], float bounds[4]);
+/* Makes the matcher's stream wait (on the device, no host synchronisation) for everything queued so far on
+ * the extractor's stream: extract_device -> frames_from_keypoints -> search_*(on_device) is one pipeline. */
+int orbb200_matcher_wait_extractor(orbb200_matcher *m, orbb200_extractor *ex);
+
 #ifdef __cplusplus
 }
 #endif

@@ -264,3 +264,58 @@ int orc_search_by_projection(
     free(cand); free(items);
     return nmatches;
 }
+
+/* ======================================================================================= */
+/* Frame glue ("next" row N1): UndistortKeyPoints (S/Frame.cc:529-559) and ComputeImageBounds */
+/* (S/Frame.cc:561-589), i.e. cv::undistortPoints(src, dst, K, distCoef, Mat(), K).           */
+/* ======================================================================================= */
+/* OpenCV's iterative inverse of the plumb-bob model, 5 fixed iterations, everything in double:
+ *   x0 = (u - cx)/fx, y0 = (v - cy)/fy;  repeat 5x:  r2 = x*x + y*y,
+ *   icdist = (1 + ((k6*r2 + k5)*r2 + k4)*r2) / (1 + ((k3*r2 + k2)*r2 + k1)*r2),
+ *   dX = 2*p1*x*y + p2*(r2 + 2*x*x), dY = p1*(r2 + 2*y*y) + 2*p2*x*y,
+ *   x = (x0 - dX)*icdist, y = (y0 - dY)*icdist;
+ * then re-projected with P = K.  k[] = {k1, k2, p1, p2, k3}; K and k are float matrices in the
+ * reference (Tracking.cc:77-112) and are widened to double like OpenCV does.  Pinned bit-exactly
+ * against cv2.undistortPoints in tests/test_oracle_primitives.py. */
+void orc_undistort_points(int n, const float *xy_in, float *xy_out, const float K[4], const float dist[5])
+{
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double k1 = dist[0], k2 = dist[1], p1 = dist[2], p2 = dist[3], k3 = dist[4];
+    for (int i = 0; i < n; i++) {
+        double x = xy_in[2 * i], y = xy_in[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx;
+        y = (y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0 * r2 + 0) * r2 + 0) * r2) / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+            const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        /* P = K, R = identity: xx = fx*x + 0*y + cx, ww = 1/(0*x + 0*y + 1) */
+        const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy;
+        const double ww = 1. / (0 * x + 0 * y + 1);
+        xy_out[2 * i] = (float)(xx * ww);
+        xy_out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+/* Frame::ComputeImageBounds (S/Frame.cc:561-589): bounds[4] = {mnMinX, mnMinY, mnMaxX, mnMaxY}. */
+void orc_image_bounds(int cols, int rows, const float K[4], const float dist[5], float bounds[4])
+{
+    if (dist[0] != 0.0f) {
+        float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows}, o[8];
+        orc_undistort_points(4, c, o, K, dist);
+        bounds[0] = o[0] < o[4] ? o[0] : o[4];     /* min(mat(0,0), mat(2,0)) */
+        bounds[2] = o[2] > o[6] ? o[2] : o[6];     /* max(mat(1,0), mat(3,0)) */
+        bounds[1] = o[1] < o[3] ? o[1] : o[3];     /* min(mat(0,1), mat(1,1)) */
+        bounds[3] = o[5] > o[7] ? o[5] : o[7];     /* max(mat(2,1), mat(3,1)) */
+    } else {
+        bounds[0] = 0.0f; bounds[2] = (float)cols; bounds[1] = 0.0f; bounds[3] = (float)rows;
+    }
+}

@@ -120,6 +120,11 @@ int orc_search_by_projection(
     int32_t *kp_mp, const int32_t *kp_mp_obs,
     int nlevels, const float *scale_factors, const float bounds[4], float nnratio, float th);
 
+/* Frame glue: cv::undistortPoints(src, dst, K, dist, Mat(), K) as Frame::UndistortKeyPoints
+ * calls it (S/Frame.cc:529-559), K = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2, k3}; and ComputeImageBounds. */
+void orc_undistort_points(int n, const float *xy_in, float *xy_out, const float K[4], const float dist[5]);
+void orc_image_bounds(int cols, int rows, const float K[4], const float dist[5], float bounds[4]);
+
 #ifdef __cplusplus
 }
 #endif

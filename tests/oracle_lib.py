@@ -265,3 +265,23 @@ def search_by_projection(mp, kp, kdesc, scale_factors, bounds, nnratio=0.8, th=1
         _ptr(kp_mp, _i32p), _ptr(kp_mp_obs, _i32p),
         len(sf), _ptr(sf, _f32p), _ptr(bnd, _f32p), nnratio, th)
     return cnt, kp_mp[:n]
+
+
+# ---- frame glue ---------------------------------------------------------------------------
+def undistort_points(xy, K, dist):
+    L = lib()
+    L.orc_undistort_points.argtypes = [C.c_int, _f32p, _f32p, _f32p, _f32p]
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    K = np.ascontiguousarray(K, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros_like(xy)
+    L.orc_undistort_points(len(xy), _ptr(xy, _f32p), _ptr(out, _f32p), _ptr(K, _f32p), _ptr(dist, _f32p))
+    return out
+
+
+def image_bounds(cols, rows, K, dist):
+    L = lib()
+    L.orc_image_bounds.argtypes = [C.c_int, C.c_int, _f32p, _f32p, _f32p]
+    K = np.ascontiguousarray(K, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    b = np.zeros(4, np.float32)
+    L.orc_image_bounds(cols, rows, _ptr(K, _f32p), _ptr(dist, _f32p), _ptr(b, _f32p))
+    return b

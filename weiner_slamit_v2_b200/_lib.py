@@ -66,6 +66,10 @@ SIGNATURES = {
                                                     C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int]),
     "orbb200_search_by_projection": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), vp, C.POINTER(MapPointView), vp, vp,
                                                vp, C.c_int, vp, C.c_float, C.c_float, vp, C.c_int]),
+    "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
+    "orbb200_matcher_wait_extractor": (C.c_int, [vp, vp]),
 }
 
 _lib = None

@@ -177,3 +177,18 @@ class ORBmatcher:
             f.mvpMapPoints[:] = kpmp[i, :f.N]
         return nm
 
+
+    # ---- Frame glue: Frame::UndistortKeyPoints / ComputeImageBounds on the device ----
+    def undistort_points(self, xy, K, dist):
+        """cv::undistortPoints(src, dst, K, dist, Mat(), K) for an (n, 2) float32 array."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        K = np.ascontiguousarray(K, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+        out = np.zeros_like(xy)
+        check(self._L.orbb200_undistort_points(self._h, xy.ctypes.data, out.ctypes.data, len(xy), K.ctypes.data, dist.ctypes.data))
+        return out
+
+    def image_bounds(self, cols, rows, K, dist):
+        K = np.ascontiguousarray(K, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+        b = np.zeros(4, np.float32)
+        check(self._L.orbb200_image_bounds(self._h, cols, rows, K.ctypes.data, dist.ctypes.data, b.ctypes.data))
+        return b
