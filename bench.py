@@ -282,6 +282,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_matching:
             line["matching"] = run_matching(local, max(2, min(args.steps, 5)))
+            line["pipeline"] = run_pipeline(local, max(2, min(args.steps, 5)))
         if world == 1 and not args.no_cpu_baseline:
             threads = _cpu_threads()
             sample = BATCH
@@ -389,6 +390,35 @@ def run_matching(local, steps):
         "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
     L.orbb200_matcher_destroy(h)
     return out
+
+
+def run_pipeline(local, steps):
+    """Device-resident front end: for 128 frame pairs, extract both frames (256 extractions),
+    undistort + SoA + grid, SearchForInitialization -- no host round trip between the stages."""
+    import numpy as np
+    import torch
+    from weiner_slamit_v2_b200.pipeline import InitializationPipeline
+    pairs = 128
+    base = _frames(7, 16)
+    f1 = np.concatenate([base] * (pairs // 16))
+    f2 = np.stack([np.roll(f, (2, 4), (0, 1)) for f in f1])
+    pipe = InitializationPipeline(max_pairs=pairs, device=local)
+    d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+    for _ in range(2):
+        pipe.run(d1, d2, pairs)
+    pipe.sync()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nm, _, _ = pipe.run(d1, d2, pairs)
+    pipe.sync()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    acc = int(nm[:pairs].sum())
+    pipe.close()
+    return {"workload": "128 frame pairs 640x480 (second frame = first shifted by (4,2) px): 2 x extraction, undistort with the "
+                        "reference's camera, grid, SearchForInitialization(window 100, ratio 0.9), all on the device",
+            "ms_per_step": dt * 1e3, "pairs_per_s": pairs / dt, "frames_per_s": 2 * pairs / dt, "accepted_matches": acc}
 
 
 def _traffic(stage):

@@ -117,3 +117,20 @@ int main(void){ float lim=6.2832f; uint32_t ul; memcpy(&ul,&lim,4); long bad=0;
         subprocess.check_call(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", p, "-o", exe,
                                "-L" + O.ORACLE_DIR, "-l:liborb_oracle.so", "-Wl,-rpath," + O.ORACLE_DIR, "-lm"])
         assert int(subprocess.check_output([exe]).strip()) == 0
+
+
+@pytest.mark.parametrize("dist", [[0.262383, -0.953104, -0.005358, 0.002628, 1.163314],     # the reference's camera (Tracking.cc:101-111)
+                                  [0.262383, -0.953104, -0.005358, 0.002628, 0.0], [-0.28, 0.07, 2e-4, 2e-5, 0.0]])
+def test_undistort_points_matches_cv2(dist):
+    K = np.array([526.69, 540.36, 313.07, 238.39], np.float32)
+    d = np.array(dist, np.float32)
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(-50, 700, 20000), rng.uniform(-50, 530, 20000)], 1).astype(np.float32)
+    pts[:4] = [[0, 0], [640, 0], [0, 480], [640, 480]]
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32)
+    dc = d[:4].reshape(4, 1) if d[4] == 0 else d.reshape(5, 1)
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), Km, dc, None, Km).reshape(-1, 2)
+    assert np.array_equal(ref, O.undistort_points(pts, K, d))
+    b = O.image_bounds(640, 480, K, d)
+    assert b[0] == min(ref[0, 0], ref[2, 0]) and b[2] == max(ref[1, 0], ref[3, 0])
+    assert b[1] == min(ref[0, 1], ref[1, 1]) and b[3] == max(ref[2, 1], ref[3, 1])
