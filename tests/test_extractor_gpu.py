@@ -145,3 +145,18 @@ def test_chunked_host_pipeline_batch64_equals_per_frame_results():
     x0, y0, s0 = ex2.get_level_keypoints(0, 0)
     x1, y1, s1 = ex.get_level_keypoints(0, 0)
     assert np.array_equal(x0, x1) and np.array_equal(y0, y1) and np.array_equal(s0, s1)
+
+
+@pytest.mark.parametrize("size", [(641, 479), (646, 486), (500, 375)])
+def test_ragged_frame_sizes(size):
+    """Widths / heights that are not multiples of 4 or 16: the frame goes through the staging slab and the
+    cell grid, tiles and reflected borders all end on ragged boundaries."""
+    w, h = size
+    frames = np.stack([synthetic_frame(300 + i, w, h) for i in range(2)])
+    ex = ORBextractor(*PARAMS, width=w, height=h, max_batch=2)
+    orc = O.OracleExtractor(*PARAMS)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(2):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], do)

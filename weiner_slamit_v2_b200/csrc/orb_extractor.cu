@@ -57,6 +57,7 @@ struct ExtractParams {
     const uint8_t* in;               // level 0 = the caller's frames
     long long inFrameStride;
     int inPitch, inRowBytes;         // inRowBytes: bytes of a level-0 row that may be read as whole aligned words
+    int inPadded;                    // level 0 sits in the staging slab with its REFLECT_101 continuation in columns w..w+3
     uint8_t* pyr;                    // levels 1.. of every frame
     long long pyrFrameBytes;
     uint8_t* blur;                   // blurred levels 0.. of every frame
@@ -90,6 +91,17 @@ __device__ __forceinline__ const uint8_t* level_ptr(const ExtractParams& P, int 
 }
 
 enum { STATUS_QT_RUNAWAY = 1, STATUS_CAND_OVERFLOW = 2, STATUS_KP_OVERFLOW = 4 };
+
+// Level 0 in the padded staging slab: write the REFLECT_101 continuation (columns w..w+3) that k_blur reads,
+// exactly as k_resize does for the other levels.  One thread per (row, frame).
+__global__ void k_pad_level0(uint8_t* base, long long frameStride, int pitch, int w, int h)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    uint8_t* row = base + (long long)blockIdx.y * frameStride + (long long)y * pitch;
+#pragma unroll
+    for (int i = 0; i < 4; i++) row[w + i] = row[w - 2 - i];
+}
 
 // ======================================================================================
 // K1: pyramid level from the previous level (cv::resize INTER_LINEAR, 8UC1; :1157)
@@ -801,7 +813,7 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
         const int x0 = cur.x0 + 4 * lane;
         if (x0 < g.w) {
             uint8_t* dst = P.blur + (long long)cur.frame * P.blurFrameBytes + g.blurOff;
-            const bool left = x0 == 0, rightFix = (cur.l == 0) && (x0 + 4 >= g.w);
+            const bool left = x0 == 0, rightFix = (cur.l == 0) && !P.inPadded && (x0 + 4 >= g.w);
             const int yEnd = min(cur.y0 + BL_ROWS, g.h);
             const uint8_t* sb = ring + stage * BL_STAGE_BYTES + 12 + 4 * lane;      // word holding columns x0-4..x0-1
             int H[7][4];
@@ -1358,6 +1370,13 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
         P.inRowBytes = (int)h->inPitch;
     }
     P.batch = batch; P.in = d_images; P.inPitch = (int)stride; P.inFrameStride = (long long)frame_stride;
+    P.inPadded = 0;
+    if (d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch && h->inPitch >= (size_t)h->width + 4) {
+        k_pad_level0<<<dim3((h->height + 127) / 128, batch), 128, 0, st>>>(const_cast<uint8_t*>(d_images), (long long)frame_stride,
+                                                                            (int)stride, h->width, h->height);
+        ORB_CHECK_LAUNCH("k_pad_level0");
+        P.inPadded = 1;
+    }
     P.outKp = d_kp; P.outDesc = d_desc; P.outCount = d_counts; P.outCap = cap;
     int launches = 0;
     ORB_CUDA(cudaMemsetAsync(P.candCount, 0, sizeof(int) * P.nlevels * batch, st));
