@@ -160,3 +160,36 @@ def test_ragged_frame_sizes(size):
         ko, do = _compare_frame(ex, orc, frames, f)
         assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
         assert np.array_equal(desc[f, :counts[f]], do)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(size=(320, 240), params=(500, 1.2, 8, 20, 7)),        # cells up to 57 px: the <36,64> FAST tile instantiation
+    dict(size=(640, 480), params=(5000, 1.2, 8, 20, 7)),       # quota far above the corner supply on upper levels
+    dict(size=(640, 480), params=(1000, 1.2, 1, 20, 7)),       # a single level
+    dict(size=(640, 480), params=(1500, 1.1, 12, 20, 7)),      # 12 levels, finer scale
+    dict(size=(1280, 720), params=(4000, 1.2, 8, 20, 7)),      # the initialisation extractor of config B (2 x nFeatures)
+    dict(size=(640, 480), params=(1000, 1.2, 8, 7, 20)),       # iniThFAST < minThFAST
+    dict(size=(640, 480), params=(0, 1.2, 8, 20, 7)),          # zero quota: the quadtree still returns the first split
+    dict(size=(752, 480), params=(1000, 2.0, 3, 30, 10)),      # largest supported scale factor
+])
+def test_parameter_corner_cases(cfg):
+    w, h = cfg["size"]
+    p = cfg["params"]
+    frames = np.stack([synthetic_frame(400 + i, w, h) for i in range(2)])
+    ex = ORBextractor(*p, width=w, height=h, max_batch=2)
+    orc = O.OracleExtractor(*p)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(2):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], do)
+
+
+def test_rejected_geometries():
+    from weiner_slamit_v2_b200 import OrbB200Error
+    with pytest.raises(OrbB200Error):
+        ORBextractor(1000, 1.2, 8, 20, 7, width=200, height=150)       # top level narrower than a FAST cell
+    with pytest.raises(OrbB200Error):
+        ORBextractor(1000, 1.2, 2, 20, 7, width=100, height=400)       # aspect ratio rounds to zero quadtree roots
+    with pytest.raises(OrbB200Error):
+        ORBextractor(1000, 2.5, 2, 20, 7)                               # scale factor above 2
