@@ -173,6 +173,33 @@ int orbb200_search_by_projection(orbb200_matcher *m, int items, const orbb200_fr
                                  const int32_t *kp_mp_obs, const float *scale_factors, int nlevels,
                                  const float bounds[4], float nnratio, float th, int32_t *nmatches, int on_device);
 
+/* The last frame as SearchByProjection(CurrentFrame, LastFrame, ...) reads it: items x stride.  has_mp =
+ * LastFrame.mvpMapPoints[i] != NULL, outlier = mvbOutlier[i], world_pos = GetWorldPos() (3 floats), mp_desc =
+ * GetDescriptor(), mp_obs = Observations(), octave = mvKeys[i].octave, angle = mvKeysUn[i].angle. */
+typedef struct {
+    const int32_t *n;
+    const uint8_t *has_mp, *outlier;
+    const float *world_pos;
+    const uint8_t *mp_desc;
+    const int32_t *mp_obs;
+    const int32_t *octave;
+    const float *angle;
+    int stride;
+} orbb200_lastframe_view;
+
+/* Replaces ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono)
+ * (S/ORBmatcher.cc:1332-1474; scope row N2) for `items` independent frame pairs.  Rcw: items x 9 (row major),
+ * tcw: items x 3 = CurrentFrame.mTcw; K = {fx, fy, cx, cy}; mbf = CurrentFrame.mbf.  mode: 0 = neither bForward
+ * nor bBackward (always the case when bMono), 1 = bForward, 2 = bBackward (:1352-1353; the caller evaluates
+ * tlc.z against mb as the reference does).  kp_mp: items x cur.stride in/out = CurrentFrame.mvpMapPoints as an
+ * index into the LAST frame's arrays (-1 none, -2 foreign with kp_mp_obs observations). */
+int orbb200_search_by_projection_last_frame(orbb200_matcher *m, int items, const orbb200_frame_view *cur,
+                                            const float *u_right, const orbb200_lastframe_view *last, const float *Rcw,
+                                            const float *tcw, const float K[4], float mbf, int32_t *kp_mp,
+                                            const int32_t *kp_mp_obs, const float *scale_factors, int nlevels,
+                                            const float bounds[4], float th, int mode, int check_orientation,
+                                            int32_t *nmatches, int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

@@ -64,3 +64,53 @@ void Mat::copyTo(OutputArray dst) const
 }
 
 }  // namespace cv
+
+// ---- the matrix expressions SearchByProjection(CurrentFrame, LastFrame, ...) evaluates: Rcw.t(), -expr,
+// expr*Mat, Mat*Mat, expr+Mat (S/ORBmatcher.cc:1342-1363).  One MatOp that means
+//     m = alpha * op(a) * b + c        (op = transpose when flags & 1; b, c optional)
+// on small CV_32F matrices, with cv::gemm's small-matrix arithmetic: float products and sums in source order
+// (tests/test_oracle_primitives.py pins that against cv2.gemm).
+namespace cv {
+
+MatOp::MatOp() {}
+MatOp::~MatOp() {}
+
+namespace {
+class MiniOp : public MatOp {
+public:
+    void assign(const MatExpr& e, Mat& m, int = -1) const
+    {
+        const Mat& A = e.a;
+        const bool tr = (e.flags & 1) != 0;
+        const int ar = tr ? A.cols : A.rows, ac = tr ? A.rows : A.cols;
+        auto a_at = [&](int r, int c) { return tr ? A.at<float>(c, r) : A.at<float>(r, c); };
+        const float alpha = (float)e.alpha;
+        Mat out;
+        if (e.b.empty()) {
+            out.create(ar, ac, CV_32F);
+            for (int r = 0; r < ar; r++) for (int c = 0; c < ac; c++) out.at<float>(r, c) = alpha * a_at(r, c);
+        } else {
+            const Mat& B = e.b;
+            out.create(ar, B.cols, CV_32F);
+            for (int r = 0; r < ar; r++)
+                for (int c = 0; c < B.cols; c++) {
+                    volatile float t = a_at(r, 0) * B.at<float>(0, c);
+                    for (int k = 1; k < ac; k++) { volatile float p = a_at(r, k) * B.at<float>(k, c); t = t + p; }
+                    volatile float v = alpha == 1.f ? (float)t : alpha * t;
+                    if (!e.c.empty()) v = v + e.c.at<float>(r, c);
+                    out.at<float>(r, c) = v;
+                }
+        }
+        m = out;
+    }
+};
+const MiniOp g_miniOp;
+}  // namespace
+
+MatExpr Mat::t() const { return MatExpr(&g_miniOp, 1, *this); }
+MatExpr operator-(const MatExpr& e) { MatExpr r(e); r.alpha = -r.alpha; return r; }
+MatExpr operator*(const MatExpr& e, const Mat& m) { MatExpr r(e); r.b = m; return r; }
+MatExpr operator*(const Mat& a, const Mat& b) { return MatExpr(&g_miniOp, 0, a, b); }
+MatExpr operator+(const MatExpr& e, const Mat& m) { MatExpr r(e); r.c = m; return r; }
+
+}  // namespace cv

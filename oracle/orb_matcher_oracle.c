@@ -319,3 +319,104 @@ void orc_image_bounds(int cols, int rows, const float K[4], const float dist[5],
         bounds[0] = 0.0f; bounds[2] = (float)cols; bounds[1] = 0.0f; bounds[3] = (float)rows;
     }
 }
+
+/* ======================================================================================= */
+/* "next" row N2: SearchByProjection(CurrentFrame, LastFrame, th, bMono) (S/ORBmatcher.cc:1332-1474) */
+/* ======================================================================================= */
+/* Flattened inputs.  Last frame, per keypoint i: has_mp (mvpMapPoints[i] != NULL), outlier (mvbOutlier[i]),
+ * wpos (GetWorldPos(), 3 floats), mp_desc (GetDescriptor()), mp_obs (Observations()), octave (mvKeys[i].octave),
+ * angle (mvKeysUn[i].angle).  Current frame: Tcw as Rcw (3x3 row-major) and tcw, camera {fx, fy, cx, cy}, mbf,
+ * bounds, scale factors, keypoints, uRight, descriptors, kp_mp in/out (index into the LAST frame's arrays;
+ * -1 none; -2 foreign map point with kp_mp_obs observations).  mode: 0 = window on octave-1..octave+1 (the
+ * monocular case and small baseline motion), 1 = bForward, 2 = bBackward (:1352-1353, decided by the caller
+ * from tlc and mb).  The 3x3 float product follows cv::gemm's small-matrix path: float multiplies and adds
+ * in source order (pinned against cv2.gemm in tests/test_oracle_primitives.py). */
+int orc_search_by_projection_last_frame(
+    int nlast, const uint8_t *has_mp, const uint8_t *outlier, const float *wpos, const uint8_t *mp_desc,
+    const int32_t *mp_obs, const int32_t *last_octave, const float *last_angle,
+    const float Rcw[9], const float tcw[3], const float K[4], float mbf,
+    int n, const float *kx, const float *ky, const int32_t *koct, const float *kang, const float *kuright,
+    const uint8_t *kdesc, int32_t *kp_mp, const int32_t *kp_mp_obs,
+    int nlevels, const float *scale_factors, const float bounds[4], float th, int mode, int check_orientation)
+{
+    (void)nlevels;
+    int nmatches = 0;
+    orc_grid g;
+    int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    int *hist_bin = (int *)malloc(sizeof(int) * (nlast + 1));
+    int *hist_idx = (int *)malloc(sizeof(int) * (nlast + 1));
+    int nhist = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    orc_grid_bounds(&g, bounds);
+    orc_grid_assign(&g, n, kx, ky, koct, items);
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+
+    for (int i = 0; i < nlast; i++) {
+        if (!has_mp[i] || outlier[i]) continue;
+        const float *X = wpos + 3 * (size_t)i;
+        float xc3[3];
+        for (int r = 0; r < 3; r++) {                       /* x3Dc = Rcw*x3Dw + tcw (:1363) */
+            volatile float t = Rcw[3 * r] * X[0];
+            volatile float t1 = Rcw[3 * r + 1] * X[1];
+            volatile float t2 = Rcw[3 * r + 2] * X[2];
+            t = t + t1;
+            t = t + t2;
+            xc3[r] = t + tcw[r];
+        }
+        const float xc = xc3[0], yc = xc3[1];
+        const float invzc = (float)(1.0 / (double)xc3[2]);
+        if (invzc < 0) continue;
+        volatile float u = fx * xc; u = u * invzc; u = u + cx;
+        volatile float v = fy * yc; v = v * invzc; v = v + cy;
+        if (u < bounds[0] || u > bounds[2]) continue;
+        if (v < bounds[1] || v > bounds[3]) continue;
+        const int oct = last_octave[i];
+        const float radius = th * scale_factors[oct];
+        int nc;
+        if (mode == 1) nc = orc_features_in_area(&g, u, v, radius, oct, -1, cand, n);
+        else if (mode == 2) nc = orc_features_in_area(&g, u, v, radius, 0, oct, cand, n);
+        else nc = orc_features_in_area(&g, u, v, radius, oct - 1, oct + 1, cand, n);
+        if (nc == 0) continue;
+        const uint8_t *dm = mp_desc + 32 * (size_t)i;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (kp_mp[i2] != -1) {
+                const int obs = kp_mp[i2] >= 0 ? mp_obs[kp_mp[i2]] : kp_mp_obs[i2];
+                if (obs > 0) continue;
+            }
+            if (kuright[i2] > 0) {
+                volatile float ur = mbf * invzc;
+                ur = u - ur;
+                const float er = fabsf(ur - kuright[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = orc_descriptor_distance(dm, kdesc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            kp_mp[bestIdx2] = i;
+            nmatches++;
+            if (check_orientation) {
+                float rot = last_angle[i] - kang[bestIdx2];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                hist_bin[nhist] = bin; hist_idx[nhist] = bestIdx2; nhist++;
+            }
+        }
+    }
+    if (check_orientation) {
+        int sizes[HISTO_LENGTH] = {0};
+        for (int k = 0; k < nhist; k++) sizes[hist_bin[k]]++;
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            const int b = hist_bin[k];
+            if (b != ind1 && b != ind2 && b != ind3) { kp_mp[hist_idx[k]] = -1; nmatches--; }   /* :1460-1465 */
+        }
+    }
+    free(hist_idx); free(hist_bin); free(cand); free(items);
+    return nmatches;
+}

@@ -120,6 +120,15 @@ int orc_search_by_projection(
     int32_t *kp_mp, const int32_t *kp_mp_obs,
     int nlevels, const float *scale_factors, const float bounds[4], float nnratio, float th);
 
+/* SearchByProjection(CurrentFrame, LastFrame, th, bMono) (S/ORBmatcher.cc:1332-1474); see the .c file */
+int orc_search_by_projection_last_frame(
+    int nlast, const uint8_t *has_mp, const uint8_t *outlier, const float *wpos, const uint8_t *mp_desc,
+    const int32_t *mp_obs, const int32_t *last_octave, const float *last_angle,
+    const float Rcw[9], const float tcw[3], const float K[4], float mbf,
+    int n, const float *kx, const float *ky, const int32_t *koct, const float *kang, const float *kuright,
+    const uint8_t *kdesc, int32_t *kp_mp, const int32_t *kp_mp_obs,
+    int nlevels, const float *scale_factors, const float bounds[4], float th, int mode, int check_orientation);
+
 /* Frame glue: cv::undistortPoints(src, dst, K, dist, Mat(), K) as Frame::UndistortKeyPoints
  * calls it (S/Frame.cc:529-559), K = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2, k3}; and ComputeImageBounds. */
 void orc_undistort_points(int n, const float *xy_in, float *xy_out, const float K[4], const float dist[5]);

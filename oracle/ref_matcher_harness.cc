@@ -123,4 +123,57 @@ int refm_search_by_projection(
     std::free(mps); std::free(foreign);
     return cnt;
 }
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (S/ORBmatcher.cc:1332-1474)
+int refm_search_by_projection_last_frame(
+    int nlast, const uint8_t* has_mp, const uint8_t* outlier, const float* wpos, const uint8_t* mp_desc,
+    const int32_t* mp_obs, const int32_t* last_octave, const float* last_angle,
+    const float* Rcw, const float* tcw, const float* K, float mbf,
+    int n, const float* kx, const float* ky, const int32_t* koct, const float* kang, const float* kuright,
+    const uint8_t* kdesc, int32_t* kp_mp, const int32_t* kp_mp_obs,
+    int nlevels, const float* scale_factors, const float* bounds, float th, int mono, int check_orientation)
+{
+    Frame Cur, Last;
+    fill_frame(Cur, n, kx, ky, koct, kang, kdesc, bounds);
+    for (int i = 0; i < n; i++) Cur.mvuRight[i] = kuright[i];
+    Cur.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+    Frame::fx = K[0]; Frame::fy = K[1]; Frame::cx = K[2]; Frame::cy = K[3];
+    Cur.mbf = mbf; Cur.mb = mbf / K[0];
+    float T[16] = {Rcw[0], Rcw[1], Rcw[2], tcw[0], Rcw[3], Rcw[4], Rcw[5], tcw[1], Rcw[6], Rcw[7], Rcw[8], tcw[2], 0, 0, 0, 1};
+    float Tl[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    Cur.mTcw = cv::Mat(4, 4, CV_32F, T);
+    Last.mTcw = cv::Mat(4, 4, CV_32F, Tl);
+    // last frame: keypoints (octave from mvKeys, angle from mvKeysUn), map points, outlier flags
+    std::vector<float> zx(nlast > 0 ? nlast : 1, 100.f);
+    std::vector<uint8_t> zd((size_t)(nlast > 0 ? nlast : 1) * 32, 0);
+    fill_frame(Last, nlast, &zx[0], &zx[0], last_octave, last_angle, &zd[0], bounds);
+    fill_frame(Cur, n, kx, ky, koct, kang, kdesc, bounds);          // (the grid statics are shared: restore Cur's)
+    for (int i = 0; i < n; i++) Cur.mvuRight[i] = kuright[i];
+    Last.mvbOutlier = std::vector<bool>(nlast, false);
+    MapPoint* mps = (MapPoint*)std::calloc(nlast > 0 ? nlast : 1, sizeof(MapPoint));
+    MapPoint* foreign = (MapPoint*)std::calloc(n > 0 ? n : 1, sizeof(MapPoint));
+    for (int i = 0; i < nlast; i++) {
+        MapPoint* p = &mps[i];
+        new (&p->mDescriptor) cv::Mat(1, 32, CV_8U, (void*)(mp_desc + 32 * (size_t)i));
+        new (&p->mWorldPos) cv::Mat(3, 1, CV_32F, (void*)(wpos + 3 * (size_t)i));
+        p->nObs = mp_obs[i];
+        Last.mvpMapPoints[i] = has_mp[i] ? p : NULL;
+        Last.mvbOutlier[i] = outlier[i] != 0;
+    }
+    for (int i = 0; i < n; i++) {
+        if (kp_mp[i] >= 0) Cur.mvpMapPoints[i] = &mps[kp_mp[i]];
+        else if (kp_mp[i] == -2) { foreign[i].nObs = kp_mp_obs[i]; Cur.mvpMapPoints[i] = &foreign[i]; }
+    }
+    ORBmatcher matcher(0.9f, check_orientation != 0);
+    const int cnt = matcher.SearchByProjection(Cur, Last, th, mono != 0);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = Cur.mvpMapPoints[i];
+        if (!p) kp_mp[i] = -1;
+        else if (p >= mps && p < mps + nlast) kp_mp[i] = (int32_t)(p - mps);
+        else kp_mp[i] = -2;
+    }
+    for (int i = 0; i < nlast; i++) { mps[i].mDescriptor.~Mat(); mps[i].mWorldPos.~Mat(); }
+    std::free(mps); std::free(foreign);
+    return cnt;
+}
 }

@@ -285,3 +285,36 @@ def image_bounds(cols, rows, K, dist):
     b = np.zeros(4, np.float32)
     L.orc_image_bounds(cols, rows, _ptr(K, _f32p), _ptr(dist, _f32p), _ptr(b, _f32p))
     return b
+
+
+def _lastframe_args(w, kp_mp, kp_mp_obs, kuright):
+    cur = w["cur"]
+    n = len(cur)
+    a = dict(has_mp=_b(w["has_mp"]), outlier=_b(w["outlier"]), wpos=_f(w["wpos"]), mp_desc=_b(w["mp_desc"]),
+             mp_obs=_i(w["mp_obs"]), loct=_i(w["last_octave"]), lang=_f(w["last_angle"]), R=_f(w["Rcw"]), t=_f(w["tcw"]),
+             K=_f(w["K"]), kx=_f(cur["x"]), ky=_f(cur["y"]), ko=_i(cur["octave"]), ka=_f(cur["angle"]),
+             kur=_f(np.full(n, -1.0, np.float32) if kuright is None else kuright), kd=_b(w["cdesc"]),
+             kpmp=np.full(max(n, 1), -1, np.int32) if kp_mp is None else _i(kp_mp).copy(),
+             kpobs=np.zeros(max(n, 1), np.int32) if kp_mp_obs is None else _i(kp_mp_obs))
+    return a, n
+
+
+def search_by_projection_last_frame(w, scale_factors, bounds, th=15.0, mode=0, check_ori=True, mbf=40.0,
+                                    kp_mp=None, kp_mp_obs=None, kuright=None, fn=None):
+    """w: workloads.motion_frame() dict.  mode 0 = octave window, 1 = forward, 2 = backward."""
+    L = lib()
+    L.orc_search_by_projection_last_frame.argtypes = [
+        C.c_int, _u8p, _u8p, _f32p, _u8p, _i32p, _i32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
+        C.c_int, _f32p, _f32p, _i32p, _f32p, _f32p, _u8p, _i32p, _i32p,
+        C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int]
+    L.orc_search_by_projection_last_frame.restype = C.c_int
+    a, n = _lastframe_args(w, kp_mp, kp_mp_obs, kuright)
+    sf, bnd = _f(scale_factors), _bounds(bounds)
+    f = fn or L.orc_search_by_projection_last_frame
+    cnt = f(len(a["has_mp"]), _ptr(a["has_mp"], _u8p), _ptr(a["outlier"], _u8p), _ptr(a["wpos"], _f32p),
+            _ptr(a["mp_desc"], _u8p), _ptr(a["mp_obs"], _i32p), _ptr(a["loct"], _i32p), _ptr(a["lang"], _f32p),
+            _ptr(a["R"], _f32p), _ptr(a["t"], _f32p), _ptr(a["K"], _f32p), mbf,
+            n, _ptr(a["kx"], _f32p), _ptr(a["ky"], _f32p), _ptr(a["ko"], _i32p), _ptr(a["ka"], _f32p), _ptr(a["kur"], _f32p),
+            _ptr(a["kd"], _u8p), _ptr(a["kpmp"], _i32p), _ptr(a["kpobs"], _i32p),
+            len(sf), _ptr(sf, _f32p), _ptr(bnd, _f32p), th, mode, int(check_ori))
+    return cnt, a["kpmp"][:n]

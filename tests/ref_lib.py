@@ -160,3 +160,21 @@ def ref_search_by_projection(mp, kp, kdesc, scale_factors, bounds, nnratio=0.8, 
         _p(de, _u8p), _p(ob, _i32p), n, _p(kx, _f32p), _p(ky, _f32p), _p(ko, _i32p), _p(kur, _f32p), _p(kdesc, _u8p),
         _p(kp_mp, _i32p), _p(kp_mp_obs, _i32p), len(sf), _p(sf, _f32p), _p(bnd, _f32p), nnratio, th)
     return cnt, kp_mp[:n]
+
+
+def ref_search_by_projection_last_frame(w, scale_factors, bounds, th=15.0, check_ori=True, mbf=40.0, kp_mp=None,
+                                        kp_mp_obs=None, kuright=None):
+    """The reference's own SearchByProjection(CurrentFrame, LastFrame, th, bMono=true)."""
+    import oracle_lib as O
+    L = mlib()
+    L.refm_search_by_projection_last_frame.argtypes = [
+        C.c_int, _u8p, _u8p, _f32p, _u8p, _i32p, _i32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
+        C.c_int, _f32p, _f32p, _i32p, _f32p, _f32p, _u8p, _i32p, _i32p,
+        C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int]
+    L.refm_search_by_projection_last_frame.restype = C.c_int
+    # same argument order as the oracle; the reference takes bMono where the oracle takes mode (mono <-> mode 0)
+    def call(*args):
+        args = list(args)
+        args[-2] = 1
+        return L.refm_search_by_projection_last_frame(*args)
+    return O.search_by_projection_last_frame(w, scale_factors, bounds, th, 0, check_ori, mbf, kp_mp, kp_mp_obs, kuright, fn=call)

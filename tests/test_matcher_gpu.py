@@ -121,3 +121,30 @@ def test_distorted_image_bounds_shift_the_grid():
     cnt = m.SearchByProjection(f, MapPoints(mp["x"], mp["y"], mp["level"], mp["viewcos"], mp["desc"], mp["in_view"], mp["bad"], mp["xr"], mp["obs"]), 5.0)
     ocnt, okp = O.search_by_projection(mp, kp, kd, SCALE_FACTORS_8, bounds, 0.8, 5.0)
     assert cnt == ocnt and np.array_equal(f.mvpMapPoints, okp)
+
+
+@pytest.mark.parametrize("th,mode,ori", [(15.0, 0, True), (7.0, 0, True), (15.0, 0, False), (15.0, 1, True), (15.0, 2, True), (40.0, 0, True)])
+def test_search_by_projection_last_frame_matches_oracle(th, mode, ori):
+    """Scope row N2: SearchByProjection(CurrentFrame, LastFrame, th, bMono) for a batch of frame pairs."""
+    from weiner_slamit_v2_b200.workloads import motion_frame
+    items = 4
+    ws = [motion_frame(i) for i in range(items)]
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    m = ORBmatcher(0.9, ori, max_items=items, max_points=2000)
+    rng = np.random.default_rng(8)
+    frames, pre = [], []
+    for w in ws:
+        ur = np.where(rng.random(len(w["cur"])) < 0.3, w["cur"]["x"] - rng.uniform(0, 20, len(w["cur"])), -1).astype(np.float32)
+        f = Frame(w["cur"], w["cdesc"], 640, 480, SCALE_FACTORS_8, u_right=ur, bounds=bounds)
+        ii = rng.choice(f.N, 120, replace=False)
+        f.mvpMapPoints[ii[:60]] = -2; f.mvpMapPointObs[ii[:60]] = rng.integers(0, 3, 60)
+        f.mvpMapPoints[ii[60:]] = rng.integers(0, len(w["has_mp"]), 60)
+        frames.append(f); pre.append((f.mvpMapPoints.copy(), f.mvpMapPointObs.copy(), ur))
+    nm = m.search_by_projection_last_frame_batch(frames, ws, th, mode, mbf=40.0)
+    tot = 0
+    for i, w in enumerate(ws):
+        cnt, kpmp = O.search_by_projection_last_frame(w, SCALE_FACTORS_8, bounds, th, mode, ori, 40.0, pre[i][0], pre[i][1], pre[i][2])
+        assert nm[i] == cnt, (i, nm[i], cnt)
+        assert np.array_equal(frames[i].mvpMapPoints, kpmp)
+        tot += cnt
+    assert tot > 200

@@ -134,3 +134,16 @@ def test_undistort_points_matches_cv2(dist):
     b = O.image_bounds(640, 480, K, d)
     assert b[0] == min(ref[0, 0], ref[2, 0]) and b[2] == max(ref[1, 0], ref[3, 0])
     assert b[1] == min(ref[0, 1], ref[1, 1]) and b[3] == max(ref[2, 1], ref[3, 1])
+
+
+def test_small_float_gemm_matches_cv2():
+    """x3Dc = Rcw*x3Dw + tcw (S/ORBmatcher.cc:1363): cv::gemm's small-matrix path = float products and sums in
+    source order; the oracle, oracle/cv341_stubs.cc and the CUDA kernel all use exactly that."""
+    rng = np.random.default_rng(0)
+    f = np.float32
+    for _ in range(5000):
+        Rm = rng.normal(0, 1, (3, 3)).astype(np.float32); x = rng.normal(0, 5, (3, 1)).astype(np.float32)
+        t = rng.normal(0, 2, (3, 1)).astype(np.float32)
+        ref = cv2.gemm(Rm, x, 1.0, t, 1.0)
+        mine = np.array([[f(f(f(Rm[i, 0] * x[0, 0]) + f(Rm[i, 1] * x[1, 0])) + f(Rm[i, 2] * x[2, 0])) + t[i, 0]] for i in range(3)], np.float32)
+        assert np.array_equal(ref, mine)

@@ -181,3 +181,23 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
 
 def test_matcher_golden_vectors_exist():
     assert len(MGOLDEN) >= 2
+
+
+@needs_refm
+@pytest.mark.parametrize("th,ori", [(7.0, True), (15.0, True), (15.0, False)])
+def test_search_by_projection_last_frame_matches_reference(th, ori):
+    """Scope row N2 against the reference's own code (its matrix expressions evaluated by oracle/cv341_stubs.cc,
+    whose float arithmetic is pinned to cv2.gemm in test_oracle_primitives.py)."""
+    from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, motion_frame
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    for idx in range(4):
+        w = motion_frame(600 + idx)
+        rng = np.random.default_rng(idx)
+        n = len(w["cur"])
+        pre = np.full(n, -1, np.int32); obs = np.zeros(n, np.int32)
+        ii = rng.choice(n, 100, replace=False)
+        pre[ii[:50]] = -2; obs[ii[:50]] = rng.integers(0, 3, 50)
+        pre[ii[50:]] = rng.integers(0, len(w["has_mp"]), 50)
+        a = O.search_by_projection_last_frame(w, SCALE_FACTORS_8, bounds, th, 0, ori, 40.0, pre, obs)
+        b = R.ref_search_by_projection_last_frame(w, SCALE_FACTORS_8, bounds, th, ori, 40.0, pre, obs)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])

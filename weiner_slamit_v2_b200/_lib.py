@@ -33,6 +33,11 @@ class MapPointView(C.Structure):
                 ("level", vp), ("view_cos", vp), ("desc", vp), ("obs", vp), ("stride", C.c_int)]
 
 
+class LastFrameView(C.Structure):
+    _fields_ = [("n", vp), ("has_mp", vp), ("outlier", vp), ("world_pos", vp), ("mp_desc", vp), ("mp_obs", vp),
+                ("octave", vp), ("angle", vp), ("stride", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/orb_b200.h declares
 SIGNATURES = {
     "orbb200_last_error": (C.c_char_p, []),
@@ -66,6 +71,9 @@ SIGNATURES = {
                                                     C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int]),
     "orbb200_search_by_projection": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), vp, C.POINTER(MapPointView), vp, vp,
                                                vp, C.c_int, vp, C.c_float, C.c_float, vp, C.c_int]),
+    "orbb200_search_by_projection_last_frame": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), vp, C.POINTER(LastFrameView), vp, vp,
+                                                          vp, C.c_float, vp, vp, vp, C.c_int, vp, C.c_float, C.c_int, C.c_int,
+                                                          vp, C.c_int]),
     "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

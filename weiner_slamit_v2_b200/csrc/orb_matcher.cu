@@ -652,6 +652,263 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
     if (lane == 0) P.nmatches[item] = nmatches;
 }
 
+// =========================================================================================
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono)  (S/ORBmatcher.cc:1332-1474), SURVEY 8(f) N2
+// =========================================================================================
+struct LastParams {
+    FrameDev f;                 // current frame
+    const float* uRight;        // items x f.stride or NULL
+    GridGeo g;
+    const int* cellStart;
+    const int* cellItems;
+    const int* lastN;           // last frame, items x lastStride
+    const uint8_t *hasMp, *outlier;
+    const float* wpos;          // x3
+    const uint8_t* mpDesc;      // x32
+    const int* mpObs;
+    const int* lastOct;
+    const float* lastAng;
+    int lastStride;
+    const float *Rcw, *tcw;     // items x 9, items x 3
+    float fx, fy, cx, cy, mbf, minX, minY, maxX, maxY;
+    int* kpMp;                  // items x f.stride, in/out: index into the last frame's arrays
+    const int* kpMpObs;
+    const float* scaleFactors;
+    int* nmatches;
+    uint4 *topk, *topkIdx;      // items x lastStride
+    int* topkCount;
+    int *histBin, *histIdx;     // items x lastStride scratch
+    int items, mode, checkOri;
+    float th;
+};
+
+struct LastQuery { float u, v, radius, invzc; int minLevel, maxLevel; bool ok; };
+
+// projection of one last-frame map point into the current frame (:1360-1390), float arithmetic in source order
+__device__ __forceinline__ LastQuery last_query(const LastParams& P, int item, int i)
+{
+    LastQuery q;
+    q.ok = false;
+    const size_t lo = (size_t)item * P.lastStride + i;
+    if (!P.hasMp[lo] || P.outlier[lo]) return q;
+    const float* R = P.Rcw + (size_t)item * 9;
+    const float* t = P.tcw + (size_t)item * 3;
+    const float* X = P.wpos + lo * 3;
+    float c3[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        c3[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3 * r], X[0]), __fmul_rn(R[3 * r + 1], X[1])), __fmul_rn(R[3 * r + 2], X[2])), t[r]);
+    q.invzc = (float)__ddiv_rn(1.0, (double)c3[2]);
+    if (q.invzc < 0) return q;
+    q.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), q.invzc), P.cx);
+    q.v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), q.invzc), P.cy);
+    if (q.u < P.minX || q.u > P.maxX || q.v < P.minY || q.v > P.maxY) return q;
+    const int oct = P.lastOct[lo];
+    q.radius = __fmul_rn(P.th, P.scaleFactors[oct]);
+    if (P.mode == 1) { q.minLevel = oct; q.maxLevel = -1; }              // bForward  (:1393)
+    else if (P.mode == 2) { q.minLevel = 0; q.maxLevel = oct; }          // bBackward (:1395)
+    else { q.minLevel = oct - 1; q.maxLevel = oct + 1; }                 // (:1397)
+    q.ok = true;
+    return q;
+}
+
+// static candidate test shared by both phases (GetFeaturesInArea level + window tests, stereo check :1414-1420)
+__device__ __forceinline__ bool last_candidate(const LastParams& P, const LastQuery& q, int idx, const float* kx, const float* ky,
+                                               const int* koct, const float* ur)
+{
+    const int o = koct[idx];
+    if ((q.minLevel > 0) || (q.maxLevel >= 0)) {
+        if (o < q.minLevel) return false;
+        if (q.maxLevel >= 0 && o > q.maxLevel) return false;
+    }
+    if (!(fabsf(__fsub_rn(kx[idx], q.u)) < q.radius && fabsf(__fsub_rn(ky[idx], q.v)) < q.radius)) return false;
+    if (ur && ur[idx] > 0) {
+        const float pr = __fsub_rn(q.u, __fmul_rn(P.mbf, q.invzc));
+        if (fabsf(__fsub_rn(pr, ur[idx])) > q.radius) return false;
+    }
+    return true;
+}
+
+// phase A: one thread per last-frame keypoint
+__global__ void __launch_bounds__(128) k_last_topk(const LastParams P)
+{
+    const int item = blockIdx.y;
+    const int nl = min(P.lastN[item], P.lastStride);
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= nl) return;
+    const size_t lo = (size_t)item * P.lastStride + i;
+    uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    int count = -1;
+    const int* ci = P.cellItems + (size_t)item * P.f.stride;
+    const LastQuery q = last_query(P, item, i);
+    int c0, c1, r0, r1;
+    if (q.ok && cell_range(P.g, q.u, q.v, q.radius, c0, c1, r0, r1)) {
+        count = 0;
+        const float* kx = P.f.x + (size_t)item * P.f.stride;
+        const float* ky = P.f.y + (size_t)item * P.f.stride;
+        const int* koct = P.f.octave + (size_t)item * P.f.stride;
+        const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
+        const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
+        const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+        const int* kpmp = P.kpMp + (size_t)item * P.f.stride;
+        const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
+        const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + lo * 32);
+        const uint4 a0 = __ldg(md), a1 = __ldg(md + 1);
+        for (int c = c0; c <= c1; c++) {
+            const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
+            for (int p = s; p < e; p++) {
+                const int idx = ci[p];
+                if (!last_candidate(P, q, idx, kx, ky, koct, ur)) continue;
+                const int held = kpmp[idx];                                      // initial occupancy (:1409-1411)
+                if (held != -1 && (held >= 0 ? P.mpObs[(size_t)item * P.lastStride + held] : (kpobs ? kpobs[idx] : 0)) > 0) continue;
+                const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                top4_insert(best, ((uint32_t)dist << 23) | ((uint32_t)p << 5));
+                count++;
+            }
+        }
+    }
+    P.topk[lo] = best;
+    P.topkCount[lo] = count;
+    if (count > 0) {
+        const uint32_t k[4] = {best.x, best.y, best.z, best.w};
+        uint32_t id[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) id[j] = j < count ? (uint32_t)ci[(k[j] >> 5) & 0x3ffffu] : 0u;
+        P.topkIdx[lo] = make_uint4(id[0], id[1], id[2], id[3]);
+    }
+}
+
+// phase B: one warp per frame pair, last-frame keypoints in order
+__global__ void __launch_bounds__(128) k_search_last(const LastParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= P.items) return;
+    const int n = min(P.f.n[item], P.f.stride), nl = min(P.lastN[item], P.lastStride);
+    const float* kx = P.f.x + (size_t)item * P.f.stride;
+    const float* ky = P.f.y + (size_t)item * P.f.stride;
+    const int* koct = P.f.octave + (size_t)item * P.f.stride;
+    const float* kang = P.f.angle + (size_t)item * P.f.stride;
+    const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
+    const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
+    const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+    const int* ci = P.cellItems + (size_t)item * P.f.stride;
+    int* kpmp = P.kpMp + (size_t)item * P.f.stride;
+    const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
+    const size_t lo = (size_t)item * P.lastStride;
+    int* hbin = P.histBin + lo;
+    int* hidx = P.histIdx + lo;
+
+    extern __shared__ uint8_t s_occ_all[];
+    uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * ((P.f.stride + 15) & ~15);
+    for (int idx = lane; idx < n; idx += 32) {
+        const int held = kpmp[idx];
+        occ[idx] = held != -1 && (held >= 0 ? P.mpObs[lo + held] : (kpobs ? kpobs[idx] : 0)) > 0;
+    }
+    for (int i = lane; i < nl; i += 32) hbin[i] = -1;
+    __syncwarp();
+
+    int nmatches = 0;
+    for (int base = 0; base < nl; base += 32) {
+      const int mine = base + lane;
+      int cntL = -1, obsL = 0;
+      float angL = 0.f;
+      uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
+      if (mine < nl) { cntL = P.topkCount[lo + mine]; kkL = P.topk[lo + mine]; idL = P.topkIdx[lo + mine]; obsL = P.mpObs[lo + mine]; angL = P.lastAng[lo + mine]; }
+      const int jEnd = min(32, nl - base);
+      for (int j = 0; j < jEnd; j++) {
+        const int i = base + j;
+        const int cnt = __shfl_sync(0xffffffffu, cntL, j);
+        if (cnt <= 0) continue;
+        const uint32_t key[4] = {__shfl_sync(0xffffffffu, kkL.x, j), __shfl_sync(0xffffffffu, kkL.y, j),
+                                 __shfl_sync(0xffffffffu, kkL.z, j), __shfl_sync(0xffffffffu, kkL.w, j)};
+        const uint32_t kid[4] = {__shfl_sync(0xffffffffu, idL.x, j), __shfl_sync(0xffffffffu, idL.y, j),
+                                 __shfl_sync(0xffffffffu, idL.z, j), __shfl_sync(0xffffffffu, idL.w, j)};
+        const int obsI = __shfl_sync(0xffffffffu, obsL, j);
+        const float angI = __shfl_sync(0xffffffffu, angL, j);
+        // only the best candidate matters here (no ratio test): the first entry of the list whose keypoint is free
+        int bestDist = 256, bestIdx = -1;
+        bool found = false;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (!found && e < cnt) {
+                const int dist = (int)(key[e] >> 23);
+                if (!occ[kid[e]] && dist < 256) { bestDist = dist; bestIdx = (int)kid[e]; found = true; }
+            }
+        }
+        const bool resolved = found || cnt <= 4 || (int)(key[3] >> 23) > TH_HIGH;
+        if (!resolved) {                                   // every listed keypoint was taken: rescan all candidates
+            const LastQuery q = last_query(P, item, i);
+            int c0, c1, r0, r1;
+            cell_range(P.g, q.u, q.v, q.radius, c0, c1, r0, r1);
+            const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + (lo + i) * 32);
+            const uint4 a0 = __ldg(md), a1 = __ldg(md + 1);
+            int bd = 256, bp = INT_MAX;
+            for (int c = c0; c <= c1; c++) {
+                const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
+                for (int p = s + lane; p < e; p += 32) {
+                    const int idx = ci[p];
+                    if (!last_candidate(P, q, idx, kx, ky, koct, ur) || occ[idx]) continue;
+                    const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                    if (dist < bd) { bd = dist; bp = p; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const int od = __shfl_xor_sync(0xffffffffu, bd, d), op = __shfl_xor_sync(0xffffffffu, bp, d);
+                if (key_lt(od, op, bd, bp)) { bd = od; bp = op; }
+            }
+            bestDist = bd;
+            bestIdx = bd < 256 ? ci[bp] : -1;
+        }
+        if (bestDist <= TH_HIGH) {                                                // :1436-1452
+            if (lane == 0) {
+                kpmp[bestIdx] = i;
+                occ[bestIdx] = obsI > 0;
+                if (P.checkOri) {
+                    float rot = __fsub_rn(angI, kang[bestIdx]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    hbin[i] = bin; hidx[i] = bestIdx;
+                }
+            }
+            nmatches++;
+        }
+        __syncwarp();
+      }
+    }
+    if (P.checkOri) {                                                             // :1455-1471
+        __syncwarp();
+        int sizes = 0;
+        for (int i = 0; i < nl; i += 32) {
+            const int b = (i + lane < nl) ? hbin[i + lane] : -1;
+            for (int q = 0; q < HISTO_LENGTH; q++) {
+                const unsigned m = __ballot_sync(0xffffffffu, b == q);
+                if (lane == q) sizes += __popc(m);
+            }
+        }
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int q = 0; q < HISTO_LENGTH; q++) {
+            const int s = __shfl_sync(0xffffffffu, sizes, q);
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = q; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = q; }
+            else if (s > max3) { max3 = s; ind3 = q; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+        int removed = 0;
+        for (int i = lane; i < nl; i += 32) {
+            const int b = hbin[i];
+            if (b >= 0 && b != ind1 && b != ind2 && b != ind3) { kpmp[hidx[i]] = -1; removed++; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, d);
+        nmatches -= removed;
+    }
+    if (lane == 0) P.nmatches[item] = nmatches;
+}
+
 }  // namespace orbb200
 
 // =========================================================================================
@@ -926,6 +1183,70 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
         k_search_proj<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_search_proj");
+    m->lastLaunches = 3;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(kp_mp, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_search_by_projection_last_frame(orbb200_matcher* m, int items, const orbb200_frame_view* cur, const float* u_right,
+                                                       const orbb200_lastframe_view* last, const float* Rcw, const float* tcw,
+                                                       const float* K, float mbf, int32_t* kp_mp, const int32_t* kp_mp_obs,
+                                                       const float* scale_factors, int nlevels, const float* bounds, float th,
+                                                       int mode, int check_orientation, int32_t* nmatches, int on_device)
+{
+    if (!m || !cur || !last || !Rcw || !tcw || !K || !kp_mp || !scale_factors || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (!cur->n || !cur->x || !cur->y || !cur->octave || !cur->desc || (check_orientation && !cur->angle) || !last->n || !last->has_mp ||
+        !last->outlier || !last->world_pos || !last->mp_desc || !last->mp_obs || !last->octave || !last->angle) { set_error("incomplete view"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, cur->stride, "current frame")) || (rc = check_view(m, items, last->stride, "last frame"))) return rc;
+    if (nlevels < 1 || nlevels > 32 || !bounds || !(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1]) || mode < 0 || mode > 2) { set_error("bad geometry"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    LastParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t np = (size_t)items * cur->stride, nl = (size_t)items * last->stride;
+    Stager s{m, 0, st};
+    int* dN;
+    if (on_device) {
+        P.f = as_dev(cur); P.uRight = u_right;
+        P.lastN = last->n; P.hasMp = last->has_mp; P.outlier = last->outlier; P.wpos = last->world_pos; P.mpDesc = last->mp_desc;
+        P.mpObs = last->mp_obs; P.lastOct = last->octave; P.lastAng = last->angle;
+        P.Rcw = Rcw; P.tcw = tcw; P.kpMp = kp_mp; P.kpMpObs = kp_mp_obs; P.scaleFactors = scale_factors; dN = nmatches;
+    } else {
+        const size_t bytes = frame_bytes(cur, items) + 3 * pad(np * 4) + 2 * pad(items * 4) + 2 * pad(nl) + pad(nl * 12) + pad(nl * 32) +
+                             3 * pad(nl * 4) + pad((size_t)items * 36) + pad((size_t)items * 12) + pad((size_t)nlevels * 4);
+        if ((rc = s.reserve(bytes))) return rc;
+        if ((rc = upload_frame(s, cur, items, &P.f, true))) return rc;
+        const int* kpmp;
+        if ((rc = s.up(u_right, np, &P.uRight)) || (rc = s.up(kp_mp, np, &kpmp)) || (rc = s.up(kp_mp_obs, np, &P.kpMpObs)) ||
+            (rc = s.up(last->n, items, &P.lastN)) || (rc = s.up(last->has_mp, nl, &P.hasMp)) || (rc = s.up(last->outlier, nl, &P.outlier)) ||
+            (rc = s.up(last->world_pos, nl * 3, &P.wpos)) || (rc = s.up(last->mp_desc, nl * 32, &P.mpDesc)) ||
+            (rc = s.up(last->mp_obs, nl, &P.mpObs)) || (rc = s.up(last->octave, nl, &P.lastOct)) || (rc = s.up(last->angle, nl, &P.lastAng)) ||
+            (rc = s.up(Rcw, (size_t)items * 9, &P.Rcw)) || (rc = s.up(tcw, (size_t)items * 3, &P.tcw)) ||
+            (rc = s.up(scale_factors, (size_t)nlevels, &P.scaleFactors))) return rc;
+        P.kpMp = const_cast<int*>(kpmp);
+        dN = s.out<int>(items);
+    }
+    P.lastStride = last->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.mbf = mbf;
+    P.minX = bounds[0]; P.minY = bounds[1]; P.maxX = bounds[2]; P.maxY = bounds[3];
+    P.nmatches = dN; P.items = items; P.mode = mode; P.checkOri = check_orientation; P.th = th;
+    P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx; P.histBin = m->scratchA; P.histIdx = m->scratchB;
+    k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
+    ORB_CHECK_LAUNCH("k_build_grid");
+    k_last_topk<<<dim3((last->stride + 127) / 128, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_last_topk");
+    {
+        const size_t sm = 4 * (size_t)((cur->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
+    }
+    ORB_CHECK_LAUNCH("k_search_last");
     m->lastLaunches = 3;
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(kp_mp, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));

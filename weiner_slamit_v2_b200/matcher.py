@@ -192,3 +192,40 @@ class ORBmatcher:
         b = np.zeros(4, np.float32)
         check(self._L.orbb200_image_bounds(self._h, cols, rows, K.ctypes.data, dist.ctypes.data, b.ctypes.data))
         return b
+
+    # ---- SearchByProjection(CurrentFrame, LastFrame, th, bMono) (S/ORBmatcher.cc:1332-1474), scope row N2 ----
+    def search_by_projection_last_frame_batch(self, cur_frames, lasts, th=15.0, mode=0, mbf=40.0):
+        """cur_frames: list of Frame (mvpMapPoints hold indices into the last frame's arrays).
+        lasts: list of dicts with has_mp, outlier, wpos (n,3), mp_desc (n,32), mp_obs, last_octave, last_angle,
+        Rcw (9), tcw (3), K (4) -- the fields of LastFrame / CurrentFrame.mTcw the reference reads.
+        mode: 0 = bMono or neither forward nor backward, 1 = bForward, 2 = bBackward."""
+        from ._lib import LastFrameView
+        items = len(cur_frames)
+        keep = []
+        fv, s = _frame_view(cur_frames, keep)
+        ls = max(1, max(len(l["has_mp"]) for l in lasts))
+        self._ensure(items, max(s, ls))
+        bnd = cur_frames[0].bounds
+        sf = cur_frames[0].mvScaleFactors
+        assert sf is not None, "Frame.mvScaleFactors is required"
+        ur = _pack([f.mvuRight for f in cur_frames], s, np.float32)
+        kpmp = _pack([f.mvpMapPoints for f in cur_frames], s, np.int32)
+        kpobs = _pack([f.mvpMapPointObs for f in cur_frames], s, np.int32)
+        ln = np.array([len(l["has_mp"]) for l in lasts], np.int32)
+        a = dict(hm=_pack([l["has_mp"] for l in lasts], ls, np.uint8), ol=_pack([l["outlier"] for l in lasts], ls, np.uint8),
+                 wp=_pack([np.asarray(l["wpos"], np.float32).reshape(-1, 3) for l in lasts], ls, np.float32, (3,)),
+                 md=_pack([l["mp_desc"] for l in lasts], ls, np.uint8, (32,)), ob=_pack([l["mp_obs"] for l in lasts], ls, np.int32),
+                 oc=_pack([l["last_octave"] for l in lasts], ls, np.int32), an=_pack([l["last_angle"] for l in lasts], ls, np.float32))
+        lv = LastFrameView(ln.ctypes.data, a["hm"].ctypes.data, a["ol"].ctypes.data, a["wp"].ctypes.data, a["md"].ctypes.data,
+                           a["ob"].ctypes.data, a["oc"].ctypes.data, a["an"].ctypes.data, ls)
+        R = np.ascontiguousarray(np.stack([np.asarray(l["Rcw"], np.float32).reshape(9) for l in lasts]))
+        t = np.ascontiguousarray(np.stack([np.asarray(l["tcw"], np.float32).reshape(3) for l in lasts]))
+        K = np.ascontiguousarray(lasts[0]["K"], np.float32)
+        nm = np.zeros(items, np.int32)
+        check(self._L.orbb200_search_by_projection_last_frame(
+            self._h, items, C.byref(fv), ur.ctypes.data, C.byref(lv), R.ctypes.data, t.ctypes.data, K.ctypes.data, float(mbf),
+            kpmp.ctypes.data, kpobs.ctypes.data, sf.ctypes.data, len(sf), bnd.ctypes.data, float(th), int(mode),
+            int(self.mbCheckOrientation), nm.ctypes.data, 0))
+        for i, f in enumerate(cur_frames):
+            f.mvpMapPoints[:] = kpmp[i, :f.N]
+        return nm

@@ -70,3 +70,43 @@ def projection_frame(index, n_kp=2000, n_mp=10000, width=1280, height=720, nleve
               in_view=(rng.random(n_mp) < 0.97).astype(np.uint8), bad=(rng.random(n_mp) < 0.02).astype(np.uint8),
               obs=(rng.random(n_mp) < 0.95).astype(np.int32) * rng.integers(1, 9, n_mp).astype(np.int32))
     return kp, kd, mp
+
+
+def motion_frame(index, n_last=1500, n_cur=2000, width=640, height=480, nlevels=8,
+                 K=(526.69, 540.36, 313.07, 238.39)):
+    """A frame pair for SearchByProjection(CurrentFrame, LastFrame, th, bMono) (motion-model tracking):
+    the last frame's keypoints carry map points (world positions); the current frame's keypoints sit near
+    their projections under a small camera motion Tcw.  Includes points behind the camera, projections
+    outside the image, keypoints without map point and outliers."""
+    rng = np.random.default_rng(120000 + index)
+    fx, fy, cx, cy = K
+    # small motion: rotation by a few degrees about a random axis + translation
+    axis = rng.normal(size=3); axis /= np.linalg.norm(axis)
+    ang = np.deg2rad(rng.uniform(0.5, 3.0))
+    Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = (np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx).astype(np.float32)
+    t = rng.normal(0, 0.05, 3).astype(np.float32)
+    last = random_keypoints(n_last, width, height, rng, nlevels)
+    u = rng.uniform(-20, width + 20, n_last); v = rng.uniform(-20, height + 20, n_last)
+    z = rng.uniform(1.0, 10.0, n_last)
+    z[rng.random(n_last) < 0.03] *= -1                                     # behind the camera
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    wpos = ((Xc - t) @ R).astype(np.float32)                               # Xw = R^T (Xc - t)
+    mp_desc = rng.integers(0, 256, (n_last, 32)).astype(np.uint8)
+    has_mp = (rng.random(n_last) < 0.9).astype(np.uint8)
+    outlier = (rng.random(n_last) < 0.05).astype(np.uint8)
+    mp_obs = ((rng.random(n_last) < 0.95) * rng.integers(1, 9, n_last)).astype(np.int32)
+    # current frame: most keypoints are noisy re-observations of last-frame map points
+    cur = random_keypoints(n_cur, width, height, rng, nlevels)
+    src = rng.integers(0, n_last, n_cur)
+    re = rng.random(n_cur) < 0.8
+    cur["x"] = np.where(re, np.clip(u[src] + rng.normal(0, 2.5, n_cur), 0, width - 1), cur["x"]).astype(np.float32)
+    cur["y"] = np.where(re, np.clip(v[src] + rng.normal(0, 2.5, n_cur), 0, height - 1), cur["y"]).astype(np.float32)
+    cur["octave"] = np.where(re, np.clip(last["octave"][src] + rng.integers(-1, 2, n_cur), 0, nlevels - 1), cur["octave"])
+    rot = rng.uniform(0, 40)
+    cur["angle"] = np.where(re, np.mod(last["angle"][src] - rot + rng.normal(0, 5, n_cur), 360), cur["angle"]).astype(np.float32)
+    cdesc = rng.integers(0, 256, (n_cur, 32)).astype(np.uint8)
+    cdesc[re] = flip_bits(mp_desc[src[re]], rng.integers(0, 70, int(re.sum())), rng)
+    return dict(has_mp=has_mp, outlier=outlier, wpos=wpos, mp_desc=mp_desc, mp_obs=mp_obs,
+                last_octave=last["octave"].astype(np.int32), last_angle=last["angle"].astype(np.float32),
+                Rcw=R.reshape(9), tcw=t, K=np.array(K, np.float32), cur=cur, cdesc=cdesc)
