@@ -388,6 +388,35 @@ def run_matching(local, steps):
         "workload": "512 frames, 10000 projected map points vs 2000 keypoints per frame, th=1, ratio 0.8",
         "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "map_points_per_s": items * nmp / ms * 1e3,
         "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    # ---- scope row N2: SearchByProjection(CurrentFrame, LastFrame, th, bMono), the per-frame motion-model tracker
+    from weiner_slamit_v2_b200._lib import LastFrameView
+    from weiner_slamit_v2_b200.workloads import motion_frame
+    items, nl, nk, distinct = 512, 1500, 2000, 16
+    ws = [motion_frame(i, nl, nk) for i in range(distinct)]
+    tk = dict(n=up(np.full(items, nk, np.int32)), x=up(tile(np.stack([w["cur"]["x"] for w in ws]), items)),
+              y=up(tile(np.stack([w["cur"]["y"] for w in ws]), items)), o=up(tile(np.stack([w["cur"]["octave"] for w in ws]), items)),
+              a=up(tile(np.stack([w["cur"]["angle"] for w in ws]), items)), d=up(tile(np.stack([w["cdesc"] for w in ws]), items)))
+    kv = FrameView(tk["n"].data_ptr(), tk["x"].data_ptr(), tk["y"].data_ptr(), tk["o"].data_ptr(), tk["a"].data_ptr(), tk["d"].data_ptr(), nk)
+    lk = ["has_mp", "outlier", "wpos", "mp_desc", "mp_obs", "last_octave", "last_angle"]
+    tl = {k: up(tile(np.stack([w[k] for w in ws]), items)) for k in lk}
+    tl["n"] = up(np.full(items, nl, np.int32))
+    lv = LastFrameView(tl["n"].data_ptr(), *[tl[k].data_ptr() for k in lk], nl)
+    Rc = up(tile(np.stack([w["Rcw"] for w in ws]), items)); tc = up(tile(np.stack([w["tcw"] for w in ws]), items))
+    Kc = np.ascontiguousarray(ws[0]["K"], np.float32)
+    b3 = np.array([-13.7, -9.2, 661.3, 492.8], np.float32)
+    kpmp3 = torch.empty((items, nk), dtype=torch.int32, device=dev)
+    nm3 = torch.empty(items, dtype=torch.int32, device=dev)
+    def last_step():
+        kpmp3.fill_(-1)
+        check(L.orbb200_search_by_projection_last_frame(h, items, C.byref(kv), None, C.byref(lv), Rc.data_ptr(), tc.data_ptr(),
+                                                        Kc.ctypes.data, 40.0, kpmp3.data_ptr(), None, sf.data_ptr(), 8,
+                                                        b3.ctypes.data, 15.0, 0, 1, nm3.data_ptr(), 1))
+    ms = timed(L.orbb200_matcher_stream(h), last_step, steps)
+    acc = int(nm3.sum())
+    out["search_by_projection_last_frame"] = {
+        "workload": "512 frame pairs, 1500 last-frame map points projected into 2000 keypoints, th=15, mono, checkOri",
+        "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "map_points_per_s": items * nl / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
     L.orbb200_matcher_destroy(h)
     return out
 

@@ -164,7 +164,13 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
     from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
     g = np.load(path)
-    if "init" in os.path.basename(path):
+    if "lastframe" in os.path.basename(path):
+        from weiner_slamit_v2_b200.workloads import motion_frame
+        for i in range(int(g["count"])):
+            idx, th, ori = int(g["cfg_%d" % i][0]), float(g["cfg_%d" % i][1]), bool(g["cfg_%d" % i][2])
+            a = O.search_by_projection_last_frame(motion_frame(idx), SCALE_FACTORS_8, (-13.7, -9.2, 661.3, 492.8), th, 0, ori)
+            assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["kpmp_%d" % i])
+    elif "init" in os.path.basename(path):
         for i in range(int(g["count"])):
             idx, n, brute, window = (int(v) for v in g["cfg_%d" % i])
             p = init_pair(idx, n=n, brute_force=bool(brute))
@@ -180,7 +186,7 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
 
 
 def test_matcher_golden_vectors_exist():
-    assert len(MGOLDEN) >= 2
+    assert len(MGOLDEN) >= 3
 
 
 @needs_refm

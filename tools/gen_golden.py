@@ -69,3 +69,14 @@ for i, (idx, nk, nmp, th) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_proj.npz"), **out)
 print("ref_match_proj.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+from weiner_slamit_v2_b200.workloads import motion_frame  # noqa: E402
+cfgs = [(700, 15.0, 1), (701, 7.0, 1), (702, 15.0, 0)]
+for i, (idx, th, ori) in enumerate(cfgs):
+    w = motion_frame(idx)
+    r = R.ref_search_by_projection_last_frame(w, SCALE_FACTORS_8, (-13.7, -9.2, 661.3, 492.8), th, bool(ori))
+    out["cfg_%d" % i] = np.array([idx, th, ori]); out["n_%d" % i] = r[0]; out["kpmp_%d" % i] = r[1]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_lastframe.npz"), **out)
+print("ref_match_lastframe.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])

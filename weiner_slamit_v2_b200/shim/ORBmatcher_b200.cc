@@ -2,6 +2,7 @@
 //   DescriptorDistance                                   (replaces S/ORBmatcher.cc:1651-1667)
 //   SearchForInitialization                              (replaces S/ORBmatcher.cc:409-524)
 //   SearchByProjection(Frame&, vector<MapPoint*>&, th)   (replaces S/ORBmatcher.cc:47-131)
+//   SearchByProjection(CurrentFrame, LastFrame, th, bMono) (replaces S/ORBmatcher.cc:1332-1474; scope row N2)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -160,6 +161,78 @@ int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMap
     }
     for (int i = 0; i < s.n; i++)
         if (kpMp[i] != before[i] && kpMp[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[kpMp[i]];   // :125
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
+{
+    // the two scalars that pick the octave window are evaluated on the host exactly as in the reference (:1342-1353)
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat twc = -Rcw.t() * tcw;
+    const cv::Mat Rlw = LastFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tlw = LastFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat tlc = Rlw * twc + tlw;
+    const bool bForward = tlc.at<float>(2) > CurrentFrame.mb && !bMono;
+    const bool bBackward = -tlc.at<float>(2) > CurrentFrame.mb && !bMono;
+    const int mode = bForward ? 1 : (bBackward ? 2 : 0);
+
+    FrameSoA cur(CurrentFrame);
+    const int nl = LastFrame.N;
+    orbb200_matcher* h = tlsMatcher.get(cur.n > nl ? cur.n : nl);
+    if (!h || nl == 0) return 0;
+
+    const int ls = nl;
+    int32_t ln = nl;
+    std::vector<unsigned char> hasMp(ls), outlier(ls), desc((size_t)ls * 32);
+    std::vector<float> wpos((size_t)ls * 3), angle(ls);
+    std::vector<int32_t> obs(ls), octave(ls);
+    std::map<const MapPoint*, int> indexOf;
+    for (int i = 0; i < nl; i++) {
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        hasMp[i] = pMP ? 1 : 0;
+        outlier[i] = LastFrame.mvbOutlier[i] ? 1 : 0;
+        octave[i] = LastFrame.mvKeys[i].octave;
+        angle[i] = LastFrame.mvKeysUn[i].angle;
+        if (!pMP) continue;
+        indexOf[pMP] = i;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        for (int k = 0; k < 3; k++) wpos[3 * (size_t)i + k] = x3Dw.at<float>(k);
+        const cv::Mat d = pMP->GetDescriptor();
+        if (!d.empty()) std::memcpy(&desc[(size_t)i * 32], d.ptr<unsigned char>(), 32);
+        obs[i] = pMP->Observations();
+    }
+    orbb200_lastframe_view lv;
+    lv.n = &ln; lv.has_mp = &hasMp[0]; lv.outlier = &outlier[0]; lv.world_pos = &wpos[0]; lv.mp_desc = &desc[0];
+    lv.mp_obs = &obs[0]; lv.octave = &octave[0]; lv.angle = &angle[0]; lv.stride = ls;
+
+    std::vector<int32_t> kpMp(cur.view.stride, -1), kpObs(cur.view.stride, 0);
+    std::vector<float> uRight(cur.view.stride, -1.f);
+    for (int i = 0; i < cur.n; i++) {
+        uRight[i] = CurrentFrame.mvuRight[i];
+        MapPoint* held = CurrentFrame.mvpMapPoints[i];
+        if (!held) continue;
+        std::map<const MapPoint*, int>::const_iterator it = indexOf.find(held);
+        if (it != indexOf.end()) kpMp[i] = it->second;
+        else { kpMp[i] = -2; kpObs[i] = held->Observations(); }
+    }
+    const std::vector<int32_t> before(kpMp);
+    float R9[9], t3[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R9[3 * r + c] = Rcw.at<float>(r, c); t3[r] = tcw.at<float>(r); }
+    const float K[4] = {CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy};
+    float bounds[4];
+    FrameBounds(bounds);
+    int32_t nmatches = 0;
+    if (orbb200_search_by_projection_last_frame(h, 1, &cur.view, &uRight[0], &lv, R9, t3, K, CurrentFrame.mbf, &kpMp[0], &kpObs[0],
+                                                &CurrentFrame.mvScaleFactors[0], (int)CurrentFrame.mvScaleFactors.size(), bounds,
+                                                th, mode, mbCheckOrientation ? 1 : 0, &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchByProjection(last frame): %s\n", orbb200_last_error());
+        return 0;
+    }
+    for (int i = 0; i < cur.n; i++) {
+        if (kpMp[i] == before[i]) continue;
+        CurrentFrame.mvpMapPoints[i] = kpMp[i] >= 0 ? LastFrame.mvpMapPoints[kpMp[i]] : static_cast<MapPoint*>(NULL);   // :1438, :1465
+    }
     return nmatches;
 }
 
