@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
 // processing order.  Nodes live in a slot table: the first non-empty child re-uses its parent's
 // slot, so the table never needs more than max-list-size + nIni entries.
 constexpr int QT_THREADS = 256;
+constexpr int QT_POINTS_ON_CHIP = 3072;   // candidates of one tree held in shared memory; larger trees run out of global memory
 
 struct QtShared {
     int size, nslots, nextseq, E, phase, finish, cut, rounds;
@@ -1230,7 +1231,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     const size_t perNode = 8 + 8 + 8 + 4 * 7 + 16 + 16;
     const size_t budget = 200 * 1024;
     if (perNode * P.qtNC + 6 * 1024 > budget) { set_error("nfeatures too large for the on-chip quadtree (%d node slots)", P.qtNC); delete h; return ORBB200_EINVAL; }
-    P.qtPC = (int)std::min<size_t>(8192, (budget - perNode * P.qtNC) / 6) & ~7;
+    P.qtPC = (int)std::min<size_t>(QT_POINTS_ON_CHIP, (budget - perNode * P.qtNC) / 6) & ~7;
     h->qtSmem = perNode * P.qtNC + 6 * (size_t)P.qtPC;
 
     // ---- device memory
