@@ -246,6 +246,15 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if sampler else None
     nkp = int(out_c.sum())
+    # single-frame latency of the drop-in call (what Frame::ExtractORB sees): batch 1, host buffers
+    ex1 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=WIDTH, height=HEIGHT, max_batch=1, device=local)
+    for _ in range(5):
+        check(ex1._L.orbb200_extract_host(ex1._h, host_in.ctypes.data, 1, WIDTH, WIDTH * HEIGHT, out_k.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), cap))
+    t0 = time.perf_counter()
+    for _ in range(50):
+        check(ex1._L.orbb200_extract_host(ex1._h, host_in.ctypes.data, 1, WIDTH, WIDTH * HEIGHT, out_k.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), cap))
+    latency_ms = (time.perf_counter() - t0) / 50 * 1e3
+    ex1.close()
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(nkp)], dtype=torch.float64, device="cuda")
@@ -272,7 +281,8 @@ def run_ours(args):
                        "frames_per_step_per_gpu": BATCH, "l2": "256 MiB flush buffer written before every timed step",
                        "parallelism": "frames sharded by batch, no data-path collective"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * WIDTH * HEIGHT,
-                    "d2h_bytes_per_step": BATCH * (4 + cap * 60), "keypoints_per_step": nkp / world},
+                    "d2h_bytes_per_step": BATCH * (4 + cap * 60), "keypoints_per_step": nkp / world,
+                    "single_frame_latency_ms": latency_ms},
             "gpu_launches": launches,
             "kernel_ms_per_step": {s: float(per_stage[i]) for i, s in enumerate(STAGES)},
             "roofline": {"bound": "hbm", "kernel": STAGES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
