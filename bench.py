@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
 BATCH = 256                       # frames per GPU per step (configs[1])
+WORKLOAD = "batched ORB extraction, 256 synthetic 640x480 frames per GPU, 1000 kp/8 levels, FAST 20/7 (configs[1])"
 DISTINCT = 32                     # distinct synthetic frames generated per rank (tiled to BATCH)
 
 # Algorithmic HBM bytes per frame and per kernel (DESIGN.md "Roofline model"):
@@ -274,10 +275,10 @@ def run_ours(args):
         line = {
             "metric": "ORB frames/s (640x480, 1000 kp, 8 lvl)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "hd" else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "batched ORB extraction, 256 synthetic 640x480 frames per GPU, 1000 kp/8 levels, "
-                                   "FAST 20/7 (configs[1])",
+            "config": {"workload": WORKLOAD,
                        "frames_per_step_per_gpu": BATCH, "l2": "256 MiB flush buffer written before every timed step",
                        "parallelism": "frames sharded by batch, no data-path collective"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * WIDTH * HEIGHT,
@@ -477,7 +478,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matching", action="store_true", help="skip the Hamming-matching configs (configs[2], configs[4])")
+    ap.add_argument("--workload", default="vga", choices=["vga", "hd"],
+                    help="vga = configs[1] (the headline, default); hd = configs[3]: 1280x720, 2000 kp, batch 1024 sharded over the GPUs")
     args = ap.parse_args()
+    if args.workload == "hd":
+        global WIDTH, HEIGHT, NFEAT, BATCH, WORKLOAD, ALG_BYTES
+        WIDTH, HEIGHT, NFEAT = 1280, 720, 2000
+        BATCH = 1024 // max(1, args.gpus)          # strong scaling: the 1024-frame batch is split over the GPUs
+        WORKLOAD = "1280x720 frames, nFeatures=2000, 8 levels, batch 1024 sharded over %d B200 (configs[3])" % args.gpus
+        ALG_BYTES = {"pyramid": 2781331 + 1931488, "fast": 2853088 + 160000, "quadtree": 160000 + 32000,
+                     "blur": 5706176, "describe": 1498000 + 1024000 + 120000}
+        args.no_matching = True
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
