@@ -162,7 +162,6 @@ struct InitParams {
     GridGeo g;
     const int* cellStart;     // items x (GRID_CELLS+1), F2 grid
     const int* cellItems;     // items x f2.stride
-    int* matchedDist;         // items x f2.stride scratch (vMatchedDistance)
     int* matches21;           // items x f2.stride scratch (vnMatches21)
     int* histBin;             // items x f1.stride scratch: rotation bin of i1 when it was accepted, else -1
     float* prevMatched;       // items x f1.stride x 2, in/out
@@ -1104,7 +1103,7 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     }
     P.g = grid_geo(bounds);
     P.cellStart = m->cellStart; P.cellItems = m->cellItems;
-    P.matchedDist = m->scratchA; P.matches21 = m->scratchB; P.histBin = m->scratchC;
+    P.matches21 = m->scratchB; P.histBin = m->scratchC;
     P.prevMatched = dPrev; P.matches12 = dM12; P.nmatches = dN;
     P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx;
     P.items = items; P.window = window_size; P.checkOri = check_orientation; P.nnratio = nnratio;

@@ -71,7 +71,6 @@ def _frame_view(frames, keep):
 
 class ORBmatcher:
     TH_HIGH, TH_LOW, HISTO_LENGTH = TH_HIGH, TH_LOW, HISTO_LENGTH
-    _shared = {}
 
     def __init__(self, nnratio=0.6, checkOri=True, device=0, max_items=1, max_points=4096):
         self.mfNNratio = float(nnratio)
