@@ -210,7 +210,7 @@ constexpr int FAST_WARPS = 2;     // cells per CTA; the warps of a CTA never syn
 template <int TPW, int TH>
 struct FastGeo {
     static constexpr int SP = TPW * 2 - 4;                // score-map pitch in bytes, >= widest cell + 2, multiple of 4
-    static constexpr int QCAP = (TPW - 4) * (TH - 6);     // pixel pairs per cell, upper bound
+    static constexpr int QCAP = (TPW - 2) * (TH - 6);     // pixel pairs per cell (incl. masked lead-in and phantom pairs), upper bound
     static constexpr int QBYTES = 2 * QCAP + 64;
     static constexpr int TILE_BYTES = TH * TPW * 4 + 64;  // (+ slack: the last pair's right neighbour word)
     static constexpr int WARP_BYTES = ((TILE_BYTES + (TH - 4) * SP + QBYTES + 15) / 16) * 16;
@@ -253,11 +253,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     int pitch;
     const uint8_t* img = level_ptr(P, l, frame, pitch);
     // 4-byte aligned load origin: tile column 0 is image column ax, the window starts at column `shift`
-    // (1..4: at least one spare column on the left, because pairs start one pixel early when par = 1)
+    // (1..4, so the first detection column is tile column 4..7 and pixel pairs can start at tile column 4)
     const int ax = (iniX - 1) & ~3, shift = iniX - ax;
     const int nwords = (shift + ww + 3) >> 2;                           // <= TPW / 2
     const uint8_t* rowp = img + (long long)iniY * pitch + ax;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3) == 0;
+    // (level 0 is 16-byte aligned too: enqueue() stages any other input into the padded slab)
 
     {   // stage the window (expanded to 16 bit): two rows per step when a row needs <= 16 words,
         // four independent loads in flight per lane
@@ -273,11 +273,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 v[u] = 0;
-                if (colAct && r0 + u * rpi < wh) {
-                    const uint8_t* qq = q + u * qstep;
-                    if (aligned) v[u] = __ldg(reinterpret_cast<const uint32_t*>(qq));
-                    else v[u] = (uint32_t)__ldg(qq) | ((uint32_t)__ldg(qq + 1) << 8) | ((uint32_t)__ldg(qq + 2) << 16) | ((uint32_t)__ldg(qq + 3) << 24);
-                }
+                if (colAct && r0 + u * rpi < wh) v[u] = __ldg(reinterpret_cast<const uint32_t*>(q + u * qstep));
             }
 #pragma unroll
             for (int u = 0; u < 4; u++)
@@ -291,44 +287,61 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     }
     __syncwarp();
 
-    // Pixel pairs start at EVEN tile columns: pair i covers detection x = 2i - par and 2i - par + 1
-    // (when par = 1 the first pair's left pixel is outside the area and is masked).
-    const int par = (shift + 3) & 1;
-    const uint32_t* tbase = tw + 3 * TPW + ((shift + 3 - par) >> 1);     // centre pair of (row 0, pair 0)
+    // Pixel pairs sit at EVEN tile words starting at tile column 4: pair i covers detection x = 2i - off and
+    // 2i - off + 1, where off = shift - 1 (0..3) columns of the first pairs lie left of the area and are masked.
+    // Two neighbouring pairs (a "quad") therefore start at an 8-byte aligned word: pass 1 reads them with LDS.64.
+    const int off = shift - 1;
+    const uint32_t* tbase = tw + 3 * TPW + 2;                            // centre pair of (row 0, pair 0)
     const int tlow = min(P.iniTh, P.minTh);
     const uint32_t T2 = (uint32_t)tlow * 0x00010001u;
-    const int npair = (dw + par + 1) >> 1, total = npair * dh;
+    const int npair = (dw + off + 1) >> 1, nquad = (npair + 1) >> 1, total = nquad * dh;
     const unsigned ltmask = (1u << lane) - 1;
 
-    // pass 1: cheap reject on the ring pairs (0,8) (4,12) (2,10) (6,14), both centre pixels at once
+    // pass 1: cheap reject on the ring pairs (0,8) (4,12) (2,10) (6,14); a lane tests one quad = 2 pairs = 4 centre
+    // pixels per step from 11 shared loads.  (An odd npair makes the last quad's second pair a phantom: it reads
+    // valid shared memory and pass 2 masks it by x >= dw.)
     int nq = 0;
     {
-        int r = lane / npair, i = lane - r * npair;
-        const int stepR = 32 / npair, stepI = 32 - stepR * npair;
+        int r = lane / nquad, k = lane - r * nquad;
+        const int stepR = 32 / nquad, stepK = 32 - stepR * nquad;
         for (int idx = lane; idx - lane < total; idx += 32) {
-            bool pass = false;
+            bool passA = false, passB = false;
             if (idx < total) {
-                const uint32_t* b = tbase + r * TPW + i;
-                const uint32_t V = b[0];
-                const uint32_t R0 = b[3 * TPW], R8 = b[-3 * TPW];
-                const uint32_t R4 = FAST_PAIR(b[1], b[2]), R12 = FAST_PAIR(b[-2], b[-1]);
-                const uint32_t R2 = b[2 * TPW + 1], R14 = b[2 * TPW - 1], R6 = b[-2 * TPW + 1], R10 = b[-2 * TPW - 1];
-                const uint32_t mb = __vminu2(__vminu2(__vmaxu2(R0, R8), __vmaxu2(R4, R12)), __vminu2(__vmaxu2(R2, R10), __vmaxu2(R6, R14)));
-                const uint32_t md = __vmaxu2(__vmaxu2(__vminu2(R0, R8), __vminu2(R4, R12)), __vmaxu2(__vminu2(R2, R10), __vminu2(R6, R14)));
-                const uint32_t hiV = V + T2;
-                pass = __vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, V) != V;
+                const uint32_t* b = tbase + r * TPW + 2 * k;
+                const uint2 c = *reinterpret_cast<const uint2*>(b);                 // centres: pair A = c.x, pair B = c.y
+                const uint2 lf = *reinterpret_cast<const uint2*>(b - 2), rt = *reinterpret_cast<const uint2*>(b + 2);
+                const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
+                const uint2 u2 = *reinterpret_cast<const uint2*>(b + 2 * TPW), d2 = *reinterpret_cast<const uint2*>(b - 2 * TPW);
+                const uint32_t u2l = b[2 * TPW - 1], u2r = b[2 * TPW + 2], d2l = b[-2 * TPW - 1], d2r = b[-2 * TPW + 2];
+                {
+                    const uint32_t R4 = FAST_PAIR(c.y, rt.x), R12 = FAST_PAIR(lf.x, lf.y);
+                    const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4, R12), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
+                    const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.x, dn.x), __vminu2(R4, R12), __vminu2(u2.y, d2l)), __vminu2(d2.y, u2l));
+                    const uint32_t hiV = c.x + T2;
+                    passA = __vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, c.x) != c.x;
+                }
+                {
+                    const uint32_t R4 = FAST_PAIR(rt.x, rt.y), R12 = FAST_PAIR(lf.y, c.x);
+                    const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.y, dn.y), __vmaxu2(R4, R12), __vmaxu2(u2r, d2.x)), __vmaxu2(d2r, u2.x));
+                    const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.y, dn.y), __vminu2(R4, R12), __vminu2(u2r, d2.x)), __vminu2(d2r, u2.x));
+                    const uint32_t hiV = c.y + T2;
+                    passB = __vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, c.y) != c.y;
+                }
             }
-            const unsigned bal = __ballot_sync(FULL, pass);
-            if (pass) queue[nq + __popc(bal & ltmask)] = (uint16_t)(r * 32 + i);
-            nq += __popc(bal);
-            r += stepR; i += stepI;
-            if (i >= npair) { i -= npair; r++; }
+            const unsigned balA = __ballot_sync(FULL, passA), balB = __ballot_sync(FULL, passB);
+            if (passA) queue[nq + __popc(balA & ltmask)] = (uint16_t)(r * 64 + 2 * k);
+            nq += __popc(balA);
+            if (passB) queue[nq + __popc(balB & ltmask)] = (uint16_t)(r * 64 + 2 * k + 1);
+            nq += __popc(balB);
+            r += stepR; k += stepK;
+            if (k >= nquad) { k -= nquad; r++; }
         }
     }
     __syncwarp();
     // pass 2: exact corner score = max over the 16 arcs of 9 of min|centre - ring|, minus 1
-    // (cv::cornerScore<16>).  Pairs with a corner are compacted in place (write index <= read index)
-    // with two flag bits saying which half is a corner.
+    // (cv::cornerScore<16>).  min/max commute with the "- centre", so the sliding min-of-9 / max-of-9 network
+    // runs on the raw ring values and the centre is subtracted once at the end.  Pairs with a corner are
+    // compacted in place (write index <= read index) with two flag bits saying which half is a corner.
     int ncp = 0;
     for (int q0 = 0; q0 < nq; q0 += 32) {
         const int q = q0 + lane;
@@ -336,20 +349,19 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
         int e = 0;
         if (q < nq) {
             e = queue[q];
-            const int r = e >> 5, i = e & 31;
+            const int r = e >> 6, i = e & 63;
             const uint32_t* b = tbase + r * TPW + i;
-            const uint32_t Cm = 0x01000100u - b[0];                  // 256 - v per half: ring + Cm = 256 + (ring - v)
             uint32_t D[16];
             {
                 const uint32_t a0 = b[3 * TPW - 1], a1 = b[3 * TPW], a2 = b[3 * TPW + 1];
-                D[15] = FAST_PAIR(a0, a1) + Cm; D[0] = a1 + Cm; D[1] = FAST_PAIR(a1, a2) + Cm;
+                D[15] = FAST_PAIR(a0, a1); D[0] = a1; D[1] = FAST_PAIR(a1, a2);
                 const uint32_t z0 = b[-3 * TPW - 1], z1 = b[-3 * TPW], z2 = b[-3 * TPW + 1];
-                D[9] = FAST_PAIR(z0, z1) + Cm; D[8] = z1 + Cm; D[7] = FAST_PAIR(z1, z2) + Cm;
-                D[14] = b[2 * TPW - 1] + Cm; D[2] = b[2 * TPW + 1] + Cm;
-                D[10] = b[-2 * TPW - 1] + Cm; D[6] = b[-2 * TPW + 1] + Cm;
-                D[13] = FAST_PAIR(b[TPW - 2], b[TPW - 1]) + Cm; D[3] = FAST_PAIR(b[TPW + 1], b[TPW + 2]) + Cm;
-                D[12] = FAST_PAIR(b[-2], b[-1]) + Cm; D[4] = FAST_PAIR(b[1], b[2]) + Cm;
-                D[11] = FAST_PAIR(b[-TPW - 2], b[-TPW - 1]) + Cm; D[5] = FAST_PAIR(b[-TPW + 1], b[-TPW + 2]) + Cm;
+                D[9] = FAST_PAIR(z0, z1); D[8] = z1; D[7] = FAST_PAIR(z1, z2);
+                D[14] = b[2 * TPW - 1]; D[2] = b[2 * TPW + 1];
+                D[10] = b[-2 * TPW - 1]; D[6] = b[-2 * TPW + 1];
+                D[13] = FAST_PAIR(b[TPW - 2], b[TPW - 1]); D[3] = FAST_PAIR(b[TPW + 1], b[TPW + 2]);
+                D[12] = FAST_PAIR(b[-2], b[-1]); D[4] = FAST_PAIR(b[1], b[2]);
+                D[11] = FAST_PAIR(b[-TPW - 2], b[-TPW - 1]); D[5] = FAST_PAIR(b[-TPW + 1], b[-TPW + 2]);
             }
             uint32_t lo3[16], hi3[16];
 #pragma unroll
@@ -371,13 +383,14 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
             }
             bright = __vmaxu2(bright, lo9[15]);
             dark = __vminu2(dark, hi9[15]);
-            // bright = 256 + max-arc-min(ring - v); dark = 256 + min-arc-max(ring - v); m = max(bright-256, 256-dark)
-            const uint32_t m2 = __vmaxu2(bright, 0x02000200u - dark);    // 256 + m per half
+            // bright = max-arc-min(ring), dark = min-arc-max(ring); m = max(bright - v, v - dark), kept positive by +256
+            const uint32_t V = b[0];
+            const uint32_t m2 = __vmaxu2(bright + (0x01000100u - V), (0x01000100u + V) - dark);    // 256 + m per half
             const int m0 = (int)(m2 & 0xffffu) - 256, m1 = (int)(m2 >> 16) - 256;
-            const int x0 = 2 * i - par;
+            const int x0 = 2 * i - off;
             uint8_t* sp = score + (r + 1) * SP + x0 + 1;
-            c0 = (m0 > tlow) && (x0 >= 0);
-            c1 = (m1 > tlow) && (x0 + 1 < dw);
+            c0 = (m0 > tlow) && (x0 >= 0) && (x0 < dw);
+            c1 = (m1 > tlow) && (x0 + 1 >= 0) && (x0 + 1 < dw);
             if (c0) sp[0] = (uint8_t)(m0 - 1);
             if (c1) sp[1] = (uint8_t)(m1 - 1);
         }
@@ -392,7 +405,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     for (int q0 = 0; q0 < ncp; q0 += 32) {
         const int q = q0 + lane;
         const int e = q < ncp ? queue[q] : 0;
-        const int r = (e >> 5) & 0x1ff, x0 = 2 * (e & 31) - par;
+        const int r = (e >> 6) & 0xff, x0 = 2 * (e & 63) - off;
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             bool keep = false;
