@@ -77,6 +77,18 @@ int orbb200_extractor_level_size(const orbb200_extractor *h, int level, int *w, 
 int orbb200_extract_host(orbb200_extractor *h, const uint8_t *images, int batch, size_t stride, size_t frame_stride,
                          orbb200_keypoint *keypoints, uint8_t *descriptors, int32_t *counts, int cap);
 
+/* The same call split in two, for a caller that streams batches: _async returns once the uploads, kernels
+ * and downloads are queued; _wait blocks until the results are in the output arrays and reports device-side
+ * failures.  `images` and the three output arrays must stay valid until _wait returns and should be
+ * page-locked (cudaHostAlloc / cudaHostRegister), otherwise the copies serialise with the host.  One call is
+ * in flight per handle (a second _async first waits for the first).  To overlap the upload of batch k+1 with
+ * the kernels of batch k, alternate between two or three handles (measured on B200: three handles reach the
+ * device-resident rate; the blocking call, which can only overlap inside one batch, reaches ~60 % of it). */
+int orbb200_extract_host_async(orbb200_extractor *h, const uint8_t *images, int batch, size_t stride,
+                               size_t frame_stride, orbb200_keypoint *keypoints, uint8_t *descriptors,
+                               int32_t *counts, int cap);
+int orbb200_extract_host_wait(orbb200_extractor *h);
+
 /* Same, for frames already in DEVICE memory; outputs stay on the device.  Asynchronous on
  * the handle's stream; orbb200_extractor_sync() waits.  d_keypoints/d_descriptors/d_counts
  * may be NULL to use handle-owned buffers (fetch them with orbb200_extractor_outputs). */

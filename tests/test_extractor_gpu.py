@@ -106,6 +106,41 @@ def test_tables_match_oracle():
     assert np.array_equal(ex.umax, orc.umax)
 
 
+def test_streaming_extractor_equals_blocking_call():
+    """orbb200_extract_host_async on three handles in turn (StreamingExtractor): seven different batches in
+    flight back to back give byte-for-byte what the blocking call gives, and one frame is checked against the
+    oracle; waiting twice and draining an idle stream are no-ops."""
+    import torch
+    from weiner_slamit_v2_b200 import StreamingExtractor
+    B, NB = 8, 7
+    batches = [np.stack([synthetic_frame(300 + 8 * k + i) for i in range(B)]) for k in range(NB)]
+    batches[3][2] = 0                                       # an empty frame
+    ex = ORBextractor(*PARAMS, max_batch=B)
+    want = [ex.extract_batch(b) for b in batches]
+    sx = StreamingExtractor(*PARAMS, max_batch=B, depth=3)
+    sx.drain()
+    cap = sx.max_keypoints
+    pin = [torch.from_numpy(b).pin_memory() for b in batches]
+    outs = [(torch.zeros((B, cap, 28), dtype=torch.uint8).pin_memory(), torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory(),
+             torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(NB)]
+    for k in range(NB):
+        slot = sx.submit(pin[k], B, 640, 640 * 480, *outs[k], cap)
+        assert slot == k % 3
+    sx.drain(); sx.drain()
+    for k in range(NB):
+        kw, dw, cw = want[k]
+        kk, dd, cc = (o.numpy() for o in outs[k])
+        assert np.array_equal(cc, cw), k
+        for f in range(B):
+            n = cw[f]
+            assert kk[f, :n].tobytes() == kw[f, :n].tobytes() and np.array_equal(dd[f, :n], dw[f, :n]), (k, f)
+    orc = O.OracleExtractor(*PARAMS)
+    ko, do = orc(batches[5][1])
+    n = outs[5][2].numpy()[1]
+    assert n == len(ko) and outs[5][0].numpy()[1, :n].tobytes() == ko.tobytes() and np.array_equal(outs[5][1].numpy()[1, :n], do)
+    sx.close()
+
+
 def test_chunked_host_pipeline_batch64_equals_per_frame_results():
     """The host entry point splits large batches into chunks that overlap H2D, kernels and D2H; every
     frame must come out exactly as when it is extracted alone, and a few are checked against the oracle."""

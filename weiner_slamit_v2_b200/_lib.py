@@ -51,6 +51,8 @@ SIGNATURES = {
     "orbb200_extractor_max_keypoints": (C.c_int, [vp]),
     "orbb200_extractor_level_size": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "orbb200_extract_host": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int]),
+    "orbb200_extract_host_async": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int]),
+    "orbb200_extract_host_wait": (C.c_int, [vp]),
     "orbb200_extract_device": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int]),
     "orbb200_extractor_sync": (C.c_int, [vp]),
     "orbb200_extractor_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int)]),

@@ -1078,6 +1078,7 @@ struct orbb200_extractor {
     bool profiling; cudaEvent_t ev[6];   // stage boundaries of the last call: resize | fast | quadtree | blur | describe
     cudaStream_t copyIn, copyOut;        // host path: H2D and D2H run beside the kernels, chunk by chunk
     cudaEvent_t evIn[8], evDone[8];
+    bool pending;                        // an orbb200_extract_host_async call has not been waited for yet
     std::vector<void*> allocs;
 };
 
@@ -1474,19 +1475,34 @@ extern "C" int orbb200_extractor_outputs(orbb200_extractor* h, orbb200_keypoint*
     return ORBB200_OK;
 }
 
-extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images, int batch, size_t stride,
-                                    size_t frame_stride, orbb200_keypoint* keypoints, uint8_t* descriptors,
-                                    int32_t* counts, int cap)
+extern "C" int orbb200_extract_host_wait(orbb200_extractor* h)
+{
+    if (!h) { set_error("null handle"); return ORBB200_EINVAL; }
+    if (!h->pending) return ORBB200_OK;
+    ORB_CUDA(cudaSetDevice(h->device));
+    h->pending = false;
+    ORB_CUDA(cudaStreamSynchronize(h->copyOut));
+    return check_status(h);
+}
+
+// `chunks` = pieces the batch is cut into so that copies and kernels of ONE call overlap (0 = choose).
+static int extract_host_queue(orbb200_extractor* h, const uint8_t* images, int batch, size_t stride,
+                              size_t frame_stride, orbb200_keypoint* keypoints, uint8_t* descriptors,
+                              int32_t* counts, int cap, int chunks)
 {
     if (!h || !images || !keypoints || !descriptors || !counts) { set_error("null argument"); return ORBB200_EINVAL; }
     if (batch < 1 || batch > h->maxBatch) { set_error("batch %d outside 1..%d", batch, h->maxBatch); return ORBB200_EINVAL; }
     if (stride < (size_t)h->width) { set_error("stride smaller than the frame width"); return ORBB200_EINVAL; }
     if (cap < h->maxKp) { set_error("cap %d < orbb200_extractor_max_keypoints() = %d", cap, h->maxKp); return ORBB200_ECAPACITY; }
     ORB_CUDA(cudaSetDevice(h->device));
+    if (h->pending) {           // one call in flight per handle: its buffers are about to be overwritten
+        int rc = orbb200_extract_host_wait(h);
+        if (rc != ORBB200_OK) return rc;
+    }
     // Chunked pipeline: while chunk c is in the kernels, chunk c+1 is on its way up and chunk c-1 on its way
     // down (three streams, events between them).  Small batches go through in one piece.
-    int nchunk = batch >= 96 ? 3 : (batch >= 32 ? 2 : 1);       // measured on B200 + PCIe gen5: 2-3 chunks are best at batch 256
-    if (const char* e = getenv("ORBB200_CHUNKS")) nchunk = std::max(1, std::min(8, std::min(batch, atoi(e))));   // tuning knob
+    int nchunk = chunks > 0 ? chunks : (batch >= 96 ? 3 : (batch >= 32 ? 2 : 1));   // measured on B200 + PCIe gen5: 2-3 chunks are best at batch 256
+    if (const char* e = chunks > 0 ? nullptr : getenv("ORBB200_CHUNKS")) nchunk = std::max(1, std::min(8, std::min(batch, atoi(e))));   // tuning knob
     const int cs = (batch + nchunk - 1) / nchunk;
     const int mk = h->maxKp;
     const size_t inFrameBytes = h->inPitch * (size_t)h->height;
@@ -1527,8 +1543,25 @@ extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images,
     }
     h->lastBatch = batch; h->lastIn = h->dIn; h->lastInPitch = (int)h->inPitch; h->lastInFrameStride = (long long)inFrameBytes;
     h->lastLaunches *= nchunk;
-    ORB_CUDA(cudaStreamSynchronize(h->copyOut));
-    return check_status(h);
+    h->pending = true;
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_extract_host(orbb200_extractor* h, const uint8_t* images, int batch, size_t stride,
+                                    size_t frame_stride, orbb200_keypoint* keypoints, uint8_t* descriptors,
+                                    int32_t* counts, int cap)
+{
+    int rc = extract_host_queue(h, images, batch, stride, frame_stride, keypoints, descriptors, counts, cap, 0);
+    if (rc != ORBB200_OK) return rc;
+    return orbb200_extract_host_wait(h);
+}
+
+// A streaming caller overlaps across calls (two or three handles in turn), where whole batches run best.
+extern "C" int orbb200_extract_host_async(orbb200_extractor* h, const uint8_t* images, int batch, size_t stride,
+                                          size_t frame_stride, orbb200_keypoint* keypoints, uint8_t* descriptors,
+                                          int32_t* counts, int cap)
+{
+    return extract_host_queue(h, images, batch, stride, frame_stride, keypoints, descriptors, counts, cap, 1);
 }
 
 // ---- stage read-back -------------------------------------------------------------------

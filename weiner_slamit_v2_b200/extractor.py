@@ -85,6 +85,15 @@ class ORBextractor:
                                            kps.ctypes.data, desc.ctypes.data, counts.ctypes.data, cap))
         return kps, desc, counts
 
+    def extract_host_async(self, images, batch, stride, frame_stride, kps, desc, counts, cap):
+        """Queue one batch from (page-locked) host memory; arguments are arrays, tensors or raw addresses.
+        wait() makes the results visible.  One call in flight per handle (see StreamingExtractor)."""
+        check(self._L.orbb200_extract_host_async(self._h, addr(images), batch, stride, frame_stride, addr(kps),
+                                                 addr(desc), addr(counts), cap))
+
+    def wait(self):
+        check(self._L.orbb200_extract_host_wait(self._h))
+
     def extract_device(self, d_images, batch, stride, frame_stride, d_kps=None, d_desc=None, d_counts=None, cap=0):
         """Asynchronous: frames already in device memory (torch tensors or raw addresses)."""
         check(self._L.orbb200_extract_device(self._h, addr(d_images), batch, stride, frame_stride, addr(d_kps),
@@ -136,3 +145,40 @@ class ORBextractor:
 
     def get_level_keypoints(self, frame, level):
         return self._packed(self._L.orbb200_extractor_get_level_keypoints, frame, level, self.max_keypoints)
+
+
+class StreamingExtractor:
+    """A stream of host batches through `depth` extractor handles used in turn, so that the upload of batch
+    k+1 and the download of batch k-1 run beside the kernels of batch k (each handle has its own streams and
+    slabs; include/orb_b200.h, orbb200_extract_host_async).  submit() returns the index of the slot it used;
+    that slot's previous batch is complete when submit() returns, and every batch is complete after drain().
+    Host buffers should be page-locked."""
+
+    def __init__(self, *args, depth=3, **kw):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.handles = [ORBextractor(*args, **kw) for _ in range(depth)]
+        self._next = 0
+
+    @property
+    def max_keypoints(self): return self.handles[0].max_keypoints
+
+    def submit(self, images, batch, stride, frame_stride, kps, desc, counts, cap):
+        slot = self._next
+        self._next = (slot + 1) % len(self.handles)
+        self.handles[slot].extract_host_async(images, batch, stride, frame_stride, kps, desc, counts, cap)
+        return slot
+
+    def wait(self, slot):
+        self.handles[slot].wait()
+
+    def drain(self):
+        for h in self.handles:
+            h.wait()
+
+    @property
+    def last_launches(self): return sum(h.last_launches for h in self.handles)
+
+    def close(self):
+        for h in self.handles:
+            h.close()
