@@ -969,22 +969,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParam
     while (l + 1 < P.nlevels && idx >= P.lv[l + 1].kpOff) l++;
     const LevelGeo& g = P.lv[l];
     const int i = idx - g.kpOff;
-    const int* counts = P.lkpCount + frame * P.nlevels;
-    if (i >= counts[l]) {
-        if (idx == 0 && lane == 0) {            // level 0 empty: this warp still publishes the frame total
-            int tot = 0;
-            for (int q = 0; q < P.nlevels; q++) tot += counts[q];
-            P.outCount[frame] = tot;
-        }
-        return;
+    // lane q holds level q's keypoint count: the slot's output offset and the frame total are two warp sums
+    const int cnt = lane < P.nlevels ? __ldg(P.lkpCount + frame * P.nlevels + lane) : 0;
+    const int off = __reduce_add_sync(0xffffffffu, lane < l ? cnt : 0);
+    if (idx == 0) {                             // slot 0 publishes the frame total (also when level 0 is empty)
+        const int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) P.outCount[frame] = tot;
     }
-    int off = 0;
-    for (int q = 0; q < l; q++) off += counts[q];
-    if (idx == 0 && lane == 0) {
-        int tot = 0;
-        for (int q = 0; q < P.nlevels; q++) tot += counts[q];
-        P.outCount[frame] = tot;
-    }
+    if (i >= __shfl_sync(0xffffffffu, cnt, l)) return;
     const int o = off + i;
     if (o >= P.outCap) { if (lane == 0) atomicOr(P.status, STATUS_KP_OVERFLOW); return; }
 
