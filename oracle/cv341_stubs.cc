@@ -81,6 +81,13 @@ public:
     void assign(const MatExpr& e, Mat& m, int = -1) const
     {
         const Mat& A = e.a;
+        if (e.flags & 2) {                                   // elementwise a - b
+            Mat d;
+            d.create(A.rows, A.cols, CV_32F);
+            for (int r = 0; r < A.rows; r++) for (int c = 0; c < A.cols; c++) d.at<float>(r, c) = A.at<float>(r, c) - e.b.at<float>(r, c);
+            m = d;
+            return;
+        }
         const bool tr = (e.flags & 1) != 0;
         const int ar = tr ? A.cols : A.rows, ac = tr ? A.rows : A.cols;
         auto a_at = [&](int r, int c) { return tr ? A.at<float>(c, r) : A.at<float>(r, c); };
@@ -112,5 +119,19 @@ MatExpr operator-(const MatExpr& e) { MatExpr r(e); r.alpha = -r.alpha; return r
 MatExpr operator*(const MatExpr& e, const Mat& m) { MatExpr r(e); r.b = m; return r; }
 MatExpr operator*(const Mat& a, const Mat& b) { return MatExpr(&g_miniOp, 0, a, b); }
 MatExpr operator+(const MatExpr& e, const Mat& m) { MatExpr r(e); r.c = m; return r; }
+MatExpr operator-(const Mat& a, const Mat& b) { return MatExpr(&g_miniOp, 2, a, b); }
+
+InputOutputArray noArray() { static _InputOutputArray none; return none; }
+
+// cv::norm, NORM_L2 of a continuous CV_32F array: squares accumulated in double in element order (core/src/stat.cpp, normL2_)
+double norm(InputArray src, int normType, InputArray)
+{
+    const Mat& m = *static_cast<const Mat*>(src.getObj());
+    CV_Assert(normType == NORM_L2 && m.type() == CV_32F && m.isContinuous());
+    double s = 0;
+    const float* p = m.ptr<float>();
+    for (size_t i = 0; i < m.total(); i++) s += (double)p[i] * (double)p[i];
+    return std::sqrt(s);
+}
 
 }  // namespace cv

@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include "../include/orb_b200_logf.inc"
 
 #define GRID_COLS 64   /* I/Frame.h:41 */
 #define GRID_ROWS 48   /* I/Frame.h:40 */
@@ -415,6 +416,145 @@ int orc_search_by_projection_last_frame(
         for (int k = 0; k < nhist; k++) {
             const int b = hist_bin[k];
             if (b != ind1 && b != ind2 && b != ind3) { kp_mp[hist_idx[k]] = -1; nmatches--; }   /* :1460-1465 */
+        }
+    }
+    free(hist_idx); free(hist_bin); free(cand); free(items);
+    return nmatches;
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * glibc >= 2.27 logf (ARM optimized-routines): table of 16 {1/c, log c}, degree-3 polynomial in double, one
+ * rounding to float.  MapPoint::PredictScale (S/MapPoint.cc:391-400) calls it through std::log(float), so the
+ * predicted pyramid level is only bit-identical with a bit-identical logf.  Identical to this machine's libm on
+ * every positive finite float (2,139,095,039 values checked; tests/test_oracle_primitives.py re-checks a sample). */
+float orc_logf(float x)
+{
+    static const struct { double invc, logc; } T[16] = { ORB_B200_LOGF_TABLE };
+    uint32_t ix;
+    memcpy(&ix, &x, 4);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2 == 0) return -INFINITY;
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return NAN;
+        const float xs = x * 0x1p23f;                       /* subnormal: normalise */
+        memcpy(&ix, &xs, 4);
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) % 16);
+    const int k = (int32_t)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    float zf;
+    memcpy(&zf, &iz, 4);
+    const double z = (double)zf;
+    const double r = z * T[i].invc - 1;
+    const double y0 = T[i].logc + (double)k * ORB_B200_LOGF_LN2;
+    const double r2 = r * r;
+    double y = ORB_B200_LOGF_A1 * r + ORB_B200_LOGF_A2;
+    y = ORB_B200_LOGF_A0 * r2 + y;
+    y = y * r2 + (y0 + r);
+    return (float)y;
+}
+
+/* MapPoint::PredictScale (S/MapPoint.cc:391-400): ceil(logf(mfMaxDistance / dist) / logScaleFactor), all float. */
+int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor)
+{
+    const float ratio = mf_max_distance / dist;
+    volatile float q = orc_logf(ratio);
+    q = q / log_scale_factor;
+    return (int)ceilf(q);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound,
+ * const float th, const int ORBdist) (S/ORBmatcher.cc:1476-1603), the relocalisation search.
+ * Flattened inputs: the key frame's map-point slots i = 0..nkf-1 with valid[i] = (pMP && !pMP->isBad() &&
+ * !sAlreadyFound.count(pMP)), world position, descriptor, raw mfMaxDistance / mfMinDistance (the invariance
+ * getters multiply by 1.2f / 0.8f, S/MapPoint.cc:379-389) and pKF->mvKeysUn[i].angle; the current frame as
+ * for the other searches; Ow = -Rcw^T tcw is an input (the caller's cv::Mat expression).  kp_mp in/out:
+ * CurrentFrame.mvpMapPoints as an index into the key frame's slots (-1 none, any other value = occupied).
+ * cv::norm of the 3-vector accumulates squares in double.
+ * The reference indexes mvScaleFactors with an unclamped predicted level (out of range for distances in
+ * [0.8 mfMin, mfMin) -- undefined behaviour, fixed upstream later by clamping); this restatement clamps to
+ * [0, nlevels-1] like the upstream fix, and the parity tests stay off that band. */
+int orc_search_by_projection_keyframe(
+    int nkf, const uint8_t *valid, const float *wpos, const uint8_t *mp_desc, const float *mf_max_distance,
+    const float *mf_min_distance, const float *kf_angle,
+    const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4],
+    int n, const float *kx, const float *ky, const int32_t *koct, const float *kang, const uint8_t *kdesc,
+    int32_t *kp_mp, int nlevels, const float *scale_factors, float log_scale_factor, const float bounds[4],
+    float th, int orb_dist, int check_orientation)
+{
+    int nmatches = 0;
+    orc_grid g;
+    int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    int *hist_bin = (int *)malloc(sizeof(int) * (nkf + 1));
+    int *hist_idx = (int *)malloc(sizeof(int) * (nkf + 1));
+    int nhist = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    orc_grid_bounds(&g, bounds);
+    orc_grid_assign(&g, n, kx, ky, koct, items);
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+
+    for (int i = 0; i < nkf; i++) {
+        if (!valid[i]) continue;
+        const float *X = wpos + 3 * (size_t)i;
+        float xc3[3];
+        for (int r = 0; r < 3; r++) {                       /* x3Dc = Rcw*x3Dw + tcw (:1503) */
+            volatile float t = Rcw[3 * r] * X[0];
+            volatile float t1 = Rcw[3 * r + 1] * X[1];
+            volatile float t2 = Rcw[3 * r + 2] * X[2];
+            t = t + t1;
+            t = t + t2;
+            xc3[r] = t + tcw[r];
+        }
+        const float invzc = (float)(1.0 / (double)xc3[2]);  /* no positive-depth test in this overload */
+        volatile float u = fx * xc3[0]; u = u * invzc; u = u + cx;
+        volatile float v = fy * xc3[1]; v = v * invzc; v = v + cy;
+        if (u < bounds[0] || u > bounds[2]) continue;
+        if (v < bounds[1] || v > bounds[3]) continue;
+        double ss = 0.0;                                    /* cv::norm(x3Dw - Ow) (:1518-1519) */
+        for (int r = 0; r < 3; r++) { const float po = X[r] - Ow[r]; ss += (double)po * (double)po; }
+        const float dist3D = (float)sqrt(ss);
+        const float maxDistance = 1.2f * mf_max_distance[i], minDistance = 0.8f * mf_min_distance[i];
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        int level = orc_predict_scale(mf_max_distance[i], dist3D, log_scale_factor);
+        if (level < 0) level = 0;
+        if (level >= nlevels) level = nlevels - 1;
+        const float radius = th * scale_factors[level];
+        const int nc = orc_features_in_area(&g, u, v, radius, level - 1, level + 1, cand, n);
+        if (nc == 0) continue;
+        const uint8_t *dm = mp_desc + 32 * (size_t)i;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (kp_mp[i2] != -1) continue;
+            const int dist = orc_descriptor_distance(dm, kdesc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            kp_mp[bestIdx2] = i;
+            nmatches++;
+            if (check_orientation) {
+                float rot = kf_angle[i] - kang[bestIdx2];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                hist_bin[nhist] = bin; hist_idx[nhist] = bestIdx2; nhist++;
+            }
+        }
+    }
+    if (check_orientation) {
+        int sizes[HISTO_LENGTH] = {0};
+        for (int k = 0; k < nhist; k++) sizes[hist_bin[k]]++;
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            const int b = hist_bin[k];
+            if (b != ind1 && b != ind2 && b != ind3) { kp_mp[hist_idx[k]] = -1; nmatches--; }   /* :1591-1597 */
         }
     }
     free(hist_idx); free(hist_bin); free(cand); free(items);

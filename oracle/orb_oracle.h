@@ -131,6 +131,15 @@ int orc_search_by_projection_last_frame(
 
 /* Frame glue: cv::undistortPoints(src, dst, K, dist, Mat(), K) as Frame::UndistortKeyPoints
  * calls it (S/Frame.cc:529-559), K = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2, k3}; and ComputeImageBounds. */
+float orc_logf(float x);
+int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
+int orc_search_by_projection_keyframe(
+    int nkf, const uint8_t *valid, const float *wpos, const uint8_t *mp_desc, const float *mf_max_distance,
+    const float *mf_min_distance, const float *kf_angle,
+    const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4],
+    int n, const float *kx, const float *ky, const int32_t *koct, const float *kang, const uint8_t *kdesc,
+    int32_t *kp_mp, int nlevels, const float *scale_factors, float log_scale_factor, const float bounds[4],
+    float th, int orb_dist, int check_orientation);
 void orc_undistort_points(int n, const float *xy_in, float *xy_out, const float K[4], const float dist[5]);
 void orc_image_bounds(int cols, int rows, const float K[4], const float dist[5], float bounds[4]);
 

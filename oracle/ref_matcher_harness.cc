@@ -176,4 +176,61 @@ int refm_search_by_projection_last_frame(
     std::free(mps); std::free(foreign);
     return cnt;
 }
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (S/ORBmatcher.cc:1476-1603).
+// valid[i] = 1: a good map point; 2: a map point that is in sAlreadyFound; 3: a bad map point; 0: empty slot.
+int refm_search_by_projection_keyframe(
+    int nkf, const uint8_t* valid, const float* wpos, const uint8_t* mp_desc, const float* mf_max_distance,
+    const float* mf_min_distance, const float* kf_angle,
+    const float* Rcw, const float* tcw, const float* K,
+    int n, const float* kx, const float* ky, const int32_t* koct, const float* kang, const uint8_t* kdesc,
+    int32_t* kp_mp, int nlevels, const float* scale_factors, float log_scale_factor, const float* bounds,
+    float th, int orb_dist, int check_orientation, float* Ow_out)
+{
+    Frame Cur;
+    fill_frame(Cur, n, kx, ky, koct, kang, kdesc, bounds);
+    Cur.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+    Cur.mfLogScaleFactor = log_scale_factor;
+    Frame::fx = K[0]; Frame::fy = K[1]; Frame::cx = K[2]; Frame::cy = K[3];
+    float T[16] = {Rcw[0], Rcw[1], Rcw[2], tcw[0], Rcw[3], Rcw[4], Rcw[5], tcw[1], Rcw[6], Rcw[7], Rcw[8], tcw[2], 0, 0, 0, 1};
+    Cur.mTcw = cv::Mat(4, 4, CV_32F, T);
+    if (Ow_out) {       // the caller's cv::Mat expression, evaluated the way the reference evaluates it here
+        const cv::Mat R = Cur.mTcw.rowRange(0, 3).colRange(0, 3), t = Cur.mTcw.rowRange(0, 3).col(3);
+        const cv::Mat Ow = -R.t() * t;
+        for (int r = 0; r < 3; r++) Ow_out[r] = Ow.at<float>(r);
+    }
+    KeyFrame* kf = (KeyFrame*)std::calloc(1, sizeof(KeyFrame));
+    new (&kf->mvpMapPoints) std::vector<MapPoint*>(nkf, static_cast<MapPoint*>(NULL));
+    std::vector<cv::KeyPoint>* kfKeys = const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn);
+    new (kfKeys) std::vector<cv::KeyPoint>(nkf);
+    MapPoint* mps = (MapPoint*)std::calloc(nkf > 0 ? nkf : 1, sizeof(MapPoint));
+    MapPoint* foreign = (MapPoint*)std::calloc(n > 0 ? n : 1, sizeof(MapPoint));
+    std::set<MapPoint*> found;
+    for (int i = 0; i < nkf; i++) {
+        MapPoint* p = &mps[i];
+        new (&p->mDescriptor) cv::Mat(1, 32, CV_8U, (void*)(mp_desc + 32 * (size_t)i));
+        new (&p->mWorldPos) cv::Mat(3, 1, CV_32F, (void*)(wpos + 3 * (size_t)i));
+        p->mfMaxDistance = mf_max_distance[i]; p->mfMinDistance = mf_min_distance[i];
+        p->mbBad = valid[i] == 3;
+        if (valid[i] == 2) found.insert(p);
+        kf->mvpMapPoints[i] = valid[i] ? p : NULL;
+        (*kfKeys)[i].angle = kf_angle[i];
+    }
+    for (int i = 0; i < n; i++) {
+        if (kp_mp[i] >= 0) Cur.mvpMapPoints[i] = &mps[kp_mp[i]];
+        else if (kp_mp[i] != -1) Cur.mvpMapPoints[i] = &foreign[i];
+    }
+    ORBmatcher matcher(0.9f, check_orientation != 0);
+    const int cnt = matcher.SearchByProjection(Cur, kf, found, th, orb_dist);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = Cur.mvpMapPoints[i];
+        if (!p) kp_mp[i] = -1;
+        else if (p >= mps && p < mps + nkf) kp_mp[i] = (int32_t)(p - mps);
+        else kp_mp[i] = -2;
+    }
+    for (int i = 0; i < nkf; i++) { mps[i].mDescriptor.~Mat(); mps[i].mWorldPos.~Mat(); }
+    kf->mvpMapPoints.~vector(); kfKeys->~vector();
+    std::free(mps); std::free(foreign); std::free(kf);
+    return cnt;
+}
 }

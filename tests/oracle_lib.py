@@ -318,3 +318,46 @@ def search_by_projection_last_frame(w, scale_factors, bounds, th=15.0, mode=0, c
             _ptr(a["kd"], _u8p), _ptr(a["kpmp"], _i32p), _ptr(a["kpobs"], _i32p),
             len(sf), _ptr(sf, _f32p), _ptr(bnd, _f32p), th, mode, int(check_ori))
     return cnt, a["kpmp"][:n]
+
+
+def _keyframe_args(w, kp_mp):
+    cur = w["cur"]
+    n = len(cur)
+    a = dict(valid=_b(w["valid"]), wpos=_f(w["wpos"]), mp_desc=_b(w["mp_desc"]), mfmax=_f(w["mf_max"]), mfmin=_f(w["mf_min"]),
+             kfang=_f(w["kf_angle"]), R=_f(w["Rcw"]), t=_f(w["tcw"]), Ow=_f(w["Ow"]), K=_f(w["K"]),
+             kx=_f(cur["x"]), ky=_f(cur["y"]), ko=_i(cur["octave"]), ka=_f(cur["angle"]), kd=_b(w["cdesc"]),
+             kpmp=_i(w["kp_mp"] if kp_mp is None else kp_mp).copy())
+    if n == 0:
+        a["kpmp"] = np.full(1, -1, np.int32)
+    return a, n
+
+
+def search_by_projection_keyframe(w, scale_factors, bounds, th=10.0, orb_dist=100, check_ori=True, kp_mp=None):
+    """w: workloads.relocalisation_frame() dict.  The oracle treats valid == 1 as a usable map point."""
+    L = lib()
+    L.orc_search_by_projection_keyframe.argtypes = [
+        C.c_int, _u8p, _f32p, _u8p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+        C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p, C.c_int, _f32p, C.c_float, _f32p,
+        C.c_float, C.c_int, C.c_int]
+    L.orc_search_by_projection_keyframe.restype = C.c_int
+    a, n = _keyframe_args(w, kp_mp)
+    ok = _b((a["valid"] == 1).astype(np.uint8))
+    sf, bnd = _f(scale_factors), _bounds(bounds)
+    cnt = L.orc_search_by_projection_keyframe(
+        len(ok), _ptr(ok, _u8p), _ptr(a["wpos"], _f32p), _ptr(a["mp_desc"], _u8p), _ptr(a["mfmax"], _f32p),
+        _ptr(a["mfmin"], _f32p), _ptr(a["kfang"], _f32p), _ptr(a["R"], _f32p), _ptr(a["t"], _f32p), _ptr(a["Ow"], _f32p),
+        _ptr(a["K"], _f32p), n, _ptr(a["kx"], _f32p), _ptr(a["ky"], _f32p), _ptr(a["ko"], _i32p), _ptr(a["ka"], _f32p),
+        _ptr(a["kd"], _u8p), _ptr(a["kpmp"], _i32p), len(sf), _ptr(sf, _f32p), float(w["log_scale"]), _ptr(bnd, _f32p),
+        th, orb_dist, int(check_ori))
+    return cnt, a["kpmp"][:n]
+
+
+def logf(x):
+    L = lib()
+    L.orc_logf.argtypes = [C.c_float]; L.orc_logf.restype = C.c_float
+    return L.orc_logf(float(x))
+
+
+def logf_array(x):
+    """orc_logf over a float32 array (loop in C via ctypes is slow; fine for ~1e5 samples)."""
+    return np.array([logf(v) for v in np.asarray(x, np.float32)], np.float32)

@@ -178,3 +178,26 @@ def ref_search_by_projection_last_frame(w, scale_factors, bounds, th=15.0, check
         args[-2] = 1
         return L.refm_search_by_projection_last_frame(*args)
     return O.search_by_projection_last_frame(w, scale_factors, bounds, th, 0, check_ori, mbf, kp_mp, kp_mp_obs, kuright, fn=call)
+
+
+def ref_search_by_projection_keyframe(w, scale_factors, bounds, th=10.0, orb_dist=100, check_ori=True, kp_mp=None):
+    """The reference's own SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist).  Also returns Ow as
+    the harness's cv::Mat expression evaluates it."""
+    import oracle_lib as O
+    L = mlib()
+    L.refm_search_by_projection_keyframe.argtypes = [
+        C.c_int, _u8p, _f32p, _u8p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+        C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p, C.c_int, _f32p, C.c_float, _f32p,
+        C.c_float, C.c_int, C.c_int, _f32p]
+    L.refm_search_by_projection_keyframe.restype = C.c_int
+    a, n = O._keyframe_args(w, kp_mp)
+    sf, bnd = O._f(scale_factors), O._bounds(bounds)
+    ow = np.zeros(3, np.float32)
+    P = O._ptr
+    cnt = L.refm_search_by_projection_keyframe(
+        len(a["valid"]), P(a["valid"], _u8p), P(a["wpos"], _f32p), P(a["mp_desc"], _u8p), P(a["mfmax"], _f32p),
+        P(a["mfmin"], _f32p), P(a["kfang"], _f32p), P(a["R"], _f32p), P(a["t"], _f32p), P(a["K"], _f32p),
+        n, P(a["kx"], _f32p), P(a["ky"], _f32p), P(a["ko"], _i32p), P(a["ka"], _f32p), P(a["kd"], _u8p),
+        P(a["kpmp"], _i32p), len(sf), P(sf, _f32p), float(w["log_scale"]), P(bnd, _f32p), th, orb_dist, int(check_ori),
+        P(ow, _f32p))
+    return cnt, a["kpmp"][:n], ow

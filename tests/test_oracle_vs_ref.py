@@ -164,7 +164,14 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
     from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
     g = np.load(path)
-    if "lastframe" in os.path.basename(path):
+    if "keyframe" in os.path.basename(path):
+        from weiner_slamit_v2_b200.workloads import relocalisation_frame
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            a = O.search_by_projection_keyframe(relocalisation_frame(int(c[0])), SCALE_FACTORS_8, (-13.7, -9.2, 661.3, 492.8),
+                                                float(c[1]), int(c[2]), bool(c[3]))
+            assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["kpmp_%d" % i])
+    elif "lastframe" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import motion_frame
         for i in range(int(g["count"])):
             idx, th, ori = int(g["cfg_%d" % i][0]), float(g["cfg_%d" % i][1]), bool(g["cfg_%d" % i][2])
@@ -207,3 +214,17 @@ def test_search_by_projection_last_frame_matches_reference(th, ori):
         a = O.search_by_projection_last_frame(w, SCALE_FACTORS_8, bounds, th, 0, ori, 40.0, pre, obs)
         b = R.ref_search_by_projection_last_frame(w, SCALE_FACTORS_8, bounds, th, ori, 40.0, pre, obs)
         assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+@needs_refm
+@pytest.mark.parametrize("th,orb_dist,ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
+def test_search_by_projection_keyframe_matches_reference(th, orb_dist, ori):
+    """The relocalisation overload (S/ORBmatcher.cc:1476-1603) against the reference's own code, including
+    MapPoint::PredictScale (logf) and cv::norm; Ow as the harness evaluates -Rcw.t()*tcw equals the workload's."""
+    from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, relocalisation_frame
+    for idx, bounds in enumerate(((0.0, 0.0, 640.0, 480.0), (-13.7, -9.2, 661.3, 492.8), (0.0, 0.0, 640.0, 480.0))):
+        w = relocalisation_frame(900 + idx, n_kf=1500 if idx < 2 else 40, n_cur=2000 if idx < 2 else 60)
+        a = O.search_by_projection_keyframe(w, SCALE_FACTORS_8, bounds, th, orb_dist, ori)
+        b = R.ref_search_by_projection_keyframe(w, SCALE_FACTORS_8, bounds, th, orb_dist, ori)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(b[2], w["Ow"])
+        assert idx == 2 or a[0] > 100

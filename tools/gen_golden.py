@@ -80,3 +80,14 @@ for i, (idx, th, ori) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_lastframe.npz"), **out)
 print("ref_match_lastframe.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+from weiner_slamit_v2_b200.workloads import relocalisation_frame  # noqa: E402
+cfgs = [(800, 10.0, 100, 1), (801, 3.0, 64, 1), (802, 10.0, 100, 0)]
+for i, (idx, th, od, ori) in enumerate(cfgs):
+    w = relocalisation_frame(idx)
+    r = R.ref_search_by_projection_keyframe(w, SCALE_FACTORS_8, (-13.7, -9.2, 661.3, 492.8), th, od, bool(ori))
+    out["cfg_%d" % i] = np.array([idx, th, od, ori]); out["n_%d" % i] = r[0]; out["kpmp_%d" % i] = r[1]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_keyframe.npz"), **out)
+print("ref_match_keyframe.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])

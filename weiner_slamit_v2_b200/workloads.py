@@ -110,3 +110,65 @@ def motion_frame(index, n_last=1500, n_cur=2000, width=640, height=480, nlevels=
     return dict(has_mp=has_mp, outlier=outlier, wpos=wpos, mp_desc=mp_desc, mp_obs=mp_obs,
                 last_octave=last["octave"].astype(np.int32), last_angle=last["angle"].astype(np.float32),
                 Rcw=R.reshape(9), tcw=t, K=np.array(K, np.float32), cur=cur, cdesc=cdesc)
+
+
+def camera_centre(Rcw, tcw):
+    """Ow = -Rcw^T tcw in float32, products and sums in source order (the 3x3 cv::Mat expression of
+    S/ORBmatcher.cc:1482 as the oracle's harness evaluates it)."""
+    R = np.asarray(Rcw, np.float32).reshape(3, 3)
+    t = np.asarray(tcw, np.float32)
+    out = np.zeros(3, np.float32)
+    for r in range(3):
+        acc = np.float32(R[0, r] * t[0])
+        acc = np.float32(acc + np.float32(R[1, r] * t[1]))
+        acc = np.float32(acc + np.float32(R[2, r] * t[2]))
+        out[r] = -acc
+    return out
+
+
+def relocalisation_frame(index, n_kf=1500, n_cur=2000, width=640, height=480, nlevels=8, scale=1.2,
+                         K=(526.69, 540.36, 313.07, 238.39)):
+    """A (current frame, key frame) pair for SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)
+    (relocalisation): key-frame map-point slots with world positions and scale-invariance distances, some empty
+    (valid 0), already found (2) or bad (3); the current frame's keypoints sit near the projections at about the
+    predicted level.  Includes projections outside the image, points behind the camera, distances outside
+    [0.8 min, 1.2 max] and pre-occupied keypoints; stays off the band [0.8 min, min) where the reference
+    indexes mvScaleFactors out of range."""
+    rng = np.random.default_rng(130000 + index)
+    fx, fy, cx, cy = K
+    axis = rng.normal(size=3); axis /= np.linalg.norm(axis)
+    ang = np.deg2rad(rng.uniform(2.0, 25.0))
+    Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = (np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx).astype(np.float32)
+    t = rng.normal(0, 0.5, 3).astype(np.float32)
+    u = rng.uniform(-20, width + 20, n_kf); v = rng.uniform(-20, height + 20, n_kf)
+    z = rng.uniform(1.0, 10.0, n_kf)
+    z[rng.random(n_kf) < 0.03] *= -1
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    wpos = ((Xc - t) @ R.astype(np.float64)).astype(np.float32)
+    Ow = camera_centre(R, t)
+    dist = np.linalg.norm(wpos.astype(np.float64) - Ow, axis=1)
+    level = rng.integers(0, nlevels, n_kf)
+    expo = level - 0.5 + rng.uniform(-0.3, 0.3, n_kf)
+    kind = rng.random(n_kf)
+    expo = np.where(kind < 0.04, -2.0, expo)                      # too far: dist > 1.2 mfMax
+    expo = np.where(kind > 0.96, nlevels + 2.0, expo)             # too close: dist < 0.8 mfMin
+    mf_max = (dist * scale ** expo).astype(np.float32)
+    mf_min = (mf_max / np.float32(scale ** (nlevels - 1))).astype(np.float32)
+    valid = rng.choice(np.array([0, 1, 2, 3], np.uint8), n_kf, p=[0.08, 0.80, 0.07, 0.05])
+    mp_desc = rng.integers(0, 256, (n_kf, 32)).astype(np.uint8)
+    kf_angle = rng.uniform(0, 360, n_kf).astype(np.float32)
+    cur = random_keypoints(n_cur, width, height, rng, nlevels)
+    src = rng.integers(0, n_kf, n_cur)
+    re = rng.random(n_cur) < 0.8
+    cur["x"] = np.where(re, np.clip(u[src] + rng.normal(0, 2.5, n_cur), 0, width - 1), cur["x"]).astype(np.float32)
+    cur["y"] = np.where(re, np.clip(v[src] + rng.normal(0, 2.5, n_cur), 0, height - 1), cur["y"]).astype(np.float32)
+    cur["octave"] = np.where(re, np.clip(level[src] + rng.integers(-1, 2, n_cur), 0, nlevels - 1), cur["octave"])
+    rot = rng.uniform(0, 40)
+    cur["angle"] = np.where(re, np.mod(kf_angle[src] - rot + rng.normal(0, 5, n_cur), 360), cur["angle"]).astype(np.float32)
+    cdesc = rng.integers(0, 256, (n_cur, 32)).astype(np.uint8)
+    cdesc[re] = flip_bits(mp_desc[src[re]], rng.integers(0, 130, int(re.sum())), rng)
+    kp_mp = np.where(rng.random(n_cur) < 0.1, -2, -1).astype(np.int32)     # keypoints that already hold a map point
+    return dict(valid=valid, wpos=wpos, mp_desc=mp_desc, mf_max=mf_max, mf_min=mf_min, kf_angle=kf_angle,
+                Rcw=R.reshape(9), tcw=t, Ow=Ow, K=np.array(K, np.float32), cur=cur, cdesc=cdesc, kp_mp=kp_mp,
+                log_scale=np.float32(np.log(np.float32(scale))))
