@@ -457,6 +457,35 @@ def run_matching(local, steps):
         "workload": "512 frame pairs, 1500 last-frame map points projected into 2000 keypoints, th=15, mono, checkOri",
         "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "map_points_per_s": items * nl / ms * 1e3,
         "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    # ---- scope row N2, relocalisation: SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)
+    from weiner_slamit_v2_b200._lib import KeyFrameView
+    from weiner_slamit_v2_b200.workloads import relocalisation_frame
+    ws = [relocalisation_frame(i, nl, nk) for i in range(distinct)]
+    tk = dict(n=up(np.full(items, nk, np.int32)), x=up(tile(np.stack([w["cur"]["x"] for w in ws]), items)),
+              y=up(tile(np.stack([w["cur"]["y"] for w in ws]), items)), o=up(tile(np.stack([w["cur"]["octave"] for w in ws]), items)),
+              a=up(tile(np.stack([w["cur"]["angle"] for w in ws]), items)), d=up(tile(np.stack([w["cdesc"] for w in ws]), items)))
+    kv = FrameView(tk["n"].data_ptr(), tk["x"].data_ptr(), tk["y"].data_ptr(), tk["o"].data_ptr(), tk["a"].data_ptr(), tk["d"].data_ptr(), nk)
+    tq = {k: up(tile(np.stack([w[k] for w in ws]), items)) for k in ["wpos", "mp_desc", "mf_max", "mf_min", "kf_angle"]}
+    tq["valid"] = up(tile(np.stack([(w["valid"] == 1).astype(np.uint8) for w in ws]), items))
+    tq["n"] = up(np.full(items, nl, np.int32))
+    qv = KeyFrameView(tq["n"].data_ptr(), tq["valid"].data_ptr(), tq["wpos"].data_ptr(), tq["mp_desc"].data_ptr(), tq["mf_max"].data_ptr(),
+                      tq["mf_min"].data_ptr(), tq["kf_angle"].data_ptr(), nl)
+    Rc = up(tile(np.stack([w["Rcw"] for w in ws]), items)); tc = up(tile(np.stack([w["tcw"] for w in ws]), items))
+    Oc = up(tile(np.stack([w["Ow"] for w in ws]), items))
+    pre = up(tile(np.stack([w["kp_mp"] for w in ws]), items))
+    kpmp4 = torch.empty((items, nk), dtype=torch.int32, device=dev)
+    nm4 = torch.empty(items, dtype=torch.int32, device=dev)
+    def reloc_step():
+        kpmp4.copy_(pre)
+        check(L.orbb200_search_by_projection_keyframe(h, items, C.byref(kv), C.byref(qv), Rc.data_ptr(), tc.data_ptr(), Oc.data_ptr(),
+                                                      Kc.ctypes.data, kpmp4.data_ptr(), sf.data_ptr(), 8, float(ws[0]["log_scale"]),
+                                                      b3.ctypes.data, 10.0, 100, 1, nm4.data_ptr(), 1))
+    ms = timed(L.orbb200_matcher_stream(h), reloc_step, steps)
+    acc = int(nm4.sum())
+    out["search_by_projection_keyframe"] = {
+        "workload": "512 (frame, key frame) pairs, 1500 key-frame map points projected into 2000 keypoints, th=10, ORBdist=100, checkOri",
+        "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "map_points_per_s": items * nl / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
     L.orbb200_matcher_destroy(h)
     return out
 

@@ -212,6 +212,34 @@ int orbb200_search_by_projection_last_frame(orbb200_matcher *m, int items, const
                                             const float bounds[4], float th, int mode, int check_orientation,
                                             int32_t *nmatches, int on_device);
 
+/* The map-point slots of a key frame (pKF->GetMapPointMatches()), items x stride each: valid[i] = the slot holds a
+ * map point that is not bad and not in sAlreadyFound; max_distance / min_distance = the raw mfMaxDistance /
+ * mfMinDistance (the invariance getters' 1.2f / 0.8f factors, S/MapPoint.cc:379-389, are applied on the device);
+ * angle = pKF->mvKeysUn[i].angle (may be NULL when check_orientation is 0). */
+typedef struct orbb200_keyframe_view {
+    const int32_t *n;
+    const uint8_t *valid;
+    const float *world_pos;       /* x3 */
+    const uint8_t *mp_desc;       /* x32 */
+    const float *max_distance, *min_distance;
+    const float *angle;
+    int stride;
+} orbb200_keyframe_view;
+
+/* Replaces ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound,
+ * const float th, const int ORBdist) (S/ORBmatcher.cc:1476-1603, the relocalisation search; scope row N2) for
+ * `items` independent (frame, key frame) pairs.  Rcw / tcw as above; Ow: items x 3 = -Rcw^T tcw (the caller's
+ * cv::Mat expression, :1482); log_scale_factor = CurrentFrame.mfLogScaleFactor.  kp_mp: items x cur.stride in/out =
+ * CurrentFrame.mvpMapPoints as an index into the key frame's slots (-1 none; any other value marks a keypoint that
+ * already holds a map point and is skipped).  The predicted level (MapPoint::PredictScale, glibc-exact logf) is
+ * clamped to [0, nlevels-1]; the reference leaves it unclamped and indexes mvScaleFactors out of range for
+ * distances in [0.8 mfMin, mfMin). */
+int orbb200_search_by_projection_keyframe(orbb200_matcher *m, int items, const orbb200_frame_view *cur,
+                                          const orbb200_keyframe_view *kf, const float *Rcw, const float *tcw,
+                                          const float *Ow, const float K[4], int32_t *kp_mp, const float *scale_factors,
+                                          int nlevels, float log_scale_factor, const float bounds[4], float th,
+                                          int orb_dist, int check_orientation, int32_t *nmatches, int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

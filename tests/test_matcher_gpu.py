@@ -148,3 +148,43 @@ def test_search_by_projection_last_frame_matches_oracle(th, mode, ori):
         assert np.array_equal(frames[i].mvpMapPoints, kpmp)
         tot += cnt
     assert tot > 200
+
+
+@pytest.mark.parametrize("th,orb_dist,ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False), (25.0, 255, True), (10.0, 0, True)])
+def test_search_by_projection_keyframe_matches_oracle(th, orb_dist, ori):
+    """Scope row N2, relocalisation overload: SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) for a
+    batch of (frame, key frame) pairs of different sizes, incl. an empty key frame; predicted levels (logf) included."""
+    from weiner_slamit_v2_b200.workloads import relocalisation_frame
+    sizes = [(1500, 2000), (1500, 2000), (700, 900), (0, 300), (40, 60)]
+    ws = [relocalisation_frame(40 + i, n_kf=a, n_cur=b) for i, (a, b) in enumerate(sizes)]
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    m = ORBmatcher(0.9, ori, max_items=len(ws), max_points=2000)
+    frames = []
+    for w in ws:
+        f = Frame(w["cur"], w["cdesc"], 640, 480, SCALE_FACTORS_8, bounds=bounds)
+        f.mvpMapPoints[:] = w["kp_mp"]
+        frames.append(f)
+    nm = m.search_by_projection_keyframe_batch(frames, ws, th, orb_dist)
+    tot = 0
+    for i, w in enumerate(ws):
+        cnt, kpmp = O.search_by_projection_keyframe(w, SCALE_FACTORS_8, bounds, th, orb_dist, ori)
+        assert nm[i] == cnt, (i, nm[i], cnt)
+        assert np.array_equal(frames[i].mvpMapPoints, kpmp), i
+        tot += cnt
+    assert tot > 400 or orb_dist == 0
+
+
+def test_search_by_projection_keyframe_reproduces_reference_golden_vectors():
+    """tests/golden/ref_match_keyframe.npz was produced by the reference's own ORBmatcher.cc (tools/gen_golden.py)."""
+    import os
+    from weiner_slamit_v2_b200.workloads import relocalisation_frame
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_keyframe.npz"))
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    for i in range(int(g["count"])):
+        c = g["cfg_%d" % i]
+        w = relocalisation_frame(int(c[0]))
+        m = ORBmatcher(0.9, bool(c[3]), max_items=1, max_points=2000)
+        f = Frame(w["cur"], w["cdesc"], 640, 480, SCALE_FACTORS_8, bounds=bounds)
+        f.mvpMapPoints[:] = w["kp_mp"]
+        nm = m.search_by_projection_keyframe_batch([f], [w], float(c[1]), int(c[2]))
+        assert nm[0] == int(g["n_%d" % i]) and np.array_equal(f.mvpMapPoints, g["kpmp_%d" % i])

@@ -38,6 +38,11 @@ class LastFrameView(C.Structure):
                 ("octave", vp), ("angle", vp), ("stride", C.c_int)]
 
 
+class KeyFrameView(C.Structure):
+    _fields_ = [("n", vp), ("valid", vp), ("world_pos", vp), ("mp_desc", vp), ("max_distance", vp), ("min_distance", vp),
+                ("angle", vp), ("stride", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/orb_b200.h declares
 SIGNATURES = {
     "orbb200_last_error": (C.c_char_p, []),
@@ -76,6 +81,8 @@ SIGNATURES = {
     "orbb200_search_by_projection_last_frame": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), vp, C.POINTER(LastFrameView), vp, vp,
                                                           vp, C.c_float, vp, vp, vp, C.c_int, vp, C.c_float, C.c_int, C.c_int,
                                                           vp, C.c_int]),
+    "orbb200_search_by_projection_keyframe": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), C.POINTER(KeyFrameView), vp, vp, vp, vp,
+                                                        vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_int, C.c_int, vp, C.c_int]),
     "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

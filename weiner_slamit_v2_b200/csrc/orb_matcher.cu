@@ -17,7 +17,9 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include <math_constants.h>
 #include "common.cuh"
+#include "../../include/orb_b200_logf.inc"
 
 namespace orbb200 {
 
@@ -679,17 +681,53 @@ struct LastParams {
     int *histBin, *histIdx;     // items x lastStride scratch
     int items, mode, checkOri;
     float th;
+    // kind 1 = the key-frame (relocalisation) overload (:1476-1603): hasMp = "usable map point", no outlier flags,
+    // level from MapPoint::PredictScale, any held keypoint is skipped, acceptance threshold orbDist
+    int kind, orbDist, nlevels;
+    const float *mfMax, *mfMin;  // items x lastStride: raw mfMaxDistance / mfMinDistance
+    const float* Ow;             // items x 3
+    float logScale;
 };
 
 struct LastQuery { float u, v, radius, invzc; int minLevel, maxLevel; bool ok; };
 
-// projection of one last-frame map point into the current frame (:1360-1390), float arithmetic in source order
+// glibc >= 2.27 logf (ARM optimized-routines): 16-entry {1/c, log c} table + degree-3 polynomial in double, one
+// rounding to float.  Bit-identical to libm on every positive finite float (checked exhaustively on the host
+// restatement, oracle/orb_matcher_oracle.c:orc_logf); MapPoint::PredictScale depends on it.
+__device__ const double d_logf_tab[16][2] = { ORB_B200_LOGF_TABLE };
+
+__device__ __forceinline__ float libm_logf(float x)
+{
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2 == 0) return -CUDART_INF_F;
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return CUDART_NAN_F;
+        ix = __float_as_uint(__fmul_rn(x, 0x1p23f));
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int)tmp >> 23;
+    const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
+    const double r = __dsub_rn(__dmul_rn(z, d_logf_tab[i][0]), 1.0);
+    const double y0 = __dadd_rn(d_logf_tab[i][1], __dmul_rn((double)k, ORB_B200_LOGF_LN2));
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(ORB_B200_LOGF_A1, r), ORB_B200_LOGF_A2);
+    y = __dadd_rn(__dmul_rn(ORB_B200_LOGF_A0, r2), y);
+    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+    return __double2float_rn(y);
+}
+
+// projection of one last-frame / key-frame map point into the current frame (:1360-1390, :1500-1532), float
+// arithmetic in source order
 __device__ __forceinline__ LastQuery last_query(const LastParams& P, int item, int i)
 {
     LastQuery q;
     q.ok = false;
     const size_t lo = (size_t)item * P.lastStride + i;
-    if (!P.hasMp[lo] || P.outlier[lo]) return q;
+    if (!P.hasMp[lo] || (P.outlier && P.outlier[lo])) return q;
     const float* R = P.Rcw + (size_t)item * 9;
     const float* t = P.tcw + (size_t)item * 3;
     const float* X = P.wpos + lo * 3;
@@ -698,10 +736,27 @@ __device__ __forceinline__ LastQuery last_query(const LastParams& P, int item, i
     for (int r = 0; r < 3; r++)
         c3[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3 * r], X[0]), __fmul_rn(R[3 * r + 1], X[1])), __fmul_rn(R[3 * r + 2], X[2])), t[r]);
     q.invzc = (float)__ddiv_rn(1.0, (double)c3[2]);
-    if (q.invzc < 0) return q;
+    if (P.kind == 0 && q.invzc < 0) return q;                            // (the key-frame overload has no depth test)
     q.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), q.invzc), P.cx);
     q.v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), q.invzc), P.cy);
     if (q.u < P.minX || q.u > P.maxX || q.v < P.minY || q.v > P.maxY) return q;
+    if (P.kind == 1) {
+        const float* O = P.Ow + (size_t)item * 3;
+        double ss = 0.0;                                                 // cv::norm(x3Dw - Ow): squares summed in double
+#pragma unroll
+        for (int r = 0; r < 3; r++) { const double po = (double)__fsub_rn(X[r], O[r]); ss = __dadd_rn(ss, __dmul_rn(po, po)); }
+        const float dist3D = __double2float_rn(__dsqrt_rn(ss));
+        const float mx = P.mfMax[lo];
+        if (dist3D < __fmul_rn(0.8f, P.mfMin[lo]) || dist3D > __fmul_rn(1.2f, mx)) return q;    // :1525-1526
+        // MapPoint::PredictScale (S/MapPoint.cc:391-400); clamped like the later upstream fix (the reference indexes
+        // mvScaleFactors out of range for dist3D in [0.8 mfMin, mfMin))
+        int level = (int)ceilf(__fdiv_rn(libm_logf(__fdiv_rn(mx, dist3D)), P.logScale));
+        level = max(0, min(level, P.nlevels - 1));
+        q.radius = __fmul_rn(P.th, P.scaleFactors[level]);
+        q.minLevel = level - 1; q.maxLevel = level + 1;
+        q.ok = true;
+        return q;
+    }
     const int oct = P.lastOct[lo];
     q.radius = __fmul_rn(P.th, P.scaleFactors[oct]);
     if (P.mode == 1) { q.minLevel = oct; q.maxLevel = -1; }              // bForward  (:1393)
@@ -758,8 +813,8 @@ __global__ void __launch_bounds__(128) k_last_topk(const LastParams P)
             for (int p = s; p < e; p++) {
                 const int idx = ci[p];
                 if (!last_candidate(P, q, idx, kx, ky, koct, ur)) continue;
-                const int held = kpmp[idx];                                      // initial occupancy (:1409-1411)
-                if (held != -1 && (held >= 0 ? P.mpObs[(size_t)item * P.lastStride + held] : (kpobs ? kpobs[idx] : 0)) > 0) continue;
+                const int held = kpmp[idx];                                      // initial occupancy (:1409-1411, :1546-1547)
+                if (held != -1 && (P.kind == 1 || (held >= 0 ? P.mpObs[(size_t)item * P.lastStride + held] : (kpobs ? kpobs[idx] : 0)) > 0)) continue;
                 const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
                 top4_insert(best, ((uint32_t)dist << 23) | ((uint32_t)p << 5));
                 count++;
@@ -802,18 +857,19 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
     uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * ((P.f.stride + 15) & ~15);
     for (int idx = lane; idx < n; idx += 32) {
         const int held = kpmp[idx];
-        occ[idx] = held != -1 && (held >= 0 ? P.mpObs[lo + held] : (kpobs ? kpobs[idx] : 0)) > 0;
+        occ[idx] = held != -1 && (P.kind == 1 || (held >= 0 ? P.mpObs[lo + held] : (kpobs ? kpobs[idx] : 0)) > 0);
     }
     for (int i = lane; i < nl; i += 32) hbin[i] = -1;
     __syncwarp();
 
     int nmatches = 0;
+    const int accept = P.kind == 1 ? P.orbDist : TH_HIGH;
     for (int base = 0; base < nl; base += 32) {
       const int mine = base + lane;
       int cntL = -1, obsL = 0;
       float angL = 0.f;
       uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
-      if (mine < nl) { cntL = P.topkCount[lo + mine]; kkL = P.topk[lo + mine]; idL = P.topkIdx[lo + mine]; obsL = P.mpObs[lo + mine]; angL = P.lastAng[lo + mine]; }
+      if (mine < nl) { cntL = P.topkCount[lo + mine]; kkL = P.topk[lo + mine]; idL = P.topkIdx[lo + mine]; obsL = P.kind == 1 ? 1 : P.mpObs[lo + mine]; angL = P.lastAng[lo + mine]; }
       const int jEnd = min(32, nl - base);
       for (int j = 0; j < jEnd; j++) {
         const int i = base + j;
@@ -835,7 +891,7 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
                 if (!occ[kid[e]] && dist < 256) { bestDist = dist; bestIdx = (int)kid[e]; found = true; }
             }
         }
-        const bool resolved = found || cnt <= 4 || (int)(key[3] >> 23) > TH_HIGH;
+        const bool resolved = found || cnt <= 4 || (int)(key[3] >> 23) > accept;
         if (!resolved) {                                   // every listed keypoint was taken: rescan all candidates
             const LastQuery q = last_query(P, item, i);
             int c0, c1, r0, r1;
@@ -860,7 +916,7 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
             bestDist = bd;
             bestIdx = bd < 256 ? ci[bp] : -1;
         }
-        if (bestDist <= TH_HIGH) {                                                // :1436-1452
+        if (bestDist <= accept) {                                                 // :1436-1452, :1561-1579
             if (lane == 0) {
                 kpmp[bestIdx] = i;
                 occ[bestIdx] = obsI > 0;
@@ -1238,6 +1294,73 @@ extern "C" int orbb200_search_by_projection_last_frame(orbb200_matcher* m, int i
     k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");
     k_last_topk<<<dim3((last->stride + 127) / 128, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_last_topk");
+    {
+        const size_t sm = 4 * (size_t)((cur->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
+    }
+    ORB_CHECK_LAUNCH("k_search_last");
+    m->lastLaunches = 3;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(kp_mp, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_search_by_projection_keyframe(orbb200_matcher* m, int items, const orbb200_frame_view* cur,
+                                                     const orbb200_keyframe_view* kf, const float* Rcw, const float* tcw,
+                                                     const float* Ow, const float* K, int32_t* kp_mp, const float* scale_factors,
+                                                     int nlevels, float log_scale_factor, const float* bounds, float th,
+                                                     int orb_dist, int check_orientation, int32_t* nmatches, int on_device)
+{
+    if (!m || !cur || !kf || !Rcw || !tcw || !Ow || !K || !kp_mp || !scale_factors || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (!cur->n || !cur->x || !cur->y || !cur->octave || !cur->desc || (check_orientation && !cur->angle) || !kf->n || !kf->valid ||
+        !kf->world_pos || !kf->mp_desc || !kf->max_distance || !kf->min_distance || (check_orientation && !kf->angle)) { set_error("incomplete view"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, cur->stride, "current frame")) || (rc = check_view(m, items, kf->stride, "key frame"))) return rc;
+    if (nlevels < 1 || nlevels > 32 || !bounds || !(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1]) || orb_dist < 0 || orb_dist > 255 ||
+        !(log_scale_factor > 0.f)) { set_error("bad geometry or threshold"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    LastParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t np = (size_t)items * cur->stride, nl = (size_t)items * kf->stride;
+    Stager s{m, 0, st};
+    int* dN;
+    if (on_device) {
+        P.f = as_dev(cur);
+        P.lastN = kf->n; P.hasMp = kf->valid; P.wpos = kf->world_pos; P.mpDesc = kf->mp_desc; P.mfMax = kf->max_distance;
+        P.mfMin = kf->min_distance; P.lastAng = kf->angle;
+        P.Rcw = Rcw; P.tcw = tcw; P.Ow = Ow; P.kpMp = kp_mp; P.scaleFactors = scale_factors; dN = nmatches;
+    } else {
+        const size_t bytes = frame_bytes(cur, items) + pad(np * 4) + 2 * pad(items * 4) + pad(nl) + pad(nl * 12) + pad(nl * 32) +
+                             3 * pad(nl * 4) + pad((size_t)items * 36) + 2 * pad((size_t)items * 12) + pad((size_t)nlevels * 4);
+        if ((rc = s.reserve(bytes))) return rc;
+        if ((rc = upload_frame(s, cur, items, &P.f, true))) return rc;
+        const int* kpmp;
+        if ((rc = s.up(kp_mp, np, &kpmp)) || (rc = s.up(kf->n, items, &P.lastN)) || (rc = s.up(kf->valid, nl, &P.hasMp)) ||
+            (rc = s.up(kf->world_pos, nl * 3, &P.wpos)) || (rc = s.up(kf->mp_desc, nl * 32, &P.mpDesc)) ||
+            (rc = s.up(kf->max_distance, nl, &P.mfMax)) || (rc = s.up(kf->min_distance, nl, &P.mfMin)) ||
+            (rc = s.up(kf->angle, kf->angle ? nl : 0, &P.lastAng)) ||
+            (rc = s.up(Rcw, (size_t)items * 9, &P.Rcw)) || (rc = s.up(tcw, (size_t)items * 3, &P.tcw)) || (rc = s.up(Ow, (size_t)items * 3, &P.Ow)) ||
+            (rc = s.up(scale_factors, (size_t)nlevels, &P.scaleFactors))) return rc;
+        P.kpMp = const_cast<int*>(kpmp);
+        dN = s.out<int>(items);
+    }
+    if (!P.lastAng) P.lastAng = P.mfMax;      // never read for a decision when check_orientation is off
+    P.kind = 1; P.orbDist = orb_dist; P.nlevels = nlevels; P.logScale = log_scale_factor;
+    P.lastStride = kf->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
+    P.minX = bounds[0]; P.minY = bounds[1]; P.maxX = bounds[2]; P.maxY = bounds[3];
+    P.nmatches = dN; P.items = items; P.mode = 0; P.checkOri = check_orientation; P.th = th;
+    P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx; P.histBin = m->scratchA; P.histIdx = m->scratchB;
+    k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
+    ORB_CHECK_LAUNCH("k_build_grid");
+    k_last_topk<<<dim3((kf->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_last_topk");
     {
         const size_t sm = 4 * (size_t)((cur->stride + 15) & ~15);

@@ -192,6 +192,42 @@ class ORBmatcher:
         check(self._L.orbb200_image_bounds(self._h, cols, rows, K.ctypes.data, dist.ctypes.data, b.ctypes.data))
         return b
 
+    # ---- SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (S/ORBmatcher.cc:1476-1603), scope row N2 ----
+    def search_by_projection_keyframe_batch(self, cur_frames, kfs, th=10.0, orb_dist=100):
+        """Relocalisation search.  cur_frames: list of Frame (mvpMapPoints: -1 = free, anything else = holds a map
+        point; on return the accepted key-frame slot indices).  kfs: list of dicts with valid (1 = usable map
+        point: not bad, not in sAlreadyFound), wpos (n,3), mp_desc (n,32), mf_max, mf_min (raw mfMaxDistance /
+        mfMinDistance), kf_angle, Rcw (9), tcw (3), Ow (3), K (4), log_scale."""
+        from ._lib import KeyFrameView
+        items = len(cur_frames)
+        keep = []
+        fv, s = _frame_view(cur_frames, keep)
+        ks = max(1, max(len(k["valid"]) for k in kfs))
+        self._ensure(items, max(s, ks))
+        bnd = cur_frames[0].bounds
+        sf = cur_frames[0].mvScaleFactors
+        assert sf is not None, "Frame.mvScaleFactors is required"
+        kpmp = _pack([f.mvpMapPoints for f in cur_frames], s, np.int32)
+        kn = np.array([len(k["valid"]) for k in kfs], np.int32)
+        a = dict(va=_pack([(np.asarray(k["valid"]) == 1).astype(np.uint8) for k in kfs], ks, np.uint8),
+                 wp=_pack([np.asarray(k["wpos"], np.float32).reshape(-1, 3) for k in kfs], ks, np.float32, (3,)),
+                 md=_pack([k["mp_desc"] for k in kfs], ks, np.uint8, (32,)), mx=_pack([k["mf_max"] for k in kfs], ks, np.float32),
+                 mn=_pack([k["mf_min"] for k in kfs], ks, np.float32), an=_pack([k["kf_angle"] for k in kfs], ks, np.float32))
+        kv = KeyFrameView(kn.ctypes.data, a["va"].ctypes.data, a["wp"].ctypes.data, a["md"].ctypes.data, a["mx"].ctypes.data,
+                          a["mn"].ctypes.data, a["an"].ctypes.data, ks)
+        R = np.ascontiguousarray(np.stack([np.asarray(k["Rcw"], np.float32).reshape(9) for k in kfs]))
+        t = np.ascontiguousarray(np.stack([np.asarray(k["tcw"], np.float32).reshape(3) for k in kfs]))
+        Ow = np.ascontiguousarray(np.stack([np.asarray(k["Ow"], np.float32).reshape(3) for k in kfs]))
+        K = np.ascontiguousarray(kfs[0]["K"], np.float32)
+        nm = np.zeros(items, np.int32)
+        check(self._L.orbb200_search_by_projection_keyframe(
+            self._h, items, C.byref(fv), C.byref(kv), R.ctypes.data, t.ctypes.data, Ow.ctypes.data, K.ctypes.data,
+            kpmp.ctypes.data, sf.ctypes.data, len(sf), float(kfs[0]["log_scale"]), bnd.ctypes.data, float(th), int(orb_dist),
+            int(self.mbCheckOrientation), nm.ctypes.data, 0))
+        for i, f in enumerate(cur_frames):
+            f.mvpMapPoints[:] = kpmp[i, :f.N]
+        return nm
+
     # ---- SearchByProjection(CurrentFrame, LastFrame, th, bMono) (S/ORBmatcher.cc:1332-1474), scope row N2 ----
     def search_by_projection_last_frame_batch(self, cur_frames, lasts, th=15.0, mode=0, mbf=40.0):
         """cur_frames: list of Frame (mvpMapPoints hold indices into the last frame's arrays).

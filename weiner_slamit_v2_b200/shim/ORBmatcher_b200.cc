@@ -3,6 +3,7 @@
 //   SearchForInitialization                              (replaces S/ORBmatcher.cc:409-524)
 //   SearchByProjection(Frame&, vector<MapPoint*>&, th)   (replaces S/ORBmatcher.cc:47-131)
 //   SearchByProjection(CurrentFrame, LastFrame, th, bMono) (replaces S/ORBmatcher.cc:1332-1474; scope row N2)
+//   SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (replaces S/ORBmatcher.cc:1476-1603; scope row N2)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -16,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <vector>
 
 #include "orb_b200.h"
@@ -233,6 +235,72 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
         if (kpMp[i] == before[i]) continue;
         CurrentFrame.mvpMapPoints[i] = kpMp[i] >= 0 ? LastFrame.mvpMapPoints[kpMp[i]] : static_cast<MapPoint*>(NULL);   // :1438, :1465
     }
+    return nmatches;
+}
+
+namespace
+{
+// MapPoint keeps mfMaxDistance / mfMinDistance protected and only exposes them multiplied by 1.2f / 0.8f; the
+// device needs the raw values (PredictScale uses the raw maximum).  A derived class may name the protected members
+// of its base, and the resulting pointers to members have type `float MapPoint::*`: no object of this type exists.
+struct MapPointFields : public MapPoint {
+    static float MapPoint::* MaxDistance() { return &MapPointFields::mfMaxDistance; }
+    static float MapPoint::* MinDistance() { return &MapPointFields::mfMinDistance; }
+    static std::mutex MapPoint::* PosMutex() { return &MapPointFields::mMutexPos; }
+};
+}  // namespace
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                                   const int ORBdist)
+{
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat Ow = -Rcw.t() * tcw;                                                 // :1482, evaluated by OpenCV as before
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+
+    FrameSoA cur(CurrentFrame);
+    const int nk = (int)vpMPs.size();
+    orbb200_matcher* h = tlsMatcher.get(cur.n > nk ? cur.n : nk);
+    if (!h || nk == 0) return 0;
+
+    int32_t kn = nk;
+    std::vector<unsigned char> valid(nk), desc((size_t)nk * 32);
+    std::vector<float> wpos((size_t)nk * 3), angle(nk), maxD(nk), minD(nk);
+    for (int i = 0; i < nk; i++) {
+        MapPoint* pMP = vpMPs[i];
+        angle[i] = pKF->mvKeysUn[i].angle;
+        valid[i] = (pMP && !pMP->isBad() && !sAlreadyFound.count(pMP)) ? 1 : 0;        // :1497-1499
+        if (!valid[i]) continue;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        for (int k = 0; k < 3; k++) wpos[3 * (size_t)i + k] = x3Dw.at<float>(k);
+        const cv::Mat d = pMP->GetDescriptor();
+        if (!d.empty()) std::memcpy(&desc[(size_t)i * 32], d.ptr<unsigned char>(), 32);
+        std::unique_lock<std::mutex> lock(pMP->*MapPointFields::PosMutex());
+        maxD[i] = pMP->*MapPointFields::MaxDistance();
+        minD[i] = pMP->*MapPointFields::MinDistance();
+    }
+    orbb200_keyframe_view kv;
+    kv.n = &kn; kv.valid = &valid[0]; kv.world_pos = &wpos[0]; kv.mp_desc = &desc[0]; kv.max_distance = &maxD[0];
+    kv.min_distance = &minD[0]; kv.angle = &angle[0]; kv.stride = nk;
+
+    std::vector<int32_t> kpMp(cur.view.stride, -1);
+    for (int i = 0; i < cur.n; i++)
+        if (CurrentFrame.mvpMapPoints[i]) kpMp[i] = -2;                                // any held map point blocks the keypoint (:1546)
+    const std::vector<int32_t> before(kpMp);
+    float R9[9], t3[3], O3[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R9[3 * r + c] = Rcw.at<float>(r, c); t3[r] = tcw.at<float>(r); O3[r] = Ow.at<float>(r); }
+    const float K[4] = {CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy};
+    float bounds[4];
+    FrameBounds(bounds);
+    int32_t nmatches = 0;
+    if (orbb200_search_by_projection_keyframe(h, 1, &cur.view, &kv, R9, t3, O3, K, &kpMp[0], &CurrentFrame.mvScaleFactors[0],
+                                              (int)CurrentFrame.mvScaleFactors.size(), CurrentFrame.mfLogScaleFactor, bounds, th, ORBdist,
+                                              mbCheckOrientation ? 1 : 0, &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchByProjection(key frame): %s\n", orbb200_last_error());
+        return 0;
+    }
+    for (int i = 0; i < cur.n; i++)
+        if (kpMp[i] != before[i] && kpMp[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[kpMp[i]];   // :1563 (rejected ones stay NULL, :1594)
     return nmatches;
 }
 

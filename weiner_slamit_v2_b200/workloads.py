@@ -159,8 +159,10 @@ def relocalisation_frame(index, n_kf=1500, n_cur=2000, width=640, height=480, nl
     mp_desc = rng.integers(0, 256, (n_kf, 32)).astype(np.uint8)
     kf_angle = rng.uniform(0, 360, n_kf).astype(np.float32)
     cur = random_keypoints(n_cur, width, height, rng, nlevels)
-    src = rng.integers(0, n_kf, n_cur)
-    re = rng.random(n_cur) < 0.8
+    src = rng.integers(0, max(n_kf, 1), n_cur)
+    re = (rng.random(n_cur) < 0.8) & (n_kf > 0)
+    if n_kf == 0:
+        u = v = np.zeros(1); level = np.zeros(1, np.int64); kf_angle = np.zeros(1, np.float32); mp_desc = np.zeros((1, 32), np.uint8)
     cur["x"] = np.where(re, np.clip(u[src] + rng.normal(0, 2.5, n_cur), 0, width - 1), cur["x"]).astype(np.float32)
     cur["y"] = np.where(re, np.clip(v[src] + rng.normal(0, 2.5, n_cur), 0, height - 1), cur["y"]).astype(np.float32)
     cur["octave"] = np.where(re, np.clip(level[src] + rng.integers(-1, 2, n_cur), 0, nlevels - 1), cur["octave"])
@@ -169,6 +171,8 @@ def relocalisation_frame(index, n_kf=1500, n_cur=2000, width=640, height=480, nl
     cdesc = rng.integers(0, 256, (n_cur, 32)).astype(np.uint8)
     cdesc[re] = flip_bits(mp_desc[src[re]], rng.integers(0, 130, int(re.sum())), rng)
     kp_mp = np.where(rng.random(n_cur) < 0.1, -2, -1).astype(np.int32)     # keypoints that already hold a map point
+    if n_kf == 0:
+        kf_angle = np.zeros(0, np.float32); mp_desc = np.zeros((0, 32), np.uint8)
     return dict(valid=valid, wpos=wpos, mp_desc=mp_desc, mf_max=mf_max, mf_min=mf_min, kf_angle=kf_angle,
                 Rcw=R.reshape(9), tcw=t, Ow=Ow, K=np.array(K, np.float32), cur=cur, cdesc=cdesc, kp_mp=kp_mp,
                 log_scale=np.float32(np.log(np.float32(scale))))
