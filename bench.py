@@ -486,6 +486,37 @@ def run_matching(local, steps):
         "workload": "512 (frame, key frame) pairs, 1500 key-frame map points projected into 2000 keypoints, th=10, ORBdist=100, checkOri",
         "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "map_points_per_s": items * nl / ms * 1e3,
         "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    # ---- scope row N3: SearchByBoW(pKF, F, vpMapPointMatches), tracking against the reference key frame
+    from weiner_slamit_v2_b200._lib import BowView
+    from weiner_slamit_v2_b200.workloads import bow_pair
+    nfe, nnodes = 2000, 100
+    ws = [bow_pair(i, nfe, nfe, nnodes) for i in range(distinct)]
+    def bow_side(pfx):
+        ns = max(len(w[pfx + "_node"]) for w in ws)
+        node = np.zeros((distinct, ns), np.uint32); start = np.zeros((distinct, ns + 1), np.int32)
+        for i, w in enumerate(ws):
+            k = len(w[pfx + "_node"])
+            node[i, :k] = w[pfx + "_node"]; start[i, :k + 1] = w[pfx + "_start"]; start[i, k + 1:] = w[pfx + "_start"][-1]
+        t = dict(n=up(np.full(items, nfe, np.int32)), nn=up(tile(np.array([len(w[pfx + "_node"]) for w in ws], np.int32), items)),
+                 desc=up(tile(np.stack([w[pfx + "_desc"] for w in ws]), items)), ang=up(tile(np.stack([w[pfx + "_angle"] for w in ws]), items)),
+                 node=up(tile(node, items)), start=up(tile(start, items)), feat=up(tile(np.stack([w[pfx + "_feat"] for w in ws]), items)))
+        if pfx == "kf":
+            t["valid"] = up(tile(np.stack([(w["kf_valid"] == 1).astype(np.uint8) for w in ws]), items))
+        v = BowView(t["n"].data_ptr(), t["desc"].data_ptr(), t["ang"].data_ptr(), t["valid"].data_ptr() if pfx == "kf" else None,
+                    t["nn"].data_ptr(), t["node"].data_ptr(), t["start"].data_ptr(), t["feat"].data_ptr(), nfe, ns)
+        return t, v
+    tkf, vkf = bow_side("kf")
+    tfr, vfr = bow_side("f")
+    m5 = torch.empty((items, nfe), dtype=torch.int32, device=dev)
+    nm5 = torch.empty(items, dtype=torch.int32, device=dev)
+    def bow_step():
+        check(L.orbb200_search_by_bow(h, items, C.byref(vkf), C.byref(vfr), 0.7, 1, m5.data_ptr(), nm5.data_ptr(), 1))
+    ms = timed(L.orbb200_matcher_stream(h), bow_step, steps)
+    acc = int(nm5.sum())
+    out["search_by_bow"] = {
+        "workload": "512 (key frame, frame) pairs, 2000 x 2000 features in ~100 shared vocabulary nodes, ratio 0.7, checkOri",
+        "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc,
+        "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
     L.orbb200_matcher_destroy(h)
     return out
 

@@ -240,6 +240,30 @@ int orbb200_search_by_projection_keyframe(orbb200_matcher *m, int items, const o
                                           int nlevels, float log_scale_factor, const float bounds[4], float th,
                                           int orb_dist, int check_orientation, int32_t *nmatches, int on_device);
 
+/* One side of SearchByBoW for `items` frames: descriptors and keypoint angles as in orbb200_frame_view, plus the
+ * DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) flattened: node_id ascending (the map's order),
+ * node_start = node_stride + 1 offsets per item into feat, feat = the feature indices node after node (every
+ * feature index appears at most once).  valid: key-frame side only, 1 = the slot holds a map point that is not
+ * bad (NULL = every slot). */
+typedef struct orbb200_bow_view {
+    const int32_t *n;
+    const uint8_t *desc;          /* items x stride x 32 */
+    const float *angle;           /* items x stride: pKF->mvKeysUn[].angle / F.mvKeys[].angle */
+    const uint8_t *valid;
+    const int32_t *n_nodes;       /* items */
+    const uint32_t *node_id;      /* items x node_stride */
+    const int32_t *node_start;    /* items x (node_stride + 1) */
+    const uint32_t *feat;         /* items x stride */
+    int stride, node_stride;
+} orbb200_bow_view;
+
+/* Replaces ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)
+ * (S/ORBmatcher.cc:161-292; scope row N3) for `items` independent (key frame, frame) pairs.
+ * matches: items x f->stride out = the key-frame slot whose map point the frame keypoint received, -1 otherwise
+ * (vpMapPointMatches as indices); nmatches: items. */
+int orbb200_search_by_bow(orbb200_matcher *m, int items, const orbb200_bow_view *kf, const orbb200_bow_view *f,
+                          float nnratio, int check_orientation, int32_t *matches, int32_t *nmatches, int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

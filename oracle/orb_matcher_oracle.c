@@ -560,3 +560,75 @@ int orc_search_by_projection_keyframe(
     free(hist_idx); free(hist_bin); free(cand); free(items);
     return nmatches;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)
+ * (S/ORBmatcher.cc:161-292): features are compared only inside a shared vocabulary node.
+ * A DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) is flattened to node ids (ascending, the map's
+ * order), node_start (nn+1 offsets) and the feature indices node after node.  kf_valid[i] = the key frame's
+ * slot i holds a map point that is not bad; kf_angle = pKF->mvKeysUn[].angle, f_angle = F.mvKeys[].angle.
+ * matches[nf] out: the key-frame slot whose map point the frame keypoint received, or -1.  Returns nmatches. */
+int orc_search_by_bow(
+    int nkf, const uint8_t *kf_valid, const uint8_t *kf_desc, const float *kf_angle,
+    int kf_nn, const uint32_t *kf_node, const int32_t *kf_start, const uint32_t *kf_feat,
+    int nf, const uint8_t *f_desc, const float *f_angle,
+    int f_nn, const uint32_t *f_node, const int32_t *f_start, const uint32_t *f_feat,
+    float nnratio, int check_orientation, int32_t *matches)
+{
+    (void)nkf;
+    int nmatches = 0;
+    int *hist_bin = (int *)malloc(sizeof(int) * (nf + 1));
+    int *hist_idx = (int *)malloc(sizeof(int) * (nf + 1));
+    int nhist = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < nf; i++) matches[i] = -1;
+    int a = 0, b = 0;
+    while (a < kf_nn && b < f_nn) {
+        if (kf_node[a] == f_node[b]) {
+            for (int ik = kf_start[a]; ik < kf_start[a + 1]; ik++) {
+                const uint32_t realIdxKF = kf_feat[ik];
+                if (!kf_valid[realIdxKF]) continue;
+                const uint8_t *dKF = kf_desc + 32 * (size_t)realIdxKF;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int jf = f_start[b]; jf < f_start[b + 1]; jf++) {
+                    const uint32_t realIdxF = f_feat[jf];
+                    if (matches[realIdxF] != -1) continue;
+                    const int dist = orc_descriptor_distance(dKF, f_desc + 32 * (size_t)realIdxF);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = (int)realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        matches[bestIdxF] = (int32_t)realIdxKF;
+                        if (check_orientation) {
+                            float rot = kf_angle[realIdxKF] - f_angle[bestIdxF];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)roundf(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            hist_bin[nhist] = bin; hist_idx[nhist] = bestIdxF; nhist++;
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (kf_node[a] < f_node[b]) {
+            while (a < kf_nn && kf_node[a] < f_node[b]) a++;       /* lower_bound (:270) */
+        } else {
+            while (b < f_nn && f_node[b] < kf_node[a]) b++;
+        }
+    }
+    if (check_orientation) {
+        int sizes[HISTO_LENGTH] = {0};
+        for (int k = 0; k < nhist; k++) sizes[hist_bin[k]]++;
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            const int bn = hist_bin[k];
+            if (bn != ind1 && bn != ind2 && bn != ind3) { matches[hist_idx[k]] = -1; nmatches--; }
+        }
+    }
+    free(hist_idx); free(hist_bin);
+    return nmatches;
+}

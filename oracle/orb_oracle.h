@@ -131,6 +131,12 @@ int orc_search_by_projection_last_frame(
 
 /* Frame glue: cv::undistortPoints(src, dst, K, dist, Mat(), K) as Frame::UndistortKeyPoints
  * calls it (S/Frame.cc:529-559), K = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2, k3}; and ComputeImageBounds. */
+int orc_search_by_bow(
+    int nkf, const uint8_t *kf_valid, const uint8_t *kf_desc, const float *kf_angle,
+    int kf_nn, const uint32_t *kf_node, const int32_t *kf_start, const uint32_t *kf_feat,
+    int nf, const uint8_t *f_desc, const float *f_angle,
+    int f_nn, const uint32_t *f_node, const int32_t *f_start, const uint32_t *f_feat,
+    float nnratio, int check_orientation, int32_t *matches);
 float orc_logf(float x);
 int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
 int orc_search_by_projection_keyframe(

@@ -233,4 +233,46 @@ int refm_search_by_projection_keyframe(
     std::free(mps); std::free(foreign); std::free(kf);
     return cnt;
 }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (S/ORBmatcher.cc:161-292).
+// kf_valid[i]: 0 = empty slot, 1 = good map point, 3 = bad map point.  Feature vectors arrive flattened and are
+// rebuilt with DBoW2::FeatureVector::addFeature (the reference's own Thirdparty/DBoW2/src/FeatureVector.cpp).
+int refm_search_by_bow(
+    int nkf, const uint8_t* kf_valid, const uint8_t* kf_desc, const float* kf_angle,
+    int kf_nn, const uint32_t* kf_node, const int32_t* kf_start, const uint32_t* kf_feat,
+    int nf, const uint8_t* f_desc, const float* f_angle,
+    int f_nn, const uint32_t* f_node, const int32_t* f_start, const uint32_t* f_feat,
+    float nnratio, int check_orientation, int32_t* matches)
+{
+    Frame F;
+    F.N = nf;
+    F.mvKeys.resize(nf);
+    for (int i = 0; i < nf; i++) F.mvKeys[i].angle = f_angle[i];
+    F.mDescriptors = cv::Mat(nf > 0 ? nf : 1, 32, CV_8U, (void*)f_desc);
+    for (int a = 0; a < f_nn; a++)
+        for (int j = f_start[a]; j < f_start[a + 1]; j++) F.mFeatVec.addFeature(f_node[a], f_feat[j]);
+
+    KeyFrame* kf = (KeyFrame*)std::calloc(1, sizeof(KeyFrame));
+    new (&kf->mvpMapPoints) std::vector<MapPoint*>(nkf, static_cast<MapPoint*>(NULL));
+    std::vector<cv::KeyPoint>* kfKeys = const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn);
+    new (kfKeys) std::vector<cv::KeyPoint>(nkf);
+    cv::Mat* kfDesc = const_cast<cv::Mat*>(&kf->mDescriptors);
+    new (kfDesc) cv::Mat(nkf > 0 ? nkf : 1, 32, CV_8U, (void*)kf_desc);
+    new (&kf->mFeatVec) DBoW2::FeatureVector();
+    for (int a = 0; a < kf_nn; a++)
+        for (int j = kf_start[a]; j < kf_start[a + 1]; j++) kf->mFeatVec.addFeature(kf_node[a], kf_feat[j]);
+    MapPoint* mps = (MapPoint*)std::calloc(nkf > 0 ? nkf : 1, sizeof(MapPoint));
+    for (int i = 0; i < nkf; i++) {
+        mps[i].mbBad = kf_valid[i] == 3;
+        kf->mvpMapPoints[i] = kf_valid[i] ? &mps[i] : NULL;
+        (*kfKeys)[i].angle = kf_angle[i];
+    }
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    std::vector<MapPoint*> out;
+    const int cnt = matcher.SearchByBoW(kf, F, out);
+    for (int i = 0; i < nf; i++) matches[i] = out[i] ? (int32_t)(out[i] - mps) : -1;
+    kf->mFeatVec.~FeatureVector(); kfDesc->~Mat(); kf->mvpMapPoints.~vector(); kfKeys->~vector();
+    std::free(mps); std::free(kf);
+    return cnt;
+}
 }

@@ -361,3 +361,32 @@ def logf(x):
 def logf_array(x):
     """orc_logf over a float32 array (loop in C via ctypes is slow; fine for ~1e5 samples)."""
     return np.array([logf(v) for v in np.asarray(x, np.float32)], np.float32)
+
+
+_u32p = C.POINTER(C.c_uint32)
+
+
+def _u(a): return np.ascontiguousarray(a, np.uint32)
+
+
+def _bow_args(w):
+    return dict(kv=_b(w["kf_valid"]), kd=_b(w["kf_desc"]), ka=_f(w["kf_angle"]), kn=_u(w["kf_node"]), ks=_i(w["kf_start"]), kf=_u(w["kf_feat"]),
+                fd=_b(w["f_desc"]), fa=_f(w["f_angle"]), fn=_u(w["f_node"]), fs=_i(w["f_start"]), ff=_u(w["f_feat"]))
+
+
+def _bow_call(f, w, nnratio, check_ori, valid):
+    a = _bow_args(w)
+    nf = len(a["fa"])
+    m = np.full(max(nf, 1), -1, np.int32)
+    f.argtypes = [C.c_int, _u8p, _u8p, _f32p, C.c_int, _u32p, _i32p, _u32p, C.c_int, _u8p, _f32p, C.c_int, _u32p, _i32p, _u32p,
+                  C.c_float, C.c_int, _i32p]
+    f.restype = C.c_int
+    cnt = f(len(a["kv"]), _ptr(valid(a["kv"]), _u8p), _ptr(a["kd"], _u8p), _ptr(a["ka"], _f32p), len(a["kn"]), _ptr(a["kn"], _u32p),
+            _ptr(a["ks"], _i32p), _ptr(a["kf"], _u32p), nf, _ptr(a["fd"], _u8p), _ptr(a["fa"], _f32p), len(a["fn"]),
+            _ptr(a["fn"], _u32p), _ptr(a["fs"], _i32p), _ptr(a["ff"], _u32p), nnratio, int(check_ori), _ptr(m, _i32p))
+    return cnt, m[:nf]
+
+
+def search_by_bow(w, nnratio=0.7, check_ori=True):
+    """w: workloads.bow_pair() dict.  Returns (nmatches, matches[nf] = key-frame slot or -1)."""
+    return _bow_call(lib().orc_search_by_bow, w, nnratio, check_ori, lambda v: _b((v == 1).astype(np.uint8)))

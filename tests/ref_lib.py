@@ -201,3 +201,9 @@ def ref_search_by_projection_keyframe(w, scale_factors, bounds, th=10.0, orb_dis
         P(a["kpmp"], _i32p), len(sf), P(sf, _f32p), float(w["log_scale"]), P(bnd, _f32p), th, orb_dist, int(check_ori),
         P(ow, _f32p))
     return cnt, a["kpmp"][:n], ow
+
+
+def ref_search_by_bow(w, nnratio=0.7, check_ori=True):
+    """The reference's own SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)."""
+    import oracle_lib as O
+    return O._bow_call(mlib().refm_search_by_bow, w, nnratio, check_ori, lambda v: v)

@@ -188,3 +188,34 @@ def test_search_by_projection_keyframe_reproduces_reference_golden_vectors():
         f.mvpMapPoints[:] = w["kp_mp"]
         nm = m.search_by_projection_keyframe_batch([f], [w], float(c[1]), int(c[2]))
         assert nm[0] == int(g["n_%d" % i]) and np.array_equal(f.mvpMapPoints, g["kpmp_%d" % i])
+
+
+@pytest.mark.parametrize("ratio,ori", [(0.7, True), (0.9, True), (0.7, False)])
+def test_search_by_bow_matches_oracle(ratio, ori):
+    """Scope row N3: SearchByBoW(pKF, F, vpMapPointMatches) for a ragged batch: ~20 features per node, nodes with
+    several hundred features (lists longer than a warp), a single node holding everything, empty sides."""
+    from weiner_slamit_v2_b200.workloads import bow_pair
+    cfg = [(2000, 2000, 100), (2000, 1500, 100), (500, 800, 30), (0, 100, 10), (100, 0, 10), (50, 50, 1), (1000, 1000, 1000),
+           (900, 1100, 2), (1500, 1500, 1)]
+    ws = [bow_pair(70 + i, *c) for i, c in enumerate(cfg)]
+    m = ORBmatcher(ratio, ori, max_items=len(ws), max_points=2000)
+    nm, matches = m.search_by_bow_batch(ws)
+    tot = 0
+    for i, w in enumerate(ws):
+        cnt, mo = O.search_by_bow(w, ratio, ori)
+        assert nm[i] == cnt, (i, nm[i], cnt)
+        assert np.array_equal(matches[i], mo), i
+        tot += cnt
+    assert tot > 1500
+
+
+def test_search_by_bow_reproduces_reference_golden_vectors():
+    """tests/golden/ref_match_bow.npz was produced by the reference's own ORBmatcher.cc (tools/gen_golden.py)."""
+    import os
+    from weiner_slamit_v2_b200.workloads import bow_pair
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_bow.npz"))
+    for i in range(int(g["count"])):
+        c = g["cfg_%d" % i]
+        m = ORBmatcher(float(c[4]), bool(c[5]), max_items=1, max_points=2000)
+        nm, matches = m.search_by_bow_batch([bow_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3]))])
+        assert nm[0] == int(g["n_%d" % i]) and np.array_equal(matches[0], g["m_%d" % i])

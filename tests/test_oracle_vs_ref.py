@@ -164,7 +164,13 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
     from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
     g = np.load(path)
-    if "keyframe" in os.path.basename(path):
+    if "bow" in os.path.basename(path):
+        from weiner_slamit_v2_b200.workloads import bow_pair
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            a = O.search_by_bow(bow_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3])), float(c[4]), bool(c[5]))
+            assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["m_%d" % i])
+    elif "keyframe" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import relocalisation_frame
         for i in range(int(g["count"])):
             c = g["cfg_%d" % i]
@@ -228,3 +234,18 @@ def test_search_by_projection_keyframe_matches_reference(th, orb_dist, ori):
         b = R.ref_search_by_projection_keyframe(w, SCALE_FACTORS_8, bounds, th, orb_dist, ori)
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(b[2], w["Ow"])
         assert idx == 2 or a[0] > 100
+
+
+@needs_refm
+@pytest.mark.parametrize("ratio,ori", [(0.7, True), (0.9, True), (0.7, False)])
+def test_search_by_bow_matches_reference(ratio, ori):
+    """SearchByBoW(KeyFrame*, Frame&, ...) (S/ORBmatcher.cc:161-292) against the reference's own code, the feature
+    vectors rebuilt with the reference's DBoW2::FeatureVector::addFeature: many nodes, few nodes, a single node,
+    more nodes than features, empty sides."""
+    from weiner_slamit_v2_b200.workloads import bow_pair
+    for idx, (nk, nf, nn) in enumerate([(2000, 2000, 100), (2000, 1500, 100), (500, 800, 30), (0, 100, 10), (100, 0, 10),
+                                        (50, 50, 1), (1000, 1000, 1000), (300, 300, 2)]):
+        w = bow_pair(960 + idx, nk, nf, nn)
+        a = O.search_by_bow(w, ratio, ori)
+        b = R.ref_search_by_bow(w, ratio, ori)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx

@@ -91,3 +91,13 @@ for i, (idx, th, od, ori) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_keyframe.npz"), **out)
 print("ref_match_keyframe.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+from weiner_slamit_v2_b200.workloads import bow_pair  # noqa: E402
+cfgs = [(850, 2000, 2000, 100, 0.7, 1), (851, 1500, 1800, 60, 0.9, 1), (852, 800, 700, 400, 0.7, 0)]
+for i, (idx, nk, nf, nn, ratio, ori) in enumerate(cfgs):
+    r = R.ref_search_by_bow(bow_pair(idx, nk, nf, nn), ratio, bool(ori))
+    out["cfg_%d" % i] = np.array([idx, nk, nf, nn, ratio, ori]); out["n_%d" % i] = r[0]; out["m_%d" % i] = r[1]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_bow.npz"), **out)
+print("ref_match_bow.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])

@@ -43,6 +43,11 @@ class KeyFrameView(C.Structure):
                 ("angle", vp), ("stride", C.c_int)]
 
 
+class BowView(C.Structure):
+    _fields_ = [("n", vp), ("desc", vp), ("angle", vp), ("valid", vp), ("n_nodes", vp), ("node_id", vp), ("node_start", vp),
+                ("feat", vp), ("stride", C.c_int), ("node_stride", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/orb_b200.h declares
 SIGNATURES = {
     "orbb200_last_error": (C.c_char_p, []),
@@ -83,6 +88,7 @@ SIGNATURES = {
                                                           vp, C.c_int]),
     "orbb200_search_by_projection_keyframe": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), C.POINTER(KeyFrameView), vp, vp, vp, vp,
                                                         vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_int, C.c_int, vp, C.c_int]),
+    "orbb200_search_by_bow": (C.c_int, [vp, C.c_int, C.POINTER(BowView), C.POINTER(BowView), C.c_float, C.c_int, vp, vp, C.c_int]),
     "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

@@ -964,6 +964,124 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
     if (lane == 0) P.nmatches[item] = nmatches;
 }
 
+// ---- SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (S/ORBmatcher.cc:161-292) ----------------------------
+// Features are compared only inside a shared vocabulary node, and a frame feature sits in exactly one node, so
+// the greedy state (vpMapPointMatches[realIdxF]) never crosses a node: one WARP per (item, key-frame node).  The
+// warp finds the node in the frame's sorted node list by binary search, then walks the node's key-frame features
+// in order; lanes own the node's frame features (the first 32 keep their descriptors in registers), the
+// best / second-best pair is the associative top-2 under (distance, list position), and the winner's lane marks
+// its feature as taken.  The rotation histogram needs the whole item and runs in k_bow_finish.
+struct BowSide {
+    const int* n; const uint8_t* desc; const float* angle; const uint8_t* valid;
+    const int* nNodes; const uint32_t* nodeId; const int* nodeStart; const uint32_t* feat;
+    int stride, nodeStride;
+};
+struct BowParams {
+    BowSide kf, f;
+    int* matches;      // items x f.stride: key-frame slot or -1
+    int* bins;         // items x f.stride scratch: rotation bin of an accepted match, else -1
+    int* nmatches;
+    int items, checkOri;
+    float nnratio;
+};
+
+__global__ void __launch_bounds__(128) k_bow_match(const BowParams P)
+{
+    const int lane = threadIdx.x & 31, item = blockIdx.y;
+    const int a = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (a >= min(P.kf.nNodes[item], P.kf.nodeStride)) return;
+    const uint32_t id = P.kf.nodeId[(size_t)item * P.kf.nodeStride + a];
+    const uint32_t* fid = P.f.nodeId + (size_t)item * P.f.nodeStride;
+    int lo = 0, hi = min(P.f.nNodes[item], P.f.nodeStride);
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (fid[mid] < id) lo = mid + 1; else hi = mid; }
+    if (lo >= min(P.f.nNodes[item], P.f.nodeStride) || fid[lo] != id) return;
+    const int* kst = P.kf.nodeStart + (size_t)item * (P.kf.nodeStride + 1);
+    const int* fst = P.f.nodeStart + (size_t)item * (P.f.nodeStride + 1);
+    const int ks = kst[a], ke = kst[a + 1], fs = fst[lo], fe = fst[lo + 1];
+    const uint32_t* kfeat = P.kf.feat + (size_t)item * P.kf.stride;
+    const uint32_t* ffeat = P.f.feat + (size_t)item * P.f.stride;
+    const uint4* kd = reinterpret_cast<const uint4*>(P.kf.desc + (size_t)item * P.kf.stride * 32);
+    const uint4* fd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
+    const uint8_t* kvalid = P.kf.valid ? P.kf.valid + (size_t)item * P.kf.stride : nullptr;
+    int* matches = P.matches + (size_t)item * P.f.stride;
+    int* bins = P.bins + (size_t)item * P.f.stride;
+    const int nF = fe - fs;
+    if (nF <= 0) return;
+
+    // chunk 0 of the frame list lives in registers
+    const int f0 = lane < nF ? (int)ffeat[fs + lane] : -1;
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    if (f0 >= 0) { r0 = __ldg(fd + 2 * f0); r1 = __ldg(fd + 2 * f0 + 1); }
+    bool taken0 = false;
+
+    for (int ik = ks; ik < ke; ik++) {
+        const int kidx = (int)kfeat[ik];
+        if (kvalid && !kvalid[kidx]) continue;                                  // :193-198 (warp-uniform)
+        const uint4 a0 = __ldg(kd + 2 * kidx), a1 = __ldg(kd + 2 * kidx + 1);
+        Top2 t = {256, INT_MAX, 0, 256, INT_MAX, 0};
+        if (f0 >= 0 && !taken0) top2_push(t, hamming256(a0, a1, r0, r1), lane, f0);
+        for (int p = 32 + lane; p < nF; p += 32) {                              // long lists: occupancy from the output array
+            const int fi = (int)ffeat[fs + p];
+            if (*reinterpret_cast<volatile int*>(matches + fi) != -1) continue;
+            top2_push(t, hamming256(a0, a1, __ldg(fd + 2 * fi), __ldg(fd + 2 * fi + 1)), p, fi);
+        }
+        t = top2_warp_reduce(t);
+        if (t.b <= TH_LOW && (float)t.b < __fmul_rn(P.nnratio, (float)t.s)) {     // :230-232
+            if (t.bp == lane) taken0 = true;
+            if (lane == 0) {
+                matches[t.ba] = kidx;
+                if (P.checkOri) {
+                    float rot = __fsub_rn(P.kf.angle[(size_t)item * P.kf.stride + kidx], P.f.angle[(size_t)item * P.f.stride + t.ba]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    bins[t.ba] = bin;
+                }
+            }
+            if (nF > 32) __syncwarp();
+        }
+    }
+}
+
+// one warp per item: rotation-consistency filter (:273-289) and the match count
+__global__ void __launch_bounds__(128) k_bow_finish(const BowParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (item >= P.items) return;
+    const int n = min(P.f.n[item], P.f.stride);
+    int* matches = P.matches + (size_t)item * P.f.stride;
+    const int* bins = P.bins + (size_t)item * P.f.stride;
+    int count = 0;
+    for (int i = lane; i < n; i += 32) count += matches[i] != -1;
+    if (P.checkOri) {
+        int sizes = 0;
+        for (int i = 0; i < n; i += 32) {
+            const int b = (i + lane < n) ? bins[i + lane] : -1;
+            for (int q = 0; q < HISTO_LENGTH; q++) {
+                const unsigned m = __ballot_sync(0xffffffffu, b == q);
+                if (lane == q) sizes += __popc(m);
+            }
+        }
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int q = 0; q < HISTO_LENGTH; q++) {
+            const int s = __shfl_sync(0xffffffffu, sizes, q);
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = q; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = q; }
+            else if (s > max3) { max3 = s; ind3 = q; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+        for (int i = lane; i < n; i += 32) {
+            const int b = bins[i];
+            if (b >= 0 && b != ind1 && b != ind2 && b != ind3) { matches[i] = -1; count--; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) count += __shfl_xor_sync(0xffffffffu, count, d);
+    if (lane == 0) P.nmatches[item] = count;
+}
+
 }  // namespace orbb200
 
 // =========================================================================================
@@ -1372,6 +1490,66 @@ extern "C" int orbb200_search_by_projection_keyframe(orbb200_matcher* m, int ite
     m->lastLaunches = 3;
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(kp_mp, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+static int upload_bow_side(Stager& s, const orbb200_bow_view* v, int items, BowSide* d)
+{
+    int rc;
+    const size_t np = (size_t)items * v->stride, nn = (size_t)items * v->node_stride;
+    if ((rc = s.up(v->n, items, &d->n)) || (rc = s.up(v->desc, np * 32, &d->desc)) || (rc = s.up(v->angle, v->angle ? np : 0, &d->angle)) ||
+        (rc = s.up(v->valid, v->valid ? np : 0, &d->valid)) || (rc = s.up(v->n_nodes, items, &d->nNodes)) ||
+        (rc = s.up(v->node_id, nn, &d->nodeId)) || (rc = s.up(v->node_start, nn + items, &d->nodeStart)) || (rc = s.up(v->feat, np, &d->feat))) return rc;
+    return ORBB200_OK;
+}
+static size_t bow_side_bytes(const orbb200_bow_view* v, int items)
+{
+    const size_t np = (size_t)items * v->stride, nn = (size_t)items * v->node_stride;
+    return 2 * pad((size_t)items * 4) + pad(np * 32) + pad(np * 4) + pad(np) + pad(nn * 4) + pad((nn + items) * 4) + pad(np * 4);
+}
+
+extern "C" int orbb200_search_by_bow(orbb200_matcher* m, int items, const orbb200_bow_view* kf, const orbb200_bow_view* f, float nnratio,
+                                     int check_orientation, int32_t* matches, int32_t* nmatches, int on_device)
+{
+    if (!m || !kf || !f || !matches || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
+    for (const orbb200_bow_view* v : {kf, f})
+        if (!v->n || !v->desc || !v->n_nodes || !v->node_id || !v->node_start || !v->feat || (check_orientation && !v->angle) || v->node_stride < 1) {
+            set_error("incomplete view"); return ORBB200_EINVAL;
+        }
+    int rc;
+    if ((rc = check_view(m, items, kf->stride, "key frame")) || (rc = check_view(m, items, f->stride, "frame"))) return rc;
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    BowParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t nf = (size_t)items * f->stride;
+    Stager s{m, 0, st};
+    int* dN;
+    if (on_device) {
+        auto side = [](const orbb200_bow_view* v) {
+            BowSide d; d.n = v->n; d.desc = v->desc; d.angle = v->angle; d.valid = v->valid; d.nNodes = v->n_nodes; d.nodeId = v->node_id;
+            d.nodeStart = v->node_start; d.feat = v->feat; d.stride = v->stride; d.nodeStride = v->node_stride; return d; };
+        P.kf = side(kf); P.f = side(f); P.matches = matches; dN = nmatches;
+    } else {
+        if ((rc = s.reserve(bow_side_bytes(kf, items) + bow_side_bytes(f, items) + pad(nf * 4) + pad((size_t)items * 4)))) return rc;
+        if ((rc = upload_bow_side(s, kf, items, &P.kf)) || (rc = upload_bow_side(s, f, items, &P.f))) return rc;
+        P.kf.stride = kf->stride; P.kf.nodeStride = kf->node_stride; P.f.stride = f->stride; P.f.nodeStride = f->node_stride;
+        P.matches = s.out<int>(nf);
+        dN = s.out<int>(items);
+    }
+    P.bins = m->scratchA; P.nmatches = dN; P.items = items; P.checkOri = check_orientation; P.nnratio = nnratio;
+    ORB_CUDA(cudaMemsetAsync(P.matches, 0xff, nf * 4, st));
+    if (check_orientation) ORB_CUDA(cudaMemsetAsync(P.bins, 0xff, nf * 4, st));
+    k_bow_match<<<dim3((kf->node_stride + 3) / 4, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_bow_match");
+    k_bow_finish<<<(items + 3) / 4, 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_bow_finish");
+    m->lastLaunches = 2;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(matches, P.matches, nf * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
     }

@@ -192,6 +192,41 @@ class ORBmatcher:
         check(self._L.orbb200_image_bounds(self._h, cols, rows, K.ctypes.data, dist.ctypes.data, b.ctypes.data))
         return b
 
+    # ---- SearchByBoW(pKF, F, vpMapPointMatches) (S/ORBmatcher.cc:161-292), scope row N3 ----
+    def search_by_bow_batch(self, pairs):
+        """pairs: list of dicts (workloads.bow_pair layout): kf_valid (1 = usable map point), kf_desc, kf_angle,
+        kf_node / kf_start / kf_feat (flattened pKF->mFeatVec), f_desc, f_angle, f_node / f_start / f_feat (F.mFeatVec).
+        Returns (nmatches (items,), [matches per item: key-frame slot per frame keypoint or -1])."""
+        from ._lib import BowView
+        items = len(pairs)
+
+        def side(pfx, with_valid):
+            n = np.array([len(p[pfx + "_angle"]) for p in pairs], np.int32)
+            nn = np.array([len(p[pfx + "_node"]) for p in pairs], np.int32)
+            s, ns = max(1, int(n.max())), max(1, int(nn.max()))
+            start = np.zeros((items, ns + 1), np.int32)
+            for i, p in enumerate(pairs):
+                st = np.asarray(p[pfx + "_start"], np.int32)
+                start[i, :len(st)] = st
+                start[i, len(st):] = st[-1] if len(st) else 0
+            a = dict(n=n, nn=nn, desc=_pack([p[pfx + "_desc"] for p in pairs], s, np.uint8, (32,)),
+                     ang=_pack([p[pfx + "_angle"] for p in pairs], s, np.float32),
+                     node=_pack([p[pfx + "_node"] for p in pairs], ns, np.uint32), start=start,
+                     feat=_pack([p[pfx + "_feat"] for p in pairs], s, np.uint32))
+            if with_valid:
+                a["valid"] = _pack([(np.asarray(p["kf_valid"]) == 1).astype(np.uint8) for p in pairs], s, np.uint8)
+            v = BowView(a["n"].ctypes.data, a["desc"].ctypes.data, a["ang"].ctypes.data, a["valid"].ctypes.data if with_valid else None,
+                        a["nn"].ctypes.data, a["node"].ctypes.data, a["start"].ctypes.data, a["feat"].ctypes.data, s, ns)
+            return a, v, s
+        ka, kv, ks = side("kf", True)
+        fa, fv, fs = side("f", False)
+        self._ensure(items, max(ks, fs))
+        m = np.full((items, fs), -1, np.int32)
+        nm = np.zeros(items, np.int32)
+        check(self._L.orbb200_search_by_bow(self._h, items, C.byref(kv), C.byref(fv), float(self.mfNNratio),
+                                            int(self.mbCheckOrientation), m.ctypes.data, nm.ctypes.data, 0))
+        return nm, [m[i, :fa["n"][i]] for i in range(items)]
+
     # ---- SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (S/ORBmatcher.cc:1476-1603), scope row N2 ----
     def search_by_projection_keyframe_batch(self, cur_frames, kfs, th=10.0, orb_dist=100):
         """Relocalisation search.  cur_frames: list of Frame (mvpMapPoints: -1 = free, anything else = holds a map

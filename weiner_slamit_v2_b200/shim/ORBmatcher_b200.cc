@@ -4,6 +4,7 @@
 //   SearchByProjection(Frame&, vector<MapPoint*>&, th)   (replaces S/ORBmatcher.cc:47-131)
 //   SearchByProjection(CurrentFrame, LastFrame, th, bMono) (replaces S/ORBmatcher.cc:1332-1474; scope row N2)
 //   SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (replaces S/ORBmatcher.cc:1476-1603; scope row N2)
+//   SearchByBoW(pKF, F, vpMapPointMatches)               (replaces S/ORBmatcher.cc:161-292; scope row N3)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -301,6 +302,72 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std
     }
     for (int i = 0; i < cur.n; i++)
         if (kpMp[i] != before[i] && kpMp[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[kpMp[i]];   // :1563 (rejected ones stay NULL, :1594)
+    return nmatches;
+}
+
+namespace
+{
+// DBoW2::FeatureVector -> the flat arrays of orbb200_bow_view (node ids in map order, offsets, feature indices)
+struct FlatFeatVec {
+    int32_t nNodes;
+    std::vector<uint32_t> node, feat;
+    std::vector<int32_t> start;
+    FlatFeatVec(const DBoW2::FeatureVector& fv, int nFeatures)
+    {
+        start.push_back(0);
+        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+            node.push_back(it->first);
+            feat.insert(feat.end(), it->second.begin(), it->second.end());
+            start.push_back((int32_t)feat.size());
+        }
+        nNodes = (int32_t)node.size();
+        if (node.empty()) node.push_back(0);
+        feat.resize(nFeatures > (int)feat.size() ? nFeatures : feat.size(), 0);
+        if (feat.empty()) feat.push_back(0);
+    }
+};
+}  // namespace
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches)
+{
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+    const int nk = (int)vpMapPointsKF.size(), nf = F.N;
+    if (nk == 0 || nf == 0) return 0;
+    orbb200_matcher* h = tlsMatcher.get(nk > nf ? nk : nf);
+    if (!h) return 0;
+
+    int32_t kn = nk, fn = nf;
+    std::vector<unsigned char> valid(nk), kdesc((size_t)nk * 32), fdesc((size_t)nf * 32);
+    std::vector<float> kang(nk), fang(nf);
+    for (int i = 0; i < nk; i++) {
+        MapPoint* pMP = vpMapPointsKF[i];
+        valid[i] = (pMP && !pMP->isBad()) ? 1 : 0;                                     // :193-198
+        kang[i] = pKF->mvKeysUn[i].angle;
+        std::memcpy(&kdesc[(size_t)i * 32], pKF->mDescriptors.ptr<unsigned char>(i), 32);
+    }
+    for (int i = 0; i < nf; i++) {
+        fang[i] = F.mvKeys[i].angle;                                                   // (the reference reads mvKeys here, :240)
+        std::memcpy(&fdesc[(size_t)i * 32], F.mDescriptors.ptr<unsigned char>(i), 32);
+    }
+    FlatFeatVec kfv(pKF->mFeatVec, nk), ffv(F.mFeatVec, nf);
+    orbb200_bow_view kv, fv;
+    kv.n = &kn; kv.desc = &kdesc[0]; kv.angle = &kang[0]; kv.valid = &valid[0]; kv.n_nodes = &kfv.nNodes; kv.node_id = &kfv.node[0];
+    kv.node_start = &kfv.start[0]; kv.feat = &kfv.feat[0]; kv.stride = nk; kv.node_stride = (int)kfv.node.size();
+    fv.n = &fn; fv.desc = &fdesc[0]; fv.angle = &fang[0]; fv.valid = 0; fv.n_nodes = &ffv.nNodes; fv.node_id = &ffv.node[0];
+    fv.node_start = &ffv.start[0]; fv.feat = &ffv.feat[0]; fv.stride = nf; fv.node_stride = (int)ffv.node.size();
+    kfv.start.resize(kv.node_stride + 1, kfv.start.back());
+    ffv.start.resize(fv.node_stride + 1, ffv.start.back());
+    kv.node_start = &kfv.start[0]; fv.node_start = &ffv.start[0];
+
+    std::vector<int32_t> matches(nf, -1);
+    int32_t nmatches = 0;
+    if (orbb200_search_by_bow(h, 1, &kv, &fv, mfNNratio, mbCheckOrientation ? 1 : 0, &matches[0], &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchByBoW: %s\n", orbb200_last_error());
+        return 0;
+    }
+    for (int i = 0; i < nf; i++)
+        if (matches[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[matches[i]];         // :234
     return nmatches;
 }
 

@@ -176,3 +176,41 @@ def relocalisation_frame(index, n_kf=1500, n_cur=2000, width=640, height=480, nl
     return dict(valid=valid, wpos=wpos, mp_desc=mp_desc, mf_max=mf_max, mf_min=mf_min, kf_angle=kf_angle,
                 Rcw=R.reshape(9), tcw=t, Ow=Ow, K=np.array(K, np.float32), cur=cur, cdesc=cdesc, kp_mp=kp_mp,
                 log_scale=np.float32(np.log(np.float32(scale))))
+
+
+def flatten_feature_vector(node_of_feature):
+    """DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>> filled by addFeature in feature order) as arrays:
+    node ids ascending, node_start (nn + 1 offsets) and the feature indices node after node."""
+    node_of_feature = np.asarray(node_of_feature, np.int64)
+    order = np.argsort(node_of_feature, kind="stable")
+    nodes, counts = np.unique(node_of_feature, return_counts=True)
+    start = np.zeros(len(nodes) + 1, np.int32)
+    start[1:] = np.cumsum(counts)
+    return nodes.astype(np.uint32), start, order.astype(np.uint32)
+
+
+def bow_pair(index, n_kf=2000, n_f=2000, n_nodes=100):
+    """A (key frame, frame) pair for SearchByBoW: every feature sits in one vocabulary node (about n_nodes distinct
+    node ids, sparse values); most frame features re-observe a key-frame feature (some bits flipped) and usually
+    fall into the same node.  Key-frame slots without map point (0) and with a bad one (3) are included."""
+    rng = np.random.default_rng(140000 + index)
+    ids = np.sort(rng.choice(np.arange(10, 10 + 12 * max(n_nodes, 1)), max(n_nodes, 1), replace=False))
+    kf_desc = rng.integers(0, 256, (n_kf, 32)).astype(np.uint8)
+    kf_node = ids[rng.integers(0, len(ids), n_kf)] if n_kf else np.zeros(0, np.int64)
+    kf_valid = rng.choice(np.array([0, 1, 3], np.uint8), n_kf, p=[0.25, 0.70, 0.05])
+    kf_angle = rng.uniform(0, 360, n_kf).astype(np.float32)
+    f_desc = rng.integers(0, 256, (n_f, 32)).astype(np.uint8)
+    f_node = ids[rng.integers(0, len(ids), n_f)] if n_f else np.zeros(0, np.int64)
+    f_angle = rng.uniform(0, 360, n_f).astype(np.float32)
+    if n_kf and n_f:
+        src = rng.integers(0, n_kf, n_f)
+        re = rng.random(n_f) < 0.75
+        f_desc[re] = flip_bits(kf_desc[src[re]], rng.integers(0, 70, int(re.sum())), rng)
+        same = re & (rng.random(n_f) < 0.85)
+        f_node = np.where(same, kf_node[src], f_node)
+        rot = rng.uniform(0, 40)
+        f_angle = np.where(re, np.mod(kf_angle[src] - rot + rng.normal(0, 5, n_f), 360), f_angle).astype(np.float32)
+    kn, ks, kfeat = flatten_feature_vector(kf_node)
+    fn, fs, ffeat = flatten_feature_vector(f_node)
+    return dict(kf_valid=kf_valid, kf_desc=kf_desc, kf_angle=kf_angle, kf_node=kn, kf_start=ks, kf_feat=kfeat,
+                f_desc=f_desc, f_angle=f_angle, f_node=fn, f_start=fs, f_feat=ffeat)
