@@ -264,6 +264,13 @@ typedef struct orbb200_bow_view {
 int orbb200_search_by_bow(orbb200_matcher *m, int items, const orbb200_bow_view *kf, const orbb200_bow_view *f,
                           float nnratio, int check_orientation, int32_t *matches, int32_t *nmatches, int on_device);
 
+/* Replaces ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12)
+ * (S/ORBmatcher.cc:526-659, loop closing; scope row N3): both views carry `valid`.  matches12: items x kf1->stride
+ * out = the slot of key frame 2 whose map point slot idx1 received, -1 otherwise. */
+int orbb200_search_by_bow_keyframes(orbb200_matcher *m, int items, const orbb200_bow_view *kf1, const orbb200_bow_view *kf2,
+                                    float nnratio, int check_orientation, int32_t *matches12, int32_t *nmatches,
+                                    int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

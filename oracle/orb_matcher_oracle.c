@@ -632,3 +632,74 @@ int orc_search_by_bow(
     free(hist_idx); free(hist_bin);
     return nmatches;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12)
+ * (S/ORBmatcher.cc:526-659, loop closing): both sides need a good map point, the acceptance test is
+ * bestDist1 < TH_LOW (strict), occupancy is vbMatched2, and the result is indexed by key frame 1:
+ * matches12[n1] out = the slot of key frame 2 whose map point slot idx1 received, or -1. */
+int orc_search_by_bow_keyframes(
+    int n1, const uint8_t *valid1, const uint8_t *desc1, const float *angle1,
+    int nn1, const uint32_t *node1, const int32_t *start1, const uint32_t *feat1,
+    int n2, const uint8_t *valid2, const uint8_t *desc2, const float *angle2,
+    int nn2, const uint32_t *node2, const int32_t *start2, const uint32_t *feat2,
+    float nnratio, int check_orientation, int32_t *matches12)
+{
+    int nmatches = 0;
+    uint8_t *matched2 = (uint8_t *)calloc((size_t)n2 + 1, 1);
+    int *hist_bin = (int *)malloc(sizeof(int) * (n1 + 1));
+    int *hist_idx = (int *)malloc(sizeof(int) * (n1 + 1));
+    int nhist = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (node1[a] == node2[b]) {
+            for (int i1 = start1[a]; i1 < start1[a + 1]; i1++) {
+                const uint32_t idx1 = feat1[i1];
+                if (!valid1[idx1]) continue;
+                const uint8_t *d1 = desc1 + 32 * (size_t)idx1;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = start2[b]; i2 < start2[b + 1]; i2++) {
+                    const uint32_t idx2 = feat2[i2];
+                    if (matched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = orc_descriptor_distance(d1, desc2 + 32 * (size_t)idx2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = (int)idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {                                   /* :601, strict */
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        matches12[idx1] = bestIdx2;
+                        matched2[bestIdx2] = 1;
+                        if (check_orientation) {
+                            float rot = angle1[idx1] - angle2[bestIdx2];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)roundf(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            hist_bin[nhist] = bin; hist_idx[nhist] = (int)idx1; nhist++;
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (node1[a] < node2[b]) {
+            while (a < nn1 && node1[a] < node2[b]) a++;
+        } else {
+            while (b < nn2 && node2[b] < node1[a]) b++;
+        }
+    }
+    if (check_orientation) {
+        int sizes[HISTO_LENGTH] = {0};
+        for (int k = 0; k < nhist; k++) sizes[hist_bin[k]]++;
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            const int bn = hist_bin[k];
+            if (bn != ind1 && bn != ind2 && bn != ind3) { matches12[hist_idx[k]] = -1; nmatches--; }
+        }
+    }
+    free(hist_idx); free(hist_bin); free(matched2);
+    return nmatches;
+}

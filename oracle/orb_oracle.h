@@ -137,6 +137,12 @@ int orc_search_by_bow(
     int nf, const uint8_t *f_desc, const float *f_angle,
     int f_nn, const uint32_t *f_node, const int32_t *f_start, const uint32_t *f_feat,
     float nnratio, int check_orientation, int32_t *matches);
+int orc_search_by_bow_keyframes(
+    int n1, const uint8_t *valid1, const uint8_t *desc1, const float *angle1,
+    int nn1, const uint32_t *node1, const int32_t *start1, const uint32_t *feat1,
+    int n2, const uint8_t *valid2, const uint8_t *desc2, const float *angle2,
+    int nn2, const uint32_t *node2, const int32_t *start2, const uint32_t *feat2,
+    float nnratio, int check_orientation, int32_t *matches12);
 float orc_logf(float x);
 int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
 int orc_search_by_projection_keyframe(

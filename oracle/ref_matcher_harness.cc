@@ -275,4 +275,49 @@ int refm_search_by_bow(
     std::free(mps); std::free(kf);
     return cnt;
 }
+
+namespace {
+struct FakeKeyFrame {
+    KeyFrame* kf; MapPoint* mps; int n;
+    FakeKeyFrame(int n_, const uint8_t* valid, const uint8_t* desc, const float* angle, int nn, const uint32_t* node,
+                 const int32_t* start, const uint32_t* feat) : n(n_)
+    {
+        kf = (KeyFrame*)std::calloc(1, sizeof(KeyFrame));
+        new (&kf->mvpMapPoints) std::vector<MapPoint*>(n, static_cast<MapPoint*>(NULL));
+        new (const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn)) std::vector<cv::KeyPoint>(n);
+        new (const_cast<cv::Mat*>(&kf->mDescriptors)) cv::Mat(n > 0 ? n : 1, 32, CV_8U, (void*)desc);
+        new (&kf->mFeatVec) DBoW2::FeatureVector();
+        for (int a = 0; a < nn; a++)
+            for (int j = start[a]; j < start[a + 1]; j++) kf->mFeatVec.addFeature(node[a], feat[j]);
+        mps = (MapPoint*)std::calloc(n > 0 ? n : 1, sizeof(MapPoint));
+        for (int i = 0; i < n; i++) {
+            mps[i].mbBad = valid[i] == 3;
+            kf->mvpMapPoints[i] = valid[i] ? &mps[i] : NULL;
+            const_cast<std::vector<cv::KeyPoint>&>(kf->mvKeysUn)[i].angle = angle[i];
+        }
+    }
+    ~FakeKeyFrame()
+    {
+        kf->mFeatVec.~FeatureVector(); const_cast<cv::Mat*>(&kf->mDescriptors)->~Mat(); kf->mvpMapPoints.~vector();
+        const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn)->~vector();
+        std::free(mps); std::free(kf);
+    }
+};
+}  // namespace
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (S/ORBmatcher.cc:526-659)
+int refm_search_by_bow_keyframes(
+    int n1, const uint8_t* valid1, const uint8_t* desc1, const float* angle1,
+    int nn1, const uint32_t* node1, const int32_t* start1, const uint32_t* feat1,
+    int n2, const uint8_t* valid2, const uint8_t* desc2, const float* angle2,
+    int nn2, const uint32_t* node2, const int32_t* start2, const uint32_t* feat2,
+    float nnratio, int check_orientation, int32_t* matches12)
+{
+    FakeKeyFrame k1(n1, valid1, desc1, angle1, nn1, node1, start1, feat1), k2(n2, valid2, desc2, angle2, nn2, node2, start2, feat2);
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    std::vector<MapPoint*> out;
+    const int cnt = matcher.SearchByBoW(k1.kf, k2.kf, out);
+    for (int i = 0; i < n1; i++) matches12[i] = out[i] ? (int32_t)(out[i] - k2.mps) : -1;
+    return cnt;
+}
 }

@@ -390,3 +390,22 @@ def _bow_call(f, w, nnratio, check_ori, valid):
 def search_by_bow(w, nnratio=0.7, check_ori=True):
     """w: workloads.bow_pair() dict.  Returns (nmatches, matches[nf] = key-frame slot or -1)."""
     return _bow_call(lib().orc_search_by_bow, w, nnratio, check_ori, lambda v: _b((v == 1).astype(np.uint8)))
+
+
+def _bow_kk_call(f, w, nnratio, check_ori, valid):
+    a = _bow_args(w)
+    v2 = _b(w["f_valid"])
+    n1 = len(a["ka"])
+    m = np.full(max(n1, 1), -1, np.int32)
+    f.argtypes = [C.c_int, _u8p, _u8p, _f32p, C.c_int, _u32p, _i32p, _u32p, C.c_int, _u8p, _u8p, _f32p, C.c_int, _u32p, _i32p, _u32p,
+                  C.c_float, C.c_int, _i32p]
+    f.restype = C.c_int
+    cnt = f(n1, _ptr(valid(a["kv"]), _u8p), _ptr(a["kd"], _u8p), _ptr(a["ka"], _f32p), len(a["kn"]), _ptr(a["kn"], _u32p),
+            _ptr(a["ks"], _i32p), _ptr(a["kf"], _u32p), len(a["fa"]), _ptr(valid(v2), _u8p), _ptr(a["fd"], _u8p), _ptr(a["fa"], _f32p),
+            len(a["fn"]), _ptr(a["fn"], _u32p), _ptr(a["fs"], _i32p), _ptr(a["ff"], _u32p), nnratio, int(check_ori), _ptr(m, _i32p))
+    return cnt, m[:n1]
+
+
+def search_by_bow_keyframes(w, nnratio=0.75, check_ori=True):
+    """w: workloads.bow_pair(..., second_is_keyframe=True) dict.  Returns (nmatches, matches12[n1] = slot of key frame 2 or -1)."""
+    return _bow_kk_call(lib().orc_search_by_bow_keyframes, w, nnratio, check_ori, lambda v: _b((v == 1).astype(np.uint8)))

@@ -207,3 +207,9 @@ def ref_search_by_bow(w, nnratio=0.7, check_ori=True):
     """The reference's own SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)."""
     import oracle_lib as O
     return O._bow_call(mlib().refm_search_by_bow, w, nnratio, check_ori, lambda v: v)
+
+
+def ref_search_by_bow_keyframes(w, nnratio=0.75, check_ori=True):
+    """The reference's own SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)."""
+    import oracle_lib as O
+    return O._bow_kk_call(mlib().refm_search_by_bow_keyframes, w, nnratio, check_ori, lambda v: v)

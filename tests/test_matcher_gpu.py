@@ -207,15 +207,25 @@ def test_search_by_bow_matches_oracle(ratio, ori):
         assert np.array_equal(matches[i], mo), i
         tot += cnt
     assert tot > 1500
+    # SearchByBoW(pKF1, pKF2, vpMatches12) (S/ORBmatcher.cc:526-659) on the same pairs
+    nm, matches = m.search_by_bow_batch(ws, keyframes=True)
+    tot = 0
+    for i, w in enumerate(ws):
+        cnt, mo = O.search_by_bow_keyframes(w, ratio, ori)
+        assert nm[i] == cnt, (i, nm[i], cnt)
+        assert np.array_equal(matches[i], mo), i
+        tot += cnt
+    assert tot > 1000
 
 
 def test_search_by_bow_reproduces_reference_golden_vectors():
     """tests/golden/ref_match_bow.npz was produced by the reference's own ORBmatcher.cc (tools/gen_golden.py)."""
     import os
     from weiner_slamit_v2_b200.workloads import bow_pair
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_bow.npz"))
-    for i in range(int(g["count"])):
-        c = g["cfg_%d" % i]
-        m = ORBmatcher(float(c[4]), bool(c[5]), max_items=1, max_points=2000)
-        nm, matches = m.search_by_bow_batch([bow_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3]))])
-        assert nm[0] == int(g["n_%d" % i]) and np.array_equal(matches[0], g["m_%d" % i])
+    for name, kk in (("ref_match_bow.npz", False), ("ref_match_bowkf.npz", True)):
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            m = ORBmatcher(float(c[4]), bool(c[5]), max_items=1, max_points=2000)
+            nm, matches = m.search_by_bow_batch([bow_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3]))], keyframes=kk)
+            assert nm[0] == int(g["n_%d" % i]) and np.array_equal(matches[0], g["m_%d" % i])

@@ -166,9 +166,10 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     g = np.load(path)
     if "bow" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import bow_pair
+        fn = O.search_by_bow_keyframes if "bowkf" in os.path.basename(path) else O.search_by_bow
         for i in range(int(g["count"])):
             c = g["cfg_%d" % i]
-            a = O.search_by_bow(bow_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3])), float(c[4]), bool(c[5]))
+            a = fn(bow_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3])), float(c[4]), bool(c[5]))
             assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["m_%d" % i])
     elif "keyframe" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import relocalisation_frame
@@ -248,4 +249,7 @@ def test_search_by_bow_matches_reference(ratio, ori):
         w = bow_pair(960 + idx, nk, nf, nn)
         a = O.search_by_bow(w, ratio, ori)
         b = R.ref_search_by_bow(w, ratio, ori)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx
+        a = O.search_by_bow_keyframes(w, ratio, ori)                # SearchByBoW(pKF1, pKF2, ...) (:526-659)
+        b = R.ref_search_by_bow_keyframes(w, ratio, ori)
         assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx

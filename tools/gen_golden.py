@@ -101,3 +101,12 @@ for i, (idx, nk, nf, nn, ratio, ori) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_bow.npz"), **out)
 print("ref_match_bow.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+cfgs = [(860, 2000, 2000, 100, 0.75, 1), (861, 1500, 1800, 60, 0.9, 1), (862, 800, 700, 400, 0.75, 0)]
+for i, (idx, nk, nf, nn, ratio, ori) in enumerate(cfgs):
+    r = R.ref_search_by_bow_keyframes(bow_pair(idx, nk, nf, nn), ratio, bool(ori))
+    out["cfg_%d" % i] = np.array([idx, nk, nf, nn, ratio, ori]); out["n_%d" % i] = r[0]; out["m_%d" % i] = r[1]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_bowkf.npz"), **out)
+print("ref_match_bowkf.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])

@@ -978,10 +978,12 @@ struct BowSide {
 };
 struct BowParams {
     BowSide kf, f;
-    int* matches;      // items x f.stride: key-frame slot or -1
-    int* bins;         // items x f.stride scratch: rotation bin of an accepted match, else -1
+    int* matches;      // mode 0: items x f.stride, key-frame slot or -1;  mode 1: items x kf.stride, slot of key frame 2 or -1
+    int* bins;         // same shape, scratch: rotation bin of an accepted match, else -1
+    int* occ;          // mode 1: items x f.stride, vbMatched2
     int* nmatches;
     int items, checkOri;
+    int mode;          // 0 = SearchByBoW(pKF, F) (:161-292), 1 = SearchByBoW(pKF1, pKF2) (:526-659)
     float nnratio;
 };
 
@@ -1003,13 +1005,18 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowParams P)
     const uint4* kd = reinterpret_cast<const uint4*>(P.kf.desc + (size_t)item * P.kf.stride * 32);
     const uint4* fd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
     const uint8_t* kvalid = P.kf.valid ? P.kf.valid + (size_t)item * P.kf.stride : nullptr;
-    int* matches = P.matches + (size_t)item * P.f.stride;
-    int* bins = P.bins + (size_t)item * P.f.stride;
+    const uint8_t* fvalid = P.f.valid ? P.f.valid + (size_t)item * P.f.stride : nullptr;
+    const int outStride = P.mode ? P.kf.stride : P.f.stride;
+    int* matches = P.matches + (size_t)item * outStride;
+    int* bins = P.bins + (size_t)item * outStride;
+    volatile int* occ = P.mode ? P.occ + (size_t)item * P.f.stride : matches;      // mode 0: a frame keypoint with a match is taken
+    const int freeMark = P.mode ? 0 : -1;
     const int nF = fe - fs;
     if (nF <= 0) return;
 
     // chunk 0 of the frame list lives in registers
-    const int f0 = lane < nF ? (int)ffeat[fs + lane] : -1;
+    int f0 = lane < nF ? (int)ffeat[fs + lane] : -1;
+    if (f0 >= 0 && fvalid && !fvalid[f0]) f0 = -1;                                  // :572-576 (no good map point on side 2)
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
     if (f0 >= 0) { r0 = __ldg(fd + 2 * f0); r1 = __ldg(fd + 2 * f0 + 1); }
     bool taken0 = false;
@@ -1022,20 +1029,22 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowParams P)
         if (f0 >= 0 && !taken0) top2_push(t, hamming256(a0, a1, r0, r1), lane, f0);
         for (int p = 32 + lane; p < nF; p += 32) {                              // long lists: occupancy from the output array
             const int fi = (int)ffeat[fs + p];
-            if (*reinterpret_cast<volatile int*>(matches + fi) != -1) continue;
+            if (occ[fi] != freeMark || (fvalid && !fvalid[fi])) continue;
             top2_push(t, hamming256(a0, a1, __ldg(fd + 2 * fi), __ldg(fd + 2 * fi + 1)), p, fi);
         }
         t = top2_warp_reduce(t);
-        if (t.b <= TH_LOW && (float)t.b < __fmul_rn(P.nnratio, (float)t.s)) {     // :230-232
+        if ((P.mode ? t.b < TH_LOW : t.b <= TH_LOW) && (float)t.b < __fmul_rn(P.nnratio, (float)t.s)) {     // :230-232, :601-603
             if (t.bp == lane) taken0 = true;
             if (lane == 0) {
-                matches[t.ba] = kidx;
+                const int slot = P.mode ? kidx : t.ba;
+                matches[slot] = P.mode ? t.ba : kidx;
+                if (P.mode) occ[t.ba] = 1;
                 if (P.checkOri) {
                     float rot = __fsub_rn(P.kf.angle[(size_t)item * P.kf.stride + kidx], P.f.angle[(size_t)item * P.f.stride + t.ba]);
                     if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                     int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
                     if (bin == HISTO_LENGTH) bin = 0;
-                    bins[t.ba] = bin;
+                    bins[slot] = bin;
                 }
             }
             if (nF > 32) __syncwarp();
@@ -1049,9 +1058,10 @@ __global__ void __launch_bounds__(128) k_bow_finish(const BowParams P)
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (item >= P.items) return;
-    const int n = min(P.f.n[item], P.f.stride);
-    int* matches = P.matches + (size_t)item * P.f.stride;
-    const int* bins = P.bins + (size_t)item * P.f.stride;
+    const BowSide& o = P.mode ? P.kf : P.f;
+    const int n = min(o.n[item], o.stride);
+    int* matches = P.matches + (size_t)item * o.stride;
+    const int* bins = P.bins + (size_t)item * o.stride;
     int count = 0;
     for (int i = lane; i < n; i += 32) count += matches[i] != -1;
     if (P.checkOri) {
@@ -1511,8 +1521,8 @@ static size_t bow_side_bytes(const orbb200_bow_view* v, int items)
     return 2 * pad((size_t)items * 4) + pad(np * 32) + pad(np * 4) + pad(np) + pad(nn * 4) + pad((nn + items) * 4) + pad(np * 4);
 }
 
-extern "C" int orbb200_search_by_bow(orbb200_matcher* m, int items, const orbb200_bow_view* kf, const orbb200_bow_view* f, float nnratio,
-                                     int check_orientation, int32_t* matches, int32_t* nmatches, int on_device)
+static int bow_search(orbb200_matcher* m, int items, const orbb200_bow_view* kf, const orbb200_bow_view* f, float nnratio,
+                      int check_orientation, int32_t* matches, int32_t* nmatches, int on_device, int mode)
 {
     if (!m || !kf || !f || !matches || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
     for (const orbb200_bow_view* v : {kf, f})
@@ -1525,7 +1535,7 @@ extern "C" int orbb200_search_by_bow(orbb200_matcher* m, int items, const orbb20
     cudaStream_t st = m->stream;
     BowParams P;
     memset(&P, 0, sizeof(P));
-    const size_t nf = (size_t)items * f->stride;
+    const size_t nf = (size_t)items * (mode ? kf->stride : f->stride);       // output entries
     Stager s{m, 0, st};
     int* dN;
     if (on_device) {
@@ -1540,7 +1550,9 @@ extern "C" int orbb200_search_by_bow(orbb200_matcher* m, int items, const orbb20
         P.matches = s.out<int>(nf);
         dN = s.out<int>(items);
     }
-    P.bins = m->scratchA; P.nmatches = dN; P.items = items; P.checkOri = check_orientation; P.nnratio = nnratio;
+    P.bins = m->scratchA; P.occ = m->scratchB; P.nmatches = dN; P.items = items; P.checkOri = check_orientation; P.nnratio = nnratio;
+    P.mode = mode;
+    if (mode) ORB_CUDA(cudaMemsetAsync(P.occ, 0, (size_t)items * f->stride * 4, st));
     ORB_CUDA(cudaMemsetAsync(P.matches, 0xff, nf * 4, st));
     if (check_orientation) ORB_CUDA(cudaMemsetAsync(P.bins, 0xff, nf * 4, st));
     k_bow_match<<<dim3((kf->node_stride + 3) / 4, items), 128, 0, st>>>(P);
@@ -1554,4 +1566,16 @@ extern "C" int orbb200_search_by_bow(orbb200_matcher* m, int items, const orbb20
         ORB_CUDA(cudaStreamSynchronize(st));
     }
     return ORBB200_OK;
+}
+
+extern "C" int orbb200_search_by_bow(orbb200_matcher* m, int items, const orbb200_bow_view* kf, const orbb200_bow_view* f, float nnratio,
+                                     int check_orientation, int32_t* matches, int32_t* nmatches, int on_device)
+{
+    return bow_search(m, items, kf, f, nnratio, check_orientation, matches, nmatches, on_device, 0);
+}
+
+extern "C" int orbb200_search_by_bow_keyframes(orbb200_matcher* m, int items, const orbb200_bow_view* kf1, const orbb200_bow_view* kf2,
+                                               float nnratio, int check_orientation, int32_t* matches12, int32_t* nmatches, int on_device)
+{
+    return bow_search(m, items, kf1, kf2, nnratio, check_orientation, matches12, nmatches, on_device, 1);
 }

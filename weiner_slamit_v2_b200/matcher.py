@@ -193,8 +193,10 @@ class ORBmatcher:
         return b
 
     # ---- SearchByBoW(pKF, F, vpMapPointMatches) (S/ORBmatcher.cc:161-292), scope row N3 ----
-    def search_by_bow_batch(self, pairs):
-        """pairs: list of dicts (workloads.bow_pair layout): kf_valid (1 = usable map point), kf_desc, kf_angle,
+    def search_by_bow_batch(self, pairs, keyframes=False):
+        """keyframes=True: SearchByBoW(pKF1, pKF2, vpMatches12) (S/ORBmatcher.cc:526-659): the second side carries
+        f_valid too and the result is indexed by the first side (slot of key frame 2 or -1).
+        pairs: list of dicts (workloads.bow_pair layout): kf_valid (1 = usable map point), kf_desc, kf_angle,
         kf_node / kf_start / kf_feat (flattened pKF->mFeatVec), f_desc, f_angle, f_node / f_start / f_feat (F.mFeatVec).
         Returns (nmatches (items,), [matches per item: key-frame slot per frame keypoint or -1])."""
         from ._lib import BowView
@@ -214,18 +216,19 @@ class ORBmatcher:
                      node=_pack([p[pfx + "_node"] for p in pairs], ns, np.uint32), start=start,
                      feat=_pack([p[pfx + "_feat"] for p in pairs], s, np.uint32))
             if with_valid:
-                a["valid"] = _pack([(np.asarray(p["kf_valid"]) == 1).astype(np.uint8) for p in pairs], s, np.uint8)
+                a["valid"] = _pack([(np.asarray(p[pfx + "_valid"]) == 1).astype(np.uint8) for p in pairs], s, np.uint8)
             v = BowView(a["n"].ctypes.data, a["desc"].ctypes.data, a["ang"].ctypes.data, a["valid"].ctypes.data if with_valid else None,
                         a["nn"].ctypes.data, a["node"].ctypes.data, a["start"].ctypes.data, a["feat"].ctypes.data, s, ns)
             return a, v, s
         ka, kv, ks = side("kf", True)
-        fa, fv, fs = side("f", False)
+        fa, fv, fs = side("f", keyframes)
         self._ensure(items, max(ks, fs))
-        m = np.full((items, fs), -1, np.int32)
+        m = np.full((items, ks if keyframes else fs), -1, np.int32)
         nm = np.zeros(items, np.int32)
-        check(self._L.orbb200_search_by_bow(self._h, items, C.byref(kv), C.byref(fv), float(self.mfNNratio),
-                                            int(self.mbCheckOrientation), m.ctypes.data, nm.ctypes.data, 0))
-        return nm, [m[i, :fa["n"][i]] for i in range(items)]
+        fn = self._L.orbb200_search_by_bow_keyframes if keyframes else self._L.orbb200_search_by_bow
+        check(fn(self._h, items, C.byref(kv), C.byref(fv), float(self.mfNNratio), int(self.mbCheckOrientation),
+                 m.ctypes.data, nm.ctypes.data, 0))
+        return nm, [m[i, :(ka if keyframes else fa)["n"][i]] for i in range(items)]
 
     # ---- SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (S/ORBmatcher.cc:1476-1603), scope row N2 ----
     def search_by_projection_keyframe_batch(self, cur_frames, kfs, th=10.0, orb_dist=100):

@@ -5,6 +5,7 @@
 //   SearchByProjection(CurrentFrame, LastFrame, th, bMono) (replaces S/ORBmatcher.cc:1332-1474; scope row N2)
 //   SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (replaces S/ORBmatcher.cc:1476-1603; scope row N2)
 //   SearchByBoW(pKF, F, vpMapPointMatches)               (replaces S/ORBmatcher.cc:161-292; scope row N3)
+//   SearchByBoW(pKF1, pKF2, vpMatches12)                 (replaces S/ORBmatcher.cc:526-659; scope row N3)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -368,6 +369,52 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpM
     }
     for (int i = 0; i < nf; i++)
         if (matches[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[matches[i]];         // :234
+    return nmatches;
+}
+
+namespace
+{
+// one key frame as an orbb200_bow_view (buffers owned by the object)
+struct KeyFrameBow {
+    int32_t n;
+    std::vector<MapPoint*> mps;
+    std::vector<unsigned char> valid, desc;
+    std::vector<float> angle;
+    FlatFeatVec fv;
+    orbb200_bow_view view;
+    explicit KeyFrameBow(KeyFrame* pKF) : mps(pKF->GetMapPointMatches()), fv(pKF->mFeatVec, (int)mps.size())
+    {
+        n = (int32_t)mps.size();
+        const int s = n > 0 ? n : 1;
+        valid.resize(s); desc.resize((size_t)s * 32); angle.resize(s);
+        for (int i = 0; i < n; i++) {
+            valid[i] = (mps[i] && !mps[i]->isBad()) ? 1 : 0;
+            angle[i] = pKF->mvKeysUn[i].angle;
+            std::memcpy(&desc[(size_t)i * 32], pKF->mDescriptors.ptr<unsigned char>(i), 32);
+        }
+        fv.start.resize(fv.node.size() + 1, fv.start.back());
+        view.n = &n; view.desc = &desc[0]; view.angle = &angle[0]; view.valid = &valid[0]; view.n_nodes = &fv.nNodes;
+        view.node_id = &fv.node[0]; view.node_start = &fv.start[0]; view.feat = &fv.feat[0]; view.stride = s;
+        view.node_stride = (int)fv.node.size();
+    }
+};
+}  // namespace
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12)
+{
+    KeyFrameBow k1(pKF1), k2(pKF2);
+    vpMatches12 = std::vector<MapPoint*>(k1.mps.size(), static_cast<MapPoint*>(NULL));
+    if (k1.n == 0 || k2.n == 0) return 0;
+    orbb200_matcher* h = tlsMatcher.get(k1.n > k2.n ? k1.n : k2.n);
+    if (!h) return 0;
+    std::vector<int32_t> matches(k1.n, -1);
+    int32_t nmatches = 0;
+    if (orbb200_search_by_bow_keyframes(h, 1, &k1.view, &k2.view, mfNNratio, mbCheckOrientation ? 1 : 0, &matches[0], &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchByBoW(KF, KF): %s\n", orbb200_last_error());
+        return 0;
+    }
+    for (int i = 0; i < k1.n; i++)
+        if (matches[i] >= 0) vpMatches12[i] = k2.mps[matches[i]];                      // :605
     return nmatches;
 }
 

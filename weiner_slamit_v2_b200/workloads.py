@@ -212,5 +212,7 @@ def bow_pair(index, n_kf=2000, n_f=2000, n_nodes=100):
         f_angle = np.where(re, np.mod(kf_angle[src] - rot + rng.normal(0, 5, n_f), 360), f_angle).astype(np.float32)
     kn, ks, kfeat = flatten_feature_vector(kf_node)
     fn, fs, ffeat = flatten_feature_vector(f_node)
+    # map-point state of the second side, used when it is a key frame too (SearchByBoW(pKF1, pKF2, ...))
+    f_valid = rng.choice(np.array([0, 1, 3], np.uint8), n_f, p=[0.25, 0.70, 0.05])
     return dict(kf_valid=kf_valid, kf_desc=kf_desc, kf_angle=kf_angle, kf_node=kn, kf_start=ks, kf_feat=kfeat,
-                f_desc=f_desc, f_angle=f_angle, f_node=fn, f_start=fs, f_feat=ffeat)
+                f_desc=f_desc, f_angle=f_angle, f_node=fn, f_start=fs, f_feat=ffeat, f_valid=f_valid)
