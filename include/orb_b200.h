@@ -271,6 +271,27 @@ int orbb200_search_by_bow_keyframes(orbb200_matcher *m, int items, const orbb200
                                     float nnratio, int check_orientation, int32_t *matches12, int32_t *nmatches,
                                     int on_device);
 
+/* Keypoint geometry of one key frame for SearchForTriangulation, items x (the bow view's stride):
+ * x, y = mvKeysUn[].pt; octave = mvKeysUn[].octave (read for key frame 2 only, may be NULL for key frame 1);
+ * u_right = mvuRight (NULL = monocular: all negative); has_mp[i] = GetMapPoint(i) != NULL. */
+typedef struct orbb200_tri_view {
+    const float *x, *y;
+    const int32_t *octave;
+    const float *u_right;
+    const uint8_t *has_mp;
+} orbb200_tri_view;
+
+/* Replaces ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)
+ * (S/ORBmatcher.cc:661-827; scope row N3) for `items` key-frame pairs (the bow views' `valid` is not read).
+ * F12: items x 9 (row major); epipole: items x 2 = {ex, ey} of :668-675 (the caller's cv::Mat expression);
+ * scale_factors2 / level_sigma2_2: pKF2->mvScaleFactors / mvLevelSigma2 (nlevels entries).
+ * matches12: items x kf1->stride out = index in key frame 2 or -1 (vMatches12; the caller packs vMatchedPairs). */
+int orbb200_search_for_triangulation(orbb200_matcher *m, int items, const orbb200_bow_view *kf1, const orbb200_tri_view *g1,
+                                     const orbb200_bow_view *kf2, const orbb200_tri_view *g2, const float *F12,
+                                     const float *epipole, const float *scale_factors2, const float *level_sigma2_2,
+                                     int nlevels, int only_stereo, int check_orientation, int32_t *matches12,
+                                     int32_t *nmatches, int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

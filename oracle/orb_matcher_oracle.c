@@ -703,3 +703,94 @@ int orc_search_by_bow_keyframes(
     free(hist_idx); free(hist_bin); free(matched2);
     return nmatches;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (S/ORBmatcher.cc:661-827):
+ * for every key-frame-1 feature without a map point, the feature of the same vocabulary node in key frame 2
+ * (also without map point) with the smallest descriptor distance <= TH_LOW that is not too close to the epipole
+ * and lies near the epipolar line; among equal distances the LAST one in list order wins (`dist > bestDist`
+ * rejects, equality replaces).  vbMatched2 is never set in this version, so features are independent.
+ * epipole = {ex, ey} (:668-675, the caller's cv::Mat expression).  matches12[n1] out: index in key frame 2 or -1. */
+int orc_search_for_triangulation(
+    int n1, const uint8_t *has_mp1, const uint8_t *desc1, const float *x1, const float *y1, const float *angle1, const float *uright1,
+    int nn1, const uint32_t *node1, const int32_t *start1, const uint32_t *feat1,
+    int n2, const uint8_t *has_mp2, const uint8_t *desc2, const float *x2, const float *y2, const int32_t *oct2, const float *angle2,
+    const float *uright2, int nn2, const uint32_t *node2, const int32_t *start2, const uint32_t *feat2,
+    const float F12[9], const float epipole[2], const float *scale_factors2, const float *level_sigma2_2,
+    int only_stereo, int check_orientation, int32_t *matches12)
+{
+    (void)n2;
+    int nmatches = 0;
+    int *hist_bin = (int *)malloc(sizeof(int) * (n1 + 1));
+    int *hist_idx = (int *)malloc(sizeof(int) * (n1 + 1));
+    int nhist = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    const float ex = epipole[0], ey = epipole[1];
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (node1[a] == node2[b]) {
+            for (int i1 = start1[a]; i1 < start1[a + 1]; i1++) {
+                const uint32_t idx1 = feat1[i1];
+                if (has_mp1[idx1]) continue;
+                const int stereo1 = uright1[idx1] >= 0;
+                if (only_stereo && !stereo1) continue;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = start2[b]; i2 < start2[b + 1]; i2++) {
+                    const uint32_t idx2 = feat2[i2];
+                    if (has_mp2[idx2]) continue;
+                    const int stereo2 = uright2[idx2] >= 0;
+                    if (only_stereo && !stereo2) continue;
+                    const int dist = orc_descriptor_distance(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    if (!stereo1 && !stereo2) {
+                        const float distex = ex - x2[idx2], distey = ey - y2[idx2];
+                        volatile float p0 = distex * distex, p1 = distey * distey;
+                        const float d2 = p0 + p1;
+                        const float lim = 100 * scale_factors2[oct2[idx2]];
+                        if (d2 < lim) continue;
+                    }
+                    /* CheckDistEpipolarLine (:142-159) */
+                    volatile float t0, t1;
+                    t0 = x1[idx1] * F12[0]; t1 = y1[idx1] * F12[3]; t0 = t0 + t1; const float la = t0 + F12[6];
+                    t0 = x1[idx1] * F12[1]; t1 = y1[idx1] * F12[4]; t0 = t0 + t1; const float lb = t0 + F12[7];
+                    t0 = x1[idx1] * F12[2]; t1 = y1[idx1] * F12[5]; t0 = t0 + t1; const float lc = t0 + F12[8];
+                    t0 = la * x2[idx2]; t1 = lb * y2[idx2]; t0 = t0 + t1; const float num = t0 + lc;
+                    t0 = la * la; t1 = lb * lb; const float den = t0 + t1;
+                    if (den == 0) continue;
+                    t0 = num * num; const float dsqr = t0 / den;
+                    if ((double)dsqr < 3.84 * (double)level_sigma2_2[oct2[idx2]]) { bestIdx2 = (int)idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (check_orientation) {
+                        float rot = angle1[idx1] - angle2[bestIdx2];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)roundf(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        hist_bin[nhist] = bin; hist_idx[nhist] = (int)idx1; nhist++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (node1[a] < node2[b]) {
+            while (a < nn1 && node1[a] < node2[b]) a++;
+        } else {
+            while (b < nn2 && node2[b] < node1[a]) b++;
+        }
+    }
+    if (check_orientation) {
+        int sizes[HISTO_LENGTH] = {0};
+        for (int k = 0; k < nhist; k++) sizes[hist_bin[k]]++;
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            const int bn = hist_bin[k];
+            if (bn != ind1 && bn != ind2 && bn != ind3) { matches12[hist_idx[k]] = -1; nmatches--; }
+        }
+    }
+    free(hist_idx); free(hist_bin);
+    return nmatches;
+}

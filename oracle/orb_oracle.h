@@ -143,6 +143,13 @@ int orc_search_by_bow_keyframes(
     int n2, const uint8_t *valid2, const uint8_t *desc2, const float *angle2,
     int nn2, const uint32_t *node2, const int32_t *start2, const uint32_t *feat2,
     float nnratio, int check_orientation, int32_t *matches12);
+int orc_search_for_triangulation(
+    int n1, const uint8_t *has_mp1, const uint8_t *desc1, const float *x1, const float *y1, const float *angle1, const float *uright1,
+    int nn1, const uint32_t *node1, const int32_t *start1, const uint32_t *feat1,
+    int n2, const uint8_t *has_mp2, const uint8_t *desc2, const float *x2, const float *y2, const int32_t *oct2, const float *angle2,
+    const float *uright2, int nn2, const uint32_t *node2, const int32_t *start2, const uint32_t *feat2,
+    const float F12[9], const float epipole[2], const float *scale_factors2, const float *level_sigma2_2,
+    int only_stereo, int check_orientation, int32_t *matches12);
 float orc_logf(float x);
 int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
 int orc_search_by_projection_keyframe(

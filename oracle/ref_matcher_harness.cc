@@ -320,4 +320,56 @@ int refm_search_by_bow_keyframes(
     for (int i = 0; i < n1; i++) matches12[i] = out[i] ? (int32_t)(out[i] - k2.mps) : -1;
     return cnt;
 }
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (S/ORBmatcher.cc:661-827).
+// has_mp: the slot holds a map point.  pose2 = {R2w (9, row major), t2w (3)}, Cw1 = pKF1->GetCameraCenter(),
+// K2 = {fx, fy, cx, cy}.  epipole_out = {ex, ey} as the same expressions give them here (:668-675).
+int refm_search_for_triangulation(
+    int n1, const uint8_t* has_mp1, const uint8_t* desc1, const float* x1, const float* y1, const float* angle1, const float* uright1,
+    int nn1, const uint32_t* node1, const int32_t* start1, const uint32_t* feat1,
+    int n2, const uint8_t* has_mp2, const uint8_t* desc2, const float* x2, const float* y2, const int32_t* oct2, const float* angle2,
+    const float* uright2, int nn2, const uint32_t* node2, const int32_t* start2, const uint32_t* feat2,
+    const float* F12, const float* Cw1, const float* pose2, const float* K2, int nlevels, const float* scale_factors2,
+    const float* level_sigma2_2, int only_stereo, int check_orientation, int32_t* matches12, float* epipole_out)
+{
+    FakeKeyFrame k1(n1, has_mp1, desc1, angle1, nn1, node1, start1, feat1), k2(n2, has_mp2, desc2, angle2, nn2, node2, start2, feat2);
+    struct Fill {
+        static void run(KeyFrame* kf, int n, const float* x, const float* y, const int32_t* oct, const float* ur)
+        {
+            *const_cast<int*>(&kf->N) = n;
+            std::vector<cv::KeyPoint>& k = const_cast<std::vector<cv::KeyPoint>&>(kf->mvKeysUn);
+            for (int i = 0; i < n; i++) { k[i].pt.x = x[i]; k[i].pt.y = y[i]; k[i].octave = oct ? oct[i] : 0; }
+            new (const_cast<std::vector<float>*>(&kf->mvuRight)) std::vector<float>(ur, ur + n);
+        }
+    };
+    Fill::run(k1.kf, n1, x1, y1, NULL, uright1);
+    Fill::run(k2.kf, n2, x2, y2, oct2, uright2);
+    new (const_cast<std::vector<float>*>(&k2.kf->mvScaleFactors)) std::vector<float>(scale_factors2, scale_factors2 + nlevels);
+    new (const_cast<std::vector<float>*>(&k2.kf->mvLevelSigma2)) std::vector<float>(level_sigma2_2, level_sigma2_2 + nlevels);
+    *const_cast<float*>(&k2.kf->fx) = K2[0]; *const_cast<float*>(&k2.kf->fy) = K2[1];
+    *const_cast<float*>(&k2.kf->cx) = K2[2]; *const_cast<float*>(&k2.kf->cy) = K2[3];
+    float T2[16] = {pose2[0], pose2[1], pose2[2], pose2[9], pose2[3], pose2[4], pose2[5], pose2[10], pose2[6], pose2[7], pose2[8], pose2[11], 0, 0, 0, 1};
+    float C1[3] = {Cw1[0], Cw1[1], Cw1[2]};
+    new (&k2.kf->Tcw) cv::Mat(4, 4, CV_32F, T2);
+    new (&k1.kf->Ow) cv::Mat(3, 1, CV_32F, C1);
+    cv::Mat F(3, 3, CV_32F, (void*)F12);
+    if (epipole_out) {
+        cv::Mat Cw = k1.kf->GetCameraCenter();
+        cv::Mat R2w = k2.kf->GetRotation();
+        cv::Mat t2w = k2.kf->GetTranslation();
+        cv::Mat C2 = R2w * Cw + t2w;
+        const float invz = 1.0f / C2.at<float>(2);
+        epipole_out[0] = k2.kf->fx * C2.at<float>(0) * invz + k2.kf->cx;
+        epipole_out[1] = k2.kf->fy * C2.at<float>(1) * invz + k2.kf->cy;
+    }
+    ORBmatcher matcher(0.6f, check_orientation != 0);
+    std::vector<std::pair<size_t, size_t> > pairs;
+    const int cnt = matcher.SearchForTriangulation(k1.kf, k2.kf, F, pairs, only_stereo != 0);
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    for (size_t k = 0; k < pairs.size(); k++) matches12[pairs[k].first] = (int32_t)pairs[k].second;
+    k2.kf->Tcw.~Mat(); k1.kf->Ow.~Mat();
+    const_cast<std::vector<float>*>(&k2.kf->mvScaleFactors)->~vector(); const_cast<std::vector<float>*>(&k2.kf->mvLevelSigma2)->~vector();
+    const_cast<std::vector<float>*>(&k1.kf->mvuRight)->~vector(); const_cast<std::vector<float>*>(&k2.kf->mvuRight)->~vector();
+    return cnt;
+}
 }

@@ -409,3 +409,32 @@ def _bow_kk_call(f, w, nnratio, check_ori, valid):
 def search_by_bow_keyframes(w, nnratio=0.75, check_ori=True):
     """w: workloads.bow_pair(..., second_is_keyframe=True) dict.  Returns (nmatches, matches12[n1] = slot of key frame 2 or -1)."""
     return _bow_kk_call(lib().orc_search_by_bow_keyframes, w, nnratio, check_ori, lambda v: _b((v == 1).astype(np.uint8)))
+
+
+def _tri_sides(w):
+    a, b = w["k1"], w["k2"]
+    A = dict(mp=_b(a["has_mp"]), d=_b(a["desc"]), x=_f(a["x"]), y=_f(a["y"]), an=_f(a["angle"]), ur=_f(a["u_right"]),
+             nd=_u(a["node"]), st=_i(a["start"]), ft=_u(a["feat"]))
+    B = dict(mp=_b(b["has_mp"]), d=_b(b["desc"]), x=_f(b["x"]), y=_f(b["y"]), oc=_i(b["octave"]), an=_f(b["angle"]), ur=_f(b["u_right"]),
+             nd=_u(b["node"]), st=_i(b["start"]), ft=_u(b["feat"]))
+    return A, B
+
+
+def search_for_triangulation(w, only_stereo=False, check_ori=True):
+    """w: workloads.triangulation_pair() dict.  Returns (nmatches, matches12[n1] = index in key frame 2 or -1)."""
+    L = lib()
+    f = L.orc_search_for_triangulation
+    f.argtypes = [C.c_int, _u8p, _u8p, _f32p, _f32p, _f32p, _f32p, C.c_int, _u32p, _i32p, _u32p,
+                  C.c_int, _u8p, _u8p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_int, _u32p, _i32p, _u32p,
+                  _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, _i32p]
+    f.restype = C.c_int
+    A, B = _tri_sides(w)
+    n1 = len(A["x"])
+    m = np.full(max(n1, 1), -1, np.int32)
+    F, ep, sf, ls = _f(w["F12"]), _f(w["epipole"]), _f(w["scale_factors"]), _f(w["level_sigma2"])
+    cnt = f(n1, _ptr(A["mp"], _u8p), _ptr(A["d"], _u8p), _ptr(A["x"], _f32p), _ptr(A["y"], _f32p), _ptr(A["an"], _f32p), _ptr(A["ur"], _f32p),
+            len(A["nd"]), _ptr(A["nd"], _u32p), _ptr(A["st"], _i32p), _ptr(A["ft"], _u32p),
+            len(B["x"]), _ptr(B["mp"], _u8p), _ptr(B["d"], _u8p), _ptr(B["x"], _f32p), _ptr(B["y"], _f32p), _ptr(B["oc"], _i32p),
+            _ptr(B["an"], _f32p), _ptr(B["ur"], _f32p), len(B["nd"]), _ptr(B["nd"], _u32p), _ptr(B["st"], _i32p), _ptr(B["ft"], _u32p),
+            _ptr(F, _f32p), _ptr(ep, _f32p), _ptr(sf, _f32p), _ptr(ls, _f32p), int(only_stereo), int(check_ori), _ptr(m, _i32p))
+    return cnt, m[:n1]

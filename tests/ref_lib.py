@@ -213,3 +213,29 @@ def ref_search_by_bow_keyframes(w, nnratio=0.75, check_ori=True):
     """The reference's own SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)."""
     import oracle_lib as O
     return O._bow_kk_call(mlib().refm_search_by_bow_keyframes, w, nnratio, check_ori, lambda v: v)
+
+
+def ref_search_for_triangulation(w, only_stereo=False, check_ori=True):
+    """The reference's own SearchForTriangulation; also returns the epipole its expressions give."""
+    import oracle_lib as O
+    _u32p = O._u32p
+    P = O._ptr
+    f = mlib().refm_search_for_triangulation
+    f.argtypes = [C.c_int, _u8p, _u8p, _f32p, _f32p, _f32p, _f32p, C.c_int, _u32p, _i32p, _u32p,
+                  C.c_int, _u8p, _u8p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_int, _u32p, _i32p, _u32p,
+                  _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, _i32p, _f32p]
+    f.restype = C.c_int
+    A, B = O._tri_sides(w)
+    n1 = len(A["x"])
+    m = np.full(max(n1, 1), -1, np.int32)
+    ep = np.zeros(2, np.float32)
+    F, sf, ls = O._f(w["F12"]), O._f(w["scale_factors"]), O._f(w["level_sigma2"])
+    pose2 = O._f(np.concatenate([w["R2w"], w["t2w"]]))
+    cw, K = O._f(w["Cw1"]), O._f(w["K"])
+    cnt = f(n1, P(A["mp"], _u8p), P(A["d"], _u8p), P(A["x"], _f32p), P(A["y"], _f32p), P(A["an"], _f32p), P(A["ur"], _f32p),
+            len(A["nd"]), P(A["nd"], _u32p), P(A["st"], _i32p), P(A["ft"], _u32p),
+            len(B["x"]), P(B["mp"], _u8p), P(B["d"], _u8p), P(B["x"], _f32p), P(B["y"], _f32p), P(B["oc"], _i32p),
+            P(B["an"], _f32p), P(B["ur"], _f32p), len(B["nd"]), P(B["nd"], _u32p), P(B["st"], _i32p), P(B["ft"], _u32p),
+            P(F, _f32p), P(cw, _f32p), P(pose2, _f32p), P(K, _f32p), len(sf), P(sf, _f32p), P(ls, _f32p),
+            int(only_stereo), int(check_ori), P(m, _i32p), P(ep, _f32p))
+    return cnt, m[:n1], ep

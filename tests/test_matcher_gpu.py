@@ -229,3 +229,31 @@ def test_search_by_bow_reproduces_reference_golden_vectors():
             m = ORBmatcher(float(c[4]), bool(c[5]), max_items=1, max_points=2000)
             nm, matches = m.search_by_bow_batch([bow_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3]))], keyframes=kk)
             assert nm[0] == int(g["n_%d" % i]) and np.array_equal(matches[0], g["m_%d" % i])
+
+
+@pytest.mark.parametrize("only_stereo,ori", [(False, True), (True, True), (False, False)])
+def test_search_for_triangulation_matches_oracle(only_stereo, ori):
+    """Scope row N3: SearchForTriangulation for a ragged batch of key-frame pairs (sideways / forward motion, mono /
+    partly stereo, a single node holding everything, empty sides), and the reference's golden vectors."""
+    from weiner_slamit_v2_b200.workloads import triangulation_pair
+    cfg = [(2000, 2000, 100, 0.0, False), (2000, 1500, 100, 0.3, False), (2000, 2000, 100, 0.0, True), (1200, 1200, 50, 0.3, True),
+           (0, 100, 10, 0.0, False), (100, 0, 10, 0.0, False), (50, 50, 1, 0.5, False), (1000, 1000, 1000, 0.0, True), (1500, 1500, 1, 0.0, True)]
+    ws = [triangulation_pair(90 + i, a, b, nn, stereo_fraction=sfr, forward=fwd) for i, (a, b, nn, sfr, fwd) in enumerate(cfg)]
+    m = ORBmatcher(0.6, ori, max_items=len(ws), max_points=2000)
+    nm, matches = m.search_for_triangulation_batch(ws, only_stereo)
+    tot = 0
+    for i, w in enumerate(ws):
+        cnt, mo = O.search_for_triangulation(w, only_stereo, ori)
+        assert nm[i] == cnt, (i, nm[i], cnt)
+        assert np.array_equal(matches[i], mo), i
+        tot += cnt
+    assert tot > (20 if only_stereo else 400)
+    if not only_stereo and ori:
+        import os
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_triangulation.npz"))
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            w = triangulation_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3]), stereo_fraction=float(c[4]), forward=bool(c[5]))
+            mm = ORBmatcher(0.6, bool(c[7]), max_items=1, max_points=2000)
+            nm1, m1 = mm.search_for_triangulation_batch([w], bool(c[6]))
+            assert nm1[0] == int(g["n_%d" % i]) and np.array_equal(m1[0], g["m_%d" % i])

@@ -164,7 +164,14 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
     from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
     g = np.load(path)
-    if "bow" in os.path.basename(path):
+    if "triangulation" in os.path.basename(path):
+        from weiner_slamit_v2_b200.workloads import triangulation_pair
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            w = triangulation_pair(int(c[0]), int(c[1]), int(c[2]), int(c[3]), stereo_fraction=float(c[4]), forward=bool(c[5]))
+            a = O.search_for_triangulation(w, bool(c[6]), bool(c[7]))
+            assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["m_%d" % i])
+    elif "bow" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import bow_pair
         fn = O.search_by_bow_keyframes if "bowkf" in os.path.basename(path) else O.search_by_bow
         for i in range(int(g["count"])):
@@ -253,3 +260,22 @@ def test_search_by_bow_matches_reference(ratio, ori):
         a = O.search_by_bow_keyframes(w, ratio, ori)                # SearchByBoW(pKF1, pKF2, ...) (:526-659)
         b = R.ref_search_by_bow_keyframes(w, ratio, ori)
         assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx
+
+
+@needs_refm
+@pytest.mark.parametrize("only_stereo,ori", [(False, True), (True, True), (False, False)])
+def test_search_for_triangulation_matches_reference(only_stereo, ori):
+    """SearchForTriangulation (S/ORBmatcher.cc:661-827) incl. CheckDistEpipolarLine against the reference's own code:
+    sideways and forward motion (epipole inside the image), mono and partly stereo key frames, empty sides.  The
+    epipole the harness computes with the reference's expressions equals the workload's."""
+    from weiner_slamit_v2_b200.workloads import triangulation_pair
+    cfg = [(2000, 2000, 100, 0.0, False), (2000, 1500, 100, 0.3, False), (2000, 2000, 100, 0.0, True), (1200, 1200, 50, 0.3, True),
+           (0, 100, 10, 0.0, False), (100, 0, 10, 0.0, False), (50, 50, 1, 0.5, False), (1000, 1000, 1000, 0.0, True)]
+    tot = 0
+    for idx, (n1, n2, nn, sfr, fwd) in enumerate(cfg):
+        w = triangulation_pair(980 + idx, n1, n2, nn, stereo_fraction=sfr, forward=fwd)
+        a = O.search_for_triangulation(w, only_stereo, ori)
+        b = R.ref_search_for_triangulation(w, only_stereo, ori)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(b[2], w["epipole"]), idx
+        tot += a[0]
+    assert tot > (20 if only_stereo else 400)

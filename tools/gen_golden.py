@@ -110,3 +110,13 @@ for i, (idx, nk, nf, nn, ratio, ori) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_bowkf.npz"), **out)
 print("ref_match_bowkf.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+from weiner_slamit_v2_b200.workloads import triangulation_pair  # noqa: E402
+cfgs = [(870, 2000, 2000, 100, 0.0, 0, 0, 1), (871, 1500, 1800, 60, 0.3, 0, 1, 1), (872, 2000, 2000, 100, 0.0, 1, 0, 1), (873, 800, 700, 400, 0.2, 1, 0, 0)]
+for i, (idx, na, nb, nn, sfr, fwd, st, ori) in enumerate(cfgs):
+    r = R.ref_search_for_triangulation(triangulation_pair(idx, na, nb, nn, stereo_fraction=sfr, forward=bool(fwd)), bool(st), bool(ori))
+    out["cfg_%d" % i] = np.array([idx, na, nb, nn, sfr, fwd, st, ori]); out["n_%d" % i] = r[0]; out["m_%d" % i] = r[1]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_triangulation.npz"), **out)
+print("ref_match_triangulation.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])

@@ -48,6 +48,10 @@ class BowView(C.Structure):
                 ("feat", vp), ("stride", C.c_int), ("node_stride", C.c_int)]
 
 
+class TriView(C.Structure):
+    _fields_ = [("x", vp), ("y", vp), ("octave", vp), ("u_right", vp), ("has_mp", vp)]
+
+
 # name -> (restype, argtypes); every symbol include/orb_b200.h declares
 SIGNATURES = {
     "orbb200_last_error": (C.c_char_p, []),
@@ -90,6 +94,8 @@ SIGNATURES = {
                                                         vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_int, C.c_int, vp, C.c_int]),
     "orbb200_search_by_bow": (C.c_int, [vp, C.c_int, C.POINTER(BowView), C.POINTER(BowView), C.c_float, C.c_int, vp, vp, C.c_int]),
     "orbb200_search_by_bow_keyframes": (C.c_int, [vp, C.c_int, C.POINTER(BowView), C.POINTER(BowView), C.c_float, C.c_int, vp, vp, C.c_int]),
+    "orbb200_search_for_triangulation": (C.c_int, [vp, C.c_int, C.POINTER(BowView), C.POINTER(TriView), C.POINTER(BowView),
+                                                   C.POINTER(TriView), vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]),
     "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

@@ -1092,6 +1092,92 @@ __global__ void __launch_bounds__(128) k_bow_finish(const BowParams P)
     if (lane == 0) P.nmatches[item] = count;
 }
 
+// ---- SearchForTriangulation (S/ORBmatcher.cc:661-827) -------------------------------------------------------
+// No greedy state in this version (vbMatched2 is never set), so every key-frame-1 feature is independent; the
+// node-parallel layout of SearchByBoW is kept (one warp per shared node, lanes over the node's key-frame-2
+// features).  The sequential rule "dist > bestDist rejects, equality replaces" picks, among the candidates that
+// pass the static tests, the smallest distance and of those the LAST in list order: one packed-key warp minimum.
+struct TriGeo { const float *x, *y; const int* octave; const float* uRight; const uint8_t* hasMp; };
+struct TriParams {
+    BowSide k1, k2;
+    TriGeo g1, g2;
+    const float *F12, *epipole, *scaleFactors2, *levelSigma2;
+    int* matches;      // items x k1.stride
+    int* bins;
+    int onlyStereo, checkOri;
+};
+
+__global__ void __launch_bounds__(128) k_tri_match(const TriParams P)
+{
+    const int lane = threadIdx.x & 31, item = blockIdx.y;
+    const int a = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (a >= min(P.k1.nNodes[item], P.k1.nodeStride)) return;
+    const uint32_t id = P.k1.nodeId[(size_t)item * P.k1.nodeStride + a];
+    const uint32_t* nid2 = P.k2.nodeId + (size_t)item * P.k2.nodeStride;
+    const int nn2 = min(P.k2.nNodes[item], P.k2.nodeStride);
+    int lo = 0, hi = nn2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (nid2[mid] < id) lo = mid + 1; else hi = mid; }
+    if (lo >= nn2 || nid2[lo] != id) return;
+    const int* st1 = P.k1.nodeStart + (size_t)item * (P.k1.nodeStride + 1);
+    const int* st2 = P.k2.nodeStart + (size_t)item * (P.k2.nodeStride + 1);
+    const int s1 = st1[a], e1 = st1[a + 1], s2 = st2[lo], e2 = st2[lo + 1];
+    const size_t o1 = (size_t)item * P.k1.stride, o2 = (size_t)item * P.k2.stride;
+    const uint32_t* feat1 = P.k1.feat + o1;
+    const uint32_t* feat2 = P.k2.feat + o2;
+    const uint4* d1 = reinterpret_cast<const uint4*>(P.k1.desc + o1 * 32);
+    const uint4* d2 = reinterpret_cast<const uint4*>(P.k2.desc + o2 * 32);
+    const float* F = P.F12 + (size_t)item * 9;
+    const float ex = P.epipole[2 * item], ey = P.epipole[2 * item + 1];
+    int* matches = P.matches + o1;
+    int* bins = P.bins + o1;
+
+    for (int i1 = s1; i1 < e1; i1++) {
+        const int idx1 = (int)feat1[i1];
+        if (P.g1.hasMp[o1 + idx1]) continue;                                        // :706-708
+        const bool stereo1 = P.g1.uRight && P.g1.uRight[o1 + idx1] >= 0;
+        if (P.onlyStereo && !stereo1) continue;
+        const float x1 = P.g1.x[o1 + idx1], y1 = P.g1.y[o1 + idx1];
+        // epipolar line l = x1' F12 (:145-147), float in source order
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[0]), __fmul_rn(y1, F[3])), F[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[1]), __fmul_rn(y1, F[4])), F[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[2]), __fmul_rn(y1, F[5])), F[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        const uint4 a0 = __ldg(d1 + 2 * idx1), a1 = __ldg(d1 + 2 * idx1 + 1);
+        uint32_t best = 0xffffffffu;
+        for (int p = lane; p < e2 - s2; p += 32) {
+            const int idx2 = (int)feat2[s2 + p];
+            if (P.g2.hasMp[o2 + idx2]) continue;
+            const bool stereo2 = P.g2.uRight && P.g2.uRight[o2 + idx2] >= 0;
+            if (P.onlyStereo && !stereo2) continue;
+            const int dist = hamming256(a0, a1, __ldg(d2 + 2 * idx2), __ldg(d2 + 2 * idx2 + 1));
+            if (dist > TH_LOW) continue;
+            const float x2 = P.g2.x[o2 + idx2], y2 = P.g2.y[o2 + idx2];
+            const int oc = P.g2.octave[o2 + idx2];
+            if (!stereo1 && !stereo2) {                                              // too close to the epipole (:745-751)
+                const float dx = __fsub_rn(ex, x2), dy = __fsub_rn(ey, y2);
+                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, P.scaleFactors2[oc])) continue;
+            }
+            if (den == 0.f) continue;                                                // CheckDistEpipolarLine (:149-158)
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            if (!((double)dsqr < __dmul_rn(3.84, (double)P.levelSigma2[oc]))) continue;
+            best = min(best, ((uint32_t)dist << 20) | (0xfffffu - (uint32_t)p));
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != 0xffffffffu && lane == 0) {
+            const int idx2 = (int)feat2[s2 + (int)(0xfffffu - (best & 0xfffffu))];
+            matches[idx1] = idx2;                                                    // :764
+            if (P.checkOri) {
+                float rot = __fsub_rn(P.k1.angle[o1 + idx1], P.k2.angle[o2 + idx2]);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+                if (bin == HISTO_LENGTH) bin = 0;
+                bins[idx1] = bin;
+            }
+        }
+    }
+}
+
 }  // namespace orbb200
 
 // =========================================================================================
@@ -1578,4 +1664,73 @@ extern "C" int orbb200_search_by_bow_keyframes(orbb200_matcher* m, int items, co
                                                float nnratio, int check_orientation, int32_t* matches12, int32_t* nmatches, int on_device)
 {
     return bow_search(m, items, kf1, kf2, nnratio, check_orientation, matches12, nmatches, on_device, 1);
+}
+
+static int upload_tri_geo(Stager& s, const orbb200_tri_view* v, size_t np, TriGeo* d)
+{
+    int rc;
+    if ((rc = s.up(v->x, np, &d->x)) || (rc = s.up(v->y, np, &d->y)) || (rc = s.up(v->octave, v->octave ? np : 0, &d->octave)) ||
+        (rc = s.up(v->u_right, v->u_right ? np : 0, &d->uRight)) || (rc = s.up(v->has_mp, np, &d->hasMp))) return rc;
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_search_for_triangulation(orbb200_matcher* m, int items, const orbb200_bow_view* kf1, const orbb200_tri_view* g1,
+                                                const orbb200_bow_view* kf2, const orbb200_tri_view* g2, const float* F12,
+                                                const float* epipole, const float* scale_factors2, const float* level_sigma2_2,
+                                                int nlevels, int only_stereo, int check_orientation, int32_t* matches12,
+                                                int32_t* nmatches, int on_device)
+{
+    if (!m || !kf1 || !kf2 || !g1 || !g2 || !F12 || !epipole || !scale_factors2 || !level_sigma2_2 || !matches12 || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
+    for (const orbb200_bow_view* v : {kf1, kf2})
+        if (!v->n || !v->desc || !v->n_nodes || !v->node_id || !v->node_start || !v->feat || (check_orientation && !v->angle) || v->node_stride < 1) {
+            set_error("incomplete view"); return ORBB200_EINVAL;
+        }
+    if (!g1->x || !g1->y || !g1->has_mp || !g2->x || !g2->y || !g2->octave || !g2->has_mp || nlevels < 1 || nlevels > 32) { set_error("incomplete geometry"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, kf1->stride, "key frame 1")) || (rc = check_view(m, items, kf2->stride, "key frame 2"))) return rc;
+    if (kf2->stride >= (1 << 20)) { set_error("more than 1048575 features in key frame 2"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    TriParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t n1 = (size_t)items * kf1->stride, n2 = (size_t)items * kf2->stride;
+    Stager s{m, 0, st};
+    int* dN;
+    if (on_device) {
+        auto side = [](const orbb200_bow_view* v) {
+            BowSide d; d.n = v->n; d.desc = v->desc; d.angle = v->angle; d.valid = nullptr; d.nNodes = v->n_nodes; d.nodeId = v->node_id;
+            d.nodeStart = v->node_start; d.feat = v->feat; d.stride = v->stride; d.nodeStride = v->node_stride; return d; };
+        auto geo = [](const orbb200_tri_view* v) { TriGeo d; d.x = v->x; d.y = v->y; d.octave = v->octave; d.uRight = v->u_right; d.hasMp = v->has_mp; return d; };
+        P.k1 = side(kf1); P.k2 = side(kf2); P.g1 = geo(g1); P.g2 = geo(g2);
+        P.F12 = F12; P.epipole = epipole; P.scaleFactors2 = scale_factors2; P.levelSigma2 = level_sigma2_2;
+        P.matches = matches12; dN = nmatches;
+    } else {
+        const size_t bytes = bow_side_bytes(kf1, items) + bow_side_bytes(kf2, items) + 4 * pad(n1 * 4) + 4 * pad(n2 * 4) + pad(n1) + pad(n2) +
+                             pad((size_t)items * 36) + pad((size_t)items * 8) + 2 * pad((size_t)nlevels * 4) + pad(n1 * 4) + pad((size_t)items * 4);
+        if ((rc = s.reserve(bytes))) return rc;
+        if ((rc = upload_bow_side(s, kf1, items, &P.k1)) || (rc = upload_bow_side(s, kf2, items, &P.k2)) ||
+            (rc = upload_tri_geo(s, g1, n1, &P.g1)) || (rc = upload_tri_geo(s, g2, n2, &P.g2)) ||
+            (rc = s.up(F12, (size_t)items * 9, &P.F12)) || (rc = s.up(epipole, (size_t)items * 2, &P.epipole)) ||
+            (rc = s.up(scale_factors2, (size_t)nlevels, &P.scaleFactors2)) || (rc = s.up(level_sigma2_2, (size_t)nlevels, &P.levelSigma2))) return rc;
+        P.k1.stride = kf1->stride; P.k1.nodeStride = kf1->node_stride; P.k2.stride = kf2->stride; P.k2.nodeStride = kf2->node_stride;
+        P.matches = s.out<int>(n1);
+        dN = s.out<int>(items);
+    }
+    P.bins = m->scratchA; P.onlyStereo = only_stereo; P.checkOri = check_orientation;
+    ORB_CUDA(cudaMemsetAsync(P.matches, 0xff, n1 * 4, st));
+    if (check_orientation) ORB_CUDA(cudaMemsetAsync(P.bins, 0xff, n1 * 4, st));
+    k_tri_match<<<dim3((kf1->node_stride + 3) / 4, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_tri_match");
+    BowParams B;
+    memset(&B, 0, sizeof(B));
+    B.kf = P.k1; B.f = P.k2; B.matches = P.matches; B.bins = P.bins; B.nmatches = dN; B.items = items; B.checkOri = check_orientation; B.mode = 1;
+    k_bow_finish<<<(items + 3) / 4, 128, 0, st>>>(B);
+    ORB_CHECK_LAUNCH("k_bow_finish");
+    m->lastLaunches = 2;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(matches12, P.matches, n1 * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
 }

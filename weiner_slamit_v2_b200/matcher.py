@@ -56,6 +56,28 @@ def _pack(arrs, stride, dtype, tail=()):
     return out
 
 
+def _bow_side(sides, valid=None):
+    """Pack one side of a SearchByBoW-style call.  sides: list of dicts with desc (n,32), angle (n), node, start, feat
+    (a flattened DBoW2::FeatureVector); valid: optional list of (n,) uint8.  Returns (arrays kept alive, BowView, stride)."""
+    from ._lib import BowView
+    items = len(sides)
+    n = np.array([len(p["angle"]) for p in sides], np.int32)
+    nn = np.array([len(p["node"]) for p in sides], np.int32)
+    s, ns = max(1, int(n.max())), max(1, int(nn.max()))
+    start = np.zeros((items, ns + 1), np.int32)
+    for i, p in enumerate(sides):
+        st = np.asarray(p["start"], np.int32)
+        start[i, :len(st)] = st
+        start[i, len(st):] = st[-1] if len(st) else 0
+    a = dict(n=n, nn=nn, desc=_pack([p["desc"] for p in sides], s, np.uint8, (32,)), ang=_pack([p["angle"] for p in sides], s, np.float32),
+             node=_pack([p["node"] for p in sides], ns, np.uint32), start=start, feat=_pack([p["feat"] for p in sides], s, np.uint32))
+    if valid is not None:
+        a["valid"] = _pack(valid, s, np.uint8)
+    v = BowView(a["n"].ctypes.data, a["desc"].ctypes.data, a["ang"].ctypes.data, a["valid"].ctypes.data if valid is not None else None,
+                a["nn"].ctypes.data, a["node"].ctypes.data, a["start"].ctypes.data, a["feat"].ctypes.data, s, ns)
+    return a, v, s
+
+
 def _frame_view(frames, keep):
     """Pack a list of Frame into padded SoA arrays + the ctypes view (arrays kept alive in `keep`)."""
     stride = max(1, max(f.N for f in frames))
@@ -199,27 +221,12 @@ class ORBmatcher:
         pairs: list of dicts (workloads.bow_pair layout): kf_valid (1 = usable map point), kf_desc, kf_angle,
         kf_node / kf_start / kf_feat (flattened pKF->mFeatVec), f_desc, f_angle, f_node / f_start / f_feat (F.mFeatVec).
         Returns (nmatches (items,), [matches per item: key-frame slot per frame keypoint or -1])."""
-        from ._lib import BowView
         items = len(pairs)
 
         def side(pfx, with_valid):
-            n = np.array([len(p[pfx + "_angle"]) for p in pairs], np.int32)
-            nn = np.array([len(p[pfx + "_node"]) for p in pairs], np.int32)
-            s, ns = max(1, int(n.max())), max(1, int(nn.max()))
-            start = np.zeros((items, ns + 1), np.int32)
-            for i, p in enumerate(pairs):
-                st = np.asarray(p[pfx + "_start"], np.int32)
-                start[i, :len(st)] = st
-                start[i, len(st):] = st[-1] if len(st) else 0
-            a = dict(n=n, nn=nn, desc=_pack([p[pfx + "_desc"] for p in pairs], s, np.uint8, (32,)),
-                     ang=_pack([p[pfx + "_angle"] for p in pairs], s, np.float32),
-                     node=_pack([p[pfx + "_node"] for p in pairs], ns, np.uint32), start=start,
-                     feat=_pack([p[pfx + "_feat"] for p in pairs], s, np.uint32))
-            if with_valid:
-                a["valid"] = _pack([(np.asarray(p[pfx + "_valid"]) == 1).astype(np.uint8) for p in pairs], s, np.uint8)
-            v = BowView(a["n"].ctypes.data, a["desc"].ctypes.data, a["ang"].ctypes.data, a["valid"].ctypes.data if with_valid else None,
-                        a["nn"].ctypes.data, a["node"].ctypes.data, a["start"].ctypes.data, a["feat"].ctypes.data, s, ns)
-            return a, v, s
+            sub = [dict(desc=p[pfx + "_desc"], angle=p[pfx + "_angle"], node=p[pfx + "_node"], start=p[pfx + "_start"], feat=p[pfx + "_feat"])
+                   for p in pairs]
+            return _bow_side(sub, [(np.asarray(p[pfx + "_valid"]) == 1).astype(np.uint8) for p in pairs] if with_valid else None)
         ka, kv, ks = side("kf", True)
         fa, fv, fs = side("f", keyframes)
         self._ensure(items, max(ks, fs))
@@ -229,6 +236,35 @@ class ORBmatcher:
         check(fn(self._h, items, C.byref(kv), C.byref(fv), float(self.mfNNratio), int(self.mbCheckOrientation),
                  m.ctypes.data, nm.ctypes.data, 0))
         return nm, [m[i, :(ka if keyframes else fa)["n"][i]] for i in range(items)]
+
+    # ---- SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (S/ORBmatcher.cc:661-827), scope row N3 ----
+    def search_for_triangulation_batch(self, pairs, only_stereo=False):
+        """pairs: list of workloads.triangulation_pair()-layout dicts (k1 / k2: x, y, octave, angle, desc, has_mp, u_right,
+        node, start, feat; F12 (9), epipole (2), scale_factors, level_sigma2).  Returns (nmatches (items,),
+        [matches12 per item: index in key frame 2 or -1]); vMatchedPairs = [(i, m[i]) for i where m[i] >= 0]."""
+        from ._lib import TriView
+        items = len(pairs)
+        a1, v1, s1 = _bow_side([p["k1"] for p in pairs])
+        a2, v2, s2 = _bow_side([p["k2"] for p in pairs])
+        self._ensure(items, max(s1, s2))
+
+        def geo(key, stride):
+            g = dict(x=_pack([p[key]["x"] for p in pairs], stride, np.float32), y=_pack([p[key]["y"] for p in pairs], stride, np.float32),
+                     o=_pack([p[key]["octave"] for p in pairs], stride, np.int32), u=_pack([p[key]["u_right"] for p in pairs], stride, np.float32),
+                     m=_pack([p[key]["has_mp"] for p in pairs], stride, np.uint8))
+            return g, TriView(g["x"].ctypes.data, g["y"].ctypes.data, g["o"].ctypes.data, g["u"].ctypes.data, g["m"].ctypes.data)
+        g1, t1 = geo("k1", s1)
+        g2, t2 = geo("k2", s2)
+        F = np.ascontiguousarray(np.stack([np.asarray(p["F12"], np.float32).reshape(9) for p in pairs]))
+        ep = np.ascontiguousarray(np.stack([np.asarray(p["epipole"], np.float32).reshape(2) for p in pairs]))
+        sf = np.ascontiguousarray(pairs[0]["scale_factors"], np.float32)
+        ls = np.ascontiguousarray(pairs[0]["level_sigma2"], np.float32)
+        m = np.full((items, s1), -1, np.int32)
+        nm = np.zeros(items, np.int32)
+        check(self._L.orbb200_search_for_triangulation(
+            self._h, items, C.byref(v1), C.byref(t1), C.byref(v2), C.byref(t2), F.ctypes.data, ep.ctypes.data, sf.ctypes.data,
+            ls.ctypes.data, len(sf), int(only_stereo), int(self.mbCheckOrientation), m.ctypes.data, nm.ctypes.data, 0))
+        return nm, [m[i, :a1["n"][i]] for i in range(items)]
 
     # ---- SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (S/ORBmatcher.cc:1476-1603), scope row N2 ----
     def search_by_projection_keyframe_batch(self, cur_frames, kfs, th=10.0, orb_dist=100):

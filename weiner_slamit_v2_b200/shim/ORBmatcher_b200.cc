@@ -6,6 +6,7 @@
 //   SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (replaces S/ORBmatcher.cc:1476-1603; scope row N2)
 //   SearchByBoW(pKF, F, vpMapPointMatches)               (replaces S/ORBmatcher.cc:161-292; scope row N3)
 //   SearchByBoW(pKF1, pKF2, vpMatches12)                 (replaces S/ORBmatcher.cc:526-659; scope row N3)
+//   SearchForTriangulation(pKF1, pKF2, F12, pairs, bOnlyStereo) (replaces S/ORBmatcher.cc:661-827; scope row N3)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -415,6 +416,60 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
     }
     for (int i = 0; i < k1.n; i++)
         if (matches[i] >= 0) vpMatches12[i] = k2.mps[matches[i]];                      // :605
+    return nmatches;
+}
+
+namespace
+{
+struct KeyFrameGeo {
+    std::vector<float> x, y, uRight;
+    std::vector<int32_t> octave;
+    std::vector<unsigned char> hasMp;
+    orbb200_tri_view view;
+    KeyFrameGeo(KeyFrame* pKF, const KeyFrameBow& b)
+    {
+        const int s = b.view.stride;
+        x.resize(s); y.resize(s); uRight.resize(s, -1.f); octave.resize(s); hasMp.resize(s);
+        for (int i = 0; i < b.n; i++) {
+            x[i] = pKF->mvKeysUn[i].pt.x; y[i] = pKF->mvKeysUn[i].pt.y; octave[i] = pKF->mvKeysUn[i].octave;
+            uRight[i] = pKF->mvuRight[i];
+            hasMp[i] = b.mps[i] ? 1 : 0;                                               // :706, :726 (a bad map point blocks too)
+        }
+        view.x = &x[0]; view.y = &y[0]; view.octave = &octave[0]; view.u_right = &uRight[0]; view.has_mp = &hasMp[0];
+    }
+};
+}  // namespace
+
+int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                                       const bool bOnlyStereo)
+{
+    // epipole in the second image, evaluated on the host exactly as in the reference (:668-675)
+    cv::Mat Cw = pKF1->GetCameraCenter();
+    cv::Mat R2w = pKF2->GetRotation();
+    cv::Mat t2w = pKF2->GetTranslation();
+    cv::Mat C2 = R2w * Cw + t2w;
+    const float invz = 1.0f / C2.at<float>(2);
+    const float epipole[2] = {pKF2->fx * C2.at<float>(0) * invz + pKF2->cx, pKF2->fy * C2.at<float>(1) * invz + pKF2->cy};
+
+    vMatchedPairs.clear();
+    KeyFrameBow k1(pKF1), k2(pKF2);
+    if (k1.n == 0 || k2.n == 0) return 0;
+    KeyFrameGeo g1(pKF1, k1), g2(pKF2, k2);
+    orbb200_matcher* h = tlsMatcher.get(k1.n > k2.n ? k1.n : k2.n);
+    if (!h) return 0;
+    float F9[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) F9[3 * r + c] = F12.at<float>(r, c);
+    std::vector<int32_t> matches(k1.n, -1);
+    int32_t nmatches = 0;
+    if (orbb200_search_for_triangulation(h, 1, &k1.view, &g1.view, &k2.view, &g2.view, F9, epipole, &pKF2->mvScaleFactors[0],
+                                         &pKF2->mvLevelSigma2[0], (int)pKF2->mvScaleFactors.size(), bOnlyStereo ? 1 : 0,
+                                         mbCheckOrientation ? 1 : 0, &matches[0], &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchForTriangulation: %s\n", orbb200_last_error());
+        return 0;
+    }
+    vMatchedPairs.reserve(nmatches);
+    for (int i = 0; i < k1.n; i++)
+        if (matches[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)matches[i]));      // :815-820
     return nmatches;
 }
 

@@ -216,3 +216,71 @@ def bow_pair(index, n_kf=2000, n_f=2000, n_nodes=100):
     f_valid = rng.choice(np.array([0, 1, 3], np.uint8), n_f, p=[0.25, 0.70, 0.05])
     return dict(kf_valid=kf_valid, kf_desc=kf_desc, kf_angle=kf_angle, kf_node=kn, kf_start=ks, kf_feat=kfeat,
                 f_desc=f_desc, f_angle=f_angle, f_node=fn, f_start=fs, f_feat=ffeat, f_valid=f_valid)
+
+
+def _rodrigues(rng, lo_deg, hi_deg):
+    axis = rng.normal(size=3); axis /= np.linalg.norm(axis)
+    ang = np.deg2rad(rng.uniform(lo_deg, hi_deg))
+    Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+
+
+def epipole_in_second(Cw1, R2w, t2w, K):
+    """ex, ey of S/ORBmatcher.cc:668-675 in float32, products and sums in source order."""
+    f = np.float32
+    R = np.asarray(R2w, f).reshape(3, 3); C = np.asarray(Cw1, f); t = np.asarray(t2w, f)
+    C2 = [f(f(f(f(R[r, 0] * C[0]) + f(R[r, 1] * C[1])) + f(R[r, 2] * C[2])) + t[r]) for r in range(3)]
+    invz = f(f(1.0) / C2[2])
+    return np.array([f(f(f(f(K[0]) * C2[0]) * invz) + f(K[2])), f(f(f(f(K[1]) * C2[1]) * invz) + f(K[3]))], f)
+
+
+def triangulation_pair(index, n1=2000, n2=2000, n_nodes=100, width=640, height=480, nlevels=8, scale=1.2,
+                       K=(526.69, 540.36, 313.07, 238.39), stereo_fraction=0.0, forward=False):
+    """Two key frames looking at the same random 3-D points for SearchForTriangulation: keypoints = projections plus
+    noise, F12 from the two poses (LocalMapping::ComputeF12's formula), corresponding features mostly in the same
+    vocabulary node with similar descriptors; slots that already hold a map point; optionally stereo keypoints."""
+    rng = np.random.default_rng(150000 + index)
+    fx, fy, cx, cy = K
+    Km = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    R1, R2 = _rodrigues(rng, 0, 10), _rodrigues(rng, 0, 10)
+    t1, t2 = rng.normal(0, 0.3, 3), rng.normal(0, 0.3, 3)
+    if forward:                                       # motion along the optical axis: the epipole falls inside the image
+        R2 = R1 @ _rodrigues(rng, 0, 1.0)
+        t2 = t1 + np.array([0.02, 0.01, -1.0])
+    npts = max(n1, n2, 1)
+    Xw = np.stack([rng.uniform(-4, 4, npts), rng.uniform(-3, 3, npts), rng.uniform(3, 12, npts)], 1)
+    def project(R, t):
+        Xc = Xw @ R.T + t
+        return fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy
+    u1, v1 = project(R1, t1); u2, v2 = project(R2, t2)
+    R12 = R1 @ R2.T; t12 = -R12 @ t2 + t1
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    F12 = (np.linalg.inv(Km).T @ tx @ R12 @ np.linalg.inv(Km)).astype(np.float32)
+    ids = np.sort(rng.choice(np.arange(10, 10 + 12 * max(n_nodes, 1)), max(n_nodes, 1), replace=False))
+    pt_node = ids[rng.integers(0, len(ids), npts)]
+    pt_desc = rng.integers(0, 256, (npts, 32)).astype(np.uint8)
+    pt_oct = rng.integers(0, nlevels, npts)
+    pt_ang = rng.uniform(0, 360, npts)
+    rot = rng.uniform(0, 40)
+    def side(n, u, v, other_rot):
+        src = rng.permutation(npts)[:n] if n else np.zeros(0, np.int64)
+        re = rng.random(n) < 0.8                      # the rest are unrelated features
+        x = np.where(re, u[src] + rng.normal(0, 1.0, n), rng.uniform(0, width, n)).astype(np.float32)
+        y = np.where(re, v[src] + rng.normal(0, 1.0, n), rng.uniform(0, height, n)).astype(np.float32)
+        node = np.where(re & (rng.random(n) < 0.85), pt_node[src], ids[rng.integers(0, len(ids), n)])
+        desc = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+        if n:
+            desc[re] = flip_bits(pt_desc[src[re]], rng.integers(0, 45, int(re.sum())), rng)
+        octv = np.clip(pt_oct[src] + rng.integers(-1, 2, n), 0, nlevels - 1).astype(np.int32)
+        ang = np.mod(pt_ang[src] - other_rot + rng.normal(0, 5, n), 360).astype(np.float32)
+        has_mp = (rng.random(n) < 0.4).astype(np.uint8)
+        ur = np.where(rng.random(n) < stereo_fraction, x - rng.uniform(1, 30, n), -1).astype(np.float32)
+        nn, st, ft = flatten_feature_vector(node)
+        return dict(x=x, y=y, octave=octv, angle=ang, desc=desc, has_mp=has_mp, u_right=ur, node=nn, start=st, feat=ft)
+    a, b = side(n1, u1, v1, 0.0), side(n2, u2, v2, rot)
+    Cw1 = (-R1.T @ t1).astype(np.float32)
+    R2f, t2f = R2.astype(np.float32), t2.astype(np.float32)
+    sf = np.array([scale ** i for i in range(nlevels)], np.float32)
+    return dict(k1=a, k2=b, F12=F12.reshape(9), Cw1=Cw1, R2w=R2f.reshape(9), t2w=t2f, K=np.array(K, np.float32),
+                epipole=epipole_in_second(Cw1, R2f, t2f, np.array(K, np.float32)), scale_factors=sf,
+                level_sigma2=(sf * sf).astype(np.float32))
