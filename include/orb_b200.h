@@ -292,6 +292,14 @@ int orbb200_search_for_triangulation(orbb200_matcher *m, int items, const orbb20
                                      int nlevels, int only_stereo, int check_orientation, int32_t *matches12,
                                      int32_t *nmatches, int on_device);
 
+/* Replaces the selection in MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313; scope row N4) for
+ * `items` map points at once: map point p's observed descriptors (those of its non-bad key frames, in the
+ * std::map's order) are rows offsets[p] .. offsets[p+1]-1 of `descriptors` (total x 32 bytes, offsets[items] ==
+ * total).  best[p] = index, relative to offsets[p], of the descriptor with the least median Hamming distance to
+ * all of them (first minimum; -1 for a map point without descriptors); best_median (may be NULL) = that median. */
+int orbb200_distinctive_descriptors(orbb200_matcher *m, int items, const int32_t *offsets, const uint8_t *descriptors,
+                                    int total, int32_t *best, int32_t *best_median, int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

@@ -794,3 +794,26 @@ int orc_search_for_triangulation(
     free(hist_idx); free(hist_bin);
     return nmatches;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * The selection of MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313): of the n observed descriptors
+ * (those of the map point's non-bad key frames, in std::map order) the one with the least median Hamming distance
+ * to all of them (its own 0 included); median = element (int)(0.5*(n-1)) of the sorted row; first minimum wins.
+ * Returns the index, -1 for n == 0; *median_out receives the winning median. */
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+int orc_distinctive_descriptor(int n, const uint8_t *desc, int *median_out)
+{
+    if (n <= 0) return -1;
+    int *row = (int *)malloc(sizeof(int) * n);
+    int bestMedian = INT_MAX, bestIdx = 0;
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) row[j] = i == j ? 0 : orc_descriptor_distance(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+        qsort(row, n, sizeof(int), cmp_int);
+        const int median = row[(int)(0.5 * (n - 1))];
+        if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+    }
+    free(row);
+    if (median_out) *median_out = bestMedian;
+    return bestIdx;
+}

@@ -150,6 +150,7 @@ int orc_search_for_triangulation(
     const float *uright2, int nn2, const uint32_t *node2, const int32_t *start2, const uint32_t *feat2,
     const float F12[9], const float epipole[2], const float *scale_factors2, const float *level_sigma2_2,
     int only_stereo, int check_orientation, int32_t *matches12);
+int orc_distinctive_descriptor(int n, const uint8_t *desc, int *median_out);
 float orc_logf(float x);
 int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
 int orc_search_by_projection_keyframe(

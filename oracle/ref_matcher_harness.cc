@@ -372,4 +372,31 @@ int refm_search_for_triangulation(
     const_cast<std::vector<float>*>(&k1.kf->mvuRight)->~vector(); const_cast<std::vector<float>*>(&k2.kf->mvuRight)->~vector();
     return cnt;
 }
+
+// MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313): nobs observing key frames (allocated as one array,
+// so the std::map<KeyFrame*, size_t> iterates them in index order), key frame k observes row idx[k] of its own
+// descriptor matrix (a 4-row matrix whose row idx[k] is desc[k]); bad[k] marks key frames that are skipped.
+// Writes the chosen descriptor to out32; returns 1 if the map point's descriptor was set.
+int refm_compute_distinctive_descriptors(int nobs, const uint8_t* desc, const uint8_t* bad, uint8_t* out32)
+{
+    MapPoint* mp = (MapPoint*)std::calloc(1, sizeof(MapPoint));
+    new (&mp->mObservations) std::map<KeyFrame*, size_t>();
+    new (&mp->mDescriptor) cv::Mat();
+    KeyFrame* kfs = (KeyFrame*)std::calloc(nobs > 0 ? nobs : 1, sizeof(KeyFrame));
+    std::vector<std::vector<uint8_t> > store(nobs, std::vector<uint8_t>(4 * 32, 0));
+    for (int k = 0; k < nobs; k++) {
+        const size_t row = (size_t)(k % 4);
+        std::memcpy(&store[k][row * 32], desc + 32 * (size_t)k, 32);
+        new (const_cast<cv::Mat*>(&kfs[k].mDescriptors)) cv::Mat(4, 32, CV_8U, &store[k][0]);
+        kfs[k].mbBad = bad[k] != 0;
+        mp->mObservations[&kfs[k]] = row;
+    }
+    mp->ComputeDistinctiveDescriptors();
+    const int set = !mp->mDescriptor.empty();
+    if (set) std::memcpy(out32, mp->mDescriptor.ptr<uint8_t>(), 32);
+    for (int k = 0; k < nobs; k++) const_cast<cv::Mat*>(&kfs[k].mDescriptors)->~Mat();
+    mp->mDescriptor.~Mat(); mp->mObservations.~map();
+    std::free(kfs); std::free(mp);
+    return set;
+}
 }

@@ -438,3 +438,14 @@ def search_for_triangulation(w, only_stereo=False, check_ori=True):
             _ptr(B["an"], _f32p), _ptr(B["ur"], _f32p), len(B["nd"]), _ptr(B["nd"], _u32p), _ptr(B["st"], _i32p), _ptr(B["ft"], _u32p),
             _ptr(F, _f32p), _ptr(ep, _f32p), _ptr(sf, _f32p), _ptr(ls, _f32p), int(only_stereo), int(check_ori), _ptr(m, _i32p))
     return cnt, m[:n1]
+
+
+def distinctive_descriptor(desc):
+    """desc: (n, 32) uint8.  Returns (best index or -1, its median distance)."""
+    L = lib()
+    L.orc_distinctive_descriptor.argtypes = [C.c_int, _u8p, C.POINTER(C.c_int)]
+    L.orc_distinctive_descriptor.restype = C.c_int
+    d = _b(desc).reshape(-1, 32)
+    med = C.c_int(0)
+    idx = L.orc_distinctive_descriptor(len(d), _ptr(d, _u8p), C.byref(med))
+    return idx, med.value

@@ -239,3 +239,16 @@ def ref_search_for_triangulation(w, only_stereo=False, check_ori=True):
             P(F, _f32p), P(cw, _f32p), P(pose2, _f32p), P(K, _f32p), len(sf), P(sf, _f32p), P(ls, _f32p),
             int(only_stereo), int(check_ori), P(m, _i32p), P(ep, _f32p))
     return cnt, m[:n1], ep
+
+
+def ref_compute_distinctive_descriptors(desc, bad=None):
+    """The reference's own MapPoint::ComputeDistinctiveDescriptors.  Returns the chosen 32-byte descriptor or None."""
+    import oracle_lib as O
+    L = mlib()
+    L.refm_compute_distinctive_descriptors.argtypes = [C.c_int, _u8p, _u8p, _u8p]
+    L.refm_compute_distinctive_descriptors.restype = C.c_int
+    d = O._b(desc).reshape(-1, 32)
+    b = O._b(np.zeros(len(d), np.uint8) if bad is None else bad)
+    out = np.zeros(32, np.uint8)
+    ok = L.refm_compute_distinctive_descriptors(len(d), O._ptr(d, _u8p), O._ptr(b, _u8p), O._ptr(out, _u8p))
+    return out if ok else None

@@ -257,3 +257,17 @@ def test_search_for_triangulation_matches_oracle(only_stereo, ori):
             mm = ORBmatcher(0.6, bool(c[7]), max_items=1, max_points=2000)
             nm1, m1 = mm.search_for_triangulation_batch([w], bool(c[6]))
             assert nm1[0] == int(g["n_%d" % i]) and np.array_equal(m1[0], g["m_%d" % i])
+
+
+def test_distinctive_descriptors_match_oracle():
+    """Scope row N4: the selection of MapPoint::ComputeDistinctiveDescriptors for a ragged batch of map points:
+    0, 1, 2 observations, exactly a warp, more than a warp, several hundred."""
+    from weiner_slamit_v2_b200.workloads import observed_descriptors
+    sizes = [0, 1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 50, 64, 100, 257] + [int(v) for v in np.random.default_rng(0).integers(1, 40, 300)]
+    obs = observed_descriptors(1, sizes)
+    m = ORBmatcher(0.9, True, max_items=1, max_points=16)
+    best, med = m.distinctive_descriptors_batch(obs)
+    for p, d in enumerate(obs):
+        idx, mo = O.distinctive_descriptor(d)
+        assert best[p] == idx, (p, len(d), best[p], idx)
+        assert idx < 0 or med[p] == mo

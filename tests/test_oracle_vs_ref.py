@@ -279,3 +279,30 @@ def test_search_for_triangulation_matches_reference(only_stereo, ori):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(b[2], w["epipole"]), idx
         tot += a[0]
     assert tot > (20 if only_stereo else 400)
+
+
+@needs_refm
+def test_distinctive_descriptor_matches_reference():
+    """MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313) run natively on fake observations (some key
+    frames bad): the oracle picks the same descriptor for 1..200 observations."""
+    from weiner_slamit_v2_b200.workloads import observed_descriptors
+    rng = np.random.default_rng(3)
+    sizes = [1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 50, 100, 200] * 3
+    for k, d in enumerate(observed_descriptors(0, sizes)):
+        bad = (rng.random(len(d)) < 0.15).astype(np.uint8)
+        good = d[bad == 0]
+        idx, med = O.distinctive_descriptor(good)
+        r = R.ref_compute_distinctive_descriptors(d, bad)
+        if len(good) == 0:
+            assert r is None and idx == -1
+        else:
+            assert np.array_equal(r, good[idx]), k
+
+
+def test_distinctive_descriptor_small_cases():
+    d = np.zeros((3, 32), np.uint8); d[1, 0] = 0xff; d[2, :2] = 0xff          # distances 0-1: 8, 0-2: 16, 1-2: 8
+    assert O.distinctive_descriptor(d) == (0, 8)                               # every row's median is 8: the first row wins
+    d = np.zeros((4, 32), np.uint8); d[0, :4] = 0xff; d[1, 0] = 0x0f; d[3, 0] = 0x03
+    assert O.distinctive_descriptor(d) == (1, 2)                               # rows sorted: (0,28,30,32) (0,2,4,28) (0,2,4,32) (0,2,2,30) -> element 1
+    assert O.distinctive_descriptor(np.zeros((0, 32), np.uint8))[0] == -1
+    assert O.distinctive_descriptor(np.full((1, 32), 7, np.uint8)) == (0, 0)

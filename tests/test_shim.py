@@ -51,6 +51,7 @@ def test_shims_compile_against_reference_headers(tmp_path):
     base = ["g++", "-std=c++11", "-fsyntax-only", "-w"]
     subprocess.check_call(base + inc + [os.path.join(SHIM, "ORBmatcher_b200.cc")])
     subprocess.check_call(base + inc + [os.path.join(SHIM, "Frame_b200.cc")])
+    subprocess.check_call(base + inc + [os.path.join(SHIM, "MapPoint_b200.cc")])
     subprocess.check_call(base + ["-I" + SHIM] + inc + [os.path.join(SHIM, "ORBextractor.cc")])
 
 

@@ -96,6 +96,7 @@ SIGNATURES = {
     "orbb200_search_by_bow_keyframes": (C.c_int, [vp, C.c_int, C.POINTER(BowView), C.POINTER(BowView), C.c_float, C.c_int, vp, vp, C.c_int]),
     "orbb200_search_for_triangulation": (C.c_int, [vp, C.c_int, C.POINTER(BowView), C.POINTER(TriView), C.POINTER(BowView),
                                                    C.POINTER(TriView), vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]),
+    "orbb200_distinctive_descriptors": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
     "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

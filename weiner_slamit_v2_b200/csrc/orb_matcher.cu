@@ -1178,6 +1178,59 @@ __global__ void __launch_bounds__(128) k_tri_match(const TriParams P)
     }
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313) ------------------------------------------
+// One warp per map point.  Lanes own rows of the n x n distance matrix; a row's median (element (n-1)/2 of the
+// sorted row, the row's own 0 included) is found without sorting: the smallest value v with count(d <= v) >= k+1,
+// by bisection over 0..256.  n <= 32: the row is computed once (descriptor j broadcast by shuffle) and kept in
+// shared memory; larger n: distances are recomputed from the L1-resident descriptors in every bisection step.
+__global__ void __launch_bounds__(128) k_distinctive(const int* __restrict__ offsets, const uint8_t* __restrict__ desc, int items,
+                                                     int* __restrict__ best, int* __restrict__ bestMedian)
+{
+    __shared__ uint16_t rowbuf[4][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int item = blockIdx.x * 4 + w;
+    if (item >= items) return;
+    const int o = offsets[item], n = offsets[item + 1] - o;
+    if (n <= 0) { if (lane == 0) { best[item] = -1; if (bestMedian) bestMedian[item] = 0; } return; }
+    const uint4* d = reinterpret_cast<const uint4*>(desc) + 2 * (size_t)o;
+    const int k = (n - 1) >> 1;                                        // (int)(0.5*(N-1)) (:298)
+    uint32_t key = 0xffffffffu;                                        // (median << 20) | row: first minimum wins
+    if (n <= 32) {
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+        if (lane < n) { a0 = __ldg(d + 2 * lane); a1 = __ldg(d + 2 * lane + 1); }
+        for (int j = 0; j < n; j++) {
+            uint4 b0, b1;
+            b0.x = __shfl_sync(0xffffffffu, a0.x, j); b0.y = __shfl_sync(0xffffffffu, a0.y, j); b0.z = __shfl_sync(0xffffffffu, a0.z, j); b0.w = __shfl_sync(0xffffffffu, a0.w, j);
+            b1.x = __shfl_sync(0xffffffffu, a1.x, j); b1.y = __shfl_sync(0xffffffffu, a1.y, j); b1.z = __shfl_sync(0xffffffffu, a1.z, j); b1.w = __shfl_sync(0xffffffffu, a1.w, j);
+            rowbuf[w][lane][j] = (uint16_t)hamming256(a0, a1, b0, b1);
+        }
+        if (lane < n) {
+            int lo = 0, hi = 256;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                int c = 0;
+                for (int j = 0; j < n; j++) c += rowbuf[w][lane][j] <= mid;
+                if (c >= k + 1) hi = mid; else lo = mid + 1;
+            }
+            key = ((uint32_t)lo << 20) | (uint32_t)lane;
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            const uint4 a0 = __ldg(d + 2 * i), a1 = __ldg(d + 2 * i + 1);
+            int lo = 0, hi = 256;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                int c = 0;
+                for (int j = 0; j < n; j++) c += hamming256(a0, a1, __ldg(d + 2 * j), __ldg(d + 2 * j + 1)) <= mid;
+                if (c >= k + 1) hi = mid; else lo = mid + 1;
+            }
+            key = min(key, ((uint32_t)lo << 20) | (uint32_t)i);
+        }
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0) { best[item] = (int)(key & 0xfffffu); if (bestMedian) bestMedian[item] = (int)(key >> 20); }
+}
+
 }  // namespace orbb200
 
 // =========================================================================================
@@ -1730,6 +1783,34 @@ extern "C" int orbb200_search_for_triangulation(orbb200_matcher* m, int items, c
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(matches12, P.matches, n1 * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_distinctive_descriptors(orbb200_matcher* m, int items, const int32_t* offsets, const uint8_t* descriptors,
+                                               int total, int32_t* best, int32_t* best_median, int on_device)
+{
+    if (!m || !offsets || !descriptors || !best || items < 1 || total < 0) { set_error("bad argument"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    const int32_t* dOff = offsets; const uint8_t* dDesc = descriptors; int *dBest = best, *dMed = best_median;
+    Stager s{m, 0, st};
+    if (!on_device) {
+        if (offsets[0] != 0 || offsets[items] != total) { set_error("offsets must run from 0 to total"); return ORBB200_EINVAL; }
+        for (int i = 0; i < items; i++)
+            if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] >= (1 << 20)) { set_error("offsets must ascend (at most 1048575 descriptors per map point)"); return ORBB200_EINVAL; }
+        int rc;
+        if ((rc = s.reserve(pad(((size_t)items + 1) * 4) + pad((size_t)total * 32 + 32) + 2 * pad((size_t)items * 4)))) return rc;
+        if ((rc = s.up(offsets, (size_t)items + 1, &dOff)) || (rc = s.up(descriptors, (size_t)total * 32, &dDesc))) return rc;
+        dBest = s.out<int>(items); dMed = s.out<int>(items);
+    }
+    k_distinctive<<<(items + 3) / 4, 128, 0, st>>>(dOff, dDesc, items, dBest, dMed);
+    ORB_CHECK_LAUNCH("k_distinctive");
+    m->lastLaunches = 1;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(best, dBest, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        if (best_median) ORB_CUDA(cudaMemcpyAsync(best_median, dMed, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
     }
     return ORBB200_OK;

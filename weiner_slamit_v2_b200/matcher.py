@@ -237,6 +237,22 @@ class ORBmatcher:
                  m.ctypes.data, nm.ctypes.data, 0))
         return nm, [m[i, :(ka if keyframes else fa)["n"][i]] for i in range(items)]
 
+    # ---- MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313), scope row N4 ----
+    def distinctive_descriptors_batch(self, observed):
+        """observed: list of (n_p, 32) uint8 arrays, one per map point (descriptors of its non-bad key frames in
+        observation-map order).  Returns (best index per map point or -1, median distance of the winner)."""
+        items = len(observed)
+        off = np.zeros(items + 1, np.int32)
+        off[1:] = np.cumsum([len(o) for o in observed])
+        total = int(off[-1])
+        desc = np.zeros((max(total, 1), 32), np.uint8)
+        if total:
+            desc[:total] = np.concatenate([np.asarray(o, np.uint8).reshape(-1, 32) for o in observed])
+        best = np.zeros(items, np.int32); med = np.zeros(items, np.int32)
+        check(self._L.orbb200_distinctive_descriptors(self._h, items, off.ctypes.data, desc.ctypes.data, total, best.ctypes.data,
+                                                      med.ctypes.data, 0))
+        return best, med
+
     # ---- SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (S/ORBmatcher.cc:661-827), scope row N3 ----
     def search_for_triangulation_batch(self, pairs, only_stereo=False):
         """pairs: list of workloads.triangulation_pair()-layout dicts (k1 / k2: x, y, octave, angle, desc, has_mp, u_right,

@@ -284,3 +284,14 @@ def triangulation_pair(index, n1=2000, n2=2000, n_nodes=100, width=640, height=4
     return dict(k1=a, k2=b, F12=F12.reshape(9), Cw1=Cw1, R2w=R2f.reshape(9), t2w=t2f, K=np.array(K, np.float32),
                 epipole=epipole_in_second(Cw1, R2f, t2f, np.array(K, np.float32)), scale_factors=sf,
                 level_sigma2=(sf * sf).astype(np.float32))
+
+
+def observed_descriptors(index, sizes):
+    """Per map point, the descriptors of its observations: noisy copies of one random descriptor (0..90 flipped bits,
+    so duplicates and ties occur)."""
+    rng = np.random.default_rng(160000 + index)
+    out = []
+    for n in sizes:
+        base = rng.integers(0, 256, (1, 32)).astype(np.uint8)
+        out.append(flip_bits(np.repeat(base, n, 0), rng.integers(0, 90, n), rng) if n else np.zeros((0, 32), np.uint8))
+    return out
