@@ -300,6 +300,33 @@ int orbb200_search_for_triangulation(orbb200_matcher *m, int items, const orbb20
 int orbb200_distinctive_descriptors(orbb200_matcher *m, int items, const int32_t *offsets, const uint8_t *descriptors,
                                     int total, int32_t *best, int32_t *best_median, int on_device);
 
+/* Candidate map points of a Fuse call, items x stride: valid[i] = pMP && !pMP->isBad() && !pMP->IsInKeyFrame(pKF);
+ * normal = GetNormal(); max_distance / min_distance = the raw mfMaxDistance / mfMinDistance. */
+typedef struct orbb200_fusepoints_view {
+    const int32_t *n;
+    const uint8_t *valid;
+    const float *world_pos;       /* x3 */
+    const float *normal;          /* x3 */
+    const uint8_t *mp_desc;       /* x32 */
+    const float *max_distance, *min_distance;
+    int stride;
+} orbb200_fusepoints_view;
+
+/* The search of ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, const float th)
+ * (S/ORBmatcher.cc:829-948; scope row N3) for `items` (key frame, candidate list) pairs: projection, frustum,
+ * distance and viewing-angle gates, MapPoint::PredictScale (clamped), KeyFrame::GetFeaturesInArea, level and
+ * chi-square gates (5.99 mono / 7.8 stereo), most similar descriptor.  best_idx: items x pts->stride out = the
+ * key-frame keypoint to fuse with (distance <= TH_LOW) or -1; best_dist (may be NULL) = the smallest distance seen
+ * (256: none).  The replace-or-add surgery of :950-971 mutates the map and stays with the caller (the shim does it
+ * in list order, re-checking isBad / IsInKeyFrame as the reference does).  kf: the key frame's mvKeysUn / octaves /
+ * descriptors; u_right = mvuRight (NULL = monocular); bounds = the float image bounds of the Frame the key frame
+ * was made from (the key frame's own int copies are derived from them); Rcw/tcw/Ow = the key frame's pose. */
+int orbb200_fuse_search(orbb200_matcher *m, int items, const orbb200_frame_view *kf, const float *u_right,
+                        const orbb200_fusepoints_view *pts, const float *Rcw, const float *tcw, const float *Ow,
+                        const float K[4], float bf, const float *scale_factors, const float *inv_level_sigma2, int nlevels,
+                        float log_scale_factor, const float bounds[4], float th, int32_t *best_idx, int32_t *best_dist,
+                        int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

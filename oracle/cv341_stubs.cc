@@ -121,6 +121,17 @@ MatExpr operator*(const Mat& a, const Mat& b) { return MatExpr(&g_miniOp, 0, a, 
 MatExpr operator+(const MatExpr& e, const Mat& m) { MatExpr r(e); r.c = m; return r; }
 MatExpr operator-(const Mat& a, const Mat& b) { return MatExpr(&g_miniOp, 2, a, b); }
 
+// Mat::dot for continuous CV_32F: products and sum in double, element order (core/src/matmul.cpp, dotProd_ for short vectors)
+double Mat::dot(InputArray other) const
+{
+    const Mat& o = *static_cast<const Mat*>(other.getObj());
+    CV_Assert(type() == CV_32F && o.type() == CV_32F && total() == o.total() && isContinuous() && o.isContinuous());
+    double r = 0;
+    const float *a = ptr<float>(), *b = o.ptr<float>();
+    for (size_t i = 0; i < total(); i++) r += (double)a[i] * (double)b[i];
+    return r;
+}
+
 InputOutputArray noArray() { static _InputOutputArray none; return none; }
 
 // cv::norm, NORM_L2 of a continuous CV_32F array: squares accumulated in double in element order (core/src/stat.cpp, normL2_)

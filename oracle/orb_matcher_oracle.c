@@ -817,3 +817,89 @@ int orc_distinctive_descriptor(int n, const uint8_t *desc, int *median_out)
     if (median_out) *median_out = bestMedian;
     return bestIdx;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * The search inside ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th)
+ * (S/ORBmatcher.cc:829-975, up to the "replace or add" surgery, which stays on the host): for every candidate map
+ * point the most similar key-frame keypoint around its projection.  valid[i] = pMP && !isBad && !IsInKeyFrame(pKF)
+ * at the time the point is visited.  bounds = the Frame's float image bounds: the key frame's grid was assigned
+ * with them, while its queries (GetFeaturesInArea, IsInImage) use the int-truncated copies (S/KeyFrame.cc:42,
+ * 577-621).  best_idx[i] = keypoint index when bestDist <= TH_LOW, else -1; best_dist[i] = that distance (256: none).
+ * Mat::dot accumulates in double; PredictScale is clamped as in the other projection searches. */
+void orc_fuse_search(
+    int nmp, const uint8_t *valid, const float *wpos, const float *normal, const uint8_t *mp_desc,
+    const float *mf_max_distance, const float *mf_min_distance,
+    const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4], float bf,
+    int n, const float *kx, const float *ky, const int32_t *koct, const float *kuright, const uint8_t *kdesc,
+    int nlevels, const float *scale_factors, const float *inv_level_sigma2, float log_scale_factor,
+    const float bounds[4], float th, int32_t *best_idx, int32_t *best_dist)
+{
+    orc_grid g, q;
+    int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    orc_grid_bounds(&g, bounds);
+    orc_grid_assign(&g, n, kx, ky, koct, items);
+    q = g;                                                  /* the key frame's own copies of the bounds are ints */
+    q.min_x = (float)(int)bounds[0]; q.min_y = (float)(int)bounds[1];
+    const int maxXi = (int)bounds[2], maxYi = (int)bounds[3];
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    for (int i = 0; i < nmp; i++) {
+        best_idx[i] = -1; if (best_dist) best_dist[i] = 256;
+        if (!valid[i]) continue;
+        const float *X = wpos + 3 * (size_t)i;
+        float c3[3];
+        for (int r = 0; r < 3; r++) {
+            volatile float t = Rcw[3 * r] * X[0];
+            volatile float t1 = Rcw[3 * r + 1] * X[1];
+            volatile float t2 = Rcw[3 * r + 2] * X[2];
+            t = t + t1; t = t + t2;
+            c3[r] = t + tcw[r];
+        }
+        if (c3[2] < 0.0f) continue;                         /* :853 */
+        const float invz = 1 / c3[2];
+        const float x = c3[0] * invz, y = c3[1] * invz;
+        volatile float u = fx * x; u = u + cx;
+        volatile float v = fy * y; v = v + cy;
+        if (!(u >= q.min_x && u < (float)maxXi && v >= q.min_y && v < (float)maxYi)) continue;     /* IsInImage */
+        volatile float ur = bf * invz; ur = u - ur;
+        double ss = 0.0, dot = 0.0;
+        for (int r = 0; r < 3; r++) {
+            const float po = X[r] - Ow[r];
+            ss += (double)po * (double)po;
+            dot += (double)po * (double)normal[3 * (size_t)i + r];
+        }
+        const float dist3D = (float)sqrt(ss);
+        if (dist3D < 0.8f * mf_min_distance[i] || dist3D > 1.2f * mf_max_distance[i]) continue;
+        if (dot < 0.5 * (double)dist3D) continue;           /* viewing angle (:880) */
+        int level = orc_predict_scale(mf_max_distance[i], dist3D, log_scale_factor);
+        if (level < 0) level = 0;
+        if (level >= nlevels) level = nlevels - 1;
+        const float radius = th * scale_factors[level];
+        const int nc = orc_features_in_area(&q, u, v, radius, -1, -1, cand, n);
+        int bestDist = 256, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            const int kpLevel = koct[idx];
+            if (kpLevel < level - 1 || kpLevel > level) continue;
+            const float ex = u - kx[idx], ey = v - ky[idx];
+            volatile float e2 = ex * ex, e2b = ey * ey;
+            e2 = e2 + e2b;
+            if (kuright[idx] >= 0) {
+                const float er = ur - kuright[idx];
+                volatile float e2c = er * er;
+                e2 = e2 + e2c;
+                const float chi = e2 * inv_level_sigma2[kpLevel];
+                if ((double)chi > 7.8) continue;
+            } else {
+                const float chi = e2 * inv_level_sigma2[kpLevel];
+                if ((double)chi > 5.99) continue;
+            }
+            const int dist = orc_descriptor_distance(mp_desc + 32 * (size_t)i, kdesc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (best_dist) best_dist[i] = bestDist;
+        if (bestDist <= TH_LOW) best_idx[i] = bestIdx;
+    }
+    free(cand); free(items);
+}

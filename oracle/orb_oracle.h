@@ -151,6 +151,13 @@ int orc_search_for_triangulation(
     const float F12[9], const float epipole[2], const float *scale_factors2, const float *level_sigma2_2,
     int only_stereo, int check_orientation, int32_t *matches12);
 int orc_distinctive_descriptor(int n, const uint8_t *desc, int *median_out);
+void orc_fuse_search(
+    int nmp, const uint8_t *valid, const float *wpos, const float *normal, const uint8_t *mp_desc,
+    const float *mf_max_distance, const float *mf_min_distance,
+    const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4], float bf,
+    int n, const float *kx, const float *ky, const int32_t *koct, const float *kuright, const uint8_t *kdesc,
+    int nlevels, const float *scale_factors, const float *inv_level_sigma2, float log_scale_factor,
+    const float bounds[4], float th, int32_t *best_idx, int32_t *best_dist);
 float orc_logf(float x);
 int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
 int orc_search_by_projection_keyframe(

@@ -399,4 +399,70 @@ int refm_compute_distinctive_descriptors(int nobs, const uint8_t* desc, const ui
     std::free(kfs); std::free(mp);
     return set;
 }
+
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) (S/ORBmatcher.cc:829-975), called once per
+// candidate map point on a key frame whose keypoints hold no map points, so the call ends in the "add observation"
+// branch and the chosen keypoint can be read back from pMP->mObservations: this pins the search, which is the part
+// that runs on the device (the replace-or-add surgery stays host code in the shim).
+// valid: 1 = usable, 2 = already observed by the key frame (IsInKeyFrame), 3 = bad, 0 = NULL.
+void refm_fuse_search(
+    int nmp, const uint8_t* valid, const float* wpos, const float* normal, const uint8_t* mp_desc,
+    const float* mf_max_distance, const float* mf_min_distance,
+    const float* Rcw, const float* tcw, const float* Ow, const float* K, float bf,
+    int n, const float* kx, const float* ky, const int32_t* koct, const float* kuright, const uint8_t* kdesc,
+    int nlevels, const float* scale_factors, const float* inv_level_sigma2, float log_scale_factor,
+    const float* bounds, float th, int32_t* best_idx)
+{
+    // the Frame the key frame was made from: its grid (float bounds) is what KeyFrame::mGrid holds
+    Frame F;
+    fill_frame(F, n, kx, ky, koct, NULL, kdesc, bounds);
+    KeyFrame* kf = (KeyFrame*)std::calloc(1, sizeof(KeyFrame));
+    *const_cast<int*>(&kf->N) = n;
+    *const_cast<int*>(&kf->mnGridCols) = FRAME_GRID_COLS; *const_cast<int*>(&kf->mnGridRows) = FRAME_GRID_ROWS;
+    *const_cast<float*>(&kf->mfGridElementWidthInv) = Frame::mfGridElementWidthInv;
+    *const_cast<float*>(&kf->mfGridElementHeightInv) = Frame::mfGridElementHeightInv;
+    *const_cast<int*>(&kf->mnMinX) = Frame::mnMinX; *const_cast<int*>(&kf->mnMinY) = Frame::mnMinY;        // float -> int as in KeyFrame.cc:42
+    *const_cast<int*>(&kf->mnMaxX) = Frame::mnMaxX; *const_cast<int*>(&kf->mnMaxY) = Frame::mnMaxY;
+    *const_cast<float*>(&kf->fx) = K[0]; *const_cast<float*>(&kf->fy) = K[1]; *const_cast<float*>(&kf->cx) = K[2]; *const_cast<float*>(&kf->cy) = K[3];
+    *const_cast<float*>(&kf->mbf) = bf; *const_cast<float*>(&kf->mfLogScaleFactor) = log_scale_factor;
+    new (&kf->mGrid) std::vector<std::vector<std::vector<size_t> > >(FRAME_GRID_COLS);
+    for (int i = 0; i < FRAME_GRID_COLS; i++) { kf->mGrid[i].resize(FRAME_GRID_ROWS); for (int j = 0; j < FRAME_GRID_ROWS; j++) kf->mGrid[i][j] = F.mGrid[i][j]; }
+    new (const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn)) std::vector<cv::KeyPoint>(F.mvKeysUn);
+    new (const_cast<std::vector<float>*>(&kf->mvuRight)) std::vector<float>(kuright, kuright + n);
+    new (const_cast<cv::Mat*>(&kf->mDescriptors)) cv::Mat(n > 0 ? n : 1, 32, CV_8U, (void*)kdesc);
+    new (const_cast<std::vector<float>*>(&kf->mvScaleFactors)) std::vector<float>(scale_factors, scale_factors + nlevels);
+    new (const_cast<std::vector<float>*>(&kf->mvInvLevelSigma2)) std::vector<float>(inv_level_sigma2, inv_level_sigma2 + nlevels);
+    new (&kf->mvpMapPoints) std::vector<MapPoint*>(n, static_cast<MapPoint*>(NULL));
+    float T[16] = {Rcw[0], Rcw[1], Rcw[2], tcw[0], Rcw[3], Rcw[4], Rcw[5], tcw[1], Rcw[6], Rcw[7], Rcw[8], tcw[2], 0, 0, 0, 1};
+    float O3[3] = {Ow[0], Ow[1], Ow[2]};
+    new (&kf->Tcw) cv::Mat(4, 4, CV_32F, T);
+    new (&kf->Ow) cv::Mat(3, 1, CV_32F, O3);
+
+    ORBmatcher matcher(0.6f, true);
+    MapPoint* mps = (MapPoint*)std::calloc(nmp > 0 ? nmp : 1, sizeof(MapPoint));
+    for (int i = 0; i < nmp; i++) {
+        best_idx[i] = -1;
+        MapPoint* p = &mps[i];
+        new (&p->mDescriptor) cv::Mat(1, 32, CV_8U, (void*)(mp_desc + 32 * (size_t)i));
+        new (&p->mWorldPos) cv::Mat(3, 1, CV_32F, (void*)(wpos + 3 * (size_t)i));
+        new (&p->mNormalVector) cv::Mat(3, 1, CV_32F, (void*)(normal + 3 * (size_t)i));
+        new (&p->mObservations) std::map<KeyFrame*, size_t>();
+        p->mfMaxDistance = mf_max_distance[i]; p->mfMinDistance = mf_min_distance[i];
+        p->mbBad = valid[i] == 3;
+        if (valid[i] == 2) p->mObservations[kf] = 0;
+        std::vector<MapPoint*> one(1, valid[i] ? p : static_cast<MapPoint*>(NULL));
+        const int fused = matcher.Fuse(kf, one, th);
+        if (fused && valid[i] == 1) {
+            best_idx[i] = (int32_t)p->mObservations[kf];
+            kf->mvpMapPoints[best_idx[i]] = NULL;                 // next map point sees an empty key frame again
+        }
+        p->mObservations.~map(); p->mNormalVector.~Mat(); p->mWorldPos.~Mat(); p->mDescriptor.~Mat();
+    }
+    std::free(mps);
+    kf->Ow.~Mat(); kf->Tcw.~Mat(); kf->mvpMapPoints.~vector(); kf->mGrid.~vector();
+    const_cast<std::vector<float>*>(&kf->mvInvLevelSigma2)->~vector(); const_cast<std::vector<float>*>(&kf->mvScaleFactors)->~vector();
+    const_cast<cv::Mat*>(&kf->mDescriptors)->~Mat(); const_cast<std::vector<float>*>(&kf->mvuRight)->~vector();
+    const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn)->~vector();
+    std::free(kf);
+}
 }

@@ -449,3 +449,28 @@ def distinctive_descriptor(desc):
     med = C.c_int(0)
     idx = L.orc_distinctive_descriptor(len(d), _ptr(d, _u8p), C.byref(med))
     return idx, med.value
+
+
+def _fuse_call(f, w, bounds, th, valid, with_dist):
+    kp = w["kp"]
+    n, nmp = len(kp), len(w["valid"])
+    a = dict(v=valid(_b(w["valid"])), wp=_f(w["wpos"]), nr=_f(w["normal"]), md=_b(w["mp_desc"]), mx=_f(w["mf_max"]), mn=_f(w["mf_min"]),
+             R=_f(w["Rcw"]), t=_f(w["tcw"]), Ow=_f(w["Ow"]), K=_f(w["K"]), kx=_f(kp["x"]), ky=_f(kp["y"]), ko=_i(kp["octave"]),
+             ur=_f(w["u_right"]), kd=_b(w["kdesc"]), sf=_f(w["scale_factors"]), il=_f(w["inv_level_sigma2"]), b=_bounds(bounds))
+    best = np.full(max(nmp, 1), -1, np.int32); dist = np.full(max(nmp, 1), 256, np.int32)
+    args = [nmp, _ptr(a["v"], _u8p), _ptr(a["wp"], _f32p), _ptr(a["nr"], _f32p), _ptr(a["md"], _u8p), _ptr(a["mx"], _f32p), _ptr(a["mn"], _f32p),
+            _ptr(a["R"], _f32p), _ptr(a["t"], _f32p), _ptr(a["Ow"], _f32p), _ptr(a["K"], _f32p), float(w["bf"]),
+            n, _ptr(a["kx"], _f32p), _ptr(a["ky"], _f32p), _ptr(a["ko"], _i32p), _ptr(a["ur"], _f32p), _ptr(a["kd"], _u8p),
+            len(a["sf"]), _ptr(a["sf"], _f32p), _ptr(a["il"], _f32p), float(w["log_scale"]), _ptr(a["b"], _f32p), float(th), _ptr(best, _i32p)]
+    f.argtypes = [C.c_int, _u8p, _f32p, _f32p, _u8p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
+                  C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, C.c_int, _f32p, _f32p, C.c_float, _f32p, C.c_float, _i32p] + ([_i32p] if with_dist else [])
+    f.restype = None
+    if with_dist:
+        args.append(_ptr(dist, _i32p))
+    f(*args)
+    return best[:nmp], dist[:nmp]
+
+
+def fuse_search(w, bounds, th=3.0):
+    """w: workloads.fuse_frame() dict.  Returns (best keypoint index per map point or -1, best distance)."""
+    return _fuse_call(lib().orc_fuse_search, w, bounds, th, lambda v: _b((v == 1).astype(np.uint8)), True)

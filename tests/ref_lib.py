@@ -252,3 +252,9 @@ def ref_compute_distinctive_descriptors(desc, bad=None):
     out = np.zeros(32, np.uint8)
     ok = L.refm_compute_distinctive_descriptors(len(d), O._ptr(d, _u8p), O._ptr(b, _u8p), O._ptr(out, _u8p))
     return out if ok else None
+
+
+def ref_fuse_search(w, bounds, th=3.0):
+    """The reference's own ORBmatcher::Fuse(pKF, {pMP}, th), one candidate map point per call (see the harness)."""
+    import oracle_lib as O
+    return O._fuse_call(mlib().refm_fuse_search, w, bounds, th, lambda v: v, False)[0]

@@ -271,3 +271,28 @@ def test_distinctive_descriptors_match_oracle():
         idx, mo = O.distinctive_descriptor(d)
         assert best[p] == idx, (p, len(d), best[p], idx)
         assert idx < 0 or med[p] == mo
+
+
+@pytest.mark.parametrize("th", [2.5, 3.0, 10.0])
+def test_fuse_search_matches_oracle(th):
+    """Scope row N3: the search of Fuse(pKF, vpMapPoints, th) for a ragged batch, and the reference's golden vectors."""
+    from weiner_slamit_v2_b200.workloads import fuse_frame
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    ws = [fuse_frame(50 + i, a, b, stereo_fraction=s) for i, (a, b, s) in enumerate([(3000, 2000, 0.2), (3000, 2000, 0.0), (500, 300, 0.5),
+                                                                                       (0, 100, 0.2), (100, 0, 0.2)])]
+    m = ORBmatcher(0.6, True, max_items=len(ws), max_points=3000)
+    res = m.fuse_search_batch(ws, bounds, th)
+    tot = 0
+    for i, w in enumerate(ws):
+        bo, do = O.fuse_search(w, bounds, th)
+        assert np.array_equal(res[i][0], bo), i
+        assert np.array_equal(res[i][1], do), i
+        tot += int((bo >= 0).sum())
+    assert tot > 400
+    if th == 3.0:
+        import os
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_fuse.npz"))
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            r = m.fuse_search_batch([fuse_frame(int(c[0]), int(c[1]), int(c[2]))], bounds, float(c[3]))
+            assert np.array_equal(r[0][0], g["best_%d" % i])

@@ -164,7 +164,13 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
     from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
     g = np.load(path)
-    if "triangulation" in os.path.basename(path):
+    if "fuse" in os.path.basename(path):
+        from weiner_slamit_v2_b200.workloads import fuse_frame
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            a = O.fuse_search(fuse_frame(int(c[0]), int(c[1]), int(c[2])), (-13.7, -9.2, 661.3, 492.8), float(c[3]))
+            assert np.array_equal(a[0], g["best_%d" % i])
+    elif "triangulation" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import triangulation_pair
         for i in range(int(g["count"])):
             c = g["cfg_%d" % i]
@@ -306,3 +312,22 @@ def test_distinctive_descriptor_small_cases():
     assert O.distinctive_descriptor(d) == (1, 2)                               # rows sorted: (0,28,30,32) (0,2,4,28) (0,2,4,32) (0,2,2,30) -> element 1
     assert O.distinctive_descriptor(np.zeros((0, 32), np.uint8))[0] == -1
     assert O.distinctive_descriptor(np.full((1, 32), 7, np.uint8)) == (0, 0)
+
+
+@needs_refm
+@pytest.mark.parametrize("th", [2.5, 3.0, 10.0])
+def test_fuse_search_matches_reference(th):
+    """The search inside Fuse(pKF, vpMapPoints, th) (S/ORBmatcher.cc:829-948) against the reference's own Fuse called
+    once per candidate on an empty key frame (oracle/ref_matcher_harness.cc): integer and fractional image bounds
+    (the key frame truncates them), mono and stereo keypoints, NULL / bad / already-observed candidates."""
+    from weiner_slamit_v2_b200.workloads import fuse_frame
+    tot = 0
+    for idx, (nmp, nkp, bounds, sfr) in enumerate([(3000, 2000, (0.0, 0.0, 640.0, 480.0), 0.2), (3000, 2000, (-13.7, -9.2, 661.3, 492.8), 0.0),
+                                                   (500, 300, (-13.7, -9.2, 661.3, 492.8), 0.5), (0, 100, (0.0, 0.0, 640.0, 480.0), 0.2),
+                                                   (100, 0, (0.0, 0.0, 640.0, 480.0), 0.2)]):
+        w = fuse_frame(990 + idx, nmp, nkp, stereo_fraction=sfr)
+        a = O.fuse_search(w, bounds, th)
+        b = R.ref_fuse_search(w, bounds, th)
+        assert np.array_equal(a[0], b), idx
+        tot += int((b >= 0).sum())
+    assert tot > 400

@@ -120,3 +120,13 @@ for i, (idx, na, nb, nn, sfr, fwd, st, ori) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_triangulation.npz"), **out)
 print("ref_match_triangulation.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+from weiner_slamit_v2_b200.workloads import fuse_frame  # noqa: E402
+cfgs = [(880, 3000, 2000, 3.0), (881, 2000, 1500, 2.5), (882, 800, 900, 10.0)]
+for i, (idx, nmp, nkp, th) in enumerate(cfgs):
+    r = R.ref_fuse_search(fuse_frame(idx, nmp, nkp), (-13.7, -9.2, 661.3, 492.8), th)
+    out["cfg_%d" % i] = np.array([idx, nmp, nkp, th]); out["best_%d" % i] = r
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_fuse.npz"), **out)
+print("ref_match_fuse.npz", [int((out["best_%d" % i] >= 0).sum()) for i in range(len(cfgs))])

@@ -52,6 +52,11 @@ class TriView(C.Structure):
     _fields_ = [("x", vp), ("y", vp), ("octave", vp), ("u_right", vp), ("has_mp", vp)]
 
 
+class FusePointsView(C.Structure):
+    _fields_ = [("n", vp), ("valid", vp), ("world_pos", vp), ("normal", vp), ("mp_desc", vp), ("max_distance", vp), ("min_distance", vp),
+                ("stride", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/orb_b200.h declares
 SIGNATURES = {
     "orbb200_last_error": (C.c_char_p, []),
@@ -97,6 +102,8 @@ SIGNATURES = {
     "orbb200_search_for_triangulation": (C.c_int, [vp, C.c_int, C.POINTER(BowView), C.POINTER(TriView), C.POINTER(BowView),
                                                    C.POINTER(TriView), vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]),
     "orbb200_distinctive_descriptors": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]),
+    "orbb200_fuse_search": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), vp, C.POINTER(FusePointsView), vp, vp, vp, vp, C.c_float, vp, vp,
+                                      C.c_int, C.c_float, vp, C.c_float, vp, vp, C.c_int]),
     "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

@@ -1231,6 +1231,98 @@ __global__ void __launch_bounds__(128) k_distinctive(const int* __restrict__ off
     if (lane == 0) { best[item] = (int)(key & 0xfffffu); if (bestMedian) bestMedian[item] = (int)(key >> 20); }
 }
 
+// ---- the search inside ORBmatcher::Fuse(pKF, vpMapPoints, th) (S/ORBmatcher.cc:829-975) ------------------------
+// Every candidate map point is independent (the keypoints are not consumed; the replace-or-add surgery that follows
+// is host code): one thread per map point projects it, applies the frustum / distance / viewing-angle gates,
+// predicts the level and scans the key frame's grid cells.  The key frame's grid holds the Frame's assignment
+// (float bounds) while its queries use the int-truncated bounds (S/KeyFrame.cc:42, 577-621).
+struct FuseParams {
+    FrameDev f;                  // the key frame's undistorted keypoints + descriptors
+    const float* uRight;         // items x f.stride or NULL (monocular)
+    GridGeo g, q;                // assignment / query geometry
+    int maxXi, maxYi;
+    const int* cellStart; const int* cellItems;
+    const int* nmp; const uint8_t* valid; const float *wpos, *normal; const uint8_t* mpDesc; const float *mfMax, *mfMin;
+    int mpStride;
+    const float *Rcw, *tcw, *Ow;
+    float fx, fy, cx, cy, bf, th, logScale;
+    const float *scaleFactors, *invLevelSigma2;
+    int nlevels;
+    int *bestIdx, *bestDist;
+};
+
+__global__ void __launch_bounds__(128) k_fuse_search(const FuseParams P)
+{
+    const int item = blockIdx.y;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= min(P.nmp[item], P.mpStride)) return;
+    const size_t lo = (size_t)item * P.mpStride + i;
+    int bestDist = 256, bestIdx = -1;
+    do {
+        if (!P.valid[lo]) break;
+        const float* R = P.Rcw + (size_t)item * 9;
+        const float* t = P.tcw + (size_t)item * 3;
+        const float* O = P.Ow + (size_t)item * 3;
+        const float* X = P.wpos + lo * 3;
+        float c3[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            c3[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3 * r], X[0]), __fmul_rn(R[3 * r + 1], X[1])), __fmul_rn(R[3 * r + 2], X[2])), t[r]);
+        if (c3[2] < 0.0f) break;                                                    // :853
+        const float invz = __fdiv_rn(1.0f, c3[2]);
+        const float u = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(c3[0], invz)), P.cx);
+        const float v = __fadd_rn(__fmul_rn(P.fy, __fmul_rn(c3[1], invz)), P.cy);
+        if (!(u >= P.q.minX && u < (float)P.maxXi && v >= P.q.minY && v < (float)P.maxYi)) break;     // KeyFrame::IsInImage
+        const float ur = __fsub_rn(u, __fmul_rn(P.bf, invz));
+        double ss = 0.0, dot = 0.0;                                                 // cv::norm, Mat::dot: double accumulation
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const double po = (double)__fsub_rn(X[r], O[r]);
+            ss = __dadd_rn(ss, __dmul_rn(po, po));
+            dot = __dadd_rn(dot, __dmul_rn(po, (double)P.normal[lo * 3 + r]));
+        }
+        const float dist3D = __double2float_rn(__dsqrt_rn(ss));
+        const float mx = P.mfMax[lo];
+        if (dist3D < __fmul_rn(0.8f, P.mfMin[lo]) || dist3D > __fmul_rn(1.2f, mx)) break;
+        if (dot < __dmul_rn(0.5, (double)dist3D)) break;                             // viewing angle (:880)
+        int level = (int)ceilf(__fdiv_rn(libm_logf(__fdiv_rn(mx, dist3D)), P.logScale));
+        level = max(0, min(level, P.nlevels - 1));
+        const float radius = __fmul_rn(P.th, P.scaleFactors[level]);
+        int c0, c1, r0, r1;
+        if (!cell_range(P.q, u, v, radius, c0, c1, r0, r1)) break;
+        const float* kx = P.f.x + (size_t)item * P.f.stride;
+        const float* ky = P.f.y + (size_t)item * P.f.stride;
+        const int* koct = P.f.octave + (size_t)item * P.f.stride;
+        const float* kur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
+        const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
+        const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+        const int* ci = P.cellItems + (size_t)item * P.f.stride;
+        const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + lo * 32);
+        const uint4 a0 = __ldg(md), a1 = __ldg(md + 1);
+        for (int c = c0; c <= c1; c++) {
+            const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
+            for (int p = s; p < e; p++) {
+                const int idx = ci[p];
+                if (!(fabsf(__fsub_rn(kx[idx], u)) < radius && fabsf(__fsub_rn(ky[idx], v)) < radius)) continue;
+                const int kl = koct[idx];
+                if (kl < level - 1 || kl > level) continue;                          // :905
+                const float ex = __fsub_rn(u, kx[idx]), ey = __fsub_rn(v, ky[idx]);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                const float kr = kur ? kur[idx] : -1.f;
+                if (kr >= 0) {
+                    const float er = __fsub_rn(ur, kr);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, P.invLevelSigma2[kl]) > 7.8) continue;
+                } else if ((double)__fmul_rn(e2, P.invLevelSigma2[kl]) > 5.99) continue;
+                const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+            }
+        }
+    } while (false);
+    P.bestIdx[lo] = bestDist <= TH_LOW ? bestIdx : -1;
+    if (P.bestDist) P.bestDist[lo] = bestDist;
+}
+
 }  // namespace orbb200
 
 // =========================================================================================
@@ -1811,6 +1903,61 @@ extern "C" int orbb200_distinctive_descriptors(orbb200_matcher* m, int items, co
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(best, dBest, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
         if (best_median) ORB_CUDA(cudaMemcpyAsync(best_median, dMed, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_fuse_search(orbb200_matcher* m, int items, const orbb200_frame_view* kf, const float* u_right,
+                                   const orbb200_fusepoints_view* pts, const float* Rcw, const float* tcw, const float* Ow,
+                                   const float* K, float bf, const float* scale_factors, const float* inv_level_sigma2, int nlevels,
+                                   float log_scale_factor, const float* bounds, float th, int32_t* best_idx, int32_t* best_dist,
+                                   int on_device)
+{
+    if (!m || !kf || !pts || !Rcw || !tcw || !Ow || !K || !scale_factors || !inv_level_sigma2 || !best_idx) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (!kf->n || !kf->x || !kf->y || !kf->octave || !kf->desc || !pts->n || !pts->valid || !pts->world_pos || !pts->normal || !pts->mp_desc ||
+        !pts->max_distance || !pts->min_distance) { set_error("incomplete view"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, kf->stride, "key frame")) || (rc = check_view(m, items, pts->stride, "map points"))) return rc;
+    if (nlevels < 1 || nlevels > 32 || !bounds || !(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1]) || !(log_scale_factor > 0.f)) { set_error("bad geometry"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    FuseParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t np = (size_t)items * kf->stride, nl = (size_t)items * pts->stride;
+    Stager s{m, 0, st};
+    if (on_device) {
+        P.f = as_dev(kf); P.uRight = u_right;
+        P.nmp = pts->n; P.valid = pts->valid; P.wpos = pts->world_pos; P.normal = pts->normal; P.mpDesc = pts->mp_desc;
+        P.mfMax = pts->max_distance; P.mfMin = pts->min_distance;
+        P.Rcw = Rcw; P.tcw = tcw; P.Ow = Ow; P.scaleFactors = scale_factors; P.invLevelSigma2 = inv_level_sigma2;
+        P.bestIdx = best_idx; P.bestDist = best_dist;
+    } else {
+        const size_t bytes = frame_bytes(kf, items) + pad(np * 4) + pad((size_t)items * 4) + pad(nl) + 2 * pad(nl * 12) + pad(nl * 32) + 2 * pad(nl * 4) +
+                             pad((size_t)items * 36) + 2 * pad((size_t)items * 12) + 2 * pad((size_t)nlevels * 4) + 2 * pad(nl * 4);
+        if ((rc = s.reserve(bytes))) return rc;
+        if ((rc = upload_frame(s, kf, items, &P.f, false))) return rc;
+        if ((rc = s.up(u_right, u_right ? np : 0, &P.uRight)) || (rc = s.up(pts->n, items, &P.nmp)) || (rc = s.up(pts->valid, nl, &P.valid)) ||
+            (rc = s.up(pts->world_pos, nl * 3, &P.wpos)) || (rc = s.up(pts->normal, nl * 3, &P.normal)) || (rc = s.up(pts->mp_desc, nl * 32, &P.mpDesc)) ||
+            (rc = s.up(pts->max_distance, nl, &P.mfMax)) || (rc = s.up(pts->min_distance, nl, &P.mfMin)) ||
+            (rc = s.up(Rcw, (size_t)items * 9, &P.Rcw)) || (rc = s.up(tcw, (size_t)items * 3, &P.tcw)) || (rc = s.up(Ow, (size_t)items * 3, &P.Ow)) ||
+            (rc = s.up(scale_factors, (size_t)nlevels, &P.scaleFactors)) || (rc = s.up(inv_level_sigma2, (size_t)nlevels, &P.invLevelSigma2))) return rc;
+        P.bestIdx = s.out<int>(nl);
+        P.bestDist = s.out<int>(nl);
+    }
+    P.mpStride = pts->stride; P.g = grid_geo(bounds); P.q = P.g;
+    P.q.minX = (float)(int)bounds[0]; P.q.minY = (float)(int)bounds[1];          // KeyFrame::mnMinX/Y are ints (S/KeyFrame.cc:42)
+    P.maxXi = (int)bounds[2]; P.maxYi = (int)bounds[3];
+    P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.bf = bf; P.th = th; P.logScale = log_scale_factor; P.nlevels = nlevels;
+    k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
+    ORB_CHECK_LAUNCH("k_build_grid");
+    k_fuse_search<<<dim3((pts->stride + 127) / 128, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_fuse_search");
+    m->lastLaunches = 2;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(best_idx, P.bestIdx, nl * 4, cudaMemcpyDeviceToHost, st));
+        if (best_dist) ORB_CUDA(cudaMemcpyAsync(best_dist, P.bestDist, nl * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
     }
     return ORBB200_OK;

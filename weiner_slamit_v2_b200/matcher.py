@@ -237,6 +237,41 @@ class ORBmatcher:
                  m.ctypes.data, nm.ctypes.data, 0))
         return nm, [m[i, :(ka if keyframes else fa)["n"][i]] for i in range(items)]
 
+    # ---- the search of Fuse(pKF, vpMapPoints, th) (S/ORBmatcher.cc:829-948), scope row N3 ----
+    def fuse_search_batch(self, ws, bounds, th=3.0):
+        """ws: list of workloads.fuse_frame()-layout dicts (valid == 1 marks usable candidates; kp / kdesc / u_right = the
+        key frame; Rcw, tcw, Ow, K, bf, scale_factors, inv_level_sigma2, log_scale).  Returns per item
+        (best keypoint index per candidate or -1, smallest distance seen)."""
+        from ._lib import FrameView, FusePointsView
+        items = len(ws)
+        nk = np.array([len(w["kp"]) for w in ws], np.int32)
+        nm = np.array([len(w["valid"]) for w in ws], np.int32)
+        s, ms = max(1, int(nk.max())), max(1, int(nm.max()))
+        self._ensure(items, max(s, ms))
+        k = dict(x=_pack([w["kp"]["x"] for w in ws], s, np.float32), y=_pack([w["kp"]["y"] for w in ws], s, np.float32),
+                 o=_pack([w["kp"]["octave"] for w in ws], s, np.int32), d=_pack([w["kdesc"] for w in ws], s, np.uint8, (32,)),
+                 ur=_pack([w["u_right"] for w in ws], s, np.float32))
+        fv = FrameView(nk.ctypes.data, k["x"].ctypes.data, k["y"].ctypes.data, k["o"].ctypes.data, None, k["d"].ctypes.data, s)
+        a = dict(v=_pack([(np.asarray(w["valid"]) == 1).astype(np.uint8) for w in ws], ms, np.uint8),
+                 wp=_pack([np.asarray(w["wpos"], np.float32).reshape(-1, 3) for w in ws], ms, np.float32, (3,)),
+                 nr=_pack([np.asarray(w["normal"], np.float32).reshape(-1, 3) for w in ws], ms, np.float32, (3,)),
+                 md=_pack([w["mp_desc"] for w in ws], ms, np.uint8, (32,)), mx=_pack([w["mf_max"] for w in ws], ms, np.float32),
+                 mn=_pack([w["mf_min"] for w in ws], ms, np.float32))
+        pv = FusePointsView(nm.ctypes.data, a["v"].ctypes.data, a["wp"].ctypes.data, a["nr"].ctypes.data, a["md"].ctypes.data,
+                            a["mx"].ctypes.data, a["mn"].ctypes.data, ms)
+        R = np.ascontiguousarray(np.stack([np.asarray(w["Rcw"], np.float32).reshape(9) for w in ws]))
+        t = np.ascontiguousarray(np.stack([np.asarray(w["tcw"], np.float32).reshape(3) for w in ws]))
+        Ow = np.ascontiguousarray(np.stack([np.asarray(w["Ow"], np.float32).reshape(3) for w in ws]))
+        K = np.ascontiguousarray(ws[0]["K"], np.float32)
+        sf = np.ascontiguousarray(ws[0]["scale_factors"], np.float32)
+        il = np.ascontiguousarray(ws[0]["inv_level_sigma2"], np.float32)
+        bnd = np.ascontiguousarray(bounds, np.float32)
+        best = np.full((items, ms), -1, np.int32); dist = np.full((items, ms), 256, np.int32)
+        check(self._L.orbb200_fuse_search(self._h, items, C.byref(fv), k["ur"].ctypes.data, C.byref(pv), R.ctypes.data, t.ctypes.data,
+                                          Ow.ctypes.data, K.ctypes.data, float(ws[0]["bf"]), sf.ctypes.data, il.ctypes.data, len(sf),
+                                          float(ws[0]["log_scale"]), bnd.ctypes.data, float(th), best.ctypes.data, dist.ctypes.data, 0))
+        return [(best[i, :nm[i]], dist[i, :nm[i]]) for i in range(items)]
+
     # ---- MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313), scope row N4 ----
     def distinctive_descriptors_batch(self, observed):
         """observed: list of (n_p, 32) uint8 arrays, one per map point (descriptors of its non-bad key frames in

@@ -7,6 +7,8 @@
 //   SearchByBoW(pKF, F, vpMapPointMatches)               (replaces S/ORBmatcher.cc:161-292; scope row N3)
 //   SearchByBoW(pKF1, pKF2, vpMatches12)                 (replaces S/ORBmatcher.cc:526-659; scope row N3)
 //   SearchForTriangulation(pKF1, pKF2, F12, pairs, bOnlyStereo) (replaces S/ORBmatcher.cc:661-827; scope row N3)
+//   Fuse(pKF, vpMapPoints, th)                           (replaces S/ORBmatcher.cc:829-975; scope row N3: the search
+//                                                         runs on the device, the replace-or-add surgery stays here)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -471,6 +473,84 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     for (int i = 0; i < k1.n; i++)
         if (matches[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)matches[i]));      // :815-820
     return nmatches;
+}
+
+int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th)
+{
+    cv::Mat Rcw = pKF->GetRotation();
+    cv::Mat tcw = pKF->GetTranslation();
+    cv::Mat Ow = pKF->GetCameraCenter();
+    const int nMPs = (int)vpMapPoints.size(), nk = pKF->N;
+    if (nMPs == 0 || nk == 0) return 0;
+    orbb200_matcher* h = tlsMatcher.get(nMPs > nk ? nMPs : nk);
+    if (!h) return 0;
+
+    // the key frame's keypoints
+    int32_t kn = nk;
+    std::vector<float> kx(nk), ky(nk), kur(nk);
+    std::vector<int32_t> koct(nk);
+    std::vector<unsigned char> kdesc((size_t)nk * 32);
+    for (int i = 0; i < nk; i++) {
+        kx[i] = pKF->mvKeysUn[i].pt.x; ky[i] = pKF->mvKeysUn[i].pt.y; koct[i] = pKF->mvKeysUn[i].octave; kur[i] = pKF->mvuRight[i];
+        std::memcpy(&kdesc[(size_t)i * 32], pKF->mDescriptors.ptr<unsigned char>(i), 32);
+    }
+    orbb200_frame_view kv;
+    kv.n = &kn; kv.x = &kx[0]; kv.y = &ky[0]; kv.octave = &koct[0]; kv.angle = 0; kv.desc = &kdesc[0]; kv.stride = nk;
+
+    // the candidates, in the state the reference would find them in when it reaches them (see below)
+    int32_t pn = nMPs;
+    std::vector<unsigned char> valid(nMPs), desc((size_t)nMPs * 32);
+    std::vector<float> wpos((size_t)nMPs * 3), normal((size_t)nMPs * 3), maxD(nMPs), minD(nMPs);
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        valid[i] = (pMP && !pMP->isBad() && !pMP->IsInKeyFrame(pKF)) ? 1 : 0;          // :845-849
+        if (!valid[i]) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos(), Pn = pMP->GetNormal(), d = pMP->GetDescriptor();
+        for (int k = 0; k < 3; k++) { wpos[3 * (size_t)i + k] = p3Dw.at<float>(k); normal[3 * (size_t)i + k] = Pn.at<float>(k); }
+        if (!d.empty()) std::memcpy(&desc[(size_t)i * 32], d.ptr<unsigned char>(), 32);
+        std::unique_lock<std::mutex> lock(pMP->*MapPointFields::PosMutex());
+        maxD[i] = pMP->*MapPointFields::MaxDistance();
+        minD[i] = pMP->*MapPointFields::MinDistance();
+    }
+    orbb200_fusepoints_view pv;
+    pv.n = &pn; pv.valid = &valid[0]; pv.world_pos = &wpos[0]; pv.normal = &normal[0]; pv.mp_desc = &desc[0];
+    pv.max_distance = &maxD[0]; pv.min_distance = &minD[0]; pv.stride = nMPs;
+
+    float R9[9], t3[3], O3[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R9[3 * r + c] = Rcw.at<float>(r, c); t3[r] = tcw.at<float>(r); O3[r] = Ow.at<float>(r); }
+    const float K[4] = {pKF->fx, pKF->fy, pKF->cx, pKF->cy};
+    float bounds[4];
+    FrameBounds(bounds);                     // the Frame statics the key frame's grid was assigned with
+    std::vector<int32_t> best(nMPs, -1);
+    if (orbb200_fuse_search(h, 1, &kv, &kur[0], &pv, R9, t3, O3, K, pKF->mbf, &pKF->mvScaleFactors[0], &pKF->mvInvLevelSigma2[0],
+                            (int)pKF->mvScaleFactors.size(), pKF->mfLogScaleFactor, bounds, th, &best[0], 0, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::Fuse: %s\n", orbb200_last_error());
+        return 0;
+    }
+
+    // The surgery, in list order, exactly as :950-971.  The search result of a candidate does not depend on earlier
+    // surgery (keypoints are not consumed, positions and descriptors of unvisited candidates are untouched); its
+    // admission does: a candidate that earlier surgery made bad, or attached to this key frame, is skipped here as
+    // the reference would skip it (a candidate cannot become admissible again).
+    int nFused = 0;
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP || !valid[i] || best[i] < 0) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        const int bestIdx = best[i];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx);
+            pKF->AddMapPoint(pMP, bestIdx);
+        }
+        nFused++;
+    }
+    return nFused;
 }
 
 }  // namespace ORB_SLAM2

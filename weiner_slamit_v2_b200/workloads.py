@@ -295,3 +295,57 @@ def observed_descriptors(index, sizes):
         base = rng.integers(0, 256, (1, 32)).astype(np.uint8)
         out.append(flip_bits(np.repeat(base, n, 0), rng.integers(0, 90, n), rng) if n else np.zeros((0, 32), np.uint8))
     return out
+
+
+def fuse_frame(index, n_mp=3000, n_kp=2000, width=640, height=480, nlevels=8, scale=1.2,
+               K=(526.69, 540.36, 313.07, 238.39), bf=40.0, stereo_fraction=0.2):
+    """A (key frame, candidate map points) pair for the search inside ORBmatcher::Fuse: map points with world
+    position, mean viewing direction, descriptor and scale-invariance distances; key-frame keypoints near the
+    projections at about the predicted level (reprojection noise around the chi-square gates), some with a stereo
+    coordinate.  valid: 1 usable, 2 already observed by the key frame, 3 bad, 0 NULL.  Includes points behind the
+    camera, outside the image, outside the distance range and seen from too steep an angle."""
+    rng = np.random.default_rng(170000 + index)
+    fx, fy, cx, cy = K
+    R = _rodrigues(rng, 2, 25).astype(np.float32)
+    t = rng.normal(0, 0.5, 3).astype(np.float32)
+    u = rng.uniform(-20, width + 20, n_mp); v = rng.uniform(-20, height + 20, n_mp)
+    z = rng.uniform(1.0, 10.0, n_mp)
+    z[rng.random(n_mp) < 0.03] *= -1
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    wpos = ((Xc - t) @ R.astype(np.float64)).astype(np.float32)
+    Ow = camera_centre(R, t)
+    PO = wpos.astype(np.float64) - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    nrm = PO / np.maximum(dist, 1e-9)[:, None] + rng.normal(0, 0.25, (n_mp, 3))
+    steep = rng.random(n_mp) < 0.1
+    nrm[steep] = rng.normal(size=(int(steep.sum()), 3))
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    level = rng.integers(0, nlevels, n_mp)
+    expo = level - 0.5 + rng.uniform(-0.3, 0.3, n_mp)
+    kind = rng.random(n_mp)
+    expo = np.where(kind < 0.04, -2.0, expo)
+    expo = np.where(kind > 0.96, nlevels + 2.0, expo)
+    mf_max = (dist * scale ** expo).astype(np.float32)
+    mf_min = (mf_max / np.float32(scale ** (nlevels - 1))).astype(np.float32)
+    valid = rng.choice(np.array([0, 1, 2, 3], np.uint8), n_mp, p=[0.05, 0.82, 0.08, 0.05])
+    mp_desc = rng.integers(0, 256, (n_mp, 32)).astype(np.uint8)
+    kp = random_keypoints(n_kp, width, height, rng, nlevels)
+    src = rng.integers(0, max(n_mp, 1), n_kp)
+    re = (rng.random(n_kp) < 0.8) & (n_mp > 0)
+    if n_mp == 0:
+        u = v = z = np.ones(1); level = np.zeros(1, np.int64); mp_desc0 = np.zeros((1, 32), np.uint8)
+    else:
+        mp_desc0 = mp_desc
+    sig = scale ** np.clip(level[src], 0, nlevels - 1)
+    kp["x"] = np.where(re, np.clip(u[src] + rng.normal(0, 1.2, n_kp) * sig, 0, width - 1), kp["x"]).astype(np.float32)
+    kp["y"] = np.where(re, np.clip(v[src] + rng.normal(0, 1.2, n_kp) * sig, 0, height - 1), kp["y"]).astype(np.float32)
+    kp["octave"] = np.where(re, np.clip(level[src] + rng.integers(-1, 2, n_kp), 0, nlevels - 1), kp["octave"])
+    kdesc = rng.integers(0, 256, (n_kp, 32)).astype(np.uint8)
+    kdesc[re] = flip_bits(mp_desc0[src[re]], rng.integers(0, 80, int(re.sum())), rng)
+    stereo = rng.random(n_kp) < stereo_fraction
+    ur = np.where(stereo, kp["x"] - bf / np.abs(z[src]) + rng.normal(0, 1.0, n_kp), -1).astype(np.float32)
+    ur = np.where(stereo & (ur < 0), 0.5, ur).astype(np.float32)
+    sf = np.array([scale ** i for i in range(nlevels)], np.float32)
+    return dict(valid=valid, wpos=wpos, normal=nrm, mp_desc=mp_desc, mf_max=mf_max, mf_min=mf_min, Rcw=R.reshape(9), tcw=t, Ow=Ow,
+                K=np.array(K, np.float32), bf=np.float32(bf), kp=kp, kdesc=kdesc, u_right=ur, scale_factors=sf,
+                inv_level_sigma2=(np.float32(1.0) / (sf * sf)).astype(np.float32), log_scale=np.float32(np.log(np.float32(scale))))
