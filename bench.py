@@ -517,6 +517,36 @@ def run_matching(local, steps):
         "workload": "512 (key frame, frame) pairs, 2000 x 2000 features in ~100 shared vocabulary nodes, ratio 0.7, checkOri",
         "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc,
         "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    # ---- scope row N3: SearchForTriangulation and the search of Fuse; N4: distinctive descriptors (host-buffer calls:
+    # these back-end routines are called with host data; the times include the uploads)
+    from weiner_slamit_v2_b200.matcher import ORBmatcher
+    from weiner_slamit_v2_b200.workloads import fuse_frame, observed_descriptors, triangulation_pair
+    mm = ORBmatcher(0.6, True, max_items=64, max_points=3000, device=local)
+    tw = [triangulation_pair(i, 2000, 2000, 100) for i in range(64)]
+    fw = [fuse_frame(i, 3000, 2000) for i in range(64)]
+    obs = observed_descriptors(0, [int(v) for v in np.random.default_rng(0).integers(2, 40, 100000)])
+
+    def host_timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3, r
+    ms, r = host_timed(lambda: mm.search_for_triangulation_batch(tw), 3)
+    out["search_for_triangulation"] = {"workload": "64 key-frame pairs, 2000 x 2000 features in ~100 shared nodes, host buffers (time includes the Python packing)",
+                                       "ms_per_call": ms, "pairs_per_s": 64 / ms * 1e3, "accepted_matches": int(r[0].sum())}
+    ms, r = host_timed(lambda: mm.fuse_search_batch(fw, (0.0, 0.0, 640.0, 480.0), 3.0), 3)
+    out["fuse_search"] = {"workload": "64 key frames x 3000 candidate map points vs 2000 keypoints, th=3, host buffers (time includes the Python packing)",
+                          "ms_per_call": ms, "map_points_per_s": 64 * 3000 / ms * 1e3, "fused": int(sum((b >= 0).sum() for b, _ in r))}
+    off = np.zeros(len(obs) + 1, np.int32); off[1:] = np.cumsum([len(o) for o in obs])
+    flat = np.ascontiguousarray(np.concatenate(obs)); bestd = np.zeros(len(obs), np.int32)
+    ms, r = host_timed(lambda: check(L.orbb200_distinctive_descriptors(mm._h, len(obs), off.ctypes.data, flat.ctypes.data, int(off[-1]),
+                                                                       bestd.ctypes.data, None, 0)), 3)
+    out["distinctive_descriptors"] = {"workload": "100000 map points with 2..39 observations each (%d descriptors), host buffers" % int(off[-1]),
+                                      "ms_per_call": ms, "map_points_per_s": 100000 / ms * 1e3}
+    mm.close()
     L.orbb200_matcher_destroy(h)
     return out
 
