@@ -320,12 +320,21 @@ typedef struct orbb200_fusepoints_view {
  * (256: none).  The replace-or-add surgery of :950-971 mutates the map and stays with the caller (the shim does it
  * in list order, re-checking isBad / IsInKeyFrame as the reference does).  kf: the key frame's mvKeysUn / octaves /
  * descriptors; u_right = mvuRight (NULL = monocular); bounds = the float image bounds of the Frame the key frame
- * was made from (the key frame's own int copies are derived from them); Rcw/tcw/Ow = the key frame's pose. */
+ * was made from (the key frame's own int copies are derived from them); Rcw/tcw/Ow = the key frame's pose.
+ * mode 0 = the overload above.
+ * mode 1 = the search of Fuse(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, float th,
+ *          vector<MapPoint*> &vpReplacePoint) (:979-1104): Rcw / tcw / Ow = the decomposed Scw (:987-991, evaluated
+ *          by the caller), no reprojection-error gates, valid[i] = !isBad && not in pKF->GetMapPoints().
+ * mode 2 = one leg of SearchBySim3 (:1106-1330): the camera point Rcw*X + tcw goes through a second similarity
+ *          R2 (items x 9 = sR21 or sR12), t2 (items x 3); dist3D is the norm of the result; no viewing-angle gate
+ *          (normal, Ow may be NULL); acceptance threshold TH_HIGH.  SearchBySim3 = leg 1 (key frame 1's map points in
+ *          key frame 2), leg 2 the other way round, then the agreement test of :1316-1328 (the shim, or
+ *          ORBmatcher.search_by_sim3_batch in Python). */
 int orbb200_fuse_search(orbb200_matcher *m, int items, const orbb200_frame_view *kf, const float *u_right,
                         const orbb200_fusepoints_view *pts, const float *Rcw, const float *tcw, const float *Ow,
                         const float K[4], float bf, const float *scale_factors, const float *inv_level_sigma2, int nlevels,
-                        float log_scale_factor, const float bounds[4], float th, int32_t *best_idx, int32_t *best_dist,
-                        int on_device);
+                        float log_scale_factor, const float bounds[4], float th, int mode, const float *R2, const float *t2,
+                        int32_t *best_idx, int32_t *best_dist, int on_device);
 
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */

@@ -120,15 +120,19 @@ MatExpr operator*(const MatExpr& e, const Mat& m) { MatExpr r(e); r.b = m; retur
 MatExpr operator*(const Mat& a, const Mat& b) { return MatExpr(&g_miniOp, 0, a, b); }
 MatExpr operator+(const MatExpr& e, const Mat& m) { MatExpr r(e); r.c = m; return r; }
 MatExpr operator-(const Mat& a, const Mat& b) { return MatExpr(&g_miniOp, 2, a, b); }
+// scalings: evaluated as a * (float)alpha, which is what convertTo does for CV_32F (cvtScale with float work type)
+MatExpr operator-(const Mat& a) { return MatExpr(&g_miniOp, 0, a, Mat(), Mat(), -1.0); }
+MatExpr operator/(const Mat& a, double s) { return MatExpr(&g_miniOp, 0, a, Mat(), Mat(), 1. / s); }
+MatExpr operator*(double s, const Mat& a) { return MatExpr(&g_miniOp, 0, a, Mat(), Mat(), s); }
+MatExpr operator*(double s, const MatExpr& e) { MatExpr r(e); r.alpha *= s; return r; }
 
 // Mat::dot for continuous CV_32F: products and sum in double, element order (core/src/matmul.cpp, dotProd_ for short vectors)
 double Mat::dot(InputArray other) const
 {
     const Mat& o = *static_cast<const Mat*>(other.getObj());
-    CV_Assert(type() == CV_32F && o.type() == CV_32F && total() == o.total() && isContinuous() && o.isContinuous());
+    CV_Assert(type() == CV_32F && o.type() == CV_32F && rows == o.rows && cols == o.cols);
     double r = 0;
-    const float *a = ptr<float>(), *b = o.ptr<float>();
-    for (size_t i = 0; i < total(); i++) r += (double)a[i] * (double)b[i];
+    for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) r += (double)at<float>(y, x) * (double)o.at<float>(y, x);
     return r;
 }
 

@@ -833,8 +833,13 @@ void orc_fuse_search(
     const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4], float bf,
     int n, const float *kx, const float *ky, const int32_t *koct, const float *kuright, const uint8_t *kdesc,
     int nlevels, const float *scale_factors, const float *inv_level_sigma2, float log_scale_factor,
-    const float bounds[4], float th, int32_t *best_idx, int32_t *best_dist)
+    const float bounds[4], float th, int mode, const float *R2, const float *t2, int32_t *best_idx, int32_t *best_dist)
 {
+    /* mode 0: Fuse(pKF, vpMapPoints, th); mode 1: Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (:979-1104: no
+     * reprojection-error gates); mode 2: one leg of SearchBySim3 (:1106-1330): the camera point goes through a second
+     * similarity (R2 = sR21 or sR12, t2), dist3D is the norm of the resulting camera point, there is no viewing-angle
+     * gate and the acceptance threshold is TH_HIGH. */
+    const int accept = mode == 2 ? TH_HIGH : TH_LOW;
     orc_grid g, q;
     int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
     int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
@@ -856,6 +861,17 @@ void orc_fuse_search(
             t = t + t1; t = t + t2;
             c3[r] = t + tcw[r];
         }
+        if (mode == 2) {                                    /* p3Dc2 = sR21*p3Dc1 + t21 (:1157) */
+            float d3[3];
+            for (int r = 0; r < 3; r++) {
+                volatile float t = R2[3 * r] * c3[0];
+                volatile float t1 = R2[3 * r + 1] * c3[1];
+                volatile float t2v = R2[3 * r + 2] * c3[2];
+                t = t + t1; t = t + t2v;
+                d3[r] = t + t2[r];
+            }
+            c3[0] = d3[0]; c3[1] = d3[1]; c3[2] = d3[2];
+        }
         if (c3[2] < 0.0f) continue;                         /* :853 */
         const float invz = 1 / c3[2];
         const float x = c3[0] * invz, y = c3[1] * invz;
@@ -865,13 +881,13 @@ void orc_fuse_search(
         volatile float ur = bf * invz; ur = u - ur;
         double ss = 0.0, dot = 0.0;
         for (int r = 0; r < 3; r++) {
-            const float po = X[r] - Ow[r];
+            const float po = mode == 2 ? c3[r] : X[r] - Ow[r];
             ss += (double)po * (double)po;
-            dot += (double)po * (double)normal[3 * (size_t)i + r];
+            if (mode != 2) dot += (double)po * (double)normal[3 * (size_t)i + r];
         }
         const float dist3D = (float)sqrt(ss);
         if (dist3D < 0.8f * mf_min_distance[i] || dist3D > 1.2f * mf_max_distance[i]) continue;
-        if (dot < 0.5 * (double)dist3D) continue;           /* viewing angle (:880) */
+        if (mode != 2 && dot < 0.5 * (double)dist3D) continue;           /* viewing angle (:880) */
         int level = orc_predict_scale(mf_max_distance[i], dist3D, log_scale_factor);
         if (level < 0) level = 0;
         if (level >= nlevels) level = nlevels - 1;
@@ -885,7 +901,9 @@ void orc_fuse_search(
             const float ex = u - kx[idx], ey = v - ky[idx];
             volatile float e2 = ex * ex, e2b = ey * ey;
             e2 = e2 + e2b;
-            if (kuright[idx] >= 0) {
+            if (mode != 0) {
+                /* no reprojection-error gate */
+            } else if (kuright[idx] >= 0) {
                 const float er = ur - kuright[idx];
                 volatile float e2c = er * er;
                 e2 = e2 + e2c;
@@ -899,7 +917,22 @@ void orc_fuse_search(
             if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
         }
         if (best_dist) best_dist[i] = bestDist;
-        if (bestDist <= TH_LOW) best_idx[i] = bestIdx;
+        if (bestDist <= accept) best_idx[i] = bestIdx;
     }
     free(cand); free(items);
+}
+
+
+/* ORBmatcher::SearchBySim3 (S/ORBmatcher.cc:1106-1330) from its two legs: vnMatch1 (map points of key frame 1 searched
+ * in key frame 2) and vnMatch2, then the agreement test (:1316-1328).  matches12[i1] out = slot of key frame 2 or -1
+ * (the newly found ones only; slots excluded by already1 keep -1).  Returns nFound. */
+int orc_sim3_agreement(int n1, const int32_t *match1, int n2, const int32_t *match2, int32_t *matches12)
+{
+    int found = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        matches12[i1] = -1;
+        const int idx2 = match1[i1];
+        if (idx2 >= 0 && idx2 < n2 && match2[idx2] == i1) { matches12[i1] = idx2; found++; }
+    }
+    return found;
 }

@@ -465,4 +465,130 @@ void refm_fuse_search(
     const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn)->~vector();
     std::free(kf);
 }
+
+namespace {
+// a key frame with everything the projection searches read: keypoints, descriptors, the Frame-assigned grid, the
+// int-truncated bounds, intrinsics, pyramid tables and pose
+struct FullKeyFrame {
+    KeyFrame* kf; MapPoint* mps; int n; float T[16], O3[3];
+    FullKeyFrame(int n_, const float* kx, const float* ky, const int32_t* koct, const float* kuright, const uint8_t* kdesc,
+                 const float* K, float bf, int nlevels, const float* sf, const float* ils, float logsf, const float* bounds,
+                 const float* Rcw, const float* tcw, const float* Ow) : n(n_)
+    {
+        Frame F;
+        fill_frame(F, n, kx, ky, koct, NULL, kdesc, bounds);
+        kf = (KeyFrame*)std::calloc(1, sizeof(KeyFrame));
+        *const_cast<int*>(&kf->N) = n;
+        *const_cast<int*>(&kf->mnGridCols) = FRAME_GRID_COLS; *const_cast<int*>(&kf->mnGridRows) = FRAME_GRID_ROWS;
+        *const_cast<float*>(&kf->mfGridElementWidthInv) = Frame::mfGridElementWidthInv;
+        *const_cast<float*>(&kf->mfGridElementHeightInv) = Frame::mfGridElementHeightInv;
+        *const_cast<int*>(&kf->mnMinX) = Frame::mnMinX; *const_cast<int*>(&kf->mnMinY) = Frame::mnMinY;
+        *const_cast<int*>(&kf->mnMaxX) = Frame::mnMaxX; *const_cast<int*>(&kf->mnMaxY) = Frame::mnMaxY;
+        *const_cast<float*>(&kf->fx) = K[0]; *const_cast<float*>(&kf->fy) = K[1]; *const_cast<float*>(&kf->cx) = K[2]; *const_cast<float*>(&kf->cy) = K[3];
+        *const_cast<float*>(&kf->mbf) = bf; *const_cast<float*>(&kf->mfLogScaleFactor) = logsf;
+        new (&kf->mGrid) std::vector<std::vector<std::vector<size_t> > >(FRAME_GRID_COLS);
+        for (int i = 0; i < FRAME_GRID_COLS; i++) { kf->mGrid[i].resize(FRAME_GRID_ROWS); for (int j = 0; j < FRAME_GRID_ROWS; j++) kf->mGrid[i][j] = F.mGrid[i][j]; }
+        new (const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn)) std::vector<cv::KeyPoint>(F.mvKeysUn);
+        new (const_cast<std::vector<float>*>(&kf->mvuRight)) std::vector<float>(kuright, kuright + n);
+        new (const_cast<cv::Mat*>(&kf->mDescriptors)) cv::Mat(n > 0 ? n : 1, 32, CV_8U, (void*)kdesc);
+        new (const_cast<std::vector<float>*>(&kf->mvScaleFactors)) std::vector<float>(sf, sf + nlevels);
+        new (const_cast<std::vector<float>*>(&kf->mvInvLevelSigma2)) std::vector<float>(ils, ils + nlevels);
+        new (&kf->mvpMapPoints) std::vector<MapPoint*>(n, static_cast<MapPoint*>(NULL));
+        const float t[16] = {Rcw[0], Rcw[1], Rcw[2], tcw[0], Rcw[3], Rcw[4], Rcw[5], tcw[1], Rcw[6], Rcw[7], Rcw[8], tcw[2], 0, 0, 0, 1};
+        std::memcpy(T, t, sizeof(T));
+        O3[0] = Ow[0]; O3[1] = Ow[1]; O3[2] = Ow[2];
+        new (&kf->Tcw) cv::Mat(4, 4, CV_32F, T);
+        new (&kf->Ow) cv::Mat(3, 1, CV_32F, O3);
+        mps = NULL;
+    }
+    ~FullKeyFrame()
+    {
+        kf->Ow.~Mat(); kf->Tcw.~Mat(); kf->mvpMapPoints.~vector(); kf->mGrid.~vector();
+        const_cast<std::vector<float>*>(&kf->mvInvLevelSigma2)->~vector(); const_cast<std::vector<float>*>(&kf->mvScaleFactors)->~vector();
+        const_cast<cv::Mat*>(&kf->mDescriptors)->~Mat(); const_cast<std::vector<float>*>(&kf->mvuRight)->~vector();
+        const_cast<std::vector<cv::KeyPoint>*>(&kf->mvKeysUn)->~vector();
+        std::free(kf);
+    }
+};
+
+struct FakePoints {
+    MapPoint* mps; int n;
+    FakePoints(int n_, const uint8_t* valid, const float* wpos, const float* normal, const uint8_t* desc, const float* mx, const float* mn) : n(n_)
+    {
+        mps = (MapPoint*)std::calloc(n > 0 ? n : 1, sizeof(MapPoint));
+        for (int i = 0; i < n; i++) {
+            MapPoint* p = &mps[i];
+            new (&p->mDescriptor) cv::Mat(1, 32, CV_8U, (void*)(desc + 32 * (size_t)i));
+            new (&p->mWorldPos) cv::Mat(3, 1, CV_32F, (void*)(wpos + 3 * (size_t)i));
+            new (&p->mNormalVector) cv::Mat(3, 1, CV_32F, (void*)(normal + 3 * (size_t)i));
+            new (&p->mObservations) std::map<KeyFrame*, size_t>();
+            p->mfMaxDistance = mx[i]; p->mfMinDistance = mn[i];
+            p->mbBad = valid[i] == 3;
+            p->mnId = i + 1;
+        }
+    }
+    ~FakePoints()
+    {
+        for (int i = 0; i < n; i++) { MapPoint* p = &mps[i]; p->mObservations.~map(); p->mNormalVector.~Mat(); p->mWorldPos.~Mat(); p->mDescriptor.~Mat(); }
+        std::free(mps);
+    }
+};
+}  // namespace
+
+// ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint)
+// (S/ORBmatcher.cc:979-1104), one candidate per call on an empty key frame (see refm_fuse_search).  Scw = [Rcw | tcw]
+// with unit scale, so the decomposition of :987-991 returns the inputs.  valid: 1 usable, 3 bad, anything else is not
+// passed (this overload takes no NULL candidates and an empty key frame has nothing "already found"); Ow_out = the camera centre as the reference's expression evaluates it here.
+void refm_fuse_search_sim3(
+    int nmp, const uint8_t* valid, const float* wpos, const float* normal, const uint8_t* mp_desc,
+    const float* mf_max_distance, const float* mf_min_distance,
+    const float* Rcw, const float* tcw, const float* Ow, const float* K, float bf,
+    int n, const float* kx, const float* ky, const int32_t* koct, const float* kuright, const uint8_t* kdesc,
+    int nlevels, const float* scale_factors, const float* inv_level_sigma2, float log_scale_factor,
+    const float* bounds, float th, int32_t* best_idx)
+{
+    FullKeyFrame k(n, kx, ky, koct, kuright, kdesc, K, bf, nlevels, scale_factors, inv_level_sigma2, log_scale_factor, bounds, Rcw, tcw, Ow);
+    FakePoints pts(nmp, valid, wpos, normal, mp_desc, mf_max_distance, mf_min_distance);
+    cv::Mat Scw(4, 4, CV_32F, k.T);
+    ORBmatcher matcher(0.6f, true);
+    for (int i = 0; i < nmp; i++) {
+        best_idx[i] = -1;
+        if (valid[i] != 1 && valid[i] != 3) continue;
+        std::vector<MapPoint*> one(1, &pts.mps[i]), rep(1, static_cast<MapPoint*>(NULL));
+        const int fused = matcher.Fuse(k.kf, Scw, one, th, rep);
+        if (fused) {
+            best_idx[i] = (int32_t)pts.mps[i].mObservations[k.kf];
+            k.kf->mvpMapPoints[best_idx[i]] = NULL;
+        }
+    }
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (S/ORBmatcher.cc:1106-1330) with s12 = 1 and no
+// previous matches.  Key frame k holds map point i at slot i (valid: 0 = empty slot, 1 good, 3 bad).
+// matches12[n1] out = slot of key frame 2 or -1.  Returns nFound.
+int refm_search_by_sim3(
+    int n1, const uint8_t* valid1, const float* wpos1, const uint8_t* mpdesc1, const float* mx1, const float* mn1,
+    const float* kx1, const float* ky1, const int32_t* koct1, const uint8_t* kdesc1, const float* Rcw1, const float* tcw1,
+    int n2, const uint8_t* valid2, const float* wpos2, const uint8_t* mpdesc2, const float* mx2, const float* mn2,
+    const float* kx2, const float* ky2, const int32_t* koct2, const uint8_t* kdesc2, const float* Rcw2, const float* tcw2,
+    const float* K, int nlevels, const float* scale_factors, const float* inv_level_sigma2, float log_scale_factor,
+    const float* bounds, const float* R12, const float* t12, float th, int32_t* matches12)
+{
+    std::vector<float> ur1(n1 > 0 ? n1 : 1, -1.f), ur2(n2 > 0 ? n2 : 1, -1.f), zero(3, 0.f);
+    std::vector<float> nrm1((size_t)(n1 > 0 ? n1 : 1) * 3, 0.f), nrm2((size_t)(n2 > 0 ? n2 : 1) * 3, 0.f);
+    FullKeyFrame k2(n2, kx2, ky2, koct2, &ur2[0], kdesc2, K, 0.f, nlevels, scale_factors, inv_level_sigma2, log_scale_factor, bounds, Rcw2, tcw2, &zero[0]);
+    FullKeyFrame k1(n1, kx1, ky1, koct1, &ur1[0], kdesc1, K, 0.f, nlevels, scale_factors, inv_level_sigma2, log_scale_factor, bounds, Rcw1, tcw1, &zero[0]);
+    FakePoints p1(n1, valid1, wpos1, &nrm1[0], mpdesc1, mx1, mn1), p2(n2, valid2, wpos2, &nrm2[0], mpdesc2, mx2, mn2);
+    for (int i = 0; i < n1; i++) k1.kf->mvpMapPoints[i] = valid1[i] ? &p1.mps[i] : NULL;
+    for (int i = 0; i < n2; i++) k2.kf->mvpMapPoints[i] = valid2[i] ? &p2.mps[i] : NULL;
+    float Rm[9], tm[3];
+    std::memcpy(Rm, R12, sizeof(Rm)); std::memcpy(tm, t12, sizeof(tm));
+    cv::Mat R(3, 3, CV_32F, Rm), t(3, 1, CV_32F, tm);
+    std::vector<MapPoint*> m12(n1, static_cast<MapPoint*>(NULL));
+    ORBmatcher matcher(0.75f, true);
+    const float s12 = 1.0f;
+    const int found = matcher.SearchBySim3(k1.kf, k2.kf, m12, s12, R, t, th);
+    for (int i = 0; i < n1; i++) matches12[i] = m12[i] ? (int32_t)(m12[i] - p2.mps) : -1;
+    return found;
+}
 }

@@ -451,7 +451,7 @@ def distinctive_descriptor(desc):
     return idx, med.value
 
 
-def _fuse_call(f, w, bounds, th, valid, with_dist):
+def _fuse_call(f, w, bounds, th, valid, with_dist, mode=0, R2=None, t2=None):
     kp = w["kp"]
     n, nmp = len(kp), len(w["valid"])
     a = dict(v=valid(_b(w["valid"])), wp=_f(w["wpos"]), nr=_f(w["normal"]), md=_b(w["mp_desc"]), mx=_f(w["mf_max"]), mn=_f(w["mf_min"]),
@@ -461,16 +461,36 @@ def _fuse_call(f, w, bounds, th, valid, with_dist):
     args = [nmp, _ptr(a["v"], _u8p), _ptr(a["wp"], _f32p), _ptr(a["nr"], _f32p), _ptr(a["md"], _u8p), _ptr(a["mx"], _f32p), _ptr(a["mn"], _f32p),
             _ptr(a["R"], _f32p), _ptr(a["t"], _f32p), _ptr(a["Ow"], _f32p), _ptr(a["K"], _f32p), float(w["bf"]),
             n, _ptr(a["kx"], _f32p), _ptr(a["ky"], _f32p), _ptr(a["ko"], _i32p), _ptr(a["ur"], _f32p), _ptr(a["kd"], _u8p),
-            len(a["sf"]), _ptr(a["sf"], _f32p), _ptr(a["il"], _f32p), float(w["log_scale"]), _ptr(a["b"], _f32p), float(th), _ptr(best, _i32p)]
+            len(a["sf"]), _ptr(a["sf"], _f32p), _ptr(a["il"], _f32p), float(w["log_scale"]), _ptr(a["b"], _f32p), float(th)]
     f.argtypes = [C.c_int, _u8p, _f32p, _f32p, _u8p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
-                  C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, C.c_int, _f32p, _f32p, C.c_float, _f32p, C.c_float, _i32p] + ([_i32p] if with_dist else [])
+                  C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, C.c_int, _f32p, _f32p, C.c_float, _f32p, C.c_float]
     f.restype = None
-    if with_dist:
-        args.append(_ptr(dist, _i32p))
+    if with_dist:                     # the oracle's signature: mode, second transform, both outputs
+        r2, tt2 = _f(np.zeros(9) if R2 is None else R2), _f(np.zeros(3) if t2 is None else t2)
+        f.argtypes = f.argtypes + [C.c_int, _f32p, _f32p, _i32p, _i32p]
+        args += [int(mode), _ptr(r2, _f32p), _ptr(tt2, _f32p), _ptr(best, _i32p), _ptr(dist, _i32p)]
+    else:                             # the reference harness: Fuse(pKF, vpMapPoints, th) only
+        f.argtypes = f.argtypes + [_i32p]
+        args.append(_ptr(best, _i32p))
     f(*args)
     return best[:nmp], dist[:nmp]
 
 
-def fuse_search(w, bounds, th=3.0):
-    """w: workloads.fuse_frame() dict.  Returns (best keypoint index per map point or -1, best distance)."""
-    return _fuse_call(lib().orc_fuse_search, w, bounds, th, lambda v: _b((v == 1).astype(np.uint8)), True)
+def fuse_search(w, bounds, th=3.0, mode=0, R2=None, t2=None):
+    """w: workloads.fuse_frame() dict.  mode 0 = Fuse(pKF, vpMapPoints, th), 1 = Fuse(pKF, Scw, ...), 2 = a SearchBySim3 leg
+    (second transform R2, t2).  Returns (best keypoint index per map point or -1, best distance)."""
+    return _fuse_call(lib().orc_fuse_search, w, bounds, th, lambda v: _b((v == 1).astype(np.uint8)), True, mode, R2, t2)
+
+
+def search_by_sim3(w, bounds, th=7.5):
+    """w: workloads.sim3_pair() dict.  SearchBySim3 from its two legs + the agreement test.
+    Returns (nFound, matches12[n1] = slot of key frame 2 or -1)."""
+    L = lib()
+    m1, _ = fuse_search(w["leg1"], bounds, th, 2, w["sR21"], w["t21"])
+    m2, _ = fuse_search(w["leg2"], bounds, th, 2, w["R12"], w["t12"])
+    L.orc_sim3_agreement.argtypes = [C.c_int, _i32p, C.c_int, _i32p, _i32p]
+    L.orc_sim3_agreement.restype = C.c_int
+    a, b = _i(m1) if len(m1) else np.zeros(1, np.int32), _i(m2) if len(m2) else np.zeros(1, np.int32)
+    out = np.full(max(len(m1), 1), -1, np.int32)
+    found = L.orc_sim3_agreement(len(m1), _ptr(a, _i32p), len(m2), _ptr(b, _i32p), _ptr(out, _i32p))
+    return found, out[:len(m1)]

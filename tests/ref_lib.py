@@ -258,3 +258,34 @@ def ref_fuse_search(w, bounds, th=3.0):
     """The reference's own ORBmatcher::Fuse(pKF, {pMP}, th), one candidate map point per call (see the harness)."""
     import oracle_lib as O
     return O._fuse_call(mlib().refm_fuse_search, w, bounds, th, lambda v: v, False)[0]
+
+
+def ref_fuse_search_sim3(w, bounds, th=3.0):
+    """The reference's own Fuse(pKF, Scw, vpPoints, th, vpReplacePoint), one candidate per call, Scw = [Rcw | tcw]."""
+    import oracle_lib as O
+    return O._fuse_call(mlib().refm_fuse_search_sim3, w, bounds, th, lambda v: v, False)[0]
+
+
+def ref_search_by_sim3(w, bounds, th=7.5):
+    """The reference's own SearchBySim3 (s12 = 1, no previous matches)."""
+    import oracle_lib as O
+    P = O._ptr
+    f = mlib().refm_search_by_sim3
+    side = [C.c_int, _u8p, _f32p, _u8p, _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, _f32p, _f32p]
+    f.argtypes = side + side + [_f32p, C.c_int, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, C.c_float, _i32p]
+    f.restype = C.c_int
+    keep = []
+
+    def args(k):
+        a = [O._b(k["valid"]), O._f(k["wpos"]), O._b(k["mp_desc"]), O._f(k["mf_max"]), O._f(k["mf_min"]), O._f(k["kp"]["x"]), O._f(k["kp"]["y"]),
+             O._i(k["kp"]["octave"]), O._b(k["kdesc"]), O._f(k["Rcw"]), O._f(k["tcw"])]
+        keep.extend(a)
+        return [len(a[0])] + [P(x, t) for x, t in zip(a, side[1:])]
+    c = w["common"]
+    sf, il, b = O._f(c["scale_factors"]), O._f(c["inv_level_sigma2"]), O._bounds(bounds)
+    K, R12, t12 = O._f(c["K"]), O._f(w["R12"]), O._f(w["t12"])
+    n1 = len(w["k1"]["valid"])
+    m = np.full(max(n1, 1), -1, np.int32)
+    found = f(*(args(w["k1"]) + args(w["k2"]) + [P(K, _f32p), len(sf), P(sf, _f32p), P(il, _f32p), float(c["log_scale"]), P(b, _f32p),
+                                                   P(R12, _f32p), P(t12, _f32p), float(th), P(m, _i32p)]))
+    return found, m[:n1]

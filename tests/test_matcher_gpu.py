@@ -296,3 +296,34 @@ def test_fuse_search_matches_oracle(th):
             c = g["cfg_%d" % i]
             r = m.fuse_search_batch([fuse_frame(int(c[0]), int(c[1]), int(c[2]))], bounds, float(c[3]))
             assert np.array_equal(r[0][0], g["best_%d" % i])
+
+
+def test_fuse_sim3_search_and_search_by_sim3_match_oracle():
+    """Scope row N3: the search of Fuse(pKF, Scw, ...) (mode 1) and SearchBySim3 (two mode-2 legs + agreement), ragged
+    batches, plus the reference's golden vectors."""
+    import os
+    from weiner_slamit_v2_b200.workloads import fuse_frame, sim3_pair
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    ws = [fuse_frame(60 + i, a, b) for i, (a, b) in enumerate([(3000, 2000), (2000, 1500), (500, 300), (0, 100), (100, 0)])]
+    m = ORBmatcher(0.6, True, max_items=len(ws), max_points=3000)
+    res = m.fuse_search_batch(ws, bounds, 4.0, mode=1)
+    for i, w in enumerate(ws):
+        bo, do = O.fuse_search(w, bounds, 4.0, 1)
+        assert np.array_equal(res[i][0], bo) and np.array_equal(res[i][1], do), i
+    ss = [sim3_pair(60 + i, a, b) for i, (a, b) in enumerate([(1500, 1500), (1500, 1200), (300, 400), (0, 100), (100, 0)])]
+    found, matches = m.search_by_sim3_batch(ss, bounds, 7.5)
+    tot = 0
+    for i, w in enumerate(ss):
+        fo, mo = O.search_by_sim3(w, bounds, 7.5)
+        assert found[i] == fo and np.array_equal(matches[i], mo), i
+        tot += fo
+    assert tot > 150
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_sim3.npz"))
+    for i in range(int(g["fcount"])):
+        c = g["fcfg_%d" % i]
+        r = m.fuse_search_batch([fuse_frame(int(c[0]), int(c[1]), int(c[2]))], bounds, float(c[3]), mode=1)
+        assert np.array_equal(r[0][0], g["fbest_%d" % i])
+    for i in range(int(g["scount"])):
+        c = g["scfg_%d" % i]
+        f, mm = m.search_by_sim3_batch([sim3_pair(int(c[0]), int(c[1]), int(c[2]))], bounds, float(c[3]))
+        assert f[0] == int(g["sn_%d" % i]) and np.array_equal(mm[0], g["sm_%d" % i])

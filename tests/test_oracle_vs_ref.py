@@ -164,7 +164,18 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
     from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
     g = np.load(path)
-    if "fuse" in os.path.basename(path):
+    if "sim3" in os.path.basename(path):
+        from weiner_slamit_v2_b200.workloads import fuse_frame, sim3_pair
+        bounds = (-13.7, -9.2, 661.3, 492.8)
+        for i in range(int(g["fcount"])):
+            c = g["fcfg_%d" % i]
+            a = O.fuse_search(fuse_frame(int(c[0]), int(c[1]), int(c[2])), bounds, float(c[3]), 1)
+            assert np.array_equal(a[0], g["fbest_%d" % i])
+        for i in range(int(g["scount"])):
+            c = g["scfg_%d" % i]
+            a = O.search_by_sim3(sim3_pair(int(c[0]), int(c[1]), int(c[2])), bounds, float(c[3]))
+            assert a[0] == int(g["sn_%d" % i]) and np.array_equal(a[1], g["sm_%d" % i])
+    elif "fuse" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import fuse_frame
         for i in range(int(g["count"])):
             c = g["cfg_%d" % i]
@@ -331,3 +342,31 @@ def test_fuse_search_matches_reference(th):
         assert np.array_equal(a[0], b), idx
         tot += int((b >= 0).sum())
     assert tot > 400
+
+
+@needs_refm
+def test_fuse_sim3_search_and_search_by_sim3_match_reference():
+    """Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (S/ORBmatcher.cc:979-1104; one candidate per call, see the harness)
+    and SearchBySim3 (:1106-1330; both legs and the agreement test in one call of the reference) against the oracle's
+    mode 1 / mode 2 searches."""
+    from weiner_slamit_v2_b200.workloads import fuse_frame, sim3_pair
+    tot = 0
+    for idx, (nmp, nkp, bounds) in enumerate([(3000, 2000, (0.0, 0.0, 640.0, 480.0)), (3000, 2000, (-13.7, -9.2, 661.3, 492.8)),
+                                              (500, 300, (-13.7, -9.2, 661.3, 492.8)), (0, 100, (0.0, 0.0, 640.0, 480.0))]):
+        for th in (3.0, 4.0):
+            w = fuse_frame(1000 + idx, nmp, nkp)
+            a = O.fuse_search(w, bounds, th, 1)
+            b = R.ref_fuse_search_sim3(w, bounds, th)
+            assert np.array_equal(a[0], b), idx
+            tot += int((b >= 0).sum())
+    assert tot > 800
+    tot = 0
+    for idx, (n1, n2, bounds) in enumerate([(1500, 1500, (0.0, 0.0, 640.0, 480.0)), (1500, 1200, (-13.7, -9.2, 661.3, 492.8)),
+                                            (300, 400, (0.0, 0.0, 640.0, 480.0)), (0, 100, (0.0, 0.0, 640.0, 480.0)), (100, 0, (0.0, 0.0, 640.0, 480.0))]):
+        for th in (7.5, 10.0):
+            w = sim3_pair(1010 + idx, n1, n2)
+            a = O.search_by_sim3(w, bounds, th)
+            b = R.ref_search_by_sim3(w, bounds, th)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx
+            tot += b[0]
+    assert tot > 300

@@ -130,3 +130,17 @@ for i, (idx, nmp, nkp, th) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_fuse.npz"), **out)
 print("ref_match_fuse.npz", [int((out["best_%d" % i] >= 0).sum()) for i in range(len(cfgs))])
+
+out = {}
+from weiner_slamit_v2_b200.workloads import sim3_pair  # noqa: E402
+cfgs = [(883, 3000, 2000, 3.0), (884, 1500, 1500, 4.0)]
+for i, (idx, nmp, nkp, th) in enumerate(cfgs):
+    out["fcfg_%d" % i] = np.array([idx, nmp, nkp, th]); out["fbest_%d" % i] = R.ref_fuse_search_sim3(fuse_frame(idx, nmp, nkp), (-13.7, -9.2, 661.3, 492.8), th)
+out["fcount"] = len(cfgs)
+cfgs = [(890, 1500, 1500, 7.5), (891, 2000, 1700, 10.0)]
+for i, (idx, na, nb, th) in enumerate(cfgs):
+    r = R.ref_search_by_sim3(sim3_pair(idx, na, nb), (-13.7, -9.2, 661.3, 492.8), th)
+    out["scfg_%d" % i] = np.array([idx, na, nb, th]); out["sn_%d" % i] = r[0]; out["sm_%d" % i] = r[1]
+out["scount"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_sim3.npz"), **out)
+print("ref_match_sim3.npz", [int((out["fbest_%d" % i] >= 0).sum()) for i in range(2)], [int(out["sn_%d" % i]) for i in range(2)])

@@ -1249,6 +1249,10 @@ struct FuseParams {
     const float *scaleFactors, *invLevelSigma2;
     int nlevels;
     int *bestIdx, *bestDist;
+    // mode 0: Fuse(pKF, vpMapPoints, th); 1: Fuse(pKF, Scw, ...) (:979-1104, no reprojection-error gates);
+    // 2: a SearchBySim3 leg (:1106-1330): second similarity (R2, t2), dist3D = |camera point|, no angle gate, TH_HIGH
+    int mode;
+    const float *R2, *t2;        // items x 9, items x 3 (mode 2)
 };
 
 __global__ void __launch_bounds__(128) k_fuse_search(const FuseParams P)
@@ -1268,6 +1272,15 @@ __global__ void __launch_bounds__(128) k_fuse_search(const FuseParams P)
 #pragma unroll
         for (int r = 0; r < 3; r++)
             c3[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3 * r], X[0]), __fmul_rn(R[3 * r + 1], X[1])), __fmul_rn(R[3 * r + 2], X[2])), t[r]);
+        if (P.mode == 2) {                                                          // p3Dc2 = sR21*p3Dc1 + t21 (:1157)
+            const float* S = P.R2 + (size_t)item * 9;
+            const float* s2 = P.t2 + (size_t)item * 3;
+            float d3[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                d3[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(S[3 * r], c3[0]), __fmul_rn(S[3 * r + 1], c3[1])), __fmul_rn(S[3 * r + 2], c3[2])), s2[r]);
+            c3[0] = d3[0]; c3[1] = d3[1]; c3[2] = d3[2];
+        }
         if (c3[2] < 0.0f) break;                                                    // :853
         const float invz = __fdiv_rn(1.0f, c3[2]);
         const float u = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(c3[0], invz)), P.cx);
@@ -1277,14 +1290,14 @@ __global__ void __launch_bounds__(128) k_fuse_search(const FuseParams P)
         double ss = 0.0, dot = 0.0;                                                 // cv::norm, Mat::dot: double accumulation
 #pragma unroll
         for (int r = 0; r < 3; r++) {
-            const double po = (double)__fsub_rn(X[r], O[r]);
+            const double po = (double)(P.mode == 2 ? c3[r] : __fsub_rn(X[r], O[r]));
             ss = __dadd_rn(ss, __dmul_rn(po, po));
-            dot = __dadd_rn(dot, __dmul_rn(po, (double)P.normal[lo * 3 + r]));
+            if (P.mode != 2) dot = __dadd_rn(dot, __dmul_rn(po, (double)P.normal[lo * 3 + r]));
         }
         const float dist3D = __double2float_rn(__dsqrt_rn(ss));
         const float mx = P.mfMax[lo];
         if (dist3D < __fmul_rn(0.8f, P.mfMin[lo]) || dist3D > __fmul_rn(1.2f, mx)) break;
-        if (dot < __dmul_rn(0.5, (double)dist3D)) break;                             // viewing angle (:880)
+        if (P.mode != 2 && dot < __dmul_rn(0.5, (double)dist3D)) break;              // viewing angle (:880)
         int level = (int)ceilf(__fdiv_rn(libm_logf(__fdiv_rn(mx, dist3D)), P.logScale));
         level = max(0, min(level, P.nlevels - 1));
         const float radius = __fmul_rn(P.th, P.scaleFactors[level]);
@@ -1309,7 +1322,9 @@ __global__ void __launch_bounds__(128) k_fuse_search(const FuseParams P)
                 const float ex = __fsub_rn(u, kx[idx]), ey = __fsub_rn(v, ky[idx]);
                 float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
                 const float kr = kur ? kur[idx] : -1.f;
-                if (kr >= 0) {
+                if (P.mode != 0) {
+                    // no reprojection-error gate in these overloads
+                } else if (kr >= 0) {
                     const float er = __fsub_rn(ur, kr);
                     e2 = __fadd_rn(e2, __fmul_rn(er, er));
                     if ((double)__fmul_rn(e2, P.invLevelSigma2[kl]) > 7.8) continue;
@@ -1319,7 +1334,7 @@ __global__ void __launch_bounds__(128) k_fuse_search(const FuseParams P)
             }
         }
     } while (false);
-    P.bestIdx[lo] = bestDist <= TH_LOW ? bestIdx : -1;
+    P.bestIdx[lo] = bestDist <= (P.mode == 2 ? TH_HIGH : TH_LOW) ? bestIdx : -1;
     if (P.bestDist) P.bestDist[lo] = bestDist;
 }
 
@@ -1911,11 +1926,12 @@ extern "C" int orbb200_distinctive_descriptors(orbb200_matcher* m, int items, co
 extern "C" int orbb200_fuse_search(orbb200_matcher* m, int items, const orbb200_frame_view* kf, const float* u_right,
                                    const orbb200_fusepoints_view* pts, const float* Rcw, const float* tcw, const float* Ow,
                                    const float* K, float bf, const float* scale_factors, const float* inv_level_sigma2, int nlevels,
-                                   float log_scale_factor, const float* bounds, float th, int32_t* best_idx, int32_t* best_dist,
-                                   int on_device)
+                                   float log_scale_factor, const float* bounds, float th, int mode, const float* R2, const float* t2,
+                                   int32_t* best_idx, int32_t* best_dist, int on_device)
 {
-    if (!m || !kf || !pts || !Rcw || !tcw || !Ow || !K || !scale_factors || !inv_level_sigma2 || !best_idx) { set_error("null argument"); return ORBB200_EINVAL; }
-    if (!kf->n || !kf->x || !kf->y || !kf->octave || !kf->desc || !pts->n || !pts->valid || !pts->world_pos || !pts->normal || !pts->mp_desc ||
+    if (!m || !kf || !pts || !Rcw || !tcw || !K || !scale_factors || !inv_level_sigma2 || !best_idx) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (mode < 0 || mode > 2 || (mode == 2 ? (!R2 || !t2) : !Ow)) { set_error("mode %d needs %s", mode, mode == 2 ? "R2 and t2" : "Ow"); return ORBB200_EINVAL; }
+    if (!kf->n || !kf->x || !kf->y || !kf->octave || !kf->desc || !pts->n || !pts->valid || !pts->world_pos || (mode != 2 && !pts->normal) || !pts->mp_desc ||
         !pts->max_distance || !pts->min_distance) { set_error("incomplete view"); return ORBB200_EINVAL; }
     int rc;
     if ((rc = check_view(m, items, kf->stride, "key frame")) || (rc = check_view(m, items, pts->stride, "map points"))) return rc;
@@ -1931,16 +1947,18 @@ extern "C" int orbb200_fuse_search(orbb200_matcher* m, int items, const orbb200_
         P.nmp = pts->n; P.valid = pts->valid; P.wpos = pts->world_pos; P.normal = pts->normal; P.mpDesc = pts->mp_desc;
         P.mfMax = pts->max_distance; P.mfMin = pts->min_distance;
         P.Rcw = Rcw; P.tcw = tcw; P.Ow = Ow; P.scaleFactors = scale_factors; P.invLevelSigma2 = inv_level_sigma2;
+        P.R2 = R2; P.t2 = t2;
         P.bestIdx = best_idx; P.bestDist = best_dist;
     } else {
         const size_t bytes = frame_bytes(kf, items) + pad(np * 4) + pad((size_t)items * 4) + pad(nl) + 2 * pad(nl * 12) + pad(nl * 32) + 2 * pad(nl * 4) +
-                             pad((size_t)items * 36) + 2 * pad((size_t)items * 12) + 2 * pad((size_t)nlevels * 4) + 2 * pad(nl * 4);
+                             2 * pad((size_t)items * 36) + 3 * pad((size_t)items * 12) + 2 * pad((size_t)nlevels * 4) + 2 * pad(nl * 4);
         if ((rc = s.reserve(bytes))) return rc;
         if ((rc = upload_frame(s, kf, items, &P.f, false))) return rc;
+        if ((rc = s.up(mode == 2 ? R2 : nullptr, (size_t)items * 9, &P.R2)) || (rc = s.up(mode == 2 ? t2 : nullptr, (size_t)items * 3, &P.t2))) return rc;
         if ((rc = s.up(u_right, u_right ? np : 0, &P.uRight)) || (rc = s.up(pts->n, items, &P.nmp)) || (rc = s.up(pts->valid, nl, &P.valid)) ||
-            (rc = s.up(pts->world_pos, nl * 3, &P.wpos)) || (rc = s.up(pts->normal, nl * 3, &P.normal)) || (rc = s.up(pts->mp_desc, nl * 32, &P.mpDesc)) ||
+            (rc = s.up(pts->world_pos, nl * 3, &P.wpos)) || (rc = s.up(mode != 2 ? pts->normal : nullptr, nl * 3, &P.normal)) || (rc = s.up(pts->mp_desc, nl * 32, &P.mpDesc)) ||
             (rc = s.up(pts->max_distance, nl, &P.mfMax)) || (rc = s.up(pts->min_distance, nl, &P.mfMin)) ||
-            (rc = s.up(Rcw, (size_t)items * 9, &P.Rcw)) || (rc = s.up(tcw, (size_t)items * 3, &P.tcw)) || (rc = s.up(Ow, (size_t)items * 3, &P.Ow)) ||
+            (rc = s.up(Rcw, (size_t)items * 9, &P.Rcw)) || (rc = s.up(tcw, (size_t)items * 3, &P.tcw)) || (rc = s.up(mode != 2 ? Ow : nullptr, (size_t)items * 3, &P.Ow)) ||
             (rc = s.up(scale_factors, (size_t)nlevels, &P.scaleFactors)) || (rc = s.up(inv_level_sigma2, (size_t)nlevels, &P.invLevelSigma2))) return rc;
         P.bestIdx = s.out<int>(nl);
         P.bestDist = s.out<int>(nl);
@@ -1950,6 +1968,7 @@ extern "C" int orbb200_fuse_search(orbb200_matcher* m, int items, const orbb200_
     P.maxXi = (int)bounds[2]; P.maxYi = (int)bounds[3];
     P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.bf = bf; P.th = th; P.logScale = log_scale_factor; P.nlevels = nlevels;
+    P.mode = mode;
     k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");
     k_fuse_search<<<dim3((pts->stride + 127) / 128, items), 128, 0, st>>>(P);

@@ -238,8 +238,9 @@ class ORBmatcher:
         return nm, [m[i, :(ka if keyframes else fa)["n"][i]] for i in range(items)]
 
     # ---- the search of Fuse(pKF, vpMapPoints, th) (S/ORBmatcher.cc:829-948), scope row N3 ----
-    def fuse_search_batch(self, ws, bounds, th=3.0):
-        """ws: list of workloads.fuse_frame()-layout dicts (valid == 1 marks usable candidates; kp / kdesc / u_right = the
+    def fuse_search_batch(self, ws, bounds, th=3.0, mode=0, R2=None, t2=None):
+        """mode 0 = Fuse(pKF, vpMapPoints, th), 1 = Fuse(pKF, Scw, ...), 2 = a SearchBySim3 leg (R2, t2: per-item second
+        similarity).  ws: list of workloads.fuse_frame()-layout dicts (valid == 1 marks usable candidates; kp / kdesc / u_right = the
         key frame; Rcw, tcw, Ow, K, bf, scale_factors, inv_level_sigma2, log_scale).  Returns per item
         (best keypoint index per candidate or -1, smallest distance seen)."""
         from ._lib import FrameView, FusePointsView
@@ -267,10 +268,29 @@ class ORBmatcher:
         il = np.ascontiguousarray(ws[0]["inv_level_sigma2"], np.float32)
         bnd = np.ascontiguousarray(bounds, np.float32)
         best = np.full((items, ms), -1, np.int32); dist = np.full((items, ms), 256, np.int32)
+        r2 = np.ascontiguousarray(np.stack([np.asarray(r, np.float32).reshape(9) for r in R2])) if R2 is not None else None
+        tt2 = np.ascontiguousarray(np.stack([np.asarray(v, np.float32).reshape(3) for v in t2])) if t2 is not None else None
         check(self._L.orbb200_fuse_search(self._h, items, C.byref(fv), k["ur"].ctypes.data, C.byref(pv), R.ctypes.data, t.ctypes.data,
                                           Ow.ctypes.data, K.ctypes.data, float(ws[0]["bf"]), sf.ctypes.data, il.ctypes.data, len(sf),
-                                          float(ws[0]["log_scale"]), bnd.ctypes.data, float(th), best.ctypes.data, dist.ctypes.data, 0))
+                                          float(ws[0]["log_scale"]), bnd.ctypes.data, float(th), int(mode),
+                                          r2.ctypes.data if r2 is not None else None, tt2.ctypes.data if tt2 is not None else None,
+                                          best.ctypes.data, dist.ctypes.data, 0))
         return [(best[i, :nm[i]], dist[i, :nm[i]]) for i in range(items)]
+
+    # ---- SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (S/ORBmatcher.cc:1106-1330), scope row N3 ----
+    def search_by_sim3_batch(self, ws, bounds, th=7.5):
+        """ws: list of workloads.sim3_pair()-layout dicts (leg1 / leg2 in fuse_frame layout, sR21, t21, R12 (= sR12), t12).
+        Two device searches and the agreement test of :1316-1328.  Returns (nFound (items,), [matches12 per item])."""
+        leg1 = self.fuse_search_batch([w["leg1"] for w in ws], bounds, th, 2, [w["sR21"] for w in ws], [w["t21"] for w in ws])
+        leg2 = self.fuse_search_batch([w["leg2"] for w in ws], bounds, th, 2, [w["R12"] for w in ws], [w["t12"] for w in ws])
+        found, out = np.zeros(len(ws), np.int32), []
+        for i in range(len(ws)):
+            m1, m2 = leg1[i][0], leg2[i][0]
+            ok = (m1 >= 0)
+            ok[ok] = m2[m1[ok]] == np.nonzero(ok)[0]
+            out.append(np.where(ok, m1, -1).astype(np.int32))
+            found[i] = int(ok.sum())
+        return found, out
 
     # ---- MapPoint::ComputeDistinctiveDescriptors (S/MapPoint.cc:248-313), scope row N4 ----
     def distinctive_descriptors_batch(self, observed):

@@ -9,6 +9,8 @@
 //   SearchForTriangulation(pKF1, pKF2, F12, pairs, bOnlyStereo) (replaces S/ORBmatcher.cc:661-827; scope row N3)
 //   Fuse(pKF, vpMapPoints, th)                           (replaces S/ORBmatcher.cc:829-975; scope row N3: the search
 //                                                         runs on the device, the replace-or-add surgery stays here)
+//   Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)         (replaces S/ORBmatcher.cc:979-1104; same split)
+//   SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (replaces S/ORBmatcher.cc:1106-1330)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -523,7 +525,7 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
     FrameBounds(bounds);                     // the Frame statics the key frame's grid was assigned with
     std::vector<int32_t> best(nMPs, -1);
     if (orbb200_fuse_search(h, 1, &kv, &kur[0], &pv, R9, t3, O3, K, pKF->mbf, &pKF->mvScaleFactors[0], &pKF->mvInvLevelSigma2[0],
-                            (int)pKF->mvScaleFactors.size(), pKF->mfLogScaleFactor, bounds, th, &best[0], 0, 0) != ORBB200_OK) {
+                            (int)pKF->mvScaleFactors.size(), pKF->mfLogScaleFactor, bounds, th, 0, 0, 0, &best[0], 0, 0) != ORBB200_OK) {
         std::fprintf(stderr, "ORBmatcher(B200)::Fuse: %s\n", orbb200_last_error());
         return 0;
     }
@@ -551,6 +553,159 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
         nFused++;
     }
     return nFused;
+}
+
+namespace
+{
+// a key frame's keypoints as an orbb200_frame_view (+ mvuRight)
+struct KeyFrameKeys {
+    int32_t n;
+    std::vector<float> x, y, uRight;
+    std::vector<int32_t> octave;
+    std::vector<unsigned char> desc;
+    orbb200_frame_view view;
+    explicit KeyFrameKeys(KeyFrame* pKF)
+    {
+        n = pKF->N;
+        const int s = n > 0 ? n : 1;
+        x.resize(s); y.resize(s); uRight.resize(s, -1.f); octave.resize(s); desc.resize((size_t)s * 32);
+        for (int i = 0; i < n; i++) {
+            x[i] = pKF->mvKeysUn[i].pt.x; y[i] = pKF->mvKeysUn[i].pt.y; octave[i] = pKF->mvKeysUn[i].octave; uRight[i] = pKF->mvuRight[i];
+            std::memcpy(&desc[(size_t)i * 32], pKF->mDescriptors.ptr<unsigned char>(i), 32);
+        }
+        view.n = &n; view.x = &x[0]; view.y = &y[0]; view.octave = &octave[0]; view.angle = 0; view.desc = &desc[0]; view.stride = s;
+    }
+};
+
+// candidate map points as an orbb200_fusepoints_view; admit[i] decides which are looked at
+struct PointSoA {
+    int32_t n;
+    std::vector<unsigned char> valid, desc;
+    std::vector<float> wpos, normal, maxD, minD;
+    orbb200_fusepoints_view view;
+    PointSoA(const std::vector<MapPoint*>& pts, const std::vector<unsigned char>& admit)
+    {
+        n = (int32_t)pts.size();
+        const int s = n > 0 ? n : 1;
+        valid.assign(s, 0); desc.resize((size_t)s * 32); wpos.resize((size_t)s * 3); normal.resize((size_t)s * 3); maxD.resize(s); minD.resize(s);
+        for (int i = 0; i < n; i++) {
+            MapPoint* pMP = pts[i];
+            if (!admit[i]) continue;
+            valid[i] = 1;
+            const cv::Mat p3Dw = pMP->GetWorldPos(), Pn = pMP->GetNormal(), d = pMP->GetDescriptor();
+            for (int k = 0; k < 3; k++) { wpos[3 * (size_t)i + k] = p3Dw.at<float>(k); normal[3 * (size_t)i + k] = Pn.at<float>(k); }
+            if (!d.empty()) std::memcpy(&desc[(size_t)i * 32], d.ptr<unsigned char>(), 32);
+            std::unique_lock<std::mutex> lock(pMP->*MapPointFields::PosMutex());
+            maxD[i] = pMP->*MapPointFields::MaxDistance();
+            minD[i] = pMP->*MapPointFields::MinDistance();
+        }
+        view.n = &n; view.valid = &valid[0]; view.world_pos = &wpos[0]; view.normal = &normal[0]; view.mp_desc = &desc[0];
+        view.max_distance = &maxD[0]; view.min_distance = &minD[0]; view.stride = s;
+    }
+};
+
+void Flatten3x3(const cv::Mat& R, float* out9) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) out9[3 * r + c] = R.at<float>(r, c); }
+void Flatten3(const cv::Mat& t, float* out3) { for (int r = 0; r < 3; r++) out3[r] = t.at<float>(r); }
+}  // namespace
+
+int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint)
+{
+    // Decompose Scw on the host, as the reference does (:987-991)
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();
+
+    const int nPoints = (int)vpPoints.size();
+    if (nPoints == 0 || pKF->N == 0) return 0;
+    orbb200_matcher* h = tlsMatcher.get(nPoints > pKF->N ? nPoints : pKF->N);
+    if (!h) return 0;
+    std::vector<unsigned char> admit(nPoints);
+    for (int i = 0; i < nPoints; i++) admit[i] = (!vpPoints[i]->isBad() && !spAlreadyFound.count(vpPoints[i])) ? 1 : 0;   // :1005-1006
+    KeyFrameKeys keys(pKF);
+    PointSoA pts(vpPoints, admit);
+    float R9[9], t3[3], O3[3], bounds[4];
+    Flatten3x3(Rcw, R9); Flatten3(tcw, t3); Flatten3(Ow, O3);
+    FrameBounds(bounds);
+    const float K[4] = {pKF->fx, pKF->fy, pKF->cx, pKF->cy};
+    std::vector<int32_t> best(nPoints, -1);
+    if (orbb200_fuse_search(h, 1, &keys.view, &keys.uRight[0], &pts.view, R9, t3, O3, K, pKF->mbf, &pKF->mvScaleFactors[0],
+                            &pKF->mvInvLevelSigma2[0], (int)pKF->mvScaleFactors.size(), pKF->mfLogScaleFactor, bounds, th, 1, 0, 0,
+                            &best[0], 0, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::Fuse(Scw): %s\n", orbb200_last_error());
+        return 0;
+    }
+    int nFused = 0;
+    for (int iMP = 0; iMP < nPoints; iMP++) {                                          // :1084-1100, in list order
+        MapPoint* pMP = vpPoints[iMP];
+        if (!admit[iMP] || best[iMP] < 0 || pMP->isBad()) continue;
+        MapPoint* pMPinKF = pKF->GetMapPoint(best[iMP]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+        } else {
+            pMP->AddObservation(pKF, best[iMP]);
+            pKF->AddMapPoint(pMP, best[iMP]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                             const cv::Mat& t12, const float th)
+{
+    // the transforms, evaluated on the host as in the reference (:1114-1126)
+    cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    cv::Mat sR12 = s12 * R12;
+    cv::Mat sR21 = (1.0 / s12) * R12.t();
+    cv::Mat t21 = -sR21 * t12;
+
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+    if (N1 == 0 || N2 == 0) return 0;
+    std::vector<unsigned char> admit1(N1, 0), admit2(N2, 0);
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {                                                     // :1137-1148
+        MapPoint* pMP = vpMatches12[i];
+        if (pMP) {
+            vbAlreadyMatched1[i] = true;
+            const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+    }
+    for (int i = 0; i < N1; i++) admit1[i] = (vpMapPoints1[i] && !vbAlreadyMatched1[i] && !vpMapPoints1[i]->isBad()) ? 1 : 0;
+    for (int i = 0; i < N2; i++) admit2[i] = (vpMapPoints2[i] && !vbAlreadyMatched2[i] && !vpMapPoints2[i]->isBad()) ? 1 : 0;
+
+    orbb200_matcher* h = tlsMatcher.get(N1 > N2 ? N1 : N2);
+    if (!h) return 0;
+    KeyFrameKeys keys1(pKF1), keys2(pKF2);
+    PointSoA pts1(vpMapPoints1, admit1), pts2(vpMapPoints2, admit2);
+    float bounds[4];
+    FrameBounds(bounds);
+    std::vector<int32_t> vnMatch1(N1, -1), vnMatch2(N2, -1);
+    float Ra[9], ta[3], Rb[9], tb[3];
+    // key frame 1's map points into key frame 2 (:1154-1230): camera 1, then sR21 / t21
+    Flatten3x3(R1w, Ra); Flatten3(t1w, ta); Flatten3x3(sR21, Rb); Flatten3(t21, tb);
+    const float K2[4] = {pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy};                      // the reference projects both legs with pKF1's intrinsics (:1109-1112)
+    int rc = orbb200_fuse_search(h, 1, &keys2.view, 0, &pts1.view, Ra, ta, 0, K2, 0.f, &pKF2->mvScaleFactors[0], &pKF2->mvInvLevelSigma2[0],
+                                 (int)pKF2->mvScaleFactors.size(), pKF2->mfLogScaleFactor, bounds, th, 2, Rb, tb, &vnMatch1[0], 0, 0);
+    // key frame 2's map points into key frame 1 (:1233-1309): camera 2, then sR12 / t12
+    Flatten3x3(R2w, Ra); Flatten3(t2w, ta); Flatten3x3(sR12, Rb); Flatten3(t12, tb);
+    if (rc == ORBB200_OK)
+        rc = orbb200_fuse_search(h, 1, &keys1.view, 0, &pts2.view, Ra, ta, 0, K2, 0.f, &pKF1->mvScaleFactors[0], &pKF1->mvInvLevelSigma2[0],
+                                 (int)pKF1->mvScaleFactors.size(), pKF1->mfLogScaleFactor, bounds, th, 2, Rb, tb, &vnMatch2[0], 0, 0);
+    if (rc != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchBySim3: %s\n", orbb200_last_error());
+        return 0;
+    }
+    int nFound = 0;                                                                    // agreement (:1312-1328)
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
+    }
+    return nFound;
 }
 
 }  // namespace ORB_SLAM2

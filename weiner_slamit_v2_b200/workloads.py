@@ -349,3 +349,49 @@ def fuse_frame(index, n_mp=3000, n_kp=2000, width=640, height=480, nlevels=8, sc
     return dict(valid=valid, wpos=wpos, normal=nrm, mp_desc=mp_desc, mf_max=mf_max, mf_min=mf_min, Rcw=R.reshape(9), tcw=t, Ow=Ow,
                 K=np.array(K, np.float32), bf=np.float32(bf), kp=kp, kdesc=kdesc, u_right=ur, scale_factors=sf,
                 inv_level_sigma2=(np.float32(1.0) / (sf * sf)).astype(np.float32), log_scale=np.float32(np.log(np.float32(scale))))
+
+
+def sim3_pair(index, n1=1500, n2=1500, width=640, height=480, nlevels=8, scale=1.2, K=(526.69, 540.36, 313.07, 238.39)):
+    """Two key frames observing a common cloud, each with its OWN map points (slot i of key frame k holds map point i of
+    k: world position, descriptor, scale-invariance distances; valid 0 = empty slot, 1 good, 3 bad), and a relative
+    similarity (s12 = 1, R12, t12) close to the true one -- the inputs of SearchBySim3.  Returns the two sides in
+    fuse_frame() layout (each side's points are searched in the OTHER side's keypoints) plus the transforms."""
+    rng = np.random.default_rng(180000 + index)
+    fx, fy, cx, cy = K
+    R1, R2 = _rodrigues(rng, 0, 8).astype(np.float32), _rodrigues(rng, 0, 8).astype(np.float32)
+    t1, t2 = rng.normal(0, 0.2, 3).astype(np.float32), rng.normal(0, 0.2, 3).astype(np.float32)
+    npts = max(n1, n2, 1)
+    P = np.stack([rng.uniform(-4, 4, npts), rng.uniform(-3, 3, npts), rng.uniform(3, 12, npts)], 1)
+    base_desc = rng.integers(0, 256, (npts, 32)).astype(np.uint8)
+    sf = np.array([scale ** i for i in range(nlevels)], np.float32)
+
+    def side(n, R, t):
+        src = rng.permutation(npts)[:n] if n else np.zeros(0, np.int64)
+        X = (P[src] + rng.normal(0, 0.01, (n, 3))).astype(np.float32)
+        Xc = X.astype(np.float64) @ R.astype(np.float64).T + t
+        z = np.where(np.abs(Xc[:, 2]) < 1e-3, 1e-3, Xc[:, 2]) if n else np.zeros(0)
+        u = fx * Xc[:, 0] / z + cx; v = fy * Xc[:, 1] / z + cy
+        dist = np.linalg.norm(Xc, axis=1)
+        level = rng.integers(0, nlevels - 1, n)       # seen from the other key frame the level may grow by one: stay in range
+        mf_max = (dist * scale ** (level - 0.5 + rng.uniform(-0.3, 0.3, n))).astype(np.float32)
+        mf_min = (mf_max / np.float32(scale ** (nlevels - 1))).astype(np.float32)
+        mp_desc = flip_bits(base_desc[src], rng.integers(0, 40, n), rng) if n else np.zeros((0, 32), np.uint8)
+        kp = random_keypoints(n, width, height, rng, nlevels)
+        kp["x"] = np.clip(u + rng.normal(0, 1.5, n), 0, width - 1).astype(np.float32)
+        kp["y"] = np.clip(v + rng.normal(0, 1.5, n), 0, height - 1).astype(np.float32)
+        kp["octave"] = np.clip(level + rng.integers(-1, 1, n), 0, nlevels - 1)
+        kdesc = flip_bits(mp_desc, rng.integers(0, 40, n), rng) if n else np.zeros((0, 32), np.uint8)
+        valid = rng.choice(np.array([0, 1, 3], np.uint8), n, p=[0.2, 0.75, 0.05])
+        return dict(valid=valid, wpos=X, normal=np.zeros((n, 3), np.float32), mp_desc=mp_desc, mf_max=mf_max, mf_min=mf_min,
+                    kp=kp, kdesc=kdesc, u_right=np.full(n, -1, np.float32), Rcw=R.reshape(9), tcw=t)
+    a, b = side(n1, R1, t1), side(n2, R2, t2)
+    R12 = (R1.astype(np.float64) @ R2.astype(np.float64).T @ _rodrigues(rng, 0, 0.3)).astype(np.float32)
+    t12 = (t1 - R12.astype(np.float64) @ t2 + rng.normal(0, 0.005, 3)).astype(np.float32)
+    sR21 = np.ascontiguousarray(R12.T)                                   # (1/s12) * R12^T with s12 = 1
+    t21 = camera_centre(R12, t12)                                        # -sR21 * t12, float in source order
+    common = dict(K=np.array(K, np.float32), bf=np.float32(0), scale_factors=sf, inv_level_sigma2=(np.float32(1) / (sf * sf)).astype(np.float32),
+                  log_scale=np.float32(np.log(np.float32(scale))), Ow=np.zeros(3, np.float32))
+    # leg 1: key frame 1's map points searched in key frame 2's keypoints; leg 2 the other way round
+    leg1 = dict(common, **{k: a[k] for k in ("valid", "wpos", "normal", "mp_desc", "mf_max", "mf_min", "Rcw", "tcw")}, kp=b["kp"], kdesc=b["kdesc"], u_right=b["u_right"])
+    leg2 = dict(common, **{k: b[k] for k in ("valid", "wpos", "normal", "mp_desc", "mf_max", "mf_min", "Rcw", "tcw")}, kp=a["kp"], kdesc=a["kdesc"], u_right=a["u_right"])
+    return dict(k1=a, k2=b, leg1=leg1, leg2=leg2, R12=R12.reshape(9), t12=t12, sR21=sR21.reshape(9), t21=t21, common=common)
