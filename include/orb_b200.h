@@ -336,6 +336,16 @@ int orbb200_fuse_search(orbb200_matcher *m, int items, const orbb200_frame_view 
                         float log_scale_factor, const float bounds[4], float th, int mode, const float *R2, const float *t2,
                         int32_t *best_idx, int32_t *best_dist, int on_device);
 
+/* Replaces ORBmatcher::SearchByProjection(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints,
+ * vector<MapPoint*> &vpMatched, int th) (S/ORBmatcher.cc:294-407, loop closing; scope row N3) for `items` (key frame,
+ * candidate list) pairs.  Views and pose as for orbb200_fuse_search mode 1 (Scw decomposed by the caller);
+ * valid[i] = !isBad && not already in vpMatched.  matched: items x kf->stride in/out = vpMatched as an index into the
+ * candidate list (-1 free; any other value on input = occupied).  Greedy in list order like the reference. */
+int orbb200_search_by_projection_sim3(orbb200_matcher *m, int items, const orbb200_frame_view *kf,
+                                      const orbb200_fusepoints_view *pts, const float *Rcw, const float *tcw, const float *Ow,
+                                      const float K[4], const float *scale_factors, int nlevels, float log_scale_factor,
+                                      const float bounds[4], int th, int32_t *matched, int32_t *nmatches, int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

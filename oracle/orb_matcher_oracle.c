@@ -936,3 +936,72 @@ int orc_sim3_agreement(int n1, const int32_t *match1, int n2, const int32_t *mat
     }
     return found;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints,
+ * vector<MapPoint*> &vpMatched, int th) (S/ORBmatcher.cc:294-407, loop closing): the Fuse(Scw)-style projection and
+ * gates, but keypoints that already hold a match are skipped and an accepted match occupies its keypoint (greedy,
+ * in list order).  valid[i] = !isBad && not already in vpMatched.  matched[n] in/out: -1 free, >= 0 index into the
+ * candidate list, any other value = occupied by a map point outside the list.  Returns nmatches. */
+int orc_search_by_projection_sim3(
+    int nmp, const uint8_t *valid, const float *wpos, const float *normal, const uint8_t *mp_desc,
+    const float *mf_max_distance, const float *mf_min_distance,
+    const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4],
+    int n, const float *kx, const float *ky, const int32_t *koct, const uint8_t *kdesc,
+    int nlevels, const float *scale_factors, float log_scale_factor, const float bounds[4], int th, int32_t *matched)
+{
+    orc_grid g, q;
+    int nmatches = 0;
+    int32_t *items = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    orc_grid_bounds(&g, bounds);
+    orc_grid_assign(&g, n, kx, ky, koct, items);
+    q = g;
+    q.min_x = (float)(int)bounds[0]; q.min_y = (float)(int)bounds[1];
+    const int maxXi = (int)bounds[2], maxYi = (int)bounds[3];
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    for (int i = 0; i < nmp; i++) {
+        if (!valid[i]) continue;
+        const float *X = wpos + 3 * (size_t)i;
+        float c3[3];
+        for (int r = 0; r < 3; r++) {
+            volatile float t = Rcw[3 * r] * X[0];
+            volatile float t1 = Rcw[3 * r + 1] * X[1];
+            volatile float t2 = Rcw[3 * r + 2] * X[2];
+            t = t + t1; t = t + t2;
+            c3[r] = t + tcw[r];
+        }
+        if (c3[2] < 0.0) continue;
+        const float invz = 1 / c3[2];
+        const float x = c3[0] * invz, y = c3[1] * invz;
+        volatile float u = fx * x; u = u + cx;
+        volatile float v = fy * y; v = v + cy;
+        if (!(u >= q.min_x && u < (float)maxXi && v >= q.min_y && v < (float)maxYi)) continue;
+        double ss = 0.0, dot = 0.0;
+        for (int r = 0; r < 3; r++) {
+            const float po = X[r] - Ow[r];
+            ss += (double)po * (double)po;
+            dot += (double)po * (double)normal[3 * (size_t)i + r];
+        }
+        const float dist = (float)sqrt(ss);
+        if (dist < 0.8f * mf_min_distance[i] || dist > 1.2f * mf_max_distance[i]) continue;
+        if (dot < 0.5 * (double)dist) continue;
+        int level = orc_predict_scale(mf_max_distance[i], dist, log_scale_factor);
+        if (level < 0) level = 0;
+        if (level >= nlevels) level = nlevels - 1;
+        const float radius = th * scale_factors[level];
+        const int nc = orc_features_in_area(&q, u, v, radius, -1, -1, cand, n);
+        int bestDist = 256, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            if (matched[idx] != -1) continue;
+            if (koct[idx] < level - 1 || koct[idx] > level) continue;
+            const int d = orc_descriptor_distance(mp_desc + 32 * (size_t)i, kdesc + 32 * (size_t)idx);
+            if (d < bestDist) { bestDist = d; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { matched[bestIdx] = i; nmatches++; }
+    }
+    free(cand); free(items);
+    return nmatches;
+}

@@ -159,6 +159,12 @@ void orc_fuse_search(
     int nlevels, const float *scale_factors, const float *inv_level_sigma2, float log_scale_factor,
     const float bounds[4], float th, int mode, const float *R2, const float *t2, int32_t *best_idx, int32_t *best_dist);
 int orc_sim3_agreement(int n1, const int32_t *match1, int n2, const int32_t *match2, int32_t *matches12);
+int orc_search_by_projection_sim3(
+    int nmp, const uint8_t *valid, const float *wpos, const float *normal, const uint8_t *mp_desc,
+    const float *mf_max_distance, const float *mf_min_distance,
+    const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4],
+    int n, const float *kx, const float *ky, const int32_t *koct, const uint8_t *kdesc,
+    int nlevels, const float *scale_factors, float log_scale_factor, const float bounds[4], int th, int32_t *matched);
 float orc_logf(float x);
 int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
 int orc_search_by_projection_keyframe(

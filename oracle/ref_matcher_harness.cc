@@ -591,4 +591,38 @@ int refm_search_by_sim3(
     for (int i = 0; i < n1; i++) matches12[i] = m12[i] ? (int32_t)(m12[i] - p2.mps) : -1;
     return found;
 }
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched,
+// int th) (S/ORBmatcher.cc:294-407), Scw = [Rcw | tcw] with unit scale.  valid: 1 usable, 3 bad; candidates with any
+// other code are not in the list the reference sees.  matched[n] in/out as in the oracle.
+int refm_search_by_projection_sim3(
+    int nmp, const uint8_t* valid, const float* wpos, const float* normal, const uint8_t* mp_desc,
+    const float* mf_max_distance, const float* mf_min_distance,
+    const float* Rcw, const float* tcw, const float* Ow, const float* K,
+    int n, const float* kx, const float* ky, const int32_t* koct, const uint8_t* kdesc,
+    int nlevels, const float* scale_factors, float log_scale_factor, const float* bounds, int th, int32_t* matched)
+{
+    std::vector<float> ur(n > 0 ? n : 1, -1.f), ils(nlevels, 1.f);
+    FullKeyFrame k(n, kx, ky, koct, &ur[0], kdesc, K, 0.f, nlevels, scale_factors, &ils[0], log_scale_factor, bounds, Rcw, tcw, Ow);
+    FakePoints pts(nmp, valid, wpos, normal, mp_desc, mf_max_distance, mf_min_distance);
+    MapPoint* foreign = (MapPoint*)std::calloc(n > 0 ? n : 1, sizeof(MapPoint));
+    std::vector<MapPoint*> list, vpMatched(n, static_cast<MapPoint*>(NULL));
+    std::vector<int> listIdx;
+    for (int i = 0; i < nmp; i++) if (valid[i] == 1 || valid[i] == 3) { list.push_back(&pts.mps[i]); listIdx.push_back(i); }
+    for (int i = 0; i < n; i++) {
+        if (matched[i] >= 0) vpMatched[i] = &pts.mps[matched[i]];
+        else if (matched[i] != -1) vpMatched[i] = &foreign[i];
+    }
+    cv::Mat Scw(4, 4, CV_32F, k.T);
+    ORBmatcher matcher(0.75f, true);
+    const int cnt = matcher.SearchByProjection(k.kf, Scw, list, vpMatched, th);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = vpMatched[i];
+        if (!p) matched[i] = -1;
+        else if (p >= pts.mps && p < pts.mps + nmp) matched[i] = (int32_t)(p - pts.mps);
+        else matched[i] = -2;
+    }
+    std::free(foreign);
+    return cnt;
+}
 }

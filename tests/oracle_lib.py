@@ -494,3 +494,27 @@ def search_by_sim3(w, bounds, th=7.5):
     out = np.full(max(len(m1), 1), -1, np.int32)
     found = L.orc_sim3_agreement(len(m1), _ptr(a, _i32p), len(m2), _ptr(b, _i32p), _ptr(out, _i32p))
     return found, out[:len(m1)]
+
+
+def _proj_sim3_call(f, w, bounds, th, valid, matched):
+    kp = w["kp"]
+    n, nmp = len(kp), len(w["valid"])
+    a = dict(v=valid(_b(w["valid"])), wp=_f(w["wpos"]), nr=_f(w["normal"]), md=_b(w["mp_desc"]), mx=_f(w["mf_max"]), mn=_f(w["mf_min"]),
+             R=_f(w["Rcw"]), t=_f(w["tcw"]), Ow=_f(w["Ow"]), K=_f(w["K"]), kx=_f(kp["x"]), ky=_f(kp["y"]), ko=_i(kp["octave"]),
+             kd=_b(w["kdesc"]), sf=_f(w["scale_factors"]), b=_bounds(bounds))
+    m = np.full(max(n, 1), -1, np.int32)
+    if matched is not None and n:
+        m[:n] = matched
+    f.argtypes = [C.c_int, _u8p, _f32p, _f32p, _u8p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                  C.c_int, _f32p, _f32p, _i32p, _u8p, C.c_int, _f32p, C.c_float, _f32p, C.c_int, _i32p]
+    f.restype = C.c_int
+    cnt = f(nmp, _ptr(a["v"], _u8p), _ptr(a["wp"], _f32p), _ptr(a["nr"], _f32p), _ptr(a["md"], _u8p), _ptr(a["mx"], _f32p), _ptr(a["mn"], _f32p),
+            _ptr(a["R"], _f32p), _ptr(a["t"], _f32p), _ptr(a["Ow"], _f32p), _ptr(a["K"], _f32p), n, _ptr(a["kx"], _f32p), _ptr(a["ky"], _f32p),
+            _ptr(a["ko"], _i32p), _ptr(a["kd"], _u8p), len(a["sf"]), _ptr(a["sf"], _f32p), float(w["log_scale"]), _ptr(a["b"], _f32p), int(th),
+            _ptr(m, _i32p))
+    return cnt, m[:n]
+
+
+def search_by_projection_sim3(w, bounds, th=10, matched=None):
+    """w: workloads.fuse_frame() dict (valid == 1 = usable candidate).  Returns (nmatches, matched[n])."""
+    return _proj_sim3_call(lib().orc_search_by_projection_sim3, w, bounds, th, lambda v: _b((v == 1).astype(np.uint8)), matched)

@@ -289,3 +289,9 @@ def ref_search_by_sim3(w, bounds, th=7.5):
     found = f(*(args(w["k1"]) + args(w["k2"]) + [P(K, _f32p), len(sf), P(sf, _f32p), P(il, _f32p), float(c["log_scale"]), P(b, _f32p),
                                                    P(R12, _f32p), P(t12, _f32p), float(th), P(m, _i32p)]))
     return found, m[:n1]
+
+
+def ref_search_by_projection_sim3(w, bounds, th=10, matched=None):
+    """The reference's own SearchByProjection(pKF, Scw, vpPoints, vpMatched, th), Scw = [Rcw | tcw]."""
+    import oracle_lib as O
+    return O._proj_sim3_call(mlib().refm_search_by_projection_sim3, w, bounds, th, lambda v: v, matched)

@@ -327,3 +327,31 @@ def test_fuse_sim3_search_and_search_by_sim3_match_oracle():
         c = g["scfg_%d" % i]
         f, mm = m.search_by_sim3_batch([sim3_pair(int(c[0]), int(c[1]), int(c[2]))], bounds, float(c[3]))
         assert f[0] == int(g["sn_%d" % i]) and np.array_equal(mm[0], g["sm_%d" % i])
+
+
+@pytest.mark.parametrize("th", [4, 10])
+def test_search_by_projection_sim3_matches_oracle(th):
+    """Scope row N3: SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) for a ragged batch with pre-occupied keypoints,
+    and the reference's golden vectors."""
+    import os
+    from weiner_slamit_v2_b200.workloads import fuse_frame
+    bounds = (-13.7, -9.2, 661.3, 492.8)
+    rng = np.random.default_rng(6)
+    ws = [fuse_frame(80 + i, a, b) for i, (a, b) in enumerate([(3000, 2000), (2000, 1500), (500, 300), (0, 100), (100, 0), (6000, 1000)])]
+    pre = [np.where(rng.random(len(w["kp"])) < 0.1, -2, -1).astype(np.int32) for w in ws]
+    m = ORBmatcher(0.75, True, max_items=len(ws), max_points=6000)
+    cnt, matched = m.search_by_projection_sim3_batch(ws, bounds, th, pre)
+    tot = 0
+    for i, w in enumerate(ws):
+        co, mo = O.search_by_projection_sim3(w, bounds, th, pre[i])
+        assert cnt[i] == co and np.array_equal(matched[i], mo), i
+        tot += co
+    assert tot > 800
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_projsim3.npz"))
+    for i in range(int(g["count"])):
+        c = g["cfg_%d" % i]
+        if int(c[3]) != th:
+            continue
+        p0 = np.where(np.random.default_rng(int(c[0])).random(int(c[2])) < 0.1, -2, -1).astype(np.int32)
+        cc, mm = m.search_by_projection_sim3_batch([fuse_frame(int(c[0]), int(c[1]), int(c[2]))], bounds, th, [p0])
+        assert cc[0] == int(g["n_%d" % i]) and np.array_equal(mm[0], g["m_%d" % i])

@@ -164,7 +164,14 @@ def test_matcher_oracle_reproduces_reference_golden_vectors(path):
     """Vectors produced by the reference's own matcher (tools/gen_golden.py); checked wherever the tests run."""
     from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
     g = np.load(path)
-    if "sim3" in os.path.basename(path):
+    if "projsim3" in os.path.basename(path):
+        from weiner_slamit_v2_b200.workloads import fuse_frame
+        for i in range(int(g["count"])):
+            c = g["cfg_%d" % i]
+            pre = np.where(np.random.default_rng(int(c[0])).random(int(c[2])) < 0.1, -2, -1).astype(np.int32)
+            a = O.search_by_projection_sim3(fuse_frame(int(c[0]), int(c[1]), int(c[2])), (-13.7, -9.2, 661.3, 492.8), int(c[3]), pre)
+            assert a[0] == int(g["n_%d" % i]) and np.array_equal(a[1], g["m_%d" % i])
+    elif "sim3" in os.path.basename(path):
         from weiner_slamit_v2_b200.workloads import fuse_frame, sim3_pair
         bounds = (-13.7, -9.2, 661.3, 492.8)
         for i in range(int(g["fcount"])):
@@ -370,3 +377,23 @@ def test_fuse_sim3_search_and_search_by_sim3_match_reference():
             assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx
             tot += b[0]
     assert tot > 300
+
+
+@needs_refm
+@pytest.mark.parametrize("th", [4, 10])
+def test_search_by_projection_sim3_matches_reference(th):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (S/ORBmatcher.cc:294-407) run whole by the reference,
+    with pre-occupied keypoints and more candidates than keypoints (the greedy occupancy matters)."""
+    from weiner_slamit_v2_b200.workloads import fuse_frame
+    rng = np.random.default_rng(4)
+    tot = 0
+    for idx, (nmp, nkp, bounds) in enumerate([(3000, 2000, (0.0, 0.0, 640.0, 480.0)), (3000, 2000, (-13.7, -9.2, 661.3, 492.8)),
+                                              (500, 300, (-13.7, -9.2, 661.3, 492.8)), (0, 100, (0.0, 0.0, 640.0, 480.0)),
+                                              (100, 0, (0.0, 0.0, 640.0, 480.0)), (6000, 1000, (0.0, 0.0, 640.0, 480.0))]):
+        w = fuse_frame(1020 + idx, nmp, nkp)
+        pre = np.where(rng.random(nkp) < 0.1, -2, -1).astype(np.int32)
+        a = O.search_by_projection_sim3(w, bounds, th, pre)
+        b = R.ref_search_by_projection_sim3(w, bounds, th, pre)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx
+        tot += b[0]
+    assert tot > 800

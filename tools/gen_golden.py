@@ -144,3 +144,13 @@ for i, (idx, na, nb, th) in enumerate(cfgs):
 out["scount"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_sim3.npz"), **out)
 print("ref_match_sim3.npz", [int((out["fbest_%d" % i] >= 0).sum()) for i in range(2)], [int(out["sn_%d" % i]) for i in range(2)])
+
+out = {}
+cfgs = [(895, 3000, 2000, 10), (896, 6000, 1000, 4)]
+for i, (idx, nmp, nkp, th) in enumerate(cfgs):
+    pre = np.where(np.random.default_rng(idx).random(nkp) < 0.1, -2, -1).astype(np.int32)
+    r = R.ref_search_by_projection_sim3(fuse_frame(idx, nmp, nkp), (-13.7, -9.2, 661.3, 492.8), th, pre)
+    out["cfg_%d" % i] = np.array([idx, nmp, nkp, th]); out["n_%d" % i] = r[0]; out["m_%d" % i] = r[1]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_match_projsim3.npz"), **out)
+print("ref_match_projsim3.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])

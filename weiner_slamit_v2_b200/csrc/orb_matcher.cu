@@ -687,6 +687,11 @@ struct LastParams {
     const float *mfMax, *mfMin;  // items x lastStride: raw mfMaxDistance / mfMinDistance
     const float* Ow;             // items x 3
     float logScale;
+    // kind 2 = SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (:294-407): Fuse-style projection and gates on a key
+    // frame (int-truncated query bounds, viewing angle), level window [level-1, level], acceptance TH_LOW
+    const float* normal;         // items x lastStride x 3
+    GridGeo q;                   // query geometry of the key frame
+    int maxXi, maxYi;
 };
 
 struct LastQuery { float u, v, radius, invzc; int minLevel, maxLevel; bool ok; };
@@ -735,6 +740,31 @@ __device__ __forceinline__ LastQuery last_query(const LastParams& P, int item, i
 #pragma unroll
     for (int r = 0; r < 3; r++)
         c3[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3 * r], X[0]), __fmul_rn(R[3 * r + 1], X[1])), __fmul_rn(R[3 * r + 2], X[2])), t[r]);
+    if (P.kind == 2) {
+        if (c3[2] < 0.0f) return q;                                      // :327
+        q.invzc = __fdiv_rn(1.0f, c3[2]);
+        q.u = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(c3[0], q.invzc)), P.cx);
+        q.v = __fadd_rn(__fmul_rn(P.fy, __fmul_rn(c3[1], q.invzc)), P.cy);
+        if (!(q.u >= P.q.minX && q.u < (float)P.maxXi && q.v >= P.q.minY && q.v < (float)P.maxYi)) return q;     // KeyFrame::IsInImage
+        const float* O = P.Ow + (size_t)item * 3;
+        double ss = 0.0, dot = 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const double po = (double)__fsub_rn(X[r], O[r]);
+            ss = __dadd_rn(ss, __dmul_rn(po, po));
+            dot = __dadd_rn(dot, __dmul_rn(po, (double)P.normal[lo * 3 + r]));
+        }
+        const float dist = __double2float_rn(__dsqrt_rn(ss));
+        const float mx = P.mfMax[lo];
+        if (dist < __fmul_rn(0.8f, P.mfMin[lo]) || dist > __fmul_rn(1.2f, mx)) return q;
+        if (dot < __dmul_rn(0.5, (double)dist)) return q;
+        int level = (int)ceilf(__fdiv_rn(libm_logf(__fdiv_rn(mx, dist)), P.logScale));
+        level = max(0, min(level, P.nlevels - 1));
+        q.radius = __fmul_rn(P.th, P.scaleFactors[level]);
+        q.minLevel = level - 1; q.maxLevel = level;                      // :371 (maxLevel >= 0, so the level test is active)
+        q.ok = true;
+        return q;
+    }
     q.invzc = (float)__ddiv_rn(1.0, (double)c3[2]);
     if (P.kind == 0 && q.invzc < 0) return q;                            // (the key-frame overload has no depth test)
     q.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), q.invzc), P.cx);
@@ -796,7 +826,7 @@ __global__ void __launch_bounds__(128) k_last_topk(const LastParams P)
     const int* ci = P.cellItems + (size_t)item * P.f.stride;
     const LastQuery q = last_query(P, item, i);
     int c0, c1, r0, r1;
-    if (q.ok && cell_range(P.g, q.u, q.v, q.radius, c0, c1, r0, r1)) {
+    if (q.ok && cell_range(P.kind == 2 ? P.q : P.g, q.u, q.v, q.radius, c0, c1, r0, r1)) {
         count = 0;
         const float* kx = P.f.x + (size_t)item * P.f.stride;
         const float* ky = P.f.y + (size_t)item * P.f.stride;
@@ -814,7 +844,7 @@ __global__ void __launch_bounds__(128) k_last_topk(const LastParams P)
                 const int idx = ci[p];
                 if (!last_candidate(P, q, idx, kx, ky, koct, ur)) continue;
                 const int held = kpmp[idx];                                      // initial occupancy (:1409-1411, :1546-1547)
-                if (held != -1 && (P.kind == 1 || (held >= 0 ? P.mpObs[(size_t)item * P.lastStride + held] : (kpobs ? kpobs[idx] : 0)) > 0)) continue;
+                if (held != -1 && (P.kind != 0 || (held >= 0 ? P.mpObs[(size_t)item * P.lastStride + held] : (kpobs ? kpobs[idx] : 0)) > 0)) continue;
                 const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
                 top4_insert(best, ((uint32_t)dist << 23) | ((uint32_t)p << 5));
                 count++;
@@ -857,19 +887,19 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
     uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * ((P.f.stride + 15) & ~15);
     for (int idx = lane; idx < n; idx += 32) {
         const int held = kpmp[idx];
-        occ[idx] = held != -1 && (P.kind == 1 || (held >= 0 ? P.mpObs[lo + held] : (kpobs ? kpobs[idx] : 0)) > 0);
+        occ[idx] = held != -1 && (P.kind != 0 || (held >= 0 ? P.mpObs[lo + held] : (kpobs ? kpobs[idx] : 0)) > 0);
     }
     for (int i = lane; i < nl; i += 32) hbin[i] = -1;
     __syncwarp();
 
     int nmatches = 0;
-    const int accept = P.kind == 1 ? P.orbDist : TH_HIGH;
+    const int accept = P.kind == 1 ? P.orbDist : (P.kind == 2 ? TH_LOW : TH_HIGH);
     for (int base = 0; base < nl; base += 32) {
       const int mine = base + lane;
       int cntL = -1, obsL = 0;
       float angL = 0.f;
       uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
-      if (mine < nl) { cntL = P.topkCount[lo + mine]; kkL = P.topk[lo + mine]; idL = P.topkIdx[lo + mine]; obsL = P.kind == 1 ? 1 : P.mpObs[lo + mine]; angL = P.lastAng[lo + mine]; }
+      if (mine < nl) { cntL = P.topkCount[lo + mine]; kkL = P.topk[lo + mine]; idL = P.topkIdx[lo + mine]; obsL = P.kind != 0 ? 1 : P.mpObs[lo + mine]; angL = P.lastAng[lo + mine]; }
       const int jEnd = min(32, nl - base);
       for (int j = 0; j < jEnd; j++) {
         const int i = base + j;
@@ -895,7 +925,7 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
         if (!resolved) {                                   // every listed keypoint was taken: rescan all candidates
             const LastQuery q = last_query(P, item, i);
             int c0, c1, r0, r1;
-            cell_range(P.g, q.u, q.v, q.radius, c0, c1, r0, r1);
+            cell_range(P.kind == 2 ? P.q : P.g, q.u, q.v, q.radius, c0, c1, r0, r1);
             const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + (lo + i) * 32);
             const uint4 a0 = __ldg(md), a1 = __ldg(md + 1);
             int bd = 256, bp = INT_MAX;
@@ -1977,6 +2007,71 @@ extern "C" int orbb200_fuse_search(orbb200_matcher* m, int items, const orbb200_
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(best_idx, P.bestIdx, nl * 4, cudaMemcpyDeviceToHost, st));
         if (best_dist) ORB_CUDA(cudaMemcpyAsync(best_dist, P.bestDist, nl * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_search_by_projection_sim3(orbb200_matcher* m, int items, const orbb200_frame_view* kf,
+                                                 const orbb200_fusepoints_view* pts, const float* Rcw, const float* tcw, const float* Ow,
+                                                 const float* K, const float* scale_factors, int nlevels, float log_scale_factor,
+                                                 const float* bounds, int th, int32_t* matched, int32_t* nmatches, int on_device)
+{
+    if (!m || !kf || !pts || !Rcw || !tcw || !Ow || !K || !scale_factors || !matched || !nmatches) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (!kf->n || !kf->x || !kf->y || !kf->octave || !kf->desc || !pts->n || !pts->valid || !pts->world_pos || !pts->normal || !pts->mp_desc ||
+        !pts->max_distance || !pts->min_distance) { set_error("incomplete view"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, kf->stride, "key frame")) || (rc = check_view(m, items, pts->stride, "map points"))) return rc;
+    if (nlevels < 1 || nlevels > 32 || !bounds || !(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1]) || !(log_scale_factor > 0.f)) { set_error("bad geometry"); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    LastParams P;
+    memset(&P, 0, sizeof(P));
+    const size_t np = (size_t)items * kf->stride, nl = (size_t)items * pts->stride;
+    Stager s{m, 0, st};
+    int* dN;
+    if (on_device) {
+        P.f = as_dev(kf);
+        P.lastN = pts->n; P.hasMp = pts->valid; P.wpos = pts->world_pos; P.normal = pts->normal; P.mpDesc = pts->mp_desc;
+        P.mfMax = pts->max_distance; P.mfMin = pts->min_distance;
+        P.Rcw = Rcw; P.tcw = tcw; P.Ow = Ow; P.kpMp = matched; P.scaleFactors = scale_factors; dN = nmatches;
+    } else {
+        const size_t bytes = frame_bytes(kf, items) + pad(np * 4) + 2 * pad((size_t)items * 4) + pad(nl) + 2 * pad(nl * 12) + pad(nl * 32) +
+                             2 * pad(nl * 4) + pad((size_t)items * 36) + 2 * pad((size_t)items * 12) + pad((size_t)nlevels * 4);
+        if ((rc = s.reserve(bytes))) return rc;
+        if ((rc = upload_frame(s, kf, items, &P.f, false))) return rc;
+        const int* kpmp;
+        if ((rc = s.up(matched, np, &kpmp)) || (rc = s.up(pts->n, items, &P.lastN)) || (rc = s.up(pts->valid, nl, &P.hasMp)) ||
+            (rc = s.up(pts->world_pos, nl * 3, &P.wpos)) || (rc = s.up(pts->normal, nl * 3, &P.normal)) || (rc = s.up(pts->mp_desc, nl * 32, &P.mpDesc)) ||
+            (rc = s.up(pts->max_distance, nl, &P.mfMax)) || (rc = s.up(pts->min_distance, nl, &P.mfMin)) ||
+            (rc = s.up(Rcw, (size_t)items * 9, &P.Rcw)) || (rc = s.up(tcw, (size_t)items * 3, &P.tcw)) || (rc = s.up(Ow, (size_t)items * 3, &P.Ow)) ||
+            (rc = s.up(scale_factors, (size_t)nlevels, &P.scaleFactors))) return rc;
+        P.kpMp = const_cast<int*>(kpmp);
+        dN = s.out<int>(items);
+    }
+    P.lastAng = P.mfMax;                       // orientation is not checked in this overload
+    P.kind = 2; P.nlevels = nlevels; P.logScale = log_scale_factor;
+    P.lastStride = pts->stride; P.g = grid_geo(bounds); P.q = P.g;
+    P.q.minX = (float)(int)bounds[0]; P.q.minY = (float)(int)bounds[1]; P.maxXi = (int)bounds[2]; P.maxYi = (int)bounds[3];
+    P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
+    P.nmatches = dN; P.items = items; P.mode = 0; P.checkOri = 0; P.th = (float)th;
+    P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx; P.histBin = m->scratchA; P.histIdx = m->scratchB;
+    k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
+    ORB_CHECK_LAUNCH("k_build_grid");
+    k_last_topk<<<dim3((pts->stride + 127) / 128, items), 128, 0, st>>>(P);
+    ORB_CHECK_LAUNCH("k_last_topk");
+    {
+        const size_t sm = 4 * (size_t)((kf->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
+    }
+    ORB_CHECK_LAUNCH("k_search_last");
+    m->lastLaunches = 3;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(matched, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
     }
     return ORBB200_OK;

@@ -277,6 +277,42 @@ class ORBmatcher:
                                           best.ctypes.data, dist.ctypes.data, 0))
         return [(best[i, :nm[i]], dist[i, :nm[i]]) for i in range(items)]
 
+    # ---- SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (S/ORBmatcher.cc:294-407), scope row N3 ----
+    def search_by_projection_sim3_batch(self, ws, bounds, th=10, matched=None):
+        """ws: list of workloads.fuse_frame()-layout dicts (valid == 1 = usable candidate, pose = the decomposed Scw).
+        matched: optional list of per-item int32 arrays (vpMatched as indices, -1 free).  Returns (nmatches, [matched])."""
+        from ._lib import FrameView, FusePointsView
+        items = len(ws)
+        nk = np.array([len(w["kp"]) for w in ws], np.int32)
+        nm = np.array([len(w["valid"]) for w in ws], np.int32)
+        s, ms = max(1, int(nk.max())), max(1, int(nm.max()))
+        self._ensure(items, max(s, ms))
+        k = dict(x=_pack([w["kp"]["x"] for w in ws], s, np.float32), y=_pack([w["kp"]["y"] for w in ws], s, np.float32),
+                 o=_pack([w["kp"]["octave"] for w in ws], s, np.int32), d=_pack([w["kdesc"] for w in ws], s, np.uint8, (32,)))
+        fv = FrameView(nk.ctypes.data, k["x"].ctypes.data, k["y"].ctypes.data, k["o"].ctypes.data, None, k["d"].ctypes.data, s)
+        a = dict(v=_pack([(np.asarray(w["valid"]) == 1).astype(np.uint8) for w in ws], ms, np.uint8),
+                 wp=_pack([np.asarray(w["wpos"], np.float32).reshape(-1, 3) for w in ws], ms, np.float32, (3,)),
+                 nr=_pack([np.asarray(w["normal"], np.float32).reshape(-1, 3) for w in ws], ms, np.float32, (3,)),
+                 md=_pack([w["mp_desc"] for w in ws], ms, np.uint8, (32,)), mx=_pack([w["mf_max"] for w in ws], ms, np.float32),
+                 mn=_pack([w["mf_min"] for w in ws], ms, np.float32))
+        pv = FusePointsView(nm.ctypes.data, a["v"].ctypes.data, a["wp"].ctypes.data, a["nr"].ctypes.data, a["md"].ctypes.data,
+                            a["mx"].ctypes.data, a["mn"].ctypes.data, ms)
+        R = np.ascontiguousarray(np.stack([np.asarray(w["Rcw"], np.float32).reshape(9) for w in ws]))
+        t = np.ascontiguousarray(np.stack([np.asarray(w["tcw"], np.float32).reshape(3) for w in ws]))
+        Ow = np.ascontiguousarray(np.stack([np.asarray(w["Ow"], np.float32).reshape(3) for w in ws]))
+        K = np.ascontiguousarray(ws[0]["K"], np.float32)
+        sf = np.ascontiguousarray(ws[0]["scale_factors"], np.float32)
+        bnd = np.ascontiguousarray(bounds, np.float32)
+        mt = np.full((items, s), -1, np.int32)
+        if matched is not None:
+            for i, mm in enumerate(matched):
+                mt[i, :len(mm)] = mm
+        cnt = np.zeros(items, np.int32)
+        check(self._L.orbb200_search_by_projection_sim3(self._h, items, C.byref(fv), C.byref(pv), R.ctypes.data, t.ctypes.data, Ow.ctypes.data,
+                                                        K.ctypes.data, sf.ctypes.data, len(sf), float(ws[0]["log_scale"]), bnd.ctypes.data,
+                                                        int(th), mt.ctypes.data, cnt.ctypes.data, 0))
+        return cnt, [mt[i, :nk[i]] for i in range(items)]
+
     # ---- SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (S/ORBmatcher.cc:1106-1330), scope row N3 ----
     def search_by_sim3_batch(self, ws, bounds, th=7.5):
         """ws: list of workloads.sim3_pair()-layout dicts (leg1 / leg2 in fuse_frame layout, sR21, t21, R12 (= sR12), t12).

@@ -11,6 +11,7 @@
 //                                                         runs on the device, the replace-or-add surgery stays here)
 //   Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)         (replaces S/ORBmatcher.cc:979-1104; same split)
 //   SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (replaces S/ORBmatcher.cc:1106-1330)
+//   SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (replaces S/ORBmatcher.cc:294-407)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
 // so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
 // their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
@@ -706,6 +707,42 @@ int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoin
         if (idx2 >= 0 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
     }
     return nFound;
+}
+
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th)
+{
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);                                  // :303-308, on the host as before
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+
+    const int nPoints = (int)vpPoints.size(), nk = pKF->N;
+    if (nPoints == 0 || nk == 0) return 0;
+    orbb200_matcher* h = tlsMatcher.get(nPoints > nk ? nPoints : nk);
+    if (!h) return 0;
+    std::vector<unsigned char> admit(nPoints);
+    for (int i = 0; i < nPoints; i++) admit[i] = (!vpPoints[i]->isBad() && !spAlreadyFound.count(vpPoints[i])) ? 1 : 0;   // :320-321
+    KeyFrameKeys keys(pKF);
+    PointSoA pts(vpPoints, admit);
+    std::vector<int32_t> matched(keys.view.stride, -1);
+    for (int i = 0; i < nk; i++) if (vpMatched[i]) matched[i] = -2;                    // occupied by an earlier match (:366)
+    const std::vector<int32_t> before(matched);
+    float R9[9], t3[3], O3[3], bounds[4];
+    Flatten3x3(Rcw, R9); Flatten3(tcw, t3); Flatten3(Ow, O3);
+    FrameBounds(bounds);
+    const float K[4] = {pKF->fx, pKF->fy, pKF->cx, pKF->cy};
+    int32_t nmatches = 0;
+    if (orbb200_search_by_projection_sim3(h, 1, &keys.view, &pts.view, R9, t3, O3, K, &pKF->mvScaleFactors[0], (int)pKF->mvScaleFactors.size(),
+                                          pKF->mfLogScaleFactor, bounds, th, &matched[0], &nmatches, 0) != ORBB200_OK) {
+        std::fprintf(stderr, "ORBmatcher(B200)::SearchByProjection(Scw): %s\n", orbb200_last_error());
+        return 0;
+    }
+    for (int i = 0; i < nk; i++)
+        if (matched[i] != before[i] && matched[i] >= 0) vpMatched[i] = vpPoints[matched[i]];      // :385
+    return nmatches;
 }
 
 }  // namespace ORB_SLAM2
