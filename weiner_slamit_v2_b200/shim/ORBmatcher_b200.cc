@@ -1,4 +1,4 @@
-// ORBmatcher_b200.cc -- B200 bodies for the three in-scope methods of ORB_SLAM2::ORBmatcher:
+// ORBmatcher_b200.cc -- B200 bodies for the search routines of ORB_SLAM2::ORBmatcher (the three core ones first):
 //   DescriptorDistance                                   (replaces S/ORBmatcher.cc:1651-1667)
 //   SearchForInitialization                              (replaces S/ORBmatcher.cc:409-524)
 //   SearchByProjection(Frame&, vector<MapPoint*>&, th)   (replaces S/ORBmatcher.cc:47-131)
@@ -13,9 +13,8 @@
 //   SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (replaces S/ORBmatcher.cc:1106-1330)
 //   SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (replaces S/ORBmatcher.cc:294-407)
 // It compiles against the reference's own, unmodified headers (ORBmatcher.h, Frame.h, MapPoint.h),
-// so Tracking.cc:799-800 and :1451-1462 call it unchanged.  The other ORBmatcher methods keep
-// their reference bodies: build ORBmatcher.cc with -DORB_B200_MATCHER and guard the three
-// replaced bodies with #ifndef ORB_B200_MATCHER.
+// so Tracking.cc, LocalMapping.cc and LoopClosing.cc call them unchanged: build ORBmatcher.cc with
+// -DORB_B200_MATCHER and guard the replaced bodies with #ifndef ORB_B200_MATCHER.
 // The pointer graph is flattened to structure-of-arrays on the host, the search runs in CUDA
 // through include/orb_b200.h, and the results are written back into the fields the reference
 // mutates.  No CPU search path exists here; on a device error the call logs and reports 0 matches.
