@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
 // FAST_TPW / FAST_TH are compile-time so every ring load is `base + immediate`:
 //   <24,42> covers cells up to 39 x 36 px (every level of the 640x480 ... 1920x1080 pyramids),
 //   <36,64> covers the largest possible cell (57 x 57).
-constexpr int FAST_WARPS = 2;     // cells per CTA; the warps of a CTA never synchronise with each other
+constexpr int FAST_WARPS = 1;     // cells per CTA (measured: 1 -> 0.749 ms, 2 -> 0.762, 4 -> 0.779 per 256 frames); warps never synchronise with each other
 
 template <int TPW, int TH>
 struct FastGeo {
@@ -888,6 +888,39 @@ constexpr PatternTable make_pattern_table()
 }
 __device__ const PatternTable d_pattern = make_pattern_table();
 
+// IC_Angle weights.  The radius-15 disc is read as 8 aligned-shifted words per row (columns u = -16 .. 15), four rows
+// per warp step: in step `it` lane L owns word j = L & 7 of row v = -15 + 4*it + (L >> 3).  Its two weight words hold,
+// per byte, u (inside the disc, else 0) and v (inside, else 0), so the moments are two IDP.4A per lane and step.
+struct AngleTable { uint2 w[8][32]; };
+constexpr int UMAX_SRC[HALF_PATCH + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+constexpr AngleTable make_angle_table()
+{
+    AngleTable t{};
+    for (int it = 0; it < 8; it++)
+        for (int L = 0; L < 32; L++) {
+            const int v = -HALF_PATCH + 4 * it + (L >> 3), j = L & 7;
+            unsigned wu = 0, wv = 0;
+            for (int b = 0; b < 4; b++) {
+                const int u = -16 + 4 * j + b;
+                const int au = u < 0 ? -u : u, av = v < 0 ? -v : v;
+                if (av <= HALF_PATCH && au <= HALF_PATCH && au <= UMAX_SRC[av]) {
+                    wu |= (unsigned)(u & 0xff) << (8 * b);
+                    wv |= (unsigned)(v & 0xff) << (8 * b);
+                }
+            }
+            t.w[it][L].x = wu; t.w[it][L].y = wv;
+        }
+    return t;
+}
+__device__ const AngleTable d_angle = make_angle_table();
+
+__device__ __forceinline__ int dp4a_u8s8(uint32_t pixels, uint32_t weights, int acc)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pixels), "r"(weights), "r"(acc));
+    return d;
+}
+
 // cv::fastAtan2: every step is a separately rounded fp32 operation (no FMA contraction).
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 {
@@ -987,16 +1020,22 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParam
     int pitch;
     const uint8_t* c = level_ptr(P, l, frame, pitch);
     c += (long long)y * pitch + x;
-    const int u = lane - HALF_PATCH;
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
+    {
+        // aligned words around columns x-16 .. x+15 (the level's pitch is a multiple of 4, so one shift serves all rows)
+        const uint8_t* row0 = c - 16 + (long long)(-HALF_PATCH + (lane >> 3)) * pitch;
+        const int sh = (int)(reinterpret_cast<uintptr_t>(row0) & 3);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(row0 - sh) + (lane & 7);
+        const long long step = (long long)pitch;               // 4 rows, in words
 #pragma unroll
-        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {         // 31 independent loads in flight
-            if (abs(u) <= c_umax[abs(v)]) {
-                const int val = __ldg(c + v * pitch + u);
-                m10 += u * val;
-                m01 += v * val;
+        for (int it = 0; it < 8; it++) {
+            const uint2 w = __ldg(&d_angle.w[it][lane]);
+            if (it < 7 || lane < 24) {                             // the last step holds rows 13, 14, 15 only
+                const uint32_t px = __funnelshift_r(__ldg(p), __ldg(p + 1), 8 * sh);
+                m10 = dp4a_u8s8(px, w.x, m10);
+                m01 = dp4a_u8s8(px, w.y, m01);
             }
+            p += step;
         }
     }
 #pragma unroll
