@@ -868,7 +868,6 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
 // ======================================================================================
 // K4+K6: IC_Angle (:82-109) and computeOrbDescriptor (:113-152), one warp per keypoint
 // ======================================================================================
-__constant__ int c_umax[HALF_PATCH + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 // The 512 pattern points, transposed and packed at compile time: entry [k*32 + b] is point 16*b + k as
 // x | y << 8.  Lane b of a warp needs point 16*b + k at step k -- 32 different addresses per access, which
 // the constant cache would serialise 32-way -- so the table lives in global memory and is read through the
