@@ -346,6 +346,28 @@ int orbb200_search_by_projection_sim3(orbb200_matcher *m, int items, const orbb2
                                       const float K[4], const float *scale_factors, int nlevels, float log_scale_factor,
                                       const float bounds[4], int th, int32_t *matched, int32_t *nmatches, int on_device);
 
+/* A DBoW2 vocabulary (ORBVocabulary = TemplatedVocabulary<cv::Mat, FORB>, TF_IDF weighting, L1 scoring -- what
+ * ORBvoc.txt declares) resident on one device, flattened: node 0 is the root; node i's children are
+ * children[child_start[i] .. child_start[i+1]) in the order of its `children` vector (for a vocabulary loaded by
+ * loadFromTextFile: ascending node id); descriptors n_nodes x 32; word_id and weight are read for leaves only;
+ * levels = m_L. */
+typedef struct orbb200_vocabulary orbb200_vocabulary;
+int orbb200_vocabulary_create(int device, int n_nodes, int levels, const int32_t *child_start, const int32_t *children,
+                              const uint8_t *descriptors, const int32_t *word_id, const double *weight,
+                              orbb200_vocabulary **out);
+void orbb200_vocabulary_destroy(orbb200_vocabulary *v);
+
+/* Replaces mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, levelsup) of Frame::ComputeBoW /
+ * KeyFrame::ComputeBoW (S/Frame.cc:520-527; Thirdparty/DBoW2 TemplatedVocabulary.h:1133-1266, BowVector.cpp:34-84;
+ * scope row N4) for `items` frames (n: features per frame, desc: items x stride x 32).
+ * BowVector: bow_n (items), bow_word / bow_value (items x stride): word ids ascending with their L1-normalised tf-idf
+ * values, bit-identical doubles.  FeatureVector: fv_n_nodes (items), fv_node_id (items x stride, ascending),
+ * fv_node_start (items x (stride+1)), fv_feat (items x stride) -- the layout orbb200_bow_view takes with
+ * node_stride = stride, so on the device the result feeds orbb200_search_by_bow directly.  stride <= 8192. */
+int orbb200_bow_transform(orbb200_matcher *m, const orbb200_vocabulary *voc, int items, const int32_t *n, const uint8_t *desc,
+                          int stride, int levelsup, int32_t *bow_n, uint32_t *bow_word, double *bow_value,
+                          int32_t *fv_n_nodes, uint32_t *fv_node_id, int32_t *fv_node_start, uint32_t *fv_feat, int on_device);
+
 /* ------------------------------------------------------------------------------------- */
 /* Frame glue (the "next" row N1 of the scope table): between extractor and matcher       */
 /* ------------------------------------------------------------------------------------- */

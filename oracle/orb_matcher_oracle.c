@@ -1005,3 +1005,83 @@ int orc_search_by_projection_sim3(
     free(cand); free(items);
     return nmatches;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * DBoW2 TemplatedVocabulary<cv::Mat, FORB>::transform(features, BowVector, FeatureVector, levelsup) as called by
+ * Frame::ComputeBoW (S/Frame.cc:520-527, levelsup = 4), for TF_IDF weighting and L1 scoring (what ORBvoc.txt
+ * declares): Thirdparty/DBoW2/include/DBoW2/TemplatedVocabulary.h:1133-1266, src/BowVector.cpp:34-84.
+ * Vocabulary tree flattened: node 0 = root; node i's children are children[child_start[i] .. child_start[i+1])
+ * in the order of its `children` vector; leaves have no children, a word id and a weight.
+ * Per feature the tree is descended (child with the smallest Hamming distance, first one on ties) down to a leaf;
+ * the node passed at level L - levelsup is the feature's FeatureVector node (0 = root if that level is <= 0).
+ * A word with weight w > 0 seen c times gets w added c times (addWeight), then the vector is L1-normalised with the
+ * norm accumulated in ascending word order.  Outputs: bow_word / bow_value (ascending word id, returns their count in
+ * *bow_n), fv_node (ascending) / fv_start / fv_feat (feature indices ascending inside a node), *fv_n nodes. */
+void orc_bow_transform(
+    int n_nodes, int L, const int32_t *child_start, const int32_t *children, const uint8_t *node_desc,
+    const int32_t *word_id, const double *weight,
+    int n, const uint8_t *desc, int levelsup,
+    int32_t *bow_n, uint32_t *bow_word, double *bow_value,
+    int32_t *fv_n, uint32_t *fv_node, int32_t *fv_start, uint32_t *fv_feat)
+{
+    (void)n_nodes;
+    const int nid_level = L - levelsup;
+    int32_t *w_of = (int32_t *)malloc(sizeof(int32_t) * (n + 1));      /* word per feature, -1 = stopped */
+    int32_t *n_of = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    double *wt_of = (double *)malloc(sizeof(double) * (n + 1));
+    for (int f = 0; f < n; f++) {
+        int node = 0, level = 0, nid = 0;
+        do {
+            ++level;
+            const int cs = child_start[node], ce = child_start[node + 1];
+            int best = children[cs];
+            int best_d = orc_descriptor_distance(desc + 32 * (size_t)f, node_desc + 32 * (size_t)best);
+            for (int c = cs + 1; c < ce; c++) {
+                const int id = children[c];
+                const int d = orc_descriptor_distance(desc + 32 * (size_t)f, node_desc + 32 * (size_t)id);
+                if (d < best_d) { best_d = d; best = id; }
+            }
+            node = best;
+            if (level == nid_level) nid = node;
+        } while (child_start[node + 1] > child_start[node]);
+        const double w = weight[node];
+        w_of[f] = w > 0 ? word_id[node] : -1;
+        wt_of[f] = w;
+        n_of[f] = nid;
+    }
+    /* BowVector: std::map<WordId, double> with addWeight in feature order; FeatureVector: std::map<NodeId, vector> */
+    int nb = 0, nf = 0;
+    for (int f = 0; f < n; f++) {
+        if (w_of[f] < 0) continue;
+        int p = 0;
+        while (p < nb && bow_word[p] < (uint32_t)w_of[f]) p++;
+        if (p < nb && bow_word[p] == (uint32_t)w_of[f]) bow_value[p] += wt_of[f];
+        else {
+            memmove(bow_word + p + 1, bow_word + p, sizeof(uint32_t) * (nb - p));
+            memmove(bow_value + p + 1, bow_value + p, sizeof(double) * (nb - p));
+            bow_word[p] = (uint32_t)w_of[f]; bow_value[p] = wt_of[f]; nb++;
+        }
+    }
+    /* nodes: collect distinct ascending, then fill lists in feature order */
+    for (int f = 0; f < n; f++) {
+        if (w_of[f] < 0) continue;
+        int p = 0;
+        while (p < nf && fv_node[p] < (uint32_t)n_of[f]) p++;
+        if (!(p < nf && fv_node[p] == (uint32_t)n_of[f])) {
+            memmove(fv_node + p + 1, fv_node + p, sizeof(uint32_t) * (nf - p));
+            fv_node[p] = (uint32_t)n_of[f]; nf++;
+        }
+    }
+    int pos = 0;
+    for (int k = 0; k < nf; k++) {
+        fv_start[k] = pos;
+        for (int f = 0; f < n; f++) if (w_of[f] >= 0 && (uint32_t)n_of[f] == fv_node[k]) fv_feat[pos++] = (uint32_t)f;
+    }
+    fv_start[nf] = pos;
+    double norm = 0.0;                                            /* BowVector::normalize(L1) */
+    for (int p = 0; p < nb; p++) norm += fabs(bow_value[p]);
+    if (norm > 0.0) for (int p = 0; p < nb; p++) bow_value[p] /= norm;
+    *bow_n = nb; *fv_n = nf;
+    free(wt_of); free(n_of); free(w_of);
+}

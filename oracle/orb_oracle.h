@@ -165,6 +165,12 @@ int orc_search_by_projection_sim3(
     const float Rcw[9], const float tcw[3], const float Ow[3], const float K[4],
     int n, const float *kx, const float *ky, const int32_t *koct, const uint8_t *kdesc,
     int nlevels, const float *scale_factors, float log_scale_factor, const float bounds[4], int th, int32_t *matched);
+void orc_bow_transform(
+    int n_nodes, int L, const int32_t *child_start, const int32_t *children, const uint8_t *node_desc,
+    const int32_t *word_id, const double *weight,
+    int n, const uint8_t *desc, int levelsup,
+    int32_t *bow_n, uint32_t *bow_word, double *bow_value,
+    int32_t *fv_n, uint32_t *fv_node, int32_t *fv_start, uint32_t *fv_feat);
 float orc_logf(float x);
 int orc_predict_scale(float mf_max_distance, float dist, float log_scale_factor);
 int orc_search_by_projection_keyframe(

@@ -30,6 +30,7 @@
 #define private public
 #define protected public
 #include "ORBmatcher.h"
+#include "ORBVocabulary.h"
 #undef private
 #undef protected
 
@@ -624,5 +625,37 @@ int refm_search_by_projection_sim3(
     }
     std::free(foreign);
     return cnt;
+}
+
+// DBoW2 ORBVocabulary::transform(features, BowVector, FeatureVector, levelsup) (Frame::ComputeBoW, S/Frame.cc:520-527)
+// on a vocabulary loaded by the reference's own loadFromTextFile from `path`.  Outputs flattened in map order.
+// Returns 0, or -1 if the file did not load.
+int refm_bow_transform(const char* path, int n, const uint8_t* desc, int levelsup,
+                       int32_t* bow_n, uint32_t* bow_word, double* bow_value,
+                       int32_t* fv_n, uint32_t* fv_node, int32_t* fv_start, uint32_t* fv_feat)
+{
+    static std::map<std::string, ORBVocabulary*> cache;
+    ORBVocabulary*& voc = cache[path];
+    if (!voc) {
+        voc = new ORBVocabulary();
+        if (!voc->loadFromTextFile(path)) { delete voc; voc = NULL; cache.erase(path); return -1; }
+    }
+    cv::Mat D(n > 0 ? n : 1, 32, CV_8U, (void*)desc);
+    std::vector<cv::Mat> feats;
+    for (int j = 0; j < n; j++) feats.push_back(D.row(j));                 // Converter::toDescriptorVector
+    DBoW2::BowVector bv;
+    DBoW2::FeatureVector fv;
+    voc->transform(feats, bv, fv, levelsup);
+    int k = 0;
+    for (DBoW2::BowVector::const_iterator it = bv.begin(); it != bv.end(); ++it, ++k) { bow_word[k] = it->first; bow_value[k] = it->second; }
+    *bow_n = k;
+    int a = 0, pos = 0;
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it, ++a) {
+        fv_node[a] = it->first; fv_start[a] = pos;
+        for (size_t j = 0; j < it->second.size(); j++) fv_feat[pos++] = it->second[j];
+    }
+    fv_start[a] = pos;
+    *fv_n = a;
+    return 0;
 }
 }

@@ -518,3 +518,35 @@ def _proj_sim3_call(f, w, bounds, th, valid, matched):
 def search_by_projection_sim3(w, bounds, th=10, matched=None):
     """w: workloads.fuse_frame() dict (valid == 1 = usable candidate).  Returns (nmatches, matched[n])."""
     return _proj_sim3_call(lib().orc_search_by_projection_sim3, w, bounds, th, lambda v: _b((v == 1).astype(np.uint8)), matched)
+
+
+_f64p = C.POINTER(C.c_double)
+
+
+def _bow_out(n):
+    m = max(n, 1)
+    return dict(bn=C.c_int32(0), bw=np.zeros(m, np.uint32), bv=np.zeros(m, np.float64), fn=C.c_int32(0), fnode=np.zeros(m, np.uint32),
+                fstart=np.zeros(m + 1, np.int32), ffeat=np.zeros(m, np.uint32))
+
+
+def _bow_result(o):
+    nb, nf = o["bn"].value, o["fn"].value
+    return dict(word=o["bw"][:nb].copy(), value=o["bv"][:nb].copy(), node=o["fnode"][:nf].copy(), start=o["fstart"][:nf + 1].copy(),
+                feat=o["ffeat"][:o["fstart"][nf]].copy())
+
+
+def bow_transform(voc, desc, levelsup=4):
+    """voc: workloads.synthetic_vocabulary() dict; desc: (n, 32) uint8.  Returns dict(word, value, node, start, feat)."""
+    L = lib()
+    f = L.orc_bow_transform
+    f.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _u8p, _i32p, _f64p, C.c_int, _u8p, C.c_int,
+                  C.POINTER(C.c_int32), _u32p, _f64p, C.POINTER(C.c_int32), _u32p, _i32p, _u32p]
+    f.restype = None
+    d = _b(desc).reshape(-1, 32)
+    cs, ch, nd, wi = _i(voc["child_start"]), _i(voc["children"]), _b(voc["desc"]), _i(voc["word_id"])
+    wt = np.ascontiguousarray(voc["weight"], np.float64)
+    o = _bow_out(len(d))
+    f(len(voc["parent"]), voc["L"], _ptr(cs, _i32p), _ptr(ch, _i32p), _ptr(nd, _u8p), _ptr(wi, _i32p), _ptr(wt, _f64p), len(d), _ptr(d, _u8p),
+      int(levelsup), C.byref(o["bn"]), _ptr(o["bw"], _u32p), _ptr(o["bv"], _f64p), C.byref(o["fn"]), _ptr(o["fnode"], _u32p),
+      _ptr(o["fstart"], _i32p), _ptr(o["ffeat"], _u32p))
+    return _bow_result(o)

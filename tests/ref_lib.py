@@ -295,3 +295,17 @@ def ref_search_by_projection_sim3(w, bounds, th=10, matched=None):
     """The reference's own SearchByProjection(pKF, Scw, vpPoints, vpMatched, th), Scw = [Rcw | tcw]."""
     import oracle_lib as O
     return O._proj_sim3_call(mlib().refm_search_by_projection_sim3, w, bounds, th, lambda v: v, matched)
+
+
+def ref_bow_transform(voc_path, desc, levelsup=4):
+    """The reference's own DBoW2 transform on the vocabulary its loadFromTextFile reads from voc_path."""
+    import oracle_lib as O
+    f = mlib().refm_bow_transform
+    f.argtypes = [C.c_char_p, C.c_int, _u8p, C.c_int, C.POINTER(C.c_int32), O._u32p, O._f64p, C.POINTER(C.c_int32), O._u32p, _i32p, O._u32p]
+    f.restype = C.c_int
+    d = O._b(desc).reshape(-1, 32)
+    o = O._bow_out(len(d))
+    rc = f(voc_path.encode(), len(d), O._ptr(d, _u8p), int(levelsup), C.byref(o["bn"]), O._ptr(o["bw"], O._u32p), O._ptr(o["bv"], O._f64p),
+           C.byref(o["fn"]), O._ptr(o["fnode"], O._u32p), O._ptr(o["fstart"], _i32p), O._ptr(o["ffeat"], O._u32p))
+    assert rc == 0, "the reference could not load the vocabulary"
+    return O._bow_result(o)

@@ -355,3 +355,32 @@ def test_search_by_projection_sim3_matches_oracle(th):
         p0 = np.where(np.random.default_rng(int(c[0])).random(int(c[2])) < 0.1, -2, -1).astype(np.int32)
         cc, mm = m.search_by_projection_sim3_batch([fuse_frame(int(c[0]), int(c[1]), int(c[2]))], bounds, th, [p0])
         assert cc[0] == int(g["n_%d" % i]) and np.array_equal(mm[0], g["m_%d" % i])
+
+
+def test_bow_transform_matches_oracle_and_reference_golden_vectors():
+    """Scope row N4: Frame::ComputeBoW (DBoW2 transform) for a ragged batch of frames on several vocabularies: words,
+    bit-identical L1-normalised tf-idf doubles, FeatureVector; then the vectors the reference's own DBoW2 produced."""
+    import os
+    from weiner_slamit_v2_b200.matcher import Vocabulary, bow_transform_batch
+    from weiner_slamit_v2_b200.workloads import synthetic_vocabulary, vocabulary_features
+    m = ORBmatcher(0.7, True, max_items=6, max_points=2048)
+
+    def same(a, b):
+        return all(np.array_equal(a[x], b[x]) for x in ("word", "node", "start", "feat")) and np.asarray(a["value"]).tobytes() == np.asarray(b["value"]).tobytes()
+    for vi, (k, L) in enumerate([(6, 4), (10, 3), (3, 6), (4, 2)]):
+        voc = synthetic_vocabulary(30 + vi, k, L)
+        V = Vocabulary(voc)
+        for lu in (4, 1, 10):
+            descs = [vocabulary_features(vi * 10 + j, voc, n) for j, n in enumerate([2000, 500, 1, 0, 1000, 33])]
+            res = bow_transform_batch(m, V, descs, lu)
+            for j, d in enumerate(descs):
+                assert same(res[j], O.bow_transform(voc, d, lu)), (vi, lu, j)
+        V.close()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_bow_transform.npz"))
+    for i in range(int(g["count"])):
+        vi, k, L, n, lu = (int(v) for v in g["cfg_%d" % i])
+        voc = synthetic_vocabulary(vi, k, L)
+        V = Vocabulary(voc)
+        r = bow_transform_batch(m, V, [vocabulary_features(vi, voc, n)], lu)[0]
+        assert same(r, {key: g["%s_%d" % (key, i)] for key in ("word", "value", "node", "start", "feat")})
+        V.close()

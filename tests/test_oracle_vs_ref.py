@@ -108,6 +108,7 @@ def test_distribute_octree_matches_reference_under_monotonic_allocator():
 
 # ---- matcher: oracle/_ref/libref_matcher.so = the reference's own ORBmatcher.cc + Frame.cc + MapPoint.cc ------
 needs_refm = pytest.mark.skipif(not R.matcher_available(), reason="oracle/_ref/libref_matcher.so not built")
+BOWGOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_bow_transform.npz")
 MGOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_match_*.npz")))
 
 
@@ -397,3 +398,32 @@ def test_search_by_projection_sim3_matches_reference(th):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]), idx
         tot += b[0]
     assert tot > 800
+
+
+def _same_bow(a, b):
+    return all(np.array_equal(a[x], b[x]) for x in ("word", "node", "start", "feat")) and a["value"].tobytes() == np.asarray(b["value"]).tobytes()
+
+
+@needs_refm
+def test_bow_transform_matches_reference(tmp_path):
+    """Frame::ComputeBoW's DBoW2 transform against the reference's own TemplatedVocabulary (vocabulary written in
+    ORBvoc.txt format and read back by the reference's loadFromTextFile): words, bit-identical tf-idf values, feature
+    vector; levelsup above the tree height (root node), a single feature, no features, stopped words."""
+    from weiner_slamit_v2_b200.workloads import synthetic_vocabulary, vocabulary_features, write_vocabulary_text
+    for vi, (k, L) in enumerate([(6, 4), (10, 3), (3, 6), (4, 2)]):
+        voc = synthetic_vocabulary(20 + vi, k, L)
+        path = str(tmp_path / ("voc%d.txt" % vi))
+        write_vocabulary_text(path, voc)
+        for n, lu in [(2000, 4), (500, 2), (1, 4), (0, 4), (1000, 1), (1000, 10)]:
+            d = vocabulary_features(vi * 10 + n % 7, voc, n)
+            assert _same_bow(O.bow_transform(voc, d, lu), R.ref_bow_transform(path, d, lu)), (vi, n, lu)
+
+
+def test_bow_transform_oracle_reproduces_reference_golden_vectors():
+    from weiner_slamit_v2_b200.workloads import synthetic_vocabulary, vocabulary_features
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_bow_transform.npz"))
+    for i in range(int(g["count"])):
+        vi, k, L, n, lu = (int(v) for v in g["cfg_%d" % i])
+        voc = synthetic_vocabulary(vi, k, L)
+        a = O.bow_transform(voc, vocabulary_features(vi, voc, n), lu)
+        assert _same_bow(a, {key: g["%s_%d" % (key, i)] for key in ("word", "value", "node", "start", "feat")})

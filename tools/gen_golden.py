@@ -154,3 +154,20 @@ for i, (idx, nmp, nkp, th) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_match_projsim3.npz"), **out)
 print("ref_match_projsim3.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])
+
+out = {}
+import tempfile  # noqa: E402
+from weiner_slamit_v2_b200.workloads import synthetic_vocabulary, vocabulary_features, write_vocabulary_text  # noqa: E402
+cfgs = [(0, 10, 4, 2000, 4), (1, 6, 5, 1500, 2), (2, 3, 6, 800, 4)]
+tmp = tempfile.mkdtemp()
+for i, (vi, k, L, n, lu) in enumerate(cfgs):
+    voc = synthetic_vocabulary(vi, k, L)
+    path = os.path.join(tmp, "voc%d.txt" % vi)
+    write_vocabulary_text(path, voc)
+    r = R.ref_bow_transform(path, vocabulary_features(vi, voc, n), lu)
+    out["cfg_%d" % i] = np.array([vi, k, L, n, lu])
+    for key in ("word", "value", "node", "start", "feat"):
+        out["%s_%d" % (key, i)] = r[key]
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_bow_transform.npz"), **out)
+print("ref_bow_transform.npz", [len(out["word_%d" % i]) for i in range(len(cfgs))])

@@ -106,6 +106,9 @@ SIGNATURES = {
                                       C.c_int, C.c_float, vp, C.c_float, C.c_int, vp, vp, vp, vp, C.c_int]),
     "orbb200_search_by_projection_sim3": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), C.POINTER(FusePointsView), vp, vp, vp, vp, vp,
                                                     C.c_int, C.c_float, vp, C.c_int, vp, vp, C.c_int]),
+    "orbb200_vocabulary_create": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    "orbb200_vocabulary_destroy": (None, [vp]),
+    "orbb200_bow_transform": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int]),
     "orbb200_frames_from_keypoints": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),

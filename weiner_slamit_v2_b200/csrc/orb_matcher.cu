@@ -1368,6 +1368,144 @@ __global__ void __launch_bounds__(128) k_fuse_search(const FuseParams P)
     if (P.bestDist) P.bestDist[lo] = bestDist;
 }
 
+// ---- DBoW2 transform (Frame::ComputeBoW, S/Frame.cc:520-527; TemplatedVocabulary.h:1133-1266) -------------------
+// Phase 1, one thread per descriptor: descend the vocabulary tree (child with the smallest Hamming distance, first on
+// ties) to a leaf, remembering the node passed at level L - levelsup.  The tree (a few MB to ~35 MB of node
+// descriptors) stays L2-resident.  Phase 2, one CTA per frame: two shared-memory bitonic sorts of (id << 32 | feature)
+// give the std::map orders of the BowVector (by word) and the FeatureVector (by node); a word seen c times gets its
+// weight added c times as addWeight does, and the L1 norm is accumulated in ascending word order by one thread,
+// because the reference's double additions are order dependent.
+struct VocDev { const int* childStart; const int* children; const uint4* desc; const int* wordId; const double* weight; int nNodes, L; };
+
+__global__ void __launch_bounds__(128) k_bow_descend(const VocDev V, const int* __restrict__ n, const uint8_t* __restrict__ desc, int stride,
+                                                     int levelsup, int* __restrict__ leafOf, int* __restrict__ nodeOf)
+{
+    const int item = blockIdx.y, f = blockIdx.x * 128 + threadIdx.x;
+    if (f >= min(n[item], stride)) return;
+    const uint4* d = reinterpret_cast<const uint4*>(desc + ((size_t)item * stride + f) * 32);
+    const uint4 a0 = __ldg(d), a1 = __ldg(d + 1);
+    const int nidLevel = V.L - levelsup;
+    int node = 0, level = 0, nid = 0;
+    int cs = V.childStart[0], ce = V.childStart[1];
+    do {
+        ++level;
+        int best = V.children[cs];
+        int bestD = hamming256(a0, a1, __ldg(V.desc + 2 * best), __ldg(V.desc + 2 * best + 1));
+        for (int c = cs + 1; c < ce; c++) {
+            const int id = V.children[c];
+            const int dd = hamming256(a0, a1, __ldg(V.desc + 2 * id), __ldg(V.desc + 2 * id + 1));
+            if (dd < bestD) { bestD = dd; best = id; }
+        }
+        node = best;
+        if (level == nidLevel) nid = node;
+        cs = V.childStart[node]; ce = V.childStart[node + 1];
+    } while (ce > cs && level < 64);
+    const size_t o = (size_t)item * stride + f;
+    leafOf[o] = V.weight[node] > 0 ? node : -1;                        // stopped words (weight 0) drop out (:1164)
+    nodeOf[o] = nid;
+}
+
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long* key, int P)
+{
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = key[i], b = key[ixj];
+                    if (((i & k) == 0) == (a > b)) { key[i] = b; key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// exclusive rank of every run start among the first `nvalid` sorted keys; returns the number of runs (to all threads)
+__device__ __forceinline__ int block_run_ranks(const unsigned long long* key, int nvalid, int* rank, int* scratch)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (nvalid + nt - 1) / nt, beg = min(tid * per, nvalid), end = min(beg + per, nvalid);
+    int local = 0;
+    for (int p = beg; p < end; p++) local += (p == 0 || (key[p] >> 32) != (key[p - 1] >> 32));
+    scratch[tid] = local;
+    __syncthreads();
+    if (tid == 0) { int acc = 0; for (int t = 0; t < nt; t++) { const int v = scratch[t]; scratch[t] = acc; acc += v; } scratch[nt] = acc; }
+    __syncthreads();
+    int r = scratch[tid];
+    for (int p = beg; p < end; p++) {
+        const bool start = (p == 0 || (key[p] >> 32) != (key[p - 1] >> 32));
+        rank[p] = start ? r : -1;
+        r += start;
+    }
+    __syncthreads();
+    return scratch[nt];
+}
+
+__global__ void __launch_bounds__(256) k_bow_assemble(const VocDev V, const int* __restrict__ n, int stride, int P,
+                                                      const int* __restrict__ leafOf, const int* __restrict__ nodeOf,
+                                                      int* __restrict__ bowN, uint32_t* __restrict__ bowWord, double* __restrict__ bowValue,
+                                                      int* __restrict__ fvN, uint32_t* __restrict__ fvNode, int* __restrict__ fvStart,
+                                                      uint32_t* __restrict__ fvFeat)
+{
+    extern __shared__ __align__(16) unsigned char bow_smem[];
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(bow_smem);       // P
+    int* rank = reinterpret_cast<int*>(key + P);                                       // P
+    int* scratch = rank + P;                                                           // blockDim.x + 1
+    __shared__ int sValid;
+    __shared__ double sNorm;
+    const int item = blockIdx.x, tid = threadIdx.x;
+    const int nf = min(n[item], stride);
+    const size_t o = (size_t)item * stride;
+    if (tid == 0) sValid = 0;
+    __syncthreads();
+
+    // ---- BowVector: sort by (word, feature)
+    int mine = 0;
+    for (int i = tid; i < P; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < nf && leafOf[o + i] >= 0) { k = ((unsigned long long)(unsigned)V.wordId[leafOf[o + i]] << 32) | (unsigned)i; mine++; }
+        key[i] = k;
+    }
+    atomicAdd(&sValid, mine);
+    __syncthreads();
+    const int nvalid = sValid;
+    block_bitonic_sort(key, P);
+    const int nb = block_run_ranks(key, nvalid, rank, scratch);
+    for (int p = tid; p < nvalid; p += blockDim.x) {
+        if (rank[p] < 0) continue;
+        int c = 1;
+        while (p + c < nvalid && (key[p + c] >> 32) == (key[p] >> 32)) c++;
+        const double w = V.weight[leafOf[o + (unsigned)(key[p] & 0xffffffffu)]];
+        double v = w;
+        for (int q = 1; q < c; q++) v = __dadd_rn(v, w);                                // addWeight, once per occurrence
+        bowWord[o + rank[p]] = (uint32_t)(key[p] >> 32);
+        bowValue[o + rank[p]] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {                                                                    // BowVector::normalize(L1), in map order
+        double norm = 0.0;
+        for (int q = 0; q < nb; q++) norm = __dadd_rn(norm, fabs(bowValue[o + q]));
+        sNorm = norm;
+        bowN[item] = nb;
+    }
+    __syncthreads();
+    if (sNorm > 0.0) for (int q = tid; q < nb; q += blockDim.x) bowValue[o + q] = __ddiv_rn(bowValue[o + q], sNorm);
+    __syncthreads();
+
+    // ---- FeatureVector: sort by (node, feature)
+    for (int i = tid; i < P; i += blockDim.x)
+        key[i] = (i < nf && leafOf[o + i] >= 0) ? (((unsigned long long)(unsigned)nodeOf[o + i] << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    block_bitonic_sort(key, P);
+    const int nn = block_run_ranks(key, nvalid, rank, scratch);
+    int* st = fvStart + (size_t)item * (stride + 1);
+    for (int p = tid; p < nvalid; p += blockDim.x) {
+        fvFeat[o + p] = (uint32_t)(key[p] & 0xffffffffu);
+        if (rank[p] >= 0) { fvNode[o + rank[p]] = (uint32_t)(key[p] >> 32); st[rank[p]] = p; }
+    }
+    if (tid == 0) { st[nn] = nvalid; fvN[item] = nn; }
+}
+
 }  // namespace orbb200
 
 // =========================================================================================
@@ -2072,6 +2210,104 @@ extern "C" int orbb200_search_by_projection_sim3(orbb200_matcher* m, int items, 
     if (!on_device) {
         ORB_CUDA(cudaMemcpyAsync(matched, P.kpMp, np * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaMemcpyAsync(nmatches, dN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ORBB200_OK;
+}
+
+struct orbb200_vocabulary {
+    int device;
+    VocDev V;
+    std::vector<void*> allocs;
+};
+
+extern "C" void orbb200_vocabulary_destroy(orbb200_vocabulary* v)
+{
+    if (!v) return;
+    cudaSetDevice(v->device);
+    for (void* p : v->allocs) cudaFree(p);
+    delete v;
+}
+
+extern "C" int orbb200_vocabulary_create(int device, int n_nodes, int levels, const int32_t* child_start, const int32_t* children,
+                                         const uint8_t* descriptors, const int32_t* word_id, const double* weight,
+                                         orbb200_vocabulary** out)
+{
+    if (!out || !child_start || !children || !descriptors || !word_id || !weight || n_nodes < 2 || levels < 1 || levels > 32) { set_error("invalid vocabulary"); return ORBB200_EINVAL; }
+    *out = nullptr;
+    if (child_start[0] != 0 || child_start[1] <= 0) { set_error("the root (node 0) needs children"); return ORBB200_EINVAL; }
+    for (int i = 0; i < n_nodes; i++)
+        if (child_start[i + 1] < child_start[i]) { set_error("child_start must ascend"); return ORBB200_EINVAL; }
+    const int nc = child_start[n_nodes];
+    for (int c = 0; c < nc; c++)
+        if (children[c] <= 0 || children[c] >= n_nodes) { set_error("child id out of range"); return ORBB200_EINVAL; }
+    int ndev = orbb200_device_count();
+    if (device < 0 || device >= ndev) { set_error("CUDA device %d not available (%d visible)", device, ndev); return ORBB200_ENODEVICE; }
+    ORB_CUDA(cudaSetDevice(device));
+    orbb200_vocabulary* v = new orbb200_vocabulary();
+    v->device = device;
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(bytes, 256)) != cudaSuccess) { set_error("cudaMalloc failed"); return ORBB200_ECUDA; }
+        v->allocs.push_back(p);
+        if (cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("cudaMemcpy failed"); return ORBB200_ECUDA; }
+        *dst = p;
+        return ORBB200_OK;
+    };
+    int rc;
+    if ((rc = up(child_start, sizeof(int32_t) * ((size_t)n_nodes + 1), (const void**)&v->V.childStart)) ||
+        (rc = up(children, sizeof(int32_t) * (size_t)std::max(nc, 1), (const void**)&v->V.children)) ||
+        (rc = up(descriptors, (size_t)n_nodes * 32, (const void**)&v->V.desc)) ||
+        (rc = up(word_id, sizeof(int32_t) * (size_t)n_nodes, (const void**)&v->V.wordId)) ||
+        (rc = up(weight, sizeof(double) * (size_t)n_nodes, (const void**)&v->V.weight))) { orbb200_vocabulary_destroy(v); return rc; }
+    v->V.nNodes = n_nodes; v->V.L = levels;
+    *out = v;
+    return ORBB200_OK;
+}
+
+extern "C" int orbb200_bow_transform(orbb200_matcher* m, const orbb200_vocabulary* voc, int items, const int32_t* n, const uint8_t* desc,
+                                     int stride, int levelsup, int32_t* bow_n, uint32_t* bow_word, double* bow_value, int32_t* fv_n_nodes,
+                                     uint32_t* fv_node_id, int32_t* fv_node_start, uint32_t* fv_feat, int on_device)
+{
+    if (!m || !voc || !n || !desc || !bow_n || !bow_word || !bow_value || !fv_n_nodes || !fv_node_id || !fv_node_start || !fv_feat) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (voc->device != m->device) { set_error("vocabulary and matcher live on different devices"); return ORBB200_EINVAL; }
+    int rc;
+    if ((rc = check_view(m, items, stride, "frame"))) return rc;
+    if (stride > 8192) { set_error("more than 8192 features per frame"); return ORBB200_ECAPACITY; }
+    ORB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    const size_t np = (size_t)items * stride;
+    Stager s{m, 0, st};
+    const int* dN = n; const uint8_t* dDesc = desc;
+    int *dBowN = bow_n, *dFvN = fv_n_nodes, *dFvStart = fv_node_start;
+    uint32_t *dBowWord = bow_word, *dFvNode = fv_node_id, *dFvFeat = fv_feat;
+    double* dBowValue = bow_value;
+    if (!on_device) {
+        if ((rc = s.reserve(pad((size_t)items * 4) + pad(np * 32) + 2 * pad((size_t)items * 4) + 3 * pad(np * 4) + pad(np * 8) + pad(((size_t)items * (stride + 1)) * 4)))) return rc;
+        if ((rc = s.up(n, items, &dN)) || (rc = s.up(desc, np * 32, &dDesc))) return rc;
+        dBowN = s.out<int>(items); dFvN = s.out<int>(items);
+        dBowWord = s.out<uint32_t>(np); dFvNode = s.out<uint32_t>(np); dFvFeat = s.out<uint32_t>(np);
+        dBowValue = s.out<double>(np);
+        dFvStart = s.out<int>((size_t)items * (stride + 1));
+    }
+    int* leafOf = m->scratchA; int* nodeOf = m->scratchB;
+    k_bow_descend<<<dim3((stride + 127) / 128, items), 128, 0, st>>>(voc->V, dN, dDesc, stride, levelsup, leafOf, nodeOf);
+    ORB_CHECK_LAUNCH("k_bow_descend");
+    int P = 32;
+    while (P < stride) P <<= 1;
+    const size_t sm = (size_t)P * 12 + 257 * 4 + 16;
+    if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_bow_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_bow_assemble<<<items, 256, sm, st>>>(voc->V, dN, stride, P, leafOf, nodeOf, dBowN, dBowWord, dBowValue, dFvN, dFvNode, dFvStart, dFvFeat);
+    ORB_CHECK_LAUNCH("k_bow_assemble");
+    m->lastLaunches = 2;
+    if (!on_device) {
+        ORB_CUDA(cudaMemcpyAsync(bow_n, dBowN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(fv_n_nodes, dFvN, (size_t)items * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(bow_word, dBowWord, np * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(bow_value, dBowValue, np * 8, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(fv_node_id, dFvNode, np * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(fv_node_start, dFvStart, (size_t)items * (stride + 1) * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(fv_feat, dFvFeat, np * 4, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
     }
     return ORBB200_OK;

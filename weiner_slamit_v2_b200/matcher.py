@@ -445,3 +445,49 @@ class ORBmatcher:
         for i, f in enumerate(cur_frames):
             f.mvpMapPoints[:] = kpmp[i, :f.N]
         return nm
+
+
+class Vocabulary:
+    """A DBoW2 vocabulary tree on the device (include/orb_b200.h, orbb200_vocabulary_create).  voc: dict with child_start,
+    children, desc (n_nodes, 32), word_id, weight (float64), L -- workloads.synthetic_vocabulary() layout; a vocabulary
+    read from ORBvoc.txt flattens the same way (node id = line number, children in file order)."""
+
+    def __init__(self, voc, device=0):
+        self._L = _lib.load()
+        self._h = _lib.vp()
+        self.device = device
+        cs = np.ascontiguousarray(voc["child_start"], np.int32); ch = np.ascontiguousarray(voc["children"], np.int32)
+        d = np.ascontiguousarray(voc["desc"], np.uint8); wi = np.ascontiguousarray(voc["word_id"], np.int32)
+        wt = np.ascontiguousarray(voc["weight"], np.float64)
+        check(self._L.orbb200_vocabulary_create(device, len(wi), int(voc["L"]), cs.ctypes.data, ch.ctypes.data, d.ctypes.data,
+                                                wi.ctypes.data, wt.ctypes.data, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._L.orbb200_vocabulary_destroy(self._h)
+            self._h = _lib.vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def bow_transform_batch(matcher, vocabulary, descs, levelsup=4):
+    """Frame::ComputeBoW for a list of (n_i, 32) uint8 descriptor arrays.  Returns a list of dicts
+    (word, value, node, start, feat) -- BowVector and flattened FeatureVector per frame."""
+    items = len(descs)
+    n = np.array([len(d) for d in descs], np.int32)
+    s = max(1, int(n.max()))
+    matcher._ensure(items, s)
+    dd = _pack([np.asarray(d, np.uint8).reshape(-1, 32) for d in descs], s, np.uint8, (32,))
+    bn, fn = np.zeros(items, np.int32), np.zeros(items, np.int32)
+    bw, fnode, ffeat = (np.zeros((items, s), np.uint32) for _ in range(3))
+    bv = np.zeros((items, s), np.float64)
+    fstart = np.zeros((items, s + 1), np.int32)
+    check(matcher._L.orbb200_bow_transform(matcher._h, vocabulary._h, items, n.ctypes.data, dd.ctypes.data, s, int(levelsup), bn.ctypes.data,
+                                           bw.ctypes.data, bv.ctypes.data, fn.ctypes.data, fnode.ctypes.data, fstart.ctypes.data,
+                                           ffeat.ctypes.data, 0))
+    return [dict(word=bw[i, :bn[i]], value=bv[i, :bn[i]], node=fnode[i, :fn[i]], start=fstart[i, :fn[i] + 1], feat=ffeat[i, :fstart[i, fn[i]]])
+            for i in range(items)]

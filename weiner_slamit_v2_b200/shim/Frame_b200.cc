@@ -1,11 +1,15 @@
-// Frame_b200.cc -- B200 bodies for the two Frame methods of the "next" row N1:
+// Frame_b200.cc -- B200 bodies for three Frame methods:
 //   Frame::UndistortKeyPoints   (replaces S/Frame.cc:529-559)
 //   Frame::ComputeImageBounds   (replaces S/Frame.cc:561-589)
+//   Frame::ComputeBoW           (replaces S/Frame.cc:520-527: the DBoW2 transform runs on the device)
 // Compiles against the reference's own Frame.h; guard the two reference bodies with
 // #ifndef ORB_B200_FRAME and add this file.  cv::undistortPoints runs on the device.
 #include "Frame.h"
 
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "orb_b200.h"
@@ -69,6 +73,72 @@ void Frame::ComputeImageBounds(const cv::Mat& imLeft)
     if (!h || orbb200_image_bounds(h, imLeft.cols, imLeft.rows, k, d, b) != ORBB200_OK)
         std::fprintf(stderr, "Frame(B200)::ComputeImageBounds: %s\n", orbb200_last_error());
     mnMinX = b[0]; mnMinY = b[1]; mnMaxX = b[2]; mnMaxY = b[3];
+}
+
+namespace
+{
+// The vocabulary tree lives in protected members of TemplatedVocabulary; a derived class may name them, and the
+// pointers to members it forms are plain `T TemplatedVocabulary::*` values (no object of this type is ever created).
+struct VocabularyFields : public ORBVocabulary {
+    typedef std::vector<Node> Nodes;
+    static Nodes ORBVocabulary::* NodesMember() { return &VocabularyFields::m_nodes; }
+    static int ORBVocabulary::* LevelsMember() { return &VocabularyFields::m_L; }
+    static orbb200_vocabulary* Upload(const ORBVocabulary* voc)
+    {
+        const Nodes& nodes = voc->*NodesMember();
+        const int n = (int)nodes.size();
+        std::vector<int32_t> childStart(n + 1, 0), children, wordId(n, -1);
+        std::vector<unsigned char> desc((size_t)n * 32, 0);
+        std::vector<double> weight(n, 0.0);
+        for (int i = 0; i < n; i++) {
+            childStart[i] = (int32_t)children.size();
+            for (size_t c = 0; c < nodes[i].children.size(); c++) children.push_back((int32_t)nodes[i].children[c]);
+            if (!nodes[i].descriptor.empty()) std::memcpy(&desc[(size_t)i * 32], nodes[i].descriptor.ptr<unsigned char>(), 32);
+            if (nodes[i].children.empty()) { wordId[i] = (int32_t)nodes[i].word_id; weight[i] = nodes[i].weight; }
+        }
+        childStart[n] = (int32_t)children.size();
+        if (children.empty()) children.push_back(0);
+        orbb200_vocabulary* h = 0;
+        if (orbb200_vocabulary_create(0, n, voc->*LevelsMember(), &childStart[0], &children[0], &desc[0], &wordId[0], &weight[0], &h) != ORBB200_OK) {
+            std::fprintf(stderr, "Frame(B200): vocabulary upload: %s\n", orbb200_last_error());
+            return 0;
+        }
+        return h;
+    }
+};
+
+// one device copy per vocabulary object, made on first use (System loads the vocabulary once, S/System.cc:70-85)
+orbb200_vocabulary* DeviceVocabulary(const ORBVocabulary* voc)
+{
+    static std::mutex mtx;
+    static std::map<const ORBVocabulary*, orbb200_vocabulary*> cache;
+    std::unique_lock<std::mutex> lock(mtx);
+    std::map<const ORBVocabulary*, orbb200_vocabulary*>::iterator it = cache.find(voc);
+    if (it != cache.end()) return it->second;
+    return cache[voc] = VocabularyFields::Upload(voc);
+}
+}  // namespace
+
+void Frame::ComputeBoW()
+{
+    if (!mBowVec.empty()) return;
+    orbb200_matcher* h = tlsHandle.get();
+    orbb200_vocabulary* voc = mpORBvocabulary ? DeviceVocabulary(mpORBvocabulary) : 0;
+    const int n = mDescriptors.rows;
+    if (!h || !voc || n == 0) return;
+    std::vector<unsigned char> desc((size_t)n * 32);
+    for (int j = 0; j < n; j++) std::memcpy(&desc[(size_t)j * 32], mDescriptors.ptr<unsigned char>(j), 32);   // Converter::toDescriptorVector
+    int32_t nn = n, bowN = 0, fvN = 0;
+    std::vector<uint32_t> word(n), node(n), feat(n);
+    std::vector<double> value(n);
+    std::vector<int32_t> start(n + 1);
+    if (orbb200_bow_transform(h, voc, 1, &nn, &desc[0], n, 4, &bowN, &word[0], &value[0], &fvN, &node[0], &start[0], &feat[0], 0) != ORBB200_OK) {
+        std::fprintf(stderr, "Frame(B200)::ComputeBoW: %s\n", orbb200_last_error());
+        return;
+    }
+    for (int k = 0; k < bowN; k++) mBowVec.insert(mBowVec.end(), DBoW2::BowVector::value_type(word[k], value[k]));
+    for (int a = 0; a < fvN; a++)
+        for (int p = start[a]; p < start[a + 1]; p++) mFeatVec.addFeature(node[a], feat[p]);
 }
 
 }  // namespace ORB_SLAM2

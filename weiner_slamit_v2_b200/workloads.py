@@ -395,3 +395,57 @@ def sim3_pair(index, n1=1500, n2=1500, width=640, height=480, nlevels=8, scale=1
     leg1 = dict(common, **{k: a[k] for k in ("valid", "wpos", "normal", "mp_desc", "mf_max", "mf_min", "Rcw", "tcw")}, kp=b["kp"], kdesc=b["kdesc"], u_right=b["u_right"])
     leg2 = dict(common, **{k: b[k] for k in ("valid", "wpos", "normal", "mp_desc", "mf_max", "mf_min", "Rcw", "tcw")}, kp=a["kp"], kdesc=a["kdesc"], u_right=a["u_right"])
     return dict(k1=a, k2=b, leg1=leg1, leg2=leg2, R12=R12.reshape(9), t12=t12, sR21=sR21.reshape(9), t21=t21, common=common)
+
+
+def synthetic_vocabulary(index, k=6, L=4, stopped=0.05):
+    """A DBoW2 vocabulary tree in the flattened form of include/orb_b200.h (orbb200_vocabulary_create): breadth-first
+    node numbering exactly as TemplatedVocabulary::loadFromTextFile assigns it when the nodes are written in this
+    order (node id = line number, word id = running count of leaves).  Inner nodes have 2..k children whose
+    descriptors are the parent's with some bits flipped; all leaves sit at level L; a few words are stopped (weight 0)."""
+    rng = np.random.default_rng(190000 + index)
+    parent, level, desc = [0], [0], [np.zeros(32, np.uint8)]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for pnode in frontier:
+            nch = int(rng.integers(2, k + 1))
+            base = desc[pnode] if pnode else rng.integers(0, 256, 32).astype(np.uint8)
+            for _ in range(nch):
+                d = flip_bits((rng.integers(0, 256, (1, 32)).astype(np.uint8) if pnode == 0 else base[None]), np.array([int(rng.integers(20, 70))]), rng)[0]
+                parent.append(pnode); level.append(lv); desc.append(d); nxt.append(len(parent) - 1)
+        frontier = nxt
+    n = len(parent)
+    parent = np.array(parent, np.int32); level = np.array(level, np.int32)
+    is_leaf = level == L
+    children = [[] for _ in range(n)]
+    for i in range(1, n):
+        children[parent[i]].append(i)
+    child_start = np.zeros(n + 1, np.int32)
+    child_start[1:] = np.cumsum([len(c) for c in children])
+    child_list = np.array([c for cs in children for c in cs], np.int32)
+    word_id = np.full(n, -1, np.int32)
+    word_id[is_leaf] = np.arange(int(is_leaf.sum()))
+    weight = np.zeros(n, np.float64)
+    weight[is_leaf] = np.round(rng.uniform(0.5, 9.0, int(is_leaf.sum())), 6)
+    weight[is_leaf & (rng.random(n) < stopped)] = 0.0
+    return dict(k=k, L=L, parent=parent, is_leaf=is_leaf, child_start=child_start, children=child_list,
+                desc=np.stack(desc).astype(np.uint8), word_id=word_id, weight=weight)
+
+
+def write_vocabulary_text(path, voc):
+    """ORBvoc.txt format (TemplatedVocabulary::saveToTextFile): header "k L scoring weighting" (0 0 = L1_NORM, TF_IDF),
+    then one line per node "parent isLeaf d0 .. d31 weight".  No trailing newline: the reference's loader would turn
+    one into an extra, empty child of the root."""
+    lines = ["%d %d 0 0" % (voc["k"], voc["L"])]
+    for i in range(1, len(voc["parent"])):
+        lines.append("%d %d %s %.6f" % (voc["parent"][i], int(voc["is_leaf"][i]), " ".join(str(int(b)) for b in voc["desc"][i]), voc["weight"][i]))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+def vocabulary_features(index, voc, n):
+    """n descriptors near random leaves of the vocabulary (so that the descent is not trivial)."""
+    rng = np.random.default_rng(191000 + index)
+    leaves = np.nonzero(voc["is_leaf"])[0]
+    pick = leaves[rng.integers(0, len(leaves), n)] if n else np.zeros(0, np.int64)
+    return flip_bits(voc["desc"][pick], rng.integers(0, 60, n), rng) if n else np.zeros((0, 32), np.uint8)
