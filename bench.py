@@ -165,7 +165,26 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+def _bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the page-locked frame and result buffers of
+    the end-to-end leg are allocated on that socket (with 8 ranks the uploads otherwise cross the socket link)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass                                   # affinity is an optimisation of the host side only
 
 
 # --------------------------------------------------------------------------------------------
@@ -183,6 +202,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the extractor has no CPU fallback")
     torch.cuda.set_device(local)
+    _bind_to_gpu_numa_node(local)            # before any pinned allocation: first touch puts the host buffers next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -329,7 +349,7 @@ def run_ours(args):
             fps, kind, _ = cpu_extract_fps(frames[:sample], threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                                     "sample": "%d of the 256 frames of one step, %d host threads" % (sample, threads)}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -546,6 +566,27 @@ def run_matching(local, steps):
                                                                        bestd.ctypes.data, None, 0)), 3)
     out["distinctive_descriptors"] = {"workload": "100000 map points with 2..39 observations each (%d descriptors), host buffers" % int(off[-1]),
                                       "ms_per_call": ms, "map_points_per_s": 100000 / ms * 1e3}
+    # ---- scope row N4: Frame::ComputeBoW (DBoW2 transform), descriptors and outputs resident in HBM
+    from weiner_slamit_v2_b200.matcher import Vocabulary
+    from weiner_slamit_v2_b200.workloads import synthetic_vocabulary, vocabulary_features
+    voc = synthetic_vocabulary(0, 10, 5)
+    V = Vocabulary(voc, device=local)
+    nfb = 2000
+    dfeat = up(tile(np.stack([vocabulary_features(i, voc, nfb) for i in range(distinct)]), items))
+    nb_ = up(np.full(items, nfb, np.int32))
+    o_i = [torch.empty(items, dtype=torch.int32, device=dev) for _ in range(2)]
+    o_u = [torch.empty((items, nfb), dtype=torch.int32, device=dev) for _ in range(3)]
+    o_d = torch.empty((items, nfb), dtype=torch.float64, device=dev)
+    o_s = torch.empty((items, nfb + 1), dtype=torch.int32, device=dev)
+    def bowt_step():
+        check(L.orbb200_bow_transform(h, V._h, items, nb_.data_ptr(), dfeat.data_ptr(), nfb, 4, o_i[0].data_ptr(), o_u[0].data_ptr(),
+                                      o_d.data_ptr(), o_i[1].data_ptr(), o_u[1].data_ptr(), o_s.data_ptr(), o_u[2].data_ptr(), 1))
+    ms = timed(L.orbb200_matcher_stream(h), bowt_step, steps)
+    out["bow_transform"] = {
+        "workload": "512 frames x 2000 descriptors through a synthetic vocabulary (%d nodes, k <= 10, L = 5), levelsup 4" % len(voc["parent"]),
+        "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "descriptors_per_s": items * nfb / ms * 1e3,
+        "words": int(o_i[0].sum()), "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    V.close()
     mm.close()
     L.orbb200_matcher_destroy(h)
     return out
@@ -589,6 +630,25 @@ def _traffic(stage):
     return None
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner ...) is sent to
+    stderr by pointing fd 1 at fd 2 for the run; _emit() writes the result to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -609,6 +669,8 @@ def main():
         ALG_BYTES = {"pyramid": 2781331 + 1931488, "fast": 2853088 + 160000, "quadtree": 160000 + 32000,
                      "blur": 5706176, "describe": 1498000 + 1024000 + 120000}
         args.no_matching = True
+    if not (args.gpus > 1 and "WORLD_SIZE" not in os.environ):
+        _quiet_stdout()                           # (the torchrun re-launch below passes the children's stdout through)
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
