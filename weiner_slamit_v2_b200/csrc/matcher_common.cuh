@@ -34,6 +34,33 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// The same distance with 5 POPC instead of 8: three carry-save adders (2 LOP3 each) compress seven of the eight
+// XOR words into one "ones" and three "twos" words.  POPC issues at 16 lanes/clk/SM on sm_100a against 64 for
+// LOP3/IADD3 (tools/int_peak.cu, profiles/r2a_int_peak.json), so in a loop that does nothing but distances the
+// POPC pipe (8 x 8 cycles per warp) is the bound; this form balances it against the ALU pipe (40 / 40 cycles).
+// (inline PTX: left to itself the compiler folds the XORs into the adders and ends up with 20 LOP3 instead of 14)
+__device__ __forceinline__ uint32_t lop_xor(uint32_t a, uint32_t b)
+{
+    uint32_t r; asm("lop3.b32 %0, %1, %2, 0, 0x3c;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t csa_xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ uint32_t csa_maj3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ int hamming256_csa(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1)
+{
+    const uint32_t x0 = lop_xor(a0.x, b0.x), x1 = lop_xor(a0.y, b0.y), x2 = lop_xor(a0.z, b0.z), x3 = lop_xor(a0.w, b0.w);
+    const uint32_t x4 = lop_xor(a1.x, b1.x), x5 = lop_xor(a1.y, b1.y), x6 = lop_xor(a1.z, b1.z), x7 = lop_xor(a1.w, b1.w);
+    const uint32_t s1 = csa_xor3(x0, x1, x2), c1 = csa_maj3(x0, x1, x2);
+    const uint32_t s2 = csa_xor3(x3, x4, x5), c2 = csa_maj3(x3, x4, x5);
+    const uint32_t s3 = csa_xor3(s1, s2, x6), c3 = csa_maj3(s1, s2, x6);
+    return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+
 // Cell range of GetFeaturesInArea (S/Frame.cc:452-466); false when the query misses the grid.
 __device__ __forceinline__ bool cell_range(const GridGeo& g, float x, float y, float r, int& c0, int& c1, int& r0, int& r1)
 {

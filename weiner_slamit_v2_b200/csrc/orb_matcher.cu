@@ -101,20 +101,42 @@ struct InitParams {
 // ---- SearchForInitialization, phase A: everything that does not depend on the greedy state ----
 // One THREAD per F1 keypoint (query); the F2 keypoints are streamed through shared memory in CSR order
 // (= GetFeaturesInArea visiting order) and every lane tests the same candidate at the same time, so the
-// candidate's descriptor is one broadcast load.  A candidate that passes the static tests of
-// GetFeaturesInArea (cell range, level, window) costs 8 XOR + 8 POPC; the 4 smallest keys
-// (distance, visiting position) and the candidate count are kept per query.
-constexpr int TOPK_CHUNK = 1024;
-struct CandMeta { float x, y; int meta; };     // meta = octave | cx << 16 | cy << 24
+// candidate's descriptor is one broadcast load.  The 4 smallest keys (distance, visiting position) and the
+// candidate count are kept per query.
+//
+// The loop is bound by the integer pipes, not by bytes (tools/int_peak.cu: 15 POPC and 63 LOP3/IADD3 lanes per
+// clock and SM): a warp-wide distance in the plain form holds the POPC pipe for 64 cycles, and every other ALU
+// instruction of the loop body costs 2 more.  So (1) the distance is the carry-save form (5 POPC + 14 LOP3),
+// (2) the cell-range test of GetFeaturesInArea is two packed adds and one LOP3 on 16-bit fields, (3) the sorted
+// top-4 insertion runs only when the key beats the current fourth, and (4) a warp whose queries all see the whole
+// grid (window larger than the image: cell range = all cells, and |x - qx| < r holds for the bounding box of the
+// indexed keypoints, hence for every keypoint because the float subtraction is monotonic) and are all on level 0
+// skips the per-candidate window tests and counts candidates once per chunk.
+constexpr int TOPK_CHUNK = 512;
+struct __align__(16) CandMeta { float x, y; uint32_t cg; int oct; };     // cg = cx | cy << 16 (PosInGrid cell)
+
+constexpr int TOPK_QPT = 2;                        // queries per thread
+constexpr int TOPK_QPB = 128 * TOPK_QPT;            // queries per block
+constexpr int TOPK_SUB = 128;                       // candidates per 16-bit key block: key16 = dist << 7 | position in the block
+
+__device__ __forceinline__ void top4_insert_x2(uint32_t (&t)[4], uint32_t k)      // two 16-bit lists side by side
+{
+    uint32_t m;
+    m = __vminu2(t[0], k); k = __vmaxu2(t[0], k); t[0] = m;
+    m = __vminu2(t[1], k); k = __vmaxu2(t[1], k); t[1] = m;
+    m = __vminu2(t[2], k); k = __vmaxu2(t[2], k); t[2] = m;
+    t[3] = __vminu2(t[3], k);
+}
 
 __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
 {
     __shared__ __align__(16) uint4 s_desc[TOPK_CHUNK * 2];
-    __shared__ CandMeta s_meta[TOPK_CHUNK];
-    const int item = blockIdx.y, tid = threadIdx.x;
-    const int n1 = min(P.f1.n[item], P.f1.stride), n2 = min(P.f2.n[item], P.f2.stride);
-    if ((int)blockIdx.x * 128 >= n1) return;
-    const int q = blockIdx.x * 128 + tid;
+    __shared__ __align__(16) CandMeta s_meta[TOPK_CHUNK];
+    __shared__ float s_box[4][4];
+    __shared__ int s_oct0;                                       // running number of staged level-0 candidates
+    const int item = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n1 = min(P.f1.n[item], P.f1.stride);
+    if ((int)blockIdx.x * TOPK_QPB >= n1) return;
     const float* k2x = P.f2.x + (size_t)item * P.f2.stride;
     const float* k2y = P.f2.y + (size_t)item * P.f2.stride;
     const int* oct2 = P.f2.octave + (size_t)item * P.f2.stride;
@@ -123,57 +145,136 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
     const int* ci = P.cellItems + (size_t)item * P.f2.stride;
     const int ngrid = cs[GRID_CELLS];                          // keypoints that are in the grid at all
 
-    bool active = q < n1;
-    int level1 = 0, c0 = 0, c1 = -1, r0 = 0, r1 = -1;
-    float qx = 0.f, qy = 0.f;
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-    const float r = (float)P.window;
-    if (active) {
-        level1 = P.f1.octave[(size_t)item * P.f1.stride + q];
-        const float* prev = P.prevMatched + ((size_t)item * P.f1.stride + q) * 2;
-        qx = prev[0]; qy = prev[1];
-        active = level1 <= 0 && cell_range(P.g, qx, qy, r, c0, c1, r0, r1);
-        const uint4* d1 = reinterpret_cast<const uint4*>(P.f1.desc + ((size_t)item * P.f1.stride + q) * 32);
-        a0 = __ldg(d1); a1 = __ldg(d1 + 1);
+    // bounding box of the indexed F2 keypoints
+    {
+        float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+        for (int c = tid; c < ngrid; c += 128) {
+            const int i2 = ci[c];
+            const float x = k2x[i2], y = k2y[i2];
+            bx0 = fminf(bx0, x); bx1 = fmaxf(bx1, x); by0 = fminf(by0, y); by1 = fmaxf(by1, y);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+            by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+        }
+        if (lane == 0) { s_box[warp][0] = bx0; s_box[warp][1] = bx1; s_box[warp][2] = by0; s_box[warp][3] = by1; }
+        if (tid == 0) s_oct0 = 0;
     }
-    uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    int count = 0;
+    __syncthreads();
+    const float bx0 = fminf(fminf(s_box[0][0], s_box[1][0]), fminf(s_box[2][0], s_box[3][0]));
+    const float bx1 = fmaxf(fmaxf(s_box[0][1], s_box[1][1]), fmaxf(s_box[2][1], s_box[3][1]));
+    const float by0 = fminf(fminf(s_box[0][2], s_box[1][2]), fminf(s_box[2][2], s_box[3][2]));
+    const float by1 = fmaxf(fmaxf(s_box[0][3], s_box[1][3]), fmaxf(s_box[2][3], s_box[3][3]));
+
+    // the thread's queries: q[u] = block base + u * 128 + tid
+    const float r = (float)P.window;
+    int qi[TOPK_QPT], level1[TOPK_QPT], octHi[TOPK_QPT], count[TOPK_QPT];
+    bool active[TOPK_QPT], whole = true, anyActive = false;
+    float qx[TOPK_QPT], qy[TOPK_QPT];
+    uint32_t loK[TOPK_QPT], hiK[TOPK_QPT];
+    uint4 a0[TOPK_QPT], a1[TOPK_QPT], best[TOPK_QPT];
+#pragma unroll
+    for (int u = 0; u < TOPK_QPT; u++) {
+        qi[u] = blockIdx.x * TOPK_QPB + u * 128 + tid;
+        active[u] = qi[u] < n1;
+        level1[u] = 0; qx[u] = qy[u] = 0.f; count[u] = 0;
+        a0[u] = a1[u] = make_uint4(0, 0, 0, 0);
+        best[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        int c0 = 0, c1 = -1, r0 = 0, r1 = -1;
+        if (active[u]) {
+            level1[u] = P.f1.octave[(size_t)item * P.f1.stride + qi[u]];
+            const float* prev = P.prevMatched + ((size_t)item * P.f1.stride + qi[u]) * 2;
+            qx[u] = prev[0]; qy[u] = prev[1];
+            active[u] = level1[u] <= 0 && cell_range(P.g, qx[u], qy[u], r, c0, c1, r0, r1);
+            const uint4* d1 = reinterpret_cast<const uint4*>(P.f1.desc + ((size_t)item * P.f1.stride + qi[u]) * 32);
+            a0[u] = __ldg(d1); a1[u] = __ldg(d1 + 1);
+        }
+        const bool w = level1[u] == 0 && c0 == 0 && c1 == GRID_COLS - 1 && r0 == 0 && r1 == GRID_ROWS - 1 &&
+                       fabsf(__fsub_rn(bx0, qx[u])) < r && fabsf(__fsub_rn(bx1, qx[u])) < r &&
+                       fabsf(__fsub_rn(by0, qy[u])) < r && fabsf(__fsub_rn(by1, qy[u])) < r;
+        whole = whole && (!active[u] || w);
+        anyActive = anyActive || active[u];
+        // cell-range test on packed 16-bit fields: with cg = cx | cy << 16 (0 <= cx, cy < 64),
+        // cg + loK has bit 15 / 31 set iff cx >= c0 / cy >= r0 and cg + hiK has them set iff cx > c1 / cy > r1
+        loK[u] = (uint32_t)(0x8000 - c0) | ((uint32_t)(0x8000 - r0) << 16);
+        hiK[u] = (uint32_t)(0x7fff - max(c1, 0)) | ((uint32_t)(0x7fff - max(r1, 0)) << 16);
+        octHi[u] = level1[u] >= 0 ? level1[u] : INT_MAX;                                   // Frame.cc:468-485
+    }
+    const bool warpWhole = __all_sync(0xffffffffu, whole);
+    const bool warpIdle = !__any_sync(0xffffffffu, anyActive);
+
     for (int base = 0; base < ngrid; base += TOPK_CHUNK) {
         const int nc = min(TOPK_CHUNK, ngrid - base);
         __syncthreads();
+        int lvl0 = 0;
         for (int c = tid; c < nc; c += 128) {
             const int i2 = ci[base + c];
             const float x = k2x[i2], y = k2y[i2];
             const int cx = (int)roundf(__fmul_rn(__fsub_rn(x, P.g.minX), P.g.invW));
             const int cy = (int)roundf(__fmul_rn(__fsub_rn(y, P.g.minY), P.g.invH));
-            s_meta[c].x = x; s_meta[c].y = y;
-            s_meta[c].meta = (oct2[i2] & 0xffff) | (cx << 16) | (cy << 24);
+            CandMeta m;
+            m.x = x; m.y = y; m.cg = (uint32_t)cx | ((uint32_t)cy << 16); m.oct = oct2[i2];
+            lvl0 += m.oct == 0;
+            s_meta[c] = m;
             s_desc[2 * c] = __ldg(d2 + 2 * i2);
             s_desc[2 * c + 1] = __ldg(d2 + 2 * i2 + 1);
         }
+        if (lvl0) atomicAdd(&s_oct0, lvl0);
         __syncthreads();
-        if (active) {
+        if (warpIdle) continue;
+        if (warpWhole) {
+            // both queries see every level-0 candidate: 16-bit keys (distance << 7 | position in a 128-candidate block),
+            // the two queries' keys side by side in one register, so one packed min/max serves both lists
+            for (int sub = 0; sub < nc; sub += TOPK_SUB) {
+                const int ns = min(TOPK_SUB, nc - sub);
+                uint32_t t[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll 4
+                for (int c = 0; c < ns; c++) {
+                    if (s_meta[sub + c].oct != 0) continue;                                // warp-uniform
+                    const uint4 b0 = s_desc[2 * (sub + c)], b1 = s_desc[2 * (sub + c) + 1];
+                    const uint32_t d01 = (uint32_t)hamming256_csa(a0[0], a1[0], b0, b1) |
+                                         ((uint32_t)hamming256_csa(a0[1], a1[1], b0, b1) << 16);
+                    top4_insert_x2(t, (d01 << 7) + (uint32_t)c * 0x10001u);
+                }
+#pragma unroll
+                for (int u = 0; u < TOPK_QPT; u++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t k16 = (t[j] >> (16 * u)) & 0xffffu;
+                        if (k16 != 0xffffu) top4_insert(best[u], ((k16 >> 7) << 20) | (uint32_t)(base + sub + (int)(k16 & 127u)));
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < TOPK_QPT; u++) count[u] = s_oct0;
+        } else {
             for (int c = 0; c < nc; c++) {
                 const CandMeta m = s_meta[c];
-                const int o2 = (short)(m.meta & 0xffff), cx = (m.meta >> 16) & 0xff, cy = (m.meta >> 24) & 0xff;
-                if (cx < c0 || cx > c1 || cy < r0 || cy > r1) continue;
-                if (o2 < level1 || (level1 >= 0 && o2 > level1)) continue;             // Frame.cc:468-485
-                if (!(fabsf(__fsub_rn(m.x, qx)) < r && fabsf(__fsub_rn(m.y, qy)) < r)) continue;
-                const int dist = hamming256(a0, a1, s_desc[2 * c], s_desc[2 * c + 1]);
-                top4_insert(best, ((uint32_t)dist << 20) | (uint32_t)(base + c));
-                count++;
+#pragma unroll
+                for (int u = 0; u < TOPK_QPT; u++) {
+                    if (!active[u]) continue;
+                    if ((((m.cg + loK[u]) & ~(m.cg + hiK[u])) & 0x80008000u) != 0x80008000u) continue;
+                    if (m.oct < level1[u] || m.oct > octHi[u]) continue;
+                    if (!(fabsf(__fsub_rn(m.x, qx[u])) < r && fabsf(__fsub_rn(m.y, qy[u])) < r)) continue;
+                    const int dist = hamming256_csa(a0[u], a1[u], s_desc[2 * c], s_desc[2 * c + 1]);
+                    top4_insert(best[u], ((uint32_t)dist << 20) | (uint32_t)(base + c));
+                    count[u]++;
+                }
             }
         }
     }
-    if (q < n1) {
-        P.topk[(size_t)item * P.f1.stride + q] = best;
-        P.topkCount[(size_t)item * P.f1.stride + q] = active ? count : -1;
-        if (active && count > 0) {
-            const uint32_t k[4] = {best.x, best.y, best.z, best.w};
+#pragma unroll
+    for (int u = 0; u < TOPK_QPT; u++) {
+        if (qi[u] >= n1) continue;
+        const size_t o = (size_t)item * P.f1.stride + qi[u];
+        P.topk[o] = best[u];
+        P.topkCount[o] = active[u] ? count[u] : -1;
+        if (active[u] && count[u] > 0) {
+            const uint32_t k[4] = {best[u].x, best[u].y, best[u].z, best[u].w};
             uint32_t id[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) id[j] = j < count ? (uint32_t)ci[k[j] & 0xfffffu] : 0u;
-            P.topkIdx[(size_t)item * P.f1.stride + q] = make_uint4(id[0], id[1], id[2], id[3]);
+            for (int j = 0; j < 4; j++) id[j] = j < count[u] ? (uint32_t)ci[k[j] & 0xfffffu] : 0u;
+            P.topkIdx[o] = make_uint4(id[0], id[1], id[2], id[3]);
         }
     }
 }
@@ -211,53 +312,54 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
     const uint4* topk = P.topk + (size_t)item * P.f1.stride;
     const uint4* topkIdx = P.topkIdx + (size_t)item * P.f1.stride;
     const int* topkCount = P.topkCount + (size_t)item * P.f1.stride;
-    // lane j loads the list of query base + j (coalesced, one latency per 32 queries); the warp then walks the
-    // queries in order, broadcasting each list by shuffle
+    // Lane j owns query base + j and decides it SPECULATIVELY against the current vMatchedDistance, all 32 at once; a
+    // decision is final when no earlier query of the batch takes a keypoint the lane looked at (its <= 4 list
+    // entries).  The longest clean prefix is committed in parallel, the rest is decided again.
     for (int base = 0; base < n1; base += 32) {
       const int mine = base + lane;
-      int cntL = -1;
-      uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
-      if (mine < n1) { cntL = topkCount[mine]; kkL = topk[mine]; idL = topkIdx[mine]; }
-      const int jEnd = min(32, n1 - base);
-      for (int jq = 0; jq < jEnd; jq++) {
-        const int i1 = base + jq;
-        const int cnt = __shfl_sync(0xffffffffu, cntL, jq);
-        if (cnt <= 0) continue;            // octave > 0 (:425-427), query outside the grid, or no candidate (:431)
-        const uint4 kk = make_uint4(__shfl_sync(0xffffffffu, kkL.x, jq), __shfl_sync(0xffffffffu, kkL.y, jq),
-                                    __shfl_sync(0xffffffffu, kkL.z, jq), __shfl_sync(0xffffffffu, kkL.w, jq));
-        const uint4 idv = make_uint4(__shfl_sync(0xffffffffu, idL.x, jq), __shfl_sync(0xffffffffu, idL.y, jq),
-                                     __shfl_sync(0xffffffffu, idL.z, jq), __shfl_sync(0xffffffffu, idL.w, jq));
-        const int level1 = oct1[i1];
-        Top2 t = {INT_MAX, INT_MAX, -1, INT_MAX, INT_MAX, -1};
-        // Fast path (every lane redundantly): walk the query's 4 best static candidates in visiting order and
-        // drop those a previous query already holds at a distance <= ours (:448).  The first two survivors are
-        // best / second-best.  That is conclusive when two survive, when the list holds every candidate, or
-        // when the best survivor already fails TH_LOW; otherwise fall back to the full scan below.
-        bool resolved;
-        {
-            const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
-            const uint32_t kid[4] = {idv.x, idv.y, idv.z, idv.w};
+      int cnt = -1;
+      uint4 kk = make_uint4(0, 0, 0, 0), idv = kk;
+      if (mine < n1) { cnt = topkCount[mine]; kk = topk[mine]; idv = topkIdx[mine]; }
+      // cnt <= 0: octave > 0 (:425-427), query outside the grid, or no candidate (:431)
+      unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+      const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+      const int kid[4] = {cnt > 0 ? (int)idv.x : -1, cnt > 1 ? (int)idv.y : -1, cnt > 2 ? (int)idv.z : -1, cnt > 3 ? (int)idv.w : -1};
+      while (todo) {
+        const int first = __ffs(todo) - 1;
+        const bool pending = (todo >> lane) & 1u;
+        // Walk the query's 4 best static candidates in visiting order and drop those a previous query already holds
+        // at a distance <= ours (:448).  The first two survivors are best / second-best.  That is conclusive when
+        // two survive, when the list holds every candidate, or when the best survivor already fails TH_LOW;
+        // otherwise the full scan below.
+        int tb = INT_MAX, ts = INT_MAX, best2 = -1;
+        bool resolved = true;
+        if (pending) {
             int found = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (found < 2 && j < cnt) {
-                    const int dist = (int)(key[j] >> 20), pos = (int)(key[j] & 0xfffffu);
+                    const int dist = (int)(key[j] >> 20);
                     if (!((int)vmd[kid[j]] <= dist)) {
-                        if (found == 0) { t.b = dist; t.bp = pos; } else { t.s = dist; t.sp = pos; }
+                        if (found == 0) { tb = dist; best2 = kid[j]; } else ts = dist;
                         found++;
                     }
                 }
             }
             // every candidate beyond the list is at least as far as its last entry (d3)
             const int d3 = (int)(key[3] >> 20);
-            resolved = found == 2 || cnt <= 4 || (found == 1 && t.b > TH_LOW) || (found == 0 && d3 > TH_LOW);
-            if (!resolved && found == 1 && (float)t.b < __fmul_rn((float)d3, P.nnratio)) {
-                t.s = d3;                  // the true second-best is >= d3: the ratio test passes either way
+            resolved = found == 2 || cnt <= 4 || (found == 1 && tb > TH_LOW) || (found == 0 && d3 > TH_LOW);
+            if (!resolved && found == 1 && (float)tb < __fmul_rn((float)d3, P.nnratio)) {
+                ts = d3;                   // the true second-best is >= d3: the ratio test passes either way
                 resolved = true;
             }
         }
-        if (!resolved) {
-            t = Top2{INT_MAX, INT_MAX, -1, INT_MAX, INT_MAX, -1};
+        bool accept;
+        int stop;
+        if (__shfl_sync(0xffffffffu, (int)!resolved, first)) {
+            // the lowest pending query sees the exact state and its list is inconclusive: the warp scans for it
+            const int i1 = base + first;
+            const int level1 = oct1[i1];
+            Top2 t = Top2{INT_MAX, INT_MAX, -1, INT_MAX, INT_MAX, -1};
             int c0, c1, r0, r1;
             cell_range(P.g, prev[2 * i1], prev[2 * i1 + 1], r, c0, c1, r0, r1);
             const float qx = prev[2 * i1], qy = prev[2 * i1 + 1];
@@ -279,24 +381,37 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
                 }
             }
             t = top2_warp_reduce(t);
+            if (lane == first) { tb = t.b; ts = t.s; best2 = t.b < INT_MAX ? ci[t.bp] : -1; }
+            accept = lane == first && t.b <= TH_LOW && (float)t.b < __fmul_rn((float)t.s, P.nnratio);   // :463-465
+            stop = first + 1;
+        } else {
+            accept = pending && resolved && tb <= TH_LOW && (float)tb < __fmul_rn((float)ts, P.nnratio);   // :463-465
+            bool blocked = pending && !resolved;
+            unsigned wm = __ballot_sync(0xffffffffu, accept);
+            while (wm) {
+                const int j = __ffs(wm) - 1;
+                wm &= wm - 1;
+                const int wj = __shfl_sync(0xffffffffu, best2, j);
+                if (lane > j && (wj == kid[0] || wj == kid[1] || wj == kid[2] || wj == kid[3])) blocked = true;
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, blocked);
+            stop = bm ? __ffs(bm) - 1 : 32;
         }
-        if (t.b <= TH_LOW && (float)t.b < __fmul_rn((float)t.s, P.nnratio)) {     // :463-465
-            if (lane == 0) {
-                const int best2 = ci[t.bp];
-                const int old = m21[best2];
-                if (old >= 0) m12[old] = -1;                                         // :467-471
-                m12[i1] = best2;
-                m21[best2] = i1;
-                vmd[best2] = (uint16_t)t.b;
-                if (P.checkOri) {
-                    float rot = __fsub_rn(ang1[i1], ang2[best2]);
-                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));       // sic (:417,:482)
-                    if (bin == HISTO_LENGTH) bin = 0;
-                    hbin[i1] = bin;
-                }
+        if (accept && lane < stop) {          // the committed queries of one round take distinct keypoints
+            const int old = m21[best2];
+            if (old >= 0) m12[old] = -1;                                             // :467-471
+            m12[mine] = best2;
+            m21[best2] = mine;
+            vmd[best2] = (uint16_t)tb;
+            if (P.checkOri) {
+                float rot = __fsub_rn(ang1[mine], ang2[best2]);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));           // sic (:417,:482)
+                if (bin == HISTO_LENGTH) bin = 0;
+                hbin[mine] = bin;
             }
         }
+        todo = stop < 32 ? (todo & (0xffffffffu << stop)) : 0u;
         __syncwarp();
       }
     }
@@ -477,39 +592,37 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
     const uint4* topk = P.topk + mo;
     const uint4* topkIdx = P.topkIdx + mo;
     const int* topkCount = P.topkCount + mo;
-    // The per-map-point lists do not depend on the greedy state: lane j loads the list of map point base + j
-    // (coalesced, one memory latency per 32 map points) and the warp walks them in order by shuffle.
+    // The per-map-point lists do not depend on the greedy state.  Lane j owns map point base + j and decides it
+    // SPECULATIVELY against the current occupancy, all 32 at once; a decision is final when no earlier map point of
+    // the batch takes a keypoint the lane looked at (its <= 4 list entries).  The longest clean prefix is committed
+    // in parallel, the rest is decided again: typically two rounds per 32 map points instead of 32 serial steps.
     for (int base = 0; base < nmp; base += 32) {
       const int mine = base + lane;
-      int cntL = -1, obsL = 0;
-      uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
-      if (mine < nmp) { cntL = topkCount[mine]; kkL = topk[mine]; idL = topkIdx[mine]; obsL = P.mpObs[mo + mine]; }
-      const int jEnd = min(32, nmp - base);
-      for (int j = 0; j < jEnd; j++) {
-        const int i = base + j;
-        const int cnt = __shfl_sync(0xffffffffu, cntL, j);
-        if (cnt <= 0) continue;          // not in view / bad (:56-60), outside the grid, or no candidate (:73)
-        const uint4 kk = make_uint4(__shfl_sync(0xffffffffu, kkL.x, j), __shfl_sync(0xffffffffu, kkL.y, j),
-                                    __shfl_sync(0xffffffffu, kkL.z, j), __shfl_sync(0xffffffffu, kkL.w, j));
-        const uint4 idv = make_uint4(__shfl_sync(0xffffffffu, idL.x, j), __shfl_sync(0xffffffffu, idL.y, j),
-                                     __shfl_sync(0xffffffffu, idL.z, j), __shfl_sync(0xffffffffu, idL.w, j));
-        const int obsI = __shfl_sync(0xffffffffu, obsL, j);
+      int cnt = -1, obs = 0;
+      uint4 kk = make_uint4(0, 0, 0, 0), idv = kk;
+      if (mine < nmp) { cnt = topkCount[mine]; kk = topk[mine]; idv = topkIdx[mine]; obs = P.mpObs[mo + mine]; }
+      // cnt <= 0: not in view / bad (:56-60), outside the grid, or no candidate (:73)
+      unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+      const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+      const int kid[4] = {cnt > 0 ? (int)idv.x : -1, cnt > 1 ? (int)idv.y : -1, cnt > 2 ? (int)idv.z : -1, cnt > 3 ? (int)idv.w : -1};
+      while (todo) {
+        const int first = __ffs(todo) - 1;
+        const bool pending = (todo >> lane) & 1u;
+        // the map point's 4 best static candidates in visiting order, minus the keypoints that were taken since
+        // (:89-91).  Conclusive when two survive, when the list holds every candidate, or when nothing within
+        // TH_HIGH can survive; otherwise the full scan below.
         Top2 t = {256, INT_MAX, -1, 256, INT_MAX, -1};
-        // Fast path (every lane redundantly): the map point's 4 best static candidates in visiting order,
-        // minus the keypoints that were taken since (:89-91).  Conclusive when two survive, when the list
-        // holds every candidate, or when nothing within TH_HIGH can survive; otherwise the full scan below.
-        bool resolved;
-        {
-            const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
-            const uint32_t kid[4] = {idv.x, idv.y, idv.z, idv.w};
+        int bestId = -1;
+        bool resolved = true;
+        if (pending) {
             int found = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (found < 2 && j < cnt) {
-                    const int dist = (int)(key[j] >> 23), pos = (int)((key[j] >> 5) & 0x3ffffu), o = (int)(key[j] & 31u);
+                    const int dist = (int)(key[j] >> 23), o = (int)(key[j] & 31u);
                     const bool taken = occ[kid[j]] != 0;
                     if (!taken && dist < 256) {
-                        if (found == 0) { t.b = dist; t.bp = pos; t.ba = o; } else { t.s = dist; t.sp = pos; t.sa = o; }
+                        if (found == 0) { t.b = dist; t.ba = o; bestId = kid[j]; } else { t.s = dist; t.sa = o; }
                         found++;
                     }
                 }
@@ -517,7 +630,10 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
             const int d3 = (int)(key[3] >> 23);
             resolved = found == 2 || cnt <= 4 || (found == 1 && t.b > TH_HIGH) || (found == 0 && d3 > TH_HIGH);
         }
-        if (!resolved) {
+        if (__shfl_sync(0xffffffffu, (int)!resolved, first)) {
+            // the lowest pending map point sees the exact state and its list is inconclusive: the warp scans for it
+            const int i = base + first;
+            const int obsI = __shfl_sync(0xffffffffu, obs, first);
             t = Top2{256, INT_MAX, -1, 256, INT_MAX, -1};
             const int lvl = P.mpLevel[mo + i];
             float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
@@ -550,15 +666,40 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
                 }
             }
             t = top2_warp_reduce(t);
-        }
-        if (t.b <= TH_HIGH && !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s))) {   // :120-127
-            if (lane == 0) {
-                const int bestIdx = ci[t.bp];
-                kpmp[bestIdx] = i;                                                   // :125
-                occ[bestIdx] = obsI > 0;
+            if (t.b <= TH_HIGH && !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s))) {   // :120-127
+                if (lane == 0) {
+                    const int bestIdx = ci[t.bp];
+                    kpmp[bestIdx] = i;                                                   // :125
+                    occ[bestIdx] = obsI > 0;
+                }
+                nmatches++;
             }
-            nmatches++;
+            todo &= ~(1u << first);
+            __syncwarp();
+            continue;
         }
+        const bool accept = pending && resolved && t.b <= TH_HIGH &&
+                            !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s));          // :120-127
+        const int w = (accept && obs > 0) ? bestId : -1;       // the occupancy this map point would set
+        bool blocked = pending && !resolved;
+        unsigned wm = __ballot_sync(0xffffffffu, w >= 0);
+        while (wm) {
+            const int j = __ffs(wm) - 1;
+            wm &= wm - 1;
+            const int wj = __shfl_sync(0xffffffffu, w, j);
+            if (lane > j && (wj == kid[0] || wj == kid[1] || wj == kid[2] || wj == kid[3])) blocked = true;
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, blocked && pending);
+        const int stop = bm ? __ffs(bm) - 1 : 32;
+        const bool commit = accept && lane < stop;
+        nmatches += __popc(__ballot_sync(0xffffffffu, commit));
+        // several map points without observations may take the same keypoint; the last one in list order stays (:125)
+        const unsigned same = __match_any_sync(0xffffffffu, commit ? bestId : -1 - lane);
+        if (commit) {
+            if (lane == 31 - __clz(same)) kpmp[bestId] = mine;
+            if (obs > 0) occ[bestId] = 1;
+        }
+        todo = stop < 32 ? (todo & (0xffffffffu << stop)) : 0u;
         __syncwarp();
       }
     }
@@ -690,7 +831,7 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     // scratch strides follow the views
     k_build_grid<<<items, 256, 0, st>>>(P.f2, P.g, m->cellStart, m->cellItems);
     ORB_CHECK_LAUNCH("k_build_grid");
-    k_init_topk<<<dim3((f1->stride + 127) / 128, items), 128, 0, st>>>(P);
+    k_init_topk<<<dim3((f1->stride + orbb200::TOPK_QPB - 1) / orbb200::TOPK_QPB, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_init_topk");
     {
         const size_t sm = 4 * sizeof(uint16_t) * (size_t)((f2->stride + 7) & ~7);
