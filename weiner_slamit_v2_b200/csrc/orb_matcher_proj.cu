@@ -251,35 +251,40 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
 
     int nmatches = 0;
     const int accept = P.kind == 1 ? P.orbDist : (P.kind == 2 ? TH_LOW : TH_HIGH);
+    // Lane j owns last-frame point base + j and decides it SPECULATIVELY against the current occupancy, all 32 at
+    // once; a decision is final when no earlier point of the batch takes a keypoint the lane looked at (its <= 4 list
+    // entries).  The longest clean prefix is committed in parallel, the rest is decided again.
     for (int base = 0; base < nl; base += 32) {
       const int mine = base + lane;
-      int cntL = -1, obsL = 0;
-      float angL = 0.f;
-      uint4 kkL = make_uint4(0, 0, 0, 0), idL = kkL;
-      if (mine < nl) { cntL = P.topkCount[lo + mine]; kkL = P.topk[lo + mine]; idL = P.topkIdx[lo + mine]; obsL = P.kind != 0 ? 1 : P.mpObs[lo + mine]; angL = P.lastAng[lo + mine]; }
-      const int jEnd = min(32, nl - base);
-      for (int j = 0; j < jEnd; j++) {
-        const int i = base + j;
-        const int cnt = __shfl_sync(0xffffffffu, cntL, j);
-        if (cnt <= 0) continue;
-        const uint32_t key[4] = {__shfl_sync(0xffffffffu, kkL.x, j), __shfl_sync(0xffffffffu, kkL.y, j),
-                                 __shfl_sync(0xffffffffu, kkL.z, j), __shfl_sync(0xffffffffu, kkL.w, j)};
-        const uint32_t kid[4] = {__shfl_sync(0xffffffffu, idL.x, j), __shfl_sync(0xffffffffu, idL.y, j),
-                                 __shfl_sync(0xffffffffu, idL.z, j), __shfl_sync(0xffffffffu, idL.w, j)};
-        const int obsI = __shfl_sync(0xffffffffu, obsL, j);
-        const float angI = __shfl_sync(0xffffffffu, angL, j);
+      int cnt = -1, obs = 0;
+      float ang = 0.f;
+      uint4 kk = make_uint4(0, 0, 0, 0), idv = kk;
+      if (mine < nl) { cnt = P.topkCount[lo + mine]; kk = P.topk[lo + mine]; idv = P.topkIdx[lo + mine]; obs = P.kind != 0 ? 1 : P.mpObs[lo + mine]; ang = P.lastAng[lo + mine]; }
+      unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+      const uint32_t key[4] = {kk.x, kk.y, kk.z, kk.w};
+      const int kid[4] = {cnt > 0 ? (int)idv.x : -1, cnt > 1 ? (int)idv.y : -1, cnt > 2 ? (int)idv.z : -1, cnt > 3 ? (int)idv.w : -1};
+      while (todo) {
+        const int first = __ffs(todo) - 1;
+        const bool pending = (todo >> lane) & 1u;
         // only the best candidate matters here (no ratio test): the first entry of the list whose keypoint is free
         int bestDist = 256, bestIdx = -1;
-        bool found = false;
+        bool resolved = true;
+        if (pending) {
+            bool found = false;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            if (!found && e < cnt) {
-                const int dist = (int)(key[e] >> 23);
-                if (!occ[kid[e]] && dist < 256) { bestDist = dist; bestIdx = (int)kid[e]; found = true; }
+            for (int e = 0; e < 4; e++) {
+                if (!found && e < cnt) {
+                    const int dist = (int)(key[e] >> 23);
+                    if (!occ[kid[e]] && dist < 256) { bestDist = dist; bestIdx = kid[e]; found = true; }
+                }
             }
+            resolved = found || cnt <= 4 || (int)(key[3] >> 23) > accept;
         }
-        const bool resolved = found || cnt <= 4 || (int)(key[3] >> 23) > accept;
-        if (!resolved) {                                   // every listed keypoint was taken: rescan all candidates
+        bool take;
+        int stop;
+        if (__shfl_sync(0xffffffffu, (int)!resolved, first)) {
+            // the lowest pending point sees the exact state and every listed keypoint was taken: rescan all candidates
+            const int i = base + first;
             const LastQuery q = last_query(P, item, i);
             int c0, c1, r0, r1;
             cell_range(P.kind == 2 ? P.q : P.g, q.u, q.v, q.radius, c0, c1, r0, r1);
@@ -300,23 +305,39 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
                 const int od = __shfl_xor_sync(0xffffffffu, bd, d), op = __shfl_xor_sync(0xffffffffu, bp, d);
                 if (key_lt(od, op, bd, bp)) { bd = od; bp = op; }
             }
-            bestDist = bd;
-            bestIdx = bd < 256 ? ci[bp] : -1;
-        }
-        if (bestDist <= accept) {                                                 // :1436-1452, :1561-1579
-            if (lane == 0) {
-                kpmp[bestIdx] = i;
-                occ[bestIdx] = obsI > 0;
-                if (P.checkOri) {
-                    float rot = __fsub_rn(angI, kang[bestIdx]);
-                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
-                    if (bin == HISTO_LENGTH) bin = 0;
-                    hbin[i] = bin; hidx[i] = bestIdx;
-                }
+            if (lane == first) { bestDist = bd; bestIdx = bd < 256 ? ci[bp] : -1; }
+            take = lane == first && bd <= accept;
+            stop = first + 1;
+        } else {
+            take = pending && resolved && bestDist <= accept;                     // :1436-1452, :1561-1579
+            const int w = (take && obs > 0) ? bestIdx : -1;        // the occupancy this point would set
+            bool blocked = pending && !resolved;
+            unsigned wm = __ballot_sync(0xffffffffu, w >= 0);
+            while (wm) {
+                const int j = __ffs(wm) - 1;
+                wm &= wm - 1;
+                const int wj = __shfl_sync(0xffffffffu, w, j);
+                if (lane > j && (wj == kid[0] || wj == kid[1] || wj == kid[2] || wj == kid[3])) blocked = true;
             }
-            nmatches++;
+            const unsigned bm = __ballot_sync(0xffffffffu, blocked);
+            stop = bm ? __ffs(bm) - 1 : 32;
         }
+        const bool commit = take && lane < stop;
+        nmatches += __popc(__ballot_sync(0xffffffffu, commit));
+        // several points without observations may take the same keypoint; the last one in list order stays
+        const unsigned same = __match_any_sync(0xffffffffu, commit ? bestIdx : -1 - lane);
+        if (commit) {
+            if (lane == 31 - __clz(same)) kpmp[bestIdx] = mine;
+            if (obs > 0) occ[bestIdx] = 1;
+            if (P.checkOri) {
+                float rot = __fsub_rn(ang, kang[bestIdx]);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+                if (bin == HISTO_LENGTH) bin = 0;
+                hbin[mine] = bin; hidx[mine] = bestIdx;
+            }
+        }
+        todo = stop < 32 ? (todo & (0xffffffffu << stop)) : 0u;
         __syncwarp();
       }
     }
