@@ -343,6 +343,7 @@ def run_ours(args):
         if world == 1 and not args.no_matching:
             line["matching"] = run_matching(local, max(2, min(args.steps, 5)))
             line["pipeline"] = run_pipeline(local, max(2, min(args.steps, 5)))
+            line["stereo"] = run_stereo(local, max(2, min(args.steps, 5)))
         if world == 1 and not args.no_cpu_baseline:
             threads = _cpu_threads()
             sample = BATCH
@@ -619,6 +620,61 @@ def run_pipeline(local, steps):
     return {"workload": "128 frame pairs 640x480 (second frame = first shifted by (4,2) px): 2 x extraction, undistort with the "
                         "reference's camera, grid, SearchForInitialization(window 100, ratio 0.9), all on the device",
             "ms_per_step": dt * 1e3, "pairs_per_s": pairs / dt, "frames_per_s": 2 * pairs / dt, "accepted_matches": acc}
+
+
+def run_stereo(local, steps):
+    """Scope row N4: the stereo Frame constructor for 128 rectified pairs on the device: two extractions per pair
+    (256 frames), keypoint views, Frame::ComputeStereoMatches reading both pyramids in place."""
+    import numpy as np
+    import torch
+    from weiner_slamit_v2_b200.frames import stereo_right_frame
+    from weiner_slamit_v2_b200.pipeline import StereoPipeline
+    pairs = 128
+    base = _frames(11, 16)
+    rb = np.stack([stereo_right_frame(f, i) for i, f in enumerate(base)])
+    left = np.concatenate([base] * (pairs // 16)); right = np.concatenate([rb] * (pairs // 16))
+    pipe = StereoPipeline(max_pairs=pairs, device=local)
+    dl, dr = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    for _ in range(2):
+        pipe.run(dl, dr, pairs)
+    pipe.sync()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nm, _, _ = pipe.run(dl, dr, pairs)
+    pipe.sync()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    # the stereo matcher alone, CUDA events on its stream
+    L = pipe.L
+    st = torch.cuda.ExternalStream(L.orbb200_matcher_stream(pipe.m), device=local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import ctypes as C
+    from weiner_slamit_v2_b200 import _lib
+    from weiner_slamit_v2_b200._lib import FrameView, check
+    views = [FrameView(s["n"].data_ptr(), s["x"].data_ptr(), s["y"].data_ptr(), s["oct"].data_ptr(), s["ang"].data_ptr(),
+                       s["desc"].data_ptr(), pipe.cap) for s in pipe.side]
+    lp, rp = pipe.exl.pyramid_view(), pipe.exr.pyramid_view()
+    def stereo_only():
+        check(L.orbb200_compute_stereo_matches(pipe.m, pairs, C.byref(views[0]), C.byref(views[1]), C.byref(lp), C.byref(rp),
+                                               pipe.scale.ctypes.data, pipe.inv_scale.ctypes.data, len(pipe.scale), pipe.mb, pipe.mbf,
+                                               pipe.u_right.data_ptr(), pipe.depth.data_ptr(), pipe.nm.data_ptr(),
+                                               _lib.DEVICE_VIEWS | _lib.DEVICE_PYRAMIDS))
+    stereo_only()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(st):
+        e0.record()
+        for _ in range(steps):
+            stereo_only()
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    acc = int(nm[:pairs].sum())
+    pipe.close()
+    return {"workload": "128 rectified stereo pairs 640x480 (right = left shifted by a per-band disparity of 1..48 px): 2 x extraction, "
+                        "keypoint views, ComputeStereoMatches (row bands, Hamming, 11x11 SAD over +-5 px, parabola, median cut), all on the device",
+            "ms_per_step": dt * 1e3, "pairs_per_s": pairs / dt, "stereo_matcher_ms": ms, "stereo_matcher_pairs_per_s": pairs / ms * 1e3,
+            "stereo_matches": acc}
 
 
 def _traffic(stage):

@@ -385,6 +385,35 @@ int orbb200_frames_from_keypoints(orbb200_matcher *m, const orbb200_keypoint *d_
 int orbb200_undistort_points(orbb200_matcher *m, const float *xy_in, float *xy_out, int n, const float K[4], const float dist[5]);
 /* Replaces Frame::ComputeImageBounds (S/Frame.cc:561-589): bounds = {mnMinX, mnMinY, mnMaxX, mnMaxY}. */
 int orbb200_image_bounds(orbb200_matcher *m, int cols, int rows, const float K[4], const float dist[5], float bounds[4]);
+/* ---- Frame::ComputeStereoMatches (S/Frame.cc:591-763) -------------------------------------------------------------
+ * The image pyramids of `items` frames as the stereo matcher reads them (ORBextractor::mvImagePyramid, I/ORBextractor.h:85,
+ * read at S/Frame.cc:596,686,703), WITHOUT the 19-pixel border (ComputeStereoMatches never reaches it for keypoints the
+ * extractor produced).  level[l] points at frame 0; frame i of level l starts frame_stride[l] * i bytes later. */
+#define ORBB200_MAX_LEVELS 16
+typedef struct orbb200_pyramid_view {
+    int nlevels;
+    const uint8_t *level[ORBB200_MAX_LEVELS];
+    size_t frame_stride[ORBB200_MAX_LEVELS];
+    int32_t pitch[ORBB200_MAX_LEVELS], width[ORBB200_MAX_LEVELS], height[ORBB200_MAX_LEVELS];
+} orbb200_pyramid_view;
+/* The pyramids of the handle's last extract call where they lie in DEVICE memory (valid until the next extract call on
+ * this handle); level 0 is the caller's own frame buffer when it was used in place. */
+int orbb200_extractor_pyramid_view(orbb200_extractor *h, orbb200_pyramid_view *view);
+/* `on_device` bits of orbb200_compute_stereo_matches */
+#define ORBB200_DEVICE_VIEWS 1      /* frame views, u_right, depth and nmatches are device pointers (asynchronous call) */
+#define ORBB200_DEVICE_PYRAMIDS 2   /* the pyramid views point at device memory (e.g. orbb200_extractor_pyramid_view) */
+/* Replaces Frame::ComputeStereoMatches for `items` rectified stereo pairs: left / right = mvKeys / mDescriptors and
+ * mvKeysRight / mDescriptorsRight (x, y, octave, desc; angle unused), lpyr / rpyr = the two extractors' pyramids (equal
+ * level sizes), scale_factors / inv_scale_factors = mvScaleFactors / mvInvScaleFactors (HOST arrays, nlevels entries),
+ * mb / mbf = Frame::mb / mbf.  Writes mvuRight and mvDepth (items x left.stride floats, -1 = no stereo match) and the
+ * number of left keypoints that end with a depth per item.  A keypoint for which the reference would read outside an
+ * image (it throws or is undefined there) gets no depth. */
+int orbb200_compute_stereo_matches(orbb200_matcher *m, int items, const orbb200_frame_view *left,
+                                   const orbb200_frame_view *right, const orbb200_pyramid_view *lpyr,
+                                   const orbb200_pyramid_view *rpyr, const float *scale_factors,
+                                   const float *inv_scale_factors, int nlevels, float mb, float mbf,
+                                   float *u_right, float *depth, int32_t *nmatches, int on_device);
+
 /* Makes the matcher's stream wait (on the device, no host synchronisation) for everything queued so far on
  * the extractor's stream: extract_device -> frames_from_keypoints -> search_*(on_device) is one pipeline. */
 int orbb200_matcher_wait_extractor(orbb200_matcher *m, orbb200_extractor *ex);

@@ -126,6 +126,42 @@ MatExpr operator/(const Mat& a, double s) { return MatExpr(&g_miniOp, 0, a, Mat(
 MatExpr operator*(double s, const Mat& a) { return MatExpr(&g_miniOp, 0, a, Mat(), Mat(), s); }
 MatExpr operator*(double s, const MatExpr& e) { MatExpr r(e); r.alpha *= s; return r; }
 
+// ---- what Frame::ComputeStereoMatches evaluates on its 11 x 11 patches (S/Frame.cc:684-707): convertTo(CV_32F) of a
+// CV_8U view (in place), c * Mat::ones(...), Mat - expr, norm(a, b, NORM_L1).  Every value is a small integer held in
+// a float, so each of these is exact whatever the evaluation order.
+MatExpr Mat::ones(int rows, int cols, int type)
+{
+    CV_Assert(type == CV_32F);
+    Mat m;
+    m.create(rows, cols, CV_32F);
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(r, c) = 1.f;
+    return MatExpr(&g_miniOp, 0, m);
+}
+MatExpr operator-(const Mat& a, const MatExpr& e)
+{
+    Mat b;
+    e.op->assign(e, b);
+    return MatExpr(&g_miniOp, 2, a, b);
+}
+void Mat::convertTo(OutputArray dst, int rtype, double alpha, double beta) const
+{
+    CV_Assert(type() == CV_8U && rtype == CV_32F && alpha == 1 && beta == 0);
+    const Mat src = *this;                         // dst may be *this (IL.convertTo(IL, CV_32F))
+    Mat out;
+    out.create(src.rows, src.cols, CV_32F);
+    for (int r = 0; r < src.rows; r++) for (int c = 0; c < src.cols; c++) out.at<float>(r, c) = (float)src.at<uchar>(r, c);
+    *static_cast<Mat*>(dst.getObj()) = out;
+}
+double norm(InputArray src1, InputArray src2, int normType, InputArray)
+{
+    const Mat& a = *static_cast<const Mat*>(src1.getObj());
+    const Mat& b = *static_cast<const Mat*>(src2.getObj());
+    CV_Assert(normType == NORM_L1 && a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    double s = 0;
+    for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) s += std::fabs((double)a.at<float>(r, c) - (double)b.at<float>(r, c));
+    return s;
+}
+
 // Mat::dot for continuous CV_32F: products and sum in double, element order (core/src/matmul.cpp, dotProd_ for short vectors)
 double Mat::dot(InputArray other) const
 {

@@ -1085,3 +1085,126 @@ void orc_bow_transform(
     *bow_n = nb; *fv_n = nf;
     free(wt_of); free(n_of); free(w_of);
 }
+
+/* ---- Frame::ComputeStereoMatches (S/Frame.cc:591-763) ------------------------------------------------------------
+ * Left keypoints against the right keypoints of the same rows (row table of the right image, :598-617), best
+ * descriptor (:631-677), then an 11 x 11 sum of absolute differences of centre-subtracted patches slid over +-5
+ * columns of the right pyramid level (:680-715), a parabola through the three costs around the minimum (:720-729)
+ * and the depth (:731-745); finally the matches whose patch cost reaches 1.5 * 1.4 * median are withdrawn (:749-762).
+ * The patches hold small integers in CV_32F, so cv::norm(NORM_L1)'s double sum is exact in any order.
+ * level images: pointer / pitch / width / height per pyramid level, WITHOUT border.  Where the reference would leave
+ * an image (cv::Mat::rowRange / colRange throw, vRowIndices is indexed out of range) the keypoint is skipped and
+ * counted in *skipped.  Returns the number of left keypoints that end with a depth. */
+static float orc_roundf_away(float v) { return roundf(v); }
+
+int orc_compute_stereo_matches(
+    int n, const float *kx, const float *ky, const int32_t *koct, const uint8_t *desc,
+    int nr, const float *rx, const float *ry, const int32_t *roct, const uint8_t *rdesc,
+    int nlevels, const float *scale, const float *inv_scale,
+    const uint8_t *const *limg, const int32_t *lpitch, const uint8_t *const *rimg, const int32_t *rpitch,
+    const int32_t *lw, const int32_t *lh, float mb, float mbf, float *u_right, float *depth, int32_t *skipped)
+{
+    const int TH_HIGH_ = 100;
+    int nskip = 0;
+    for (int i = 0; i < n; i++) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    const int nRows = lh[0];                                                      /* :596 */
+    /* row table (:598-617): CSR in push_back order */
+    int *rowCount = (int *)calloc((size_t)nRows + 1, sizeof(int));
+    for (int iR = 0; iR < nr; iR++) {
+        const float r = 2.0f * scale[roct[iR]];
+        const int maxr = (int)ceilf(ry[iR] + r), minr = (int)floorf(ry[iR] - r);
+        for (int yi = minr; yi <= maxr; yi++) { if (yi >= 0 && yi < nRows) rowCount[yi + 1]++; else nskip++; }
+    }
+    for (int y = 0; y < nRows; y++) rowCount[y + 1] += rowCount[y];
+    int *rowItems = (int *)malloc(sizeof(int) * (size_t)(rowCount[nRows] + 1));
+    int *fill = (int *)malloc(sizeof(int) * (size_t)(nRows + 1));
+    memcpy(fill, rowCount, sizeof(int) * (size_t)(nRows + 1));
+    for (int iR = 0; iR < nr; iR++) {
+        const float r = 2.0f * scale[roct[iR]];
+        const int maxr = (int)ceilf(ry[iR] + r), minr = (int)floorf(ry[iR] - r);
+        for (int yi = minr; yi <= maxr; yi++) if (yi >= 0 && yi < nRows) rowItems[fill[yi]++] = iR;
+    }
+    const float minZ = mb, minD = -3, maxD = mbf / minZ;                          /* :620-622 */
+    int *vDist = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    int *vIdx = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    int nd = 0;
+    for (int iL = 0; iL < n; iL++) {
+        const int levelL = koct[iL];
+        const float vL = ky[iL], uL = kx[iL];
+        if (!(vL >= 0.0f) || !(vL < (float)nRows)) { nskip++; continue; }            /* vRowIndices[vL] out of range */
+        const int row = (int)vL;
+        const int cs = rowCount[row], ce = rowCount[row + 1];
+        if (cs == ce) continue;                                                   /* :637-638 */
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;                                                   /* :643-644 */
+        int bestDist = TH_HIGH_, bestIdxR = 0;
+        for (int c = cs; c < ce; c++) {                                           /* :651-672 */
+            const int iR = rowItems[c];
+            if (roct[iR] < levelL - 1 || roct[iR] > levelL + 1) continue;
+            const float uR = rx[iR];
+            if (uR >= minU && uR <= maxU) {
+                const int dist = orc_descriptor_distance(desc + 32 * (size_t)iL, rdesc + 32 * (size_t)iR);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (!(bestDist < TH_HIGH_)) continue;                                     /* :675 */
+        const float uR0 = rx[bestIdxR];
+        const float scaleFactor = inv_scale[levelL];
+        const float scaleduL = orc_roundf_away(kx[iL] * scaleFactor);
+        const float scaledvL = orc_roundf_away(ky[iL] * scaleFactor);
+        const float scaleduR0 = orc_roundf_away(uR0 * scaleFactor);
+        const int w = 5, L = 5;
+        const int W = lw[levelL], H = lh[levelL];
+        /* IL (:684): rows scaledvL-w .. scaledvL+w, columns scaleduL-w .. scaleduL+w of the left level */
+        if (!(scaledvL - w >= 0 && scaledvL + w + 1 <= H && scaleduL - w >= 0 && scaleduL + w + 1 <= W)) { nskip++; continue; }
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;       /* :693-696 */
+        if (iniu < 0 || endu >= W) continue;
+        if (!(scaleduR0 - L - w >= 0)) { nskip++; continue; }                    /* colRange would throw (:700) */
+        const int v0 = (int)scaledvL, u0 = (int)scaleduL, r0 = (int)scaleduR0;
+        const uint8_t *Lp = limg[levelL], *Rp = rimg[levelL];
+        const int lp = lpitch[levelL], rp = rpitch[levelL];
+        const int cL = Lp[(size_t)v0 * lp + u0];
+        int best = 2147483647, bestincR = 0;
+        float vDists[11];
+        for (int incR = -L; incR <= L; incR++) {                                  /* :698-713 */
+            const int cR = Rp[(size_t)v0 * rp + r0 + incR];
+            int sad = 0;
+            for (int dy = -w; dy <= w; dy++)
+                for (int dx = -w; dx <= w; dx++) {
+                    const int a = Lp[(size_t)(v0 + dy) * lp + u0 + dx] - cL;
+                    const int b = Rp[(size_t)(v0 + dy) * rp + r0 + incR + dx] - cR;
+                    sad += a > b ? a - b : b - a;
+                }
+            const float dist = (float)sad;
+            if (dist < (float)best) { best = (int)dist; bestincR = incR; }
+            vDists[L + incR] = dist;
+        }
+        if (bestincR == -L || bestincR == L) continue;                            /* :715-716 */
+        const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+        const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+        if (deltaR < -1 || deltaR > 1) continue;                                  /* :725-726 */
+        float bestuR = scale[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+        float disparity = uL - bestuR;
+        if (disparity >= 0 && disparity < maxD) {                                 /* :733-744 */
+            if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+            depth[iL] = mbf / disparity;
+            u_right[iL] = bestuR;
+            vDist[nd] = best; vIdx[nd] = iL; nd++;
+        }
+    }
+    int kept = nd;
+    if (nd > 0) {
+        /* sort(vDistIdx) (:749): only the median and "distance >= threshold" matter, both independent of tie order */
+        int *sorted = (int *)malloc(sizeof(int) * (size_t)nd);
+        memcpy(sorted, vDist, sizeof(int) * (size_t)nd);
+        for (int a = 1; a < nd; a++) { const int v = sorted[a]; int b = a - 1; while (b >= 0 && sorted[b] > v) { sorted[b + 1] = sorted[b]; b--; } sorted[b + 1] = v; }
+        const float median = (float)sorted[nd / 2];
+        const float thDist = 1.5f * 1.4f * median;
+        for (int k = 0; k < nd; k++)
+            if (!((float)vDist[k] < thDist)) { u_right[vIdx[k]] = -1; depth[vIdx[k]] = -1; kept--; }
+        free(sorted);
+    }
+    if (skipped) *skipped = nskip;
+    free(vIdx); free(vDist); free(fill); free(rowItems); free(rowCount);
+    return kept;
+}

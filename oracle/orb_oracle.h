@@ -180,6 +180,13 @@ int orc_search_by_projection_keyframe(
     int n, const float *kx, const float *ky, const int32_t *koct, const float *kang, const uint8_t *kdesc,
     int32_t *kp_mp, int nlevels, const float *scale_factors, float log_scale_factor, const float bounds[4],
     float th, int orb_dist, int check_orientation);
+/* Frame::ComputeStereoMatches (Frame.cc:591-763); level images without border, same sizes left and right */
+int orc_compute_stereo_matches(
+    int n, const float *kx, const float *ky, const int32_t *koct, const uint8_t *desc,
+    int nr, const float *rx, const float *ry, const int32_t *roct, const uint8_t *rdesc,
+    int nlevels, const float *scale, const float *inv_scale,
+    const uint8_t *const *limg, const int32_t *lpitch, const uint8_t *const *rimg, const int32_t *rpitch,
+    const int32_t *lw, const int32_t *lh, float mb, float mbf, float *u_right, float *depth, int32_t *skipped);
 void orc_undistort_points(int n, const float *xy_in, float *xy_out, const float K[4], const float dist[5]);
 void orc_image_bounds(int cols, int rows, const float K[4], const float dist[5], float bounds[4]);
 

@@ -658,4 +658,40 @@ int refm_bow_transform(const char* path, int n, const uint8_t* desc, int levelsu
     *fv_n = a;
     return 0;
 }
+
+// Frame::ComputeStereoMatches (S/Frame.cc:591-763) on a Frame whose two extractors only carry their image pyramids.
+// An ORBextractor cannot be constructed here (ORBextractor.cc is not part of this library): zeroed storage with the
+// one member the function reads, mvImagePyramid, constructed in place.
+int refm_compute_stereo_matches(
+    int n, const float* kx, const float* ky, const int32_t* koct, const uint8_t* desc,
+    int nr, const float* rx, const float* ry, const int32_t* roct, const uint8_t* rdesc,
+    int nlevels, const float* scale, const float* inv_scale,
+    const uint8_t* const* limg, const int32_t* lpitch, const uint8_t* const* rimg, const int32_t* rpitch,
+    const int32_t* lw, const int32_t* lh, float mb, float mbf, float* u_right, float* depth)
+{
+    Frame F;
+    F.N = n;
+    F.mvKeys.resize(n); F.mvKeysRight.resize(nr);
+    for (int i = 0; i < n; i++) { cv::KeyPoint& k = F.mvKeys[i]; k.pt.x = kx[i]; k.pt.y = ky[i]; k.octave = koct[i]; k.angle = 0; k.size = 31.f; }
+    for (int i = 0; i < nr; i++) { cv::KeyPoint& k = F.mvKeysRight[i]; k.pt.x = rx[i]; k.pt.y = ry[i]; k.octave = roct[i]; k.angle = 0; k.size = 31.f; }
+    F.mDescriptors = cv::Mat(n > 0 ? n : 1, 32, CV_8U, (void*)desc);
+    F.mDescriptorsRight = cv::Mat(nr > 0 ? nr : 1, 32, CV_8U, (void*)rdesc);
+    F.mvScaleFactors.assign(scale, scale + nlevels);
+    F.mvInvScaleFactors.assign(inv_scale, inv_scale + nlevels);
+    F.mb = mb; F.mbf = mbf;
+    ORBextractor* ex[2];
+    for (int s = 0; s < 2; s++) {
+        ex[s] = (ORBextractor*)std::calloc(1, sizeof(ORBextractor));
+        new (&ex[s]->mvImagePyramid) std::vector<cv::Mat>(nlevels);
+        for (int l = 0; l < nlevels; l++)
+            ex[s]->mvImagePyramid[l] = cv::Mat(lh[l], lw[l], CV_8U, (void*)(s ? rimg[l] : limg[l]), (size_t)(s ? rpitch[l] : lpitch[l]));
+    }
+    F.mpORBextractorLeft = ex[0]; F.mpORBextractorRight = ex[1];
+    F.ComputeStereoMatches();
+    int cnt = 0;
+    for (int i = 0; i < n; i++) { u_right[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; cnt += F.mvuRight[i] != -1.0f; }
+    for (int s = 0; s < 2; s++) { ex[s]->mvImagePyramid.~vector(); std::free(ex[s]); }
+    F.mpORBextractorLeft = F.mpORBextractorRight = NULL;
+    return cnt;
+}
 }

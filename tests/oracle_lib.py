@@ -550,3 +550,33 @@ def bow_transform(voc, desc, levelsup=4):
       int(levelsup), C.byref(o["bn"]), _ptr(o["bw"], _u32p), _ptr(o["bv"], _f64p), C.byref(o["fn"]), _ptr(o["fnode"], _u32p),
       _ptr(o["fstart"], _i32p), _ptr(o["ffeat"], _u32p))
     return _bow_result(o)
+
+
+def _pyr_args(pyr):
+    """list of 2-D uint8 level images -> (keep-alive list, pointer array, pitch array)."""
+    lv = [np.ascontiguousarray(p, np.uint8) for p in pyr]
+    ptrs = (_u8p * len(lv))(*[_ptr(p, _u8p) for p in lv])
+    pitch = np.array([p.strides[0] for p in lv], np.int32)
+    return lv, ptrs, pitch
+
+
+def compute_stereo_matches(kl, dl, kr, dr, scale, inv_scale, lpyr, rpyr, mb, mbf):
+    """Frame::ComputeStereoMatches.  kl / kr: keypoint records (x, y, octave); dl / dr: (n, 32) descriptors;
+    lpyr / rpyr: pyramid levels without border.  Returns (u_right, depth, kept, skipped)."""
+    f = lib().orc_compute_stereo_matches
+    f.argtypes = [C.c_int, _f32p, _f32p, _i32p, _u8p, C.c_int, _f32p, _f32p, _i32p, _u8p, C.c_int, _f32p, _f32p,
+                  C.POINTER(_u8p), _i32p, C.POINTER(_u8p), _i32p, _i32p, _i32p, C.c_float, C.c_float, _f32p, _f32p, _i32p]
+    f.restype = C.c_int
+    n, nr = len(kl), len(kr)
+    a = [_f(kl["x"]), _f(kl["y"]), _i(kl["octave"]), _b(dl) if n else np.zeros((1, 32), np.uint8)]
+    b = [_f(kr["x"]), _f(kr["y"]), _i(kr["octave"]), _b(dr) if nr else np.zeros((1, 32), np.uint8)]
+    sc, isc = _f(scale), _f(inv_scale)
+    lk, lp, lpitch = _pyr_args(lpyr)
+    rk, rp, rpitch = _pyr_args(rpyr)
+    lw = np.array([p.shape[1] for p in lk], np.int32); lh = np.array([p.shape[0] for p in lk], np.int32)
+    ur = np.zeros(max(n, 1), np.float32); dep = np.zeros(max(n, 1), np.float32); skipped = np.zeros(1, np.int32)
+    kept = f(n, _ptr(a[0], _f32p), _ptr(a[1], _f32p), _ptr(a[2], _i32p), _ptr(a[3], _u8p),
+             nr, _ptr(b[0], _f32p), _ptr(b[1], _f32p), _ptr(b[2], _i32p), _ptr(b[3], _u8p), len(sc), _ptr(sc, _f32p), _ptr(isc, _f32p),
+             lp, _ptr(lpitch, _i32p), rp, _ptr(rpitch, _i32p), _ptr(lw, _i32p), _ptr(lh, _i32p), mb, mbf,
+             _ptr(ur, _f32p), _ptr(dep, _f32p), _ptr(skipped, _i32p))
+    return ur[:n], dep[:n], kept, int(skipped[0])

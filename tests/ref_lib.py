@@ -309,3 +309,24 @@ def ref_bow_transform(voc_path, desc, levelsup=4):
            C.byref(o["fn"]), O._ptr(o["fnode"], O._u32p), O._ptr(o["fstart"], _i32p), O._ptr(o["ffeat"], O._u32p))
     assert rc == 0, "the reference could not load the vocabulary"
     return O._bow_result(o)
+
+
+def ref_compute_stereo_matches(kl, dl, kr, dr, scale, inv_scale, lpyr, rpyr, mb, mbf):
+    """The reference's own Frame::ComputeStereoMatches (S/Frame.cc:591-763).  Returns (u_right, depth, count)."""
+    import oracle_lib as O
+    f = mlib().refm_compute_stereo_matches
+    f.argtypes = [C.c_int, _f32p, _f32p, _i32p, _u8p, C.c_int, _f32p, _f32p, _i32p, _u8p, C.c_int, _f32p, _f32p,
+                  C.POINTER(_u8p), _i32p, C.POINTER(_u8p), _i32p, _i32p, _i32p, C.c_float, C.c_float, _f32p, _f32p]
+    f.restype = C.c_int
+    n, nr = len(kl), len(kr)
+    a = [_f(kl["x"]), _f(kl["y"]), _i(kl["octave"]), _b(dl) if n else np.zeros((1, 32), np.uint8)]
+    b = [_f(kr["x"]), _f(kr["y"]), _i(kr["octave"]), _b(dr) if nr else np.zeros((1, 32), np.uint8)]
+    sc, isc = _f(scale), _f(inv_scale)
+    lk, lp, lpitch = O._pyr_args(lpyr)
+    rk, rp, rpitch = O._pyr_args(rpyr)
+    lw = np.array([p.shape[1] for p in lk], np.int32); lh = np.array([p.shape[0] for p in lk], np.int32)
+    ur = np.zeros(max(n, 1), np.float32); dep = np.zeros(max(n, 1), np.float32)
+    cnt = f(n, _p(a[0], _f32p), _p(a[1], _f32p), _p(a[2], _i32p), _p(a[3], _u8p),
+            nr, _p(b[0], _f32p), _p(b[1], _f32p), _p(b[2], _i32p), _p(b[3], _u8p), len(sc), _p(sc, _f32p), _p(isc, _f32p),
+            lp, _p(lpitch, _i32p), rp, _p(rpitch, _i32p), _p(lw, _i32p), _p(lh, _i32p), mb, mbf, _p(ur, _f32p), _p(dep, _f32p))
+    return ur[:n], dep[:n], cnt

@@ -427,3 +427,49 @@ def test_bow_transform_oracle_reproduces_reference_golden_vectors():
         voc = synthetic_vocabulary(vi, k, L)
         a = O.bow_transform(voc, vocabulary_features(vi, voc, n), lu)
         assert _same_bow(a, {key: g["%s_%d" % (key, i)] for key in ("word", "value", "node", "start", "feat")})
+
+
+# ---- Frame::ComputeStereoMatches -----------------------------------------------------------------------------------
+def _stereo_case(index, w=640, h=480, nfeat=1000):
+    left = F.synthetic_frame(index, w, h)
+    right = F.stereo_right_frame(left, index)
+    out = []
+    for img in (left, right):
+        ex = O.OracleExtractor(nfeat, 1.2, 8, 20, 7)
+        k, d = ex(img)
+        out.append((k, d, [ex.level_pixels(l) for l in range(8)], ex.scale_factors, ex.inv_scale_factors))
+    return out
+
+
+@needs_refm
+@pytest.mark.parametrize("index,mb,mbf", [(0, 0.1, 40.0), (1, 0.5, 20.0), (2, 0.05, 8.0)])
+def test_compute_stereo_matches_matches_reference(index, mb, mbf):
+    (kl, dl, lp, sc, isc), (kr, dr, rp, _, _) = _stereo_case(index)
+    ur_o, dep_o, kept, skipped = O.compute_stereo_matches(kl, dl, kr, dr, sc, isc, lp, rp, mb, mbf)
+    ur_r, dep_r, cnt = R.ref_compute_stereo_matches(kl, dl, kr, dr, sc, isc, lp, rp, mb, mbf)
+    assert skipped == 0                       # extractor keypoints keep every patch inside the image
+    assert kept == cnt and cnt > 50
+    assert ur_o.tobytes() == ur_r.tobytes() and dep_o.tobytes() == dep_r.tobytes()
+
+
+SGOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_stereo_matches.npz")
+
+
+def test_stereo_oracle_reproduces_reference_golden_vectors():
+    """Vectors from the reference's own extractor + ComputeStereoMatches (tools/gen_golden.py)."""
+    g = np.load(SGOLDEN)
+    assert int(g["count"]) >= 3
+    for i in range(int(g["count"])):
+        idx, w, h, nf = (int(v) for v in g["cfg_%d" % i][:4])
+        mb, mbf = float(g["cfg_%d" % i][4]), float(g["cfg_%d" % i][5])
+        left = F.synthetic_frame(idx, w, h); right = F.stereo_right_frame(left, idx)
+        side = []
+        for img in (left, right):
+            ex = O.OracleExtractor(nf, 1.2, 8, 20, 7)
+            k, d = ex(img)
+            side.append((k, d, [ex.level_pixels(l) for l in range(8)], ex.scale_factors, ex.inv_scale_factors))
+        (kl, dl, lp, sc, isc), (kr, dr, rp, _, _) = side
+        assert np.array_equal(_sha(kl), g["kl_sha_%d" % i]) and np.array_equal(_sha(kr), g["kr_sha_%d" % i])
+        ur, dep, kept, skipped = O.compute_stereo_matches(kl, dl, kr, dr, sc, isc, lp, rp, mb, mbf)
+        assert skipped == 0 and kept == int(g["n_%d" % i])
+        assert ur.tobytes() == g["ur_%d" % i].tobytes() and dep.tobytes() == g["depth_%d" % i].tobytes()

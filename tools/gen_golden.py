@@ -171,3 +171,24 @@ for i, (vi, k, L, n, lu) in enumerate(cfgs):
 out["count"] = len(cfgs)
 np.savez_compressed(os.path.join(OUT, "ref_bow_transform.npz"), **out)
 print("ref_bow_transform.npz", [len(out["word_%d" % i]) for i in range(len(cfgs))])
+
+# Frame::ComputeStereoMatches: the reference's own extractor (keypoints, descriptors, pyramids of both images) feeding
+# the reference's own stereo matcher; the images are regenerated from their seed
+from weiner_slamit_v2_b200.frames import stereo_right_frame  # noqa: E402
+out = {}
+cfgs = [(0, 640, 480, 1000, 0.1, 40.0), (5, 640, 480, 1000, 0.5, 20.0), (7, 752, 480, 1200, 0.11, 47.9)]
+for i, (idx, w, h, nf, mb, mbf) in enumerate(cfgs):
+    left = synthetic_frame(idx, w, h); right = stereo_right_frame(left, idx)
+    side = []
+    for img in (left, right):
+        ex = R.RefExtractor(nf, 1.2, 8, 20, 7)
+        k, d = ex(img)
+        side.append((k, d, [ex.level_pixels(l) for l in range(8)], ex.tables()))
+    (kl, dl, lp, tb), (kr, dr, rp, _) = side
+    ur, dep, cnt = R.ref_compute_stereo_matches(kl, dl, kr, dr, tb["scale"], tb["inv_scale"], lp, rp, mb, mbf)
+    out["cfg_%d" % i] = np.array([idx, w, h, nf, mb, mbf], np.float64)
+    out["ur_%d" % i] = ur; out["depth_%d" % i] = dep; out["n_%d" % i] = cnt
+    out["kl_sha_%d" % i] = digest(kl); out["kr_sha_%d" % i] = digest(kr)
+out["count"] = len(cfgs)
+np.savez_compressed(os.path.join(OUT, "ref_stereo_matches.npz"), **out)
+print("ref_stereo_matches.npz", [int(out["n_%d" % i]) for i in range(len(cfgs))])

@@ -57,6 +57,16 @@ class FusePointsView(C.Structure):
                 ("stride", C.c_int)]
 
 
+MAX_LEVELS = 16
+
+
+class PyramidView(C.Structure):
+    _fields_ = [("nlevels", C.c_int), ("level", vp * MAX_LEVELS), ("frame_stride", C.c_size_t * MAX_LEVELS),
+                ("pitch", C.c_int32 * MAX_LEVELS), ("width", C.c_int32 * MAX_LEVELS), ("height", C.c_int32 * MAX_LEVELS)]
+
+
+DEVICE_VIEWS, DEVICE_PYRAMIDS = 1, 2
+
 # name -> (restype, argtypes); every symbol include/orb_b200.h declares
 SIGNATURES = {
     "orbb200_last_error": (C.c_char_p, []),
@@ -113,6 +123,9 @@ SIGNATURES = {
     "orbb200_undistort_points": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "orbb200_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
     "orbb200_matcher_wait_extractor": (C.c_int, [vp, vp]),
+    "orbb200_extractor_pyramid_view": (C.c_int, [vp, C.POINTER(PyramidView)]),
+    "orbb200_compute_stereo_matches": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(PyramidView),
+                                                 C.POINTER(PyramidView), vp, vp, C.c_int, C.c_float, C.c_float, vp, vp, vp, C.c_int]),
 }
 
 _lib = None

@@ -1609,6 +1609,21 @@ extern "C" int orbb200_extractor_get_level(orbb200_extractor* h, int frame, int 
     return ORBB200_OK;
 }
 
+extern "C" int orbb200_extractor_pyramid_view(orbb200_extractor* h, orbb200_pyramid_view* v)
+{
+    if (!h || !v) { set_error("null argument"); return ORBB200_EINVAL; }
+    if (h->lastBatch < 1 || !h->lastIn) { set_error("no extract call yet"); return ORBB200_EINVAL; }
+    memset(v, 0, sizeof(*v));
+    v->nlevels = h->nlevels;
+    for (int l = 0; l < h->nlevels; l++) {
+        const LevelGeo& g = h->P.lv[l];
+        v->width[l] = g.w; v->height[l] = g.h;
+        if (l == 0) { v->level[0] = h->lastIn; v->frame_stride[0] = (size_t)h->lastInFrameStride; v->pitch[0] = h->lastInPitch; }
+        else { v->level[l] = h->P.pyr + g.pyrOff; v->frame_stride[l] = h->P.pyrFrameBytes; v->pitch[l] = g.pitch; }
+    }
+    return ORBB200_OK;
+}
+
 static int fetch_packed(orbb200_extractor* h, const uint32_t* dsrc, const int* dcount, int maxn, std::vector<uint32_t>& v)
 {
     int n = 0;

@@ -121,6 +121,12 @@ class ORBextractor:
         check(self._L.orbb200_extractor_stage_ms(self._h, ms.ctypes.data))
         return ms
 
+    def pyramid_view(self):
+        """mvImagePyramid of the last batch where it lies in device memory (for compute_stereo_matches)."""
+        v = _lib.PyramidView()
+        check(self._L.orbb200_extractor_pyramid_view(self._h, C.byref(v)))
+        return v
+
     # ---- stage read-back (parity tests; mvImagePyramid) ----
     def level_size(self, level):
         w, h = C.c_int(), C.c_int()

@@ -69,3 +69,22 @@ def low_contrast_frame(index, width=640, height=480):
         x, y = rng.integers(30, width - 60), rng.integers(30, height - 60)
         img[y:y + 25, x:x + 25] = 220
     return img
+
+
+def stereo_right_frame(left, index, max_disparity=48.0, band=40):
+    """The right image of a rectified pair: every band of rows sees the left image shifted by its own (fractional)
+    disparity, linearly interpolated, plus a little noise, so ComputeStereoMatches finds row-aligned matches, a cost
+    minimum inside the +-5 column window and a non-trivial parabola."""
+    rng = np.random.default_rng(9000 + int(index))
+    h, w = left.shape
+    L = left.astype(np.float64)
+    right = np.empty_like(L)
+    xs = np.arange(w)
+    for y0 in range(0, h, band):
+        d = rng.uniform(1.0, max_disparity)
+        src = np.clip(xs + d, 0, w - 1)
+        i0 = np.floor(src).astype(np.int64); f = src - i0
+        i1 = np.minimum(i0 + 1, w - 1)
+        right[y0:y0 + band] = L[y0:y0 + band][:, i0] * (1 - f) + L[y0:y0 + band][:, i1] * f
+    right += rng.integers(-2, 3, right.shape)
+    return np.clip(np.rint(right), 0, 255).astype(np.uint8)

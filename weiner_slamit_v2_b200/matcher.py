@@ -344,6 +344,50 @@ class ORBmatcher:
                                                       med.ctypes.data, 0))
         return best, med
 
+    # ---- Frame::ComputeStereoMatches (S/Frame.cc:591-763), scope row N4 ----
+    def compute_stereo_matches_batch(self, lefts, rights, lpyr, rpyr, scale_factors, inv_scale_factors, mb, mbf):
+        """lefts / rights: per stereo pair (keypoint records, (n, 32) descriptors) = mvKeys / mDescriptors and
+        mvKeysRight / mDescriptorsRight.  lpyr / rpyr: either a _lib.PyramidView of device memory
+        (ORBextractor.pyramid_view()) or, per pair, the list of level images (host arrays, no border).
+        Returns (mvuRight, mvDepth) per pair and the number of stereo matches per pair."""
+        items = len(lefts)
+        keep = []
+
+        def side(fr):
+            stride = max(1, max(len(k) for k, _ in fr))
+            n = np.array([len(k) for k, _ in fr], np.int32)
+            x = _pack([k["x"] for k, _ in fr], stride, np.float32)
+            y = _pack([k["y"] for k, _ in fr], stride, np.float32)
+            o = _pack([k["octave"] for k, _ in fr], stride, np.int32)
+            d = _pack([np.asarray(dd, np.uint8).reshape(-1, 32) for _, dd in fr], stride, np.uint8, (32,))
+            keep.extend([n, x, y, o, d])
+            return FrameView(n.ctypes.data, x.ctypes.data, y.ctypes.data, o.ctypes.data, None, d.ctypes.data, stride), stride
+
+        def pyramid(p):
+            if isinstance(p, _lib.PyramidView):
+                return p, _lib.DEVICE_PYRAMIDS
+            v = _lib.PyramidView()
+            v.nlevels = len(p[0])
+            for l in range(v.nlevels):
+                lv = np.ascontiguousarray(np.stack([np.asarray(q[l], np.uint8) for q in p]))
+                keep.append(lv)
+                v.level[l] = lv.ctypes.data; v.frame_stride[l] = lv.strides[0]; v.pitch[l] = lv.strides[1]
+                v.height[l], v.width[l] = lv.shape[1], lv.shape[2]
+            return v, 0
+
+        lv, ls = side(lefts)
+        rv, rs = side(rights)
+        self._ensure(items, max(ls, rs))
+        lp, lflag = pyramid(lpyr)
+        rp, rflag = pyramid(rpyr)
+        assert lflag == rflag, "both pyramids must live on the same side"
+        sc = np.ascontiguousarray(scale_factors, np.float32); isc = np.ascontiguousarray(inv_scale_factors, np.float32)
+        ur = np.zeros((items, ls), np.float32); dep = np.zeros((items, ls), np.float32); nm = np.zeros(items, np.int32)
+        check(self._L.orbb200_compute_stereo_matches(self._h, items, C.byref(lv), C.byref(rv), C.byref(lp), C.byref(rp), sc.ctypes.data,
+                                                     isc.ctypes.data, len(sc), float(mb), float(mbf), ur.ctypes.data, dep.ctypes.data,
+                                                     nm.ctypes.data, lflag))
+        return [(ur[i, :len(lefts[i][0])], dep[i, :len(lefts[i][0])]) for i in range(items)], nm
+
     # ---- SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (S/ORBmatcher.cc:661-827), scope row N3 ----
     def search_for_triangulation_batch(self, pairs, only_stereo=False):
         """pairs: list of workloads.triangulation_pair()-layout dicts (k1 / k2: x, y, octave, angle, desc, has_mp, u_right,

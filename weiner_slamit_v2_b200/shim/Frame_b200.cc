@@ -1,7 +1,8 @@
-// Frame_b200.cc -- B200 bodies for three Frame methods:
+// Frame_b200.cc -- B200 bodies for four Frame methods:
 //   Frame::UndistortKeyPoints   (replaces S/Frame.cc:529-559)
 //   Frame::ComputeImageBounds   (replaces S/Frame.cc:561-589)
 //   Frame::ComputeBoW           (replaces S/Frame.cc:520-527: the DBoW2 transform runs on the device)
+//   Frame::ComputeStereoMatches (replaces S/Frame.cc:591-763)
 // Compiles against the reference's own Frame.h; guard the two reference bodies with
 // #ifndef ORB_B200_FRAME and add this file.  cv::undistortPoints runs on the device.
 #include "Frame.h"
@@ -139,6 +140,51 @@ void Frame::ComputeBoW()
     for (int k = 0; k < bowN; k++) mBowVec.insert(mBowVec.end(), DBoW2::BowVector::value_type(word[k], value[k]));
     for (int a = 0; a < fvN; a++)
         for (int p = start[a]; p < start[a + 1]; p++) mFeatVec.addFeature(node[a], feat[p]);
+}
+
+void Frame::ComputeStereoMatches()
+{
+    mvuRight = std::vector<float>(N, -1.0f);
+    mvDepth = std::vector<float>(N, -1.0f);
+    const int Nr = (int)mvKeysRight.size();
+    orbb200_matcher* h = tlsHandle.get();
+    if (!h || N == 0 || Nr == 0) return;
+
+    // mvKeys / mvKeysRight as structure-of-arrays; the descriptor matrices are continuous N x 32
+    std::vector<float> lx(N), ly(N), rx(Nr), ry(Nr);
+    std::vector<int32_t> lo(N), ro(Nr);
+    for (int i = 0; i < N; i++) { lx[i] = mvKeys[i].pt.x; ly[i] = mvKeys[i].pt.y; lo[i] = mvKeys[i].octave; }
+    for (int i = 0; i < Nr; i++) { rx[i] = mvKeysRight[i].pt.x; ry[i] = mvKeysRight[i].pt.y; ro[i] = mvKeysRight[i].octave; }
+    const cv::Mat dl = mDescriptors.isContinuous() ? mDescriptors : mDescriptors.clone();
+    const cv::Mat dr = mDescriptorsRight.isContinuous() ? mDescriptorsRight : mDescriptorsRight.clone();
+    int32_t nl = N, nr = Nr, nmatches = 0;
+    orbb200_frame_view left = {&nl, &lx[0], &ly[0], &lo[0], 0, dl.ptr<unsigned char>(), N};
+    orbb200_frame_view right = {&nr, &rx[0], &ry[0], &ro[0], 0, dr.ptr<unsigned char>(), Nr};
+
+    // the pyramids: where the two extractors left them on the device, else the host copies in mvImagePyramid
+    orbb200_pyramid_view lp, rp;
+    int where = ORBB200_DEVICE_PYRAMIDS;
+    if (!mpORBextractorLeft->Handle() || !mpORBextractorRight->Handle() ||
+        orbb200_extractor_pyramid_view(mpORBextractorLeft->Handle(), &lp) != ORBB200_OK ||
+        orbb200_extractor_pyramid_view(mpORBextractorRight->Handle(), &rp) != ORBB200_OK) {
+        where = 0;
+        std::memset(&lp, 0, sizeof(lp)); std::memset(&rp, 0, sizeof(rp));
+        const int L = (int)mpORBextractorLeft->mvImagePyramid.size();
+        lp.nlevels = rp.nlevels = L;
+        for (int l = 0; l < L && l < ORBB200_MAX_LEVELS; l++) {
+            const cv::Mat& a = mpORBextractorLeft->mvImagePyramid[l];
+            const cv::Mat& b = mpORBextractorRight->mvImagePyramid[l];
+            lp.level[l] = a.data; lp.pitch[l] = (int32_t)a.step; lp.width[l] = a.cols; lp.height[l] = a.rows;
+            rp.level[l] = b.data; rp.pitch[l] = (int32_t)b.step; rp.width[l] = b.cols; rp.height[l] = b.rows;
+        }
+    }
+    const int L = (int)mvScaleFactors.size();
+    if (orbb200_compute_stereo_matches(h, 1, &left, &right, &lp, &rp, &mvScaleFactors[0], &mvInvScaleFactors[0], L, mb, mbf,
+                                       &mvuRight[0], &mvDepth[0], &nmatches, where) != ORBB200_OK) {
+        std::fprintf(stderr, "Frame(B200)::ComputeStereoMatches: %s\n", orbb200_last_error());
+        mvuRight.assign(N, -1.0f);
+        mvDepth.assign(N, -1.0f);
+    }
 }
 
 }  // namespace ORB_SLAM2

@@ -43,6 +43,9 @@ public:
     // (0: OpenCV >= 3 taps, 1: OpenCV 2.4.9 taps) used when the device handle is (re)created.
     void SetDevice(int device) { mnDevice = device; }
     void SetBlurTaps(int taps) { mnBlurTaps = taps; }
+    // the device handle of the last call (0 before the first one): Frame::ComputeStereoMatches reads the pyramids
+    // where they lie in device memory through orbb200_extractor_pyramid_view
+    orbb200_extractor* Handle() const { return mpHandle; }
 
 protected:
     bool EnsureHandle(int width, int height);
