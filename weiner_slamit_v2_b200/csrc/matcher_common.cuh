@@ -36,7 +36,7 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 
 // The same distance with 5 POPC instead of 8: three carry-save adders (2 LOP3 each) compress seven of the eight
 // XOR words into one "ones" and three "twos" words.  POPC issues at 16 lanes/clk/SM on sm_100a against 64 for
-// LOP3/IADD3 (tools/int_peak.cu, profiles/r2a_int_peak.json), so in a loop that does nothing but distances the
+// LOP3/IADD3 (tools/int_peak.cu, profiles/r1k_int_peak.json), so in a loop that does nothing but distances the
 // POPC pipe (8 x 8 cycles per warp) is the bound; this form balances it against the ALU pipe (40 / 40 cycles).
 // (inline PTX: left to itself the compiler folds the XORs into the adders and ends up with 20 LOP3 instead of 14)
 __device__ __forceinline__ uint32_t lop_xor(uint32_t a, uint32_t b)
@@ -120,6 +120,28 @@ __device__ __forceinline__ void top4_insert(uint4& t, uint32_t k)
     m = min(t.y, k); k = max(t.y, k); t.y = m;
     m = min(t.z, k); k = max(t.z, k); t.z = m;
     t.w = min(t.w, k);
+}
+
+// The speculative greedy resolve (k_search_init / k_search_proj / k_search_last): each lane has decided its own query
+// against the current state; `w` is the keypoint whose state the lane would change (-1: none) and kid[] the <= 4
+// keypoints whose state it read.  A lane is final when no EARLIER lane writes one of the keypoints it read.  Returns
+// the first lane that is not final (32 if all are): writers publish their lane number in `claim` (one byte per
+// keypoint, 0xff when idle; the lowest lane of several writers of one keypoint), everybody looks its reads up, and
+// the claims are withdrawn again -- a constant number of steps instead of one broadcast per writer.
+__device__ __forceinline__ int clean_prefix(uint8_t* claim, int lane, int w, const int (&kid)[4], bool blockedSelf)
+{
+    const unsigned same = __match_any_sync(0xffffffffu, w >= 0 ? w : -1 - lane);
+    const bool leader = w >= 0 && lane == __ffs(same) - 1;
+    if (leader) claim[w] = (uint8_t)lane;
+    __syncwarp();
+    bool blocked = blockedSelf;
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+        if (kid[e] >= 0 && (int)claim[kid[e]] < lane) blocked = true;
+    __syncwarp();
+    if (leader) claim[w] = 0xff;
+    const unsigned bm = __ballot_sync(0xffffffffu, blocked);
+    return bm ? __ffs(bm) - 1 : 32;
 }
 
 // Frame::AssignFeaturesToGrid as CSR for `items` frames on stream st (kernel in orb_matcher.cu)

@@ -303,8 +303,10 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
 
     // vMatchedDistance (:419) lives in shared memory as 16 bits (0xffff = INT_MAX; real values are <= TH_LOW)
     extern __shared__ uint16_t s_vmd_all[];
-    uint16_t* vmd = s_vmd_all + (size_t)(threadIdx.x >> 5) * ((P.f2.stride + 7) & ~7);
-    for (int i = lane; i < n2; i += 32) { vmd[i] = 0xffff; m21[i] = -1; }
+    const int padded = (P.f2.stride + 15) & ~15;
+    uint16_t* vmd = s_vmd_all + (size_t)(threadIdx.x >> 5) * padded;
+    uint8_t* claim = reinterpret_cast<uint8_t*>(s_vmd_all + (size_t)(blockDim.x >> 5) * padded) + (size_t)(threadIdx.x >> 5) * padded;
+    for (int i = lane; i < n2; i += 32) { vmd[i] = 0xffff; m21[i] = -1; claim[i] = 0xff; }
     for (int i = lane; i < n1; i += 32) { m12[i] = -1; hbin[i] = -1; }
     __syncwarp();
 
@@ -386,16 +388,7 @@ __global__ void __launch_bounds__(128) k_search_init(const InitParams P)
             stop = first + 1;
         } else {
             accept = pending && resolved && tb <= TH_LOW && (float)tb < __fmul_rn((float)ts, P.nnratio);   // :463-465
-            bool blocked = pending && !resolved;
-            unsigned wm = __ballot_sync(0xffffffffu, accept);
-            while (wm) {
-                const int j = __ffs(wm) - 1;
-                wm &= wm - 1;
-                const int wj = __shfl_sync(0xffffffffu, best2, j);
-                if (lane > j && (wj == kid[0] || wj == kid[1] || wj == kid[2] || wj == kid[3])) blocked = true;
-            }
-            const unsigned bm = __ballot_sync(0xffffffffu, blocked);
-            stop = bm ? __ffs(bm) - 1 : 32;
+            stop = clean_prefix(claim, lane, accept ? best2 : -1, kid, pending && !resolved);
         }
         if (accept && lane < stop) {          // the committed queries of one round take distinct keypoints
             const int old = m21[best2];
@@ -580,10 +573,12 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
     // occupancy of every keypoint (holds a map point with observations -> skipped, :89-91) as one byte in shared
     // memory: the greedy state is read several times per map point and must not cost a global round trip
     extern __shared__ uint8_t s_occ_all[];
-    uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * ((P.f.stride + 15) & ~15);
+    uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * 2 * ((P.f.stride + 15) & ~15);
+    uint8_t* claim = occ + ((P.f.stride + 15) & ~15);
     for (int idx = lane; idx < n; idx += 32) {
         const int held = kpmp[idx];
         occ[idx] = held != -1 && (held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0)) > 0;
+        claim[idx] = 0xff;
     }
     __syncwarp();
 
@@ -681,16 +676,7 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
         const bool accept = pending && resolved && t.b <= TH_HIGH &&
                             !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s));          // :120-127
         const int w = (accept && obs > 0) ? bestId : -1;       // the occupancy this map point would set
-        bool blocked = pending && !resolved;
-        unsigned wm = __ballot_sync(0xffffffffu, w >= 0);
-        while (wm) {
-            const int j = __ffs(wm) - 1;
-            wm &= wm - 1;
-            const int wj = __shfl_sync(0xffffffffu, w, j);
-            if (lane > j && (wj == kid[0] || wj == kid[1] || wj == kid[2] || wj == kid[3])) blocked = true;
-        }
-        const unsigned bm = __ballot_sync(0xffffffffu, blocked && pending);
-        const int stop = bm ? __ffs(bm) - 1 : 32;
+        const int stop = clean_prefix(claim, lane, w, kid, pending && !resolved);
         const bool commit = accept && lane < stop;
         nmatches += __popc(__ballot_sync(0xffffffffu, commit));
         // several map points without observations may take the same keypoint; the last one in list order stays (:125)
@@ -834,8 +820,8 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     k_init_topk<<<dim3((f1->stride + orbb200::TOPK_QPB - 1) / orbb200::TOPK_QPB, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_init_topk");
     {
-        const size_t sm = 4 * sizeof(uint16_t) * (size_t)((f2->stride + 7) & ~7);
-        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
+        const size_t sm = 4 * 3 * (size_t)((f2->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 16 * 1024); return ORBB200_EINVAL; }
         if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_search_init<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
@@ -897,8 +883,8 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
     k_proj_topk<<<dim3((mp->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_proj_topk");
     {
-        const size_t sm = 4 * (size_t)((f->stride + 15) & ~15);
-        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        const size_t sm = 8 * (size_t)((f->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
         if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_search_proj<<<(items + 3) / 4, 128, sm, st>>>(P);
     }

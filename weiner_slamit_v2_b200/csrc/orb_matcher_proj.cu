@@ -241,10 +241,12 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
     int* hidx = P.histIdx + lo;
 
     extern __shared__ uint8_t s_occ_all[];
-    uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * ((P.f.stride + 15) & ~15);
+    uint8_t* occ = s_occ_all + (size_t)(threadIdx.x >> 5) * 2 * ((P.f.stride + 15) & ~15);
+    uint8_t* claim = occ + ((P.f.stride + 15) & ~15);
     for (int idx = lane; idx < n; idx += 32) {
         const int held = kpmp[idx];
         occ[idx] = held != -1 && (P.kind != 0 || (held >= 0 ? P.mpObs[lo + held] : (kpobs ? kpobs[idx] : 0)) > 0);
+        claim[idx] = 0xff;
     }
     for (int i = lane; i < nl; i += 32) hbin[i] = -1;
     __syncwarp();
@@ -311,16 +313,7 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
         } else {
             take = pending && resolved && bestDist <= accept;                     // :1436-1452, :1561-1579
             const int w = (take && obs > 0) ? bestIdx : -1;        // the occupancy this point would set
-            bool blocked = pending && !resolved;
-            unsigned wm = __ballot_sync(0xffffffffu, w >= 0);
-            while (wm) {
-                const int j = __ffs(wm) - 1;
-                wm &= wm - 1;
-                const int wj = __shfl_sync(0xffffffffu, w, j);
-                if (lane > j && (wj == kid[0] || wj == kid[1] || wj == kid[2] || wj == kid[3])) blocked = true;
-            }
-            const unsigned bm = __ballot_sync(0xffffffffu, blocked);
-            stop = bm ? __ffs(bm) - 1 : 32;
+            stop = clean_prefix(claim, lane, w, kid, pending && !resolved);
         }
         const bool commit = take && lane < stop;
         nmatches += __popc(__ballot_sync(0xffffffffu, commit));
@@ -534,8 +527,8 @@ extern "C" int orbb200_search_by_projection_last_frame(orbb200_matcher* m, int i
     k_last_topk<<<dim3((last->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_last_topk");
     {
-        const size_t sm = 4 * (size_t)((cur->stride + 15) & ~15);
-        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        const size_t sm = 8 * (size_t)((cur->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
         if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
@@ -600,8 +593,8 @@ extern "C" int orbb200_search_by_projection_keyframe(orbb200_matcher* m, int ite
     k_last_topk<<<dim3((kf->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_last_topk");
     {
-        const size_t sm = 4 * (size_t)((cur->stride + 15) & ~15);
-        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        const size_t sm = 8 * (size_t)((cur->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
         if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
@@ -722,8 +715,8 @@ extern "C" int orbb200_search_by_projection_sim3(orbb200_matcher* m, int items, 
     k_last_topk<<<dim3((pts->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_last_topk");
     {
-        const size_t sm = 4 * (size_t)((kf->stride + 15) & ~15);
-        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 50 * 1024); return ORBB200_EINVAL; }
+        const size_t sm = 8 * (size_t)((kf->stride + 15) & ~15);
+        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
         if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
