@@ -726,8 +726,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
 // byte windows cut out of three words with PRMT; vertical pass over a 7-row register window of 16-bit
 // row sums (loop unrolled by 7 so the window rotates by renaming), symmetric taps folded;
 // out = (sum + 2^15) >> 16 is byte 2 of the accumulator.
-constexpr int BL_ROWS = 36, BL_WARPS = 4;     // 36 output rows + 6 halo rows = 6 groups of 7 input rows
+constexpr int BL_ROWS = 24, BL_WARPS = 4;     // 24 output rows + 6 halo rows = 5 groups of 6 input rows (measured 24 / 36: 0.243 / 0.247 ms)
 constexpr int BL_IN_ROWS = BL_ROWS + 6;
+constexpr int BL_CTAS_PER_SM = 5;             // persistent CTAs per SM (shared memory: 9.6 KB per warp)
 constexpr int BL_ROW_BYTES = 160;             // image columns x0-16 .. x0+143 (16-byte aligned window around 128 px)
 constexpr int BL_STAGE_BYTES = BL_IN_ROWS * BL_ROW_BYTES;
 constexpr int BL_WARP_BYTES = 2 * BL_STAGE_BYTES + 16;
@@ -769,6 +770,7 @@ __device__ __forceinline__ bool blur_tile(const ExtractParams& P, long long t, B
     return P.lkpCount[frame * P.nlevels + l] != 0;
 }
 
+template <bool VARIANT>     // false: OpenCV >= 3 taps {18,34,48,56,48,34,18}; true: OpenCV 2.4.9 taps {18,34,49,55,49,34,18}
 __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -784,9 +786,10 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
 
     const long long nTiles = (long long)P.totalBlurTiles * P.batch;
     const long long stride = (long long)gridDim.x * BL_WARPS;
-    const uint32_t k0 = 18, k1 = 34, k2 = P.blurVariant ? 49 : 48, k3 = P.blurVariant ? 55 : 56;
-    const uint32_t kA = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);     // taps for p[x-3..x]
-    const uint32_t kB = k2 | (k1 << 8) | (k0 << 16);                  // taps for p[x+1..x+3]
+    constexpr uint32_t k0 = 18, k1 = 34, k2 = VARIANT ? 49 : 48, k3 = VARIANT ? 55 : 56;
+    constexpr uint32_t kA = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);     // taps for p[x-3..x]
+    constexpr uint32_t kB = k2 | (k1 << 8) | (k0 << 16);                  // taps for p[x+1..x+3]
+    constexpr uint32_t kV01 = k0 | (k1 << 8), kV23 = k2 | (k3 << 8), kV45 = k2 | (k1 << 8);   // vertical taps by row pair
 
     // issue the 42 row copies of tile bt into ring stage s
     auto issue = [&](const BlurTile& bt, int s) {
@@ -826,36 +829,52 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
         const LevelGeo& g = P.lv[cur.l];
         const int x0 = cur.x0 + 4 * lane;
         if (x0 < g.w) {
-            uint8_t* dst = P.blur + (long long)cur.frame * P.blurFrameBytes + g.blurOff;
             const bool left = x0 == 0, rightFix = (cur.l == 0) && !P.inPadded && (x0 + 4 >= g.w);
-            const int yEnd = min(cur.y0 + BL_ROWS, g.h);
+            const int nOut = min(BL_ROWS, g.h - cur.y0);                             // output rows of this tile
             const uint8_t* sb = ring + stage * BL_STAGE_BYTES + 12 + 4 * lane;      // word holding columns x0-4..x0-1
-            int H[7][4];
-#pragma unroll 1
-            for (int grp = 0; grp < BL_IN_ROWS / 7; grp++) {
+            uint8_t* outp = P.blur + (long long)cur.frame * P.blurFrameBytes + g.blurOff + (long long)cur.y0 * g.pitch + x0;
+            // horizontal pass of one staged row: 4 sums of 7 taps (<= 255 * 256, 16 bits), two IDP.4A each
+            auto hrow = [&](int ir, uint32_t (&h)[4]) {
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(sb + ir * BL_ROW_BYTES);
+                uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                if (left) w0 = __byte_perm(w1, w2, 0x1234);            // p[-4..-1] = p[4], p[3], p[2], p[1]
+                if (rightFix) w2 = __byte_perm(w0, w1, 0x3456);        // p[w..w+3] = p[w-2], p[w-3], p[w-4], p[w-5]
+                h[0] = __dp4a(__byte_perm(w0, w1, 0x4321), kA, __dp4a(__byte_perm(w1, w2, 0x4321), kB, 0u));
+                h[1] = __dp4a(__byte_perm(w0, w1, 0x5432), kA, __dp4a(__byte_perm(w1, w2, 0x5432), kB, 0u));
+                h[2] = __dp4a(__byte_perm(w0, w1, 0x6543), kA, __dp4a(__byte_perm(w1, w2, 0x6543), kB, 0u));
+                h[3] = __dp4a(w1, kA, __dp4a(w2, kB, 0u));
+            };
+            // Vertical pass on PAIRS of rows: Q[s][j] = H[r][j] | H[r + 1][j] << 16 for the six most recent pairs, so an
+            // output row is k6 * H[newest] + three IDP.2A (two taps each) instead of seven multiplies; the six pair slots
+            // rotate with the unrolled row index.
+            uint32_t Q[6][4], prev[4], cur4[4];
+            hrow(0, prev);
 #pragma unroll
-                for (int u = 0; u < 7; u++) {
-                    const int ir = grp * 7 + u;
-                    const int oy = cur.y0 + ir - 6;                    // output row completed by this input row
-                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(sb + ir * BL_ROW_BYTES);
-                    uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
-                    if (left) w0 = __byte_perm(w1, w2, 0x1234);        // p[-4..-1] = p[4], p[3], p[2], p[1]
-                    if (rightFix) w2 = __byte_perm(w0, w1, 0x3456);    // p[w..w+3] = p[w-2], p[w-3], p[w-4], p[w-5]
-                    H[u][0] = __dp4a(__byte_perm(w0, w1, 0x4321), kA, __dp4a(__byte_perm(w1, w2, 0x4321), kB, 0u));
-                    H[u][1] = __dp4a(__byte_perm(w0, w1, 0x5432), kA, __dp4a(__byte_perm(w1, w2, 0x5432), kB, 0u));
-                    H[u][2] = __dp4a(__byte_perm(w0, w1, 0x6543), kA, __dp4a(__byte_perm(w1, w2, 0x6543), kB, 0u));
-                    H[u][3] = __dp4a(w1, kA, __dp4a(w2, kB, 0u));
-                    if (oy >= cur.y0 && oy < yEnd) {
+            for (int u = 1; u < 6; u++) {                                            // rows 1..5 only fill the window
+                hrow(u, cur4);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410); prev[j] = cur4[j]; }
+            }
+#pragma unroll 1
+            for (int grp = 1; grp < BL_IN_ROWS / 6; grp++) {
+#pragma unroll
+                for (int u = 0; u < 6; u++) {
+                    const int ir = grp * 6 + u;                                      // completes output row ir - 6
+                    if (ir - 6 < nOut) {
+                        hrow(ir, cur4);
                         uint32_t acc[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            // window rows: oldest = slot (u+1)%7 ... newest = slot u
-                            acc[j] = 32768u + k0 * (uint32_t)(H[(u + 1) % 7][j] + H[u][j]) + k1 * (uint32_t)(H[(u + 2) % 7][j] + H[(u + 6) % 7][j]) +
-                                     k2 * (uint32_t)(H[(u + 3) % 7][j] + H[(u + 5) % 7][j]) + k3 * (uint32_t)H[(u + 4) % 7][j];
-                            if (P.blurVariant) acc[j] = min(acc[j], 0x00ffffffu);    // taps sum to 257: saturate like OpenCV
+                            // pairs ending at rows ir-5, ir-3, ir-1 sit in slots (u+1)%6, (u+3)%6, (u+5)%6
+                            acc[j] = __dp2a_lo(Q[(u + 1) % 6][j], kV01, __dp2a_lo(Q[(u + 3) % 6][j], kV23,
+                                     __dp2a_lo(Q[(u + 5) % 6][j], kV45, k0 * cur4[j] + 32768u)));
+                            if (VARIANT) acc[j] = min(acc[j], 0x00ffffffu);          // taps sum to 257: saturate like OpenCV
+                            Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410);
+                            prev[j] = cur4[j];
                         }
                         const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
-                        *reinterpret_cast<uint32_t*>(dst + (long long)oy * g.pitch + x0) = __byte_perm(lo, hi, 0x5410);
+                        *reinterpret_cast<uint32_t*>(outp) = __byte_perm(lo, hi, 0x5410);
+                        outp += g.pitch;
                     }
                 }
             }
@@ -1314,7 +1333,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         ? cudaFuncSetAttribute(k_fast<36, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem)
         : cudaFuncSetAttribute(k_fast<24, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qtSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
         set_error("extractor_create: %s", cudaGetErrorString(e));
@@ -1446,8 +1466,9 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
     STAGE_MARK(3);
     {   // persistent warps: a few CTAs per SM walk the (frame, level, tile) list
         const long long tiles = (long long)h->totalBlurTiles * batch;
-        const int ctas = (int)std::min<long long>((tiles + BL_WARPS - 1) / BL_WARPS, (long long)h->numSMs * 4);
-        k_blur<<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, st>>>(P);
+        const int ctas = (int)std::min<long long>((tiles + BL_WARPS - 1) / BL_WARPS, (long long)h->numSMs * BL_CTAS_PER_SM);
+        if (P.blurVariant) k_blur<true><<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, st>>>(P);
+        else k_blur<false><<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_blur"); launches++;
     STAGE_MARK(4);
