@@ -117,13 +117,21 @@ __global__ void k_pad_level0(uint8_t* base, long long frameStride, int pitch, in
 // Columns w..w+3 are written too: they hold the REFLECT_101 continuation that k_blur reads.
 constexpr int RZ_ROWS = 8, RZ_WARPS = 4;
 
-__device__ __forceinline__ void resize_hrow(const uint8_t* row, int a, bool ld1, bool ld2, uint32_t selShift,
-                                            const uint32_t (&sel)[4], const uint32_t (&coef)[4], uint32_t (&r)[4])
+struct ResizeRaw { uint32_t w0, w1, w2; };     // the three aligned source words a thread's 4 columns draw from
+
+__device__ __forceinline__ ResizeRaw resize_load(const uint8_t* row, int a, bool ld1, bool ld2)
 {
-    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(row + a));
-    const uint32_t w1 = ld1 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 4)) : 0u;
-    const uint32_t w2 = ld2 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 8)) : 0u;
-    const uint32_t lo = __byte_perm(w0, w1, selShift), hi = __byte_perm(w1, w2, selShift);
+    ResizeRaw w;
+    w.w0 = __ldg(reinterpret_cast<const uint32_t*>(row + a));
+    w.w1 = ld1 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 4)) : 0u;
+    w.w2 = ld2 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 8)) : 0u;
+    return w;
+}
+
+__device__ __forceinline__ void resize_hrow(const ResizeRaw& w, uint32_t selShift, const uint32_t (&sel)[4],
+                                            const uint32_t (&coef)[4], uint32_t (&r)[4])
+{
+    const uint32_t lo = __byte_perm(w.w0, w.w1, selShift), hi = __byte_perm(w.w1, w.w2, selShift);
 #pragma unroll
     for (int j = 0; j < 4; j++) r[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;
 }
@@ -159,30 +167,36 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
     }
     const bool ld1 = a + 4 < rowBytes, ld2 = a + 8 < rowBytes;
 
+    // (the row-table entry of the next destination row is loaded one row ahead: table entry -> source row is a
+    // dependent load chain; prefetching the source words as well costs more in registers than it hides, measured)
     const short4* yt = P.tabs + g.ytabOff;
     const int yEnd = min(yBeg + RZ_ROWS, g.h);
     uint32_t r0[4], r1[4];
     int cur1 = -1;                                            // source row held in r1
+    short4 tnext = __ldg(yt + yBeg);
+    uint8_t* outp = dst + (long long)yBeg * g.pitch + x0;
     for (int y = yBeg; y < yEnd; y++) {
-        const short4 ty = __ldg(yt + y);
+        const short4 ty = tnext;
+        tnext = __ldg(yt + min(y + 1, g.h - 1));
         if (ty.x == cur1) {
 #pragma unroll
             for (int j = 0; j < 4; j++) r0[j] = r1[j];
         } else {
-            resize_hrow(src + (long long)ty.x * sp, a, ld1, ld2, selShift, sel, coef, r0);
+            resize_hrow(resize_load(src + (long long)ty.x * sp, a, ld1, ld2), selShift, sel, coef, r0);
         }
         if (ty.y == ty.x) {
 #pragma unroll
             for (int j = 0; j < 4; j++) r1[j] = r0[j];
         } else {
-            resize_hrow(src + (long long)ty.y * sp, a, ld1, ld2, selShift, sel, coef, r1);
+            resize_hrow(resize_load(src + (long long)ty.y * sp, a, ld1, ld2), selShift, sel, coef, r1);
         }
         cur1 = ty.y;
         const uint32_t B0 = (uint32_t)ty.z << 16, B1 = (uint32_t)ty.w << 16;
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) o[j] = min((__umulhi(B0, r0[j]) + __umulhi(B1, r1[j]) + 2u) >> 2, 255u);
-        *reinterpret_cast<uint32_t*>(dst + (long long)y * g.pitch + x0) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        *reinterpret_cast<uint32_t*>(outp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        outp += g.pitch;
     }
 }
 
