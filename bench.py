@@ -355,6 +355,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _int_roofline(evals_per_s):
+    """Matching is bound by the integer pipes, not by bytes: the denominator is the POPC issue rate
+    measured on this GPU model by tools/int_peak.cu (profiles/r1k_int_peak.json), at the 5 POPC per 256-bit
+    evaluation the carry-save distance needs (the 14 LOP3 + ~6 other ALU instructions per evaluation put the ALU
+    pipe at the same level: 63.3 lanes/clk/SM / 20.4)."""
+    p = os.path.join(ROOT, "profiles", "r1k_int_peak.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        k = json.load(f)
+    peak = k["popc_per_clk_per_sm"] * k["sms"] * k["sm_clock_mhz"] * 1e6 / 5.0
+    return {"bound": "integer pipe (POPC)", "achieved": evals_per_s / 1e9, "peak": peak / 1e9, "unit": "G evaluations/s", "frac": evals_per_s / peak,
+            "peak_source": "profiles/r1k_int_peak.json: %.2f POPC lanes/clk/SM x %d SMs x %.0f MHz / 5 POPC per evaluation; whole call "
+                           "(grid + top-4 + greedy resolve) in the numerator" % (k["popc_per_clk_per_sm"], k["sms"], k["sm_clock_mhz"])}
+
+
 def run_matching(local, steps):
     """configs[2] and configs[4]: SearchForInitialization on 4096 brute-force-shaped pairs (1000 x 1000
     descriptors, ratio 0.9) and SearchByProjection on 512 frames (10k map points vs 2000 keypoints), data
@@ -418,7 +434,8 @@ def run_matching(local, steps):
     out["search_for_initialization"] = {
         "workload": "4096 frame pairs, 1000 x 1000 descriptors per pair (all octave 0, window > image), ratio 0.9, checkOri",
         "ms_per_step": ms, "pairs_per_s": items / ms * 1e3, "distance_evals_per_s": items * n * n / ms * 1e3,
-        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h),
+        "roofline": _int_roofline(items * n * n / ms * 1e3)}
     del t1, t2, prev, prev0, m12
     L.orbb200_matcher_destroy(h)
 
