@@ -1,8 +1,8 @@
-"""Regenerate profiles/README.md from the committed measurement files (developer tool): python tools/profiles_readme.py r1i"""
+"""Regenerate profiles/README.md from the committed measurement files (developer tool): python tools/profiles_readme.py r1k"""
 import csv, json, os, sys
 from collections import defaultdict
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1i"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1k"
 P = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
 J = lambda n: json.load(open(os.path.join(P, n)))
 l = J(tag + "_bench.json")
@@ -30,16 +30,25 @@ for k in stage:
                                                         ("%.1f %%" % (100 * ev[s] / evtot)) if s else "")
 rz = [e for e in d if e["kernel"] == "k_resize"]
 ktab = "| kernel (one 256-frame launch) | time us | issue slots busy | resident warps | DRAM read MB | DRAM write MB | DRAM % of peak | regs | warp instructions |\n|---|---|---|---|---|---|---|---|---|\n"
-ktab += "| `k_resize` x7 (levels 1..7) | %.0f | %.0f-%.0f %% | %.0f-%.0f %% | %.0f | %.0f | %.0f-%.0f | 40 | %.0f M |\n" % (
+ktab += "| `k_resize` x7 (levels 1..7) | %.0f | %.0f-%.0f %% | %.0f-%.0f %% | %.0f | %.0f | %.0f-%.0f | %d | %.0f M |\n" % (
     sum(e["time_us"] for e in rz), min(e["issue_active_pct"] for e in rz), max(e["issue_active_pct"] for e in rz),
     min(e["warps_active_pct"] for e in rz), max(e["warps_active_pct"] for e in rz), sum(e["dram_read_MB"] for e in rz),
-    sum(e["dram_write_MB"] for e in rz), min(e["dram_pct"] for e in rz), max(e["dram_pct"] for e in rz), sum(e["inst_executed"] for e in rz) / 1e6)
+    sum(e["dram_write_MB"] for e in rz), min(e["dram_pct"] for e in rz), max(e["dram_pct"] for e in rz), int(rz[0]["regs"]), sum(e["inst_executed"] for e in rz) / 1e6)
 for e in d:
     if e["kernel"] != "k_resize":
         ktab += "| `%s` | %.0f | %.0f %% | %.0f %% | %.0f | %.0f | %.1f | %d | %.0f M |\n" % (
             e["kernel"], e["time_us"], e["issue_active_pct"], e["warps_active_pct"], e["dram_read_MB"], e["dram_write_MB"], e["dram_pct"],
             int(e["regs"]), e["inst_executed"] / 1e6)
 m, p, c = l["matching"], l["pipeline"], l["cpu_baseline"]
+st = l.get("stereo")
+mk = {e["kernel"]: e for e in J(tag + "_ncu_match_summary.json")}
+ip = J("r1k_int_peak.json")
+sfi = m["search_for_initialization"]
+mtab = "| kernel (longest launch) | time us | issue slots busy | ALU pipe | resident warps | regs | warp instructions |\n|---|---|---|---|---|---|---|\n"
+for k in ("k_build_grid", "k_init_topk", "k_search_init", "k_proj_topk", "k_search_proj", "k_last_topk", "k_search_last"):
+    if k in mk:
+        e = mk[k]
+        mtab += "| `%s` | %.0f | %.0f %% | %.0f %% | %.0f %% | %d | %.0f M |\n" % (k, e["time_us"], e["issue_active_pct"], e.get("alu_pipe_pct", 0), e["warps_active_pct"], int(e["regs"]), e["inst_executed"] / 1e6)
 mrows = "\n".join("| `%s` | %s | %.2f |" % (k, v["workload"], v.get("ms_per_step", v.get("ms_per_call"))) for k, v in m.items())
 scale = ""
 for f, what in (("_bench_2gpu", None), ("_bench_4gpu", "4 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_8gpu", "8 GPUs, 256 VGA frames per GPU (weak)"),
@@ -62,7 +71,9 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 | `traffic.json` | `dram__bytes_read.sum + dram__bytes_write.sum` per launch and stage from that capture; `bench.py` reports it as `roofline.traffic` | |
 | `{tag}_bench_4gpu.json`, `{tag}_bench_8gpu.json`, `{tag}_bench_hd_1gpu.json`, `{tag}_bench_hd_4gpu.json` | scaling runs of the current code (below) | `torchrun --nproc-per-node N bench.py --gpus N [--workload hd]` |
 | `r1j_bench_8gpu.json`, `r1j_topology_8gpu.txt` | the 8-GPU run repeated with each rank bound to its GPU's CPU set (no change: the box is one NUMA node with 32 virtual CPUs for 8 ranks) | |
-| `r1h_ncu_match_summary.json` | `ncu --set full` of the matcher kernels of the first two matching configs (largest launch per kernel) | `ncu --set full ... -k regex:"k_init_topk|k_search_init|k_proj_topk|k_search_proj|..." -c 24 python tools/prof_match.py` |
+| `{tag}_ncu_match_summary.json` | `ncu --set full` of the matcher kernels (longest launch per kernel) | `ncu --set full ... -k regex:"k_init_topk|k_search_init|k_proj_topk|k_search_proj|k_last_topk|k_search_last|k_build_grid" -c 14 python tools/prof_match.py`, summarised by `tools/ncu_match_summary.py` |
+| `r1k_int_peak.json` | integer-pipe peaks (POPC, LOP3, IADD3 lanes per clock and SM) and register-only Hamming rates: the matching roofline's denominator | `tools/int_peak.cu` |
+| `r1i_*`, `r1h_ncu_match_summary.json` | the previous step of this round (before the carry-save distance, the speculative resolve, the row-pair blur and the stereo row): 152 k frames/s, SearchForInitialization 12.3 ms | |
 | `r1c_*` ... `r1h_*` | earlier steps of this round, kept for the record (`r1f`: FAST 0.76 ms, describe 0.32 ms; `r1e`: FAST 0.85 ms) | |
 | `r1a_*`, `r1b_*` | first bit-exact CUDA path, before any tuning | |
 | `tools/profiles_readme.py` | writes this file from the ones above | |
@@ -76,6 +87,7 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 * CPU reference arm (`oracle/_ref` = the reference's own `ORBextractor.cc`, {c['cores']} host threads): {c['value']:.0f} frames/s
 * SM clock {l['clocks']['sm_mhz']:.0f} MHz of {l['clocks']['sm_max_mhz']:.0f}, throttle reasons {l['clocks']['reasons']}
 * device pipeline (128 frame pairs: 2 x extraction + undistort/grid + SearchForInitialization, no host round trip): {p['ms_per_step']:.2f} ms = {p['frames_per_s']:.0f} frames/s
+* stereo pipeline (128 rectified pairs: 2 x extraction + keypoint views + ComputeStereoMatches on the extractors' device pyramids): {st['ms_per_step']:.2f} ms = {st['pairs_per_s']:.0f} pairs/s; the stereo matcher alone {st['stereo_matcher_ms']:.3f} ms
 
 ### scaling (frames/s: device-resident | end to end streamed | end to end blocking call)
 
@@ -94,11 +106,15 @@ past 4 GPUs: eight ranks share one virtual host (32 vCPUs, one NUMA node, `r1j_t
 |---|---|---|
 {mrows}
 
-`k_init_topk` (the 4096 x 1000 x 1000 brute-force-shaped config) runs 7.9 G warp instructions in 10.9 ms at 62 % issue
-utilisation: it is bound by the integer pipe (8 XOR + 8 POPC per 256-bit pair).  `k_search_proj` / `k_search_init` are the
-greedy, order-dependent halves: one warp per frame (pair), so 512 frames occupy 6 % of the machine and the time is a
-dependent chain, not throughput; it shrinks per frame as the batch grows (`r1h_ncu_match_summary.json`).
+The headline matching config (4096 x 1000 x 1000 = 4.1 G distance evaluations) is bound by the integer pipes, not by bytes.
+`tools/int_peak.cu` measured them on this GPU (`r1k_int_peak.json`): {ip['popc_per_clk_per_sm']:.1f} POPC and {ip['lop3_per_clk_per_sm']:.1f} LOP3 lanes per clock and SM; a
+register-only loop reaches {ip['hamming256_Geval_s']['popc8']:.0f} G evaluations/s with the plain 8-POPC distance and {ip['hamming256_Geval_s']['csa_popc6']:.0f} / {ip['hamming256_Geval_s']['csa_popc4']:.0f} G/s with 6 / 4 POPC after
+carry-save adders.  `k_init_topk` uses the 5-POPC form (POPC bound: {sfi['roofline']['peak']:.0f} G evaluations/s); the whole call (grid + top-4 +
+greedy resolve) reaches **{sfi['roofline']['achieved']:.0f} G evaluations/s = {100*sfi['roofline']['frac']:.0f} % of that bound** (`{tag}_bench.json: matching.search_for_initialization.roofline`), the kernel alone
+{4096e6/mk['k_init_topk']['time_us']/1e3:.0f} G/s with the ALU pipe {mk['k_init_topk'].get('alu_pipe_pct',0):.0f} % busy (`{tag}_ncu_match_summary.json`).  The greedy, order-dependent halves (`k_search_*`) run one
+warp per frame (pair) and decide 32 queries speculatively per round; their time is a dependent chain per frame, not throughput.
 
+{mtab}
 ### kernel shares: ncu launch list vs CUDA events
 
 The ncu pass covers the whole short bench run (3 warm-up + 2 timed device-resident steps of 256 frames, then the host-call
@@ -116,7 +132,7 @@ lost to dependent-load latency.  `k_fast` (the kernel `bench.py` names in `roofl
 launch against {l['roofline']['achieved']*ev['fast']:.0f} MB algorithmic, so there are no wasted re-reads; it executes {fast['inst_executed']/1e6:.0f} M warp instructions per launch
 (about {fast['inst_executed']/243200:.0f} per 30 x 30-px cell) at {fast['issue_active_pct']:.0f} % issue utilisation, which is what its {ev['fast']:.2f} ms is made of.  The work this round went into removing
 instructions (`{tag}_ncu_source_k_fast.json` shows where the remaining ones are): 1.80 ms -> {ev['fast']:.2f} ms for `k_fast`,
-0.60 -> {ev['describe']:.2f} ms for `k_describe`, 3.88 ms -> {l['ms_per_step']:.2f} ms for the step.
+0.60 -> {ev['describe']:.2f} ms for `k_describe`, 0.91 -> {ev['blur']:.2f} ms for `k_blur`, 3.88 ms -> {l['ms_per_step']:.2f} ms for the step.
 
 ## r1a/r1b (first correct path, before tuning) -- kept for the record
 

@@ -145,7 +145,7 @@ __device__ __forceinline__ int clean_prefix(uint8_t* claim, int lane, int w, con
 }
 
 // Frame::AssignFeaturesToGrid as CSR for `items` frames on stream st (kernel in orb_matcher.cu)
-int launch_build_grid(const FrameDev& f, const GridGeo& g, int* cellStart, int* cellItems, int items, cudaStream_t st);
+int launch_build_grid(const FrameDev& f, const GridGeo& g, int* cellStart, int* cellItems, uint4* cellRec, int items, cudaStream_t st);
 
 }  // namespace orbb200
 
@@ -159,6 +159,7 @@ struct orbb200_matcher {
     cudaStream_t stream;
     int *cellStart, *cellItems, *scratchA, *scratchB, *scratchC, *topkCount;
     uint4 *topk, *topkIdx;
+    uint4* cellRec;         // items x maxPoints x 3: the grid's keypoints in CSR order, {x, y, index, octave} + descriptor (k_build_grid)
     std::vector<void*> allocs;
     // staging for host-pointer calls
     uint8_t* stage; size_t stageBytes;

@@ -27,7 +27,7 @@ __global__ void k_distance(const uint4* a, const uint4* b, int n, int* dist)
 // ---- Frame::AssignFeaturesToGrid as CSR (one CTA per frame) --------------------------------
 // cell = ix*48+iy with ix,iy = roundf((pt - min) * inv) (PosInGrid, S/Frame.cc:505-517); points whose
 // cell falls outside the 64x48 grid are not indexed.  Inside a cell, indices ascend (push_back order).
-__global__ void __launch_bounds__(256) k_build_grid(FrameDev f, GridGeo g, int* cellStart, int* cellItems)
+__global__ void __launch_bounds__(256) k_build_grid(FrameDev f, GridGeo g, int* cellStart, int* cellItems, uint4* cellRec)
 {
     __shared__ int cnt[GRID_CELLS + 1];
     __shared__ int wsum[9];
@@ -77,6 +77,20 @@ __global__ void __launch_bounds__(256) k_build_grid(FrameDev f, GridGeo g, int* 
             while (b >= s && ci[b] > v) { ci[b + 1] = ci[b]; b--; }
             ci[b + 1] = v;
         }
+    }
+    // The same keypoints once more as 48-byte records IN CSR ORDER: {x, y, index, octave} and the descriptor.  A search
+    // that walks a cell range then reads consecutive records instead of chasing index -> four arrays -> descriptor.
+    if (!cellRec) return;
+    __syncthreads();
+    uint4* rec = cellRec + (size_t)item * f.stride * 3;
+    const int* oc = f.octave + (size_t)item * f.stride;
+    const uint4* de = reinterpret_cast<const uint4*>(f.desc + (size_t)item * f.stride * 32);
+    const int ng = cs[GRID_CELLS];
+    for (int p = tid; p < ng; p += 256) {
+        const int i = ci[p];
+        rec[3 * p] = make_uint4(__float_as_uint(kx[i]), __float_as_uint(ky[i]), (uint32_t)i, (uint32_t)oc[i]);
+        rec[3 * p + 1] = __ldg(de + 2 * i);
+        rec[3 * p + 2] = __ldg(de + 2 * i + 1);
     }
 }
 
@@ -459,6 +473,7 @@ struct ProjParams {
     GridGeo g;
     const int* cellStart;
     const int* cellItems;
+    const uint4* cellRec;
     const int* mpN;
     const uint8_t *mpInView, *mpBad;
     const float *mpX, *mpY, *mpXR;
@@ -494,13 +509,8 @@ __global__ void __launch_bounds__(128) k_proj_topk(const ProjParams P)
     const int* ciw = P.cellItems + (size_t)item * P.f.stride;
     int count = -1;
     if (P.mpInView[mo + i] && !P.mpBad[mo + i]) {                                    // :56-60
-        const float* kx = P.f.x + (size_t)item * P.f.stride;
-        const float* ky = P.f.y + (size_t)item * P.f.stride;
-        const int* koct = P.f.octave + (size_t)item * P.f.stride;
-        const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
         const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
         const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
-        const int* ci = P.cellItems + (size_t)item * P.f.stride;
         const int* kpmp = P.kpMp + (size_t)item * P.f.stride;
         const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
         const int lvl = P.mpLevel[mo + i];
@@ -515,16 +525,18 @@ __global__ void __launch_bounds__(128) k_proj_topk(const ProjParams P)
             const bool check = (minLevel > 0) || (maxLevel >= 0);
             const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + (mo + i) * 32);
             const uint4 a0 = __ldg(md), a1 = __ldg(md + 1);
+            const uint4* cr = P.cellRec + (size_t)item * P.f.stride * 3;
             for (int c = c0; c <= c1; c++) {
                 const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
                 for (int p = s; p < e; p++) {
-                    const int idx = ci[p];
-                    const int o = koct[idx];
+                    const uint4 rec = __ldg(cr + 3 * p);                            // {x, y, index, octave} in CSR order
+                    const uint4 b0 = __ldg(cr + 3 * p + 1), b1 = __ldg(cr + 3 * p + 2);
+                    const int idx = (int)rec.z, o = (int)rec.w;
                     if (check) {
                         if (o < minLevel) continue;
                         if (maxLevel >= 0 && o > maxLevel) continue;
                     }
-                    if (!(fabsf(__fsub_rn(kx[idx], qx)) < rs && fabsf(__fsub_rn(ky[idx], qy)) < rs)) continue;
+                    if (!(fabsf(__fsub_rn(__uint_as_float(rec.x), qx)) < rs && fabsf(__fsub_rn(__uint_as_float(rec.y), qy)) < rs)) continue;
                     const int held = kpmp[idx];                                      // :89-91, initial state
                     if (held != -1) {
                         const int obs = held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[idx] : 0);
@@ -534,7 +546,7 @@ __global__ void __launch_bounds__(128) k_proj_topk(const ProjParams P)
                         const float er = fabsf(__fsub_rn(qxr, ur[idx]));
                         if (er > rs) continue;
                     }
-                    const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                    const int dist = hamming256(a0, a1, b0, b1);
                     top4_insert(best, ((uint32_t)dist << 23) | ((uint32_t)p << 5) | (uint32_t)(o & 31));
                     count++;
                 }
@@ -692,9 +704,9 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
     if (lane == 0) P.nmatches[item] = nmatches;
 }
 
-int launch_build_grid(const FrameDev& f, const GridGeo& g, int* cellStart, int* cellItems, int items, cudaStream_t st)
+int launch_build_grid(const FrameDev& f, const GridGeo& g, int* cellStart, int* cellItems, uint4* cellRec, int items, cudaStream_t st)
 {
-    k_build_grid<<<items, 256, 0, st>>>(f, g, cellStart, cellItems);
+    k_build_grid<<<items, 256, 0, st>>>(f, g, cellStart, cellItems, cellRec);
     ORB_CHECK_LAUNCH("k_build_grid");
     return ORBB200_OK;
 }
@@ -727,6 +739,7 @@ extern "C" int orbb200_matcher_create(int max_items, int max_points, int device,
     const size_t np = (size_t)max_items * max_points;
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->cellStart, sizeof(int) * (size_t)max_items * (GRID_CELLS + 1));
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->cellItems, sizeof(int) * np);
+    if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->cellRec, sizeof(uint4) * 3 * np);
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchA, sizeof(int) * np);
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchB, sizeof(int) * np);
     if (rc == ORBB200_OK) rc = m_alloc(m, (void**)&m->scratchC, sizeof(int) * np);
@@ -815,7 +828,7 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx;
     P.items = items; P.window = window_size; P.checkOri = check_orientation; P.nnratio = nnratio;
     // scratch strides follow the views
-    k_build_grid<<<items, 256, 0, st>>>(P.f2, P.g, m->cellStart, m->cellItems);
+    k_build_grid<<<items, 256, 0, st>>>(P.f2, P.g, m->cellStart, m->cellItems, nullptr);
     ORB_CHECK_LAUNCH("k_build_grid");
     k_init_topk<<<dim3((f1->stride + orbb200::TOPK_QPB - 1) / orbb200::TOPK_QPB, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_init_topk");
@@ -875,10 +888,10 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
         P.kpMp = const_cast<int*>(kpmp);
         dN = s.out<int>(items);
     }
-    P.mpStride = mp->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.mpStride = mp->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems; P.cellRec = m->cellRec;
     P.nlevels = nlevels; P.nmatches = dN; P.items = items; P.nnratio = nnratio; P.th = th;
     P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx;
-    k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems);
+    k_build_grid<<<items, 256, 0, st>>>(P.f, P.g, m->cellStart, m->cellItems, m->cellRec);
     ORB_CHECK_LAUNCH("k_build_grid");
     k_proj_topk<<<dim3((mp->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_proj_topk");

@@ -19,6 +19,7 @@ struct LastParams {
     GridGeo g;
     const int* cellStart;
     const int* cellItems;
+    const uint4* cellRec;       // the grid's keypoints in CSR order: {x, y, index, octave} + descriptor (k_build_grid)
     const int* lastN;           // last frame, items x lastStride
     const uint8_t *hasMp, *outlier;
     const float* wpos;          // x3
@@ -154,20 +155,23 @@ __device__ __forceinline__ LastQuery last_query(const LastParams& P, int item, i
 }
 
 // static candidate test shared by both phases (GetFeaturesInArea level + window tests, stereo check :1414-1420)
-__device__ __forceinline__ bool last_candidate(const LastParams& P, const LastQuery& q, int idx, const float* kx, const float* ky,
-                                               const int* koct, const float* ur)
+__device__ __forceinline__ bool last_candidate(const LastParams& P, const LastQuery& q, int idx, float x, float y, int o, const float* ur)
 {
-    const int o = koct[idx];
     if ((q.minLevel > 0) || (q.maxLevel >= 0)) {
         if (o < q.minLevel) return false;
         if (q.maxLevel >= 0 && o > q.maxLevel) return false;
     }
-    if (!(fabsf(__fsub_rn(kx[idx], q.u)) < q.radius && fabsf(__fsub_rn(ky[idx], q.v)) < q.radius)) return false;
+    if (!(fabsf(__fsub_rn(x, q.u)) < q.radius && fabsf(__fsub_rn(y, q.v)) < q.radius)) return false;
     if (ur && ur[idx] > 0) {
         const float pr = __fsub_rn(q.u, __fmul_rn(P.mbf, q.invzc));
         if (fabsf(__fsub_rn(pr, ur[idx])) > q.radius) return false;
     }
     return true;
+}
+__device__ __forceinline__ bool last_candidate(const LastParams& P, const LastQuery& q, int idx, const float* kx, const float* ky,
+                                               const int* koct, const float* ur)
+{
+    return last_candidate(P, q, idx, kx[idx], ky[idx], koct[idx], ur);
 }
 
 // phase A: one thread per last-frame keypoint
@@ -185,24 +189,23 @@ __global__ void __launch_bounds__(128) k_last_topk(const LastParams P)
     int c0, c1, r0, r1;
     if (q.ok && cell_range(P.kind == 2 ? P.q : P.g, q.u, q.v, q.radius, c0, c1, r0, r1)) {
         count = 0;
-        const float* kx = P.f.x + (size_t)item * P.f.stride;
-        const float* ky = P.f.y + (size_t)item * P.f.stride;
-        const int* koct = P.f.octave + (size_t)item * P.f.stride;
-        const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
         const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
         const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
         const int* kpmp = P.kpMp + (size_t)item * P.f.stride;
         const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
         const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + lo * 32);
         const uint4 a0 = __ldg(md), a1 = __ldg(md + 1);
+        const uint4* cr = P.cellRec + (size_t)item * P.f.stride * 3;
         for (int c = c0; c <= c1; c++) {
             const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
             for (int p = s; p < e; p++) {
-                const int idx = ci[p];
-                if (!last_candidate(P, q, idx, kx, ky, koct, ur)) continue;
+                const uint4 rec = __ldg(cr + 3 * p);                             // {x, y, index, octave} in CSR order
+                const uint4 b0 = __ldg(cr + 3 * p + 1), b1 = __ldg(cr + 3 * p + 2);
+                const int idx = (int)rec.z;
+                if (!last_candidate(P, q, idx, __uint_as_float(rec.x), __uint_as_float(rec.y), (int)rec.w, ur)) continue;
                 const int held = kpmp[idx];                                      // initial occupancy (:1409-1411, :1546-1547)
                 if (held != -1 && (P.kind != 0 || (held >= 0 ? P.mpObs[(size_t)item * P.lastStride + held] : (kpobs ? kpobs[idx] : 0)) > 0)) continue;
-                const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                const int dist = hamming256(a0, a1, b0, b1);
                 top4_insert(best, ((uint32_t)dist << 23) | ((uint32_t)p << 5));
                 count++;
             }
@@ -518,12 +521,12 @@ extern "C" int orbb200_search_by_projection_last_frame(orbb200_matcher* m, int i
         P.kpMp = const_cast<int*>(kpmp);
         dN = s.out<int>(items);
     }
-    P.lastStride = last->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.lastStride = last->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems; P.cellRec = m->cellRec;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.mbf = mbf;
     P.minX = bounds[0]; P.minY = bounds[1]; P.maxX = bounds[2]; P.maxY = bounds[3];
     P.nmatches = dN; P.items = items; P.mode = mode; P.checkOri = check_orientation; P.th = th;
     P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx; P.histBin = m->scratchA; P.histIdx = m->scratchB;
-    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, items, st))) return rc;
+    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, m->cellRec, items, st))) return rc;
     k_last_topk<<<dim3((last->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_last_topk");
     {
@@ -584,12 +587,12 @@ extern "C" int orbb200_search_by_projection_keyframe(orbb200_matcher* m, int ite
     }
     if (!P.lastAng) P.lastAng = P.mfMax;      // never read for a decision when check_orientation is off
     P.kind = 1; P.orbDist = orb_dist; P.nlevels = nlevels; P.logScale = log_scale_factor;
-    P.lastStride = kf->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.lastStride = kf->stride; P.g = grid_geo(bounds); P.cellStart = m->cellStart; P.cellItems = m->cellItems; P.cellRec = m->cellRec;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
     P.minX = bounds[0]; P.minY = bounds[1]; P.maxX = bounds[2]; P.maxY = bounds[3];
     P.nmatches = dN; P.items = items; P.mode = 0; P.checkOri = check_orientation; P.th = th;
     P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx; P.histBin = m->scratchA; P.histIdx = m->scratchB;
-    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, items, st))) return rc;
+    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, m->cellRec, items, st))) return rc;
     k_last_topk<<<dim3((kf->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_last_topk");
     {
@@ -654,7 +657,7 @@ extern "C" int orbb200_fuse_search(orbb200_matcher* m, int items, const orbb200_
     P.cellStart = m->cellStart; P.cellItems = m->cellItems;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.bf = bf; P.th = th; P.logScale = log_scale_factor; P.nlevels = nlevels;
     P.mode = mode;
-    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, items, st))) return rc;
+    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, m->cellRec, items, st))) return rc;
     k_fuse_search<<<dim3((pts->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_fuse_search");
     m->lastLaunches = 2;
@@ -707,11 +710,11 @@ extern "C" int orbb200_search_by_projection_sim3(orbb200_matcher* m, int items, 
     P.kind = 2; P.nlevels = nlevels; P.logScale = log_scale_factor;
     P.lastStride = pts->stride; P.g = grid_geo(bounds); P.q = P.g;
     P.q.minX = (float)(int)bounds[0]; P.q.minY = (float)(int)bounds[1]; P.maxXi = (int)bounds[2]; P.maxYi = (int)bounds[3];
-    P.cellStart = m->cellStart; P.cellItems = m->cellItems;
+    P.cellStart = m->cellStart; P.cellItems = m->cellItems; P.cellRec = m->cellRec;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
     P.nmatches = dN; P.items = items; P.mode = 0; P.checkOri = 0; P.th = (float)th;
     P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx; P.histBin = m->scratchA; P.histIdx = m->scratchB;
-    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, items, st))) return rc;
+    if ((rc = launch_build_grid(P.f, P.g, m->cellStart, m->cellItems, m->cellRec, items, st))) return rc;
     k_last_topk<<<dim3((pts->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_last_topk");
     {
