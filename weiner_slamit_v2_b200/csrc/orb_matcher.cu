@@ -571,13 +571,10 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
     const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= P.items) return;
     const int n = min(P.f.n[item], P.f.stride), nmp = min(P.mpN[item], P.mpStride);
-    const float* kx = P.f.x + (size_t)item * P.f.stride;
-    const float* ky = P.f.y + (size_t)item * P.f.stride;
-    const int* koct = P.f.octave + (size_t)item * P.f.stride;
-    const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
     const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
     const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
     const int* ci = P.cellItems + (size_t)item * P.f.stride;
+    const uint4* cr = P.cellRec + (size_t)item * P.f.stride * 3;
     int* kpmp = P.kpMp + (size_t)item * P.f.stride;
     const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
     const size_t mo = (size_t)item * P.mpStride;
@@ -656,20 +653,20 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
             for (int c = c0; c <= c1; c++) {
                 const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
                 for (int p = s + lane; p < e; p += 32) {
-                    const int idx = ci[p];
-                    const int o = koct[idx];
+                    const uint4 rec = __ldg(cr + 3 * p);                            // {x, y, index, octave} in CSR order
+                    const uint4 b0 = __ldg(cr + 3 * p + 1), b1 = __ldg(cr + 3 * p + 2);
+                    const int idx = (int)rec.z, o = (int)rec.w;
                     if (check) {
                         if (o < minLevel) continue;
                         if (maxLevel >= 0 && o > maxLevel) continue;
                     }
-                    if (!(fabsf(__fsub_rn(kx[idx], qx)) < rs && fabsf(__fsub_rn(ky[idx], qy)) < rs)) continue;
+                    if (!(fabsf(__fsub_rn(__uint_as_float(rec.x), qx)) < rs && fabsf(__fsub_rn(__uint_as_float(rec.y), qy)) < rs)) continue;
                     if (occ[idx]) continue;                                              // :89-91
                     if (ur && ur[idx] > 0) {                                            // :93-98
                         const float er = fabsf(__fsub_rn(qxr, ur[idx]));
                         if (er > rs) continue;
                     }
-                    const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
-                    top2_push(t, dist, p, o);
+                    top2_push(t, hamming256(a0, a1, b0, b1), p, o);
                 }
             }
             t = top2_warp_reduce(t);

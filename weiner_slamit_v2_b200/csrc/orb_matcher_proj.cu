@@ -229,14 +229,11 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
     const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= P.items) return;
     const int n = min(P.f.n[item], P.f.stride), nl = min(P.lastN[item], P.lastStride);
-    const float* kx = P.f.x + (size_t)item * P.f.stride;
-    const float* ky = P.f.y + (size_t)item * P.f.stride;
-    const int* koct = P.f.octave + (size_t)item * P.f.stride;
     const float* kang = P.f.angle + (size_t)item * P.f.stride;
-    const uint4* kd = reinterpret_cast<const uint4*>(P.f.desc + (size_t)item * P.f.stride * 32);
     const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
     const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
     const int* ci = P.cellItems + (size_t)item * P.f.stride;
+    const uint4* cr = P.cellRec + (size_t)item * P.f.stride * 3;
     int* kpmp = P.kpMp + (size_t)item * P.f.stride;
     const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
     const size_t lo = (size_t)item * P.lastStride;
@@ -299,9 +296,11 @@ __global__ void __launch_bounds__(128) k_search_last(const LastParams P)
             for (int c = c0; c <= c1; c++) {
                 const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
                 for (int p = s + lane; p < e; p += 32) {
-                    const int idx = ci[p];
-                    if (!last_candidate(P, q, idx, kx, ky, koct, ur) || occ[idx]) continue;
-                    const int dist = hamming256(a0, a1, __ldg(kd + 2 * idx), __ldg(kd + 2 * idx + 1));
+                    const uint4 rec = __ldg(cr + 3 * p);                         // {x, y, index, octave} in CSR order
+                    const uint4 b0 = __ldg(cr + 3 * p + 1), b1 = __ldg(cr + 3 * p + 2);
+                    const int idx = (int)rec.z;
+                    if (!last_candidate(P, q, idx, __uint_as_float(rec.x), __uint_as_float(rec.y), (int)rec.w, ur) || occ[idx]) continue;
+                    const int dist = hamming256(a0, a1, b0, b1);
                     if (dist < bd) { bd = dist; bp = p; }
                 }
             }
