@@ -28,3 +28,16 @@ pipe = InitializationPipeline(max_pairs=2)
 f1 = np.stack([synthetic_frame(9 + i) for i in range(2)])
 nm, _, _ = pipe.run(torch.from_numpy(f1).cuda(), torch.from_numpy(np.roll(f1, 3, 2)).cuda(), 2); pipe.sync(); print("pipeline", nm.cpu().numpy())
 print("done")
+# stereo (row N4): device pyramids and host pyramids
+from weiner_slamit_v2_b200.frames import stereo_right_frame
+from weiner_slamit_v2_b200.pipeline import StereoPipeline
+lf = np.stack([synthetic_frame(20 + i) for i in range(2)]); rf = np.stack([stereo_right_frame(lf[i], 20 + i) for i in range(2)])
+sp = StereoPipeline(max_pairs=2)
+nm, _, _ = sp.run(torch.from_numpy(lf).cuda(), torch.from_numpy(rf).cuda(), 2); sp.sync(); print("stereo pipeline", nm.cpu().numpy())
+exl = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=1); exr = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=1)
+kl, dl, cl = exl.extract_batch(lf[:1]); kr, dr, cr = exr.extract_batch(rf[:1])
+lp = [[exl.get_level(0, l) for l in range(8)]]; rp = [[exr.get_level(0, l) for l in range(8)]]
+res, nm = m.compute_stereo_matches_batch([(kl[0, :cl[0]], dl[0, :cl[0]])], [(kr[0, :cr[0]], dr[0, :cr[0]])], lp, rp,
+                                         exl.GetScaleFactors(), exl.GetInverseScaleFactors(), 0.1, 40.0)
+print("stereo host pyramids", nm)
+print("done (stereo)")
