@@ -337,6 +337,8 @@ def run_ours(args):
             "kernel_ms_per_step": {s: float(per_stage[i]) for i, s in enumerate(STAGES)},
             "roofline": {"bound": "hbm", "kernel": STAGES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": _traffic(STAGES[dom]), "peak_source": which,
+                         "issue": _issue_profile({"pyramid": "k_resize", "fast": "k_fast", "quadtree": "k_quadtree", "blur": "k_blur",
+                                                  "describe": "k_describe"}[STAGES[dom]]),
                          "all": {s: ALG_BYTES[s] * BATCH / (per_stage[i] * 1e-3) / 1e9 / peak for i, s in enumerate(STAGES)}},
             "clocks": clocks,
         }
@@ -692,6 +694,20 @@ def run_stereo(local, steps):
                         "keypoint views, ComputeStereoMatches (row bands, Hamming, 11x11 SAD over +-5 px, parabola, median cut), all on the device",
             "ms_per_step": dt * 1e3, "pairs_per_s": pairs / dt, "stereo_matcher_ms": ms, "stereo_matcher_pairs_per_s": pairs / ms * 1e3,
             "stereo_matches": acc}
+
+
+def _issue_profile(kernel):
+    """Issue-slot use and instruction count of `kernel` from the committed ncu --set full summary: the path is
+    integer/byte work bound by instruction issue, so this is the number that explains the HBM fraction."""
+    for tag in ("r1k",):
+        p = os.path.join(ROOT, "profiles", tag + "_ncu_full_summary.json")
+        if os.path.exists(p):
+            with open(p) as f:
+                for e in json.load(f):
+                    if e["kernel"] == kernel:
+                        return {"issue_slots_busy_pct": e["issue_active_pct"], "warp_instructions_per_launch": e["inst_executed"],
+                                "dram_pct_of_peak": e["dram_pct"], "source": "profiles/%s_ncu_full_summary.json" % tag}
+    return None
 
 
 def _traffic(stage):

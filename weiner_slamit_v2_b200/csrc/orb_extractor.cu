@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 #include "common.cuh"
 
@@ -32,6 +33,7 @@ void set_error(const char* fmt, ...)
 }
 
 constexpr int MAXL = 16;             // pyramid levels supported per handle
+constexpr int GRAPH_MAX_BATCH = 8;   // host-path calls up to this many frames replay a captured CUDA graph
 constexpr int EDGE = 19;             // EDGE_THRESHOLD (S/ORBextractor.cc:79)
 constexpr int BORDER = EDGE - 3;     // minBorderX/Y (:789)
 constexpr int HALF_PATCH = 15;       // HALF_PATCH_SIZE (:78)
@@ -1142,6 +1144,7 @@ struct orbb200_extractor {
     cudaStream_t copyIn, copyOut;        // host path: H2D and D2H run beside the kernels, chunk by chunk
     cudaEvent_t evIn[8], evDone[8];
     bool pending;                        // an orbb200_extract_host_async call has not been waited for yet
+    std::map<int, cudaGraphExec_t> graphs;   // host path, small batches: the kernel sequence of one call as a CUDA graph, by batch size
     std::vector<void*> allocs;
 };
 
@@ -1364,6 +1367,7 @@ extern "C" void orbb200_extractor_destroy(orbb200_extractor* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (std::map<int, cudaGraphExec_t>::iterator it = h->graphs.begin(); it != h->graphs.end(); ++it) cudaGraphExecDestroy(it->second);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 8; i++) { if (h->evIn[i]) cudaEventDestroy(h->evIn[i]); if (h->evDone[i]) cudaEventDestroy(h->evDone[i]); }
     if (h->copyIn) cudaStreamDestroy(h->copyIn);
@@ -1418,46 +1422,13 @@ extern "C" int orbb200_extractor_stage_ms(orbb200_extractor* h, float* ms5)
     return ORBB200_OK;
 }
 
-// enqueue the whole pipeline for `batch` frames whose level 0 is at d_images
-// `first` = index of the scratch slabs (pyramid, candidates, ...) the batch's frame 0 uses, so that several
-// chunks of one host call can be in flight in disjoint parts of the handle's buffers.
-static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, size_t stride, size_t frame_stride,
-                   orbb200_keypoint* d_kp, uint8_t* d_desc, int32_t* d_counts, int cap, int first = 0)
+// The kernel sequence of one extraction call on stream st (also what a CUDA graph of the call contains).
+static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batch, cudaStream_t st, int& launches)
 {
-    ExtractParams P = h->P;
-    cudaStream_t st = h->stream;
-    P.pyr += (size_t)first * P.pyrFrameBytes; P.blur += (size_t)first * P.blurFrameBytes;
-    P.cand += (size_t)first * P.candFrameCap; P.qtScratch += (size_t)first * P.candFrameCap;
-    P.candCount += (size_t)first * P.nlevels; P.lkp += (size_t)first * P.kpFrameCap; P.lkpCount += (size_t)first * P.nlevels;
-    const size_t inFrameBytes = h->inPitch * (size_t)h->height;
-    const bool staged = d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch;
-    // The kernels read level 0 as aligned words and 16-byte TMA bulk rows.  A caller buffer qualifies when base,
-    // strides and width are multiples of 16 (then no chunk straddles the end of a row); anything else is
-    // first copied into the handle's padded staging slab.
-    if (!staged) {
-        const bool canonical = ((reinterpret_cast<uintptr_t>(d_images) | stride | frame_stride | (size_t)h->width) & 15) == 0;
-        if (canonical) {
-            P.inRowBytes = h->width;
-        } else {
-            for (int f = 0; f < batch; f++)
-                ORB_CUDA(cudaMemcpy2DAsync(h->dIn + (size_t)(first + f) * inFrameBytes, h->inPitch, d_images + f * frame_stride,
-                                           stride, h->width, h->height, cudaMemcpyDeviceToDevice, st));
-            d_images = h->dIn + (size_t)first * inFrameBytes; stride = h->inPitch; frame_stride = inFrameBytes;
-            P.inRowBytes = (int)h->inPitch;
-        }
-    } else {
-        P.inRowBytes = (int)h->inPitch;
-    }
-    P.batch = batch; P.in = d_images; P.inPitch = (int)stride; P.inFrameStride = (long long)frame_stride;
-    P.inPadded = 0;
-    if (d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch && h->inPitch >= (size_t)h->width + 4) {
-        k_pad_level0<<<dim3((h->height + 127) / 128, batch), 128, 0, st>>>(const_cast<uint8_t*>(d_images), (long long)frame_stride,
-                                                                            (int)stride, h->width, h->height);
+    if (P.inPadded) {       // level 0 sits in the padded staging slab: write the REFLECT_101 continuation columns the blur reads
+        k_pad_level0<<<dim3((h->height + 127) / 128, batch), 128, 0, st>>>(const_cast<uint8_t*>(P.in), P.inFrameStride, P.inPitch, h->width, h->height);
         ORB_CHECK_LAUNCH("k_pad_level0");
-        P.inPadded = 1;
     }
-    P.outKp = d_kp; P.outDesc = d_desc; P.outCount = d_counts; P.outCap = cap;
-    int launches = 0;
     ORB_CUDA(cudaMemsetAsync(P.candCount, 0, sizeof(int) * P.nlevels * batch, st));
 #define STAGE_MARK(i) do { if (h->profiling) ORB_CUDA(cudaEventRecord(h->ev[i], st)); } while (0)
     STAGE_MARK(0);
@@ -1490,6 +1461,69 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
     ORB_CHECK_LAUNCH("k_describe"); launches++;
     STAGE_MARK(5);
 #undef STAGE_MARK
+    return ORBB200_OK;
+}
+
+// enqueue the whole pipeline for `batch` frames whose level 0 is at d_images
+// `first` = index of the scratch slabs (pyramid, candidates, ...) the batch's frame 0 uses, so that several
+// chunks of one host call can be in flight in disjoint parts of the handle's buffers.
+static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, size_t stride, size_t frame_stride,
+                   orbb200_keypoint* d_kp, uint8_t* d_desc, int32_t* d_counts, int cap, int first = 0)
+{
+    ExtractParams P = h->P;
+    cudaStream_t st = h->stream;
+    P.pyr += (size_t)first * P.pyrFrameBytes; P.blur += (size_t)first * P.blurFrameBytes;
+    P.cand += (size_t)first * P.candFrameCap; P.qtScratch += (size_t)first * P.candFrameCap;
+    P.candCount += (size_t)first * P.nlevels; P.lkp += (size_t)first * P.kpFrameCap; P.lkpCount += (size_t)first * P.nlevels;
+    const size_t inFrameBytes = h->inPitch * (size_t)h->height;
+    const bool staged = d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch;
+    // The kernels read level 0 as aligned words and 16-byte TMA bulk rows.  A caller buffer qualifies when base,
+    // strides and width are multiples of 16 (then no chunk straddles the end of a row); anything else is
+    // first copied into the handle's padded staging slab.
+    if (!staged) {
+        const bool canonical = ((reinterpret_cast<uintptr_t>(d_images) | stride | frame_stride | (size_t)h->width) & 15) == 0;
+        if (canonical) {
+            P.inRowBytes = h->width;
+        } else {
+            for (int f = 0; f < batch; f++)
+                ORB_CUDA(cudaMemcpy2DAsync(h->dIn + (size_t)(first + f) * inFrameBytes, h->inPitch, d_images + f * frame_stride,
+                                           stride, h->width, h->height, cudaMemcpyDeviceToDevice, st));
+            d_images = h->dIn + (size_t)first * inFrameBytes; stride = h->inPitch; frame_stride = inFrameBytes;
+            P.inRowBytes = (int)h->inPitch;
+        }
+    } else {
+        P.inRowBytes = (int)h->inPitch;
+    }
+    P.batch = batch; P.in = d_images; P.inPitch = (int)stride; P.inFrameStride = (long long)frame_stride;
+    P.inPadded = (d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch && h->inPitch >= (size_t)h->width + 4) ? 1 : 0;
+    P.outKp = d_kp; P.outDesc = d_desc; P.outCount = d_counts; P.outCap = cap;
+    int launches = 0;
+    // Small host-path calls (one frame per call is what Frame::ExtractORB issues) are bound by launch overhead, not by
+    // the kernels: their kernel sequence is captured once per batch size and replayed as one CUDA graph.  Every
+    // parameter of such a call is the handle's own (staging slab in, output buffers out), so the replay is exact.
+    const bool graphable = !h->profiling && staged && first == 0 && batch <= GRAPH_MAX_BATCH && d_images == h->dIn &&
+                           d_kp == h->dOutKp && d_desc == h->dOutDesc && d_counts == h->dOutCount && cap == h->maxKp;
+    if (graphable) {
+        std::map<int, cudaGraphExec_t>::iterator it = h->graphs.find(batch);
+        if (it == h->graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            ORB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_kernels(h, P, batch, st, launches);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != ORBB200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return ORBB200_ECUDA; }
+            ORB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            it = h->graphs.insert(std::make_pair(batch, exec)).first;
+        } else {
+            launches = P.nlevels - 1 + 4;
+        }
+        ORB_CUDA(cudaGraphLaunch(it->second, st));
+    } else {
+        int rc = launch_kernels(h, P, batch, st, launches);
+        if (rc != ORBB200_OK) return rc;
+    }
     h->lastLaunches = launches; h->lastBatch = batch;
     h->lastIn = d_images; h->lastInPitch = (int)stride; h->lastInFrameStride = (long long)frame_stride;
     return ORBB200_OK;
