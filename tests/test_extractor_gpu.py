@@ -228,3 +228,21 @@ def test_rejected_geometries():
         ORBextractor(1000, 1.2, 2, 20, 7, width=100, height=400)       # aspect ratio rounds to zero quadtree roots
     with pytest.raises(OrbB200Error):
         ORBextractor(1000, 2.5, 2, 20, 7)                               # scale factor above 2
+
+
+def test_small_host_calls_replay_a_graph_exactly():
+    """Host-path calls of up to 8 frames replay a CUDA graph captured on the first call of that batch size: repeated
+    calls with different images, interleaved with other batch sizes, must stay bit-exact."""
+    orc = O.OracleExtractor(*PARAMS)
+    ex = ORBextractor(*PARAMS, width=640, height=480, max_batch=16, device=0)
+    frames = np.stack([synthetic_frame(30 + i) for i in range(16)])
+    want = [orc(frames[i]) for i in range(16)]
+
+    def check(first, n):
+        kps, desc, counts = ex.extract_batch(frames[first:first + n])
+        for j in range(n):
+            ko, do = want[first + j]
+            c = int(counts[j])
+            assert c == len(ko) and kps[j, :c].tobytes() == ko.tobytes() and np.array_equal(desc[j, :c], do)
+    for first, n in ((0, 1), (1, 1), (2, 4), (6, 1), (0, 16), (7, 4), (11, 1), (12, 3), (15, 1)):
+        check(first, n)

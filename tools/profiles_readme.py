@@ -2,7 +2,7 @@
 import csv, json, os, sys
 from collections import defaultdict
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1k"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1l"
 P = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
 J = lambda n: json.load(open(os.path.join(P, n)))
 l = J(tag + "_bench.json")
@@ -53,10 +53,12 @@ mrows = "\n".join("| `%s` | %s | %.2f |" % (k, v["workload"], v.get("ms_per_step
 scale = ""
 for f, what in (("_bench_2gpu", None), ("_bench_4gpu", "4 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_8gpu", "8 GPUs, 256 VGA frames per GPU (weak)"),
                 ("_bench_hd_1gpu", "1 GPU, 1280x720 / 2000 kp, 1024 frames"), ("_bench_hd_4gpu", "4 GPUs, the same 1024 HD frames (strong)")):
-    fn = os.path.join(P, tag + f + ".json")
-    if what and os.path.exists(fn):
-        x = json.load(open(fn))
-        scale += "| %s | %.0f | %.0f | %.0f |\n" % (what, x["value"], x["e2e"]["value"], x["e2e"]["blocking_call_value"])
+    for src in (tag, "r1k", "r1i"):            # the newest run of each configuration (the multi-GPU runs are not repeated for every step)
+        fn = os.path.join(P, src + f + ".json")
+        if what and os.path.exists(fn):
+            x = json.load(open(fn))
+            scale += "| %s (`%s`) | %.0f | %.0f | %.0f |\n" % (what, src + f + ".json", x["value"], x["e2e"]["value"], x["e2e"]["blocking_call_value"])
+            break
 fast = [e for e in d if e["kernel"] == "k_fast"][0]
 readme = f"""# profiles/ — measured evidence, named per round and step
 
@@ -73,7 +75,8 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 | `r1j_bench_8gpu.json`, `r1j_topology_8gpu.txt` | the 8-GPU run repeated with each rank bound to its GPU's CPU set (no change: the box is one NUMA node with 32 virtual CPUs for 8 ranks) | |
 | `{tag}_ncu_match_summary.json` | `ncu --set full` of the matcher kernels (longest launch per kernel) | `ncu --set full ... -k regex:"k_init_topk|k_search_init|k_proj_topk|k_search_proj|k_last_topk|k_search_last|k_build_grid" -c 14 python tools/prof_match.py`, summarised by `tools/ncu_match_summary.py` |
 | `r1k_int_peak.json` | integer-pipe peaks (POPC, LOP3, IADD3 lanes per clock and SM) and register-only Hamming rates: the matching roofline's denominator | `tools/int_peak.cu` |
-| `r1i_*`, `r1h_ncu_match_summary.json` | the previous step of this round (before the carry-save distance, the speculative resolve, the row-pair blur and the stereo row): 152 k frames/s, SearchForInitialization 12.3 ms | |
+| `r1k_*` | the step before (before the CSR-ordered candidate records and the CUDA graph of small host calls): same extractor kernels; its 4- and 8-GPU runs are the current multi-GPU evidence | |
+| `r1i_*`, `r1h_ncu_match_summary.json` | an earlier step of this round (before the carry-save distance, the speculative resolve, the row-pair blur and the stereo row): 152 k frames/s, SearchForInitialization 12.3 ms | |
 | `r1c_*` ... `r1h_*` | earlier steps of this round, kept for the record (`r1f`: FAST 0.76 ms, describe 0.32 ms; `r1e`: FAST 0.85 ms) | |
 | `r1a_*`, `r1b_*` | first bit-exact CUDA path, before any tuning | |
 | `tools/profiles_readme.py` | writes this file from the ones above | |
@@ -96,9 +99,9 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 | 1 GPU, 256 VGA frames | {l['value']:.0f} | {l['e2e']['value']:.0f} | {l['e2e']['blocking_call_value']:.0f} |
 {scale}
 Device-resident throughput scales 4.0x on 4 and 8.0x on 8 GPUs (no data-path collective). The end-to-end figures stop scaling
-past 4 GPUs: eight ranks share one virtual host (32 vCPUs, one NUMA node, `r1j_topology_8gpu.txt`) and together ask for
-~140 GB/s of page-locked uploads, which that host does not deliver; the HD workload is upload-bound already on one GPU
-(0.92 MB per frame against ~55 GB/s of PCIe).
+at 3-4 GPUs and vary from box to box: the ranks share one virtual host (32 vCPUs, one NUMA node, `r1j_topology_8gpu.txt`) and
+each asks it for 48 GB/s of page-locked uploads (157 k frames/s x 307 KB), which that host does not deliver eight times over; the
+HD workload is upload-bound already on one GPU (0.92 MB per frame against ~55 GB/s of PCIe).
 
 ### matching rows (`{tag}_bench.json`)
 
