@@ -119,16 +119,21 @@ __global__ void k_pad_level0(uint8_t* base, long long frameStride, int pitch, in
 // Columns w..w+3 are written too: they hold the REFLECT_101 continuation that k_blur reads.
 constexpr int RZ_ROWS = 8, RZ_WARPS = 4;
 
-// The three aligned source words a thread's 4 columns draw from.  o1 / o2 are the byte offsets of the second and third
-// word, clamped to the last readable word of the row: a clamped word only feeds byte lanes that no column selects (the
-// selected bytes S[sx], S[min(sx + 1, sw - 1)] always lie below the end of the row), so no predicates are needed.
-__device__ __forceinline__ void resize_hrow(const uint8_t* rowa, int o1, int o2, uint32_t selShift, const uint32_t (&sel)[4],
+struct ResizeRaw { uint32_t w0, w1, w2; };     // the three aligned source words a thread's 4 columns draw from
+
+__device__ __forceinline__ ResizeRaw resize_load(const uint8_t* row, int a, bool ld1, bool ld2)
+{
+    ResizeRaw w;
+    w.w0 = __ldg(reinterpret_cast<const uint32_t*>(row + a));
+    w.w1 = ld1 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 4)) : 0u;
+    w.w2 = ld2 ? __ldg(reinterpret_cast<const uint32_t*>(row + a + 8)) : 0u;
+    return w;
+}
+
+__device__ __forceinline__ void resize_hrow(const ResizeRaw& w, uint32_t selShift, const uint32_t (&sel)[4],
                                             const uint32_t (&coef)[4], uint32_t (&r)[4])
 {
-    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(rowa));
-    const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(rowa + o1));
-    const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(rowa + o2));
-    const uint32_t lo = __byte_perm(w0, w1, selShift), hi = __byte_perm(w1, w2, selShift);
+    const uint32_t lo = __byte_perm(w.w0, w.w1, selShift), hi = __byte_perm(w.w1, w.w2, selShift);
 #pragma unroll
     for (int j = 0; j < 4; j++) r[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;
 }
@@ -162,8 +167,7 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
         sel[j] = (uint32_t)(t[j].x - bmin) | ((uint32_t)(t[j].w - bmin) << 4);    // bytes S[sx], S[sx+1] -> byte lanes 0,1
         coef[j] = (uint32_t)(uint16_t)t[j].y | ((uint32_t)(uint16_t)t[j].z << 16);
     }
-    const int o1 = min(a + 4, rowBytes - 4) - a, o2 = min(a + 8, rowBytes - 4) - a;
-    const uint8_t* srca = src + a;
+    const bool ld1 = a + 4 < rowBytes, ld2 = a + 8 < rowBytes;
 
     // (the row-table entry of the next destination row is loaded one row ahead: table entry -> source row is a
     // dependent load chain; prefetching the source words as well costs more in registers than it hides, measured)
@@ -180,20 +184,20 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
 #pragma unroll
             for (int j = 0; j < 4; j++) r0[j] = r1[j];
         } else {
-            resize_hrow(srca + (long long)ty.x * sp, o1, o2, selShift, sel, coef, r0);
+            resize_hrow(resize_load(src + (long long)ty.x * sp, a, ld1, ld2), selShift, sel, coef, r0);
         }
         if (ty.y == ty.x) {
 #pragma unroll
             for (int j = 0; j < 4; j++) r1[j] = r0[j];
         } else {
-            resize_hrow(srca + (long long)ty.y * sp, o1, o2, selShift, sel, coef, r1);
+            resize_hrow(resize_load(src + (long long)ty.y * sp, a, ld1, ld2), selShift, sel, coef, r1);
         }
         cur1 = ty.y;
         const uint32_t B0 = (uint32_t)ty.z << 16, B1 = (uint32_t)ty.w << 16;
         uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) o[j] = (__umulhi(B0, r0[j]) + __umulhi(B1, r1[j]) + 2u) >> 2;   // <= 255: b0 + b1 <= 2049, S >> 4 <= 32656
-        *reinterpret_cast<uint32_t*>(outp) = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+        for (int j = 0; j < 4; j++) o[j] = min((__umulhi(B0, r0[j]) + __umulhi(B1, r1[j]) + 2u) >> 2, 255u);
+        *reinterpret_cast<uint32_t*>(outp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
         outp += g.pitch;
     }
 }
