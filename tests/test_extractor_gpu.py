@@ -246,3 +246,27 @@ def test_small_host_calls_replay_a_graph_exactly():
             assert c == len(ko) and kps[j, :c].tobytes() == ko.tobytes() and np.array_equal(desc[j, :c], do)
     for first, n in ((0, 1), (1, 1), (2, 4), (6, 1), (0, 16), (7, 4), (11, 1), (12, 3), (15, 1)):
         check(first, n)
+
+
+def test_opencv_249_blur_taps():
+    """blur_taps = 1 selects the OpenCV 2.4.9 Gaussian taps {18,34,49,55,49,34,18} (sum 257: the column pass saturates
+    on bright areas).  Blurred levels, keypoints and descriptors against the oracle's variant 1, on a textured frame
+    and on one with saturated regions."""
+    bright = synthetic_frame(41).copy()
+    bright[100:300, 200:500] = 255
+    bright[300:420, 50:180] = np.where(np.indices((120, 130)).sum(0) % 7 == 0, 0, 255)
+    frames = np.stack([synthetic_frame(40), bright])
+    ex = ORBextractor(*PARAMS, width=640, height=480, max_batch=2, device=0, blur_taps=1)
+    kps, desc, counts = ex.extract_batch(frames)
+    orc = O.OracleExtractor(*PARAMS, blur_variant=1)
+    ref0 = O.OracleExtractor(*PARAMS)
+    for f in range(2):
+        ko, do = orc(frames[f])
+        c = int(counts[f])
+        for l in range(8):
+            ob = orc.level_blurred(l)
+            if ob is not None:
+                assert np.array_equal(ex.get_level(f, l, blurred=True), ob), "blur level %d" % l
+        assert c == len(ko) and kps[f, :c].tobytes() == ko.tobytes() and np.array_equal(desc[f, :c], do)
+        k0, d0 = ref0(frames[f])
+        assert not np.array_equal(d0, do)           # the two tap sets really differ
