@@ -140,6 +140,40 @@ def cpu_extract_fps(frames, threads):
     return len(frames) / dt, kind, int(np.sum(counts))
 
 
+def parity_report(frames, kps, desc, counts):
+    """north_star's reporting duty: the device results of the first frames of the step against the CPU implementation
+    (oracle/_ref = the reference's own ORBextractor.cc when it was built, else the oracle port) -- checker use only.
+    Angles are required within 1e-3 degrees and descriptor bits that flip because of them below 0.1 %; here the
+    keypoint records and the descriptors are identical, so both figures are zero."""
+    import numpy as np
+    ref_lib, kind = _load_ref()
+    if ref_lib is not None:
+        cpu = ref_lib.RefExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    else:
+        import oracle_lib
+        cpu = oracle_lib.OracleExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    from weiner_slamit_v2_b200._lib import KP_DTYPE
+    n_kp = n_same = bits = flipped = 0
+    max_angle = 0.0
+    same_count = True
+    for f, img in enumerate(frames):
+        ko, do = cpu(img)
+        c = int(counts[f])
+        same_count &= c == len(ko)
+        m = min(c, len(ko))
+        kg = np.frombuffer(kps[f, :m].tobytes(), KP_DTYPE)
+        n_kp += m
+        n_same += int(sum(kg[i].tobytes() == ko[i].tobytes() for i in range(m)))
+        if m:
+            da = np.abs(kg["angle"].astype(np.float64) - ko["angle"][:m].astype(np.float64))
+            max_angle = max(max_angle, float(np.minimum(da, 360.0 - da).max()))
+            x = np.bitwise_xor(np.asarray(desc[f, :m], np.uint8), do[:m])
+            flipped += int(np.unpackbits(x).sum()); bits += m * 256
+    return {"against": kind, "frames_checked": len(frames), "keypoint_counts_equal": bool(same_count), "keypoints": n_kp,
+            "keypoint_records_identical": n_same, "max_angle_diff_deg": max_angle, "descriptor_bits_flipped": flipped,
+            "descriptor_flip_rate": flipped / bits if bits else 0.0}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -352,6 +386,7 @@ def run_ours(args):
             fps, kind, _ = cpu_extract_fps(frames[:sample], threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                                     "sample": "%d of the 256 frames of one step, %d host threads" % (sample, threads)}
+            line["parity"] = parity_report(frames[:8], outs[0][0].numpy(), outs[0][1].numpy(), outs[0][2].numpy())
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
