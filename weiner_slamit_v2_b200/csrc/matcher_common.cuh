@@ -61,6 +61,22 @@ __device__ __forceinline__ int hamming256_csa(const uint4 a0, const uint4 a1, co
     return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
 }
 
+// shared-memory accesses by 32-bit shared-space address
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// Distance over the first 128 bits only (3 POPC + 6 LOP3): a lower bound of the full distance.
+__device__ __forceinline__ int hamming128_lower(const uint4 a0, const uint4 b0)
+{
+    const uint32_t x0 = lop_xor(a0.x, b0.x), x1 = lop_xor(a0.y, b0.y), x2 = lop_xor(a0.z, b0.z), x3 = lop_xor(a0.w, b0.w);
+    return __popc(csa_xor3(x0, x1, x2)) + __popc(x3) + 2 * __popc(csa_maj3(x0, x1, x2));
+}
+
 // Cell range of GetFeaturesInArea (S/Frame.cc:452-466); false when the query misses the grid.
 __device__ __forceinline__ bool cell_range(const GridGeo& g, float x, float y, float r, int& c0, int& c1, int& r0, int& r1)
 {

@@ -110,37 +110,38 @@ struct InitParams {
     uint4* topkIdx;           // items x f1.stride: F2 keypoint index of each of the 4 entries
     int items, window, checkOri;
     float nnratio;
+    int farDist;              // every second-best at this distance or beyond passes the ratio test against any best <= TH_LOW
 };
 
 // ---- SearchForInitialization, phase A: everything that does not depend on the greedy state ----
-// One THREAD per F1 keypoint (query); the F2 keypoints are streamed through shared memory in CSR order
+// One THREAD per two F1 keypoints (queries); the F2 keypoints are streamed through shared memory in CSR order
 // (= GetFeaturesInArea visiting order) and every lane tests the same candidate at the same time, so the
 // candidate's descriptor is one broadcast load.  The 4 smallest keys (distance, visiting position) and the
 // candidate count are kept per query.
 //
 // The loop is bound by the integer pipes, not by bytes (tools/int_peak.cu: 15 POPC and 63 LOP3/IADD3 lanes per
-// clock and SM): a warp-wide distance in the plain form holds the POPC pipe for 64 cycles, and every other ALU
-// instruction of the loop body costs 2 more.  So (1) the distance is the carry-save form (5 POPC + 14 LOP3),
-// (2) the cell-range test of GetFeaturesInArea is two packed adds and one LOP3 on 16-bit fields, (3) the sorted
-// top-4 insertion runs only when the key beats the current fourth, and (4) a warp whose queries all see the whole
-// grid (window larger than the image: cell range = all cells, and |x - qx| < r holds for the bounding box of the
-// indexed keypoints, hence for every keypoint because the float subtraction is monotonic) and are all on level 0
-// skips the per-candidate window tests and counts candidates once per chunk.
+// clock and SM): a warp-wide 256-bit distance in the plain form holds the POPC pipe for 64 cycles, and every other
+// ALU instruction of the loop body costs 2 more.  So
+//  (1) distances use the carry-save form (5 POPC + 14 LOP3 instead of 8 + 8);
+//  (2) a warp whose queries all see the whole grid (window larger than the image: cell range = all cells, and
+//      |x - qx| < r holds for the bounding box of the indexed keypoints, hence for every keypoint because the float
+//      subtraction is monotonic) and are all on level 0 skips the per-candidate window tests;
+//  (3) on that path only candidates that can matter are evaluated in full.  A match needs best <= TH_LOW and
+//      best < ratio * second (:463-465); with farDist = the smallest distance d for which TH_LOW < ratio * d, any
+//      second-best at farDist or beyond passes that test whatever its exact value, and any best there fails the first.
+//      Candidates at farDist or beyond are therefore interchangeable: the list keeps the 4 smallest keys among the
+//      NEAR candidates (distance < farDist), and when fewer than 4 are near the count reported to the greedy pass is
+//      the number of near ones, so it knows the list is complete.  The distance over the first 128 bits is a lower
+//      bound: a candidate whose half distance reaches farDist is dropped after 3 POPC + 6 LOP3; the survivors (about
+//      one in ten on unrelated descriptors) are queued per lane in shared memory and finished in dense batches,
+//      because finishing them in place would make every lane pay for the few that survive;
+//  (4) elsewhere (windowed searches) the cell-range test of GetFeaturesInArea is two packed adds and one LOP3.
 constexpr int TOPK_CHUNK = 512;
 struct __align__(16) CandMeta { float x, y; uint32_t cg; int oct; };     // cg = cx | cy << 16 (PosInGrid cell)
-
 constexpr int TOPK_QPT = 2;                        // queries per thread
 constexpr int TOPK_QPB = 128 * TOPK_QPT;            // queries per block
-constexpr int TOPK_SUB = 128;                       // candidates per 16-bit key block: key16 = dist << 7 | position in the block
-
-__device__ __forceinline__ void top4_insert_x2(uint32_t (&t)[4], uint32_t k)      // two 16-bit lists side by side
-{
-    uint32_t m;
-    m = __vminu2(t[0], k); k = __vmaxu2(t[0], k); t[0] = m;
-    m = __vminu2(t[1], k); k = __vmaxu2(t[1], k); t[1] = m;
-    m = __vminu2(t[2], k); k = __vmaxu2(t[2], k); t[2] = m;
-    t[3] = __vminu2(t[3], k);
-}
+constexpr int TOPK_SUB = 256;                       // candidates between two survivor flushes at the latest (positions are stored as bytes)
+constexpr int TOPK_LIST = 48;                       // survivor slots per query between flushes
 
 __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
 {
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
     __shared__ __align__(16) CandMeta s_meta[TOPK_CHUNK];
     __shared__ float s_box[4][4];
     __shared__ int s_oct0;                                       // running number of staged level-0 candidates
+    __shared__ uint8_t s_list[TOPK_QPT * TOPK_LIST * 128];       // [query slot][entry][thread]: position of a survivor in its sub-block
     const int item = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n1 = min(P.f1.n[item], P.f1.stride);
     if ((int)blockIdx.x * TOPK_QPB >= n1) return;
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
 
     // the thread's queries: q[u] = block base + u * 128 + tid
     const float r = (float)P.window;
-    int qi[TOPK_QPT], level1[TOPK_QPT], octHi[TOPK_QPT], count[TOPK_QPT];
+    int qi[TOPK_QPT], level1[TOPK_QPT], octHi[TOPK_QPT], count[TOPK_QPT], near[TOPK_QPT];
     bool active[TOPK_QPT], whole = true, anyActive = false;
     float qx[TOPK_QPT], qy[TOPK_QPT];
     uint32_t loK[TOPK_QPT], hiK[TOPK_QPT];
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
     for (int u = 0; u < TOPK_QPT; u++) {
         qi[u] = blockIdx.x * TOPK_QPB + u * 128 + tid;
         active[u] = qi[u] < n1;
-        level1[u] = 0; qx[u] = qy[u] = 0.f; count[u] = 0;
+        level1[u] = 0; qx[u] = qy[u] = 0.f; count[u] = 0; near[u] = 0;
         a0[u] = a1[u] = make_uint4(0, 0, 0, 0);
         best[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         int c0 = 0, c1 = -1, r0 = 0, r1 = -1;
@@ -238,26 +240,44 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
         __syncthreads();
         if (warpIdle) continue;
         if (warpWhole) {
-            // both queries see every level-0 candidate: 16-bit keys (distance << 7 | position in a 128-candidate block),
-            // the two queries' keys side by side in one register, so one packed min/max serves both lists
+            // (explicit shared-space addresses: with generic pointers the compiler rebuilds the shared window base
+            // for every candidate and carries 64-bit list pointers)
+            const int far = P.farDist;
             for (int sub = 0; sub < nc; sub += TOPK_SUB) {
                 const int ns = min(TOPK_SUB, nc - sub);
-                uint32_t t[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-#pragma unroll 4
-                for (int c = 0; c < ns; c++) {
-                    if (s_meta[sub + c].oct != 0) continue;                                // warp-uniform
-                    const uint4 b0 = s_desc[2 * (sub + c)], b1 = s_desc[2 * (sub + c) + 1];
-                    const uint32_t d01 = (uint32_t)hamming256_csa(a0[0], a1[0], b0, b1) |
-                                         ((uint32_t)hamming256_csa(a0[1], a1[1], b0, b1) << 16);
-                    top4_insert_x2(t, (d01 << 7) + (uint32_t)c * 0x10001u);
-                }
-#pragma unroll
-                for (int u = 0; u < TOPK_QPT; u++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t k16 = (t[j] >> (16 * u)) & 0xffffu;
-                        if (k16 != 0xffffu) top4_insert(best[u], ((k16 >> 7) << 20) | (uint32_t)(base + sub + (int)(k16 & 127u)));
+                const uint32_t sdesc = (uint32_t)__cvta_generic_to_shared(s_desc + 2 * sub);
+                const uint32_t soct = (uint32_t)__cvta_generic_to_shared(&s_meta[sub].oct);
+                const uint32_t lb0 = (uint32_t)__cvta_generic_to_shared(s_list + tid), lb1 = lb0 + TOPK_LIST * 128;
+                uint32_t lp0 = lb0, lp1 = lb1;                                  // next free entry of the lane's two survivor lists
+                // finish the queued survivors: full distance, near ones enter the top-4 list
+                auto flush_one = [&](int u, uint32_t lbase, uint32_t& lptr) {
+                    const int n = (int)(lptr - lbase) >> 7;
+                    const int nmax = __reduce_max_sync(0xffffffffu, n);
+                    for (int j = 0; j < nmax; j++) {
+                        if (j < n) {
+                            const int c = sub + (int)lds_u8(lbase + 128 * j);
+                            const int dist = hamming256_csa(a0[u], a1[u], s_desc[2 * c], s_desc[2 * c + 1]);
+                            if (dist < far) { top4_insert(best[u], ((uint32_t)dist << 20) | (uint32_t)(base + c)); near[u]++; }
+                        }
                     }
+                    lptr = lbase;
+                };
+                for (int c4 = 0; c4 < ns; c4 += 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int c = c4 + k;
+                        if (c < ns && lds_u32(soct + 16 * c) == 0u) {                          // warp-uniform
+                            const uint4 b0 = lds_v4(sdesc + 32 * c);
+                            if (hamming128_lower(a0[0], b0) < far) { sts_u8(lp0, (uint32_t)c); lp0 += 128; }
+                            if (hamming128_lower(a0[1], b0) < far) { sts_u8(lp1, (uint32_t)c); lp1 += 128; }
+                        }
+                    }
+                    // at most 4 entries were added per list since the last check
+                    if (__any_sync(0xffffffffu, max(lp0 - lb0, lp1 - lb1) > (uint32_t)((TOPK_LIST - 4) * 128))) {
+                        flush_one(0, lb0, lp0); flush_one(1, lb1, lp1);
+                    }
+                }
+                flush_one(0, lb0, lp0); flush_one(1, lb1, lp1);
             }
 #pragma unroll
             for (int u = 0; u < TOPK_QPT; u++) count[u] = s_oct0;
@@ -272,7 +292,7 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
                     if (!(fabsf(__fsub_rn(m.x, qx[u])) < r && fabsf(__fsub_rn(m.y, qy[u])) < r)) continue;
                     const int dist = hamming256_csa(a0[u], a1[u], s_desc[2 * c], s_desc[2 * c + 1]);
                     top4_insert(best[u], ((uint32_t)dist << 20) | (uint32_t)(base + c));
-                    count[u]++;
+                    count[u]++; near[u]++;
                 }
             }
         }
@@ -281,13 +301,15 @@ __global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
     for (int u = 0; u < TOPK_QPT; u++) {
         if (qi[u] >= n1) continue;
         const size_t o = (size_t)item * P.f1.stride + qi[u];
+        // fewer than 4 near candidates: the list holds all of them and nothing beyond it can matter (see (3) above)
+        const int reported = near[u] >= 4 ? count[u] : near[u];
         P.topk[o] = best[u];
-        P.topkCount[o] = active[u] ? count[u] : -1;
-        if (active[u] && count[u] > 0) {
+        P.topkCount[o] = active[u] ? reported : -1;
+        if (active[u] && reported > 0) {
             const uint32_t k[4] = {best[u].x, best[u].y, best[u].z, best[u].w};
             uint32_t id[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) id[j] = j < count[u] ? (uint32_t)ci[k[j] & 0xfffffu] : 0u;
+            for (int j = 0; j < 4; j++) id[j] = j < reported ? (uint32_t)ci[k[j] & 0xfffffu] : 0u;
             P.topkIdx[o] = make_uint4(id[0], id[1], id[2], id[3]);
         }
     }
@@ -824,6 +846,10 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     P.prevMatched = dPrev; P.matches12 = dM12; P.nmatches = dN;
     P.topk = m->topk; P.topkCount = m->topkCount; P.topkIdx = m->topkIdx;
     P.items = items; P.window = window_size; P.checkOri = check_orientation; P.nnratio = nnratio;
+    // smallest second-best distance that passes `best < nnratio * second` for every best <= TH_LOW, in the float arithmetic of :465
+    P.farDist = 257;
+    for (int d = TH_LOW + 1; d <= 256; d++)
+        if ((float)TH_LOW < (float)d * nnratio) { P.farDist = d; break; }
     // scratch strides follow the views
     k_build_grid<<<items, 256, 0, st>>>(P.f2, P.g, m->cellStart, m->cellItems, nullptr);
     ORB_CHECK_LAUNCH("k_build_grid");
