@@ -136,14 +136,14 @@ struct InitParams {
 //      one in ten on unrelated descriptors) are queued per lane in shared memory and finished in dense batches,
 //      because finishing them in place would make every lane pay for the few that survive;
 //  (4) elsewhere (windowed searches) the cell-range test of GetFeaturesInArea is two packed adds and one LOP3.
-constexpr int TOPK_CHUNK = 512;
+constexpr int TOPK_CHUNK = 256;
 struct __align__(16) CandMeta { float x, y; uint32_t cg; int oct; };     // cg = cx | cy << 16 (PosInGrid cell)
 constexpr int TOPK_QPT = 2;                        // queries per thread
 constexpr int TOPK_QPB = 128 * TOPK_QPT;            // queries per block
 constexpr int TOPK_SUB = 256;                       // candidates between two survivor flushes at the latest (positions are stored as bytes)
-constexpr int TOPK_LIST = 48;                       // survivor slots per query between flushes
+constexpr int TOPK_LIST = 32;                       // survivor slots per query between flushes
 
-__global__ void __launch_bounds__(128) k_init_topk(const InitParams P)
+__global__ void __launch_bounds__(128, 8) k_init_topk(const InitParams P)
 {
     __shared__ __align__(16) uint4 s_desc[TOPK_CHUNK * 2];
     __shared__ __align__(16) CandMeta s_meta[TOPK_CHUNK];
