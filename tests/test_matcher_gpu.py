@@ -41,6 +41,36 @@ def test_search_for_initialization_matches_oracle(brute, window, n):
     assert total > 0
 
 
+@pytest.mark.parametrize("ratio", [0.3, 0.6, 0.75, 1.0, 1.5])
+def test_search_for_initialization_whole_grid_pruning_is_exact_for_every_ratio(ratio):
+    """The whole-grid path drops candidates whose half distance reaches farDist = the smallest d with TH_LOW < ratio * d
+    (167, 84, 67, 51, 51 here; 0.3 disables the pruning): results must not depend on it.  Descriptors are close to
+    each other (few flipped bits, many near candidates per query) so lists fill, steals and ties happen."""
+    items, n = 4, 700
+    rng = np.random.default_rng(int(ratio * 100))
+    pairs = []
+    for i in range(items):
+        k1, d1, k2, d2, prev = init_pair(200 + i, n=n, brute_force=True)
+        # pull a third of the descriptors towards a few prototypes: several candidates below farDist per query
+        proto = rng.integers(0, 256, (6, 32)).astype(np.uint8)
+        sel = rng.random(n) < 0.33
+        for arr in (d1, d2):
+            noise = np.packbits(rng.random((n, 256)) < rng.uniform(0.02, 0.25, (n, 1)), axis=1)
+            arr[sel] = (proto[rng.integers(0, 6, n)] ^ noise)[sel]
+        pairs.append((k1, d1, k2, d2, prev))
+    m = ORBmatcher(ratio, True, max_items=items, max_points=n)
+    F1 = [Frame(p[0], p[1], 640, 480) for p in pairs]
+    F2 = [Frame(p[2], p[3], 640, 480) for p in pairs]
+    nm, m12, pm = m.search_for_initialization_batch(F1, F2, [p[4] for p in pairs], 1000)
+    total = 0
+    for i, p in enumerate(pairs):
+        on, om12, opm = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], (0, 0, 640, 480), ratio, True, 1000)
+        assert nm[i] == on, (i, nm[i], on)
+        assert np.array_equal(m12[i], om12) and np.array_equal(pm[i], opm)
+        total += on
+    assert total > 0
+
+
 def test_search_for_initialization_no_orientation_and_second_round():
     p = init_pair(11, n=800)
     m = ORBmatcher(0.9, False)

@@ -2,11 +2,12 @@
 import csv, json, os, sys
 from collections import defaultdict
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1l"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1m"
 P = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
 J = lambda n: json.load(open(os.path.join(P, n)))
 l = J(tag + "_bench.json")
-d = J(tag + "_ncu_full_summary.json")
+xtag = tag if os.path.exists(os.path.join(P, tag + "_ncu_full_summary.json")) else "r1l"     # the extractor kernels' last full capture
+d = J(xtag + "_ncu_full_summary.json")
 rows = [r for r in csv.reader(open(os.path.join(P, tag + "_launches.csv"))) if len(r) > 5]
 ix = {h: i for i, h in enumerate(rows[0])}
 t, n = defaultdict(float), defaultdict(int)
@@ -53,7 +54,7 @@ mrows = "\n".join("| `%s` | %s | %.2f |" % (k, v["workload"], v.get("ms_per_step
 scale = ""
 for f, what in (("_bench_2gpu", None), ("_bench_4gpu", "4 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_8gpu", "8 GPUs, 256 VGA frames per GPU (weak)"),
                 ("_bench_hd_1gpu", "1 GPU, 1280x720 / 2000 kp, 1024 frames"), ("_bench_hd_4gpu", "4 GPUs, the same 1024 HD frames (strong)")):
-    for src in (tag, "r1k", "r1i"):            # the newest run of each configuration (the multi-GPU runs are not repeated for every step)
+    for src in (tag, "r1l", "r1k", "r1i"):            # the newest run of each configuration (the multi-GPU runs are not repeated for every step)
         fn = os.path.join(P, src + f + ".json")
         if what and os.path.exists(fn):
             x = json.load(open(fn))
@@ -68,14 +69,15 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 |---|---|---|
 | `{tag}_bench.json` | **current code**: `python bench.py --steps 20 --warmup 3`, no profiler (extractor, every matching row, device pipeline, CPU reference arm) | |
 | `{tag}_launches.csv` | ncu launch list of the same code (`gpu__time_duration.sum`, `--clock-control none`, cold-cache and serialised) | `ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-matching` |
-| `{tag}_ncu_full_summary.json` | `ncu --set full --clock-control none --import-source on`, one batch-256 launch of every extractor kernel | `ncu --set full ... -k regex:"k_fast|k_blur|k_describe|k_resize|k_quadtree" -s 11 -c 11 python tools/prof_extract.py`, summarised by `tools/ncu_summary.py` |
-| `{tag}_ncu_source_k_*.json` | the source page of the same capture: share of executed instructions and of stall samples per source line (lines >= 1 %) | `tools/ncu_summary.py` |
+| `{xtag}_ncu_full_summary.json` | `ncu --set full --clock-control none --import-source on`, one batch-256 launch of every extractor kernel (unchanged since) | `ncu --set full ... -k regex:"k_fast|k_blur|k_describe|k_resize|k_quadtree" -s 11 -c 11 python tools/prof_extract.py`, summarised by `tools/ncu_summary.py` |
+| `{xtag}_ncu_source_k_*.json` | the source page of the same capture: share of executed instructions and of stall samples per source line (lines >= 1 %) | `tools/ncu_summary.py` |
 | `traffic.json` | `dram__bytes_read.sum + dram__bytes_write.sum` per launch and stage from that capture; `bench.py` reports it as `roofline.traffic` | |
 | `{tag}_bench_4gpu.json`, `{tag}_bench_8gpu.json`, `{tag}_bench_hd_1gpu.json`, `{tag}_bench_hd_4gpu.json` | scaling runs of the current code (below) | `torchrun --nproc-per-node N bench.py --gpus N [--workload hd]` |
 | `r1j_bench_8gpu.json`, `r1j_topology_8gpu.txt` | the 8-GPU run repeated with each rank bound to its GPU's CPU set (no change: the box is one NUMA node with 32 virtual CPUs for 8 ranks) | |
 | `{tag}_ncu_match_summary.json` | `ncu --set full` of the matcher kernels (longest launch per kernel) | `ncu --set full ... -k regex:"k_init_topk|k_search_init|k_proj_topk|k_search_proj|k_last_topk|k_search_last|k_build_grid" -c 14 python tools/prof_match.py`, summarised by `tools/ncu_match_summary.py` |
 | `r1k_int_peak.json` | integer-pipe peaks (POPC, LOP3, IADD3 lanes per clock and SM) and register-only Hamming rates: the matching roofline's denominator | `tools/int_peak.cu` |
-| `r1k_*` | the step before (before the CSR-ordered candidate records and the CUDA graph of small host calls): same extractor kernels; its 4- and 8-GPU runs are the current multi-GPU evidence | |
+| `r1l_*` | the step before (before the threshold pruning in `k_init_topk`: SearchForInitialization 5.71 ms); same extractor kernels, whose full ncu capture it holds | |
+| `r1k_*` | two steps before (before the CSR-ordered candidate records and the CUDA graph of small host calls); its 4- and 8-GPU runs are the current multi-GPU evidence | |
 | `r1i_*`, `r1h_ncu_match_summary.json` | an earlier step of this round (before the carry-save distance, the speculative resolve, the row-pair blur and the stereo row): 152 k frames/s, SearchForInitialization 12.3 ms | |
 | `r1c_*` ... `r1h_*` | earlier steps of this round, kept for the record (`r1f`: FAST 0.76 ms, describe 0.32 ms; `r1e`: FAST 0.85 ms) | |
 | `r1a_*`, `r1b_*` | first bit-exact CUDA path, before any tuning | |
@@ -109,13 +111,15 @@ HD workload is upload-bound already on one GPU (0.92 MB per frame against ~55 GB
 |---|---|---|
 {mrows}
 
-The headline matching config (4096 x 1000 x 1000 = 4.1 G distance evaluations) is bound by the integer pipes, not by bytes.
+The headline matching config (4096 x 1000 x 1000 = 4.1 G candidate evaluations) is bound by the integer pipes, not by bytes.
 `tools/int_peak.cu` measured them on this GPU (`r1k_int_peak.json`): {ip['popc_per_clk_per_sm']:.1f} POPC and {ip['lop3_per_clk_per_sm']:.1f} LOP3 lanes per clock and SM; a
 register-only loop reaches {ip['hamming256_Geval_s']['popc8']:.0f} G evaluations/s with the plain 8-POPC distance and {ip['hamming256_Geval_s']['csa_popc6']:.0f} / {ip['hamming256_Geval_s']['csa_popc4']:.0f} G/s with 6 / 4 POPC after
-carry-save adders.  `k_init_topk` uses the 5-POPC form (POPC bound: {sfi['roofline']['peak']:.0f} G evaluations/s); the whole call (grid + top-4 +
-greedy resolve) reaches **{sfi['roofline']['achieved']:.0f} G evaluations/s = {100*sfi['roofline']['frac']:.0f} % of that bound** (`{tag}_bench.json: matching.search_for_initialization.roofline`), the kernel alone
-{4096e6/mk['k_init_topk']['time_us']/1e3:.0f} G/s with the ALU pipe {mk['k_init_topk'].get('alu_pipe_pct',0):.0f} % busy (`{tag}_ncu_match_summary.json`).  The greedy, order-dependent halves (`k_search_*`) run one
-warp per frame (pair) and decide 32 queries speculatively per round; their time is a dependent chain per frame, not throughput.
+carry-save adders.  `k_init_topk` evaluates the 128-bit half distance of every candidate (3 POPC) and finishes only the
+candidates that can still matter (5 POPC more for about one in ten; exact, see DESIGN.md).  Against the POPC pipe at 3 POPC per
+candidate ({sfi['roofline']['peak']:.0f} G candidates/s) the whole call (grid + top-4 + greedy resolve) reaches **{sfi['roofline']['achieved']:.0f} G candidates/s =
+{100*sfi['roofline']['frac']:.0f} %** (`{tag}_bench.json: matching.search_for_initialization.roofline`), the kernel alone {4096e6/mk['k_init_topk']['time_us']/1e3:.0f} G/s with the
+ALU pipe {mk['k_init_topk'].get('alu_pipe_pct',0):.0f} % busy (`{tag}_ncu_match_summary.json`).  The greedy, order-dependent halves (`k_search_*`) run one warp per
+frame (pair) and decide 32 queries speculatively per round; their time is a dependent chain per frame, not throughput.
 
 {mtab}
 ### kernel shares: ncu launch list vs CUDA events
@@ -134,7 +138,7 @@ operations per byte, and every kernel is bound by instruction issue (50-80 % of 
 lost to dependent-load latency.  `k_fast` (the kernel `bench.py` names in `roofline`) moves {l['roofline']['traffic']/1e6:.0f} MB of DRAM traffic per
 launch against {l['roofline']['achieved']*ev['fast']:.0f} MB algorithmic, so there are no wasted re-reads; it executes {fast['inst_executed']/1e6:.0f} M warp instructions per launch
 (about {fast['inst_executed']/243200:.0f} per 30 x 30-px cell) at {fast['issue_active_pct']:.0f} % issue utilisation, which is what its {ev['fast']:.2f} ms is made of.  The work this round went into removing
-instructions (`{tag}_ncu_source_k_fast.json` shows where the remaining ones are): 1.80 ms -> {ev['fast']:.2f} ms for `k_fast`,
+instructions (`{xtag}_ncu_source_k_fast.json` shows where the remaining ones are): 1.80 ms -> {ev['fast']:.2f} ms for `k_fast`,
 0.60 -> {ev['describe']:.2f} ms for `k_describe`, 0.91 -> {ev['blur']:.2f} ms for `k_blur`, 3.88 ms -> {l['ms_per_step']:.2f} ms for the step.
 
 ## r1a/r1b (first correct path, before tuning) -- kept for the record
