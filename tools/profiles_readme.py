@@ -52,7 +52,7 @@ for k in ("k_build_grid", "k_init_topk", "k_search_init", "k_proj_topk", "k_sear
         mtab += "| `%s` | %.0f | %.0f %% | %.0f %% | %.0f %% | %d | %.0f M |\n" % (k, e["time_us"], e["issue_active_pct"], e.get("alu_pipe_pct", 0), e["warps_active_pct"], int(e["regs"]), e["inst_executed"] / 1e6)
 mrows = "\n".join("| `%s` | %s | %.2f |" % (k, v["workload"], v.get("ms_per_step", v.get("ms_per_call"))) for k, v in m.items())
 scale = ""
-for f, what in (("_bench_2gpu", None), ("_bench_4gpu", "4 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_8gpu", "8 GPUs, 256 VGA frames per GPU (weak)"),
+for f, what in (("_bench_2gpu", "2 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_4gpu", "4 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_8gpu", "8 GPUs, 256 VGA frames per GPU (weak)"),
                 ("_bench_hd_1gpu", "1 GPU, 1280x720 / 2000 kp, 1024 frames"), ("_bench_hd_4gpu", "4 GPUs, the same 1024 HD frames (strong)")):
     for src in (tag, "r1l", "r1k", "r1i"):            # the newest run of each configuration (the multi-GPU runs are not repeated for every step)
         fn = os.path.join(P, src + f + ".json")
