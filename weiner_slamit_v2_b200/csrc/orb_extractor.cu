@@ -79,7 +79,7 @@ struct ExtractParams {
     int* status;                     // device error bits
     int blurVariant;
     // k_fast shared-memory geometry
-    int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <36,64> instantiation
+    int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <38,64> instantiation
     // k_quadtree shared-memory geometry
     int qtNC, qtPC;
     LevelGeo lv[MAXL];
@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
 //  * pass 3: 3x3 NMS on the byte score map; the iniThFAST -> minThFAST retry is a per-cell count
 //    (a corner at threshold t is exactly "score >= t", so one score map serves both thresholds).
 // FAST_TPW / FAST_TH are compile-time so every ring load is `base + immediate`:
-//   <24,42> covers cells up to 39 x 36 px (every level of the 640x480 ... 1920x1080 pyramids),
-//   <36,64> covers the largest possible cell (57 x 57).
+//   <26,42> covers cells up to 39 x 36 px (every level of the 640x480 ... 1920x1080 pyramids),
+//   <38,64> covers the largest possible cell (57 x 57); the pitches 26 and 38 are 2 x odd (see pass 1).
 constexpr int FAST_WARPS = 1;     // cells per CTA (measured: 1 -> 0.749 ms, 2 -> 0.762, 4 -> 0.779 per 256 frames); warps never synchronise with each other
 
 template <int TPW, int TH>
@@ -318,8 +318,12 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     // valid shared memory and pass 2 masks it by x >= dw.)
     int nq = 0;
     {
-        int r = lane / nquad, k = lane - r * nquad;
-        const int stepR = 32 / nquad, stepK = 32 - stepR * nquad;
+        // Lanes walk DOWN a column of quads (consecutive lanes = consecutive rows of the same quad column): with a row
+        // pitch of TPW = 26 (or 38) words, sixteen consecutive rows start in sixteen different even banks, so the
+        // 8-byte loads of a half-warp touch all 32 banks once.  Walking along the rows (10 quads per row, 24-word
+        // pitch) cost two wavefronts per half-warp and made the kernel shared-memory bound (83 % of the data pipe).
+        int k = lane / dh, r = lane - k * dh;
+        const int stepK = 32 / dh, stepR = 32 - stepK * dh;
         for (int idx = lane; idx - lane < total; idx += 32) {
             bool passA = false, passB = false;
             if (idx < total) {
@@ -349,8 +353,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
             nq += __popc(balA);
             if (passB) queue[nq + __popc(balB & ltmask)] = (uint16_t)(r * 64 + 2 * k + 1);
             nq += __popc(balB);
-            r += stepR; k += stepK;
-            if (k >= nquad) { k -= nquad; r++; }
+            k += stepK; r += stepR;
+            if (r >= dh) { r -= dh; k++; }
         }
     }
     __syncwarp();
@@ -1302,10 +1306,10 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
 
     // k_fast: pick the tile instantiation that holds the largest cell (+6 halo, +6 alignment slack)
     if (maxWCell > 57 || maxHCell > 57) { set_error("FAST cell larger than 57 px"); delete h; return ORBB200_EGEOMETRY; }
-    P.fastLarge = FastGeo<24, 42>::fits(maxWCell, maxHCell) ? 0 : 1;
-    if (P.fastLarge && !FastGeo<36, 64>::fits(maxWCell, maxHCell)) { set_error("FAST cell does not fit the staging tile"); delete h; return ORBB200_EGEOMETRY; }
+    P.fastLarge = FastGeo<26, 42>::fits(maxWCell, maxHCell) ? 0 : 1;
+    if (P.fastLarge && !FastGeo<38, 64>::fits(maxWCell, maxHCell)) { set_error("FAST cell does not fit the staging tile"); delete h; return ORBB200_EGEOMETRY; }
     P.totalCells = cells;
-    h->fastSmem = (size_t)FAST_WARPS * (P.fastLarge ? FastGeo<36, 64>::WARP_BYTES : FastGeo<24, 42>::WARP_BYTES);
+    h->fastSmem = (size_t)FAST_WARPS * (P.fastLarge ? FastGeo<38, 64>::WARP_BYTES : FastGeo<26, 42>::WARP_BYTES);
     // k_quadtree shared memory: 88 bytes per node slot + 6 bytes per candidate held on chip
     P.qtNC = (int)align_up(maxKpCap + 8, 8);
     const size_t perNode = 8 + 8 + 8 + 4 * 7 + 16 + 16;
@@ -1347,8 +1351,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = P.fastLarge
-        ? cudaFuncSetAttribute(k_fast<36, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem)
-        : cudaFuncSetAttribute(k_fast<24, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
+        ? cudaFuncSetAttribute(k_fast<38, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem)
+        : cudaFuncSetAttribute(k_fast<26, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qtSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
@@ -1441,8 +1445,8 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
     STAGE_MARK(1);
     {
         const dim3 grid((h->totalCells + FAST_WARPS - 1) / FAST_WARPS, batch);
-        if (P.fastLarge) k_fast<36, 64><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
-        else k_fast<24, 42><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
+        if (P.fastLarge) k_fast<38, 64><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
+        else k_fast<26, 42><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_fast"); launches++;
     STAGE_MARK(2);
