@@ -16,6 +16,9 @@ M = {"time_us": "gpu__time_duration.sum", "issue_active_pct": "smsp__issue_activ
      "stall_wait": "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
      "stall_barrier": "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
      "stall_math_throttle": "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+     "alu_pipe_pct": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+     "xu_pipe_pct": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+     "shared_mem_pipe_pct": "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
      "regs": "launch__registers_per_thread", "smem_per_block": "launch__shared_mem_per_block_dynamic",
      "inst_executed": "smsp__inst_executed.sum"}
 
