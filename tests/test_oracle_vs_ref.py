@@ -473,3 +473,40 @@ def test_stereo_oracle_reproduces_reference_golden_vectors():
         ur, dep, kept, skipped = O.compute_stereo_matches(kl, dl, kr, dr, sc, isc, lp, rp, mb, mbf)
         assert skipped == 0 and kept == int(g["n_%d" % i])
         assert ur.tobytes() == g["ur_%d" % i].tobytes() and dep.tobytes() == g["depth_%d" % i].tobytes()
+
+
+@needs_refm
+def test_compute_stereo_matches_random_keypoints_match_reference():
+    """Keypoints that are not the extractor's: random positions (kept far enough inside every level that the reference's
+    rowRange / colRange stay legal), random octaves, descriptor pairs at every distance, disparities on both sides of the
+    accepted range -- the reference's own ComputeStereoMatches against the restatement, 25 frames."""
+    rng = np.random.default_rng(2024)
+    ex = O.OracleExtractor(300, 1.2, 8, 20, 7)
+    for trial in range(25):
+        left = F.synthetic_frame(500 + trial, 320, 240)
+        right = F.stereo_right_frame(left, 500 + trial, max_disparity=30.0, band=24)
+        ex(left); lp = [ex.level_pixels(l).copy() for l in range(8)]
+        ex(right); rp = [ex.level_pixels(l).copy() for l in range(8)]
+        sc, isc = ex.scale_factors, ex.inv_scale_factors
+        n = 220
+        kl = np.zeros(n, O.KP_DTYPE)
+        kl["octave"] = rng.integers(0, 6, n)
+        m = 22.0 * sc[kl["octave"]] + 12.0               # margin in level-0 pixels: patch + sweep stay inside the level
+        kl["x"] = (m + rng.random(n) * (320 - 2 * m)).astype(np.float32)
+        kl["y"] = (m + rng.random(n) * (240 - 2 * m)).astype(np.float32)
+        dl = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+        kr = kl.copy()
+        kr["x"] = np.clip(kl["x"] - rng.uniform(-6, 45, n).astype(np.float32), m, 320 - m).astype(np.float32)
+        kr["y"] = (kl["y"] + rng.uniform(-3, 3, n)).astype(np.float32)
+        kr["octave"] = np.clip(kl["octave"] + rng.integers(-2, 3, n), 0, 7)
+        flips = np.packbits(rng.random((n, 256)) < rng.uniform(0.0, 0.45, (n, 1)), axis=1)
+        dr = dl ^ flips
+        perm = rng.permutation(n)
+        kr, dr = kr[perm], dr[perm]
+        mb, mbf = float(rng.uniform(0.05, 0.6)), float(rng.uniform(5, 40))
+        ur_o, dep_o, kept, skipped = O.compute_stereo_matches(kl, dl, kr, dr, sc, isc, lp, rp, mb, mbf)
+        if skipped:                                           # would be undefined in the reference: not comparable
+            continue
+        ur_r, dep_r, cnt = R.ref_compute_stereo_matches(kl, dl, kr, dr, sc, isc, lp, rp, mb, mbf)
+        assert kept == cnt
+        assert ur_o.tobytes() == ur_r.tobytes() and dep_o.tobytes() == dep_r.tobytes()
