@@ -2,7 +2,7 @@
 import csv, json, os, sys
 from collections import defaultdict
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1n"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1o"
 P = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
 J = lambda n: json.load(open(os.path.join(P, n)))
 l = J(tag + "_bench.json")
@@ -21,7 +21,7 @@ for r in rows[1:]:
         t[nm] += v; n[nm] += 1
 tot = sum(t.values())
 ev = l["kernel_ms_per_step"]; evtot = sum(ev.values())
-stage = {"k_resize": "pyramid", "k_fast<24, 42>": "fast", "k_quadtree": "quadtree", "k_blur": "blur", "k_describe": "describe", "k_pad_level0": None}
+stage = {"k_resize": "pyramid", "k_fast<26, 42>": "fast", "k_quadtree": "quadtree", "k_blur": "blur", "k_describe": "describe", "k_pad_level0": None}
 tab = "| kernel | launches | total us (ncu) | ncu share | CUDA-event ms / 256-frame step | event share |\n|---|---|---|---|---|---|\n"
 for k in stage:
     if k not in t:
@@ -54,7 +54,7 @@ mrows = "\n".join("| `%s` | %s | %.2f |" % (k, v["workload"], v.get("ms_per_step
 scale = ""
 for f, what in (("_bench_2gpu", "2 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_4gpu", "4 GPUs, 256 VGA frames per GPU (weak)"), ("_bench_8gpu", "8 GPUs, 256 VGA frames per GPU (weak)"),
                 ("_bench_hd_1gpu", "1 GPU, 1280x720 / 2000 kp, 1024 frames"), ("_bench_hd_4gpu", "4 GPUs, the same 1024 HD frames (strong)")):
-    for src in (tag, "r1m", "r1l", "r1k", "r1i"):            # the newest run of each configuration (the multi-GPU runs are not repeated for every step)
+    for src in (tag, "r1n", "r1m", "r1l", "r1k", "r1i"):            # the newest run of each configuration (the multi-GPU runs are not repeated for every step)
         fn = os.path.join(P, src + f + ".json")
         if what and os.path.exists(fn):
             x = json.load(open(fn))
@@ -76,9 +76,10 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 | `r1j_bench_8gpu.json`, `r1j_topology_8gpu.txt` | the 8-GPU run repeated with each rank bound to its GPU's CPU set (no change: the box is one NUMA node with 32 virtual CPUs for 8 ranks) | |
 | `{tag}_ncu_match_summary.json` | `ncu --set full` of the matcher kernels (longest launch per kernel) | `ncu --set full ... -k regex:"k_init_topk|k_search_init|k_proj_topk|k_search_proj|k_last_topk|k_search_last|k_build_grid" -c 14 python tools/prof_match.py`, summarised by `tools/ncu_match_summary.py` |
 | `r1k_int_peak.json` | integer-pipe peaks (POPC, LOP3, IADD3 lanes per clock and SM) and register-only Hamming rates: the matching roofline's denominator | `tools/int_peak.cu` |
-| `r1m_*`, `r1m_pipe_utilisation.csv`, `r1m_fast_shared_memory.csv` / `r1n_fast_shared_memory.csv` | the step before (before the bank-conflict-free FAST pass 1: `k_fast` 0.747 ms, 156 k frames/s); pipe utilisation of every extractor kernel; shared-memory wavefronts and bank conflicts of `k_fast` before / after; `r1n_ncu_match_summary.json` is a copy of `r1m_…` (matcher kernels unchanged) | |
-| `r1l_*` | two steps before (before the threshold pruning in `k_init_topk`: SearchForInitialization 5.71 ms) | |
-| `r1k_*` | three steps before (before the CSR-ordered candidate records and the CUDA graph of small host calls); its 4- and 8-GPU runs are the current multi-GPU evidence | |
+| `r1n_*` | the step before (one FAST pass at min(iniThFAST, minThFAST) instead of iniThFAST first: `k_fast` 0.716 ms, 160 k frames/s); its 1-GPU HD run and the matcher capture `r1n_ncu_match_summary.json` (matcher kernels unchanged since) still stand | |
+| `r1m_*`, `r1m_pipe_utilisation.csv`, `r1m_fast_shared_memory.csv` / `r1n_fast_shared_memory.csv` | two steps before (before the bank-conflict-free FAST pass 1: `k_fast` 0.747 ms, 156 k frames/s); pipe utilisation of every extractor kernel; shared-memory wavefronts and bank conflicts of `k_fast` before / after; `r1n_ncu_match_summary.json` is a copy of `r1m_…` (matcher kernels unchanged) | |
+| `r1l_*` | three steps before (before the threshold pruning in `k_init_topk`: SearchForInitialization 5.71 ms) | |
+| `r1k_*` | four steps before (before the CSR-ordered candidate records and the CUDA graph of small host calls); its 4- and 8-GPU runs are the current multi-GPU evidence | |
 | `r1i_*`, `r1h_ncu_match_summary.json` | an earlier step of this round (before the carry-save distance, the speculative resolve, the row-pair blur and the stereo row): 152 k frames/s, SearchForInitialization 12.3 ms | |
 | `r1c_*` ... `r1h_*` | earlier steps of this round, kept for the record (`r1f`: FAST 0.76 ms, describe 0.32 ms; `r1e`: FAST 0.85 ms) | |
 | `r1a_*`, `r1b_*` | first bit-exact CUDA path, before any tuning | |
