@@ -195,7 +195,7 @@ def run_reference(args):
         "config": {"workload": "batched ORB extraction, 256 synthetic 640x480 frames, 1000 kp/8 levels (configs[1])",
                    "frames_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": "%d of the 256 frames of one step, %d host threads, one ORBextractor each" % (sample, threads)},
+                         "sample": "%d of the %d frames of one step, %d host threads, one ORBextractor each" % (sample, BATCH, threads)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -385,7 +385,7 @@ def run_ours(args):
             sample = BATCH
             fps, kind, _ = cpu_extract_fps(frames[:sample], threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                                    "sample": "%d of the 256 frames of one step, %d host threads" % (sample, threads)}
+                                    "sample": "%d of the %d frames of one step, %d host threads" % (sample, BATCH, threads)}
             line["parity"] = parity_report(frames[:8], outs[0][0].numpy(), outs[0][1].numpy(), outs[0][2].numpy())
         _emit(line)
     if world > 1:
