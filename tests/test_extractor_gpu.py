@@ -6,7 +6,7 @@ import pytest
 
 import oracle_lib as O
 from weiner_slamit_v2_b200 import ORBextractor
-from weiner_slamit_v2_b200.frames import low_contrast_frame, synthetic_frame
+from weiner_slamit_v2_b200.frames import low_contrast_frame, plateau_retry_frame, synthetic_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -67,6 +67,21 @@ def test_low_contrast_retry_and_constant_image():
     assert counts[1] == 0                                    # constant image: no keypoints, descriptors released
     for f in (0, 2):
         ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], do)
+
+
+def test_retry_when_nms_empties_a_cell():
+    """k_fast runs at iniThFAST and repeats at minThFAST only for a cell left WITHOUT A KEYPOINT -- which is not the same
+    as without a corner: a plateau of equal scores has corners at 20 and no NMS survivor (ORBextractor.cc:827-833)."""
+    frames = np.stack([plateau_retry_frame(i) for i in range(4)])
+    ex = ORBextractor(*PARAMS, max_batch=4)
+    orc = O.OracleExtractor(*PARAMS)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(4):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        resp = orc.level_candidates(0)["response"]
+        assert (resp < 20).any() and (resp >= 20).any()
         assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
         assert np.array_equal(desc[f, :counts[f]], do)
 

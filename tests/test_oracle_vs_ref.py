@@ -72,6 +72,20 @@ def test_full_extractor_matches_reference_fresh_frames():
 
 
 @needs_ref
+def test_retry_when_nms_empties_a_cell_matches_reference():
+    """FAST(20) has corners in the cell but NMS keeps none (a plateau of equal scores) -> the reference retries at 7
+    (ORBextractor.cc:827-833).  The frames must really contain such cells: candidates below 20 next to corners at 20."""
+    o, r = O.OracleExtractor(), R.RefExtractor()
+    for i in range(3):
+        img = F.plateau_retry_frame(i)
+        ko, do = o(img)
+        kr, dr = r(img)
+        assert len(ko) > 0 and ko.tobytes() == kr.tobytes() and np.array_equal(do, dr)
+        resp = o.level_candidates(0)["response"]
+        assert (resp < 20).any() and (resp >= 20).any()
+
+
+@needs_ref
 def test_pyramid_border_matches_reference():
     r = R.RefExtractor(); o = O.OracleExtractor()
     img = F.synthetic_frame(5)

@@ -71,6 +71,27 @@ def low_contrast_frame(index, width=640, height=480):
     return img
 
 
+def plateau_retry_frame(index, width=640, height=480):
+    """Cells in which FAST(iniThFAST) finds corners but non-maximum suppression keeps none of them: the end of a 2-px wide
+    bar is a plateau of equal scores (a corner must be STRICTLY greater than its 8 neighbours), so the reference's
+    `if (vKeysCell.empty())` (ORBextractor.cc:829) fires although the cell has corners at 20, and the faint corner next to
+    it (contrast 12) appears through the FAST(minThFAST) retry.  Other cells hold a strong corner, a faint one, or both."""
+    rng = np.random.default_rng(7000 + int(index))
+    img = np.full((height, width), 60, np.uint8)
+    for j, cy in enumerate(range(40, height - 40, 48)):
+        for i, cx in enumerate(range(40, width - 40, 48)):
+            kind = (i + 2 * j + int(index)) % 4
+            ox, oy = rng.integers(-4, 5, 2)
+            x, y = cx + ox, cy + oy
+            if kind in (0, 1):
+                img[y - 14:y, x:x + 2] = 200                  # bar: plateau of equal FAST scores at its end
+            if kind in (1, 2):
+                img[y + 4:y + 14, x + 6:x + 16] = 180         # strong isolated corners
+            if kind in (0, 2, 3):
+                img[y + 4:y + 12, x - 14:x - 6] = 72          # faint corners: only FAST(7) sees them
+    return img
+
+
 def stereo_right_frame(left, index, max_disparity=48.0, band=40):
     """The right image of a rectified pair: every band of rows sees the left image shifted by its own (fractional)
     disparity, linearly interpolated, plus a little noise, so ComputeStereoMatches finds row-aligned matches, a cost
