@@ -104,7 +104,7 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 {scale}
 Device-resident throughput scales 4.0x on 4 and 8.0x on 8 GPUs (no data-path collective). The end-to-end figures stop scaling
 at 3-4 GPUs and vary from box to box: the ranks share one virtual host (32 vCPUs, one NUMA node, `r1j_topology_8gpu.txt`) and
-each asks it for 48 GB/s of page-locked uploads (157 k frames/s x 307 KB), which that host does not deliver eight times over; the
+each asks it for 54 GB/s of page-locked uploads (175 k frames/s x 307 KB), which that host does not deliver eight times over; the
 HD workload is upload-bound already on one GPU (0.92 MB per frame against ~55 GB/s of PCIe).
 
 ### matching rows (`{tag}_bench.json`)
