@@ -334,9 +334,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
         int k = lane / dh, r = lane - k * dh;
         const int stepK = 32 / dh, stepR = 32 - stepK * dh;
         for (int idx = lane; idx - lane < total; idx += 32) {
-            bool passA = false, passB = false;
-            if (idx < total) {
-                const uint32_t* b = tbase + r * TPW + 2 * k;
+            bool passA, passB;
+            const bool act = idx < total;
+            {   // lanes past the end test quad (0, 0) and are masked afterwards: no divergent region around the loads
+                const uint32_t* b = tbase + (act ? r * TPW + 2 * k : 0);
                 const uint2 c = *reinterpret_cast<const uint2*>(b);                 // centres: pair A = c.x, pair B = c.y
                 const uint2 lf = *reinterpret_cast<const uint2*>(b - 2), rt = *reinterpret_cast<const uint2*>(b + 2);
                 const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
@@ -347,14 +348,14 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
                     const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4, R12), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
                     const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.x, dn.x), __vminu2(R4, R12), __vminu2(u2.y, d2l)), __vminu2(d2.y, u2l));
                     const uint32_t hiV = c.x + T2;
-                    passA = __vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, c.x) != c.x;
+                    passA = act && (__vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, c.x) != c.x);
                 }
                 {
                     const uint32_t R4 = FAST_PAIR(rt.x, rt.y), R12 = FAST_PAIR(lf.y, c.x);
                     const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.y, dn.y), __vmaxu2(R4, R12), __vmaxu2(u2r, d2.x)), __vmaxu2(d2r, u2.x));
                     const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.y, dn.y), __vminu2(R4, R12), __vminu2(u2r, d2.x)), __vminu2(d2r, u2.x));
                     const uint32_t hiV = c.y + T2;
-                    passB = __vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, c.y) != c.y;
+                    passB = act && (__vmaxu2(mb, hiV) != hiV || __vminu2(md + T2, c.y) != c.y);
                 }
             }
             const unsigned balA = __ballot_sync(FULL, passA), balB = __ballot_sync(FULL, passB);
