@@ -735,7 +735,7 @@ def run_stereo(local, steps):
 def _issue_profile(kernel):
     """Issue-slot use and instruction count of `kernel` from the committed ncu --set full summary: the path is
     integer/byte work bound by instruction issue, so this is the number that explains the HBM fraction."""
-    for tag in ("r1o", "r1n", "r1m", "r1l", "r1k"):
+    for tag in ("r1p", "r1o", "r1n", "r1m", "r1l", "r1k"):
         p = os.path.join(ROOT, "profiles", tag + "_ncu_full_summary.json")
         if os.path.exists(p):
             with open(p) as f:

@@ -76,7 +76,7 @@ Everything here was produced on a B200 through `gpurun`; bench numbers are never
 | `r1j_bench_8gpu.json`, `r1j_topology_8gpu.txt` | the 8-GPU run repeated with each rank bound to its GPU's CPU set (no change: the box is one NUMA node with 32 virtual CPUs for 8 ranks) | |
 | `{tag}_ncu_match_summary.json` | `ncu --set full` of the matcher kernels (longest launch per kernel) | `ncu --set full ... -k regex:"k_init_topk|k_search_init|k_proj_topk|k_search_proj|k_last_topk|k_search_last|k_build_grid" -c 14 python tools/prof_match.py`, summarised by `tools/ncu_match_summary.py` |
 | `r1k_int_peak.json` | integer-pipe peaks (POPC, LOP3, IADD3 lanes per clock and SM) and register-only Hamming rates: the matching roofline's denominator | `tools/int_peak.cu` |
-| `r1p_bench_extractor_only.json` | `bench.py --no-cpu-baseline --no-matching` after one more `k_fast` change (pass 1 without the divergent region around its loads: 0.578 -> 0.572 ms, 175.7 k frames/s); everything else in `r1o_*` is unchanged by it | |
+| `r1p_bench_extractor_only.json` | `bench.py --no-cpu-baseline --no-matching` after one more `k_fast` change (pass 1 without the divergent region around its loads: 0.578 -> 0.572 ms, 175.7 k frames/s); everything else in `r1o_*` is unchanged by it; `r1p_ncu_full_summary.json`, `r1p_ncu_source_k_fast.json`: `ncu --set full` of that final `k_fast` (one batch-256 launch: 582 us under ncu, 463 M warp instructions, issue slots 71 %, ALU pipe 75 %, 24 resident warps per SM of the 25 that 8 KB + 1 KB of shared memory per one-warp CTA allow) | `ncu --set full ... -k regex:k_fast -s 1 -c 1 python tools/prof_extract.py` |
 | `r1n_*` | the step before (one FAST pass at min(iniThFAST, minThFAST) instead of iniThFAST first: `k_fast` 0.716 ms, 160 k frames/s); its 1-GPU HD run and the matcher capture `r1n_ncu_match_summary.json` (matcher kernels unchanged since) still stand | |
 | `r1m_*`, `r1m_pipe_utilisation.csv`, `r1m_fast_shared_memory.csv` / `r1n_fast_shared_memory.csv` | two steps before (before the bank-conflict-free FAST pass 1: `k_fast` 0.747 ms, 156 k frames/s); pipe utilisation of every extractor kernel; shared-memory wavefronts and bank conflicts of `k_fast` before / after; `r1n_ncu_match_summary.json` is a copy of `r1m_…` (matcher kernels unchanged) | |
 | `r1l_*` | three steps before (before the threshold pruning in `k_init_topk`: SearchForInitialization 5.71 ms) | |
