@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 WIDTH, HEIGHT, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
 BATCH = 256                       # frames per GPU per step (configs[1])
 WORKLOAD = "batched ORB extraction, 256 synthetic 640x480 frames per GPU, 1000 kp/8 levels, FAST 20/7 (configs[1])"
+METRIC = "ORB frames/s (640x480, 1000 kp, 8 lvl)"
 DISTINCT = 32                     # distinct synthetic frames generated per rank (tiled to BATCH)
 
 # Algorithmic HBM bytes per frame and per kernel (DESIGN.md "Roofline model"):
@@ -189,11 +190,10 @@ def run_reference(args):
         total_t += sample / fps
     value = sample * args.steps / total_t
     line = {
-        "impl": "reference", "metric": "ORB frames/s (640x480, 1000 kp, 8 lvl)", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_t / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "batched ORB extraction, 256 synthetic 640x480 frames, 1000 kp/8 levels (configs[1])",
-                   "frames_per_step": sample},
+        "config": {"workload": WORKLOAD, "frames_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
                          "sample": "%d of the %d frames of one step, %d host threads, one ORBextractor each" % (sample, BATCH, threads)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -354,7 +354,7 @@ def run_ours(args):
         dom = int(np.argmax(per_stage))
         ach = ALG_BYTES[STAGES[dom]] * BATCH / (per_stage[dom] * 1e-3) / 1e9
         line = {
-            "metric": "ORB frames/s (640x480, 1000 kp, 8 lvl)", "value": value, "unit": "frames/s",
+            "metric": METRIC, "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "hd" else "weak",
@@ -787,8 +787,9 @@ def main():
                     help="vga = configs[1] (the headline, default); hd = configs[3]: 1280x720, 2000 kp, batch 1024 sharded over the GPUs")
     args = ap.parse_args()
     if args.workload == "hd":
-        global WIDTH, HEIGHT, NFEAT, BATCH, WORKLOAD, ALG_BYTES
+        global WIDTH, HEIGHT, NFEAT, BATCH, WORKLOAD, ALG_BYTES, METRIC
         WIDTH, HEIGHT, NFEAT = 1280, 720, 2000
+        METRIC = "ORB frames/s (1280x720, 2000 kp, 8 lvl)"
         BATCH = 1024 // max(1, args.gpus)          # strong scaling: the 1024-frame batch is split over the GPUs
         WORKLOAD = "1280x720 frames, nFeatures=2000, 8 levels, batch 1024 sharded over %d B200 (configs[3])" % args.gpus
         ALG_BYTES = {"pyramid": 2781331 + 1931488, "fast": 2853088 + 160000, "quadtree": 160000 + 32000,
