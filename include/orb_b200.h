@@ -10,7 +10,8 @@
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a
  * negative ORBB200_E* code (orbb200_last_error() gives the text, per thread); nothing
- * throws; a handle owns all device memory and one CUDA stream and is NOT re-entrant (same
+ * throws; a handle owns all device memory and its CUDA streams (calls are ordered on ONE of them,
+ * orbb200_extractor_stream / orbb200_matcher_stream) and is NOT re-entrant (same
  * rule as an ORBextractor instance, S/Frame.cc:93-96 uses two instances from two threads);
  * different handles may be used from different threads / on different GPUs.
  * There is no CPU fallback: without a CUDA device every compute entry point fails.
@@ -104,6 +105,9 @@ int orbb200_extractor_last_launches(const orbb200_extractor *h);
 
 /* Per-stage device time of the most recent call, from CUDA events recorded on the handle's stream
  * between the kernels: ms5 = {pyramid (all resize launches), FAST, quadtree, blur, orientation+descriptor}.
+ * In calls of up to 8 frames the blur runs on the handle's internal side stream beside the quadtree (joined
+ * before the descriptors; everything stays ordered on the handle's stream): there "blur" is the part of the
+ * blur that outlasts the quadtree.
  * Off by default; the bench harness turns it on to compute per-kernel roofline fractions. */
 int orbb200_extractor_set_profiling(orbb200_extractor *h, int on);
 int orbb200_extractor_stage_ms(orbb200_extractor *h, float *ms5);
