@@ -71,12 +71,13 @@ def test_low_contrast_retry_and_constant_image():
         assert np.array_equal(desc[f, :counts[f]], do)
 
 
-def test_retry_when_nms_empties_a_cell():
+@pytest.mark.parametrize("size,params", [((640, 480), PARAMS), ((320, 240), (500, 1.2, 8, 20, 7))])   # both FAST tile instantiations
+def test_retry_when_nms_empties_a_cell(size, params):
     """k_fast runs at iniThFAST and repeats at minThFAST only for a cell left WITHOUT A KEYPOINT -- which is not the same
     as without a corner: a plateau of equal scores has corners at 20 and no NMS survivor (ORBextractor.cc:827-833)."""
-    frames = np.stack([plateau_retry_frame(i) for i in range(4)])
-    ex = ORBextractor(*PARAMS, max_batch=4)
-    orc = O.OracleExtractor(*PARAMS)
+    frames = np.stack([plateau_retry_frame(i, *size) for i in range(4)])
+    ex = ORBextractor(*params, width=size[0], height=size[1], max_batch=4)
+    orc = O.OracleExtractor(*params)
     kps, desc, counts = ex.extract_batch(frames)
     for f in range(4):
         ko, do = _compare_frame(ex, orc, frames, f)

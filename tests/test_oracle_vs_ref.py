@@ -76,8 +76,8 @@ def test_retry_when_nms_empties_a_cell_matches_reference():
     """FAST(20) has corners in the cell but NMS keeps none (a plateau of equal scores) -> the reference retries at 7
     (ORBextractor.cc:827-833).  The frames must really contain such cells: candidates below 20 next to corners at 20."""
     o, r = O.OracleExtractor(), R.RefExtractor()
-    for i in range(3):
-        img = F.plateau_retry_frame(i)
+    for i in range(6):
+        img = F.plateau_retry_frame(i) if i < 3 else F.plateau_retry_frame(i, 320, 240)
         ko, do = o(img)
         kr, dr = r(img)
         assert len(ko) > 0 and ko.tobytes() == kr.tobytes() and np.array_equal(do, dr)
