@@ -102,6 +102,14 @@ int orbb200_extractor_outputs(orbb200_extractor *h, orbb200_keypoint **d_keypoin
 void *orbb200_extractor_stream(orbb200_extractor *h);
 /* Number of kernel launches the last extract call issued. */
 int orbb200_extractor_last_launches(const orbb200_extractor *h);
+/* CUDA device ordinal the handle lives on (every entry point makes it current for the calling thread). */
+int orbb200_extractor_device(const orbb200_extractor *h);
+/* TEST HOOK for the device-side error path: clamps the per-level FAST candidate capacity to `candidates_per_level`
+ * (the real capacity is a strict bound, so the overflow bit cannot be provoked otherwise; <= 0 restores it).  A later
+ * extract call that finds more candidates on a level drops the excess, raises the device status bit and the
+ * synchronising call (orbb200_extract_host, _host_wait, orbb200_extractor_sync) returns ORBB200_ECUDA with
+ * orbb200_last_error() naming "candidate overflow". */
+int orbb200_extractor_debug_set_capacity(orbb200_extractor *h, int candidates_per_level);
 
 /* Per-stage device time of the most recent call, from CUDA events recorded on the handle's stream
  * between the kernels: ms5 = {pyramid (all resize launches), FAST, quadtree, blur, orientation+descriptor}.
@@ -137,6 +145,7 @@ void orbb200_matcher_destroy(orbb200_matcher *m);
 void *orbb200_matcher_stream(orbb200_matcher *m);
 int orbb200_matcher_sync(orbb200_matcher *m);
 int orbb200_matcher_last_launches(const orbb200_matcher *m);
+int orbb200_matcher_device(const orbb200_matcher *m);
 
 /* Replaces ORBmatcher::DescriptorDistance (S/ORBmatcher.cc:1651-1667) for n independent
  * descriptor pairs a[i], b[i] (32 bytes each, HOST memory); dist[i] in 0..256. */

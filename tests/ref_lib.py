@@ -1,5 +1,6 @@
 """ctypes binding of oracle/_ref/libref_orb.so: the reference's OWN unmodified ORBextractor.cc
 compiled for x86 against mini-cv (see oracle/ref_harness.cc).  TEST INFRASTRUCTURE ONLY."""
+import contextlib
 import ctypes as C
 import os
 
@@ -101,19 +102,53 @@ def matcher_available():
     return os.path.exists(REFM_SO)
 
 
+def _load_matcher_library(path):
+    L = C.CDLL(path)
+    L.refm_descriptor_distance.argtypes = [_u8p, _u8p]
+    L.refm_search_for_initialization.argtypes = ([C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p] * 2 +
+                                                 [_f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p])
+    L.refm_search_by_projection.argtypes = [
+        C.c_int, _u8p, _u8p, _f32p, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p,
+        C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p, _i32p,
+        C.c_int, _f32p, _f32p, C.c_float, C.c_float]
+    return L
+
+
 def mlib():
     global _mlib
     if _mlib is None:
-        L = C.CDLL(REFM_SO)
-        L.refm_descriptor_distance.argtypes = [_u8p, _u8p]
-        L.refm_search_for_initialization.argtypes = ([C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p] * 2 +
-                                                     [_f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p])
-        L.refm_search_by_projection.argtypes = [
-            C.c_int, _u8p, _u8p, _f32p, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p,
-            C.c_int, _f32p, _f32p, _i32p, _f32p, _u8p, _i32p, _i32p,
-            C.c_int, _f32p, _f32p, C.c_float, C.c_float]
-        _mlib = L
+        _mlib = _load_matcher_library(REFM_SO)
     return _mlib
+
+
+# ---- the same harness with the DROP-IN bodies linked in place of the reference's (oracle/Makefile, `make shimm`):
+# every ref_* wrapper below then drives weiner_slamit_v2_b200/shim/*.cc on real ORB_SLAM2::Frame / MapPoint / KeyFrame
+# objects, and the search itself runs on the GPU through liborb_b200.so.
+SHIMM_SO = os.path.join(ORACLE_DIR, "_ref", "libshim_matcher.so")
+_shimlib = None
+
+
+def shim_available():
+    return os.path.exists(SHIMM_SO)
+
+
+def shimlib():
+    global _shimlib
+    if _shimlib is None:
+        _shimlib = _load_matcher_library(SHIMM_SO)
+    return _shimlib
+
+
+@contextlib.contextmanager
+def shim_bodies():
+    """Inside this block the ref_* wrappers call libshim_matcher.so instead of libref_matcher.so."""
+    global _mlib
+    saved = _mlib
+    _mlib = shimlib()
+    try:
+        yield _mlib
+    finally:
+        _mlib = saved
 
 
 def _p(a, t):

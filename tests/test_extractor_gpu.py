@@ -286,3 +286,128 @@ def test_opencv_249_blur_taps():
         assert c == len(ko) and kps[f, :c].tobytes() == ko.tobytes() and np.array_equal(desc[f, :c], do)
         k0, d0 = ref0(frames[f])
         assert not np.array_equal(d0, do)           # the two tap sets really differ
+
+
+# ---- the reference's own outputs, directly (tests/golden/ref_extract_*.npz come from oracle/_ref = the reference's
+# unmodified ORBextractor.cc run by tools/gen_golden.py): CUDA against the reference without the oracle in between
+import glob
+import hashlib
+import os
+import threading
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_extract_*.npz")))
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cuda_reproduces_reference_golden_vectors(path):
+    g = np.load(path)
+    nf, sf, nl, ini, mn = g["params"]
+    meta = [str(m) for m in g["meta"]]
+    gen = {"synthetic_frame": synthetic_frame, "low_contrast_frame": low_contrast_frame}[meta[0]]
+    w, h = int(meta[1]), int(meta[2])
+    frames = np.stack([gen(int(i), w, h) for i in meta[3:]])
+    ex = ORBextractor(int(nf), float(sf), int(nl), int(ini), int(mn), width=w, height=h, max_batch=len(frames))
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(len(frames)):
+        assert np.array_equal(_sha(frames[f]), g["frame_sha_%d" % f]), "frame generator drifted"
+        n = int(counts[f])
+        assert n == len(g["kps_%d" % f])
+        assert kps[f, :n].tobytes() == g["kps_%d" % f].tobytes(), "keypoints differ from the reference's"
+        assert np.array_equal(desc[f, :n], g["desc_%d" % f]), "descriptors differ from the reference's"
+        for l in range(int(nl)):
+            assert np.array_equal(_sha(ex.get_level(f, l)), g["pyr_sha_%d" % f][l]), "pyramid level %d" % l
+
+
+def test_handles_of_different_sizes_in_any_order():
+    """A kernel's dynamic shared-memory limit is per-function state shared by all handles: a handle created LATER with
+    a smaller quadtree must not lower it under an older, larger one (Tracking.cc:156-162 creates the 2 * nFeatures
+    initialisation extractor first and the nFeatures one after it, and Reset() returns to the first)."""
+    frames = np.stack([synthetic_frame(20 + i) for i in range(16)])
+    big = ORBextractor(2000, 1.2, 8, 20, 7, max_batch=16)
+    small = ORBextractor(500, 1.2, 8, 20, 7, max_batch=16)
+    ks, ds, cs = small.extract_batch(frames[:2])
+    kb, db, cb = big.extract_batch(frames)                        # batch > 8: plain launches, not the captured graph
+    ob, os_ = O.OracleExtractor(2000, 1.2, 8, 20, 7), O.OracleExtractor(500, 1.2, 8, 20, 7)
+    for f in (0, 9, 15):
+        ko, do = ob(frames[f])
+        assert cb[f] == len(ko) and kb[f, :cb[f]].tobytes() == ko.tobytes() and np.array_equal(db[f, :cb[f]], do)
+    ko, do = os_(frames[1])
+    assert cs[1] == len(ko) and ks[1, :cs[1]].tobytes() == ko.tobytes() and np.array_equal(ds[1, :cs[1]], do)
+    k1, d1 = big(frames[3])                                       # and the one-frame (graph) path of the older handle
+    ko, do = ob(frames[3])
+    assert k1.tobytes() == ko.tobytes() and np.array_equal(d1, do)
+
+
+def test_two_extractors_from_two_host_threads():
+    """Stereo drives two ORBextractor instances from two std::threads (S/Frame.cc:93-96); handles are independent, the
+    error string is per thread.  Two host threads, each with its own handle, many calls at once."""
+    frames = [np.stack([synthetic_frame(30 + 4 * t + i) for i in range(4)]) for t in range(2)]
+    exs = [ORBextractor(*PARAMS, max_batch=4) for _ in range(2)]
+    results = [None, None]
+
+    def worker(t):
+        out = []
+        for rep in range(8):
+            out.append(exs[t].extract_batch(frames[t]) if rep % 2 == 0 else (exs[t](frames[t][rep % 4]),))
+        results[t] = out
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    orc = O.OracleExtractor(*PARAMS)
+    for t in range(2):
+        want = [orc(frames[t][i]) for i in range(4)]
+        for rep, r in enumerate(results[t]):
+            if rep % 2 == 0:
+                kps, desc, counts = r
+                for i in range(4):
+                    n = counts[i]
+                    assert n == len(want[i][0]) and kps[i, :n].tobytes() == want[i][0].tobytes() and np.array_equal(desc[i, :n], want[i][1])
+            else:
+                k, d = r[0]
+                assert k.tobytes() == want[rep % 4][0].tobytes() and np.array_equal(d, want[rep % 4][1])
+
+
+def test_candidate_overflow_is_reported_not_corrupted():
+    """Device-side error path: with the candidate capacity clamped (test hook), a textured frame overflows it; the call
+    reports ORBB200_ECUDA with the status bits in orbb200_last_error(), and the handle works again once restored."""
+    from weiner_slamit_v2_b200 import OrbB200Error
+    from weiner_slamit_v2_b200 import _lib
+    img = synthetic_frame(2)
+    ex = ORBextractor(*PARAMS, max_batch=1)
+    good = ex(img)
+    assert ex._L.orbb200_extractor_debug_set_capacity(ex._h, 40) == 0
+    with pytest.raises(OrbB200Error) as info:
+        ex(img)
+    assert "candidate overflow" in str(info.value) and "0x2" in str(info.value)
+    assert b"candidate overflow" in _lib.load().orbb200_last_error()
+    assert ex._L.orbb200_extractor_debug_set_capacity(ex._h, 0) == 0
+    again = ex(img)
+    assert again[0].tobytes() == good[0].tobytes() and np.array_equal(again[1], good[1])
+
+
+def test_handles_on_two_devices_interleaved():
+    """One host thread alternating between handles on device 0 and device 1 (every entry point sets its device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from weiner_slamit_v2_b200.matcher import ORBmatcher
+    from weiner_slamit_v2_b200.pipeline import REFERENCE_DIST, REFERENCE_K
+    img = synthetic_frame(5)
+    e0, e1 = ORBextractor(*PARAMS, device=0), ORBextractor(*PARAMS, device=1)
+    m0, m1 = ORBmatcher(device=0), ORBmatcher(device=1)
+    ko, do = O.OracleExtractor(*PARAMS)(img)
+    pts = np.stack([ko["x"], ko["y"]], 1)
+    want = O.undistort_points(pts, REFERENCE_K, REFERENCE_DIST)
+    for _ in range(3):
+        for e, m in ((e0, m0), (e1, m1)):
+            k, d = e(img)
+            assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
+            assert np.array_equal(m.undistort_points(pts, REFERENCE_K, REFERENCE_DIST), want)
+            assert np.array_equal(m.image_bounds(640, 480, REFERENCE_K, REFERENCE_DIST), O.image_bounds(640, 480, REFERENCE_K, REFERENCE_DIST))

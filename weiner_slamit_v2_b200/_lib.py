@@ -97,6 +97,9 @@ SIGNATURES = {
     "orbb200_matcher_stream": (vp, [vp]),
     "orbb200_matcher_sync": (C.c_int, [vp]),
     "orbb200_matcher_last_launches": (C.c_int, [vp]),
+    "orbb200_matcher_device": (C.c_int, [vp]),
+    "orbb200_extractor_device": (C.c_int, [vp]),
+    "orbb200_extractor_debug_set_capacity": (C.c_int, [vp, C.c_int]),
     "orbb200_descriptor_distance": (C.c_int, [vp, vp, vp, C.c_int, vp]),
     "orbb200_search_for_initialization": (C.c_int, [vp, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), vp,
                                                     C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int]),

@@ -1142,6 +1142,8 @@ struct orbb200_extractor {
     int totalCells, totalBlurTiles, maxKp, numSMs;
     size_t fastSmem, qtSmem;
     int lastLaunches, lastBatch;
+    int realCandCap[MAXL];     // per-level candidate capacity as computed at create (orbb200_extractor_debug_set_capacity clamps P.lv[l].candCap)
+    int chunkOverride;         // ORBB200_CHUNKS read once at create (0 = choose by batch size): tuning knob of the blocking host call
     const uint8_t* lastIn; long long lastInFrameStride; int lastInPitch;
     orbb200_keypoint* dOutKp; uint8_t* dOutDesc; int* dOutCount;
     void* pinned; size_t pinnedBytes;
@@ -1225,6 +1227,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     h->width = width; h->height = height; h->maxBatch = max_batch; h->device = device; h->blurTaps = blur_taps ? 1 : 0;
     h->pinned = nullptr; h->pinnedBytes = 0; h->lastLaunches = 0; h->lastBatch = 0; h->lastIn = nullptr;
     h->profiling = false;
+    h->chunkOverride = 0;
+    if (const char* e = getenv("ORBB200_CHUNKS")) h->chunkOverride = std::max(0, std::min(8, atoi(e)));
     for (int i = 0; i < 6; i++) h->ev[i] = nullptr;
     h->copyIn = h->copyOut = nullptr;
     for (int i = 0; i < 8; i++) h->evIn[i] = h->evDone[i] = nullptr;
@@ -1277,8 +1281,18 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
             delete h; return ORBB200_EGEOMETRY;
         }
         g.hX = (float)(g.maxBX - BORDER) / g.nIni;                                  // :558
-        // NMS keeps at most one corner per 2x2 block of the detection area
-        g.candCap = ((g.maxBX - BORDER) / 2 + 2) * ((g.maxBY - BORDER) / 2 + 2);
+        // 3x3 NMS with a strict ">" keeps at most one corner per 2x2 block of a cell's detection area, so the sum over
+        // the cells of ceil(dw / 2) * ceil(dh / 2) bounds the level's candidates (STATUS_CAND_OVERFLOW cannot be reached
+        // unless the capacity is shrunk on purpose, orbb200_extractor_debug_set_capacity)
+        g.candCap = 0;
+        for (int ci = 0; ci < g.nRows; ci++)
+            for (int cj = 0; cj < g.nCols; cj++) {
+                const int iniY = BORDER + ci * g.hCell, iniX = BORDER + cj * g.wCell;
+                if (iniY >= g.maxBY - 3 || iniX >= g.maxBX - 6) continue;
+                const int dw = std::min(iniX + g.wCell + 6, g.maxBX) - iniX - 6, dh = std::min(iniY + g.hCell + 6, g.maxBY) - iniY - 6;
+                if (dw > 0 && dh > 0) g.candCap += ((dw + 1) / 2) * ((dh + 1) / 2);
+            }
+        g.candCap = std::max(g.candCap, 64);
         g.candOff = candOff; candOff += (int)align_up(g.candCap, 64);
         g.kpCap = std::max(g.N + 3, 4 * g.nIni);
         g.kpOff = kpOff; kpOff += g.kpCap;
@@ -1301,6 +1315,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         g.blurTilesX = (g.w + 127) / 128;
         g.blurTileStart = tiles; tiles += g.blurTilesX * ((g.h + BL_ROWS - 1) / BL_ROWS);
     }
+    for (int l = 0; l < nlevels; l++) h->realCandCap[l] = P.lv[l].candCap;
     h->totalCells = cells; h->totalBlurTiles = tiles; h->maxKp = kpOff;
     P.totalBlurTiles = tiles;
     P.pyrFrameBytes = std::max<long long>(pyrOff, 256); P.blurFrameBytes = blurOff;
@@ -1355,12 +1370,9 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         e = cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = P.fastLarge
-        ? cudaFuncSetAttribute(k_fast<38, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem)
-        : cudaFuncSetAttribute(k_fast<26, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qtSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_blur<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_WARPS * BL_WARP_BYTES);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
+    if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)k_quadtree, device, h->qtSmem);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(P.blurVariant ? (const void*)k_blur<true> : (const void*)k_blur<false>, device, BL_WARPS * BL_WARP_BYTES);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
         set_error("extractor_create: %s", cudaGetErrorString(e));
@@ -1415,6 +1427,16 @@ extern "C" int orbb200_extractor_level_size(const orbb200_extractor* h, int leve
 }
 extern "C" void* orbb200_extractor_stream(orbb200_extractor* h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int orbb200_extractor_last_launches(const orbb200_extractor* h) { return h ? h->lastLaunches : 0; }
+extern "C" int orbb200_extractor_device(const orbb200_extractor* h) { return h ? h->device : ORBB200_EINVAL; }
+extern "C" int orbb200_extractor_debug_set_capacity(orbb200_extractor* h, int candidates_per_level)
+{
+    if (!h) { set_error("null handle"); return ORBB200_EINVAL; }
+    for (int l = 0; l < h->nlevels; l++)
+        h->P.lv[l].candCap = candidates_per_level > 0 ? std::min(h->realCandCap[l], candidates_per_level) : h->realCandCap[l];
+    for (std::map<int, cudaGraphExec_t>::iterator it = h->graphs.begin(); it != h->graphs.end(); ++it) cudaGraphExecDestroy(it->second);
+    h->graphs.clear();          // captured launches carry the old geometry
+    return ORBB200_OK;
+}
 
 extern "C" int orbb200_extractor_set_profiling(orbb200_extractor* h, int on)
 {
@@ -1632,10 +1654,11 @@ static int extract_host_queue(orbb200_extractor* h, const uint8_t* images, int b
     // Chunked pipeline: while chunk c is in the kernels, chunk c+1 is on its way up and chunk c-1 on its way
     // down (three streams, events between them).  Small batches go through in one piece.
     int nchunk = chunks > 0 ? chunks : (batch >= 96 ? 3 : (batch >= 32 ? 2 : 1));   // measured on B200 + PCIe gen5: 2-3 chunks are best at batch 256
-    if (const char* e = chunks > 0 ? nullptr : getenv("ORBB200_CHUNKS")) nchunk = std::max(1, std::min(8, std::min(batch, atoi(e))));   // tuning knob
+    if (chunks <= 0 && h->chunkOverride > 0) nchunk = std::min(batch, h->chunkOverride);
     const int cs = (batch + nchunk - 1) / nchunk;
     const int mk = h->maxKp;
     const size_t inFrameBytes = h->inPitch * (size_t)h->height;
+    int launches = 0;
     for (int c = 0; c < nchunk; c++) {
         const int f0 = c * cs, n = std::min(cs, batch - f0);
         if (n <= 0) break;
@@ -1655,6 +1678,7 @@ static int extract_host_queue(orbb200_extractor* h, const uint8_t* images, int b
         int rc = enqueue(h, dIn, n, h->inPitch, inFrameBytes, h->dOutKp + (size_t)f0 * mk, h->dOutDesc + (size_t)f0 * mk * 32,
                          h->dOutCount + f0, mk, f0);
         if (rc != ORBB200_OK) return rc;
+        launches += h->lastLaunches;
         ORB_CUDA(cudaEventRecord(h->evDone[c], h->stream));
         ORB_CUDA(cudaStreamWaitEvent(h->copyOut, h->evDone[c], 0));
         ORB_CUDA(cudaMemcpyAsync(counts + f0, h->dOutCount + f0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->copyOut));
@@ -1672,7 +1696,7 @@ static int extract_host_queue(orbb200_extractor* h, const uint8_t* images, int b
         }
     }
     h->lastBatch = batch; h->lastIn = h->dIn; h->lastInPitch = (int)h->inPitch; h->lastInFrameStride = (long long)inFrameBytes;
-    h->lastLaunches *= nchunk;
+    h->lastLaunches = launches;
     h->pending = true;
     return ORBB200_OK;
 }

@@ -81,6 +81,7 @@ extern "C" int orbb200_frames_from_keypoints(orbb200_matcher* m, const orbb200_k
         set_error("orbb200_frames_from_keypoints: bad argument");
         return ORBB200_EINVAL;
     }
+    ORB_CUDA(cudaSetDevice(orbb200_matcher_device(m)));
     cudaStream_t st = (cudaStream_t)orbb200_matcher_stream(m);
     k_frame_prepare<<<dim3((cap + 255) / 256, items), 256, 0, st>>>(d_keypoints, d_counts, cap, cam_model(K, dist),
                                                                     dist[0] != 0.0f ? 1 : 0, d_x, d_y, d_octave, d_angle);
@@ -92,6 +93,7 @@ extern "C" int orbb200_undistort_points(orbb200_matcher* m, const float* xy_in, 
 {
     if (!m || !xy_in || !xy_out || !K || !dist || n < 0) { set_error("orbb200_undistort_points: bad argument"); return ORBB200_EINVAL; }
     if (n == 0) return ORBB200_OK;
+    ORB_CUDA(cudaSetDevice(orbb200_matcher_device(m)));
     cudaStream_t st = (cudaStream_t)orbb200_matcher_stream(m);
     float *din = nullptr, *dout = nullptr;
     ORB_CUDA(cudaMallocAsync((void**)&din, sizeof(float) * 2 * n, st));
@@ -127,6 +129,9 @@ extern "C" int orbb200_image_bounds(orbb200_matcher* m, int cols, int rows, cons
 extern "C" int orbb200_matcher_wait_extractor(orbb200_matcher* m, orbb200_extractor* ex)
 {
     if (!m || !ex) { set_error("orbb200_matcher_wait_extractor: null handle"); return ORBB200_EINVAL; }
+    const int exDevice = orbb200_extractor_device(ex);
+    if (exDevice != orbb200_matcher_device(m)) { set_error("orbb200_matcher_wait_extractor: extractor on device %d, matcher on device %d", exDevice, orbb200_matcher_device(m)); return ORBB200_EINVAL; }
+    ORB_CUDA(cudaSetDevice(orbb200_matcher_device(m)));
     cudaEvent_t ev;
     ORB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     ORB_CUDA(cudaEventRecord(ev, (cudaStream_t)orbb200_extractor_stream(ex)));

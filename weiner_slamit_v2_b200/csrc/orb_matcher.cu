@@ -538,7 +538,9 @@ __global__ void __launch_bounds__(128) k_proj_topk(const ProjParams P)
         const int lvl = P.mpLevel[mo + i];
         float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
         if (P.th != 1.0f) r = __fmul_rn(r, P.th);
-        const float rs = __fmul_rn(r, P.scaleFactors[lvl]);
+        // MapPoint::PredictScale (S/MapPoint.cc:391-400) is unclamped, so the caller's level may lie outside the table:
+        // the radius uses the nearest valid entry (the reference reads out of bounds there), minLevel / maxLevel keep the raw value
+        const float rs = __fmul_rn(r, P.scaleFactors[min(max(lvl, 0), P.nlevels - 1)]);
         const float qx = P.mpX[mo + i], qy = P.mpY[mo + i], qxr = P.mpXR[mo + i];
         int c0, c1, r0, r1;
         if (cell_range(P.g, qx, qy, rs, c0, c1, r0, r1)) {
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
             const int lvl = P.mpLevel[mo + i];
             float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
             if (bFactor) r = __fmul_rn(r, P.th);
-            const float rs = __fmul_rn(r, P.scaleFactors[lvl]);
+            const float rs = __fmul_rn(r, P.scaleFactors[min(max(lvl, 0), P.nlevels - 1)]);
             const float qx = P.mpX[mo + i], qy = P.mpY[mo + i];
             int c0, c1, r0, r1;
             cell_range(P.g, qx, qy, rs, c0, c1, r0, r1);
@@ -784,6 +786,7 @@ extern "C" void orbb200_matcher_destroy(orbb200_matcher* m)
 }
 extern "C" void* orbb200_matcher_stream(orbb200_matcher* m) { return m ? (void*)m->stream : nullptr; }
 extern "C" int orbb200_matcher_last_launches(const orbb200_matcher* m) { return m ? m->lastLaunches : 0; }
+extern "C" int orbb200_matcher_device(const orbb200_matcher* m) { return m ? m->device : ORBB200_EINVAL; }
 extern "C" int orbb200_matcher_sync(orbb200_matcher* m)
 {
     if (!m) { set_error("null handle"); return ORBB200_EINVAL; }
@@ -858,7 +861,7 @@ extern "C" int orbb200_search_for_initialization(orbb200_matcher* m, int items, 
     {
         const size_t sm = 4 * 3 * (size_t)((f2->stride + 15) & ~15);
         if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 16 * 1024); return ORBB200_EINVAL; }
-        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        ORB_CUDA(ensure_dynamic_smem((const void*)k_search_init, m->device, sm));
         k_search_init<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_search_init");
@@ -921,7 +924,7 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
     {
         const size_t sm = 8 * (size_t)((f->stride + 15) & ~15);
         if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
-        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        ORB_CUDA(ensure_dynamic_smem((const void*)k_search_proj, m->device, sm));
         k_search_proj<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_search_proj");

@@ -670,7 +670,7 @@ extern "C" int orbb200_bow_transform(orbb200_matcher* m, const orbb200_vocabular
     int P = 32;
     while (P < stride) P <<= 1;
     const size_t sm = (size_t)P * 12 + 257 * 4 + 16;
-    if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_bow_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    ORB_CUDA(ensure_dynamic_smem((const void*)k_bow_assemble, m->device, sm));
     k_bow_assemble<<<items, 256, sm, st>>>(voc->V, dN, stride, P, leafOf, nodeOf, dBowN, dBowWord, dBowValue, dFvN, dFvNode, dFvStart, dFvFeat);
     ORB_CHECK_LAUNCH("k_bow_assemble");
     m->lastLaunches = 2;

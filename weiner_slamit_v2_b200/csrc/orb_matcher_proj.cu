@@ -531,7 +531,7 @@ extern "C" int orbb200_search_by_projection_last_frame(orbb200_matcher* m, int i
     {
         const size_t sm = 8 * (size_t)((cur->stride + 15) & ~15);
         if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
-        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        ORB_CUDA(ensure_dynamic_smem((const void*)k_search_last, m->device, sm));
         k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_search_last");
@@ -597,7 +597,7 @@ extern "C" int orbb200_search_by_projection_keyframe(orbb200_matcher* m, int ite
     {
         const size_t sm = 8 * (size_t)((cur->stride + 15) & ~15);
         if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
-        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        ORB_CUDA(ensure_dynamic_smem((const void*)k_search_last, m->device, sm));
         k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_search_last");
@@ -719,7 +719,7 @@ extern "C" int orbb200_search_by_projection_sim3(orbb200_matcher* m, int items, 
     {
         const size_t sm = 8 * (size_t)((kf->stride + 15) & ~15);
         if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
-        if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        ORB_CUDA(ensure_dynamic_smem((const void*)k_search_last, m->device, sm));
         k_search_last<<<(items + 3) / 4, 128, sm, st>>>(P);
     }
     ORB_CHECK_LAUNCH("k_search_last");

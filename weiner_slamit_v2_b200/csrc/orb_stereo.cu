@@ -244,7 +244,9 @@ extern "C" int orbb200_compute_stereo_matches(orbb200_matcher* m, int items, con
     if (nlevels < 1 || nlevels > STEREO_MAXL || lpyr->nlevels < nlevels || rpyr->nlevels < nlevels) { set_error("bad number of pyramid levels"); return ORBB200_EINVAL; }
     if (right->stride > 65535) { set_error("more than 65535 right keypoints per frame"); return ORBB200_EINVAL; }
     if (lpyr->height[0] > 8191) { set_error("images taller than 8191 rows"); return ORBB200_EINVAL; }
-    if (!(mb > 0.0f)) { set_error("baseline must be positive"); return ORBB200_EINVAL; }
+    // (mb <= 0 is not an error: the reference's stereo constructor calls ComputeStereoMatches BEFORE it assigns mb,
+    // S/Frame.cc:104 against :130, so the first frame runs with whatever the storage held; mb = 0 gives maxD = +inf in
+    // IEEE arithmetic, here as there)
     const bool devViews = (on_device & ORBB200_DEVICE_VIEWS) != 0, devPyr = (on_device & ORBB200_DEVICE_PYRAMIDS) != 0;
     ORB_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = m->stream;
@@ -275,7 +277,7 @@ extern "C" int orbb200_compute_stereo_matches(orbb200_matcher* m, int items, con
     if ((rc = pyr_to_dev(s, lpyr, items, nlevels, devPyr, &P.lp, P.w, P.h)) || (rc = pyr_to_dev(s, rpyr, items, nlevels, devPyr, &P.rp, P.w, P.h))) return rc;
     const size_t sm = 8 * (size_t)right->stride;
     if (sm > 200 * 1024) { set_error("more than %d right keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
-    if (sm > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    ORB_CUDA(ensure_dynamic_smem((const void*)k_stereo_match, m->device, sm));
     const int chunks = std::max(1, std::min((left->stride + 63) / 64, (148 * 8 + items - 1) / items));
     k_stereo_match<<<dim3(chunks, items), 256, sm, st>>>(P);
     ORB_CHECK_LAUNCH("k_stereo_match");
