@@ -28,7 +28,13 @@ WIDTH, HEIGHT, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 2
 BATCH = 256                       # frames per GPU per step (configs[1])
 WORKLOAD = "batched ORB extraction, 256 synthetic 640x480 frames per GPU, 1000 kp/8 levels, FAST 20/7 (configs[1])"
 METRIC = "ORB frames/s (640x480, 1000 kp, 8 lvl)"
-DISTINCT = 32                     # distinct synthetic frames generated per rank (tiled to BATCH)
+DISTINCT = BATCH                  # distinct synthetic frames generated per rank (every frame of a step is its own image)
+HD = dict(width=1280, height=720, nfeatures=2000, total=1024, distinct=64,
+          metric="ORB frames/s (1280x720, 2000 kp, 8 lvl)",
+          alg_bytes={"pyramid": 2781331 + 1931488, "fast": 2853088 + 160000, "quadtree": 160000 + 32000,
+                     "blur": 5706176, "describe": 1498000 + 1024000 + 120000})
+MATCH_PAIRS, MATCH_N = 4096, 1000              # configs[2]
+PROJ_FRAMES, PROJ_KP, PROJ_MP = 512, 2000, 10000   # configs[4]
 
 # Algorithmic HBM bytes per frame and per kernel (DESIGN.md "Roofline model"):
 # every stage reads its input once and writes its output once.
@@ -95,12 +101,22 @@ class ClockSampler:
         return out
 
 
-def _frames(rank, count):
+def _frames(rank, count, width=None, height=None, distinct=None):
     import numpy as np
     from weiner_slamit_v2_b200.frames import synthetic_frame
-    base = [synthetic_frame(rank * 100000 + i, WIDTH, HEIGHT) for i in range(min(DISTINCT, count))]
+    width, height = width or WIDTH, height or HEIGHT
+    base = [synthetic_frame(rank * 100000 + i, width, height) for i in range(min(distinct or DISTINCT, count))]
     reps = (count + len(base) - 1) // len(base)
     return np.stack((base * reps)[:count])
+
+
+def _config(world):
+    """The workload description both arms print, key for key (the driver compares the two dicts)."""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": BATCH, "distinct_frames_per_gpu": min(DISTINCT, BATCH),
+            "l2": "256 MiB flush buffer written before every timed step (GPU arm); inputs of a step exceed the CPU caches (reference arm)",
+            "parallelism": "frames sharded by batch, no data-path collective",
+            "also_in_this_line": "hd = configs[3] (1024 frames 1280x720 / 2000 kp split over the GPUs), matching = configs[2] "
+                                 "(4096 pairs) and configs[4] (512 frames) split over the GPUs"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -121,24 +137,82 @@ def _load_ref():
     return None, "port"
 
 
-def cpu_extract_fps(frames, threads):
+def cpu_extract_fps(frames, threads, nfeatures=None):
     """frames/s of the CPU implementation over `frames` with `threads` host threads."""
     import numpy as np
+    nfeatures = nfeatures or NFEAT
     ref_lib, kind = _load_ref()
     t0 = time.perf_counter()
     if ref_lib is not None:
-        counts = ref_lib.extract_batch_mt(frames, threads, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+        counts = ref_lib.extract_batch_mt(frames, threads, nfeatures, SCALE, NLEVELS, INI_TH, MIN_TH)
     else:  # oracle port, single instance per thread via a thread pool (ctypes releases the GIL)
         import oracle_lib
         from concurrent.futures import ThreadPoolExecutor
         def work(chunk):
-            o = oracle_lib.OracleExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+            o = oracle_lib.OracleExtractor(nfeatures, SCALE, NLEVELS, INI_TH, MIN_TH)
             return [len(o(f)[0]) for f in chunk]
         chunks = [frames[i::threads] for i in range(threads)]
         with ThreadPoolExecutor(threads) as ex:
             counts = np.concatenate([np.asarray(c) for c in ex.map(work, chunks)])
     dt = time.perf_counter() - t0
     return len(frames) / dt, kind, int(np.sum(counts))
+
+
+def cpu_single_thread(frames):
+    """BASELINE configs[0] / SURVEY 8(d) config 1: the CPU implementation on ONE host thread, ms per 640x480 frame."""
+    cpu_extract_fps(frames[:2], 1)
+    fps, kind, _ = cpu_extract_fps(frames, 1)
+    return {"single_thread_ms_per_frame": 1e3 / fps, "single_thread_frames_per_s": fps, "single_thread_sample": "%d frames" % len(frames)}
+
+
+def cpu_matching_baselines(threads):
+    """The reference's own ORBmatcher.cc (oracle/_ref/libref_matcher.so; the oracle port if it was not built) on the host
+    threads for configs[2] and configs[4], on a bounded sample of the same synthetic workload: one call per frame pair /
+    frame as Tracking issues them, `threads` calls in flight (ORBmatcher is stateless, S/System.cc:156,160).  The time of a
+    call includes the harness building the ORB_SLAM2::Frame / MapPoint objects the reference's function takes."""
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import ref_lib as R
+    from weiner_slamit_v2_b200.workloads import SCALE_FACTORS_8, init_pair, projection_frame
+    use_ref = R.matcher_available()
+    kind = "reference" if use_ref else "port"
+    if use_ref:
+        R.mlib()
+    out = {}
+
+    def timed(fn, work):
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(fn, work[:threads]))                      # warm-up: first touch of every thread
+            t0 = time.perf_counter()
+            res = list(ex.map(fn, work))
+            return time.perf_counter() - t0, res
+
+    n = MATCH_N
+    pairs = [init_pair(900000 + i, n=n, brute_force=True) for i in range(max(4 * threads, 32))]
+    f = R.ref_search_for_initialization if use_ref else O.search_for_initialization
+    dt, res = timed(lambda p: f(p[0], p[1], p[2], p[3], p[4], (0, 0, 640, 480), 0.9, True, 1000)[0], pairs)
+    out["search_for_initialization"] = {
+        "value": len(pairs) * n * n / dt, "unit": "distance evaluations/s", "pairs_per_s": len(pairs) / dt,
+        "accepted_matches_per_s": float(sum(res)) / dt, "cores": threads, "kind": kind,
+        "sample": "%d of the %d frame pairs (1000 x 1000 descriptors, ratio 0.9), %d host threads, one call per pair" % (len(pairs), MATCH_PAIRS, threads)}
+    frames = [projection_frame(900000 + i, PROJ_KP, PROJ_MP) for i in range(max(2 * threads, 16))]
+    g = R.ref_search_by_projection if use_ref else O.search_by_projection
+    dt, res = timed(lambda w: g(w[2], w[0], w[1], SCALE_FACTORS_8, (0, 0, 1280, 720), 0.8, 1.0)[0], frames)
+    out["search_by_projection"] = {
+        "value": len(frames) * PROJ_MP / dt, "unit": "map points/s", "frames_per_s": len(frames) / dt,
+        "accepted_matches_per_s": float(sum(res)) / dt, "cores": threads, "kind": kind,
+        "sample": "%d of the %d frames (10000 map points vs 2000 keypoints, th=1, ratio 0.8), %d host threads, one call per frame" % (len(frames), PROJ_FRAMES, threads)}
+    return out
+
+
+def cpu_hd_baseline(threads):
+    import numpy as np
+    frames = _frames(0, max(2 * threads, 16), HD["width"], HD["height"], HD["distinct"])
+    cpu_extract_fps(frames[:threads], threads, HD["nfeatures"])
+    fps, kind, _ = cpu_extract_fps(frames, threads, HD["nfeatures"])
+    return {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+            "sample": "%d of the %d frames (1280x720, 2000 kp), %d host threads, one ORBextractor each" % (len(frames), HD["total"], threads)}
 
 
 def parity_report(frames, kps, desc, counts):
@@ -180,7 +254,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = _cpu_threads()
-    sample = BATCH                                   # one full step: 256 frames (~20 s of CPU work)
+    sample = BATCH                                   # one full step: 256 frames
     frames = _frames(0, sample)
     for _ in range(args.warmup):
         cpu_extract_fps(frames[: max(threads, 8)], threads)
@@ -189,16 +263,23 @@ def run_reference(args):
         fps, kind, _ = cpu_extract_fps(frames, threads)
         total_t += sample / fps
     value = sample * args.steps / total_t
+    base = {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
+            "sample": "%d of the %d frames of one step, %d host threads, one ORBextractor each" % (sample, BATCH, threads),
+            "primitives": "the reference's ORBextractor.cc over the scalar mini-cv stand-in for OpenCV (about 3x slower than OpenCV's SIMD build)"}
+    base.update(cpu_single_thread(frames[:8]))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_t / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": "%d of the %d frames of one step, %d host threads, one ORBextractor each" % (sample, BATCH, threads)},
+        "config": _config(args.gpus),
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload == "vga":
+        if not args.no_matching:
+            line["matching"] = cpu_matching_baselines(threads)
+        line["hd"] = dict(cpu_hd_baseline(threads), metric=HD["metric"])
     _emit(line)
 
 
@@ -344,6 +425,35 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks (device-timed)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)    # the path's only "collective": a count gather
     dev_ms_max, e2e_ms_max, e2e_sync_ms_max = t.tolist()
+    nkp_all = int(tot.item())
+
+    # free the VGA handles before the other workloads of the line allocate theirs
+    parity_in = (outs[0][0].numpy()[:8].copy(), outs[0][1].numpy()[:8].copy(), outs[0][2].numpy()[:8].copy())
+    ex.close()
+    del d_frames, out_k, out_d, outs, pinned
+    torch.cuda.empty_cache()
+
+    def reduce_max(x):
+        if world == 1:
+            return float(x)
+        v = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return float(x)
+        v = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return float(v.item())
+
+    hd = matching = None
+    if args.workload == "vga":
+        # every rank takes part: the shards of configs[3], configs[2] and configs[4] are timed like the headline
+        # (barrier, CUDA events on the launch stream, MAX over ranks)
+        hd = run_hd(local, rank, world, max(3, min(args.steps, 5)), barrier, reduce_max, reduce_sum, flush)
+        if not args.no_matching:
+            matching = run_matching(local, rank, world, max(3, min(args.steps, 5)), barrier, reduce_max, reduce_sum)
 
     if rank == 0:
         frames_total = BATCH * world * args.steps
@@ -359,11 +469,10 @@ def run_ours(args):
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "hd" else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "frames_per_step_per_gpu": BATCH, "l2": "256 MiB flush buffer written before every timed step",
-                       "parallelism": "frames sharded by batch, no data-path collective"},
+            "config": _config(world),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * WIDTH * HEIGHT,
-                    "d2h_bytes_per_step": BATCH * (4 + cap * 60), "keypoints_per_step": nkp / world,
+                    "d2h_bytes_per_step": BATCH * (4 + cap * 60), "keypoints_per_step_per_gpu": nkp_all / world,
+                    "keypoints_per_step": nkp_all,
                     "api": "StreamingExtractor (orbb200_extract_host_async, %d handles in turn)" % depth,
                     "blocking_call_value": frames_total / (e2e_sync_ms_max * 1e-3),
                     "single_frame_latency_ms": latency_ms},
@@ -373,11 +482,15 @@ def run_ours(args):
                          "frac": ach / peak, "traffic": _traffic(STAGES[dom]), "peak_source": which,
                          "issue": _issue_profile({"pyramid": "k_resize", "fast": "k_fast", "quadtree": "k_quadtree", "blur": "k_blur",
                                                   "describe": "k_describe"}[STAGES[dom]]),
-                         "all": {s: ALG_BYTES[s] * BATCH / (per_stage[i] * 1e-3) / 1e9 / peak for i, s in enumerate(STAGES)}},
+                         "all": {s: ALG_BYTES[s] * BATCH / (per_stage[i] * 1e-3) / 1e9 / peak for i, s in enumerate(STAGES)},
+                         "whole_step": sum(ALG_BYTES.values()) * BATCH / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak},
             "clocks": clocks,
         }
+        if hd is not None:
+            line["hd"] = hd
+        if matching is not None:
+            line["matching"] = matching
         if world == 1 and not args.no_matching:
-            line["matching"] = run_matching(local, max(2, min(args.steps, 5)))
             line["pipeline"] = run_pipeline(local, max(2, min(args.steps, 5)))
             line["stereo"] = run_stereo(local, max(2, min(args.steps, 5)))
         if world == 1 and not args.no_cpu_baseline:
@@ -385,11 +498,83 @@ def run_ours(args):
             sample = BATCH
             fps, kind, _ = cpu_extract_fps(frames[:sample], threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                                    "sample": "%d of the %d frames of one step, %d host threads" % (sample, BATCH, threads)}
-            line["parity"] = parity_report(frames[:8], outs[0][0].numpy(), outs[0][1].numpy(), outs[0][2].numpy())
+                                    "sample": "%d of the %d frames of one step, %d host threads" % (sample, BATCH, threads),
+                                    "primitives": "the reference's ORBextractor.cc over the scalar mini-cv stand-in for OpenCV (about 3x slower "
+                                                  "than OpenCV's SIMD build)"}
+            line["cpu_baseline"].update(cpu_single_thread(frames[:8]))
+            line["parity"] = parity_report(frames[:8], *parity_in)
+            if hd is not None:
+                line["hd"]["cpu_baseline"] = cpu_hd_baseline(threads)
+            if matching is not None:
+                cb = cpu_matching_baselines(threads)
+                for k in cb:
+                    matching[k]["cpu_baseline"] = cb[k]
         _emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def run_hd(local, rank, world, steps, barrier, reduce_max, reduce_sum, flush):
+    """configs[3]: 1024 frames 1280x720, nFeatures 2000, split contiguously over the GPUs (strong scaling).  Device-resident
+    throughput (CUDA events on the launch stream, L2 flushed before every step, MAX over ranks) and the same through the
+    blocking host-buffer call (uploads and downloads inside the timed region)."""
+    import numpy as np
+    import torch
+    from weiner_slamit_v2_b200 import ORBextractor
+    from weiner_slamit_v2_b200._lib import check
+    w, h, n = HD["width"], HD["height"], HD["total"] // world
+    ex = ORBextractor(HD["nfeatures"], SCALE, NLEVELS, INI_TH, MIN_TH, width=w, height=h, max_batch=n, device=local)
+    ex.set_profiling(True)
+    pinned = torch.empty((n, h, w), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = _frames(1000 + rank, n, w, h, HD["distinct"])
+    d_frames = pinned.cuda()
+    stream = torch.cuda.ExternalStream(ex.stream, device=local)
+    for _ in range(3):
+        ex.extract_device(d_frames, n, w, w * h)
+    ex.sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stage_ms = np.zeros(5)
+    barrier()
+    with torch.cuda.stream(stream):
+        for k in range(steps):
+            flush.fill_(k & 0xff)
+            ev[k][0].record()
+            ex.extract_device(d_frames, n, w, w * h)
+            ev[k][1].record()
+            stage_ms += ex.stage_ms()
+    ex.sync()
+    barrier()
+    dev_ms = reduce_max(sum(a.elapsed_time(b) for a, b in ev) / steps)
+    cap = ex.max_keypoints
+    out_k = torch.empty((n, cap, 28), dtype=torch.uint8, pin_memory=True)
+    out_d = torch.empty((n, cap, 32), dtype=torch.uint8, pin_memory=True)
+    out_c = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+    host_in = pinned.numpy()
+
+    def e2e_step():
+        check(ex._L.orbb200_extract_host(ex._h, host_in.ctypes.data, n, w, w * h, out_k.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), cap))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = reduce_max((time.perf_counter() - t0) / steps * 1e3)
+    nkp = reduce_sum(int(out_c.sum()))
+    launches = ex.last_launches
+    ex.close()
+    del d_frames, pinned, out_k, out_d
+    torch.cuda.empty_cache()
+    peak, which = _peaks()
+    per_stage = stage_ms / steps
+    return {"metric": HD["metric"], "workload": "1280x720 frames, nFeatures=2000, 8 levels, batch 1024 sharded over %d B200 (configs[3])" % world,
+            "value": HD["total"] / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "frames_per_gpu": n, "steps": steps,
+            "ms_per_step": dev_ms, "scaling": "strong", "keypoints_per_step": nkp, "gpu_launches_per_step": launches,
+            "kernel_ms_per_step": {s: float(per_stage[i]) for i, s in enumerate(STAGES)},
+            "roofline_all": {s: HD["alg_bytes"][s] * n / (per_stage[i] * 1e-3) / 1e9 / peak for i, s in enumerate(STAGES)},
+            "e2e": {"value": HD["total"] / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": n * w * h,
+                    "d2h_bytes_per_step": n * (4 + cap * 60), "api": "orbb200_extract_host (blocking; copies and kernels overlap chunk by chunk inside the call)"}}
 
 
 def _int_roofline(evals_per_s):
@@ -409,10 +594,21 @@ def _int_roofline(evals_per_s):
                            "lower bound); whole call (grid + top-4 + greedy resolve) in the numerator" % (k["popc_per_clk_per_sm"], k["sms"], k["sm_clock_mhz"])}
 
 
-def run_matching(local, steps):
-    """configs[2] and configs[4]: SearchForInitialization on 4096 brute-force-shaped pairs (1000 x 1000
-    descriptors, ratio 0.9) and SearchByProjection on 512 frames (10k map points vs 2000 keypoints), data
-    resident in HBM, CUDA events on the matcher's stream."""
+def _half_distance_survivors(d1, d2, far=56):
+    """Fraction of the (query, candidate) pairs of two descriptor sets whose distance over the first 128 bits is below `far`
+    (the candidates k_init_topk finishes to 256 bits; the rest is dropped after 3 POPC).  torch on the GPU: plumbing."""
+    import torch
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int16, device=d1.device)
+    x = torch.bitwise_xor(d1[:, None, :16], d2[None, :, :16]).long()
+    return float((lut[x].sum(-1) < far).float().mean().item())
+
+
+def run_matching(local, rank, world, steps, barrier, reduce_max, reduce_sum):
+    """configs[2] and configs[4], split contiguously over the ranks (strong scaling): SearchForInitialization on 4096
+    brute-force-shaped pairs (1000 x 1000 descriptors, ratio 0.9) and SearchByProjection on 512 frames (10k map points vs
+    2000 keypoints); data resident in HBM, CUDA events on the matcher's stream after a barrier, MAX over ranks.  On one GPU
+    also config 3a (reference-semantics windowed search on extracted keypoints), the brute-force shape on extracted
+    descriptors, and the widened rows."""
     import ctypes as C
     import numpy as np
     import torch
@@ -432,10 +628,11 @@ def run_matching(local, steps):
         return np.concatenate([a] * reps)[:items]
 
     def timed(stream, fn, steps):
+        """ms per call, this rank; then MAX over ranks"""
         st = torch.cuda.ExternalStream(stream, device=local)
         for _ in range(2):
             fn()
-        torch.cuda.synchronize()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(st):
             e0.record()
@@ -443,11 +640,12 @@ def run_matching(local, steps):
                 fn()
             e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps
+        return reduce_max(e0.elapsed_time(e1) / steps)
 
     # ---- configs[2]
-    items, n, distinct = 4096, 1000, 32
-    pairs = [init_pair(i, n=n, brute_force=True) for i in range(distinct)]
+    total, n, distinct = MATCH_PAIRS, MATCH_N, 32
+    items = total // world
+    pairs = [init_pair(rank * 1000 + i, n=n, brute_force=True) for i in range(distinct)]
     def fv(idx_k, idx_d):
         t = dict(n=up(np.full(items, n, np.int32)),
                  x=up(tile(np.stack([p[idx_k]["x"] for p in pairs]), items)), y=up(tile(np.stack([p[idx_k]["y"] for p in pairs]), items)),
@@ -468,20 +666,24 @@ def run_matching(local, steps):
         check(L.orbb200_search_for_initialization(h, items, C.byref(v1), C.byref(v2), bounds.ctypes.data, 0.9, 1, 1000,
                                                   prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 1))
     ms = timed(L.orbb200_matcher_stream(h), init_step, steps)
-    acc = int(nm.sum())
+    acc = reduce_sum(int(nm.sum()))
+    surv = _half_distance_survivors(t1["d"][0], t2["d"][0])
     out["search_for_initialization"] = {
-        "workload": "4096 frame pairs, 1000 x 1000 descriptors per pair (all octave 0, window > image), ratio 0.9, checkOri",
-        "ms_per_step": ms, "pairs_per_s": items / ms * 1e3, "distance_evals_per_s": items * n * n / ms * 1e3,
-        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h),
-        "roofline": _int_roofline(items * n * n / ms * 1e3)}
+        "workload": "4096 frame pairs split over %d GPU(s), 1000 x 1000 descriptors per pair (all octave 0, window > image), ratio 0.9, checkOri (configs[2])" % world,
+        "n_gpus": world, "pairs_per_gpu": items, "scaling": "strong",
+        "ms_per_step": ms, "pairs_per_s": total / ms * 1e3, "distance_evals_per_s": total * n * n / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": int(acc), "gpu_launches_per_step": L.orbb200_matcher_last_launches(h),
+        "half_distance_survivor_fraction": surv,
+        "roofline": _int_roofline(total * n * n / ms * 1e3 / world)}
     del t1, t2, prev, prev0, m12
     L.orbb200_matcher_destroy(h)
 
     # ---- configs[4]
-    items, nk, nmp, distinct = 512, 2000, 10000, 16
+    total, nk, nmp, distinct = PROJ_FRAMES, PROJ_KP, PROJ_MP, 16
+    items = total // world
     h = _lib.vp()
     check(L.orbb200_matcher_create(items, nmp, local, C.byref(h)))
-    fr = [projection_frame(i, nk, nmp) for i in range(distinct)]
+    fr = [projection_frame(rank * 1000 + i, nk, nmp) for i in range(distinct)]
     tk = dict(n=up(np.full(items, nk, np.int32)), x=up(tile(np.stack([f[0]["x"] for f in fr]), items)),
               y=up(tile(np.stack([f[0]["y"] for f in fr]), items)), o=up(tile(np.stack([f[0]["octave"] for f in fr]), items)),
               d=up(tile(np.stack([f[1] for f in fr]), items)))
@@ -499,11 +701,19 @@ def run_matching(local, steps):
         check(L.orbb200_search_by_projection(h, items, C.byref(kv), None, C.byref(mv), kpmp.data_ptr(), None, sf.data_ptr(), 8,
                                              b2.ctypes.data, 0.8, 1.0, nm2.data_ptr(), 1))
     ms = timed(L.orbb200_matcher_stream(h), proj_step, steps)
-    acc = int(nm2.sum())
+    acc = reduce_sum(int(nm2.sum()))
+    alg = PROJ_MP * (32 + 24) + PROJ_KP * (32 + 20) + 64 * 48 * 4 + PROJ_KP * 4        # bytes per frame
+    peak, _ = _peaks()
     out["search_by_projection"] = {
-        "workload": "512 frames, 10000 projected map points vs 2000 keypoints per frame, th=1, ratio 0.8",
-        "ms_per_step": ms, "frames_per_s": items / ms * 1e3, "map_points_per_s": items * nmp / ms * 1e3,
-        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+        "workload": "512 frames split over %d GPU(s), 10000 projected map points vs 2000 keypoints per frame, th=1, ratio 0.8 (configs[4])" % world,
+        "n_gpus": world, "frames_per_gpu": items, "scaling": "strong",
+        "ms_per_step": ms, "frames_per_s": total / ms * 1e3, "map_points_per_s": total * nmp / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": int(acc), "gpu_launches_per_step": L.orbb200_matcher_last_launches(h),
+        "algorithmic_GB_per_s_per_gpu": alg * items / (ms * 1e-3) / 1e9, "hbm_frac": alg * items / (ms * 1e-3) / 1e9 / peak}
+    if world > 1:
+        L.orbb200_matcher_destroy(h)
+        return out
+    out.update(run_matching_extracted(local, steps, timed))
     # ---- scope row N2: SearchByProjection(CurrentFrame, LastFrame, th, bMono), the per-frame motion-model tracker
     from weiner_slamit_v2_b200._lib import LastFrameView
     from weiner_slamit_v2_b200.workloads import motion_frame
@@ -611,17 +821,29 @@ def run_matching(local, steps):
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / reps * 1e3, r
     ms, r = host_timed(lambda: mm.search_for_triangulation_batch(tw), 3)
-    out["search_for_triangulation"] = {"workload": "64 key-frame pairs, 2000 x 2000 features in ~100 shared nodes, host buffers (time includes the Python packing)",
-                                       "ms_per_call": ms, "pairs_per_s": 64 / ms * 1e3, "accepted_matches": int(r[0].sum())}
+    mm.search_for_triangulation_batch(tw, device_reps=steps)
+    out["search_for_triangulation"] = {"workload": "64 key-frame pairs, 2000 x 2000 features in ~100 shared nodes",
+                                       "ms_per_step": mm.last_device_ms, "pairs_per_s": 64 / mm.last_device_ms * 1e3,
+                                       "timing": "inputs and outputs resident in HBM, CUDA events on the matcher's stream",
+                                       "host_buffer_call_ms_incl_python_packing": ms, "accepted_matches": int(r[0].sum())}
     ms, r = host_timed(lambda: mm.fuse_search_batch(fw, (0.0, 0.0, 640.0, 480.0), 3.0), 3)
-    out["fuse_search"] = {"workload": "64 key frames x 3000 candidate map points vs 2000 keypoints, th=3, host buffers (time includes the Python packing)",
-                          "ms_per_call": ms, "map_points_per_s": 64 * 3000 / ms * 1e3, "fused": int(sum((b >= 0).sum() for b, _ in r))}
+    mm.fuse_search_batch(fw, (0.0, 0.0, 640.0, 480.0), 3.0, device_reps=steps)
+    out["fuse_search"] = {"workload": "64 key frames x 3000 candidate map points vs 2000 keypoints, th=3",
+                          "ms_per_step": mm.last_device_ms, "map_points_per_s": 64 * 3000 / mm.last_device_ms * 1e3,
+                          "timing": "inputs and outputs resident in HBM, CUDA events on the matcher's stream",
+                          "host_buffer_call_ms_incl_python_packing": ms, "fused": int(sum((b >= 0).sum() for b, _ in r))}
     off = np.zeros(len(obs) + 1, np.int32); off[1:] = np.cumsum([len(o) for o in obs])
     flat = np.ascontiguousarray(np.concatenate(obs)); bestd = np.zeros(len(obs), np.int32)
     ms, r = host_timed(lambda: check(L.orbb200_distinctive_descriptors(mm._h, len(obs), off.ctypes.data, flat.ctypes.data, int(off[-1]),
                                                                        bestd.ctypes.data, None, 0)), 3)
-    out["distinctive_descriptors"] = {"workload": "100000 map points with 2..39 observations each (%d descriptors), host buffers" % int(off[-1]),
-                                      "ms_per_call": ms, "map_points_per_s": 100000 / ms * 1e3}
+    d_off, d_flat, d_best = up(off), up(flat), torch.empty(len(obs), dtype=torch.int32, device=dev)
+    dms = timed(L.orbb200_matcher_stream(mm._h), lambda: check(L.orbb200_distinctive_descriptors(
+        mm._h, len(obs), d_off.data_ptr(), d_flat.data_ptr(), int(off[-1]), d_best.data_ptr(), None, 1)), steps)
+    assert np.array_equal(d_best.cpu().numpy(), bestd), "device-resident call differs from the host-buffer call"
+    out["distinctive_descriptors"] = {"workload": "100000 map points with 2..39 observations each (%d descriptors)" % int(off[-1]),
+                                      "ms_per_step": dms, "map_points_per_s": 100000 / dms * 1e3,
+                                      "timing": "inputs and outputs resident in HBM, CUDA events on the matcher's stream",
+                                      "host_buffer_call_ms": ms}
     # ---- scope row N4: Frame::ComputeBoW (DBoW2 transform), descriptors and outputs resident in HBM
     from weiner_slamit_v2_b200.matcher import Vocabulary
     from weiner_slamit_v2_b200.workloads import synthetic_vocabulary, vocabulary_features
@@ -644,6 +866,70 @@ def run_matching(local, steps):
         "words": int(o_i[0].sum()), "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
     V.close()
     mm.close()
+    L.orbb200_matcher_destroy(h)
+    return out
+
+
+def run_matching_extracted(local, steps, timed):
+    """SearchForInitialization on keypoints and descriptors that come out of the extractor (256 frame pairs: frame i and its
+    copy shifted by (4, 2) px, extracted, undistorted with the reference's camera and gridded on the device, tiled to 4096
+    pairs): (3a) the reference's semantics as Tracking calls it -- octave-0 queries, +-100 px window, greedy steal -- and
+    (3b') the brute-force shape of configs[2] on these REAL descriptors (every octave forced to 0, window > image), where
+    true matches make far more candidates survive the half-distance test than on the unrelated descriptors of configs[2]."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from weiner_slamit_v2_b200 import _lib
+    from weiner_slamit_v2_b200._lib import FrameView, check
+    from weiner_slamit_v2_b200.pipeline import InitializationPipeline
+    L = _lib.load()
+    pairs, items = 256, MATCH_PAIRS
+    f1 = _frames(3, pairs)
+    f2 = np.stack([np.roll(f, (2, 4), (0, 1)) for f in f1])
+    pipe = InitializationPipeline(max_pairs=pairs, device=local)
+    pipe.run(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(), pairs)
+    pipe.sync()
+    cap, rep = pipe.cap, items // pairs
+    side = [{k: v[:pairs].repeat((rep,) + (1,) * (v.dim() - 1)).contiguous() for k, v in sd.items() if k != "kps"} for sd in pipe.side]
+    bounds = pipe.bounds.copy()
+    pipe.close()
+    n1 = side[0]["n"].float().mean().item(); n2 = side[1]["n"].float().mean().item()
+    lvl0 = (side[0]["oct"][:pairs] == 0) & (torch.arange(cap, device=side[0]["oct"].device)[None, :] < side[0]["n"][:pairs, None])
+    q0 = lvl0.sum(1).float().mean().item()
+    h = _lib.vp()
+    check(L.orbb200_matcher_create(items, cap, local, C.byref(h)))
+    prev0 = torch.stack([side[0]["x"], side[0]["y"]], dim=-1).contiguous()
+    prev = prev0.clone()
+    m12 = torch.empty((items, cap), dtype=torch.int32, device=prev.device)
+    nm = torch.empty(items, dtype=torch.int32, device=prev.device)
+    out = {}
+
+    def view(sd, octv):
+        return FrameView(sd["n"].data_ptr(), sd["x"].data_ptr(), sd["y"].data_ptr(), octv.data_ptr(), sd["ang"].data_ptr(), sd["desc"].data_ptr(), cap)
+
+    def run(v1, v2, window):
+        def step():
+            prev.copy_(prev0)
+            check(L.orbb200_search_for_initialization(h, items, C.byref(v1), C.byref(v2), bounds.ctypes.data, 0.9, 1, window,
+                                                      prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 1))
+        ms = timed(L.orbb200_matcher_stream(h), step, steps)
+        return ms, int(nm.sum())
+    ms, acc = run(view(side[0], side[0]["oct"]), view(side[1], side[1]["oct"]), 100)
+    out["search_for_initialization_extracted_3a"] = {
+        "workload": "4096 pairs of extracted frames (~%.0f and ~%.0f keypoints, ~%.0f octave-0 queries per pair), reference semantics: "
+                    "octave 0 only, +-100 px window, ratio 0.9, checkOri (SURVEY 8(d) config 3a), matcher only" % (n1, n2, q0),
+        "ms_per_step": ms, "pairs_per_s": items / ms * 1e3, "queries_per_s": items * q0 / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc, "gpu_launches_per_step": L.orbb200_matcher_last_launches(h)}
+    z = [torch.zeros_like(sd["oct"]) for sd in side]
+    ms, acc = run(view(side[0], z[0]), view(side[1], z[1]), 1000)
+    ev = float((side[0]["n"].double() * side[1]["n"].double()).sum().item())
+    n0, m0 = int(side[0]["n"][0]), int(side[1]["n"][0])
+    out["search_for_initialization_extracted_brute"] = {
+        "workload": "the same 4096 pairs with every octave forced to 0 and window > image: ~%.0f x %.0f REAL descriptors per pair, ratio 0.9" % (n1, n2),
+        "ms_per_step": ms, "pairs_per_s": items / ms * 1e3, "distance_evals_per_s": ev / ms * 1e3,
+        "accepted_matches_per_s": acc / ms * 1e3, "accepted_matches": acc,
+        "half_distance_survivor_fraction": _half_distance_survivors(side[0]["desc"][0, :n0], side[1]["desc"][0, :m0]),
+        "roofline": _int_roofline(ev / ms * 1e3)}
     L.orbb200_matcher_destroy(h)
     return out
 

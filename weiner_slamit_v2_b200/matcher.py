@@ -56,6 +56,47 @@ def _pack(arrs, stride, dtype, tail=()):
     return out
 
 
+def _device_copy(view, arrays, device, keep):
+    """A copy of the ctypes view `view` whose pointer fields address device copies of the host arrays they pointed to
+    (`arrays`: the numpy arrays the view was built from).  torch is plumbing: device memory only.  Used by bench.py to time
+    an entry point with on_device = 1 on exactly the data its host-buffer form was checked on."""
+    import torch
+    by_addr = {a.ctypes.data: a for a in arrays if a is not None}
+    out = type(view)()
+    for name, ctype in view._fields_:
+        v = getattr(view, name)
+        if ctype is _lib.vp and v in by_addr:
+            t = torch.from_numpy(by_addr[v]).to(torch.device("cuda", device))
+            keep.append(t)
+            setattr(out, name, t.data_ptr())
+        else:
+            setattr(out, name, v)
+    return out
+
+
+def _device_array(a, device, keep):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(torch.device("cuda", device))
+    keep.append(t)
+    return t.data_ptr()
+
+
+def _device_time(stream, device, fn, reps):
+    """ms per call of fn (which queues work on `stream`), CUDA events on that stream."""
+    import torch
+    st = torch.cuda.ExternalStream(stream, device=device)
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def _bow_side(sides, valid=None):
     """Pack one side of a SearchByBoW-style call.  sides: list of dicts with desc (n,32), angle (n), node, start, feat
     (a flattened DBoW2::FeatureVector); valid: optional list of (n,) uint8.  Returns (arrays kept alive, BowView, stride)."""
@@ -238,7 +279,7 @@ class ORBmatcher:
         return nm, [m[i, :(ka if keyframes else fa)["n"][i]] for i in range(items)]
 
     # ---- the search of Fuse(pKF, vpMapPoints, th) (S/ORBmatcher.cc:829-948), scope row N3 ----
-    def fuse_search_batch(self, ws, bounds, th=3.0, mode=0, R2=None, t2=None):
+    def fuse_search_batch(self, ws, bounds, th=3.0, mode=0, R2=None, t2=None, device_reps=0):
         """mode 0 = Fuse(pKF, vpMapPoints, th), 1 = Fuse(pKF, Scw, ...), 2 = a SearchBySim3 leg (R2, t2: per-item second
         similarity).  ws: list of workloads.fuse_frame()-layout dicts (valid == 1 marks usable candidates; kp / kdesc / u_right = the
         key frame; Rcw, tcw, Ow, K, bf, scale_factors, inv_level_sigma2, log_scale).  Returns per item
@@ -275,6 +316,18 @@ class ORBmatcher:
                                           float(ws[0]["log_scale"]), bnd.ctypes.data, float(th), int(mode),
                                           r2.ctypes.data if r2 is not None else None, tt2.ctypes.data if tt2 is not None else None,
                                           best.ctypes.data, dist.ctypes.data, 0))
+        if device_reps:          # the same call on device-resident copies of the same data, CUDA events on the matcher's stream
+            keep = []
+            dfv = _device_copy(fv, [nk] + list(k.values()), self.device, keep)
+            dpv = _device_copy(pv, [nm] + list(a.values()), self.device, keep)
+            d = lambda x: _device_array(x, self.device, keep) if x is not None else None
+            dur, dR, dT, dOw, dr2, dt2, dsf, dil = d(k["ur"]), d(R), d(t), d(Ow), d(r2), d(tt2), d(sf), d(il)
+            dbest, ddist = d(best), d(dist)
+            self.last_device_ms = _device_time(self._L.orbb200_matcher_stream(self._h), self.device, lambda: check(
+                self._L.orbb200_fuse_search(self._h, items, C.byref(dfv), dur, C.byref(dpv), dR, dT, dOw, K.ctypes.data, float(ws[0]["bf"]),
+                                            dsf, dil, len(sf), float(ws[0]["log_scale"]), bnd.ctypes.data, float(th),
+                                            int(mode), dr2, dt2, dbest, ddist, 1)), device_reps)
+            assert np.array_equal(keep[-2].cpu().numpy(), best), "device-resident call differs from the host-buffer call"
         return [(best[i, :nm[i]], dist[i, :nm[i]]) for i in range(items)]
 
     # ---- SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (S/ORBmatcher.cc:294-407), scope row N3 ----
@@ -389,7 +442,7 @@ class ORBmatcher:
         return [(ur[i, :len(lefts[i][0])], dep[i, :len(lefts[i][0])]) for i in range(items)], nm
 
     # ---- SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (S/ORBmatcher.cc:661-827), scope row N3 ----
-    def search_for_triangulation_batch(self, pairs, only_stereo=False):
+    def search_for_triangulation_batch(self, pairs, only_stereo=False, device_reps=0):
         """pairs: list of workloads.triangulation_pair()-layout dicts (k1 / k2: x, y, octave, angle, desc, has_mp, u_right,
         node, start, feat; F12 (9), epipole (2), scale_factors, level_sigma2).  Returns (nmatches (items,),
         [matches12 per item: index in key frame 2 or -1]); vMatchedPairs = [(i, m[i]) for i where m[i] >= 0]."""
@@ -415,6 +468,18 @@ class ORBmatcher:
         check(self._L.orbb200_search_for_triangulation(
             self._h, items, C.byref(v1), C.byref(t1), C.byref(v2), C.byref(t2), F.ctypes.data, ep.ctypes.data, sf.ctypes.data,
             ls.ctypes.data, len(sf), int(only_stereo), int(self.mbCheckOrientation), m.ctypes.data, nm.ctypes.data, 0))
+        if device_reps:          # the same call on device-resident copies of the same data, CUDA events on the matcher's stream
+            keep = []
+            dv1, dv2 = _device_copy(v1, list(a1.values()), self.device, keep), _device_copy(v2, list(a2.values()), self.device, keep)
+            dt1, dt2 = _device_copy(t1, list(g1.values()), self.device, keep), _device_copy(t2, list(g2.values()), self.device, keep)
+            dF, dep = _device_array(F, self.device, keep), _device_array(ep, self.device, keep)
+            dsf, dls = _device_array(sf, self.device, keep), _device_array(ls, self.device, keep)
+            dm, dnm = _device_array(m, self.device, keep), _device_array(nm, self.device, keep)
+            self.last_device_ms = _device_time(self._L.orbb200_matcher_stream(self._h), self.device, lambda: check(
+                self._L.orbb200_search_for_triangulation(self._h, items, C.byref(dv1), C.byref(dt1), C.byref(dv2), C.byref(dt2), dF, dep,
+                                                         dsf, dls, len(sf), int(only_stereo),
+                                                         int(self.mbCheckOrientation), dm, dnm, 1)), device_reps)
+            assert np.array_equal(keep[-1].cpu().numpy(), nm), "device-resident call differs from the host-buffer call"
         return nm, [m[i, :a1["n"][i]] for i in range(items)]
 
     # ---- SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (S/ORBmatcher.cc:1476-1603), scope row N2 ----
