@@ -14,6 +14,9 @@
 #include "orb_oracle.h"
 
 // ---- monotonic per-thread arena behind operator new -------------------------------------
+// (-DREF_DEFAULT_MALLOC builds the same library WITHOUT it: libref_orb_malloc.so, the reference under glibc's allocator,
+// for the tie-break sensitivity report tools/tiebreak_report.py -> profiles/r2_tiebreak.json)
+#ifndef REF_DEFAULT_MALLOC
 namespace {
 struct Arena {
     char* base; size_t top, cap;
@@ -45,6 +48,9 @@ void operator delete(void*) noexcept {}
 void operator delete[](void*) noexcept {}
 void operator delete(void*, size_t) noexcept {}
 void operator delete[](void*, size_t) noexcept {}
+#else
+namespace { int g_direction = 0; struct NoArena { size_t top; }; thread_local NoArena g_arena = {0}; }   // marks are no-ops
+#endif
 
 namespace {
 class RefExtractor : public ORB_SLAM2::ORBextractor {

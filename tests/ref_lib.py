@@ -17,33 +17,55 @@ def available():
     return os.path.exists(REF_SO)
 
 
+def _load_extractor_library(path):
+    L = C.CDLL(path)
+    L.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.ref_extractor_create.restype = C.c_void_p
+    L.ref_extractor_destroy.argtypes = [C.c_void_p]
+    L.ref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    L.ref_extract.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p, C.c_int]
+    L.ref_extract.restype = C.c_int
+    L.ref_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ref_level_pixels.argtypes = [C.c_void_p, C.c_int, C.c_int, _u8p]
+    L.ref_distribute_octree.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.ref_distribute_octree.restype = C.c_int
+    L.ref_extract_batch_mt.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.ref_set_alloc_direction.argtypes = [C.c_int]
+    L.minicv_set_blur_variant.argtypes = [C.c_int]
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
         build_oracle()
-        L = C.CDLL(REF_SO)
-        L.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
-        L.ref_extractor_create.restype = C.c_void_p
-        L.ref_extractor_destroy.argtypes = [C.c_void_p]
-        L.ref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
-        L.ref_extract.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p, C.c_int]
-        L.ref_extract.restype = C.c_int
-        L.ref_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-        L.ref_level_pixels.argtypes = [C.c_void_p, C.c_int, C.c_int, _u8p]
-        L.ref_distribute_octree.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                            C.c_int, C.c_int, C.c_void_p, C.c_int]
-        L.ref_distribute_octree.restype = C.c_int
-        L.ref_extract_batch_mt.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int,
-                                           C.c_int, C.c_int, C.POINTER(C.c_int)]
-        L.ref_set_alloc_direction.argtypes = [C.c_int]
-        L.minicv_set_blur_variant.argtypes = [C.c_int]
-        _lib = L
+        _lib = _load_extractor_library(REF_SO)
     return _lib
 
 
+# the same reference build WITHOUT the bump allocator (glibc malloc decides the quadtree's pointer-valued tie-break,
+# S/ORBextractor.cc:694-698): what an integrator who links the real reference sees.  tools/tiebreak_report.py
+REF_MALLOC_SO = os.path.join(ORACLE_DIR, "_ref", "libref_orb_malloc.so")
+_malloc_lib = None
+
+
+def malloc_variant_available():
+    return os.path.exists(REF_MALLOC_SO)
+
+
+def malloc_lib():
+    global _malloc_lib
+    if _malloc_lib is None:
+        build_oracle()
+        _malloc_lib = _load_extractor_library(REF_MALLOC_SO)
+    return _malloc_lib
+
+
 class RefExtractor:
-    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
-        self.L = lib()
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, default_malloc=False):
+        self.L = malloc_lib() if default_malloc else lib()
         self.h = self.L.ref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
         self.nfeatures, self.nlevels = nfeatures, nlevels
 

@@ -524,3 +524,22 @@ def test_compute_stereo_matches_random_keypoints_match_reference():
         ur_r, dep_r, cnt = R.ref_compute_stereo_matches(kl, dl, kr, dr, sc, isc, lp, rp, mb, mbf)
         assert kept == cnt
         assert ur_o.tobytes() == ur_r.tobytes() and dep_o.tobytes() == dep_r.tobytes()
+
+
+@pytest.mark.skipif(not (R.available() and R.malloc_variant_available()), reason="oracle/_ref/libref_orb_malloc.so not built")
+def test_tiebreak_report_reference_under_glibc_malloc():
+    """SURVEY 7 hard part 1: the reference's DistributeOctTree orders equal-count nodes by heap address
+    (S/ORBextractor.cc:694-698).  Under glibc malloc the same reference build differs from the canonical (bump
+    allocator) order in a few keypoints per frame, and even from itself when the heap history changes; everything both
+    runs keep is identical.  tools/tiebreak_report.py writes the numbers to profiles/r2_tiebreak.json."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import tiebreak_report as T
+    frames = [F.synthetic_frame(i) for i in range(3)]
+    r = T.compare(frames)
+    assert r["frames"] == 3 and r["keypoints_canonical_total"] > 2900
+    assert r["fraction_of_keypoints_not_in_both"] < 0.05          # a handful of leaves per frame, never a different image
+    for f in r["per_frame"]:
+        assert abs(f["keypoints"] - f["keypoints_glibc"]) <= 16
+    committed = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_tiebreak.json")
+    assert os.path.exists(committed)
