@@ -12,6 +12,7 @@
 //   k_quadtree   one CTA per (frame,level): DistributeOctTree as parallel rounds over a node table
 //   k_blur       7x7 fixed-point separable Gaussian, shared-memory tiles
 //   k_describe   one warp per keypoint: IC_Angle moments (warp reduction) + steered BRIEF + output
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -80,6 +81,8 @@ struct ExtractParams {
     int blurVariant;
     // k_fast shared-memory geometry
     int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <38,64> instantiation
+    const int4* cells;                               // k_fast cell table (one entry per detection cell that exists, level-major)
+    int nCells, frameBase;                           // entries; index of the batch's first frame inside the handle's slabs
     // k_quadtree shared-memory geometry
     int qtNC, qtPC;
     LevelGeo lv[MAXL];
@@ -200,6 +203,21 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
         *reinterpret_cast<uint32_t*>(outp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
         outp += g.pitch;
     }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 // ======================================================================================
@@ -460,6 +478,262 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast(const ExtractParams P)
     tlow = P.minTh;
     }   // attempt
     if (nk == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&P.candCount[frame * P.nlevels + l], nk);
+    base = __shfl_sync(FULL, base, 0);
+    uint32_t* out = P.cand + (long long)frame * P.candFrameCap + g.candOff;
+    for (int i = lane; i < nk; i += 32) {
+        const int p = base + i;
+        if (p < g.candCap) out[p] = klist[i];
+        else atomicOr(P.status, STATUS_CAND_OVERFLOW);
+    }
+}
+#undef FAST_PAIR
+
+// ---- k_fast, second generation ---------------------------------------------------------------------------------------
+// Same three passes and the same arithmetic as above; what changed is everything around them (ncu r1p: window staging was
+// 16 % of the instructions and 24 % of the stall samples, cell set-up 5 %, NMS 12 %):
+//  * the cell's window arrives as ONE 3-D TMA tensor copy (cp.async.bulk.tensor.3d over a {column, row, frame} map of the
+//    level, SASS UTMALDG): no per-lane global addresses.  The TMA unit wants the box to start on a 16-byte boundary (measured:
+//    any other column raises "illegal instruction"), so the raw bytes land up to 15 columns left of the window, in the region
+//    the score map and the queue use later, and the expansion to the 16-bit tile realigns them with one funnel shift per
+//    word: the window always sits at tile column 1 and the first detection pixel at tile column 4.  The pixel-pair grid
+//    therefore never has masked lead-in pairs (the old kernel's `off`, up to 3 of ~17 pairs per row);
+//  * cell geometry (level, window origin and size, offset of the cell inside the level) comes from a table built at create:
+//    one 16-byte load instead of the level search, two divisions and the border tests;
+//  * NMS handles both pixels of a pair at once on packed 16-bit lanes (3 x 4 score bytes -> nine PRMT -> four packed max);
+//  * the pass-1 threshold tests are two IADD3 + one LOP3 per pair (sign bits of 0x8000 + a - b per half).
+struct FastMaps { CUtensorMap m[MAXL]; };
+
+template <int TPW, int TH>
+struct FastGeo2 {
+    static constexpr int SP = TPW * 2 - 4;                    // score-map pitch in bytes (multiple of 4)
+    static constexpr int BW = TPW == 26 ? 64 : 96;            // TMA box: BW bytes x TH rows (15 alignment columns + window + 5)
+    static constexpr int QCAP = (TPW - 2) * (TH - 6);
+    static constexpr int QBYTES = 2 * QCAP + 64;
+    static constexpr int RAW_BYTES = BW * TH;
+    static constexpr int REGION = (((TH - 4) * SP + QBYTES > RAW_BYTES ? (TH - 4) * SP + QBYTES : RAW_BYTES) + 127) / 128 * 128;
+    static constexpr int TILE_BYTES = TH * TPW * 4 + 64;
+    static constexpr int BAR_OFF = (REGION + TILE_BYTES + 15) / 16 * 16;
+    static constexpr int SMEM_BYTES = BAR_OFF + 16;
+    static constexpr int CHL = BW / 16 <= 4 ? 4 : 8;          // lanes per row in the expansion (>= 16-column chunks per row)
+    // window (cell + 6) needs tile columns 0 .. ww + 4 and rows 0 .. wh - 1, behind up to 15 alignment columns in the box
+    static constexpr bool fits(int wCell, int hCell) { return 15 + wCell + 6 + 5 <= BW && wCell + 6 + 5 <= 2 * TPW && hCell + 6 <= TH; }
+    static_assert(RAW_BYTES + 16 <= REGION, "the expansion reads whole words past the last needed column");
+    static_assert(TH * TPW * 4 >= 4 * (QCAP / 2 + 64), "NMS survivors are written over the dead tile");
+};
+
+#define FAST_PAIR(a, b) __byte_perm(a, b, 0x5432)
+
+template <int TPW, int TH>
+__global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractParams P, const __grid_constant__ FastMaps M)
+{
+    using G = FastGeo2<TPW, TH>;
+    constexpr int SP = G::SP, BW = G::BW;
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int frame = blockIdx.y;
+    const int4 cr = __ldg(P.cells + blockIdx.x);
+    const int iniX = cr.x & 0xffff, iniY = (int)((unsigned)cr.x >> 16);
+    const int ww = cr.y & 0xff, wh = (cr.y >> 8) & 0xff, l = cr.y >> 16;
+    const int dw = ww - 6, dh = wh - 6;
+
+    uint8_t* raw = smem;                                                 // [TH][BW] bytes from the TMA unit
+    uint8_t* score = smem;                                               // [(dh + 2)][SP], zero ring (after the expansion)
+    uint16_t* queue = reinterpret_cast<uint16_t*>(smem + (TH - 4) * SP);
+    uint32_t* tw = reinterpret_cast<uint32_t*>(smem + G::REGION);        // [TH][TPW], 2 px per word
+    uint32_t* klist = tw;
+    const uint32_t bar = smem_u32(smem + G::BAR_OFF);
+
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)G::RAW_BYTES) : "memory");
+        // box origin: the 16-byte boundary at or left of image column iniX - 1 (= tile column 0; the TMA unit wants the box to
+        // start on one), row iniY, frame; anything past the level's edge reads as 0
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(raw)), "l"(reinterpret_cast<uint64_t>(&M.m[l])), "r"(bar), "r"((iniX - 1) & ~15), "r"(iniY),
+                       "r"((l == 0 ? 0 : P.frameBase) + frame) : "memory");
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    {   // expand to 16 bit and realign: tile column c = raw column c + sx (the box starts at a 16-byte boundary, sx = 0 .. 15
+        // columns left of the window's tile column 0).  Lane = (row of a group, 16 tile columns); columns 0 .. ww + 4 are needed
+        constexpr int RPI = 32 / G::CHL;
+        const int q = lane & (G::CHL - 1), sub = lane / G::CHL;
+        const int nch = (ww + 5 + 15) >> 4;
+        const int sx = (iniX - 1) & 15, sh = (sx & 3) * 8;
+        if (q < nch) {
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw + sub * BW) + (sx >> 2) + 4 * q;
+            uint32_t* d = tw + sub * TPW + 8 * q;
+            for (int r = sub; r < wh; r += RPI) {
+                const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3], w4 = rp[4];
+                const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (8 * q + 2 * k < TPW)
+                        *reinterpret_cast<uint2*>(d + 2 * k) = make_uint2(__byte_perm(v[k], 0, 0x4140), __byte_perm(v[k], 0, 0x4342));
+                rp += RPI * (BW / 4);
+                d += RPI * TPW;
+            }
+        }
+    }
+    __syncwarp();
+    {
+        uint4* sz = reinterpret_cast<uint4*>(score);
+        for (int i = lane; i < ((dh + 2) * SP + 15) / 16; i += 32) sz[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+
+    // pair i covers detection x = 2i, 2i + 1 (tile columns 4 + 2i, 5 + 2i = word 2 + i); two neighbouring pairs (a quad)
+    // start at an 8-byte aligned word
+    const uint32_t* tbase = tw + 3 * TPW + 2;
+    const int npair = (dw + 1) >> 1, nquad = (npair + 1) >> 1, total = nquad * dh;
+    const unsigned ltmask = (1u << lane) - 1;
+
+    int tlow = P.iniTh;
+    int nk = 0;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; attempt++) {
+    // per half: 0x8000 + c + t - ringmin has its top bit clear exactly when ringmin > c + t (bright candidate), and
+    // 0x8000 + ringmax + t - c when ringmax < c - t (dark candidate); no borrow crosses the halves (all terms < 0x8000)
+    const uint32_t TK = (uint32_t)tlow * 0x00010001u + 0x80008000u;
+
+    int nq = 0;
+    {
+        int k = lane / dh, r = lane - k * dh;
+        const int stepK = 32 / dh, stepR = 32 - stepK * dh;
+        for (int idx = lane; idx - lane < total; idx += 32) {
+            bool passA, passB;
+            const bool act = idx < total;
+            {
+                const uint32_t* b = tbase + (act ? r * TPW + 2 * k : 0);
+                const uint2 c = *reinterpret_cast<const uint2*>(b);
+                const uint2 lf = *reinterpret_cast<const uint2*>(b - 2), rt = *reinterpret_cast<const uint2*>(b + 2);
+                const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
+                const uint2 u2 = *reinterpret_cast<const uint2*>(b + 2 * TPW), d2 = *reinterpret_cast<const uint2*>(b - 2 * TPW);
+                const uint32_t u2l = b[2 * TPW - 1], u2r = b[2 * TPW + 2], d2l = b[-2 * TPW - 1], d2r = b[-2 * TPW + 2];
+                {
+                    const uint32_t R4 = FAST_PAIR(c.y, rt.x), R12 = FAST_PAIR(lf.x, lf.y);
+                    const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4, R12), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
+                    const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.x, dn.x), __vminu2(R4, R12), __vminu2(u2.y, d2l)), __vminu2(d2.y, u2l));
+                    passA = act && ((((c.x + TK) - mb) & ((md + TK) - c.x) & 0x80008000u) != 0x80008000u);
+                }
+                {
+                    const uint32_t R4 = FAST_PAIR(rt.x, rt.y), R12 = FAST_PAIR(lf.y, c.x);
+                    const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.y, dn.y), __vmaxu2(R4, R12), __vmaxu2(u2r, d2.x)), __vmaxu2(d2r, u2.x));
+                    const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.y, dn.y), __vminu2(R4, R12), __vminu2(u2r, d2.x)), __vminu2(d2r, u2.x));
+                    passB = act && ((((c.y + TK) - mb) & ((md + TK) - c.y) & 0x80008000u) != 0x80008000u);
+                }
+            }
+            const unsigned balA = __ballot_sync(FULL, passA), balB = __ballot_sync(FULL, passB);
+            if (passA) queue[nq + __popc(balA & ltmask)] = (uint16_t)(r * 64 + 2 * k);
+            nq += __popc(balA);
+            if (passB) queue[nq + __popc(balB & ltmask)] = (uint16_t)(r * 64 + 2 * k + 1);
+            nq += __popc(balB);
+            k += stepK; r += stepR;
+            if (r >= dh) { r -= dh; k++; }
+        }
+    }
+    __syncwarp();
+    // pass 2: exact corner score (see k_fast)
+    int ncp = 0;
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int q = q0 + lane;
+        bool c0 = false, c1 = false;
+        int e = 0;
+        if (q < nq) {
+            e = queue[q];
+            const int r = e >> 6, i = e & 63;
+            const uint32_t* b = tbase + r * TPW + i;
+            uint32_t D[16];
+            {
+                const uint32_t a0 = b[3 * TPW - 1], a1 = b[3 * TPW], a2 = b[3 * TPW + 1];
+                D[15] = FAST_PAIR(a0, a1); D[0] = a1; D[1] = FAST_PAIR(a1, a2);
+                const uint32_t z0 = b[-3 * TPW - 1], z1 = b[-3 * TPW], z2 = b[-3 * TPW + 1];
+                D[9] = FAST_PAIR(z0, z1); D[8] = z1; D[7] = FAST_PAIR(z1, z2);
+                D[14] = b[2 * TPW - 1]; D[2] = b[2 * TPW + 1];
+                D[10] = b[-2 * TPW - 1]; D[6] = b[-2 * TPW + 1];
+                D[13] = FAST_PAIR(b[TPW - 2], b[TPW - 1]); D[3] = FAST_PAIR(b[TPW + 1], b[TPW + 2]);
+                D[12] = FAST_PAIR(b[-2], b[-1]); D[4] = FAST_PAIR(b[1], b[2]);
+                D[11] = FAST_PAIR(b[-TPW - 2], b[-TPW - 1]); D[5] = FAST_PAIR(b[-TPW + 1], b[-TPW + 2]);
+            }
+            uint32_t lo3[16], hi3[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                lo3[k] = __vimin3_u16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
+                hi3[k] = __vimax3_u16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
+            }
+            uint32_t lo9[16], hi9[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                lo9[k] = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+                hi9[k] = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+            }
+            uint32_t bright = __vimax3_u16x2(lo9[0], lo9[1], lo9[2]), dark = __vimin3_u16x2(hi9[0], hi9[1], hi9[2]);
+#pragma unroll
+            for (int k = 3; k < 15; k += 2) {
+                bright = __vimax3_u16x2(bright, lo9[k], lo9[k + 1]);
+                dark = __vimin3_u16x2(dark, hi9[k], hi9[k + 1]);
+            }
+            bright = __vmaxu2(bright, lo9[15]);
+            dark = __vminu2(dark, hi9[15]);
+            const uint32_t V = b[0];
+            const uint32_t m2 = __vmaxu2(bright + (0x01000100u - V), (0x01000100u + V) - dark);    // 256 + m per half
+            const int m0 = (int)(m2 & 0xffffu) - 256, m1 = (int)(m2 >> 16) - 256;
+            const int x0 = 2 * i;
+            c0 = (m0 > tlow) && (x0 < dw);
+            c1 = (m1 > tlow) && (x0 + 1 < dw);
+            // both bytes of the pair in one 16-bit store (0 = no corner; the map is zero there anyway)
+            if (c0 || c1)
+                *reinterpret_cast<uint16_t*>(score + (r + 1) * SP + x0 + 2) = (uint16_t)((c0 ? m0 - 1 : 0) | ((c1 ? m1 - 1 : 0) << 8));
+        }
+        const unsigned bal = __ballot_sync(FULL, c0 || c1);
+        if (c0 || c1) queue[ncp + __popc(bal & ltmask)] = (uint16_t)e;
+        ncp += __popc(bal);
+    }
+    __syncwarp();
+    // pass 3: 3x3 NMS of both pixels of a corner pair at once.  The pair's own score bytes sit at map columns x0 + 2, x0 + 3
+    // (detection x + 2, so a pair starts at an even byte); the 4 bytes x0 + 1 .. x0 + 4 of the three rows are cut out of two
+    // aligned words each and spread to packed 16-bit lanes: L = (x0 - 1, x0), C = (x0, x0 + 1), R = (x0 + 1, x0 + 2).
+    for (int q0 = 0; q0 < ncp; q0 += 32) {
+        const int q = q0 + lane;
+        const int e = q < ncp ? queue[q] : 0;
+        const int r = e >> 6, x0 = 2 * (e & 63);
+        bool k0 = false, k1 = false;
+        uint32_t C = 0;
+        if (q < ncp) {
+            const uint8_t* sp = score + (r + 1) * SP + x0 + 1;
+            const int sh = (int)(reinterpret_cast<uintptr_t>(sp) & 3) * 8;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(sp - (sh >> 3));
+            constexpr int SPW = SP / 4;
+            const uint32_t rowU = __funnelshift_r(wp[-SPW], wp[-SPW + 1], sh);
+            const uint32_t rowC = __funnelshift_r(wp[0], wp[1], sh);
+            const uint32_t rowD = __funnelshift_r(wp[SPW], wp[SPW + 1], sh);
+            C = __byte_perm(rowC, 0, 0x4241);
+            const uint32_t nU = __vimax3_u16x2(__byte_perm(rowU, 0, 0x4140), __byte_perm(rowU, 0, 0x4241), __byte_perm(rowU, 0, 0x4342));
+            const uint32_t nD = __vimax3_u16x2(__byte_perm(rowD, 0, 0x4140), __byte_perm(rowD, 0, 0x4241), __byte_perm(rowD, 0, 0x4342));
+            const uint32_t nb = __vimax3_u16x2(nU, nD, __vmaxu2(__byte_perm(rowC, 0, 0x4140), __byte_perm(rowC, 0, 0x4342)));
+            // keep = C > nb per half, and C != 0: a corner always has a score byte >= tlow - ... but 0 marks "no corner"
+            const uint32_t gt = (nb | 0x80008000u) - C;                 // top bit of a half clear <=> C > nb
+            k0 = !(gt & 0x00008000u);
+            k1 = !(gt & 0x80000000u);
+        }
+        const unsigned bal0 = __ballot_sync(FULL, k0), bal1 = __ballot_sync(FULL, k1);
+        const int xr = x0 + 3 + (cr.z & 0xffff), yr = r + 3 + (int)((unsigned)cr.z >> 16);   // relative to the border (:840-841)
+        if (k0) klist[nk + __popc(bal0 & ltmask)] = (uint32_t)xr | ((uint32_t)yr << 12) | ((C & 0xffu) << 24);
+        nk += __popc(bal0);
+        if (k1) klist[nk + __popc(bal1 & ltmask)] = (uint32_t)(xr + 1) | ((uint32_t)yr << 12) | ((C >> 16) << 24);
+        nk += __popc(bal1);
+    }
+    __syncwarp();
+    if (nk > 0 || P.minTh >= P.iniTh) break;
+    tlow = P.minTh;
+    }   // attempt
+    if (nk == 0) return;
+    const LevelGeo& g = P.lv[l];
     int base = 0;
     if (lane == 0) base = atomicAdd(&P.candCount[frame * P.nlevels + l], nk);
     base = __shfl_sync(FULL, base, 0);
@@ -758,21 +1032,6 @@ __device__ __forceinline__ int reflect101(int p, int n)
     if (p < 0) p = -p;
     if (p >= n) p = 2 * (n - 1) - p;
     return p;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 struct BlurTile { int l, frame, x0, y0; };
@@ -1141,6 +1400,8 @@ struct orbb200_extractor {
     size_t inPitch;
     int totalCells, totalBlurTiles, maxKp, numSMs;
     size_t fastSmem, qtSmem;
+    int fastVariant;           // 2 = k_fast2 (TMA tensor staging, default), 1 = k_fast (ORBB200_FAST_VARIANT=1: the first-generation kernel, kept for A/B runs)
+    FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
     int lastLaunches, lastBatch;
     int realCandCap[MAXL];     // per-level candidate capacity as computed at create (orbb200_extractor_debug_set_capacity clamps P.lv[l].candCap)
     int chunkOverride;         // ORBB200_CHUNKS read once at create (0 = choose by batch size): tuning knob of the blocking host call
@@ -1185,6 +1446,30 @@ static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<shor
         const int y0 = std::min(std::max(sy, 0), sh - 1), y1 = std::min(std::max(sy + 1, 0), sh - 1);
         yt[dy] = make_short4((short)y0, (short)y1, coef11(1.f - fy), coef11(fy));
     }
+}
+
+// 3-D tensor map {column, row, frame} over one pyramid level for k_fast2's window copies (uint8, no swizzle, zero fill).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_level_map(CUtensorMap* map, const void* base, int w, int h, int frames, size_t pitch, size_t frameStride, int boxW, int boxH)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ORB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return ORBB200_ECUDA; }
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
+    const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d level, pitch %zu, frame stride %zu", (int)r, w, h, frames, pitch, frameStride); return ORBB200_ECUDA; }
+    return ORBB200_OK;
 }
 
 template <typename T>
@@ -1326,7 +1611,28 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     P.fastLarge = FastGeo<26, 42>::fits(maxWCell, maxHCell) ? 0 : 1;
     if (P.fastLarge && !FastGeo<38, 64>::fits(maxWCell, maxHCell)) { set_error("FAST cell does not fit the staging tile"); delete h; return ORBB200_EGEOMETRY; }
     P.totalCells = cells;
+    h->fastVariant = 2;
+    if (const char* e = getenv("ORBB200_FAST_VARIANT")) h->fastVariant = atoi(e) == 1 ? 1 : 2;
+    if (h->fastVariant == 2) {
+        P.fastLarge = FastGeo2<26, 42>::fits(maxWCell, maxHCell) ? 0 : 1;
+        if (P.fastLarge && !FastGeo2<38, 64>::fits(maxWCell, maxHCell)) { set_error("FAST cell does not fit the staging tile"); delete h; return ORBB200_EGEOMETRY; }
+        h->fastSmem = P.fastLarge ? FastGeo2<38, 64>::SMEM_BYTES : FastGeo2<26, 42>::SMEM_BYTES;
+    } else
     h->fastSmem = (size_t)FAST_WARPS * (P.fastLarge ? FastGeo<38, 64>::WARP_BYTES : FastGeo<26, 42>::WARP_BYTES);
+    // k_fast2's cell table: window origin and size, level, offset of the cell inside the level (:807-822, :840-841)
+    std::vector<int4> cellTab;
+    for (int l = 0; l < nlevels; l++) {
+        const LevelGeo& g = P.lv[l];
+        for (int ci = 0; ci < g.nRows; ci++)
+            for (int cj = 0; cj < g.nCols; cj++) {
+                const int iniY = BORDER + ci * g.hCell, iniX = BORDER + cj * g.wCell;
+                if (iniY >= g.maxBY - 3 || iniX >= g.maxBX - 6) continue;                    // :810, :819
+                const int ww = std::min(iniX + g.wCell + 6, g.maxBX) - iniX, wh = std::min(iniY + g.hCell + 6, g.maxBY) - iniY;
+                if (ww < 7 || wh < 7) continue;                                               // cv::FAST finds nothing in < 7 px
+                cellTab.push_back(make_int4(iniX | (iniY << 16), ww | (wh << 8) | (l << 16), (cj * g.wCell) | ((ci * g.hCell) << 16), 0));
+            }
+    }
+    P.nCells = (int)cellTab.size();
     // k_quadtree shared memory: 88 bytes per node slot + 6 bytes per candidate held on chip
     P.qtNC = (int)align_up(maxKpCap + 8, 8);
     const size_t perNode = 8 + 8 + 8 + 4 * 7 + 16 + 16;
@@ -1355,9 +1661,17 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     TRY(dev_alloc(h, &h->dOutDesc, (size_t)P.outCap * max_batch * 32));
     TRY(dev_alloc(h, &h->dOutCount, (size_t)max_batch));
     TRY(dev_alloc(h, &P.status, 1));
+    int4* dCells = nullptr;
+    TRY(dev_alloc(h, &dCells, cellTab.size() + 1));
+    P.cells = dCells;
+    for (int l = 1; l < nlevels && h->fastVariant == 2; l++)      // levels >= 1 live in the handle's pyramid slab: maps made once
+        TRY(encode_level_map(&h->fastMaps.m[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes,
+                             P.fastLarge ? FastGeo2<38, 64>::BW : FastGeo2<26, 42>::BW, P.fastLarge ? 64 : 42));
 #undef TRY
     P.tabs = dTabs;
     cudaError_t e = cudaSuccess;
+    if (!cellTab.empty()) e = cudaMemcpy(dCells, cellTab.data(), cellTab.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("extractor_create: %s", cudaGetErrorString(e)); orbb200_extractor_destroy(h); return ORBB200_ECUDA; }
     if (!tabs.empty()) e = cudaMemcpy(dTabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(P.status, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -1370,7 +1684,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         e = cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
+    if (e == cudaSuccess && h->fastVariant == 1) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
+    if (e == cudaSuccess && h->fastVariant == 2) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast2<38, 64> : (const void*)k_fast2<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)k_quadtree, device, h->qtSmem);
     if (e == cudaSuccess) e = ensure_dynamic_smem(P.blurVariant ? (const void*)k_blur<true> : (const void*)k_blur<false>, device, BL_WARPS * BL_WARP_BYTES);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
@@ -1473,7 +1788,15 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
     STAGE_MARK(1);
-    {
+    if (h->fastVariant == 2) {
+        // level 0 may be the caller's own buffer: its map is encoded per call (a host-side table fill, no driver round trip)
+        int rc = encode_level_map(&h->fastMaps.m[0], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride,
+                                  P.fastLarge ? FastGeo2<38, 64>::BW : FastGeo2<26, 42>::BW, P.fastLarge ? 64 : 42);
+        if (rc != ORBB200_OK) return rc;
+        const dim3 grid(P.nCells, batch);
+        if (P.fastLarge) k_fast2<38, 64><<<grid, 32, h->fastSmem, st>>>(P, h->fastMaps);
+        else k_fast2<26, 42><<<grid, 32, h->fastSmem, st>>>(P, h->fastMaps);
+    } else {
         const dim3 grid((h->totalCells + FAST_WARPS - 1) / FAST_WARPS, batch);
         if (P.fastLarge) k_fast<38, 64><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
         else k_fast<26, 42><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
@@ -1548,6 +1871,7 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
         P.inRowBytes = (int)h->inPitch;
     }
     P.batch = batch; P.in = d_images; P.inPitch = (int)stride; P.inFrameStride = (long long)frame_stride;
+    P.frameBase = first;
     P.inPadded = (d_images >= h->dIn && d_images < h->dIn + inFrameBytes * h->maxBatch && h->inPitch >= (size_t)h->width + 4) ? 1 : 0;
     P.outKp = d_kp; P.outDesc = d_desc; P.outCount = d_counts; P.outCap = cap;
     int launches = 0;
