@@ -519,7 +519,7 @@ struct FastGeo2 {
     static constexpr int CHL = BW / 16 <= 4 ? 4 : 8;          // lanes per row in the expansion (>= 16-column chunks per row)
     // window (cell + 6) needs tile columns 0 .. ww + 4 and rows 0 .. wh - 1, behind up to 15 alignment columns in the box
     static constexpr bool fits(int wCell, int hCell) { return 15 + wCell + 6 + 5 <= BW && wCell + 6 + 5 <= 2 * TPW && hCell + 6 <= TH; }
-    static_assert(RAW_BYTES + 16 <= REGION, "the expansion reads whole words past the last needed column");
+    static_assert(RAW_BYTES + 32 <= REGION, "the expansion reads a whole 16-byte chunk past the last needed column");
     static_assert(TH * TPW * 4 >= 4 * (QCAP / 2 + 64), "NMS survivors are written over the dead tile");
 };
 
@@ -566,16 +566,26 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
         const int nch = (ww + 5 + 15) >> 4;
         const int sx = (iniX - 1) & 15, sh = (sx & 3) * 8;
         if (q < nch) {
-            const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw + sub * BW) + (sx >> 2) + 4 * q;
+            // two aligned 16-byte loads per lane (conflict-free: a quarter-warp reads 8 different 16-byte chunks), then the five
+            // words from word offset sx >> 2 on -- a warp-uniform choice, so the switch costs no divergence
+            const uint4* rp = reinterpret_cast<const uint4*>(raw + sub * BW) + q;
             uint32_t* d = tw + sub * TPW + 8 * q;
+            const int wsel = sx >> 2;
             for (int r = sub; r < wh; r += RPI) {
-                const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3], w4 = rp[4];
+                const uint4 a = rp[0], b = rp[1];
+                uint32_t w0, w1, w2, w3, w4;
+                switch (wsel) {
+                    case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+                    case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+                    case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+                    default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+                }
                 const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if (8 * q + 2 * k < TPW)
                         *reinterpret_cast<uint2*>(d + 2 * k) = make_uint2(__byte_perm(v[k], 0, 0x4140), __byte_perm(v[k], 0, 0x4342));
-                rp += RPI * (BW / 4);
+                rp += RPI * (BW / 16);
                 d += RPI * TPW;
             }
         }
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
     // pair i covers detection x = 2i, 2i + 1 (tile columns 4 + 2i, 5 + 2i = word 2 + i); two neighbouring pairs (a quad)
     // start at an 8-byte aligned word
     const uint32_t* tbase = tw + 3 * TPW + 2;
-    const int npair = (dw + 1) >> 1, nquad = (npair + 1) >> 1, total = nquad * dh;
+    const int npair = (dw + 1) >> 1, nquad = (npair + 1) >> 1;
     const unsigned ltmask = (1u << lane) - 1;
 
     int tlow = P.iniTh;
@@ -603,38 +613,49 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
 
     int nq = 0;
     {
-        int k = lane / dh, r = lane - k * dh;
-        const int stepK = 32 / dh, stepR = 32 - stepK * dh;
-        for (int idx = lane; idx - lane < total; idx += 32) {
+        // one quad (2 pairs, 4 centre pixels) per lane and step: 11 shared loads, 24 packed min/max, two sign tests
+        auto test_quad = [&](const uint32_t* b, bool act, int entry) {
             bool passA, passB;
-            const bool act = idx < total;
+            const uint2 c = *reinterpret_cast<const uint2*>(b);
+            const uint2 lf = *reinterpret_cast<const uint2*>(b - 2), rt = *reinterpret_cast<const uint2*>(b + 2);
+            const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
+            const uint2 u2 = *reinterpret_cast<const uint2*>(b + 2 * TPW), d2 = *reinterpret_cast<const uint2*>(b - 2 * TPW);
+            const uint32_t u2l = b[2 * TPW - 1], u2r = b[2 * TPW + 2], d2l = b[-2 * TPW - 1], d2r = b[-2 * TPW + 2];
             {
-                const uint32_t* b = tbase + (act ? r * TPW + 2 * k : 0);
-                const uint2 c = *reinterpret_cast<const uint2*>(b);
-                const uint2 lf = *reinterpret_cast<const uint2*>(b - 2), rt = *reinterpret_cast<const uint2*>(b + 2);
-                const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
-                const uint2 u2 = *reinterpret_cast<const uint2*>(b + 2 * TPW), d2 = *reinterpret_cast<const uint2*>(b - 2 * TPW);
-                const uint32_t u2l = b[2 * TPW - 1], u2r = b[2 * TPW + 2], d2l = b[-2 * TPW - 1], d2r = b[-2 * TPW + 2];
-                {
-                    const uint32_t R4 = FAST_PAIR(c.y, rt.x), R12 = FAST_PAIR(lf.x, lf.y);
-                    const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4, R12), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
-                    const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.x, dn.x), __vminu2(R4, R12), __vminu2(u2.y, d2l)), __vminu2(d2.y, u2l));
-                    passA = act && ((((c.x + TK) - mb) & ((md + TK) - c.x) & 0x80008000u) != 0x80008000u);
-                }
-                {
-                    const uint32_t R4 = FAST_PAIR(rt.x, rt.y), R12 = FAST_PAIR(lf.y, c.x);
-                    const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.y, dn.y), __vmaxu2(R4, R12), __vmaxu2(u2r, d2.x)), __vmaxu2(d2r, u2.x));
-                    const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.y, dn.y), __vminu2(R4, R12), __vminu2(u2r, d2.x)), __vminu2(d2r, u2.x));
-                    passB = act && ((((c.y + TK) - mb) & ((md + TK) - c.y) & 0x80008000u) != 0x80008000u);
-                }
+                const uint32_t R4 = FAST_PAIR(c.y, rt.x), R12 = FAST_PAIR(lf.x, lf.y);
+                const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4, R12), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
+                const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.x, dn.x), __vminu2(R4, R12), __vminu2(u2.y, d2l)), __vminu2(d2.y, u2l));
+                passA = act && ((((c.x + TK) - mb) & ((md + TK) - c.x) & 0x80008000u) != 0x80008000u);
+            }
+            {
+                const uint32_t R4 = FAST_PAIR(rt.x, rt.y), R12 = FAST_PAIR(lf.y, c.x);
+                const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.y, dn.y), __vmaxu2(R4, R12), __vmaxu2(u2r, d2.x)), __vmaxu2(d2r, u2.x));
+                const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.y, dn.y), __vminu2(R4, R12), __vminu2(u2r, d2.x)), __vminu2(d2r, u2.x));
+                passB = act && ((((c.y + TK) - mb) & ((md + TK) - c.y) & 0x80008000u) != 0x80008000u);
             }
             const unsigned balA = __ballot_sync(FULL, passA), balB = __ballot_sync(FULL, passB);
-            if (passA) queue[nq + __popc(balA & ltmask)] = (uint16_t)(r * 64 + 2 * k);
+            if (passA) queue[nq + __popc(balA & ltmask)] = (uint16_t)entry;
             nq += __popc(balA);
-            if (passB) queue[nq + __popc(balB & ltmask)] = (uint16_t)(r * 64 + 2 * k + 1);
+            if (passB) queue[nq + __popc(balB & ltmask)] = (uint16_t)(entry + 1);
             nq += __popc(balB);
-            k += stepK; r += stepR;
-            if (r >= dh) { r -= dh; k++; }
+        };
+        // rows 0 .. 31: lane = row, one quad column per step.  Consecutive lanes = consecutive rows of the same column: with a
+        // row pitch of TPW = 26 (or 38) words, sixteen consecutive rows start in sixteen different even banks, so the 8-byte
+        // loads of a half-warp touch all 32 banks once; and there is no index arithmetic left in the loop
+        {
+            const bool act = lane < dh;
+            const uint32_t* b = tbase + (act ? lane * TPW : 0);
+            int entry = lane * 64;
+#pragma unroll 1
+            for (int k = 0; k < nquad; k++, b += 2, entry += 2) test_quad(b, act, entry);
+        }
+        // rows 32 .. dh - 1 (cells taller than 32 detection rows): lanes run over (row, quad column)
+        const int tail = (dh - 32) * nquad;
+#pragma unroll 1
+        for (int idx = lane; idx - lane < tail; idx += 32) {
+            const bool act = idx < tail;
+            const int rr = act ? idx / nquad : 0, k = act ? idx - rr * nquad : 0;
+            test_quad(tbase + (32 + rr) * TPW + 2 * k, act, (32 + rr) * 64 + 2 * k);
         }
     }
     __syncwarp();
