@@ -613,14 +613,10 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
 
     int nq = 0;
     {
-        // one quad (2 pairs, 4 centre pixels) per lane and step: 11 shared loads, 24 packed min/max, two sign tests
-        auto test_quad = [&](const uint32_t* b, bool act, int entry) {
+        // one quad (2 pairs, 4 centre pixels) per lane and step: 24 packed min/max and two sign tests on eleven tile words
+        auto eval_quad = [&](const uint2 c, const uint2 lf, const uint2 rt, const uint2 up, const uint2 dn, const uint2 u2, const uint2 d2,
+                             const uint32_t u2l, const uint32_t u2r, const uint32_t d2l, const uint32_t d2r, bool act, int entry) {
             bool passA, passB;
-            const uint2 c = *reinterpret_cast<const uint2*>(b);
-            const uint2 lf = *reinterpret_cast<const uint2*>(b - 2), rt = *reinterpret_cast<const uint2*>(b + 2);
-            const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
-            const uint2 u2 = *reinterpret_cast<const uint2*>(b + 2 * TPW), d2 = *reinterpret_cast<const uint2*>(b - 2 * TPW);
-            const uint32_t u2l = b[2 * TPW - 1], u2r = b[2 * TPW + 2], d2l = b[-2 * TPW - 1], d2r = b[-2 * TPW + 2];
             {
                 const uint32_t R4 = FAST_PAIR(c.y, rt.x), R12 = FAST_PAIR(lf.x, lf.y);
                 const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4, R12), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
@@ -639,16 +635,34 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
             if (passB) queue[nq + __popc(balB & ltmask)] = (uint16_t)(entry + 1);
             nq += __popc(balB);
         };
-        // rows 0 .. 31: lane = row, one quad column per step.  Consecutive lanes = consecutive rows of the same column: with a
-        // row pitch of TPW = 26 (or 38) words, sixteen consecutive rows start in sixteen different even banks, so the 8-byte
-        // loads of a half-warp touch all 32 banks once; and there is no index arithmetic left in the loop
+        // Rows 0 .. 31: lane = row, one quad column per step, walking right.  Consecutive lanes = consecutive rows of the same
+        // column: with a row pitch of TPW = 26 (or 38) words sixteen consecutive rows start in sixteen different even banks, so
+        // the 8-byte loads of a half-warp touch all 32 banks once.  The kernel is bound by shared-memory wavefronts (ncu r2d:
+        // LSU data pipe 93 %), so the walk keeps what the next quad needs in registers: its left neighbours are this quad's
+        // centres, its centres this quad's right neighbours, and on rows +-2 the word pair loaded ahead for the right diagonal
+        // becomes the next quad's own pair -- five 8-byte loads per step instead of seven plus four 4-byte ones.
         {
             const bool act = lane < dh;
             const uint32_t* b = tbase + (act ? lane * TPW : 0);
             int entry = lane * 64;
+            uint2 lf = *reinterpret_cast<const uint2*>(b - 2), c = *reinterpret_cast<const uint2*>(b);
+            uint2 u2 = *reinterpret_cast<const uint2*>(b + 2 * TPW), d2 = *reinterpret_cast<const uint2*>(b - 2 * TPW);
+            uint32_t u2l = b[2 * TPW - 1], d2l = b[-2 * TPW - 1];
 #pragma unroll 1
-            for (int k = 0; k < nquad; k++, b += 2, entry += 2) test_quad(b, act, entry);
+            for (int k = 0; k < nquad; k++, b += 2, entry += 2) {
+                const uint2 rt = *reinterpret_cast<const uint2*>(b + 2);
+                const uint2 u2n = *reinterpret_cast<const uint2*>(b + 2 * TPW + 2), d2n = *reinterpret_cast<const uint2*>(b - 2 * TPW + 2);
+                const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
+                eval_quad(c, lf, rt, up, dn, u2, d2, u2l, u2n.x, d2l, d2n.x, act, entry);
+                lf = c; c = rt; u2l = u2.y; d2l = d2.y; u2 = u2n; d2 = d2n;
+            }
         }
+        auto test_quad = [&](const uint32_t* b, bool act, int entry) {
+            eval_quad(*reinterpret_cast<const uint2*>(b), *reinterpret_cast<const uint2*>(b - 2), *reinterpret_cast<const uint2*>(b + 2),
+                      *reinterpret_cast<const uint2*>(b + 3 * TPW), *reinterpret_cast<const uint2*>(b - 3 * TPW),
+                      *reinterpret_cast<const uint2*>(b + 2 * TPW), *reinterpret_cast<const uint2*>(b - 2 * TPW),
+                      b[2 * TPW - 1], b[2 * TPW + 2], b[-2 * TPW - 1], b[-2 * TPW + 2], act, entry);
+        };
         // rows 32 .. dh - 1 (cells taller than 32 detection rows): lanes run over (row, quad column)
         const int tail = (dh - 32) * nquad;
 #pragma unroll 1
