@@ -613,23 +613,24 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
 
     int nq = 0;
     {
-        // one quad (2 pairs, 4 centre pixels) per lane and step: 24 packed min/max and two sign tests on eleven tile words
-        auto eval_quad = [&](const uint2 c, const uint2 lf, const uint2 rt, const uint2 up, const uint2 dn, const uint2 u2, const uint2 d2,
-                             const uint32_t u2l, const uint32_t u2r, const uint32_t d2l, const uint32_t d2r, bool act, int entry) {
+        // one quad (2 pairs, 4 centre pixels) per lane and step: 24 packed min/max and two sign tests.  R4a .. R12b are the
+        // horizontal ring pairs (x+3, x+4) and (x-3, x-2) of the quad's two centre pairs.  `live` masks the lanes that hold a row:
+        // the others compute on row 0 and are dropped from the ballots (their queue writes land behind the valid entries)
+        auto eval_quad = [&](const uint2 c, const uint32_t R4a, const uint32_t R12a, const uint32_t R4b, const uint32_t R12b,
+                             const uint2 up, const uint2 dn, const uint2 u2, const uint2 d2,
+                             const uint32_t u2l, const uint32_t u2r, const uint32_t d2l, const uint32_t d2r, unsigned live, int entry) {
             bool passA, passB;
             {
-                const uint32_t R4 = FAST_PAIR(c.y, rt.x), R12 = FAST_PAIR(lf.x, lf.y);
-                const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4, R12), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
-                const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.x, dn.x), __vminu2(R4, R12), __vminu2(u2.y, d2l)), __vminu2(d2.y, u2l));
-                passA = act && ((((c.x + TK) - mb) & ((md + TK) - c.x) & 0x80008000u) != 0x80008000u);
+                const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.x, dn.x), __vmaxu2(R4a, R12a), __vmaxu2(u2.y, d2l)), __vmaxu2(d2.y, u2l));
+                const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.x, dn.x), __vminu2(R4a, R12a), __vminu2(u2.y, d2l)), __vminu2(d2.y, u2l));
+                passA = (((c.x + TK) - mb) & ((md + TK) - c.x) & 0x80008000u) != 0x80008000u;
             }
             {
-                const uint32_t R4 = FAST_PAIR(rt.x, rt.y), R12 = FAST_PAIR(lf.y, c.x);
-                const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.y, dn.y), __vmaxu2(R4, R12), __vmaxu2(u2r, d2.x)), __vmaxu2(d2r, u2.x));
-                const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.y, dn.y), __vminu2(R4, R12), __vminu2(u2r, d2.x)), __vminu2(d2r, u2.x));
-                passB = act && ((((c.y + TK) - mb) & ((md + TK) - c.y) & 0x80008000u) != 0x80008000u);
+                const uint32_t mb = __vminu2(__vimin3_u16x2(__vmaxu2(up.y, dn.y), __vmaxu2(R4b, R12b), __vmaxu2(u2r, d2.x)), __vmaxu2(d2r, u2.x));
+                const uint32_t md = __vmaxu2(__vimax3_u16x2(__vminu2(up.y, dn.y), __vminu2(R4b, R12b), __vminu2(u2r, d2.x)), __vminu2(d2r, u2.x));
+                passB = (((c.y + TK) - mb) & ((md + TK) - c.y) & 0x80008000u) != 0x80008000u;
             }
-            const unsigned balA = __ballot_sync(FULL, passA), balB = __ballot_sync(FULL, passB);
+            const unsigned balA = __ballot_sync(FULL, passA) & live, balB = __ballot_sync(FULL, passB) & live;
             if (passA) queue[nq + __popc(balA & ltmask)] = (uint16_t)entry;
             nq += __popc(balA);
             if (passB) queue[nq + __popc(balB & ltmask)] = (uint16_t)(entry + 1);
@@ -637,31 +638,35 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
         };
         // Rows 0 .. 31: lane = row, one quad column per step, walking right.  Consecutive lanes = consecutive rows of the same
         // column: with a row pitch of TPW = 26 (or 38) words sixteen consecutive rows start in sixteen different even banks, so
-        // the 8-byte loads of a half-warp touch all 32 banks once.  The kernel is bound by shared-memory wavefronts (ncu r2d:
-        // LSU data pipe 93 %), so the walk keeps what the next quad needs in registers: its left neighbours are this quad's
-        // centres, its centres this quad's right neighbours, and on rows +-2 the word pair loaded ahead for the right diagonal
-        // becomes the next quad's own pair -- five 8-byte loads per step instead of seven plus four 4-byte ones.
+        // the 8-byte loads of a half-warp touch all 32 banks once.  The walk keeps what the next quad needs in registers: its
+        // centres are this quad's right neighbours, two of its four horizontal ring pairs were cut (PRMT) for earlier quads, and
+        // on rows +-2 the word pair loaded ahead for the right diagonal becomes the next quad's own pair -- five 8-byte loads
+        // and two PRMT per step instead of seven loads plus four 4-byte ones and four PRMT.
         {
-            const bool act = lane < dh;
-            const uint32_t* b = tbase + (act ? lane * TPW : 0);
+            const unsigned live = dh >= 32 ? FULL : (1u << dh) - 1;
+            const uint32_t* b = tbase + (lane < dh ? lane * TPW : 0);
             int entry = lane * 64;
-            uint2 lf = *reinterpret_cast<const uint2*>(b - 2), c = *reinterpret_cast<const uint2*>(b);
+            uint2 c = *reinterpret_cast<const uint2*>(b);
             uint2 u2 = *reinterpret_cast<const uint2*>(b + 2 * TPW), d2 = *reinterpret_cast<const uint2*>(b - 2 * TPW);
             uint32_t u2l = b[2 * TPW - 1], d2l = b[-2 * TPW - 1];
-#pragma unroll 1
+            uint32_t R12a = FAST_PAIR(b[-2], b[-1]), R12b = FAST_PAIR(b[-1], c.x), Pcc = FAST_PAIR(c.x, c.y);   // Pcc: the next quad's R12a
+#pragma unroll 2
             for (int k = 0; k < nquad; k++, b += 2, entry += 2) {
                 const uint2 rt = *reinterpret_cast<const uint2*>(b + 2);
                 const uint2 u2n = *reinterpret_cast<const uint2*>(b + 2 * TPW + 2), d2n = *reinterpret_cast<const uint2*>(b - 2 * TPW + 2);
                 const uint2 up = *reinterpret_cast<const uint2*>(b + 3 * TPW), dn = *reinterpret_cast<const uint2*>(b - 3 * TPW);
-                eval_quad(c, lf, rt, up, dn, u2, d2, u2l, u2n.x, d2l, d2n.x, act, entry);
-                lf = c; c = rt; u2l = u2.y; d2l = d2.y; u2 = u2n; d2 = d2n;
+                const uint32_t R4a = FAST_PAIR(c.y, rt.x), R4b = FAST_PAIR(rt.x, rt.y);
+                eval_quad(c, R4a, R12a, R4b, R12b, up, dn, u2, d2, u2l, u2n.x, d2l, d2n.x, live, entry);
+                R12a = Pcc; R12b = R4a; Pcc = R4b;
+                c = rt; u2l = u2.y; d2l = d2.y; u2 = u2n; d2 = d2n;
             }
         }
         auto test_quad = [&](const uint32_t* b, bool act, int entry) {
-            eval_quad(*reinterpret_cast<const uint2*>(b), *reinterpret_cast<const uint2*>(b - 2), *reinterpret_cast<const uint2*>(b + 2),
+            const uint2 c = *reinterpret_cast<const uint2*>(b), lf = *reinterpret_cast<const uint2*>(b - 2), rt = *reinterpret_cast<const uint2*>(b + 2);
+            eval_quad(c, FAST_PAIR(c.y, rt.x), FAST_PAIR(lf.x, lf.y), FAST_PAIR(rt.x, rt.y), FAST_PAIR(lf.y, c.x),
                       *reinterpret_cast<const uint2*>(b + 3 * TPW), *reinterpret_cast<const uint2*>(b - 3 * TPW),
                       *reinterpret_cast<const uint2*>(b + 2 * TPW), *reinterpret_cast<const uint2*>(b - 2 * TPW),
-                      b[2 * TPW - 1], b[2 * TPW + 2], b[-2 * TPW - 1], b[-2 * TPW + 2], act, entry);
+                      b[2 * TPW - 1], b[2 * TPW + 2], b[-2 * TPW - 1], b[-2 * TPW + 2], __ballot_sync(FULL, act), entry);
         };
         // rows 32 .. dh - 1 (cells taller than 32 detection rows): lanes run over (row, quad column)
         const int tail = (dh - 32) * nquad;
