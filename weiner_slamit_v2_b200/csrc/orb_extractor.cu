@@ -1422,6 +1422,135 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParam
     }
 }
 
+// ---- k_describe, second generation ------------------------------------------------------------------------------------
+// Same arithmetic, different data path (ncu r2i: the first version was bound by L1 wavefronts, 79 %, because every one of the
+// 16 byte gathers of a lane is its own sector, and by the conversion pipe, 58 %, for int -> float of the pattern and
+// float -> int of the rotated coordinates):
+//  * each warp's two 37-row patches -- the unblurred level around the keypoint for IC_Angle, the blurred one for BRIEF --
+//    arrive as two 3-D TMA tensor copies (64 bytes x 37 rows, box start on the 16-byte boundary left of x - 18) into the
+//    warp's own shared memory; the moments and the 512 samples then read shared memory;
+//  * the pattern is stored as floats (no I2F), and cvRound is the magic-constant addition (1.5 * 2^23, round-to-nearest-even
+//    like cvRound, exact because the value is already a float far below 2^22): no F2I either;
+//  * grid = (slot, level, frame): no level search.
+struct DescMaps { CUtensorMap u[MAXL], b[MAXL]; };      // unblurred / blurred levels, box 64 x DESC_ROWS x 1
+constexpr int DESC_ROWS = 37, DESC_BOXW = 64, DESC_HALF = 18;
+constexpr int DESC_PATCH = (DESC_ROWS * DESC_BOXW + 127) / 128 * 128;   // bytes per patch slot (TMA destinations are 128-byte aligned)
+constexpr int DESC_WARP_BYTES = 2 * DESC_PATCH + 128;    // two patches + the warp's mbarrier
+
+struct PatternTableF { float2 v[512]; };
+constexpr PatternTableF make_pattern_table_f()
+{
+    PatternTableF t{};
+    for (int i = 0; i < 512; i++) {
+        const int byte = i >> 4, k = i & 15;
+        t.v[k * 32 + byte].x = (float)PATTERN_SRC[2 * i];
+        t.v[k * 32 + byte].y = (float)PATTERN_SRC[2 * i + 1];
+    }
+    return t;
+}
+__device__ const PatternTableF d_pattern_f = make_pattern_table_f();
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe2(const __grid_constant__ ExtractParams P, const __grid_constant__ DescMaps M)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.z, l = blockIdx.y;
+    const LevelGeo& g = P.lv[l];
+    const int i = blockIdx.x * DESC_WARPS + warp;           // slot of level l
+    // lane q holds level q's keypoint count: the slot's output offset and the frame total are two warp sums
+    const int cnt = lane < P.nlevels ? __ldg(P.lkpCount + frame * P.nlevels + lane) : 0;
+    const int off = __reduce_add_sync(0xffffffffu, lane < l ? cnt : 0);
+    if (l == 0 && i == 0) {                     // slot 0 of level 0 publishes the frame total (also when level 0 is empty)
+        const int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) P.outCount[frame] = tot;
+    }
+    if (i >= __shfl_sync(0xffffffffu, cnt, l)) return;
+    const int o = off + i;
+    if (o >= P.outCap) { if (lane == 0) atomicOr(P.status, STATUS_KP_OVERFLOW); return; }
+
+    const uint32_t e = __ldg(P.lkp + (long long)frame * P.kpFrameCap + g.kpOff + i);
+    const int x = (e & 0xfff) + BORDER, y = ((e >> 12) & 0xfff) + BORDER, score = e >> 24;   // :857-858
+
+    uint8_t* pu = smem + (size_t)warp * DESC_WARP_BYTES;    // unblurred patch, rows y - 18 .. y + 18
+    uint8_t* pb = pu + DESC_PATCH;                          // blurred patch
+    const uint32_t bar = smem_u32(pu + 2 * DESC_PATCH);
+    const int xs = (x - DESC_HALF) & ~15, cx = x - xs;      // box start column; the keypoint's column inside the box (18 .. 33)
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * DESC_ROWS * DESC_BOXW)) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(pu)), "l"(reinterpret_cast<uint64_t>(&M.u[l])), "r"(bar), "r"(xs), "r"(y - DESC_HALF),
+                       "r"((l == 0 ? 0 : P.frameBase) + frame) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(pb)), "l"(reinterpret_cast<uint64_t>(&M.b[l])), "r"(bar), "r"(xs), "r"(y - DESC_HALF),
+                       "r"(P.frameBase + frame) : "memory");
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    // ---- orientation: intensity centroid over the radius-15 disc of the UNBLURRED level (weights: see d_angle) ----
+    int m10 = 0, m01 = 0;
+    {
+        // columns x - 16 .. x + 15 = box bytes cx - 16 .. cx + 15; lane owns word j = lane & 7 of row v = -15 + 4 * it + (lane >> 3)
+        const int b0 = cx - 16, sh = (b0 & 3) * 8;
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(pu + (DESC_HALF - HALF_PATCH + (lane >> 3)) * DESC_BOXW) + (b0 >> 2) + (lane & 7);
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const uint2 w = __ldg(&d_angle.w[it][lane]);
+            if (it < 7 || lane < 24) {                             // the last step holds rows 13, 14, 15 only
+                const uint32_t px = __funnelshift_r(p[0], p[1], sh);
+                m10 = dp4a_u8s8(px, w.x, m10);
+                m01 = dp4a_u8s8(px, w.y, m01);
+            }
+            p += 4 * DESC_BOXW / 4;
+        }
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- descriptor on the BLURRED level: lane b produces byte b (pairs 8b..8b+7) ----
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+    float a, b;
+    libm_sincosf(__fmul_rn(angle, factorPI), b, a);
+    // cvRound(v) = bits(v + 1.5 * 2^23) - 0x4B400000 (round to nearest even, |v| < 2^22).  The sample's shared-memory address is
+    // base + ry * 64 + rx in 32-bit arithmetic that wraps, so the two constants are folded into the base once
+    const float MAGIC = 12582912.0f;
+    const uint32_t cb = smem_u32(pb) + DESC_HALF * DESC_BOXW + cx - 0x4B400000u * (uint32_t)(DESC_BOXW + 1);
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t t[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const float2 pt = __ldg(&d_pattern_f.v[(2 * k + s) * 32 + lane]);
+            const uint32_t ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), MAGIC));
+            const uint32_t rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), MAGIC));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[s]) : "r"(cb + ry * (uint32_t)DESC_BOXW + rx));
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    P.outDesc[((long long)frame * P.outCap + o) * 32 + lane] = (uint8_t)val;
+
+    // ---- keypoint record (cv::KeyPoint layout), coordinates scaled to level 0 (:1126-1132) ----
+    if (lane < 7) {
+        float fx = (float)x, fy = (float)y;
+        if (l != 0) { fx = __fmul_rn(fx, g.scale); fy = __fmul_rn(fy, g.scale); }
+        uint32_t w;
+        switch (lane) {
+            case 0: w = __float_as_uint(fx); break;
+            case 1: w = __float_as_uint(fy); break;
+            case 2: w = __float_as_uint(g.kpSize); break;
+            case 3: w = __float_as_uint(angle); break;
+            case 4: w = __float_as_uint((float)score); break;
+            case 5: w = (uint32_t)l; break;
+            default: w = 0xffffffffu; break;
+        }
+        reinterpret_cast<uint32_t*>(P.outKp + (long long)frame * P.outCap + o)[lane] = w;
+    }
+}
+
 }  // namespace orbb200
 
 // ======================================================================================
@@ -1442,6 +1571,8 @@ struct orbb200_extractor {
     size_t fastSmem, qtSmem;
     int fastVariant;           // 2 = k_fast2 (TMA tensor staging, default), 1 = k_fast (ORBB200_FAST_VARIANT=1: the first-generation kernel, kept for A/B runs)
     FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
+    DescMaps descMaps;         // k_describe2's patch maps of the unblurred and the blurred levels (box 64 x 37)
+    int descVariant, maxLevelKpCap;   // 2 = k_describe2 (default), 1 = k_describe (ORBB200_DESCRIBE_VARIANT=1, kept for A/B runs)
     int lastLaunches, lastBatch;
     int realCandCap[MAXL];     // per-level candidate capacity as computed at create (orbb200_extractor_debug_set_capacity clamps P.lv[l].candCap)
     int chunkOverride;         // ORBB200_CHUNKS read once at create (0 = choose by batch size): tuning knob of the blocking host call
@@ -1704,6 +1835,14 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     int4* dCells = nullptr;
     TRY(dev_alloc(h, &dCells, cellTab.size() + 1));
     P.cells = dCells;
+    h->descVariant = 2;
+    if (const char* ev = getenv("ORBB200_DESCRIBE_VARIANT")) h->descVariant = atoi(ev) == 1 ? 1 : 2;
+    h->maxLevelKpCap = 0;
+    for (int l = 0; l < nlevels; l++) h->maxLevelKpCap = std::max(h->maxLevelKpCap, P.lv[l].kpCap);
+    for (int l = 0; l < nlevels && h->descVariant == 2; l++) {
+        if (l > 0) TRY(encode_level_map(&h->descMaps.u[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes, DESC_BOXW, DESC_ROWS));
+        TRY(encode_level_map(&h->descMaps.b[l], P.blur + P.lv[l].blurOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.blurFrameBytes, DESC_BOXW, DESC_ROWS));
+    }
     for (int l = 1; l < nlevels && h->fastVariant == 2; l++)      // levels >= 1 live in the handle's pyramid slab: maps made once
         TRY(encode_level_map(&h->fastMaps.m[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes,
                              P.fastLarge ? FastGeo2<38, 64>::BW : FastGeo2<26, 42>::BW, P.fastLarge ? 64 : 42));
@@ -1726,6 +1865,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     }
     if (e == cudaSuccess && h->fastVariant == 1) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->fastVariant == 2) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast2<38, 64> : (const void*)k_fast2<26, 42>, device, h->fastSmem);
+    if (e == cudaSuccess && h->descVariant == 2) e = ensure_dynamic_smem((const void*)k_describe2, device, DESC_WARPS * DESC_WARP_BYTES);
     if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)k_quadtree, device, h->qtSmem);
     if (e == cudaSuccess) e = ensure_dynamic_smem(P.blurVariant ? (const void*)k_blur<true> : (const void*)k_blur<false>, device, BL_WARPS * BL_WARP_BYTES);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
@@ -1873,6 +2013,11 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
         ORB_CUDA(cudaStreamWaitEvent(st, h->evJoin, 0));
     }
     STAGE_MARK(4);
+    if (h->descVariant == 2) {
+        int rc = encode_level_map(&h->descMaps.u[0], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, DESC_BOXW, DESC_ROWS);
+        if (rc != ORBB200_OK) return rc;
+        k_describe2<<<dim3((h->maxLevelKpCap + DESC_WARPS - 1) / DESC_WARPS, P.nlevels, batch), DESC_WARPS * 32, DESC_WARPS * DESC_WARP_BYTES, st>>>(P, h->descMaps);
+    } else
     k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_describe"); launches++;
     STAGE_MARK(5);
