@@ -409,6 +409,29 @@ def run_ours(args):
     sx.close()
     if not stream_ok:
         raise SystemExit("bench.py: streamed results differ from the synchronous call")
+    # the host's copy ceiling in the same run: every rank uploads its step's frames and downloads its step's results from / to
+    # the same page-locked buffers, concurrently, with no kernels in between (profiles/r2_pcie_aggregate.json has the full probe)
+    def copy_ceiling(seconds=0.6):
+        d_in = torch.empty((BATCH, HEIGHT, WIDTH), dtype=torch.uint8, device="cuda")
+        d_k = torch.empty((BATCH, cap, 28), dtype=torch.uint8, device="cuda"); d_d = torch.empty((BATCH, cap, 32), dtype=torch.uint8, device="cuda")
+        su, sd = torch.cuda.Stream(), torch.cuda.Stream()
+        def once():
+            with torch.cuda.stream(su):
+                d_in.copy_(pinned, non_blocking=True)
+            with torch.cuda.stream(sd):
+                out_k.copy_(d_k, non_blocking=True); out_d.copy_(d_d, non_blocking=True)
+        for _ in range(2):
+            once()
+        barrier()
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < seconds:
+            once(); once()
+            su.synchronize(); sd.synchronize()
+            n += 2
+        dt = time.perf_counter() - t0
+        barrier()
+        return n * BATCH / dt
+    ceiling_fps = copy_ceiling()
     # single-frame latency of the drop-in call (what Frame::ExtractORB sees): batch 1, host buffers
     ex1 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=WIDTH, height=HEIGHT, max_batch=1, device=local)
     for _ in range(5):
@@ -420,12 +443,12 @@ def run_ours(args):
     ex1.close()
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_sync_s * 1e3], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(nkp)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(nkp), ceiling_fps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks (device-timed)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)    # the path's only "collective": a count gather
     dev_ms_max, e2e_ms_max, e2e_sync_ms_max = t.tolist()
-    nkp_all = int(tot.item())
+    nkp_all, ceiling_all = int(tot[0].item()), float(tot[1].item())
 
     # free the VGA handles before the other workloads of the line allocate theirs
     parity_in = (outs[0][0].numpy()[:8].copy(), outs[0][1].numpy()[:8].copy(), outs[0][2].numpy()[:8].copy())
@@ -475,6 +498,9 @@ def run_ours(args):
                     "keypoints_per_step": nkp_all,
                     "api": "StreamingExtractor (orbb200_extract_host_async, %d handles in turn)" % depth,
                     "blocking_call_value": frames_total / (e2e_sync_ms_max * 1e-3),
+                    "host_copy_ceiling": {"value": ceiling_all, "unit": "frames/s", "frac": e2e / ceiling_all,
+                                          "how": "the same uploads (pinned frames) and downloads (keypoints + descriptors) by all ranks at once "
+                                                 "with no kernels in between, summed over ranks: what this host's PCIe paths deliver"},
                     "single_frame_latency_ms": latency_ms},
             "gpu_launches": launches,
             "kernel_ms_per_step": {s: float(per_stage[i]) for i, s in enumerate(STAGES)},
