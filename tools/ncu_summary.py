@@ -7,7 +7,8 @@ writes <prefix>_ncu_full_summary.json (per-launch: time, issue-slot use, occupan
 import csv, io, json, os, subprocess, sys
 
 rep, prefix = sys.argv[1], sys.argv[2]
-STAGE = {"k_resize": "pyramid", "k_fast": "fast", "k_quadtree": "quadtree", "k_blur": "blur", "k_describe": "describe"}
+STAGE = {"k_resize": "pyramid", "k_fast": "fast", "k_fast2": "fast", "k_quadtree": "quadtree", "k_blur": "blur", "k_describe": "describe",
+         "k_describe2": "describe"}
 M = {"time_us": "gpu__time_duration.sum", "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
      "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active", "dram_read_MB": "dram__bytes_read.sum",
      "dram_write_MB": "dram__bytes_write.sum", "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -19,6 +20,8 @@ M = {"time_us": "gpu__time_duration.sum", "issue_active_pct": "smsp__issue_activ
      "alu_pipe_pct": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
      "xu_pipe_pct": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
      "shared_mem_pipe_pct": "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+     "lsu_data_pipe_pct": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+     "fma_pipe_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
      "regs": "launch__registers_per_thread", "smem_per_block": "launch__shared_mem_per_block_dynamic",
      "inst_executed": "smsp__inst_executed.sum"}
 
@@ -50,7 +53,7 @@ for r in rows[2:]:
 json.dump(out, open(prefix + "_ncu_full_summary.json", "w"), indent=1)
 json.dump(traffic, open(os.path.join(os.path.dirname(prefix), "traffic.json"), "w"), indent=1)
 
-for kern in ("k_fast", "k_describe", "k_blur", "k_resize", "k_quadtree"):
+for kern in ("k_fast2", "k_describe2", "k_blur", "k_resize", "k_quadtree"):
     rows = list(csv.reader(io.StringIO(ncu("--page", "source", "--print-source", "cuda,sass", "--csv", "-k", "regex:" + kern))))
     acc, tot, smp = {}, 0, 0
     for r in rows:
