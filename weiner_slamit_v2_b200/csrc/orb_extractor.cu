@@ -81,6 +81,7 @@ struct ExtractParams {
     int blurVariant;
     // k_fast shared-memory geometry
     int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <38,64> instantiation
+    const uint32_t* blurTiles;                       // k_blur tile table: level << 24 | tile row << 12 | tile column
     const int4* cells;                               // k_fast cell table (one entry per detection cell that exists, level-major)
     int nCells, frameBase;                           // entries; index of the batch's first frame inside the handle's slabs
     // k_quadtree shared-memory geometry
@@ -1076,18 +1077,15 @@ __device__ __forceinline__ int reflect101(int p, int n)
 
 struct BlurTile { int l, frame, x0, y0; };
 
-// tile index -> (frame, level, position); false when the level has no keypoints (skipped like :1112)
-__device__ __forceinline__ bool blur_tile(const ExtractParams& P, long long t, BlurTile& bt)
+// tile index -> (frame, level, position); false when the level has no keypoints (skipped like :1112).  The per-frame tile
+// list is a table built at create (level << 24 | tile row << 12 | tile column).
+__device__ __forceinline__ bool blur_tile(const ExtractParams& P, unsigned t, BlurTile& bt)
 {
-    const int frame = (int)(t / P.totalBlurTiles), tile = (int)(t - (long long)frame * P.totalBlurTiles);
-    int l = 0;
-    while (l + 1 < P.nlevels && tile >= P.lv[l + 1].blurTileStart) l++;
-    const LevelGeo& g = P.lv[l];
-    const int q = tile - g.blurTileStart;
-    const int ty = q / g.blurTilesX, tx = q - ty * g.blurTilesX;
-    bt.l = l; bt.frame = frame; bt.x0 = tx * 128; bt.y0 = ty * BL_ROWS;
+    const unsigned frame = t / (unsigned)P.totalBlurTiles, tile = t - frame * (unsigned)P.totalBlurTiles;
+    const uint32_t e = __ldg(P.blurTiles + tile);
+    bt.l = e >> 24; bt.frame = (int)frame; bt.x0 = (e & 0xfff) * 128; bt.y0 = ((e >> 12) & 0xfff) * BL_ROWS;
     // (a level keeps >= 1 keypoint exactly when FAST found >= 1 candidate on it: the test does not wait for the quadtree)
-    return P.candCount[frame * P.nlevels + l] != 0;
+    return P.candCount[frame * P.nlevels + bt.l] != 0;
 }
 
 template <bool VARIANT>     // false: OpenCV >= 3 taps {18,34,48,56,48,34,18}; true: OpenCV 2.4.9 taps {18,34,49,55,49,34,18}
@@ -1104,8 +1102,8 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
     }
     __syncwarp();
 
-    const long long nTiles = (long long)P.totalBlurTiles * P.batch;
-    const long long stride = (long long)gridDim.x * BL_WARPS;
+    const unsigned nTiles = (unsigned)P.totalBlurTiles * (unsigned)P.batch;
+    const unsigned stride = gridDim.x * BL_WARPS;
     constexpr uint32_t k0 = 18, k1 = 34, k2 = VARIANT ? 49 : 48, k3 = VARIANT ? 55 : 56;
     constexpr uint32_t kA = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);     // taps for p[x-3..x]
     constexpr uint32_t kB = k2 | (k1 << 8) | (k0 << 16);                  // taps for p[x+1..x+3]
@@ -1133,7 +1131,7 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
         }
     };
 
-    long long t = (long long)blockIdx.x * BL_WARPS + warp;
+    unsigned t = blockIdx.x * BL_WARPS + warp;
     BlurTile cur, nxt;
     while (t < nTiles && !blur_tile(P, t, cur)) t += stride;
     if (t >= nTiles) return;
@@ -1141,7 +1139,7 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
     int stage = 0;
     uint32_t phase0 = 0, phase1 = 0;
     while (t < nTiles) {
-        long long tn = t + stride;
+        unsigned tn = t + stride;
         while (tn < nTiles && !blur_tile(P, tn, nxt)) tn += stride;
         if (tn < nTiles) issue(nxt, stage ^ 1);
         if (stage == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; } else { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
@@ -1180,22 +1178,22 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
 #pragma unroll
                 for (int u = 0; u < 6; u++) {
                     const int ir = grp * 6 + u;                                      // completes output row ir - 6
-                    if (ir - 6 < nOut) {
-                        hrow(ir, cur4);
-                        uint32_t acc[4];
+                    // (rows past the tile's last output row are still filtered -- their input rows are staged, clamped to the
+                    // image -- and only the store is skipped: straight-line code lets the six-row window rotate by renaming)
+                    hrow(ir, cur4);
+                    uint32_t acc[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            // pairs ending at rows ir-5, ir-3, ir-1 sit in slots (u+1)%6, (u+3)%6, (u+5)%6
-                            acc[j] = __dp2a_lo(Q[(u + 1) % 6][j], kV01, __dp2a_lo(Q[(u + 3) % 6][j], kV23,
-                                     __dp2a_lo(Q[(u + 5) % 6][j], kV45, k0 * cur4[j] + 32768u)));
-                            if (VARIANT) acc[j] = min(acc[j], 0x00ffffffu);          // taps sum to 257: saturate like OpenCV
-                            Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410);
-                            prev[j] = cur4[j];
-                        }
-                        const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
-                        *reinterpret_cast<uint32_t*>(outp) = __byte_perm(lo, hi, 0x5410);
-                        outp += g.pitch;
+                    for (int j = 0; j < 4; j++) {
+                        // pairs ending at rows ir-5, ir-3, ir-1 sit in slots (u+1)%6, (u+3)%6, (u+5)%6
+                        acc[j] = __dp2a_lo(Q[(u + 1) % 6][j], kV01, __dp2a_lo(Q[(u + 3) % 6][j], kV23,
+                                 __dp2a_lo(Q[(u + 5) % 6][j], kV45, k0 * cur4[j] + 32768u)));
+                        if (VARIANT) acc[j] = min(acc[j], 0x00ffffffu);          // taps sum to 257: saturate like OpenCV
+                        Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410);
+                        prev[j] = cur4[j];
                     }
+                    const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
+                    if (ir - 6 < nOut) *reinterpret_cast<uint32_t*>(outp) = __byte_perm(lo, hi, 0x5410);
+                    outp += g.pitch;
                 }
             }
         }
@@ -1835,6 +1833,13 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     int4* dCells = nullptr;
     TRY(dev_alloc(h, &dCells, cellTab.size() + 1));
     P.cells = dCells;
+    std::vector<uint32_t> blurTab;
+    for (int l = 0; l < nlevels; l++)
+        for (int ty = 0; ty < (P.lv[l].h + BL_ROWS - 1) / BL_ROWS; ty++)
+            for (int tx = 0; tx < P.lv[l].blurTilesX; tx++) blurTab.push_back(((uint32_t)l << 24) | ((uint32_t)ty << 12) | (uint32_t)tx);
+    uint32_t* dBlurTiles = nullptr;
+    TRY(dev_alloc(h, &dBlurTiles, blurTab.size() + 1));
+    P.blurTiles = dBlurTiles;
     h->descVariant = 2;
     if (const char* ev = getenv("ORBB200_DESCRIBE_VARIANT")) h->descVariant = atoi(ev) == 1 ? 1 : 2;
     h->maxLevelKpCap = 0;
@@ -1850,6 +1855,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     P.tabs = dTabs;
     cudaError_t e = cudaSuccess;
     if (!cellTab.empty()) e = cudaMemcpy(dCells, cellTab.data(), cellTab.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !blurTab.empty()) e = cudaMemcpy(dBlurTiles, blurTab.data(), blurTab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("extractor_create: %s", cudaGetErrorString(e)); orbb200_extractor_destroy(h); return ORBB200_ECUDA; }
     if (!tabs.empty()) e = cudaMemcpy(dTabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(P.status, 0, sizeof(int));
