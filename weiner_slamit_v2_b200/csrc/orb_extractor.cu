@@ -83,6 +83,7 @@ struct ExtractParams {
     int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <38,64> instantiation
     const uint32_t* blurTiles;                       // k_blur tile table: level << 24 | tile row << 12 | tile column
     const int4* cells;                               // k_fast cell table (one entry per detection cell that exists, level-major)
+    int descChunk;                                   // k_describe2: consecutive output rows a warp takes at a time (power of two)
     int nCells, frameBase;                           // entries; index of the batch's first frame inside the handle's slabs
     // k_quadtree shared-memory geometry
     int qtNC, qtPC;
@@ -1423,17 +1424,20 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParam
 // ---- k_describe, second generation ------------------------------------------------------------------------------------
 // Same arithmetic, different data path (ncu r2i: the first version was bound by L1 wavefronts, 79 %, because every one of the
 // 16 byte gathers of a lane is its own sector, and by the conversion pipe, 58 %, for int -> float of the pattern and
-// float -> int of the rotated coordinates):
-//  * each warp's two 37-row patches -- the unblurred level around the keypoint for IC_Angle, the blurred one for BRIEF --
-//    arrive as two 3-D TMA tensor copies (64 bytes x 37 rows, box start on the 16-byte boundary left of x - 18) into the
-//    warp's own shared memory; the moments and the 512 samples then read shared memory;
-//  * the pattern is stored as floats (no I2F), and cvRound is the magic-constant addition (1.5 * 2^23, round-to-nearest-even
-//    like cvRound, exact because the value is already a float far below 2^22): no F2I either;
-//  * grid = (slot, level, frame): no level search.
-struct DescMaps { CUtensorMap u[MAXL], b[MAXL]; };      // unblurred / blurred levels, box 64 x DESC_ROWS x 1
-constexpr int DESC_ROWS = 37, DESC_BOXW = 64, DESC_HALF = 18;
-constexpr int DESC_PATCH = (DESC_ROWS * DESC_BOXW + 127) / 128 * 128;   // bytes per patch slot (TMA destinations are 128-byte aligned)
-constexpr int DESC_WARP_BYTES = 2 * DESC_PATCH + 128;    // two patches + the warp's mbarrier
+// float -> int of the rotated coordinates; r2k: a one-keypoint-per-warp TMA version waited on its own copy, long scoreboard):
+//  * persistent warps (3 CTAs per SM), each walks one contiguous range of the batch's (frame, output row) slots.  What depends on the lane only
+//    -- its 16 pattern points as floats (no I2F) and its 8 IC_Angle weight words -- is loaded once and stays in registers;
+//  * the keypoint's two patches -- the unblurred level around it for IC_Angle (48 bytes x 31 rows), the blurred one for BRIEF
+//    (64 x 37) -- arrive as two 3-D TMA tensor copies (box start on the 16-byte boundary left of the patch) into one of the
+//    warp's two shared-memory buffers, and the copies of keypoint n + 1 are issued before keypoint n is worked on;
+//  * cvRound is the magic-constant addition (1.5 * 2^23, round-to-nearest-even like cvRound, exact because the value is
+//    already a float far below 2^22): no F2I either.
+struct DescMaps { CUtensorMap u[MAXL], b[MAXL]; };      // unblurred levels: box 48 x 31 x 1; blurred levels: box 64 x 37 x 1
+constexpr int DESC_UW = 48, DESC_UROWS = 2 * HALF_PATCH + 1, DESC_BW = 64, DESC_BROWS = 37, DESC_HALF = 18;
+constexpr int DESC_USLOT = (DESC_UW * DESC_UROWS + 127) / 128 * 128, DESC_BSLOT = (DESC_BW * DESC_BROWS + 127) / 128 * 128;
+constexpr int DESC_BUF = DESC_USLOT + DESC_BSLOT;        // one buffer = both patches of one keypoint (TMA destinations: 128-byte aligned)
+constexpr int DESC_WARP_BYTES = 2 * DESC_BUF + 128;      // two buffers + the warp's two mbarriers
+constexpr int DESC_CTAS_PER_SM = 3;                     // persistent CTAs per SM (registers: 80 x 256; shared memory: 63 KB)
 
 struct PatternTableF { float2 v[512]; };
 constexpr PatternTableF make_pattern_table_f()
@@ -1448,104 +1452,159 @@ constexpr PatternTableF make_pattern_table_f()
 }
 __device__ const PatternTableF d_pattern_f = make_pattern_table_f();
 
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe2(const __grid_constant__ ExtractParams P, const __grid_constant__ DescMaps M)
+__global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe2(const __grid_constant__ ExtractParams P, const __grid_constant__ DescMaps M)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = blockIdx.z, l = blockIdx.y;
-    const LevelGeo& g = P.lv[l];
-    const int i = blockIdx.x * DESC_WARPS + warp;           // slot of level l
-    // lane q holds level q's keypoint count: the slot's output offset and the frame total are two warp sums
-    const int cnt = lane < P.nlevels ? __ldg(P.lkpCount + frame * P.nlevels + lane) : 0;
-    const int off = __reduce_add_sync(0xffffffffu, lane < l ? cnt : 0);
-    if (l == 0 && i == 0) {                     // slot 0 of level 0 publishes the frame total (also when level 0 is empty)
-        const int tot = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) P.outCount[frame] = tot;
-    }
-    if (i >= __shfl_sync(0xffffffffu, cnt, l)) return;
-    const int o = off + i;
-    if (o >= P.outCap) { if (lane == 0) atomicOr(P.status, STATUS_KP_OVERFLOW); return; }
+    // the (frame, output row) slots of the batch in chunks of P.descChunk (4; 1 in small calls, where latency counts), dealt to the warps round robin: at any time the warps
+    // of the grid work inside a window of a few frames (their patches overlap, so they hit L2), and a warp changes frame rarely
+    const int nslots = P.batch * P.outCap, nw = gridDim.x * DESC_WARPS;
+    const int CH = P.descChunk;
+    const int s0 = (blockIdx.x * DESC_WARPS + warp) * CH, s1 = nslots;
+    if (s0 >= s1) return;
 
-    const uint32_t e = __ldg(P.lkp + (long long)frame * P.kpFrameCap + g.kpOff + i);
-    const int x = (e & 0xfff) + BORDER, y = ((e >> 12) & 0xfff) + BORDER, score = e >> 24;   // :857-858
+    // per-lane constants: level tables, the lane's 16 pattern points, its 8 IC_Angle weight words
+    const int kpOffLane = lane < P.nlevels ? P.lv[lane].kpOff : 0;
+    const float scaleLane = lane < P.nlevels ? P.lv[lane].scale : 0.f, sizeLane = lane < P.nlevels ? P.lv[lane].kpSize : 0.f;
+    float2 pat[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) pat[k] = __ldg(&d_pattern_f.v[k * 32 + lane]);
+    uint2 wgt[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) wgt[it] = __ldg(&d_angle.w[it][lane]);
 
-    uint8_t* pu = smem + (size_t)warp * DESC_WARP_BYTES;    // unblurred patch, rows y - 18 .. y + 18
-    uint8_t* pb = pu + DESC_PATCH;                          // blurred patch
-    const uint32_t bar = smem_u32(pu + 2 * DESC_PATCH);
-    const int xs = (x - DESC_HALF) & ~15, cx = x - xs;      // box start column; the keypoint's column inside the box (18 .. 33)
+    uint8_t* buf = smem + (size_t)warp * DESC_WARP_BYTES;
+    const uint32_t bar0 = smem_u32(buf + 2 * DESC_BUF);
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * DESC_ROWS * DESC_BOXW)) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(smem_u32(pu)), "l"(reinterpret_cast<uint64_t>(&M.u[l])), "r"(bar), "r"(xs), "r"(y - DESC_HALF),
-                       "r"((l == 0 ? 0 : P.frameBase) + frame) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(smem_u32(pb)), "l"(reinterpret_cast<uint64_t>(&M.b[l])), "r"(bar), "r"(xs), "r"(y - DESC_HALF),
-                       "r"(P.frameBase + frame) : "memory");
     }
     __syncwarp();
-    mbar_wait(bar, 0);
 
-    // ---- orientation: intensity centroid over the radius-15 disc of the UNBLURRED level (weights: see d_angle) ----
-    int m10 = 0, m01 = 0;
-    {
-        // columns x - 16 .. x + 15 = box bytes cx - 16 .. cx + 15; lane owns word j = lane & 7 of row v = -15 + 4 * it + (lane >> 3)
-        const int b0 = cx - 16, sh = (b0 & 3) * 8;
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(pu + (DESC_HALF - HALF_PATCH + (lane >> 3)) * DESC_BOXW) + (b0 >> 2) + (lane & 7);
+    // iterator over the range's keypoints: slot -> (frame, row o); lane q keeps the frame's count of level q and the number of
+    // keypoints below it.  A frame whose first slot lies in the range gets its total published by this warp (also when it is 0).
+    int itSlot = s0, itFrame = -1, itPre = 0, itTotal = 0;
+    auto next = [&](int& frame, int& o, int& l, uint32_t& e) -> bool {
+        while (itSlot < s1) {
+            const int f = itSlot / P.outCap, oo = itSlot - f * P.outCap;
+            if (f != itFrame) {
+                itFrame = f;
+                const int cnt = lane < P.nlevels ? __ldg(P.lkpCount + f * P.nlevels + lane) : 0;
+                int pre = cnt;
 #pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const uint2 w = __ldg(&d_angle.w[it][lane]);
-            if (it < 7 || lane < 24) {                             // the last step holds rows 13, 14, 15 only
-                const uint32_t px = __funnelshift_r(p[0], p[1], sh);
-                m10 = dp4a_u8s8(px, w.x, m10);
-                m01 = dp4a_u8s8(px, w.y, m01);
+                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += v; }
+                itTotal = min(__shfl_sync(FULL, pre, 31), P.outCap);     // (more cannot happen: outCap = the sum of the level capacities)
+                itPre = pre - cnt;
+                if (oo == 0 && lane == 0) P.outCount[f] = itTotal;
             }
-            p += 4 * DESC_BOXW / 4;
+            if (oo >= itTotal) {                              // past the frame's last keypoint: on to this warp's next chunk
+                const int chunkBeg = itSlot - ((itSlot - s0) & (CH - 1)), nextFrame = (f + 1) * P.outCap;
+                itSlot = nextFrame < chunkBeg + CH ? nextFrame : chunkBeg + nw * CH;      // (a chunk may straddle two frames)
+                continue;
+            }
+            frame = f; o = oo;
+            l = __popc(__ballot_sync(FULL, lane < P.nlevels && itPre <= oo)) - 1;
+            e = __ldg(P.lkp + (long long)f * P.kpFrameCap + __shfl_sync(FULL, kpOffLane, l) + (oo - __shfl_sync(FULL, itPre, l)));
+            itSlot++;
+            if (((itSlot - s0) & (CH - 1)) == 0) itSlot += (nw - 1) * CH;
+            return true;
         }
-    }
-    m10 = __reduce_add_sync(0xffffffffu, m10);
-    m01 = __reduce_add_sync(0xffffffffu, m01);
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
+        return false;
+    };
+    auto issue = [&](int frame, int l, uint32_t e, int s) {
+        const int x = (e & 0xfff) + BORDER, y = ((e >> 12) & 0xfff) + BORDER;
+        const uint32_t bar = bar0 + 8 * s, dst = smem_u32(buf + s * DESC_BUF);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of this buffer are done
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(DESC_UW * DESC_UROWS + DESC_BW * DESC_BROWS)) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&M.u[l])), "r"(bar), "r"((x - 16) & ~15), "r"(y - HALF_PATCH),
+                           "r"((l == 0 ? 0 : P.frameBase) + frame) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(dst + DESC_USLOT), "l"(reinterpret_cast<uint64_t>(&M.b[l])), "r"(bar), "r"((x - DESC_HALF) & ~15), "r"(y - DESC_HALF),
+                           "r"(P.frameBase + frame) : "memory");
+        }
+        __syncwarp();
+    };
 
-    // ---- descriptor on the BLURRED level: lane b produces byte b (pairs 8b..8b+7) ----
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
-    float a, b;
-    libm_sincosf(__fmul_rn(angle, factorPI), b, a);
-    // cvRound(v) = bits(v + 1.5 * 2^23) - 0x4B400000 (round to nearest even, |v| < 2^22).  The sample's shared-memory address is
-    // base + ry * 64 + rx in 32-bit arithmetic that wraps, so the two constants are folded into the base once
-    const float MAGIC = 12582912.0f;
-    const uint32_t cb = smem_u32(pb) + DESC_HALF * DESC_BOXW + cx - 0x4B400000u * (uint32_t)(DESC_BOXW + 1);
-    int val = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        uint32_t t[2];
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const float2 pt = __ldg(&d_pattern_f.v[(2 * k + s) * 32 + lane]);
-            const uint32_t ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), MAGIC));
-            const uint32_t rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), MAGIC));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[s]) : "r"(cb + ry * (uint32_t)DESC_BOXW + rx));
-        }
-        val |= (t[0] < t[1]) << k;
-    }
-    P.outDesc[((long long)frame * P.outCap + o) * 32 + lane] = (uint8_t)val;
+    int frame, o, l, frameN = 0, oN = 0, lN = 0;
+    uint32_t e, eN = 0;
+    bool have = next(frame, o, l, e);
+    if (have) issue(frame, l, e, 0);
+    uint32_t phase = 0;                                     // bit s = parity to wait for on buffer s
+    int s = 0;
+#pragma unroll 1
+    while (have) {
+        const bool more = next(frameN, oN, lN, eN);
+        if (more) issue(frameN, lN, eN, s ^ 1);
+        mbar_wait(bar0 + 8 * s, (phase >> s) & 1);
+        phase ^= 1u << s;
 
-    // ---- keypoint record (cv::KeyPoint layout), coordinates scaled to level 0 (:1126-1132) ----
-    if (lane < 7) {
-        float fx = (float)x, fy = (float)y;
-        if (l != 0) { fx = __fmul_rn(fx, g.scale); fy = __fmul_rn(fy, g.scale); }
-        uint32_t w;
-        switch (lane) {
-            case 0: w = __float_as_uint(fx); break;
-            case 1: w = __float_as_uint(fy); break;
-            case 2: w = __float_as_uint(g.kpSize); break;
-            case 3: w = __float_as_uint(angle); break;
-            case 4: w = __float_as_uint((float)score); break;
-            case 5: w = (uint32_t)l; break;
-            default: w = 0xffffffffu; break;
+        const int x = (e & 0xfff) + BORDER, y = ((e >> 12) & 0xfff) + BORDER, score = e >> 24;   // :857-858
+        const uint8_t* pu = buf + s * DESC_BUF;             // unblurred patch: rows y - 15 .. y + 15, columns from (x - 16) & ~15
+        // ---- orientation: intensity centroid over the radius-15 disc of the UNBLURRED level (weights: see d_angle) ----
+        int m10 = 0, m01 = 0;
+        {
+            // columns x - 16 .. x + 15 = patch bytes b0 .. b0 + 31; lane owns word j = lane & 7 of row v = -15 + 4 * it + (lane >> 3)
+            const int b0 = (x - 16) & 15, sh = (b0 & 3) * 8;
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(pu + (lane >> 3) * DESC_UW) + (b0 >> 2) + (lane & 7);
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                if (it < 7 || lane < 24) {                         // the last step holds rows 13, 14, 15 only
+                    const uint32_t px = __funnelshift_r(p[0], p[1], sh);
+                    m10 = dp4a_u8s8(px, wgt[it].x, m10);
+                    m01 = dp4a_u8s8(px, wgt[it].y, m01);
+                }
+                p += 4 * DESC_UW / 4;
+            }
         }
-        reinterpret_cast<uint32_t*>(P.outKp + (long long)frame * P.outCap + o)[lane] = w;
+        m10 = __reduce_add_sync(FULL, m10);
+        m01 = __reduce_add_sync(FULL, m01);
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        // ---- descriptor on the BLURRED level: lane b produces byte b (pairs 8b..8b+7) ----
+        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+        float a, b;
+        libm_sincosf(__fmul_rn(angle, factorPI), b, a);
+        // cvRound(v) = bits(v + 1.5 * 2^23) - 0x4B400000 (round to nearest even, |v| < 2^22).  The sample's shared-memory address
+        // is base + ry * 64 + rx in 32-bit arithmetic that wraps, so the two constants are folded into the base once
+        const float MAGIC = 12582912.0f;
+        const uint32_t cb = smem_u32(pu + DESC_USLOT) + DESC_HALF * DESC_BW + ((x - DESC_HALF) & 15) + DESC_HALF - 0x4B400000u * (uint32_t)(DESC_BW + 1);
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t t[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float2 pt = pat[2 * k + h];
+                const uint32_t ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), MAGIC));
+                const uint32_t rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), MAGIC));
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[h]) : "r"(cb + ry * (uint32_t)DESC_BW + rx));
+            }
+            val |= (t[0] < t[1]) << k;
+        }
+        P.outDesc[((long long)frame * P.outCap + o) * 32 + lane] = (uint8_t)val;
+
+        // ---- keypoint record (cv::KeyPoint layout), coordinates scaled to level 0 (:1126-1132) ----
+        const float sc = __shfl_sync(FULL, scaleLane, l), ksz = __shfl_sync(FULL, sizeLane, l);
+        if (lane < 7) {
+            float fx = (float)x, fy = (float)y;
+            if (l != 0) { fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); }
+            uint32_t w;
+            switch (lane) {
+                case 0: w = __float_as_uint(fx); break;
+                case 1: w = __float_as_uint(fy); break;
+                case 2: w = __float_as_uint(ksz); break;
+                case 3: w = __float_as_uint(angle); break;
+                case 4: w = __float_as_uint((float)score); break;
+                case 5: w = (uint32_t)l; break;
+                default: w = 0xffffffffu; break;
+            }
+            reinterpret_cast<uint32_t*>(P.outKp + (long long)frame * P.outCap + o)[lane] = w;
+        }
+        have = more; frame = frameN; o = oN; l = lN; e = eN; s ^= 1;
     }
 }
 
@@ -1845,8 +1904,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     h->maxLevelKpCap = 0;
     for (int l = 0; l < nlevels; l++) h->maxLevelKpCap = std::max(h->maxLevelKpCap, P.lv[l].kpCap);
     for (int l = 0; l < nlevels && h->descVariant == 2; l++) {
-        if (l > 0) TRY(encode_level_map(&h->descMaps.u[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes, DESC_BOXW, DESC_ROWS));
-        TRY(encode_level_map(&h->descMaps.b[l], P.blur + P.lv[l].blurOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.blurFrameBytes, DESC_BOXW, DESC_ROWS));
+        if (l > 0) TRY(encode_level_map(&h->descMaps.u[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes, DESC_UW, DESC_UROWS));
+        TRY(encode_level_map(&h->descMaps.b[l], P.blur + P.lv[l].blurOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.blurFrameBytes, DESC_BW, DESC_BROWS));
     }
     for (int l = 1; l < nlevels && h->fastVariant == 2; l++)      // levels >= 1 live in the handle's pyramid slab: maps made once
         TRY(encode_level_map(&h->fastMaps.m[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes,
@@ -2020,9 +2079,13 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
     }
     STAGE_MARK(4);
     if (h->descVariant == 2) {
-        int rc = encode_level_map(&h->descMaps.u[0], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, DESC_BOXW, DESC_ROWS);
+        int rc = encode_level_map(&h->descMaps.u[0], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, DESC_UW, DESC_UROWS);
         if (rc != ORBB200_OK) return rc;
-        k_describe2<<<dim3((h->maxLevelKpCap + DESC_WARPS - 1) / DESC_WARPS, P.nlevels, batch), DESC_WARPS * 32, DESC_WARPS * DESC_WARP_BYTES, st>>>(P, h->descMaps);
+        // full batches: persistent warps over chunks of 4 rows; calls of a few frames (latency counts): one row per warp and step
+        ExtractParams Pd = P;
+        Pd.descChunk = batch <= SIDE_MAX_BATCH ? 1 : 4;
+        const int ctas = std::max(1, std::min(h->numSMs * DESC_CTAS_PER_SM, (batch * P.outCap + DESC_WARPS * Pd.descChunk - 1) / (DESC_WARPS * Pd.descChunk)));
+        k_describe2<<<ctas, DESC_WARPS * 32, DESC_WARPS * DESC_WARP_BYTES, st>>>(Pd, h->descMaps);
     } else
     k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_describe"); launches++;
