@@ -578,8 +578,22 @@ def run_hd(local, rank, world, steps, barrier, reduce_max, reduce_sum, flush):
     out_c = torch.empty((n,), dtype=torch.int32, pin_memory=True)
     host_in = pinned.numpy()
 
+    launches = ex.last_launches
+    ex.close()
+    del d_frames
+    torch.cuda.empty_cache()
+    # end to end: the step's frames streamed from page-locked memory in sub-batches of up to 128 through three handles in turn
+    # (StreamingExtractor, orbb200_extract_host_async): the upload of one sub-batch, the kernels of the previous one and the
+    # download of the one before run side by side; every frame is uploaded and every result downloaded inside the timed region
+    from weiner_slamit_v2_b200 import StreamingExtractor
+    sub = min(128, n)
+    sx = StreamingExtractor(HD["nfeatures"], SCALE, NLEVELS, INI_TH, MIN_TH, width=w, height=h, max_batch=sub, device=local, depth=3)
+
     def e2e_step():
-        check(ex._L.orbb200_extract_host(ex._h, host_in.ctypes.data, n, w, w * h, out_k.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), cap))
+        for f0 in range(0, n, sub):
+            m = min(sub, n - f0)
+            sx.submit(host_in[f0:f0 + m], m, w, w * h, out_k[f0:f0 + m], out_d[f0:f0 + m], out_c[f0:f0 + m], cap)
+        sx.drain()
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -587,10 +601,9 @@ def run_hd(local, rank, world, steps, barrier, reduce_max, reduce_sum, flush):
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = reduce_max((time.perf_counter() - t0) / steps * 1e3)
+    sx.close()
     nkp = reduce_sum(int(out_c.sum()))
-    launches = ex.last_launches
-    ex.close()
-    del d_frames, pinned, out_k, out_d
+    del pinned, out_k, out_d
     torch.cuda.empty_cache()
     peak, which = _peaks()
     per_stage = stage_ms / steps
@@ -600,7 +613,8 @@ def run_hd(local, rank, world, steps, barrier, reduce_max, reduce_sum, flush):
             "kernel_ms_per_step": {s: float(per_stage[i]) for i, s in enumerate(STAGES)},
             "roofline_all": {s: HD["alg_bytes"][s] * n / (per_stage[i] * 1e-3) / 1e9 / peak for i, s in enumerate(STAGES)},
             "e2e": {"value": HD["total"] / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": n * w * h,
-                    "d2h_bytes_per_step": n * (4 + cap * 60), "api": "orbb200_extract_host (blocking; copies and kernels overlap chunk by chunk inside the call)"}}
+                    "d2h_bytes_per_step": n * (4 + cap * 60),
+                    "api": "StreamingExtractor (orbb200_extract_host_async), sub-batches of %d frames through 3 handles in turn" % sub}}
 
 
 def _int_roofline(evals_per_s):
