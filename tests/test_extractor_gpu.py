@@ -411,3 +411,19 @@ def test_handles_on_two_devices_interleaved():
             assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
             assert np.array_equal(m.undistort_points(pts, REFERENCE_K, REFERENCE_DIST), want)
             assert np.array_equal(m.image_bounds(640, 480, REFERENCE_K, REFERENCE_DIST), O.image_bounds(640, 480, REFERENCE_K, REFERENCE_DIST))
+
+
+@pytest.mark.parametrize("fast,describe", [("1", "1"), ("1", "2"), ("2", "1")])
+def test_first_generation_kernels_stay_bit_exact(fast, describe, monkeypatch):
+    """Round 1's k_fast / k_describe stay selectable for A/B runs (ORBB200_FAST_VARIANT / ORBB200_DESCRIBE_VARIANT, read when a
+    handle is created): every combination gives the oracle's result."""
+    monkeypatch.setenv("ORBB200_FAST_VARIANT", fast)
+    monkeypatch.setenv("ORBB200_DESCRIBE_VARIANT", describe)
+    frames = np.stack([synthetic_frame(70 + i) for i in range(3)])
+    ex = ORBextractor(*PARAMS, max_batch=3)
+    orc = O.OracleExtractor(*PARAMS)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(3):
+        ko, do = orc(frames[f])
+        n = counts[f]
+        assert n == len(ko) and kps[f, :n].tobytes() == ko.tobytes() and np.array_equal(desc[f, :n], do)
