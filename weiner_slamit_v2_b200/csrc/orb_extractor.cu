@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
 // slot, so the table never needs more than max-list-size + nIni entries.
 constexpr int QT_THREADS = 256;
 constexpr int SIDE_MAX_BATCH = 8;      // up to this many frames per call the blur runs beside the quadtree (launch_kernels)
-constexpr int QT_POINTS_ON_CHIP = 3072;   // candidates of one tree held in shared memory; larger trees run out of global memory
+constexpr int QT_POINTS_ON_CHIP = 1536;   // candidates of one tree held in shared memory; larger trees run out of global memory (measured 1024 / 1536 / 2304 / 3072 / 4600: 0.125 / 0.118 / 0.118 / 0.124 / 0.140 ms per 256 VGA frames: the footprint decides how many trees share an SM)
 
 struct QtShared {
     int size, nslots, nextseq, E, phase, finish, cut, rounds;
