@@ -83,6 +83,8 @@ struct ExtractParams {
     int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <38,64> instantiation
     const uint32_t* blurTiles;                       // k_blur tile table: level << 24 | tile row << 12 | tile column
     const int4* cells;                               // k_fast cell table (one entry per detection cell that exists, level-major)
+    const int* rzXs; int rzXsOff[MAXL];              // k_resize2: first source column (16-aligned) of every 128-column output block, per level
+    int rzBoxW[MAXL], rzBoxH[MAXL];                  // k_resize2: TMA box of the source window of one 128 x 32 output block of level l (0: use k_resize)
     int descChunk;                                   // k_describe2: consecutive output rows a warp takes at a time (power of two)
     int nCells, frameBase;                           // entries; index of the batch's first frame inside the handle's slabs
     // k_quadtree shared-memory geometry
@@ -108,6 +110,21 @@ __global__ void k_pad_level0(uint8_t* base, long long frameStride, int pitch, in
     uint8_t* row = base + (long long)blockIdx.y * frameStride + (long long)y * pitch;
 #pragma unroll
     for (int i = 0; i < 4; i++) row[w + i] = row[w - 2 - i];
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 // ======================================================================================
@@ -207,19 +224,92 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
     }
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// ---- k_resize, second generation: the block's source window arrives by TMA --------------------------------------------------
+// ncu (r2a) put 56 % of k_resize's stall samples on the first use of the source words: every row is three global loads behind a
+// dependent table load, at 32 registers there is nothing else in flight.  Here the 128 x 32 output block's source window (about
+// 160 x 41 pixels at scale 1.2; box start on the 16-byte boundary left of its first column) is ONE 3-D TMA tensor copy into shared
+// memory, and the row loop reads shared memory: no global latency, no 64-bit address arithmetic, no row-end predicates.  The
+// arithmetic is unchanged (resize_hrow).
+struct ResizeMaps { CUtensorMap m[MAXL]; };     // m[l] = source map for producing level l (level l - 1), box rzBoxW[l] x rzBoxH[l] x 1
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+__global__ void __launch_bounds__(RZ_WARPS * 32) k_resize2(const __grid_constant__ ExtractParams P, const __grid_constant__ ResizeMaps M, int l)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const LevelGeo& g = P.lv[l];
+    const int frame = blockIdx.z;
+    const short4* xt = P.tabs + g.xtabOff;
+    const short4* yt = P.tabs + g.ytabOff;
+    const int boxW = P.rzBoxW[l], boxH = P.rzBoxH[l];
+    // the block's source window: first source column of its first destination column, first source row of its first row
+    const int xs = __ldg(P.rzXs + P.rzXsOff[l] + blockIdx.x);      // 16-byte boundary at or left of the block's leftmost source column
+    const int ys = (int)__ldg(yt + blockIdx.y * RZ_WARPS * RZ_ROWS).x;
+    const uint32_t bar = smem_u32(smem + boxW * boxH);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(boxW * boxH)) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(&M.m[l])), "r"(bar), "r"(xs), "r"(ys),
+                       "r"((l == 1 ? 0 : P.frameBase) + frame) : "memory");
+    }
+    __syncthreads();                                   // the barrier is initialised before anybody polls it
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int yBeg = (blockIdx.y * RZ_WARPS + (threadIdx.x >> 5)) * RZ_ROWS;
+    if (x0 >= g.w + 4 || yBeg >= g.h) return;
+    uint8_t* dst = P.pyr + (long long)frame * P.pyrFrameBytes + g.pyrOff;
+
+    // column geometry, once per thread
+    short4 t[4];
+    int bmin = 1 << 30;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        t[j] = __ldg(xt + min(x0 + j, g.w + 3));
+        bmin = min(bmin, (int)t[j].x);
+    }
+    const int a = bmin & ~3;
+    const uint32_t selShift = 0x3210u + 0x1111u * (uint32_t)(bmin - a);
+    uint32_t sel[4], coef[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        sel[j] = (uint32_t)(t[j].x - bmin) | ((uint32_t)(t[j].w - bmin) << 4);    // bytes S[sx], S[sx+1] -> byte lanes 0,1
+        coef[j] = (uint32_t)(uint16_t)t[j].y | ((uint32_t)(uint16_t)t[j].z << 16);
+    }
+    const uint8_t* sbase = smem + (a - xs) - ys * boxW;     // source (row, column a) = sbase + row * boxW
+    const int yEnd = min(yBeg + RZ_ROWS, g.h);
+    uint32_t r0[4], r1[4];
+    int cur1 = -1;                                            // source row held in r1
+    short4 tnext = __ldg(yt + yBeg);
+    uint8_t* outp = dst + (long long)yBeg * g.pitch + x0;
+    mbar_wait(bar, 0);
+    auto hrow = [&](int row, uint32_t (&r)[4]) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(sbase + row * boxW);
+        ResizeRaw raw;
+        raw.w0 = w[0]; raw.w1 = w[1]; raw.w2 = w[2];
+        resize_hrow(raw, selShift, sel, coef, r);
+    };
+    for (int y = yBeg; y < yEnd; y++) {
+        const short4 ty = tnext;
+        tnext = __ldg(yt + min(y + 1, g.h - 1));
+        if (ty.x == cur1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) r0[j] = r1[j];
+        } else {
+            hrow(ty.x, r0);
+        }
+        if (ty.y == ty.x) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) r1[j] = r0[j];
+        } else {
+            hrow(ty.y, r1);
+        }
+        cur1 = ty.y;
+        const uint32_t B0 = (uint32_t)ty.z << 16, B1 = (uint32_t)ty.w << 16;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = min((__umulhi(B0, r0[j]) + __umulhi(B1, r1[j]) + 2u) >> 2, 255u);
+        *reinterpret_cast<uint32_t*>(outp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        outp += g.pitch;
+    }
 }
 
 // ======================================================================================
@@ -1627,6 +1717,8 @@ struct orbb200_extractor {
     int totalCells, totalBlurTiles, maxKp, numSMs;
     size_t fastSmem, qtSmem;
     int fastVariant;           // 2 = k_fast2 (TMA tensor staging, default), 1 = k_fast (ORBB200_FAST_VARIANT=1: the first-generation kernel, kept for A/B runs)
+    ResizeMaps resizeMaps;     // k_resize2's source-window maps (m[1] is encoded per call: level 0 may be the caller's buffer)
+    int resizeVariant;         // 2 = k_resize2 (TMA-staged source window, default), 1 = k_resize (ORBB200_RESIZE_VARIANT=1)
     FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
     DescMaps descMaps;         // k_describe2's patch maps of the unblurred and the blurred levels (box 64 x 37)
     int descVariant, maxLevelKpCap;   // 2 = k_describe2 (default), 1 = k_describe (ORBB200_DESCRIBE_VARIANT=1, kept for A/B runs)
@@ -1770,6 +1862,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     memset(&P, 0, sizeof(P));
     P.nlevels = nlevels; P.iniTh = iniThFAST; P.minTh = minThFAST; P.blurVariant = h->blurTaps;
     std::vector<short4> tabs;
+    std::vector<int> rzXs;
     long long pyrOff = 0, blurOff = 0;
     int cells = 0, candOff = 0, kpOff = 0, tiles = 0, maxWCell = 0, maxHCell = 0, maxKpCap = 0;
     for (int l = 0; l < nlevels; l++) {
@@ -1824,6 +1917,24 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
             }
             g.xtabOff = (int)tabs.size(); tabs.insert(tabs.end(), xt.begin(), xt.end());
             g.ytabOff = (int)tabs.size(); tabs.insert(tabs.end(), yt.begin(), yt.end());
+            // k_resize2: per 128-column block the 16-aligned first source column, and the box that holds any block's source window
+            P.rzXsOff[l] = (int)rzXs.size();
+            int boxW = 0, boxH = 0;
+            for (int bx = 0; bx * 128 < g.w + 4; bx++) {
+                int lo = 1 << 30, hi = 0;
+                for (int x0 = bx * 128; x0 < std::min(bx * 128 + 128, g.w + 4); x0 += 4) {
+                    int bmin = 1 << 30;
+                    for (int j = 0; j < 4; j++) bmin = std::min(bmin, (int)xt[std::min(x0 + j, g.w + 3)].x);
+                    lo = std::min(lo, bmin & ~3); hi = std::max(hi, (bmin & ~3) + 12);
+                }
+                rzXs.push_back(lo & ~15);
+                boxW = std::max(boxW, hi - (lo & ~15));
+            }
+            for (int by = 0; by * RZ_ROWS * RZ_WARPS < g.h; by++)
+                boxH = std::max(boxH, (int)yt[std::min(by * RZ_ROWS * RZ_WARPS + RZ_ROWS * RZ_WARPS - 1, g.h - 1)].y - (int)yt[by * RZ_ROWS * RZ_WARPS].x + 1);
+            boxW = (int)align_up(boxW, 16);
+            P.rzBoxW[l] = (boxW <= 256 && boxH <= 256) ? boxW : 0;      // a TMA box side is at most 256: larger scale factors keep k_resize
+            P.rzBoxH[l] = boxH;
         }
         g.blurTilesX = (g.w + 127) / 128;
         g.blurTileStart = tiles; tiles += g.blurTilesX * ((g.h + BL_ROWS - 1) / BL_ROWS);
@@ -1892,6 +2003,14 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     int4* dCells = nullptr;
     TRY(dev_alloc(h, &dCells, cellTab.size() + 1));
     P.cells = dCells;
+    int* dRzXs = nullptr;
+    TRY(dev_alloc(h, &dRzXs, rzXs.size() + 1));
+    P.rzXs = dRzXs;
+    h->resizeVariant = 2;
+    if (const char* ev = getenv("ORBB200_RESIZE_VARIANT")) h->resizeVariant = atoi(ev) == 1 ? 1 : 2;
+    for (int l = 2; l < nlevels && h->resizeVariant == 2; l++)      // source = level l - 1 in the handle's pyramid slab
+        if (P.rzBoxW[l]) TRY(encode_level_map(&h->resizeMaps.m[l], P.pyr + P.lv[l - 1].pyrOff, P.lv[l - 1].w + 4, P.lv[l - 1].h, max_batch, P.lv[l - 1].pitch,
+                                              (size_t)P.pyrFrameBytes, P.rzBoxW[l], P.rzBoxH[l]));
     std::vector<uint32_t> blurTab;
     for (int l = 0; l < nlevels; l++)
         for (int ty = 0; ty < (P.lv[l].h + BL_ROWS - 1) / BL_ROWS; ty++)
@@ -1915,6 +2034,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     cudaError_t e = cudaSuccess;
     if (!cellTab.empty()) e = cudaMemcpy(dCells, cellTab.data(), cellTab.size() * sizeof(int4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !blurTab.empty()) e = cudaMemcpy(dBlurTiles, blurTab.data(), blurTab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !rzXs.empty()) e = cudaMemcpy(dRzXs, rzXs.data(), rzXs.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("extractor_create: %s", cudaGetErrorString(e)); orbb200_extractor_destroy(h); return ORBB200_ECUDA; }
     if (!tabs.empty()) e = cudaMemcpy(dTabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(P.status, 0, sizeof(int));
@@ -1931,6 +2051,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     if (e == cudaSuccess && h->fastVariant == 1) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->fastVariant == 2) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast2<38, 64> : (const void*)k_fast2<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->descVariant == 2) e = ensure_dynamic_smem((const void*)k_describe2, device, DESC_WARPS * DESC_WARP_BYTES);
+    for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant == 2; l++)
+        e = ensure_dynamic_smem((const void*)k_resize2, device, (size_t)P.rzBoxW[l] * P.rzBoxH[l] + 16);
     if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)k_quadtree, device, h->qtSmem);
     if (e == cudaSuccess) e = ensure_dynamic_smem(P.blurVariant ? (const void*)k_blur<true> : (const void*)k_blur<false>, device, BL_WARPS * BL_WARP_BYTES);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
@@ -2026,10 +2148,15 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
     ORB_CUDA(cudaMemsetAsync(P.candCount, 0, sizeof(int) * P.nlevels * batch, st));
 #define STAGE_MARK(i) do { if (h->profiling) ORB_CUDA(cudaEventRecord(h->ev[i], st)); } while (0)
     STAGE_MARK(0);
+    if (h->resizeVariant == 2 && P.nlevels > 1 && P.rzBoxW[1]) {
+        int rc = encode_level_map(&h->resizeMaps.m[1], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, P.rzBoxW[1], P.rzBoxH[1]);
+        if (rc != ORBB200_OK) return rc;
+    }
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeo& g = P.lv[l];
         dim3 grid((g.w + 4 + 127) / 128, (g.h + RZ_ROWS * RZ_WARPS - 1) / (RZ_ROWS * RZ_WARPS), batch);
-        k_resize<<<grid, RZ_WARPS * 32, 0, st>>>(P, l);
+        if (h->resizeVariant == 2 && P.rzBoxW[l]) k_resize2<<<grid, RZ_WARPS * 32, P.rzBoxW[l] * P.rzBoxH[l] + 16, st>>>(P, h->resizeMaps, l);
+        else k_resize<<<grid, RZ_WARPS * 32, 0, st>>>(P, l);
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
     STAGE_MARK(1);
