@@ -276,8 +276,11 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize2(const __grid_constant
     }
     const uint8_t* sbase = smem + (a - xs) - ys * boxW;     // source (row, column a) = sbase + row * boxW
     const int yEnd = min(yBeg + RZ_ROWS, g.h);
-    uint32_t r0[4], r1[4];
-    int cur1 = -1;                                            // source row held in r1
+    // Two register sets A and B hold the horizontal passes of two source rows.  Consecutive destination rows usually share a
+    // source row (the lower row of one is the upper row of the next), so the sets swap roles from row to row -- the loop is
+    // unrolled by two and a set is recomputed only when it does not already hold the row it is asked for: no copies.
+    uint32_t A[4], B[4];
+    int rowA = -1, rowB = -1;
     short4 tnext = __ldg(yt + yBeg);
     uint8_t* outp = dst + (long long)yBeg * g.pitch + x0;
     mbar_wait(bar, 0);
@@ -287,28 +290,30 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize2(const __grid_constant
         raw.w0 = w[0]; raw.w1 = w[1]; raw.w2 = w[2];
         resize_hrow(raw, selShift, sel, coef, r);
     };
-    for (int y = yBeg; y < yEnd; y++) {
-        const short4 ty = tnext;
-        tnext = __ldg(yt + min(y + 1, g.h - 1));
-        if (ty.x == cur1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) r0[j] = r1[j];
-        } else {
-            hrow(ty.x, r0);
-        }
-        if (ty.y == ty.x) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) r1[j] = r0[j];
-        } else {
-            hrow(ty.y, r1);
-        }
-        cur1 = ty.y;
+    auto emit = [&](const short4 ty, const uint32_t (&r0)[4], const uint32_t (&r1)[4]) {
         const uint32_t B0 = (uint32_t)ty.z << 16, B1 = (uint32_t)ty.w << 16;
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) o[j] = min((__umulhi(B0, r0[j]) + __umulhi(B1, r1[j]) + 2u) >> 2, 255u);
         *reinterpret_cast<uint32_t*>(outp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
         outp += g.pitch;
+    };
+#pragma unroll 1
+    for (int y = yBeg; y < yEnd; y += 2) {
+        {   // even row of the pair: upper source row in A, lower in B
+            const short4 ty = tnext;
+            tnext = __ldg(yt + min(y + 1, g.h - 1));
+            if (rowA != ty.x) { hrow(ty.x, A); rowA = ty.x; }
+            if (rowB != ty.y) { hrow(ty.y, B); rowB = ty.y; }
+            emit(ty, A, B);
+        }
+        if (y + 1 < yEnd) {   // odd row: upper in B (usually what the even row left there), lower in A
+            const short4 ty = tnext;
+            tnext = __ldg(yt + min(y + 2, g.h - 1));
+            if (rowB != ty.x) { hrow(ty.x, B); rowB = ty.x; }
+            if (rowA != ty.y) { hrow(ty.y, A); rowA = ty.y; }
+            emit(ty, B, A);
+        }
     }
 }
 
