@@ -165,6 +165,41 @@ def cpu_single_thread(frames):
     return {"single_thread_ms_per_frame": 1e3 / fps, "single_thread_frames_per_s": fps, "single_thread_sample": "%d frames" % len(frames)}
 
 
+def cpu_primitive_ratio(frames):
+    """How much of the CPU baseline is the stand-in OpenCV: the three image primitives ORBextractor spends its time in (the
+    resize chain, FAST per level, GaussianBlur per level) on one thread, once through the scalar mini-cv / oracle primitives the
+    reference arm links and once through cv2 (OpenCV's SIMD build, same results bit for bit: tests/test_oracle_primitives.py)."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    cv2.setNumThreads(1)
+    ex = O.OracleExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    ex(frames[0])
+    sizes = [ex.level_shape(l) for l in range(NLEVELS)]            # (h, w) per level
+
+    def run(resize, fast, blur, timed=True):
+        if timed:
+            run(resize, fast, blur, False)             # first calls initialise the library
+        t0 = time.perf_counter()
+        for img in (frames if timed else frames[:1]):
+            lv = [img]
+            for l in range(1, NLEVELS):
+                lv.append(resize(lv[-1], sizes[l][1], sizes[l][0]))
+            for im in lv:
+                fast(im); blur(im)
+        return (time.perf_counter() - t0) / len(frames) * 1e3
+    det = cv2.FastFeatureDetector_create(INI_TH, True)
+    t_cv = run(lambda im, w, h: cv2.resize(im, (w, h), interpolation=cv2.INTER_LINEAR), lambda im: det.detect(im, None),
+               lambda im: cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+    t_or = run(lambda im, w, h: O.resize_linear(im, w, h), lambda im: O.fast(im, INI_TH, True), lambda im: O.gaussian_blur7(im))
+    return {"scalar_primitives_ms_per_frame": t_or, "opencv_simd_primitives_ms_per_frame": t_cv, "ratio": t_or / t_cv,
+            "what": "resize chain + FAST(%d) + GaussianBlur 7x7 on all %d levels of %d frames, one host thread; cv2 %s" % (INI_TH, NLEVELS, len(frames), cv2.__version__)}
+
+
 def cpu_matching_baselines(threads):
     """The reference's own ORBmatcher.cc (oracle/_ref/libref_matcher.so; the oracle port if it was not built) on the host
     threads for configs[2] and configs[4], on a bounded sample of the same synthetic workload: one call per frame pair /
@@ -267,6 +302,9 @@ def run_reference(args):
             "sample": "%d of the %d frames of one step, %d host threads, one ORBextractor each" % (sample, BATCH, threads),
             "primitives": "the reference's ORBextractor.cc over the scalar mini-cv stand-in for OpenCV (about 3x slower than OpenCV's SIMD build)"}
     base.update(cpu_single_thread(frames[:8]))
+    pr = cpu_primitive_ratio(frames[:4])
+    if pr:
+        base["primitive_cost"] = pr
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_t / args.steps * 1e3,
@@ -528,6 +566,9 @@ def run_ours(args):
                                     "primitives": "the reference's ORBextractor.cc over the scalar mini-cv stand-in for OpenCV (about 3x slower "
                                                   "than OpenCV's SIMD build)"}
             line["cpu_baseline"].update(cpu_single_thread(frames[:8]))
+            pr = cpu_primitive_ratio(frames[:4])
+            if pr:
+                line["cpu_baseline"]["primitive_cost"] = pr
             line["parity"] = parity_report(frames[:8], *parity_in)
             if hd is not None:
                 line["hd"]["cpu_baseline"] = cpu_hd_baseline(threads)
