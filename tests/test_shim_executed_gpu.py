@@ -291,33 +291,36 @@ def test_tracking_extractor_sequence_on_one_thread():
 def test_matcher_shim_from_three_host_threads():
     """ORBmatcher is used concurrently from the Tracking, LocalMapping and LoopClosing threads (S/System.cc:156,160):
     three host threads call different entry points of the drop-in class at once (ctypes releases the GIL), each through
-    its own thread-local device handle, and every result equals the reference's golden vector."""
-    gi, gp, gl = gold("ref_match_init.npz"), gold("ref_match_proj.npz"), gold("ref_match_lastframe.npz")
+    its own thread-local device handle.  All three use ONE image rectangle, as one camera does: Frame::mnMinX ... are
+    static members of the reference's Frame, which every harness call sets."""
+    common = (0, 0, 1280, 720)
+    gp = gold("ref_match_proj.npz")
     R.shimlib()
     errors = []
+    p = init_pair(400, n=1000)
+    want_init = O.search_for_initialization(p[0], p[1], p[2], p[3], p[4], common, 0.9, True, 100)
+    c = gp["cfg_1"]
+    kp, kd, mp = projection_frame(int(c[0]), int(c[1]), int(c[2]))
+    w = motion_frame(700)
+    want_last = O.search_by_projection_last_frame(w, SCALE_FACTORS_8, common, 15.0, 0, True)
+    assert want_init[0] > 20 and want_last[0] > 100
 
     def init_worker():
-        idx, n, brute, window = (int(v) for v in gi["cfg_0"])
-        p = init_pair(idx, n=n, brute_force=bool(brute))
         for _ in range(6):
-            cnt, m12, prev = R.ref_search_for_initialization(p[0], p[1], p[2], p[3], p[4], (0, 0, 640, 480), 0.9, True, window)
-            if cnt != int(gi["n_0"]) or not np.array_equal(m12, gi["m12_0"]) or not np.array_equal(prev, gi["prev_0"]):
+            cnt, m12, prev = R.ref_search_for_initialization(p[0], p[1], p[2], p[3], p[4], common, 0.9, True, 100)
+            if cnt != want_init[0] or not np.array_equal(m12, want_init[1]) or not np.array_equal(prev, want_init[2]):
                 errors.append("init")
 
     def proj_worker():
-        c = gp["cfg_1"]
-        kp, kd, mp = projection_frame(int(c[0]), int(c[1]), int(c[2]))
         for _ in range(6):
-            cnt, kpmp = R.ref_search_by_projection(mp, kp, kd, SCALE_FACTORS_8, (0, 0, 1280, 720), 0.8, float(c[3]))
+            cnt, kpmp = R.ref_search_by_projection(mp, kp, kd, SCALE_FACTORS_8, common, 0.8, float(c[3]))
             if cnt != int(gp["n_1"]) or not np.array_equal(kpmp, gp["kpmp_1"]):
                 errors.append("proj")
 
     def last_worker():
-        c = gl["cfg_0"]
-        w = motion_frame(int(c[0]))
         for _ in range(6):
-            cnt, kpmp = R.ref_search_by_projection_last_frame(w, SCALE_FACTORS_8, BOUNDS, float(c[1]), bool(c[2]))
-            if cnt != int(gl["n_0"]) or not np.array_equal(kpmp, gl["kpmp_0"]):
+            cnt, kpmp = R.ref_search_by_projection_last_frame(w, SCALE_FACTORS_8, common, 15.0, True)
+            if cnt != want_last[0] or not np.array_equal(kpmp, want_last[1]):
                 errors.append("last")
 
     with R.shim_bodies():

@@ -1,5 +1,12 @@
-"""Profiling target for the matcher configs (developer tool): runs bench.run_matching once."""
+"""Profiling target for the matcher configs (developer tool): runs bench.run_matching once on one GPU."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 import bench
-print(json.dumps(bench.run_matching(0, 2)))
+
+
+def barrier():
+    torch.cuda.synchronize()
+
+
+print(json.dumps(bench.run_matching(0, 0, 1, 2, barrier, float, float)))

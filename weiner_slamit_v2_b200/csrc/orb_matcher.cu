@@ -725,6 +725,197 @@ __global__ void __launch_bounds__(128) k_search_proj(const ProjParams P)
     if (lane == 0) P.nmatches[item] = nmatches;
 }
 
+// ---- SearchByProjection, phase B, frame-wide: one CTA per frame, deterministic reservations ---------------------------------
+// The greedy pass above is one dependent chain per frame (10 k map points in list order, 32 at a time): 0.53 of the call's
+// 1.05 ms at 512 frames, and no shorter with fewer frames per GPU.  Here every pending map point i posts its index with
+// atomicMin on each keypoint of its candidate set C_i -- the keypoints that pass the state-independent tests of :62-98, i.e.
+// everything i can ever read (occupancy) or write (its best) -- and a map point whose index survives on all of them is FINAL: no
+// earlier pending map point shares a keypoint with it, so the occupancy it sees is the one the sequential loop would show it.
+// Final map points decide and commit together, the rest go round again; the lowest pending index is always final, so the
+// rounds end, after about as many as map points share a keypoint (5-10 in configs[4]) instead of 313 dependent batches.
+// Decisions are the reference's: best / second among the unoccupied candidates in visiting order (from the top-4 list when it
+// is conclusive, else a rescan under the current occupancy), ratio test on equal levels, the last accepting map point in list
+// order stays on a keypoint that is never occupied (atomicMax).
+constexpr int SP2_THREADS = 512;     // (256 threads and four frames per SM measured slower: 0.95 against 0.83 ms)
+
+template <typename F>
+__device__ __forceinline__ void proj_for_each_candidate(const ProjParams& P, int item, size_t mo, int i, F&& f)
+{
+    const int* cs = P.cellStart + (size_t)item * (GRID_CELLS + 1);
+    const uint4* cr = P.cellRec + (size_t)item * P.f.stride * 3;
+    const float* ur = P.uRight ? P.uRight + (size_t)item * P.f.stride : nullptr;
+    const int lvl = P.mpLevel[mo + i];
+    float r = ((double)P.mpViewCos[mo + i] > 0.998) ? 2.5f : 4.0f;               // :133-139
+    if (P.th != 1.0f) r = __fmul_rn(r, P.th);
+    const float rs = __fmul_rn(r, P.scaleFactors[min(max(lvl, 0), P.nlevels - 1)]);
+    const float qx = P.mpX[mo + i], qy = P.mpY[mo + i], qxr = P.mpXR[mo + i];
+    int c0, c1, r0, r1;
+    if (!cell_range(P.g, qx, qy, rs, c0, c1, r0, r1)) return;
+    const int minLevel = lvl - 1, maxLevel = lvl;
+    const bool check = (minLevel > 0) || (maxLevel >= 0);
+    for (int c = c0; c <= c1; c++) {
+        const int s = cs[c * GRID_ROWS + r0], e = cs[c * GRID_ROWS + r1 + 1];
+        for (int p = s; p < e; p++) {
+            const uint4 rec = __ldg(cr + 3 * p);                                // {x, y, index, octave} in CSR order
+            const int idx = (int)rec.z, o = (int)rec.w;
+            if (check) {
+                if (o < minLevel) continue;
+                if (maxLevel >= 0 && o > maxLevel) continue;
+            }
+            if (!(fabsf(__fsub_rn(__uint_as_float(rec.x), qx)) < rs && fabsf(__fsub_rn(__uint_as_float(rec.y), qy)) < rs)) continue;
+            if (ur && ur[idx] > 0) {                                            // :93-98
+                const float er = fabsf(__fsub_rn(qxr, ur[idx]));
+                if (er > rs) continue;
+            }
+            f(p, idx, o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SP2_THREADS) k_search_proj2(const ProjParams P)
+{
+    constexpr int T = SP2_THREADS, U = 4;                      // U map points per thread and step: their list loads are in flight together
+    const int tid = threadIdx.x;
+    const int item = blockIdx.x;
+    const int n = min(P.f.n[item], P.f.stride), nmp = min(P.mpN[item], P.mpStride);
+    const int* ci = P.cellItems + (size_t)item * P.f.stride;
+    const uint4* cr = P.cellRec + (size_t)item * P.f.stride * 3;
+    int* kpmp = P.kpMp + (size_t)item * P.f.stride;
+    const int* kpobs = P.kpMpObs ? P.kpMpObs + (size_t)item * P.f.stride : nullptr;
+    const size_t mo = (size_t)item * P.mpStride;
+    const uint4* md = reinterpret_cast<const uint4*>(P.mpDesc + mo * 32);
+    const uint4* topk = P.topk + mo;
+    const uint4* topkIdx = P.topkIdx + mo;
+    const int* topkCount = P.topkCount + mo;
+
+    extern __shared__ __align__(16) uint8_t sp2_smem[];
+    const int nP = (P.f.stride + 15) & ~15, nL = (P.mpStride + 7) & ~7;
+    // claim[k] = (0xffff - round) << 16 | lowest pending map point that lists keypoint k this round: a newer round's entries are
+    // smaller than anything older, so the array never needs clearing
+    unsigned* claim = reinterpret_cast<unsigned*>(sp2_smem);
+    uint16_t* winner = reinterpret_cast<uint16_t*>(claim + nP);         // 1 + last accepting map point per keypoint (0: none)
+    uint16_t* list[2] = {winner + nP, winner + nP + nL};                // pending map points, this round / next round
+    uint8_t* occ = reinterpret_cast<uint8_t*>(list[1] + nL);            // keypoint holds a map point with observations (:89-91)
+    __shared__ int s_len[2], s_nmatch;
+
+    for (int k = tid; k < n; k += T) {
+        const int held = kpmp[k];
+        occ[k] = held != -1 && (held >= 0 ? P.mpObs[mo + held] : (kpobs ? kpobs[k] : 0)) > 0;
+        winner[k] = 0;
+        claim[k] = 0xffffffffu;
+    }
+    if (tid == 0) { s_len[0] = 0; s_len[1] = 0; s_nmatch = 0; }
+    __syncthreads();
+    for (int i = tid; i < nmp; i += T)
+        if (topkCount[i] > 0) list[0][atomicAdd(&s_len[0], 1)] = (uint16_t)i;     // cnt <= 0: not in view / bad (:56-60) / no candidate (:73)
+    __syncthreads();
+
+    int cur = 0, acc = 0;
+    unsigned stamp = 0xffffu << 16;
+    while (true) {
+        const int len = s_len[cur];
+        if (len == 0) break;
+        const uint16_t* L = list[cur];
+        if (stamp == 0) {                                              // 65535 rounds used up (cannot happen with < 65536 map points; kept for safety)
+            for (int k = tid; k < n; k += T) claim[k] = 0xffffffffu;
+            stamp = 0xffffu << 16;
+        }
+        stamp -= 1u << 16;
+        if (tid == 0) s_len[cur ^ 1] = 0;
+        __syncthreads();
+        // post: every pending map point on every unoccupied keypoint of its candidate set
+        for (int b = tid; b < len; b += U * T) {
+            int i[U], cnt[U];
+            uint4 idv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int pos = b + u * T;
+                i[u] = pos < len ? (int)L[pos] : -1;
+                cnt[u] = i[u] >= 0 ? topkCount[i[u]] : 0;
+                idv[u] = i[u] >= 0 ? topkIdx[i[u]] : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (i[u] < 0) continue;
+                if (cnt[u] <= 4) {
+                    const int kid[4] = {(int)idv[u].x, (int)idv[u].y, (int)idv[u].z, (int)idv[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (j < cnt[u] && !occ[kid[j]]) atomicMin(&claim[kid[j]], stamp | (unsigned)i[u]);
+                } else {
+                    const unsigned mine = stamp | (unsigned)i[u];
+                    proj_for_each_candidate(P, item, mo, i[u], [&](int, int idx, int) { if (!occ[idx]) atomicMin(&claim[idx], mine); });
+                }
+            }
+        }
+        __syncthreads();
+        // final map points decide and commit, the others go on next round's list
+        for (int b = tid; b < len; b += U * T) {
+            int i[U], cnt[U];
+            uint4 idv[U], kk[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int pos = b + u * T;
+                i[u] = pos < len ? (int)L[pos] : -1;
+                cnt[u] = i[u] >= 0 ? topkCount[i[u]] : 0;
+                idv[u] = i[u] >= 0 ? topkIdx[i[u]] : make_uint4(0, 0, 0, 0);
+                kk[u] = i[u] >= 0 ? topk[i[u]] : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int ii = i[u], c = cnt[u];
+                if (ii < 0) continue;
+                const int kid[4] = {c > 0 ? (int)idv[u].x : -1, c > 1 ? (int)idv[u].y : -1, c > 2 ? (int)idv[u].z : -1, c > 3 ? (int)idv[u].w : -1};
+                bool fin = true;
+                const unsigned mine = stamp | (unsigned)ii;
+                if (c <= 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (j < c && !occ[kid[j]] && claim[kid[j]] != mine) fin = false;
+                } else {
+                    proj_for_each_candidate(P, item, mo, ii, [&](int, int idx, int) { if (!occ[idx] && claim[idx] != mine) fin = false; });
+                }
+                if (!fin) { list[cur ^ 1][atomicAdd(&s_len[cur ^ 1], 1)] = (uint16_t)ii; continue; }
+                const uint32_t key[4] = {kk[u].x, kk[u].y, kk[u].z, kk[u].w};
+                Top2 t = {256, INT_MAX, -1, 256, INT_MAX, -1};
+                int bestId = -1, found = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (found < 2 && j < c) {
+                        const int dist = (int)(key[j] >> 23), o = (int)(key[j] & 31u);
+                        if (!occ[kid[j]] && dist < 256) {
+                            if (found == 0) { t.b = dist; t.ba = o; bestId = kid[j]; } else { t.s = dist; t.sa = o; }
+                            found++;
+                        }
+                    }
+                }
+                const int d3 = (int)(key[3] >> 23);
+                const bool resolved = found == 2 || c <= 4 || (found == 1 && t.b > TH_HIGH) || (found == 0 && d3 > TH_HIGH);
+                if (!resolved) {        // the list is a truncation and too much of it is taken: rescan under the current occupancy
+                    t = Top2{256, INT_MAX, -1, 256, INT_MAX, -1};
+                    const uint4 a0 = __ldg(md + 2 * ii), a1 = __ldg(md + 2 * ii + 1);
+                    proj_for_each_candidate(P, item, mo, ii, [&](int p, int idx, int o) {
+                        if (occ[idx]) return;
+                        top2_push(t, hamming256(a0, a1, __ldg(cr + 3 * p + 1), __ldg(cr + 3 * p + 2)), p, o);
+                    });
+                    bestId = t.bp >= 0 && t.b < 256 ? ci[t.bp] : -1;
+                }
+                if (t.b <= TH_HIGH && !(t.ba == t.sa && (float)t.b > __fmul_rn(P.nnratio, (float)t.s))) {   // :120-127
+                    // :125, the last one in list order stays.  (Two map points that are final in the same round share no keypoint, and
+                    // rounds are separated by barriers: a plain read-modify-write is race free)
+                    if (winner[bestId] < ii + 1) winner[bestId] = (uint16_t)(ii + 1);
+                    if (P.mpObs[mo + ii] > 0) occ[bestId] = 1;
+                    acc++;
+                }
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (acc) atomicAdd(&s_nmatch, acc);
+    __syncthreads();
+    for (int k = tid; k < n; k += T) if (winner[k] != 0) kpmp[k] = (int)winner[k] - 1;
+    if (tid == 0) P.nmatches[item] = s_nmatch;
+}
+
 int launch_build_grid(const FrameDev& f, const GridGeo& g, int* cellStart, int* cellItems, uint4* cellRec, int items, cudaStream_t st)
 {
     k_build_grid<<<items, 256, 0, st>>>(f, g, cellStart, cellItems, cellRec);
@@ -922,10 +1113,18 @@ extern "C" int orbb200_search_by_projection(orbb200_matcher* m, int items, const
     k_proj_topk<<<dim3((mp->stride + 127) / 128, items), 128, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_proj_topk");
     {
-        const size_t sm = 8 * (size_t)((f->stride + 15) & ~15);
-        if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
-        ORB_CUDA(ensure_dynamic_smem((const void*)k_search_proj, m->device, sm));
-        k_search_proj<<<(items + 3) / 4, 128, sm, st>>>(P);
+        // frame-wide reservations when the per-frame state fits a CTA's shared memory comfortably, else one warp per frame
+        const size_t nP = (size_t)((f->stride + 15) & ~15), sm2 = 7 * nP + 4 * (size_t)((mp->stride + 7) & ~7) + 16;
+        static const bool oldResolve = getenv("ORBB200_PROJ_RESOLVE") && atoi(getenv("ORBB200_PROJ_RESOLVE")) == 1;
+        if (sm2 <= 100 * 1024 && mp->stride < 65535 && !oldResolve) {
+            ORB_CUDA(ensure_dynamic_smem((const void*)k_search_proj2, m->device, sm2));
+            k_search_proj2<<<items, SP2_THREADS, sm2, st>>>(P);
+        } else {
+            const size_t sm = 8 * (size_t)((f->stride + 15) & ~15);
+            if (sm > 200 * 1024) { set_error("more than %d keypoints per frame", 25 * 1024); return ORBB200_EINVAL; }
+            ORB_CUDA(ensure_dynamic_smem((const void*)k_search_proj, m->device, sm));
+            k_search_proj<<<(items + 3) / 4, 128, sm, st>>>(P);
+        }
     }
     ORB_CHECK_LAUNCH("k_search_proj");
     m->lastLaunches = 3;
