@@ -85,6 +85,11 @@ struct ExtractParams {
     const int4* cells;                               // k_fast cell table (one entry per detection cell that exists, level-major)
     const int* rzXs; int rzXsOff[MAXL];              // k_resize2: first source column (16-aligned) of every 128-column output block, per level
     int rzBoxW[MAXL], rzBoxH[MAXL];                  // k_resize2: TMA box of the source window of one 128 x 32 output block of level l (0: use k_resize)
+    // k_resize3: a warp = 64 columns x 16 rows of two frames; per level the 16-aligned first source column of every 64-column block
+    // (in rzXs from rz3XsOff on), the source-window box (rz3BoxW x rz3BoxH x 2 frames, 0: use k_resize2) and the row table in groups of
+    // RZ3_GROUP entries {lower source row, b0 << 16, b1 << 16, -}
+    int rz3XsOff[MAXL], rz3BoxW[MAXL], rz3BoxH[MAXL], ytab3Off[MAXL];
+    const int4* ytab3;
     int descChunk;                                   // k_describe2: consecutive output rows a warp takes at a time (power of two)
     int nCells, frameBase;                           // entries; index of the batch's first frame inside the handle's slabs
     // k_quadtree shared-memory geometry
@@ -314,6 +319,114 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize2(const __grid_constant
             if (rowA != ty.y) { hrow(ty.y, A); rowA = ty.y; }
             emit(ty, B, A);
         }
+    }
+}
+
+// ---- k_resize, third generation: the loop runs over SOURCE rows -------------------------------------------------------------
+// k_resize2 still spent ~35 instructions per pixel (ncu r2s): per destination row a table load behind address arithmetic, two
+// "do I already hold this source row" tests with their reconvergence points, an eight-row walk that amortises the column setup
+// over 32 pixels only, and 128-column blocks that leave 16 % of the lanes past the level's right edge.  Here
+//  * a warp owns 64 columns x 16 rows of TWO frames (lane = column quad + 16 * frame): the control flow depends on the row
+//    tables only, so it is the same for both half-warps, and 64-column blocks fit the level widths to 94 % on average;
+//  * every warp stages its own source window (one 3-D TMA box over {column, row, 2 frames}) behind its own mbarrier -- no block
+//    barrier, warps of a block are independent;
+//  * the loop walks the window's source rows once: each gets one horizontal pass (the two register sets swap roles), and a
+//    destination row is emitted when its LOWER source row has just been computed (its upper row is then the previous one,
+//    because the lower rows of consecutive destination rows never decrease).  A level with a row whose two taps sit on the same
+//    source row (only when consecutive levels have the same height) keeps k_resize2;
+//  * the row table (a copy of the warp's 16 entries + a sentinel in shared memory) holds the lower row and the coefficients
+//    already shifted (b << 16); the vertical blend packs two pixels per register before the rounding shift, and the clamp to
+//    255 is gone: b0 + b1 = 2048 and r <= 255 * 2048 >> 4 bound the sum by 1020.
+constexpr int RZ3_ROWS = 16, RZ3_WARPS = 4;
+constexpr int RZ3_GROUP = RZ3_ROWS + 1;        // row-table entries per 16-row group: its rows, then a sentinel that matches no source row
+
+__global__ void __launch_bounds__(RZ3_WARPS * 32) k_resize3(const __grid_constant__ ExtractParams P, const __grid_constant__ ResizeMaps M, int l)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const LevelGeo& g = P.lv[l];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = blockIdx.y * RZ3_WARPS + warp;
+    if (group * RZ3_ROWS >= g.h) return;                                       // the whole warp
+    const int boxW = P.rz3BoxW[l], frameBytes = boxW * P.rz3BoxH[l], warpBytes = (2 * frameBytes + 127) & ~127;
+    uint8_t* win = smem + warp * warpBytes;
+    int4* rows = reinterpret_cast<int4*>(smem + RZ3_WARPS * warpBytes) + warp * RZ3_GROUP;      // this warp's row-table entries
+    const uint32_t bar = smem_u32(smem + RZ3_WARPS * (warpBytes + RZ3_GROUP * 16) + 8 * warp);
+    const int4* yt = P.ytab3 + P.ytab3Off[l] + group * RZ3_GROUP;
+    const int xs = __ldg(P.rzXs + P.rz3XsOff[l] + blockIdx.x);
+    const int frame0 = blockIdx.z * 2;
+    if (lane < RZ3_GROUP) rows[lane] = __ldg(yt + lane);
+    if (lane == 0) {
+        const int s0 = __ldg(&yt[0].x) - 1;                                    // first source row of the window
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * frameBytes)) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(win)), "l"(reinterpret_cast<uint64_t>(&M.m[l])), "r"(bar), "r"(xs), "r"(s0),
+                       "r"((l == 1 ? 0 : P.frameBase) + frame0) : "memory");
+    }
+    __syncwarp();
+    const int fz = lane >> 4, frame = frame0 + fz;
+    const int x0 = (blockIdx.x * 16 + (lane & 15)) * 4;
+    if (x0 >= g.w + 4 || frame >= P.batch) return;       // lane 0 never leaves here: the window is consumed before the block retires
+
+    // column geometry, once per thread (as in k_resize)
+    const short4* xt = P.tabs + g.xtabOff;
+    short4 tx[4];
+    int bmin = 1 << 30;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        tx[j] = __ldg(xt + min(x0 + j, g.w + 3));
+        bmin = min(bmin, (int)tx[j].x);
+    }
+    const int a = bmin & ~3;
+    const uint32_t selShift = 0x3210u + 0x1111u * (uint32_t)(bmin - a);
+    uint32_t sel[4], coef[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        sel[j] = (uint32_t)(tx[j].x - bmin) | ((uint32_t)(tx[j].w - bmin) << 4);
+        coef[j] = (uint32_t)(uint16_t)tx[j].y | ((uint32_t)(uint16_t)tx[j].z << 16);
+    }
+    uint32_t srow = smem_u32(win) + fz * frameBytes + (a - xs);                // source row s, column a
+    uint32_t rowp = smem_u32(rows);
+    uint8_t* outp = P.pyr + (long long)frame * P.pyrFrameBytes + g.pyrOff + (long long)group * RZ3_ROWS * g.pitch + x0;
+    int pitch;
+    asm volatile("mov.u32 %0, %1;" : "=r"(pitch) : "r"(g.pitch));              // kept in a register (otherwise re-read from the parameters per row)
+    uint32_t A[4], B[4];
+    int tLower;
+    uint32_t tB0, tB1;
+    auto next_row = [&]() {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, _}, [%3];" : "=r"(tLower), "=r"(tB0), "=r"(tB1) : "r"(rowp));
+        rowp += 16;
+    };
+    auto hrow = [&](uint32_t (&r)[4]) {
+        uint32_t w0, w1, w2;
+        asm volatile("ld.shared.u32 %0, [%3]; ld.shared.u32 %1, [%3 + 4]; ld.shared.u32 %2, [%3 + 8];" : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(srow));
+        const uint32_t lo = __byte_perm(w0, w1, selShift), hi = __byte_perm(w1, w2, selShift);
+#pragma unroll
+        for (int j = 0; j < 4; j++) r[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;
+        srow += boxW;
+    };
+    // destination rows whose lower source row is s (just computed into `cur`; `prev` holds row s - 1)
+    auto flush = [&](int s, const uint32_t (&prev)[4], const uint32_t (&cur)[4]) {
+        while (tLower == s) {
+            uint32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = __umulhi(tB0, prev[j]) + __umulhi(tB1, cur[j]);
+            const uint32_t p01 = ((v[1] << 16) + v[0] + 0x00020002u) >> 2, p23 = ((v[3] << 16) + v[2] + 0x00020002u) >> 2;
+            *reinterpret_cast<uint32_t*>(outp) = __byte_perm(p01, p23, 0x6420);
+            outp += pitch;
+            next_row();
+        }
+    };
+    next_row();
+    int s = tLower - 1;
+    mbar_wait(bar, 0);
+    hrow(A);
+#pragma unroll 1
+    while (tLower >= 0) {                                                      // the sentinel ends the group
+        s++; hrow(B); flush(s, A, B);
+        if (tLower < 0) break;
+        s++; hrow(A); flush(s, B, A);
     }
 }
 
@@ -1710,6 +1823,11 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe2(const __grid_c
 // ======================================================================================
 using namespace orbb200;
 
+static size_t resize3_smem(const ExtractParams& P, int l)
+{
+    return (size_t)RZ3_WARPS * ((((size_t)2 * P.rz3BoxW[l] * P.rz3BoxH[l] + 127) & ~(size_t)127) + RZ3_GROUP * 16 + 8);
+}
+
 struct orbb200_extractor {
     int nfeatures, nlevels, iniTh, minTh, width, height, maxBatch, device, blurTaps;
     double scaleFactorD;
@@ -1723,7 +1841,7 @@ struct orbb200_extractor {
     size_t fastSmem, qtSmem;
     int fastVariant;           // 2 = k_fast2 (TMA tensor staging, default), 1 = k_fast (ORBB200_FAST_VARIANT=1: the first-generation kernel, kept for A/B runs)
     ResizeMaps resizeMaps;     // k_resize2's source-window maps (m[1] is encoded per call: level 0 may be the caller's buffer)
-    int resizeVariant;         // 2 = k_resize2 (TMA-staged source window, default), 1 = k_resize (ORBB200_RESIZE_VARIANT=1)
+    int resizeVariant;         // 3 = k_resize3 (source-row walk, default), 2 = k_resize2, 1 = k_resize (ORBB200_RESIZE_VARIANT, read at create)
     FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
     DescMaps descMaps;         // k_describe2's patch maps of the unblurred and the blurred levels (box 64 x 37)
     int descVariant, maxLevelKpCap;   // 2 = k_describe2 (default), 1 = k_describe (ORBB200_DESCRIBE_VARIANT=1, kept for A/B runs)
@@ -1777,7 +1895,7 @@ static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<shor
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int encode_level_map(CUtensorMap* map, const void* base, int w, int h, int frames, size_t pitch, size_t frameStride, int boxW, int boxH)
+static int encode_level_map(CUtensorMap* map, const void* base, int w, int h, int frames, size_t pitch, size_t frameStride, int boxW, int boxH, int boxFrames = 1)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -1789,7 +1907,7 @@ static int encode_level_map(CUtensorMap* map, const void* base, int w, int h, in
     }
     const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
-    const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxFrames};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1868,6 +1986,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     P.nlevels = nlevels; P.iniTh = iniThFAST; P.minTh = minThFAST; P.blurVariant = h->blurTaps;
     std::vector<short4> tabs;
     std::vector<int> rzXs;
+    std::vector<int4> ytab3;
     long long pyrOff = 0, blurOff = 0;
     int cells = 0, candOff = 0, kpOff = 0, tiles = 0, maxWCell = 0, maxHCell = 0, maxKpCap = 0;
     for (int l = 0; l < nlevels; l++) {
@@ -1940,6 +2059,35 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
             boxW = (int)align_up(boxW, 16);
             P.rzBoxW[l] = (boxW <= 256 && boxH <= 256) ? boxW : 0;      // a TMA box side is at most 256: larger scale factors keep k_resize
             P.rzBoxH[l] = boxH;
+            // k_resize3: the same per 64-column block, and the row table {lower source row, b0 << 16, b1 << 16, both taps on one row}
+            P.rz3XsOff[l] = (int)rzXs.size();
+            int boxW3 = 0, boxH3 = 0;
+            for (int bx = 0; bx * 64 < g.w + 4; bx++) {
+                int lo = 1 << 30, hi = 0;
+                for (int x0 = bx * 64; x0 < std::min(bx * 64 + 64, g.w + 4); x0 += 4) {
+                    int bmin = 1 << 30;
+                    for (int j = 0; j < 4; j++) bmin = std::min(bmin, (int)xt[std::min(x0 + j, g.w + 3)].x);
+                    lo = std::min(lo, bmin & ~3); hi = std::max(hi, (bmin & ~3) + 12);
+                }
+                rzXs.push_back(lo & ~15);
+                boxW3 = std::max(boxW3, hi - (lo & ~15));
+            }
+            bool monotone = true;
+            for (int y = 0; y < g.h; y++)
+                if (yt[y].y != yt[y].x + 1 || (y > 0 && yt[y].y < yt[y - 1].y)) monotone = false;
+            P.ytab3Off[l] = (int)ytab3.size();
+            for (int y0 = 0; y0 < g.h; y0 += RZ3_ROWS) {
+                for (int y = y0; y < y0 + RZ3_ROWS; y++) {
+                    const short4 e = yt[std::min(y, g.h - 1)];
+                    if (y < g.h) ytab3.push_back(make_int4((int)e.y, (int)((uint32_t)(uint16_t)e.z << 16), (int)((uint32_t)(uint16_t)e.w << 16), 0));
+                    else ytab3.push_back(make_int4(-1, 0, 0, 0));
+                }
+                ytab3.push_back(make_int4(-1, 0, 0, 0));
+                boxH3 = std::max(boxH3, (int)yt[std::min(y0 + RZ3_ROWS, g.h) - 1].y - ((int)yt[y0].y - 1) + 1);
+            }
+            boxW3 = (int)align_up(boxW3, 16);
+            P.rz3BoxW[l] = (monotone && boxW3 <= 256 && boxH3 <= 256) ? boxW3 : 0;
+            P.rz3BoxH[l] = boxH3;
         }
         g.blurTilesX = (g.w + 127) / 128;
         g.blurTileStart = tiles; tiles += g.blurTilesX * ((g.h + BL_ROWS - 1) / BL_ROWS);
@@ -2011,11 +2159,16 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     int* dRzXs = nullptr;
     TRY(dev_alloc(h, &dRzXs, rzXs.size() + 1));
     P.rzXs = dRzXs;
-    h->resizeVariant = 2;
-    if (const char* ev = getenv("ORBB200_RESIZE_VARIANT")) h->resizeVariant = atoi(ev) == 1 ? 1 : 2;
-    for (int l = 2; l < nlevels && h->resizeVariant == 2; l++)      // source = level l - 1 in the handle's pyramid slab
-        if (P.rzBoxW[l]) TRY(encode_level_map(&h->resizeMaps.m[l], P.pyr + P.lv[l - 1].pyrOff, P.lv[l - 1].w + 4, P.lv[l - 1].h, max_batch, P.lv[l - 1].pitch,
-                                              (size_t)P.pyrFrameBytes, P.rzBoxW[l], P.rzBoxH[l]));
+    int4* dYtab3 = nullptr;
+    TRY(dev_alloc(h, &dYtab3, ytab3.size() + 1));
+    P.ytab3 = dYtab3;
+    h->resizeVariant = 3;
+    if (const char* ev = getenv("ORBB200_RESIZE_VARIANT")) h->resizeVariant = std::max(1, std::min(3, atoi(ev)));
+    for (int l = 2; l < nlevels && h->resizeVariant >= 2; l++) {     // source = level l - 1 in the handle's pyramid slab
+        const bool v3 = h->resizeVariant == 3 && P.rz3BoxW[l];
+        if (v3 || P.rzBoxW[l]) TRY(encode_level_map(&h->resizeMaps.m[l], P.pyr + P.lv[l - 1].pyrOff, P.lv[l - 1].w + 4, P.lv[l - 1].h, max_batch, P.lv[l - 1].pitch,
+                                              (size_t)P.pyrFrameBytes, v3 ? P.rz3BoxW[l] : P.rzBoxW[l], v3 ? P.rz3BoxH[l] : P.rzBoxH[l], v3 ? 2 : 1));
+    }
     std::vector<uint32_t> blurTab;
     for (int l = 0; l < nlevels; l++)
         for (int ty = 0; ty < (P.lv[l].h + BL_ROWS - 1) / BL_ROWS; ty++)
@@ -2040,6 +2193,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     if (!cellTab.empty()) e = cudaMemcpy(dCells, cellTab.data(), cellTab.size() * sizeof(int4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !blurTab.empty()) e = cudaMemcpy(dBlurTiles, blurTab.data(), blurTab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !rzXs.empty()) e = cudaMemcpy(dRzXs, rzXs.data(), rzXs.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !ytab3.empty()) e = cudaMemcpy(dYtab3, ytab3.data(), ytab3.size() * sizeof(int4), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("extractor_create: %s", cudaGetErrorString(e)); orbb200_extractor_destroy(h); return ORBB200_ECUDA; }
     if (!tabs.empty()) e = cudaMemcpy(dTabs, tabs.data(), tabs.size() * sizeof(short4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(P.status, 0, sizeof(int));
@@ -2056,8 +2210,10 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     if (e == cudaSuccess && h->fastVariant == 1) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->fastVariant == 2) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast2<38, 64> : (const void*)k_fast2<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->descVariant == 2) e = ensure_dynamic_smem((const void*)k_describe2, device, DESC_WARPS * DESC_WARP_BYTES);
-    for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant == 2; l++)
-        e = ensure_dynamic_smem((const void*)k_resize2, device, (size_t)P.rzBoxW[l] * P.rzBoxH[l] + 16);
+    for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant >= 2; l++)
+        if (P.rzBoxW[l]) e = ensure_dynamic_smem((const void*)k_resize2, device, (size_t)P.rzBoxW[l] * P.rzBoxH[l] + 16);
+    for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant == 3; l++)
+        if (P.rz3BoxW[l]) e = ensure_dynamic_smem((const void*)k_resize3, device, resize3_smem(P, l));
     if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)k_quadtree, device, h->qtSmem);
     if (e == cudaSuccess) e = ensure_dynamic_smem(P.blurVariant ? (const void*)k_blur<true> : (const void*)k_blur<false>, device, BL_WARPS * BL_WARP_BYTES);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
@@ -2153,14 +2309,19 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
     ORB_CUDA(cudaMemsetAsync(P.candCount, 0, sizeof(int) * P.nlevels * batch, st));
 #define STAGE_MARK(i) do { if (h->profiling) ORB_CUDA(cudaEventRecord(h->ev[i], st)); } while (0)
     STAGE_MARK(0);
-    if (h->resizeVariant == 2 && P.nlevels > 1 && P.rzBoxW[1]) {
+    if (h->resizeVariant == 3 && P.nlevels > 1 && P.rz3BoxW[1]) {
+        int rc = encode_level_map(&h->resizeMaps.m[1], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, P.rz3BoxW[1], P.rz3BoxH[1], 2);
+        if (rc != ORBB200_OK) return rc;
+    } else if (h->resizeVariant >= 2 && P.nlevels > 1 && P.rzBoxW[1]) {
         int rc = encode_level_map(&h->resizeMaps.m[1], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, P.rzBoxW[1], P.rzBoxH[1]);
         if (rc != ORBB200_OK) return rc;
     }
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeo& g = P.lv[l];
         dim3 grid((g.w + 4 + 127) / 128, (g.h + RZ_ROWS * RZ_WARPS - 1) / (RZ_ROWS * RZ_WARPS), batch);
-        if (h->resizeVariant == 2 && P.rzBoxW[l]) k_resize2<<<grid, RZ_WARPS * 32, P.rzBoxW[l] * P.rzBoxH[l] + 16, st>>>(P, h->resizeMaps, l);
+        if (h->resizeVariant == 3 && P.rz3BoxW[l])
+            k_resize3<<<dim3((g.w + 4 + 63) / 64, (g.h + RZ3_ROWS * RZ3_WARPS - 1) / (RZ3_ROWS * RZ3_WARPS), (batch + 1) / 2), RZ3_WARPS * 32, resize3_smem(P, l), st>>>(P, h->resizeMaps, l);
+        else if (h->resizeVariant >= 2 && P.rzBoxW[l]) k_resize2<<<grid, RZ_WARPS * 32, P.rzBoxW[l] * P.rzBoxH[l] + 16, st>>>(P, h->resizeMaps, l);
         else k_resize<<<grid, RZ_WARPS * 32, 0, st>>>(P, l);
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
