@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <vector>
 #include "common.cuh"
 
@@ -118,6 +119,15 @@ __global__ void k_pad_level0(uint8_t* base, long long frameStride, int pitch, in
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Programmatic dependent launch (launch_pdl below): a kernel lets its successor in the stream start launching at once (the
+// successor's blocks become resident as this grid's blocks retire and run their set-up), and waits for its predecessor's
+// results right before it first touches anything an earlier kernel wrote.  Used inside the pyramid's chain of seven short
+// launches (0.173 -> 0.158 ms); measured and dropped between the long kernels: behind FAST and the quadtree it changes
+// nothing, and the persistent kernels (blur, descriptors) get SLOWER when their blocks become resident early (step 1.12 ->
+// 1.17 ms with the blur launched this way, 1.31 ms with the descriptors too).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -346,6 +356,7 @@ __global__ void __launch_bounds__(RZ3_WARPS * 32) k_resize3(const __grid_constan
     const LevelGeo& g = P.lv[l];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.y * RZ3_WARPS + warp;
+    pdl_trigger();
     if (group * RZ3_ROWS >= g.h) return;                                       // the whole warp
     const int boxW = P.rz3BoxW[l], frameBytes = boxW * P.rz3BoxH[l], warpBytes = (2 * frameBytes + 127) & ~127;
     uint8_t* win = smem + warp * warpBytes;
@@ -359,6 +370,7 @@ __global__ void __launch_bounds__(RZ3_WARPS * 32) k_resize3(const __grid_constan
         const int s0 = __ldg(&yt[0].x) - 1;                                    // first source row of the window
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        pdl_wait();                                                            // level l - 1 is complete
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * frameBytes)) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                      ::"r"(smem_u32(win)), "l"(reinterpret_cast<uint64_t>(&M.m[l])), "r"(bar), "r"(xs), "r"(s0),
@@ -1316,6 +1328,17 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
     constexpr uint32_t k0 = 18, k1 = 34, k2 = VARIANT ? 49 : 48, k3 = VARIANT ? 55 : 56;
     constexpr uint32_t kA = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);     // taps for p[x-3..x]
     constexpr uint32_t kB = k2 | (k1 << 8) | (k0 << 16);                  // taps for p[x+1..x+3]
+    // the 7 taps of output column x0 + j laid over the three aligned words w0 = p[x0-4..x0-1], w1 = p[x0..x0+3], w2 = p[x0+4..x0+7]
+    // (tap i sits on byte j + 1 + i of the twelve): dot products against constants, no byte shuffles
+    constexpr uint32_t kT[7] = {k0, k1, k2, k3, k2, k1, k0};
+    auto tapw = [](const uint32_t (&t)[7], int j, int w) constexpr {
+        uint32_t v = 0;
+        for (int b = 0; b < 4; b++) { const int i = 4 * w + b - j - 1; if (i >= 0 && i < 7) v |= t[i] << (8 * b); }
+        return v;
+    };
+    constexpr uint32_t c00 = tapw(kT, 0, 0), c01 = tapw(kT, 0, 1), c10 = tapw(kT, 1, 0), c11 = tapw(kT, 1, 1), c12 = tapw(kT, 1, 2),
+                       c20 = tapw(kT, 2, 0), c21 = tapw(kT, 2, 1), c22 = tapw(kT, 2, 2);
+    static_assert(tapw(kT, 0, 2) == 0 && tapw(kT, 3, 0) == 0 && tapw(kT, 3, 1) == kA && tapw(kT, 3, 2) == kB, "tap layout");
     constexpr uint32_t kV01 = k0 | (k1 << 8), kV23 = k2 | (k3 << 8), kV45 = k2 | (k1 << 8);   // vertical taps by row pair
 
     // issue the 42 row copies of tile bt into ring stage s
@@ -1360,15 +1383,15 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
             const int nOut = min(BL_ROWS, g.h - cur.y0);                             // output rows of this tile
             const uint8_t* sb = ring + stage * BL_STAGE_BYTES + 12 + 4 * lane;      // word holding columns x0-4..x0-1
             uint8_t* outp = P.blur + (long long)cur.frame * P.blurFrameBytes + g.blurOff + (long long)cur.y0 * g.pitch + x0;
-            // horizontal pass of one staged row: 4 sums of 7 taps (<= 255 * 256, 16 bits), two IDP.4A each
+            // horizontal pass of one staged row: 4 sums of 7 taps (<= 255 * 256, 16 bits), ten IDP.4A against constant tap words
             auto hrow = [&](int ir, uint32_t (&h)[4]) {
                 const uint32_t* rw = reinterpret_cast<const uint32_t*>(sb + ir * BL_ROW_BYTES);
                 uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
                 if (left) w0 = __byte_perm(w1, w2, 0x1234);            // p[-4..-1] = p[4], p[3], p[2], p[1]
                 if (rightFix) w2 = __byte_perm(w0, w1, 0x3456);        // p[w..w+3] = p[w-2], p[w-3], p[w-4], p[w-5]
-                h[0] = __dp4a(__byte_perm(w0, w1, 0x4321), kA, __dp4a(__byte_perm(w1, w2, 0x4321), kB, 0u));
-                h[1] = __dp4a(__byte_perm(w0, w1, 0x5432), kA, __dp4a(__byte_perm(w1, w2, 0x5432), kB, 0u));
-                h[2] = __dp4a(__byte_perm(w0, w1, 0x6543), kA, __dp4a(__byte_perm(w1, w2, 0x6543), kB, 0u));
+                h[0] = __dp4a(w0, c00, __dp4a(w1, c01, 0u));
+                h[1] = __dp4a(w0, c10, __dp4a(w1, c11, __dp4a(w2, c12, 0u)));
+                h[2] = __dp4a(w0, c20, __dp4a(w1, c21, __dp4a(w2, c22, 0u)));
                 h[3] = __dp4a(w1, kA, __dp4a(w2, kB, 0u));
             };
             // Vertical pass on PAIRS of rows: Q[s][j] = H[r][j] | H[r + 1][j] << 16 for the six most recent pairs, so an
@@ -1822,6 +1845,22 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe2(const __grid_c
 // host side: handle, geometry, launches, C ABI
 // ======================================================================================
 using namespace orbb200;
+
+// Launch with programmatic stream serialization: the kernel may start once its predecessor in the stream has let it
+// (pdl_trigger), and orders itself behind the predecessor's results with pdl_wait.  Behind anything that is not a kernel
+// (a memset, an event) the attribute has no effect; the kernel behind such a launch needs no change (FAST after the pyramid's
+// last level waits for the whole grid as usual).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 static size_t resize3_smem(const ExtractParams& P, int l)
 {
@@ -2320,7 +2359,7 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
         const LevelGeo& g = P.lv[l];
         dim3 grid((g.w + 4 + 127) / 128, (g.h + RZ_ROWS * RZ_WARPS - 1) / (RZ_ROWS * RZ_WARPS), batch);
         if (h->resizeVariant == 3 && P.rz3BoxW[l])
-            k_resize3<<<dim3((g.w + 4 + 63) / 64, (g.h + RZ3_ROWS * RZ3_WARPS - 1) / (RZ3_ROWS * RZ3_WARPS), (batch + 1) / 2), RZ3_WARPS * 32, resize3_smem(P, l), st>>>(P, h->resizeMaps, l);
+            launch_pdl(k_resize3, dim3((g.w + 4 + 63) / 64, (g.h + RZ3_ROWS * RZ3_WARPS - 1) / (RZ3_ROWS * RZ3_WARPS), (batch + 1) / 2), RZ3_WARPS * 32, resize3_smem(P, l), st, P, h->resizeMaps, l);
         else if (h->resizeVariant >= 2 && P.rzBoxW[l]) k_resize2<<<grid, RZ_WARPS * 32, P.rzBoxW[l] * P.rzBoxH[l] + 16, st>>>(P, h->resizeMaps, l);
         else k_resize<<<grid, RZ_WARPS * 32, 0, st>>>(P, l);
         ORB_CHECK_LAUNCH("k_resize"); launches++;
