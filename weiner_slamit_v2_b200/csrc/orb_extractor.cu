@@ -1839,6 +1839,196 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe2(const __grid_c
     }
 }
 
+// ---- k_describe, third generation: the per-keypoint scalar work is done for a group of keypoints at once ---------------------
+// ncu (r2z) on k_describe2: the moments and the 256 comparisons are only ~40 % of its 624 warp instructions per keypoint; the rest
+// is work every lane repeats with the same operands -- finding the slot's frame / level / keypoint (12 %, an integer division in
+// it), fastAtan2 and the double-precision sin/cos (16 %), the cv::KeyPoint record (7 %), issuing the copies (8 %).  Here a warp
+// takes GROUPS of P.descChunk (8; 1 in small calls) consecutive output rows of one frame, and works on two groups at a time:
+//  * lane i finds keypoint i of a group (level by comparing with the frame's running level counts, one load of the packed level
+//    keypoint): once per group;
+//  * a step = the moments of keypoint k of group g (unblurred patch) AND the descriptor of keypoint k of group g - 1 (blurred
+//    patch, sin/cos by shuffle from lane k).  Both patches arrive as TMA copies behind one mbarrier, the next step's copies are in
+//    flight while this one is worked on -- the same latency cover as k_describe2, where a step was one keypoint's two patches;
+//  * between two rounds the lanes compute the angles, sin/cos and keypoint records of group g side by side: one pass per group.
+// (First attempt, measured: moments of a whole group, then its descriptors, one ring of patch slots with two copies ahead --
+// 0.245 ms against k_describe2's 0.209: a moments step is too short for two copies ahead to cover the copy latency.)
+constexpr int D3_WARP_BYTES = 2 * DESC_BUF + 128;          // two step buffers (unblurred + blurred patch) + the warp's two mbarriers
+constexpr int D3_CTA_BYTES = DESC_WARPS * D3_WARP_BYTES + 8 * 32 * 8;      // + the IC_Angle weight words
+
+__global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe3(const __grid_constant__ ExtractParams P, const __grid_constant__ DescMaps M)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int DG = P.descChunk;                                                // keypoints per group (<= 32)
+    const int gpf = (P.outCap + DG - 1) / DG;                                  // groups per frame
+    const int nItems = P.batch * gpf, nw = gridDim.x * DESC_WARPS;
+    int item = blockIdx.x * DESC_WARPS + warp;
+
+    // per-lane constants: level tables and the lane's 16 pattern points
+    const int kpOffLane = lane < P.nlevels ? P.lv[lane].kpOff : 0;
+    const float scaleLane = lane < P.nlevels ? P.lv[lane].scale : 0.f, sizeLane = lane < P.nlevels ? P.lv[lane].kpSize : 0.f;
+    float2 pat[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) pat[k] = __ldg(&d_pattern_f.v[k * 32 + lane]);
+    // (the 8 IC_Angle weight words of every lane sit in shared memory, one conflict-free 8-byte load per step: in registers they
+    // pushed the kernel past the 80 it may use at three blocks per SM)
+    const uint2* wgt = reinterpret_cast<const uint2*>(smem + DESC_WARPS * D3_WARP_BYTES);
+    for (int i = threadIdx.x; i < 8 * 32; i += DESC_WARPS * 32) const_cast<uint2*>(wgt)[i] = __ldg(&d_angle.w[i >> 5][i & 31]);
+    __syncthreads();
+    wgt += lane;
+
+    uint8_t* buf = smem + (size_t)warp * D3_WARP_BYTES;
+    const uint32_t buf32 = smem_u32(buf), bar0 = buf32 + 2 * DESC_BUF;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (item >= nItems) return;
+
+    // A group: frame, first output row, number of keypoints (0: no group), and in lane i keypoint i's packed level record and level.
+    int nN = 0, frameN = 0, o0N = 0, lN = 0;  uint32_t eN = 0;                 // the group after next (decoded ahead)
+    int nA = 0, frameA = 0, o0A = 0, lA = 0;  uint32_t eA = 0;                 // the group whose moments are being taken
+    int nD = 0, frameD = 0, o0D = 0;          uint32_t eD = 0;                 // the group whose descriptors are being made
+    float caD = 0.f, sbD = 0.f;                                                // ... and lane i's cos / sin of keypoint i's angle
+    // the next non-empty group of this warp at or after `item` into N (nN = 0: none left)
+    auto decode = [&]() {
+        nN = 0;
+        while (item < nItems) {
+            const int f = item / gpf, o0 = (item - f * gpf) * DG;
+            item += nw;
+            const int cnt = lane < P.nlevels ? __ldg(P.lkpCount + f * P.nlevels + lane) : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }   // MAXL = 16 levels
+            const int total = min(__shfl_sync(FULL, incl, 15), P.outCap);     // (more cannot happen: outCap = the sum of the level capacities)
+            if (o0 == 0 && lane == 0) P.outCount[f] = total;                  // the frame's first group publishes its total (also 0)
+            const int n = min(total - o0, DG);
+            if (n <= 0) continue;
+            const int o = o0 + lane;
+            int l = 0;
+            for (int q = 0; q + 1 < P.nlevels; q++) l += (__shfl_sync(FULL, incl, q) <= o) ? 1 : 0;
+            const int pre = __shfl_sync(FULL, incl - cnt, l), off = __shfl_sync(FULL, kpOffLane, l);
+            frameN = f; o0N = o0; nN = n; lN = l;
+            eN = lane < n ? __ldg(P.lkp + (long long)f * P.kpFrameCap + off + (o - pre)) : 0u;
+            return;
+        }
+    };
+    // the copies of one step into buffer s: the unblurred patch of keypoint k of group (na, ...) and the blurred patch of
+    // keypoint k of group (nd, ...), whichever exist (at least one does)
+    auto issue = [&](int na, int fa, uint32_t ea, int la, int nd, int fd, uint32_t ed, int ld, int k, int s) {
+        const uint32_t ka = __shfl_sync(FULL, ea, k), kd = __shfl_sync(FULL, ed, k);
+        const int lka = __shfl_sync(FULL, la, k), lkd = __shfl_sync(FULL, ld, k);
+        const uint32_t bar = bar0 + 8 * s, dst = buf32 + s * DESC_BUF;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of this buffer are done
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t bytes = (k < na ? DESC_UW * DESC_UROWS : 0) + (k < nd ? DESC_BW * DESC_BROWS : 0);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            if (k < na) {
+                const int x = (ka & 0xfff) + BORDER, y = ((ka >> 12) & 0xfff) + BORDER;
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&M.u[lka])), "r"(bar), "r"((x - 16) & ~15), "r"(y - HALF_PATCH),
+                               "r"((lka == 0 ? 0 : P.frameBase) + fa) : "memory");
+            }
+            if (k < nd) {
+                const int x = (kd & 0xfff) + BORDER, y = ((kd >> 12) & 0xfff) + BORDER;
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                             ::"r"(dst + DESC_USLOT), "l"(reinterpret_cast<uint64_t>(&M.b[lkd])), "r"(bar), "r"((x - DESC_HALF) & ~15), "r"(y - DESC_HALF),
+                               "r"(P.frameBase + fd) : "memory");
+            }
+        }
+    };
+
+    decode();
+    if (nN == 0) return;
+    nA = nN; frameA = frameN; o0A = o0N; lA = lN; eA = eN;
+    decode();
+    int lD = 0;
+    issue(nA, frameA, eA, lA, 0, 0, 0u, 0, 0, 0);
+    uint32_t phase = 0;                                                       // bit s = parity to wait for on buffer s
+    int s = 0;
+#pragma unroll 1
+    while (nA | nD) {
+        const int K = max(nA, nD);
+        const int xA = (eA & 0xfff) + BORDER, xD = (eD & 0xfff) + BORDER;     // lane i: keypoint i of either group
+        uint8_t* outd = P.outDesc + ((long long)frameD * P.outCap + o0D) * 32 + lane;
+        int M10 = 0, M01 = 0;
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            // the next step's copies: this round's step k + 1, or step 0 of the next round (moments of N, descriptors of A)
+            if (k + 1 < K) issue(nA, frameA, eA, lA, nD, frameD, eD, lD, k + 1, s ^ 1);
+            else if (nN | nA) issue(nN, frameN, eN, lN, nA, frameA, eA, lA, 0, s ^ 1);
+            mbar_wait(bar0 + 8 * s, (phase >> s) & 1);
+            phase ^= 1u << s;
+            const uint8_t* pu = buf + s * DESC_BUF;                           // unblurred patch: rows y - 15 .. y + 15, columns from (x - 16) & ~15
+            if (k < nA) {
+                // ---- intensity centroid over the radius-15 disc of the UNBLURRED level (weights: see d_angle) ----
+                const int x = __shfl_sync(FULL, xA, k);
+                int m10 = 0, m01 = 0;
+                // columns x - 16 .. x + 15 = patch bytes b0 .. b0 + 31; lane owns word j = lane & 7 of row v = -15 + 4 * it + (lane >> 3)
+                const int b0 = (x - 16) & 15, sh = (b0 & 3) * 8;
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(pu + (lane >> 3) * DESC_UW) + (b0 >> 2) + (lane & 7);
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    if (it < 7 || lane < 24) {                                 // the last step holds rows 13, 14, 15 only
+                        const uint32_t px = __funnelshift_r(p[0], p[1], sh);
+                        const uint2 w = wgt[it * 32];
+                        m10 = dp4a_u8s8(px, w.x, m10);
+                        m01 = dp4a_u8s8(px, w.y, m01);
+                    }
+                    p += 4 * DESC_UW / 4;
+                }
+                m10 = __reduce_add_sync(FULL, m10);
+                m01 = __reduce_add_sync(FULL, m01);
+                if (lane == k) { M10 = m10; M01 = m01; }
+            }
+            if (k < nD) {
+                // ---- descriptor on the BLURRED level: lane b produces byte b (pairs 8b..8b+7) ----
+                const int x = __shfl_sync(FULL, xD, k);
+                const float a = __shfl_sync(FULL, caD, k), b = __shfl_sync(FULL, sbD, k);
+                // cvRound(v) = bits(v + 1.5 * 2^23) - 0x4B400000 (round to nearest even, |v| < 2^22).  The sample's shared-memory address
+                // is base + ry * 64 + rx in 32-bit arithmetic that wraps, so the two constants are folded into the base once
+                const float MAGIC = 12582912.0f;
+                const uint32_t cb = smem_u32(pu + DESC_USLOT) + DESC_HALF * DESC_BW + ((x - DESC_HALF) & 15) + DESC_HALF - 0x4B400000u * (uint32_t)(DESC_BW + 1);
+                int val = 0;
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    uint32_t t[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float2 pt = pat[2 * kk + h];
+                        const uint32_t ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), MAGIC));
+                        const uint32_t rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), MAGIC));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[h]) : "r"(cb + ry * (uint32_t)DESC_BW + rx));
+                    }
+                    val |= (t[0] < t[1]) << kk;
+                }
+                outd[k * 32] = (uint8_t)val;
+            }
+            s ^= 1;
+        }
+        // ---- group A's angles, sin/cos and keypoint records, lane i for keypoint i; A becomes D, N becomes A ----
+        const float angle = fast_atan2_deg((float)M01, (float)M10);
+        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+        libm_sincosf(__fmul_rn(angle, factorPI), sbD, caD);
+        const float sc = __shfl_sync(FULL, scaleLane, lA), ksz = __shfl_sync(FULL, sizeLane, lA);
+        if (lane < nA) {                                                       // cv::KeyPoint layout, coordinates scaled to level 0 (:1126-1132)
+            float fx = (float)xA, fy = (float)(int)(((eA >> 12) & 0xfff) + BORDER);
+            if (lA != 0) { fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); }
+            uint32_t* rec = reinterpret_cast<uint32_t*>(P.outKp + (long long)frameA * P.outCap + o0A + lane);
+            rec[0] = __float_as_uint(fx); rec[1] = __float_as_uint(fy); rec[2] = __float_as_uint(ksz); rec[3] = __float_as_uint(angle);
+            rec[4] = __float_as_uint((float)(eA >> 24)); rec[5] = (uint32_t)lA; rec[6] = 0xffffffffu;
+        }
+        __syncwarp();
+        nD = nA; frameD = frameA; o0D = o0A; eD = eA; lD = lA;
+        nA = nN; frameA = frameN; o0A = o0N; eA = eN; lA = lN;
+        if (nA) decode(); else nN = 0;
+    }
+}
+
 }  // namespace orbb200
 
 // ======================================================================================
@@ -1883,7 +2073,7 @@ struct orbb200_extractor {
     int resizeVariant;         // 3 = k_resize3 (source-row walk, default), 2 = k_resize2, 1 = k_resize (ORBB200_RESIZE_VARIANT, read at create)
     FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
     DescMaps descMaps;         // k_describe2's patch maps of the unblurred and the blurred levels (box 64 x 37)
-    int descVariant, maxLevelKpCap;   // 2 = k_describe2 (default), 1 = k_describe (ORBB200_DESCRIBE_VARIANT=1, kept for A/B runs)
+    int descVariant, maxLevelKpCap;   // 3 = k_describe3 (default), 2 = k_describe2, 1 = k_describe (ORBB200_DESCRIBE_VARIANT, kept for A/B runs)
     int lastLaunches, lastBatch;
     int realCandCap[MAXL];     // per-level candidate capacity as computed at create (orbb200_extractor_debug_set_capacity clamps P.lv[l].candCap)
     int chunkOverride;         // ORBB200_CHUNKS read once at create (0 = choose by batch size): tuning knob of the blocking host call
@@ -2215,11 +2405,11 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     uint32_t* dBlurTiles = nullptr;
     TRY(dev_alloc(h, &dBlurTiles, blurTab.size() + 1));
     P.blurTiles = dBlurTiles;
-    h->descVariant = 2;
-    if (const char* ev = getenv("ORBB200_DESCRIBE_VARIANT")) h->descVariant = atoi(ev) == 1 ? 1 : 2;
+    h->descVariant = 3;
+    if (const char* ev = getenv("ORBB200_DESCRIBE_VARIANT")) h->descVariant = std::max(1, std::min(3, atoi(ev)));
     h->maxLevelKpCap = 0;
     for (int l = 0; l < nlevels; l++) h->maxLevelKpCap = std::max(h->maxLevelKpCap, P.lv[l].kpCap);
-    for (int l = 0; l < nlevels && h->descVariant == 2; l++) {
+    for (int l = 0; l < nlevels && h->descVariant >= 2; l++) {
         if (l > 0) TRY(encode_level_map(&h->descMaps.u[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes, DESC_UW, DESC_UROWS));
         TRY(encode_level_map(&h->descMaps.b[l], P.blur + P.lv[l].blurOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.blurFrameBytes, DESC_BW, DESC_BROWS));
     }
@@ -2249,6 +2439,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     if (e == cudaSuccess && h->fastVariant == 1) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->fastVariant == 2) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast2<38, 64> : (const void*)k_fast2<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->descVariant == 2) e = ensure_dynamic_smem((const void*)k_describe2, device, DESC_WARPS * DESC_WARP_BYTES);
+    if (e == cudaSuccess && h->descVariant == 3) e = ensure_dynamic_smem((const void*)k_describe3, device, D3_CTA_BYTES);
     for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant >= 2; l++)
         if (P.rzBoxW[l]) e = ensure_dynamic_smem((const void*)k_resize2, device, (size_t)P.rzBoxW[l] * P.rzBoxH[l] + 16);
     for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant == 3; l++)
@@ -2410,13 +2601,18 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
         ORB_CUDA(cudaStreamWaitEvent(st, h->evJoin, 0));
     }
     STAGE_MARK(4);
-    if (h->descVariant == 2) {
+    if (h->descVariant >= 2) {
         int rc = encode_level_map(&h->descMaps.u[0], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, DESC_UW, DESC_UROWS);
         if (rc != ORBB200_OK) return rc;
         // full batches: persistent warps over chunks of 4 rows; calls of a few frames (latency counts): one row per warp and step
         ExtractParams Pd = P;
         Pd.descChunk = batch <= SIDE_MAX_BATCH ? 1 : 4;
         const int ctas = std::max(1, std::min(h->numSMs * DESC_CTAS_PER_SM, (batch * P.outCap + DESC_WARPS * Pd.descChunk - 1) / (DESC_WARPS * Pd.descChunk)));
+        if (h->descVariant == 3) {       // groups of 8 output rows per warp and step (1 in calls of a few frames)
+            Pd.descChunk = batch <= SIDE_MAX_BATCH ? 1 : 8;
+            const int items = batch * ((P.outCap + Pd.descChunk - 1) / Pd.descChunk);
+            k_describe3<<<std::max(1, std::min(h->numSMs * DESC_CTAS_PER_SM, (items + DESC_WARPS - 1) / DESC_WARPS)), DESC_WARPS * 32, D3_CTA_BYTES, st>>>(Pd, h->descMaps);
+        } else
         k_describe2<<<ctas, DESC_WARPS * 32, DESC_WARPS * DESC_WARP_BYTES, st>>>(Pd, h->descMaps);
     } else
     k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
