@@ -1272,22 +1272,25 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
 // ======================================================================================
 // K5: GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (:1117), 8.8 fixed point like OpenCV
 // ======================================================================================
-// A warp owns a 128 x 36 output tile.  The 42 input rows it needs are fetched by the TMA unit as 1-D
-// bulk copies (cp.async.bulk, one per row, completion counted on an mbarrier) into a two-stage ring in
-// shared memory, so the loads of tile t+1 fly while tile t is being filtered and no load latency sits
-// on the critical path.  REFLECT_101 in y is a choice of source row per copy; in x it is one PRMT at the
-// left edge and (level 0 only) at the right edge -- levels >= 1 carry their reflected continuation in
-// columns w..w+3 (written by k_resize).
-// Arithmetic, per thread = 4 adjacent pixels: horizontal pass on packed bytes, two IDP.4A per pixel on
-// byte windows cut out of three words with PRMT; vertical pass over a 7-row register window of 16-bit
-// row sums (loop unrolled by 7 so the window rotates by renaming), symmetric taps folded;
-// out = (sum + 2^15) >> 16 is byte 2 of the accumulator.
+// A warp owns a 128 x 24 output tile.  Its 160 x 30 input window arrives as ONE 3-D TMA tensor copy (completion on an
+// mbarrier) into a two-stage ring in shared memory, so the window of tile t+1 flies while tile t is being filtered and no load
+// latency sits on the critical path.  (Round 1 issued one 1-D bulk copy per row: the compiler serialises such copies over the
+// lanes -- ELECT, five R2UR, UBLKCP, branch -- and ncu r2z counted 13.5 % of the kernel's instructions there.)  REFLECT_101 in
+// y: rows outside the level arrive as zeros and the (at most three) rows a border tile needs are copied over them inside shared
+// memory; in x it is one PRMT at the left edge and (level 0 only) at the right edge -- levels >= 1 carry their reflected
+// continuation in columns w..w+3 (written by k_resize).
+// Arithmetic, per thread = 4 adjacent pixels: horizontal pass = ten IDP.4A of the three aligned words against constant tap
+// words; vertical pass over a window of six row PAIRS of 16-bit row sums (loop unrolled by 6 so the window rotates by
+// renaming), two taps per IDP.2A; out = (sum + 2^15) >> 16 is byte 2 of the accumulator.
 constexpr int BL_ROWS = 24, BL_WARPS = 4;     // 24 output rows + 6 halo rows = 5 groups of 6 input rows (measured 24 / 36: 0.243 / 0.247 ms)
 constexpr int BL_IN_ROWS = BL_ROWS + 6;
 constexpr int BL_CTAS_PER_SM = 5;             // persistent CTAs per SM (shared memory: 9.6 KB per warp)
 constexpr int BL_ROW_BYTES = 160;             // image columns x0-16 .. x0+143 (16-byte aligned window around 128 px)
-constexpr int BL_STAGE_BYTES = BL_IN_ROWS * BL_ROW_BYTES;
-constexpr int BL_WARP_BYTES = 2 * BL_STAGE_BYTES + 16;
+constexpr int BL_WINDOW_BYTES = BL_IN_ROWS * BL_ROW_BYTES;
+constexpr int BL_STAGE_BYTES = (BL_WINDOW_BYTES + 127) / 128 * 128;      // a TMA destination is 128-byte aligned
+constexpr int BL_WARP_BYTES = 2 * BL_STAGE_BYTES + 128;
+
+struct BlurMaps { CUtensorMap m[MAXL]; };     // {column, row, frame} over each level incl. its continuation columns, box 160 x 30 x 1
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
@@ -1310,9 +1313,9 @@ __device__ __forceinline__ bool blur_tile(const ExtractParams& P, unsigned t, Bl
 }
 
 template <bool VARIANT>     // false: OpenCV >= 3 taps {18,34,48,56,48,34,18}; true: OpenCV 2.4.9 taps {18,34,49,55,49,34,18}
-__global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
+__global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const __grid_constant__ ExtractParams P, const __grid_constant__ BlurMaps M)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* ring = smem + (size_t)warp * BL_WARP_BYTES;
     const uint32_t bar0 = smem_u32(ring + 2 * BL_STAGE_BYTES);          // two 8-byte mbarriers
@@ -1341,25 +1344,16 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
     static_assert(tapw(kT, 0, 2) == 0 && tapw(kT, 3, 0) == 0 && tapw(kT, 3, 1) == kA && tapw(kT, 3, 2) == kB, "tap layout");
     constexpr uint32_t kV01 = k0 | (k1 << 8), kV23 = k2 | (k3 << 8), kV45 = k2 | (k1 << 8);   // vertical taps by row pair
 
-    // issue the 42 row copies of tile bt into ring stage s
+    // issue the window copy of tile bt into ring stage s: columns x0 - 16 .. x0 + 143, rows y0 - 3 .. y0 + 26 (zeros outside the level)
     auto issue = [&](const BlurTile& bt, int s) {
-        const LevelGeo& g = P.lv[bt.l];
-        int pitch;
-        const uint8_t* img = level_ptr(P, bt.l, bt.frame, pitch);
-        const int rowLimit = bt.l == 0 ? P.inRowBytes : pitch;          // bytes of a row that may be read (multiple of 16)
-        const int xs = max(bt.x0 - 16, 0), xe = min(bt.x0 + 144, rowLimit);
-        const uint32_t nbytes = (uint32_t)(xe - xs);
-        const uint32_t bar = bar0 + 8 * s;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage are done
-        if (lane == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbytes * BL_IN_ROWS) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads (and border-row writes) of this stage are done
         __syncwarp();
-        for (int ir = lane; ir < BL_IN_ROWS; ir += 32) {
-            const int iy = reflect101(min(bt.y0 - 3 + ir, g.h + 2), g.h);
-            const uint8_t* src = img + (long long)iy * pitch + xs;
-            const uint32_t dst = smem_u32(ring + s * BL_STAGE_BYTES + ir * BL_ROW_BYTES + (xs - (bt.x0 - 16)));
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(src), "r"(nbytes), "r"(bar) : "memory");
+        if (lane == 0) {
+            const uint32_t bar = bar0 + 8 * s;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)BL_WINDOW_BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(smem_u32(ring + s * BL_STAGE_BYTES)), "l"(reinterpret_cast<uint64_t>(&M.m[bt.l])), "r"(bar), "r"(bt.x0 - 16), "r"(bt.y0 - 3),
+                           "r"((bt.l == 0 ? 0 : P.frameBase) + bt.frame) : "memory");
         }
     };
 
@@ -1377,6 +1371,26 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
         if (stage == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; } else { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
 
         const LevelGeo& g = P.lv[cur.l];
+        {   // REFLECT_101 in y: window row ir holds image row y0 - 3 + ir; rows -3..-1 are rows 3..1 and rows h..h+2 are rows h-2..h-4
+            // (rows further down only feed output rows that are not stored)
+            uint32_t* st = reinterpret_cast<uint32_t*>(ring + stage * BL_STAGE_BYTES);
+            bool fixed = false;
+            if (cur.y0 == 0) {
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    for (int i = lane; i < BL_ROW_BYTES / 4; i += 32) st[r * (BL_ROW_BYTES / 4) + i] = st[(6 - r) * (BL_ROW_BYTES / 4) + i];
+                fixed = true;
+            }
+            const int irH = g.h - (cur.y0 - 3);                                     // window row of image row h
+            if (irH < BL_IN_ROWS) {
+                for (int ir = irH; ir < min(irH + 3, BL_IN_ROWS); ir++) {
+                    const int src = 2 * irH - 2 - ir;                               // image row 2 (h - 1) - y
+                    for (int i = lane; i < BL_ROW_BYTES / 4; i += 32) st[ir * (BL_ROW_BYTES / 4) + i] = st[src * (BL_ROW_BYTES / 4) + i];
+                }
+                fixed = true;
+            }
+            if (fixed) __syncwarp();
+        }
         const int x0 = cur.x0 + 4 * lane;
         if (x0 < g.w) {
             const bool left = x0 == 0, rightFix = (cur.l == 0) && !P.inPadded && (x0 + 4 >= g.w);
@@ -1403,7 +1417,7 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
             for (int u = 1; u < 6; u++) {                                            // rows 1..5 only fill the window
                 hrow(u, cur4);
 #pragma unroll
-                for (int j = 0; j < 4; j++) { Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410); prev[j] = cur4[j]; }
+                for (int j = 0; j < 4; j++) { Q[u][j] = cur4[j] * 65536u + prev[j]; prev[j] = cur4[j]; }
             }
 #pragma unroll 1
             for (int grp = 1; grp < BL_IN_ROWS / 6; grp++) {
@@ -1420,7 +1434,7 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const ExtractParams P)
                         acc[j] = __dp2a_lo(Q[(u + 1) % 6][j], kV01, __dp2a_lo(Q[(u + 3) % 6][j], kV23,
                                  __dp2a_lo(Q[(u + 5) % 6][j], kV45, k0 * cur4[j] + 32768u)));
                         if (VARIANT) acc[j] = min(acc[j], 0x00ffffffu);          // taps sum to 257: saturate like OpenCV
-                        Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410);
+                        Q[u][j] = cur4[j] * 65536u + prev[j];                   // (an IMAD: the FMA pipe has room, the ALU pipe does not)
                         prev[j] = cur4[j];
                     }
                     const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
@@ -2071,6 +2085,7 @@ struct orbb200_extractor {
     int fastVariant;           // 2 = k_fast2 (TMA tensor staging, default), 1 = k_fast (ORBB200_FAST_VARIANT=1: the first-generation kernel, kept for A/B runs)
     ResizeMaps resizeMaps;     // k_resize2's source-window maps (m[1] is encoded per call: level 0 may be the caller's buffer)
     int resizeVariant;         // 3 = k_resize3 (source-row walk, default), 2 = k_resize2, 1 = k_resize (ORBB200_RESIZE_VARIANT, read at create)
+    BlurMaps blurMaps;         // k_blur's window maps (level 0 per call)
     FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
     DescMaps descMaps;         // k_describe2's patch maps of the unblurred and the blurred levels (box 64 x 37)
     int descVariant, maxLevelKpCap;   // 3 = k_describe3 (default), 2 = k_describe2, 1 = k_describe (ORBB200_DESCRIBE_VARIANT, kept for A/B runs)
@@ -2413,6 +2428,8 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
         if (l > 0) TRY(encode_level_map(&h->descMaps.u[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes, DESC_UW, DESC_UROWS));
         TRY(encode_level_map(&h->descMaps.b[l], P.blur + P.lv[l].blurOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.blurFrameBytes, DESC_BW, DESC_BROWS));
     }
+    for (int l = 1; l < nlevels; l++)
+        TRY(encode_level_map(&h->blurMaps.m[l], P.pyr + P.lv[l].pyrOff, P.lv[l].pitch, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes, BL_ROW_BYTES, BL_IN_ROWS));
     for (int l = 1; l < nlevels && h->fastVariant == 2; l++)      // levels >= 1 live in the handle's pyramid slab: maps made once
         TRY(encode_level_map(&h->fastMaps.m[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes,
                              P.fastLarge ? FastGeo2<38, 64>::BW : FastGeo2<26, 42>::BW, P.fastLarge ? 64 : 42));
@@ -2589,8 +2606,10 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
     {   // persistent warps: a few CTAs per SM walk the (frame, level, tile) list
         const long long tiles = (long long)h->totalBlurTiles * batch;
         const int ctas = (int)std::min<long long>((tiles + BL_WARPS - 1) / BL_WARPS, (long long)h->numSMs * BL_CTAS_PER_SM);
-        if (P.blurVariant) k_blur<true><<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, bs>>>(P);
-        else k_blur<false><<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, bs>>>(P);
+        int rc = encode_level_map(&h->blurMaps.m[0], P.in, P.inRowBytes, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, BL_ROW_BYTES, BL_IN_ROWS);
+        if (rc != ORBB200_OK) return rc;
+        if (P.blurVariant) k_blur<true><<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, bs>>>(P, h->blurMaps);
+        else k_blur<false><<<ctas, BL_WARPS * 32, BL_WARPS * BL_WARP_BYTES, bs>>>(P, h->blurMaps);
     }
     ORB_CHECK_LAUNCH("k_blur"); launches++;
     if (beside) {
