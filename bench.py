@@ -1107,7 +1107,7 @@ def _issue_profile(kernel):
         if os.path.exists(p):
             with open(p) as f:
                 for e in json.load(f):
-                    if e["kernel"] in (kernel, kernel + "2"):
+                    if e["kernel"] in (kernel, kernel + "2", kernel + "3"):
                         return {"issue_slots_busy_pct": e["issue_active_pct"], "warp_instructions_per_launch": e["inst_executed"],
                                 "dram_pct_of_peak": e["dram_pct"], "source": "profiles/%s_ncu_full_summary.json" % tag}
     return None

@@ -413,12 +413,13 @@ def test_handles_on_two_devices_interleaved():
             assert np.array_equal(m.image_bounds(640, 480, REFERENCE_K, REFERENCE_DIST), O.image_bounds(640, 480, REFERENCE_K, REFERENCE_DIST))
 
 
-@pytest.mark.parametrize("fast,describe", [("1", "1"), ("1", "2"), ("2", "1")])
-def test_first_generation_kernels_stay_bit_exact(fast, describe, monkeypatch):
-    """Round 1's k_fast / k_describe stay selectable for A/B runs (ORBB200_FAST_VARIANT / ORBB200_DESCRIBE_VARIANT, read when a
-    handle is created): every combination gives the oracle's result."""
+@pytest.mark.parametrize("fast,describe,resize", [("1", "1", "1"), ("1", "3", "3"), ("2", "1", "3"), ("2", "3", "1")])
+def test_first_generation_kernels_stay_bit_exact(fast, describe, resize, monkeypatch):
+    """Round 1's k_fast / k_describe / k_resize stay selectable for A/B runs (ORBB200_FAST_VARIANT / ORBB200_DESCRIBE_VARIANT /
+    ORBB200_RESIZE_VARIANT, read when a handle is created): every combination gives the oracle's result."""
     monkeypatch.setenv("ORBB200_FAST_VARIANT", fast)
     monkeypatch.setenv("ORBB200_DESCRIBE_VARIANT", describe)
+    monkeypatch.setenv("ORBB200_RESIZE_VARIANT", resize)
     frames = np.stack([synthetic_frame(70 + i) for i in range(3)])
     ex = ORBextractor(*PARAMS, max_batch=3)
     orc = O.OracleExtractor(*PARAMS)
@@ -427,3 +428,22 @@ def test_first_generation_kernels_stay_bit_exact(fast, describe, monkeypatch):
         ko, do = orc(frames[f])
         n = counts[f]
         assert n == len(ko) and kps[f, :n].tobytes() == ko.tobytes() and np.array_equal(desc[f, :n], do)
+
+
+def test_describe_groups_cover_every_batch_size_and_empty_frames():
+    """k_describe3 hands groups of 8 output rows to its warps (1 in calls of up to 8 frames) and works on two groups at a time:
+    batches around the switch, frames without keypoints between textured ones (groups of size 0, frame totals of 0) and a
+    batch whose last group is ragged all reproduce the oracle."""
+    orc = O.OracleExtractor(*PARAMS)
+    textured = [synthetic_frame(80 + i) for i in range(3)]
+    flat = np.full((480, 640), 90, np.uint8)
+    want = {id(f): orc(f) for f in textured + [flat]}
+    for batch in (1, 8, 9, 13):
+        frames = [textured[i % 3] if (i % 4) != 2 else flat for i in range(batch)]
+        ex = ORBextractor(*PARAMS, max_batch=batch)
+        kps, desc, counts = ex.extract_batch(np.stack(frames))
+        for f in range(batch):
+            ko, do = want[id(frames[f])]
+            n = counts[f]
+            assert n == len(ko), (batch, f, n, len(ko))
+            assert kps[f, :n].tobytes() == ko.tobytes() and np.array_equal(desc[f, :n], do)

@@ -7,8 +7,8 @@ writes <prefix>_ncu_full_summary.json (per-launch: time, issue-slot use, occupan
 import csv, io, json, os, subprocess, sys
 
 rep, prefix = sys.argv[1], sys.argv[2]
-STAGE = {"k_resize": "pyramid", "k_fast": "fast", "k_fast2": "fast", "k_quadtree": "quadtree", "k_blur": "blur", "k_describe": "describe",
-         "k_describe2": "describe"}
+STAGE = {"k_resize": "pyramid", "k_resize2": "pyramid", "k_resize3": "pyramid", "k_fast": "fast", "k_fast2": "fast", "k_quadtree": "quadtree",
+         "k_blur": "blur", "k_describe": "describe", "k_describe2": "describe", "k_describe3": "describe"}
 M = {"time_us": "gpu__time_duration.sum", "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
      "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active", "dram_read_MB": "dram__bytes_read.sum",
      "dram_write_MB": "dram__bytes_write.sum", "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -53,7 +53,7 @@ for r in rows[2:]:
 json.dump(out, open(prefix + "_ncu_full_summary.json", "w"), indent=1)
 json.dump(traffic, open(os.path.join(os.path.dirname(prefix), "traffic.json"), "w"), indent=1)
 
-for kern in ("k_fast2", "k_describe2", "k_blur", "k_resize", "k_quadtree"):
+for kern in ("k_fast2", "k_describe3", "k_blur", "k_resize3", "k_quadtree"):
     rows = list(csv.reader(io.StringIO(ncu("--page", "source", "--print-source", "cuda,sass", "--csv", "-k", "regex:" + kern))))
     acc, tot, smp = {}, 0, 0
     for r in rows:

@@ -84,14 +84,13 @@ struct ExtractParams {
     int fastLarge, totalCells, totalBlurTiles;       // fastLarge: cells exceed 37 x 34 px -> the <38,64> instantiation
     const uint32_t* blurTiles;                       // k_blur tile table: level << 24 | tile row << 12 | tile column
     const int4* cells;                               // k_fast cell table (one entry per detection cell that exists, level-major)
-    const int* rzXs; int rzXsOff[MAXL];              // k_resize2: first source column (16-aligned) of every 128-column output block, per level
-    int rzBoxW[MAXL], rzBoxH[MAXL];                  // k_resize2: TMA box of the source window of one 128 x 32 output block of level l (0: use k_resize)
+    const int* rzXs;                                 // k_resize3: first source column (16-aligned) of every 64-column output block, level after level
     // k_resize3: a warp = 64 columns x 16 rows of two frames; per level the 16-aligned first source column of every 64-column block
-    // (in rzXs from rz3XsOff on), the source-window box (rz3BoxW x rz3BoxH x 2 frames, 0: use k_resize2) and the row table in groups of
+    // (in rzXs from rz3XsOff on), the source-window box (rz3BoxW x rz3BoxH x 2 frames, 0: use k_resize) and the row table in groups of
     // RZ3_GROUP entries {lower source row, b0 << 16, b1 << 16, -}
     int rz3XsOff[MAXL], rz3BoxW[MAXL], rz3BoxH[MAXL], ytab3Off[MAXL];
     const int4* ytab3;
-    int descChunk;                                   // k_describe2: consecutive output rows a warp takes at a time (power of two)
+    int descChunk;                                   // k_describe3: keypoints (consecutive output rows) per group
     int nCells, frameBase;                           // entries; index of the batch's first frame inside the handle's slabs
     // k_quadtree shared-memory geometry
     int qtNC, qtPC;
@@ -239,101 +238,11 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize(const ExtractParams P,
     }
 }
 
-// ---- k_resize, second generation: the block's source window arrives by TMA --------------------------------------------------
-// ncu (r2a) put 56 % of k_resize's stall samples on the first use of the source words: every row is three global loads behind a
-// dependent table load, at 32 registers there is nothing else in flight.  Here the 128 x 32 output block's source window (about
-// 160 x 41 pixels at scale 1.2; box start on the 16-byte boundary left of its first column) is ONE 3-D TMA tensor copy into shared
-// memory, and the row loop reads shared memory: no global latency, no 64-bit address arithmetic, no row-end predicates.  The
-// arithmetic is unchanged (resize_hrow).
-struct ResizeMaps { CUtensorMap m[MAXL]; };     // m[l] = source map for producing level l (level l - 1), box rzBoxW[l] x rzBoxH[l] x 1
-
-__global__ void __launch_bounds__(RZ_WARPS * 32) k_resize2(const __grid_constant__ ExtractParams P, const __grid_constant__ ResizeMaps M, int l)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    const LevelGeo& g = P.lv[l];
-    const int frame = blockIdx.z;
-    const short4* xt = P.tabs + g.xtabOff;
-    const short4* yt = P.tabs + g.ytabOff;
-    const int boxW = P.rzBoxW[l], boxH = P.rzBoxH[l];
-    // the block's source window: first source column of its first destination column, first source row of its first row
-    const int xs = __ldg(P.rzXs + P.rzXsOff[l] + blockIdx.x);      // 16-byte boundary at or left of the block's leftmost source column
-    const int ys = (int)__ldg(yt + blockIdx.y * RZ_WARPS * RZ_ROWS).x;
-    const uint32_t bar = smem_u32(smem + boxW * boxH);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(boxW * boxH)) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(&M.m[l])), "r"(bar), "r"(xs), "r"(ys),
-                       "r"((l == 1 ? 0 : P.frameBase) + frame) : "memory");
-    }
-    __syncthreads();                                   // the barrier is initialised before anybody polls it
-    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
-    const int yBeg = (blockIdx.y * RZ_WARPS + (threadIdx.x >> 5)) * RZ_ROWS;
-    if (x0 >= g.w + 4 || yBeg >= g.h) return;
-    uint8_t* dst = P.pyr + (long long)frame * P.pyrFrameBytes + g.pyrOff;
-
-    // column geometry, once per thread
-    short4 t[4];
-    int bmin = 1 << 30;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        t[j] = __ldg(xt + min(x0 + j, g.w + 3));
-        bmin = min(bmin, (int)t[j].x);
-    }
-    const int a = bmin & ~3;
-    const uint32_t selShift = 0x3210u + 0x1111u * (uint32_t)(bmin - a);
-    uint32_t sel[4], coef[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        sel[j] = (uint32_t)(t[j].x - bmin) | ((uint32_t)(t[j].w - bmin) << 4);    // bytes S[sx], S[sx+1] -> byte lanes 0,1
-        coef[j] = (uint32_t)(uint16_t)t[j].y | ((uint32_t)(uint16_t)t[j].z << 16);
-    }
-    const uint8_t* sbase = smem + (a - xs) - ys * boxW;     // source (row, column a) = sbase + row * boxW
-    const int yEnd = min(yBeg + RZ_ROWS, g.h);
-    // Two register sets A and B hold the horizontal passes of two source rows.  Consecutive destination rows usually share a
-    // source row (the lower row of one is the upper row of the next), so the sets swap roles from row to row -- the loop is
-    // unrolled by two and a set is recomputed only when it does not already hold the row it is asked for: no copies.
-    uint32_t A[4], B[4];
-    int rowA = -1, rowB = -1;
-    short4 tnext = __ldg(yt + yBeg);
-    uint8_t* outp = dst + (long long)yBeg * g.pitch + x0;
-    mbar_wait(bar, 0);
-    auto hrow = [&](int row, uint32_t (&r)[4]) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(sbase + row * boxW);
-        ResizeRaw raw;
-        raw.w0 = w[0]; raw.w1 = w[1]; raw.w2 = w[2];
-        resize_hrow(raw, selShift, sel, coef, r);
-    };
-    auto emit = [&](const short4 ty, const uint32_t (&r0)[4], const uint32_t (&r1)[4]) {
-        const uint32_t B0 = (uint32_t)ty.z << 16, B1 = (uint32_t)ty.w << 16;
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) o[j] = min((__umulhi(B0, r0[j]) + __umulhi(B1, r1[j]) + 2u) >> 2, 255u);
-        *reinterpret_cast<uint32_t*>(outp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-        outp += g.pitch;
-    };
-#pragma unroll 1
-    for (int y = yBeg; y < yEnd; y += 2) {
-        {   // even row of the pair: upper source row in A, lower in B
-            const short4 ty = tnext;
-            tnext = __ldg(yt + min(y + 1, g.h - 1));
-            if (rowA != ty.x) { hrow(ty.x, A); rowA = ty.x; }
-            if (rowB != ty.y) { hrow(ty.y, B); rowB = ty.y; }
-            emit(ty, A, B);
-        }
-        if (y + 1 < yEnd) {   // odd row: upper in B (usually what the even row left there), lower in A
-            const short4 ty = tnext;
-            tnext = __ldg(yt + min(y + 2, g.h - 1));
-            if (rowB != ty.x) { hrow(ty.x, B); rowB = ty.x; }
-            if (rowA != ty.y) { hrow(ty.y, A); rowA = ty.y; }
-            emit(ty, B, A);
-        }
-    }
-}
+struct ResizeMaps { CUtensorMap m[MAXL]; };     // m[l] = source map for producing level l (level l - 1), box rz3BoxW[l] x rz3BoxH[l] x 2 frames
 
 // ---- k_resize, third generation: the loop runs over SOURCE rows -------------------------------------------------------------
-// k_resize2 still spent ~35 instructions per pixel (ncu r2s): per destination row a table load behind address arithmetic, two
+// (The second generation, k_resize2, staged a 128 x 32 block's source window with one TMA copy and kept k_resize's row loop:
+// 0.274 -> 0.236 ms.)  It still spent ~35 instructions per pixel (ncu r2s): per destination row a table load behind address arithmetic, two
 // "do I already hold this source row" tests with their reconvergence points, an eight-row walk that amortises the column setup
 // over 32 pixels only, and 128-column blocks that leave 16 % of the lanes past the level's right edge.  Here
 //  * a warp owns 64 columns x 16 rows of TWO frames (lane = column quad + 16 * frame): the control flow depends on the row
@@ -343,7 +252,7 @@ __global__ void __launch_bounds__(RZ_WARPS * 32) k_resize2(const __grid_constant
 //  * the loop walks the window's source rows once: each gets one horizontal pass (the two register sets swap roles), and a
 //    destination row is emitted when its LOWER source row has just been computed (its upper row is then the previous one,
 //    because the lower rows of consecutive destination rows never decrease).  A level with a row whose two taps sit on the same
-//    source row (only when consecutive levels have the same height) keeps k_resize2;
+//    source row (only when consecutive levels have the same height) keeps k_resize;
 //  * the row table (a copy of the warp's 16 entries + a sentinel in shared memory) holds the lower row and the coefficients
 //    already shifted (b << 16); the vertical blend packs two pixels per register before the rounding shift, and the clamp to
 //    255 is gone: b0 + b1 = 2048 and r <= 255 * 2048 >> 4 bound the sum by 1020.
@@ -1666,7 +1575,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const ExtractParam
     }
 }
 
-// ---- k_describe, second generation ------------------------------------------------------------------------------------
+// ---- k_describe, second generation (k_describe2, superseded by k_describe3 below, which keeps its data path) -------------
 // Same arithmetic, different data path (ncu r2i: the first version was bound by L1 wavefronts, 79 %, because every one of the
 // 16 byte gathers of a lane is its own sector, and by the conversion pipe, 58 %, for int -> float of the pattern and
 // float -> int of the rotated coordinates; r2k: a one-keypoint-per-warp TMA version waited on its own copy, long scoreboard):
@@ -1681,7 +1590,6 @@ struct DescMaps { CUtensorMap u[MAXL], b[MAXL]; };      // unblurred levels: box
 constexpr int DESC_UW = 48, DESC_UROWS = 2 * HALF_PATCH + 1, DESC_BW = 64, DESC_BROWS = 37, DESC_HALF = 18;
 constexpr int DESC_USLOT = (DESC_UW * DESC_UROWS + 127) / 128 * 128, DESC_BSLOT = (DESC_BW * DESC_BROWS + 127) / 128 * 128;
 constexpr int DESC_BUF = DESC_USLOT + DESC_BSLOT;        // one buffer = both patches of one keypoint (TMA destinations: 128-byte aligned)
-constexpr int DESC_WARP_BYTES = 2 * DESC_BUF + 128;      // two buffers + the warp's two mbarriers
 constexpr int DESC_CTAS_PER_SM = 3;                     // persistent CTAs per SM (registers: 80 x 256; shared memory: 63 KB)
 
 struct PatternTableF { float2 v[512]; };
@@ -1696,162 +1604,6 @@ constexpr PatternTableF make_pattern_table_f()
     return t;
 }
 __device__ const PatternTableF d_pattern_f = make_pattern_table_f();
-
-__global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe2(const __grid_constant__ ExtractParams P, const __grid_constant__ DescMaps M)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    constexpr unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // the (frame, output row) slots of the batch in chunks of P.descChunk (4; 1 in small calls, where latency counts), dealt to the warps round robin: at any time the warps
-    // of the grid work inside a window of a few frames (their patches overlap, so they hit L2), and a warp changes frame rarely
-    const int nslots = P.batch * P.outCap, nw = gridDim.x * DESC_WARPS;
-    const int CH = P.descChunk;
-    const int s0 = (blockIdx.x * DESC_WARPS + warp) * CH, s1 = nslots;
-    if (s0 >= s1) return;
-
-    // per-lane constants: level tables, the lane's 16 pattern points, its 8 IC_Angle weight words
-    const int kpOffLane = lane < P.nlevels ? P.lv[lane].kpOff : 0;
-    const float scaleLane = lane < P.nlevels ? P.lv[lane].scale : 0.f, sizeLane = lane < P.nlevels ? P.lv[lane].kpSize : 0.f;
-    float2 pat[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) pat[k] = __ldg(&d_pattern_f.v[k * 32 + lane]);
-    uint2 wgt[8];
-#pragma unroll
-    for (int it = 0; it < 8; it++) wgt[it] = __ldg(&d_angle.w[it][lane]);
-
-    uint8_t* buf = smem + (size_t)warp * DESC_WARP_BYTES;
-    const uint32_t bar0 = smem_u32(buf + 2 * DESC_BUF);
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    // iterator over the range's keypoints: slot -> (frame, row o); lane q keeps the frame's count of level q and the number of
-    // keypoints below it.  A frame whose first slot lies in the range gets its total published by this warp (also when it is 0).
-    int itSlot = s0, itFrame = -1, itPre = 0, itTotal = 0;
-    auto next = [&](int& frame, int& o, int& l, uint32_t& e) -> bool {
-        while (itSlot < s1) {
-            const int f = itSlot / P.outCap, oo = itSlot - f * P.outCap;
-            if (f != itFrame) {
-                itFrame = f;
-                const int cnt = lane < P.nlevels ? __ldg(P.lkpCount + f * P.nlevels + lane) : 0;
-                int pre = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += v; }
-                itTotal = min(__shfl_sync(FULL, pre, 31), P.outCap);     // (more cannot happen: outCap = the sum of the level capacities)
-                itPre = pre - cnt;
-                if (oo == 0 && lane == 0) P.outCount[f] = itTotal;
-            }
-            if (oo >= itTotal) {                              // past the frame's last keypoint: on to this warp's next chunk
-                const int chunkBeg = itSlot - ((itSlot - s0) & (CH - 1)), nextFrame = (f + 1) * P.outCap;
-                itSlot = nextFrame < chunkBeg + CH ? nextFrame : chunkBeg + nw * CH;      // (a chunk may straddle two frames)
-                continue;
-            }
-            frame = f; o = oo;
-            l = __popc(__ballot_sync(FULL, lane < P.nlevels && itPre <= oo)) - 1;
-            e = __ldg(P.lkp + (long long)f * P.kpFrameCap + __shfl_sync(FULL, kpOffLane, l) + (oo - __shfl_sync(FULL, itPre, l)));
-            itSlot++;
-            if (((itSlot - s0) & (CH - 1)) == 0) itSlot += (nw - 1) * CH;
-            return true;
-        }
-        return false;
-    };
-    auto issue = [&](int frame, int l, uint32_t e, int s) {
-        const int x = (e & 0xfff) + BORDER, y = ((e >> 12) & 0xfff) + BORDER;
-        const uint32_t bar = bar0 + 8 * s, dst = smem_u32(buf + s * DESC_BUF);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of this buffer are done
-        if (lane == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(DESC_UW * DESC_UROWS + DESC_BW * DESC_BROWS)) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&M.u[l])), "r"(bar), "r"((x - 16) & ~15), "r"(y - HALF_PATCH),
-                           "r"((l == 0 ? 0 : P.frameBase) + frame) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                         ::"r"(dst + DESC_USLOT), "l"(reinterpret_cast<uint64_t>(&M.b[l])), "r"(bar), "r"((x - DESC_HALF) & ~15), "r"(y - DESC_HALF),
-                           "r"(P.frameBase + frame) : "memory");
-        }
-        __syncwarp();
-    };
-
-    int frame, o, l, frameN = 0, oN = 0, lN = 0;
-    uint32_t e, eN = 0;
-    bool have = next(frame, o, l, e);
-    if (have) issue(frame, l, e, 0);
-    uint32_t phase = 0;                                     // bit s = parity to wait for on buffer s
-    int s = 0;
-#pragma unroll 1
-    while (have) {
-        const bool more = next(frameN, oN, lN, eN);
-        if (more) issue(frameN, lN, eN, s ^ 1);
-        mbar_wait(bar0 + 8 * s, (phase >> s) & 1);
-        phase ^= 1u << s;
-
-        const int x = (e & 0xfff) + BORDER, y = ((e >> 12) & 0xfff) + BORDER, score = e >> 24;   // :857-858
-        const uint8_t* pu = buf + s * DESC_BUF;             // unblurred patch: rows y - 15 .. y + 15, columns from (x - 16) & ~15
-        // ---- orientation: intensity centroid over the radius-15 disc of the UNBLURRED level (weights: see d_angle) ----
-        int m10 = 0, m01 = 0;
-        {
-            // columns x - 16 .. x + 15 = patch bytes b0 .. b0 + 31; lane owns word j = lane & 7 of row v = -15 + 4 * it + (lane >> 3)
-            const int b0 = (x - 16) & 15, sh = (b0 & 3) * 8;
-            const uint32_t* p = reinterpret_cast<const uint32_t*>(pu + (lane >> 3) * DESC_UW) + (b0 >> 2) + (lane & 7);
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                if (it < 7 || lane < 24) {                         // the last step holds rows 13, 14, 15 only
-                    const uint32_t px = __funnelshift_r(p[0], p[1], sh);
-                    m10 = dp4a_u8s8(px, wgt[it].x, m10);
-                    m01 = dp4a_u8s8(px, wgt[it].y, m01);
-                }
-                p += 4 * DESC_UW / 4;
-            }
-        }
-        m10 = __reduce_add_sync(FULL, m10);
-        m01 = __reduce_add_sync(FULL, m01);
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-        // ---- descriptor on the BLURRED level: lane b produces byte b (pairs 8b..8b+7) ----
-        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
-        float a, b;
-        libm_sincosf(__fmul_rn(angle, factorPI), b, a);
-        // cvRound(v) = bits(v + 1.5 * 2^23) - 0x4B400000 (round to nearest even, |v| < 2^22).  The sample's shared-memory address
-        // is base + ry * 64 + rx in 32-bit arithmetic that wraps, so the two constants are folded into the base once
-        const float MAGIC = 12582912.0f;
-        const uint32_t cb = smem_u32(pu + DESC_USLOT) + DESC_HALF * DESC_BW + ((x - DESC_HALF) & 15) + DESC_HALF - 0x4B400000u * (uint32_t)(DESC_BW + 1);
-        int val = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            uint32_t t[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const float2 pt = pat[2 * k + h];
-                const uint32_t ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), MAGIC));
-                const uint32_t rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), MAGIC));
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[h]) : "r"(cb + ry * (uint32_t)DESC_BW + rx));
-            }
-            val |= (t[0] < t[1]) << k;
-        }
-        P.outDesc[((long long)frame * P.outCap + o) * 32 + lane] = (uint8_t)val;
-
-        // ---- keypoint record (cv::KeyPoint layout), coordinates scaled to level 0 (:1126-1132) ----
-        const float sc = __shfl_sync(FULL, scaleLane, l), ksz = __shfl_sync(FULL, sizeLane, l);
-        if (lane < 7) {
-            float fx = (float)x, fy = (float)y;
-            if (l != 0) { fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); }
-            uint32_t w;
-            switch (lane) {
-                case 0: w = __float_as_uint(fx); break;
-                case 1: w = __float_as_uint(fy); break;
-                case 2: w = __float_as_uint(ksz); break;
-                case 3: w = __float_as_uint(angle); break;
-                case 4: w = __float_as_uint((float)score); break;
-                case 5: w = (uint32_t)l; break;
-                default: w = 0xffffffffu; break;
-            }
-            reinterpret_cast<uint32_t*>(P.outKp + (long long)frame * P.outCap + o)[lane] = w;
-        }
-        have = more; frame = frameN; o = oN; l = lN; e = eN; s ^= 1;
-    }
-}
 
 // ---- k_describe, third generation: the per-keypoint scalar work is done for a group of keypoints at once ---------------------
 // ncu (r2z) on k_describe2: the moments and the 256 comparisons are only ~40 % of its 624 warp instructions per keypoint; the rest
@@ -2083,12 +1835,12 @@ struct orbb200_extractor {
     int totalCells, totalBlurTiles, maxKp, numSMs;
     size_t fastSmem, qtSmem;
     int fastVariant;           // 2 = k_fast2 (TMA tensor staging, default), 1 = k_fast (ORBB200_FAST_VARIANT=1: the first-generation kernel, kept for A/B runs)
-    ResizeMaps resizeMaps;     // k_resize2's source-window maps (m[1] is encoded per call: level 0 may be the caller's buffer)
-    int resizeVariant;         // 3 = k_resize3 (source-row walk, default), 2 = k_resize2, 1 = k_resize (ORBB200_RESIZE_VARIANT, read at create)
+    ResizeMaps resizeMaps;     // k_resize3's source-window maps (m[1] is encoded per call: level 0 may be the caller's buffer)
+    int resizeVariant;         // 3 = k_resize3 (source-row walk over TMA-staged windows, default), 1 = k_resize (ORBB200_RESIZE_VARIANT=1 at create, kept for A/B runs)
     BlurMaps blurMaps;         // k_blur's window maps (level 0 per call)
     FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
     DescMaps descMaps;         // k_describe2's patch maps of the unblurred and the blurred levels (box 64 x 37)
-    int descVariant, maxLevelKpCap;   // 3 = k_describe3 (default), 2 = k_describe2, 1 = k_describe (ORBB200_DESCRIBE_VARIANT, kept for A/B runs)
+    int descVariant, maxLevelKpCap;   // 3 = k_describe3 (default), 1 = k_describe (ORBB200_DESCRIBE_VARIANT=1 at create, kept for A/B runs)
     int lastLaunches, lastBatch;
     int realCandCap[MAXL];     // per-level candidate capacity as computed at create (orbb200_extractor_debug_set_capacity clamps P.lv[l].candCap)
     int chunkOverride;         // ORBB200_CHUNKS read once at create (0 = choose by batch size): tuning knob of the blocking host call
@@ -2285,25 +2037,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
             }
             g.xtabOff = (int)tabs.size(); tabs.insert(tabs.end(), xt.begin(), xt.end());
             g.ytabOff = (int)tabs.size(); tabs.insert(tabs.end(), yt.begin(), yt.end());
-            // k_resize2: per 128-column block the 16-aligned first source column, and the box that holds any block's source window
-            P.rzXsOff[l] = (int)rzXs.size();
-            int boxW = 0, boxH = 0;
-            for (int bx = 0; bx * 128 < g.w + 4; bx++) {
-                int lo = 1 << 30, hi = 0;
-                for (int x0 = bx * 128; x0 < std::min(bx * 128 + 128, g.w + 4); x0 += 4) {
-                    int bmin = 1 << 30;
-                    for (int j = 0; j < 4; j++) bmin = std::min(bmin, (int)xt[std::min(x0 + j, g.w + 3)].x);
-                    lo = std::min(lo, bmin & ~3); hi = std::max(hi, (bmin & ~3) + 12);
-                }
-                rzXs.push_back(lo & ~15);
-                boxW = std::max(boxW, hi - (lo & ~15));
-            }
-            for (int by = 0; by * RZ_ROWS * RZ_WARPS < g.h; by++)
-                boxH = std::max(boxH, (int)yt[std::min(by * RZ_ROWS * RZ_WARPS + RZ_ROWS * RZ_WARPS - 1, g.h - 1)].y - (int)yt[by * RZ_ROWS * RZ_WARPS].x + 1);
-            boxW = (int)align_up(boxW, 16);
-            P.rzBoxW[l] = (boxW <= 256 && boxH <= 256) ? boxW : 0;      // a TMA box side is at most 256: larger scale factors keep k_resize
-            P.rzBoxH[l] = boxH;
-            // k_resize3: the same per 64-column block, and the row table {lower source row, b0 << 16, b1 << 16, both taps on one row}
+            // k_resize3: per 64-column block the 16-aligned first source column and the box that holds any block's source window, and the row table {lower source row, b0 << 16, b1 << 16, both taps on one row}
             P.rz3XsOff[l] = (int)rzXs.size();
             int boxW3 = 0, boxH3 = 0;
             for (int bx = 0; bx * 64 < g.w + 4; bx++) {
@@ -2407,12 +2141,10 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     TRY(dev_alloc(h, &dYtab3, ytab3.size() + 1));
     P.ytab3 = dYtab3;
     h->resizeVariant = 3;
-    if (const char* ev = getenv("ORBB200_RESIZE_VARIANT")) h->resizeVariant = std::max(1, std::min(3, atoi(ev)));
-    for (int l = 2; l < nlevels && h->resizeVariant >= 2; l++) {     // source = level l - 1 in the handle's pyramid slab
-        const bool v3 = h->resizeVariant == 3 && P.rz3BoxW[l];
-        if (v3 || P.rzBoxW[l]) TRY(encode_level_map(&h->resizeMaps.m[l], P.pyr + P.lv[l - 1].pyrOff, P.lv[l - 1].w + 4, P.lv[l - 1].h, max_batch, P.lv[l - 1].pitch,
-                                              (size_t)P.pyrFrameBytes, v3 ? P.rz3BoxW[l] : P.rzBoxW[l], v3 ? P.rz3BoxH[l] : P.rzBoxH[l], v3 ? 2 : 1));
-    }
+    if (const char* ev = getenv("ORBB200_RESIZE_VARIANT")) h->resizeVariant = atoi(ev) == 1 ? 1 : 3;
+    for (int l = 2; l < nlevels && h->resizeVariant == 3; l++)      // source = level l - 1 in the handle's pyramid slab
+        if (P.rz3BoxW[l]) TRY(encode_level_map(&h->resizeMaps.m[l], P.pyr + P.lv[l - 1].pyrOff, P.lv[l - 1].w + 4, P.lv[l - 1].h, max_batch, P.lv[l - 1].pitch,
+                                              (size_t)P.pyrFrameBytes, P.rz3BoxW[l], P.rz3BoxH[l], 2));
     std::vector<uint32_t> blurTab;
     for (int l = 0; l < nlevels; l++)
         for (int ty = 0; ty < (P.lv[l].h + BL_ROWS - 1) / BL_ROWS; ty++)
@@ -2421,10 +2153,10 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     TRY(dev_alloc(h, &dBlurTiles, blurTab.size() + 1));
     P.blurTiles = dBlurTiles;
     h->descVariant = 3;
-    if (const char* ev = getenv("ORBB200_DESCRIBE_VARIANT")) h->descVariant = std::max(1, std::min(3, atoi(ev)));
+    if (const char* ev = getenv("ORBB200_DESCRIBE_VARIANT")) h->descVariant = atoi(ev) == 1 ? 1 : 3;
     h->maxLevelKpCap = 0;
     for (int l = 0; l < nlevels; l++) h->maxLevelKpCap = std::max(h->maxLevelKpCap, P.lv[l].kpCap);
-    for (int l = 0; l < nlevels && h->descVariant >= 2; l++) {
+    for (int l = 0; l < nlevels && h->descVariant == 3; l++) {
         if (l > 0) TRY(encode_level_map(&h->descMaps.u[l], P.pyr + P.lv[l].pyrOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.pyrFrameBytes, DESC_UW, DESC_UROWS));
         TRY(encode_level_map(&h->descMaps.b[l], P.blur + P.lv[l].blurOff, P.lv[l].w, P.lv[l].h, max_batch, P.lv[l].pitch, (size_t)P.blurFrameBytes, DESC_BW, DESC_BROWS));
     }
@@ -2455,10 +2187,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     }
     if (e == cudaSuccess && h->fastVariant == 1) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast<38, 64> : (const void*)k_fast<26, 42>, device, h->fastSmem);
     if (e == cudaSuccess && h->fastVariant == 2) e = ensure_dynamic_smem(P.fastLarge ? (const void*)k_fast2<38, 64> : (const void*)k_fast2<26, 42>, device, h->fastSmem);
-    if (e == cudaSuccess && h->descVariant == 2) e = ensure_dynamic_smem((const void*)k_describe2, device, DESC_WARPS * DESC_WARP_BYTES);
     if (e == cudaSuccess && h->descVariant == 3) e = ensure_dynamic_smem((const void*)k_describe3, device, D3_CTA_BYTES);
-    for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant >= 2; l++)
-        if (P.rzBoxW[l]) e = ensure_dynamic_smem((const void*)k_resize2, device, (size_t)P.rzBoxW[l] * P.rzBoxH[l] + 16);
     for (int l = 1; l < nlevels && e == cudaSuccess && h->resizeVariant == 3; l++)
         if (P.rz3BoxW[l]) e = ensure_dynamic_smem((const void*)k_resize3, device, resize3_smem(P, l));
     if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)k_quadtree, device, h->qtSmem);
@@ -2559,16 +2288,12 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
     if (h->resizeVariant == 3 && P.nlevels > 1 && P.rz3BoxW[1]) {
         int rc = encode_level_map(&h->resizeMaps.m[1], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, P.rz3BoxW[1], P.rz3BoxH[1], 2);
         if (rc != ORBB200_OK) return rc;
-    } else if (h->resizeVariant >= 2 && P.nlevels > 1 && P.rzBoxW[1]) {
-        int rc = encode_level_map(&h->resizeMaps.m[1], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, P.rzBoxW[1], P.rzBoxH[1]);
-        if (rc != ORBB200_OK) return rc;
     }
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeo& g = P.lv[l];
         dim3 grid((g.w + 4 + 127) / 128, (g.h + RZ_ROWS * RZ_WARPS - 1) / (RZ_ROWS * RZ_WARPS), batch);
         if (h->resizeVariant == 3 && P.rz3BoxW[l])
             launch_pdl(k_resize3, dim3((g.w + 4 + 63) / 64, (g.h + RZ3_ROWS * RZ3_WARPS - 1) / (RZ3_ROWS * RZ3_WARPS), (batch + 1) / 2), RZ3_WARPS * 32, resize3_smem(P, l), st, P, h->resizeMaps, l);
-        else if (h->resizeVariant >= 2 && P.rzBoxW[l]) k_resize2<<<grid, RZ_WARPS * 32, P.rzBoxW[l] * P.rzBoxH[l] + 16, st>>>(P, h->resizeMaps, l);
         else k_resize<<<grid, RZ_WARPS * 32, 0, st>>>(P, l);
         ORB_CHECK_LAUNCH("k_resize"); launches++;
     }
@@ -2620,19 +2345,14 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
         ORB_CUDA(cudaStreamWaitEvent(st, h->evJoin, 0));
     }
     STAGE_MARK(4);
-    if (h->descVariant >= 2) {
+    if (h->descVariant == 3) {
         int rc = encode_level_map(&h->descMaps.u[0], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride, DESC_UW, DESC_UROWS);
         if (rc != ORBB200_OK) return rc;
-        // full batches: persistent warps over chunks of 4 rows; calls of a few frames (latency counts): one row per warp and step
+        // persistent warps over groups of 8 output rows; calls of a few frames (latency counts): one row per group
         ExtractParams Pd = P;
-        Pd.descChunk = batch <= SIDE_MAX_BATCH ? 1 : 4;
-        const int ctas = std::max(1, std::min(h->numSMs * DESC_CTAS_PER_SM, (batch * P.outCap + DESC_WARPS * Pd.descChunk - 1) / (DESC_WARPS * Pd.descChunk)));
-        if (h->descVariant == 3) {       // groups of 8 output rows per warp and step (1 in calls of a few frames)
-            Pd.descChunk = batch <= SIDE_MAX_BATCH ? 1 : 8;
-            const int items = batch * ((P.outCap + Pd.descChunk - 1) / Pd.descChunk);
-            k_describe3<<<std::max(1, std::min(h->numSMs * DESC_CTAS_PER_SM, (items + DESC_WARPS - 1) / DESC_WARPS)), DESC_WARPS * 32, D3_CTA_BYTES, st>>>(Pd, h->descMaps);
-        } else
-        k_describe2<<<ctas, DESC_WARPS * 32, DESC_WARPS * DESC_WARP_BYTES, st>>>(Pd, h->descMaps);
+        Pd.descChunk = batch <= SIDE_MAX_BATCH ? 1 : 8;
+        const int items = batch * ((P.outCap + Pd.descChunk - 1) / Pd.descChunk);
+        k_describe3<<<std::max(1, std::min(h->numSMs * DESC_CTAS_PER_SM, (items + DESC_WARPS - 1) / DESC_WARPS)), DESC_WARPS * 32, D3_CTA_BYTES, st>>>(Pd, h->descMaps);
     } else
     k_describe<<<dim3((P.kpFrameCap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, st>>>(P);
     ORB_CHECK_LAUNCH("k_describe"); launches++;
