@@ -1405,6 +1405,32 @@ constexpr AngleTable make_angle_table()
 }
 __device__ const AngleTable d_angle = make_angle_table();
 
+// The same weights for k_describe3, whose patch rows sit 48 bytes = 12 words apart in shared memory: with four CONSECUTIVE rows
+// per step the four 8-word windows start at banks 0, 12, 24, 4 and overlap (two wavefronts per load); with rows 2 apart they
+// start at 0, 24, 16, 8 -- every bank once, also for the neighbouring word the funnel shift needs.  Step `it` takes rows
+// v = -15 + 8 * (it >> 1) + (it & 1) + 2 * (L >> 3).
+__host__ __device__ constexpr int angle3_row(int it, int grp) { return 8 * (it >> 1) + (it & 1) + 2 * grp; }      // patch row 0 .. 31 (31: outside, weights 0)
+constexpr AngleTable make_angle_table3()
+{
+    AngleTable t{};
+    for (int it = 0; it < 8; it++)
+        for (int L = 0; L < 32; L++) {
+            const int v = -HALF_PATCH + angle3_row(it, L >> 3), j = L & 7;
+            unsigned wu = 0, wv = 0;
+            for (int b = 0; b < 4; b++) {
+                const int u = -16 + 4 * j + b;
+                const int au = u < 0 ? -u : u, av = v < 0 ? -v : v;
+                if (av <= HALF_PATCH && au <= HALF_PATCH && au <= UMAX_SRC[av]) {
+                    wu |= (unsigned)(u & 0xff) << (8 * b);
+                    wv |= (unsigned)(v & 0xff) << (8 * b);
+                }
+            }
+            t.w[it][L].x = wu; t.w[it][L].y = wv;
+        }
+    return t;
+}
+__device__ const AngleTable d_angle3 = make_angle_table3();
+
 __device__ __forceinline__ int dp4a_u8s8(uint32_t pixels, uint32_t weights, int acc)
 {
     int d;
@@ -1640,7 +1666,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe3(const __grid_c
     // (the 8 IC_Angle weight words of every lane sit in shared memory, one conflict-free 8-byte load per step: in registers they
     // pushed the kernel past the 80 it may use at three blocks per SM)
     const uint2* wgt = reinterpret_cast<const uint2*>(smem + DESC_WARPS * D3_WARP_BYTES);
-    for (int i = threadIdx.x; i < 8 * 32; i += DESC_WARPS * 32) const_cast<uint2*>(wgt)[i] = __ldg(&d_angle.w[i >> 5][i & 31]);
+    for (int i = threadIdx.x; i < 8 * 32; i += DESC_WARPS * 32) const_cast<uint2*>(wgt)[i] = __ldg(&d_angle3.w[i >> 5][i & 31]);
     __syncthreads();
     wgt += lane;
 
@@ -1734,18 +1760,18 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 3) k_describe3(const __grid_c
                 // ---- intensity centroid over the radius-15 disc of the UNBLURRED level (weights: see d_angle) ----
                 const int x = __shfl_sync(FULL, xA, k);
                 int m10 = 0, m01 = 0;
-                // columns x - 16 .. x + 15 = patch bytes b0 .. b0 + 31; lane owns word j = lane & 7 of row v = -15 + 4 * it + (lane >> 3)
+                // columns x - 16 .. x + 15 = patch bytes b0 .. b0 + 31; lane owns word j = lane & 7 of patch row angle3_row(it, lane >> 3)
                 const int b0 = (x - 16) & 15, sh = (b0 & 3) * 8;
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(pu + (lane >> 3) * DESC_UW) + (b0 >> 2) + (lane & 7);
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(pu + 2 * (lane >> 3) * DESC_UW) + (b0 >> 2) + (lane & 7);
 #pragma unroll
                 for (int it = 0; it < 8; it++) {
-                    if (it < 7 || lane < 24) {                                 // the last step holds rows 13, 14, 15 only
-                        const uint32_t px = __funnelshift_r(p[0], p[1], sh);
+                    if (it < 7 || lane < 24) {                                 // the last step holds rows 10, 12, 14 only
+                        const uint32_t* q = p + angle3_row(it, 0) * (DESC_UW / 4);
+                        const uint32_t px = __funnelshift_r(q[0], q[1], sh);
                         const uint2 w = wgt[it * 32];
                         m10 = dp4a_u8s8(px, w.x, m10);
                         m01 = dp4a_u8s8(px, w.y, m01);
                     }
-                    p += 4 * DESC_UW / 4;
                 }
                 m10 = __reduce_add_sync(FULL, m10);
                 m01 = __reduce_add_sync(FULL, m01);
