@@ -1208,6 +1208,19 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
+// 18 * h + 2^15 (the newest row's tap and the rounding constant) as two shift-adds: IDP and IMAD share one half-rate pipe, which
+// is what bounds this kernel (ncu r2c: the two make up 72 % of the row loop, "math pipe throttle" is the top stall reason),
+// while the pipe of the shifts, adds and byte permutes is 41 % busy
+__device__ __forceinline__ uint32_t blur_k0_term(uint32_t h)
+{
+    uint32_t t, r;
+    asm("shf.l.wrap.b32 %0, 0, %1, 1;" : "=r"(t) : "r"(h));                    // 2 h  (h < 2^16)
+    asm("add.u32 %0, %1, 32768;" : "=r"(t) : "r"(t));
+    asm("shf.l.wrap.b32 %0, 0, %1, 4;" : "=r"(r) : "r"(h));                    // 16 h
+    asm("add.u32 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(t));
+    return r;
+}
+
 struct BlurTile { int l, frame, x0, y0; };
 
 // tile index -> (frame, level, position); false when the level has no keypoints (skipped like :1112).  The per-frame tile
@@ -1326,7 +1339,7 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const __grid_constant__ 
             for (int u = 1; u < 6; u++) {                                            // rows 1..5 only fill the window
                 hrow(u, cur4);
 #pragma unroll
-                for (int j = 0; j < 4; j++) { Q[u][j] = cur4[j] * 65536u + prev[j]; prev[j] = cur4[j]; }
+                for (int j = 0; j < 4; j++) { Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410); prev[j] = cur4[j]; }
             }
 #pragma unroll 1
             for (int grp = 1; grp < BL_IN_ROWS / 6; grp++) {
@@ -1341,9 +1354,9 @@ __global__ void __launch_bounds__(BL_WARPS * 32) k_blur(const __grid_constant__ 
                     for (int j = 0; j < 4; j++) {
                         // pairs ending at rows ir-5, ir-3, ir-1 sit in slots (u+1)%6, (u+3)%6, (u+5)%6
                         acc[j] = __dp2a_lo(Q[(u + 1) % 6][j], kV01, __dp2a_lo(Q[(u + 3) % 6][j], kV23,
-                                 __dp2a_lo(Q[(u + 5) % 6][j], kV45, k0 * cur4[j] + 32768u)));
+                                 __dp2a_lo(Q[(u + 5) % 6][j], kV45, blur_k0_term(cur4[j]))));
                         if (VARIANT) acc[j] = min(acc[j], 0x00ffffffu);          // taps sum to 257: saturate like OpenCV
-                        Q[u][j] = cur4[j] * 65536u + prev[j];                   // (an IMAD: the FMA pipe has room, the ALU pipe does not)
+                        Q[u][j] = __byte_perm(prev[j], cur4[j], 0x5410);
                         prev[j] = cur4[j];
                     }
                     const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
