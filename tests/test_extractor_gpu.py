@@ -236,6 +236,26 @@ def test_parameter_corner_cases(cfg):
         assert np.array_equal(desc[f, :counts[f]], do)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_geometries_odd_batch(seed):
+    """Random frame sizes and scale factors with a batch of 3: k_resize3 pairs frames (the last pair's second window lies outside
+    the batch), its 64-column blocks and 16-row groups, k_blur's tiles and reflected rows all end on ragged boundaries, and the
+    row tables change with every scale factor.  Every stage of every frame against the oracle."""
+    rng = np.random.default_rng(9100 + seed)
+    w, h = int(rng.integers(360, 900)), int(rng.integers(300, 620))
+    scale = float(rng.choice([1.15, 1.2, 1.25, 1.33, 1.5, 1.75]))
+    levels = int(rng.integers(3, 7))
+    params = (int(rng.integers(300, 1500)), scale, levels, 20, 7)
+    frames = np.stack([synthetic_frame(500 + 10 * seed + i, w, h) for i in range(3)])
+    ex = ORBextractor(*params, width=w, height=h, max_batch=3)
+    orc = O.OracleExtractor(*params)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(3):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes(), (w, h, params, f)
+        assert np.array_equal(desc[f, :counts[f]], do)
+
+
 def test_rejected_geometries():
     from weiner_slamit_v2_b200 import OrbB200Error
     with pytest.raises(OrbB200Error):

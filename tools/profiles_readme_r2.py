@@ -2,8 +2,8 @@
 import csv, json, os, sys
 from collections import defaultdict
 
-btag = sys.argv[1] if len(sys.argv) > 1 else "r2b"
-ntag = sys.argv[2] if len(sys.argv) > 2 else "r2a"
+btag = sys.argv[1] if len(sys.argv) > 1 else "r2d"
+ntag = sys.argv[2] if len(sys.argv) > 2 else "r2d"
 P = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
 J = lambda n: json.load(open(os.path.join(P, n)))
 l = J(btag + "_bench.json")
@@ -20,7 +20,7 @@ w("| `%s_bench_reference_arm.json` | `python bench.py --impl reference`: the ref
 w("| `%s_launches.csv` | ncu launch list (`gpu__time_duration.sum`, `--clock-control none`; cold-cache and serialised: compare shares) of `bench.py --steps 2 --warmup 3 --no-matching --no-cpu-baseline` |" % ntag)
 w("| `%s_ncu_full_summary.json`, `%s_ncu_source_k_*.json` | `ncu --set full --clock-control none --import-source on`, one batch-256 launch of every extractor kernel (`tools/prof_extract.py`), summarised by `tools/ncu_summary.py`: time, issue slots, resident warps, ALU / FMA / XU pipes, LSU data-pipe wavefronts, DRAM bytes; instruction and stall-sample share per source line |" % (ntag, ntag))
 w("| `traffic.json` | DRAM read + write bytes per launch and stage from that capture (`roofline.traffic` in the bench line) |")
-w("| `r2_sass_digest.json` | per-kernel instruction-class counts of the shipped `liborb_b200.so` (`tools/sass_digest.py`): `UTMALDG` in `k_fast2` and `k_describe2`, `UBLKCP` in `k_blur`, `LDS.128` / `LDG.E.128` where used |")
+w("| `r2_sass_digest.json` | per-kernel instruction-class counts of the shipped `liborb_b200.so` (`tools/sass_digest.py`): `UTMALDG` (TMA tensor copies) in `k_resize3`, `k_fast2`, `k_blur` and `k_describe3`, `LDS.128` / `LDG.E.128` where used |")
 w("| `r2a_pipe_peak.json` | issue rates of the instruction classes the kernels are made of, alone and in pairs (`tools/pipe_peak.cu`): which pipe each sits on |")
 w("| `r2_pcie_aggregate.json` | pinned host <-> device copy bandwidth with 1, 2, 4, 8 ranks copying at once (`tools/pcie_aggregate.py`): the end-to-end ceiling of the host |")
 w("| `r2_tiebreak.json` | the reference under glibc malloc against the canonical quadtree order (`tools/tiebreak_report.py`) |")
@@ -44,15 +44,15 @@ w("\nwhole step: %.3f of the HBM peak (the kernels are bound by the SM's integer
 
 w("### ncu --set full (%s), one batch-256 launch per kernel\n" % ntag)
 w("| kernel | time us | issue slots | resident warps | ALU pipe | FMA pipe | LSU data pipe | regs | warp instructions |\n|---|---|---|---|---|---|---|---|---|")
-rz = [x for x in d if x["kernel"] == "k_resize"]
+rz = [x for x in d if x["kernel"].startswith("k_resize")]
 if rz:
-    w("| `k_resize` x%d | %.0f | %.0f-%.0f %% | %.0f-%.0f %% | %.0f-%.0f %% | %.0f-%.0f %% | %.0f-%.0f %% | %d | %.0f M |" % (
+    w("| `" + rz[0]["kernel"] + "` x%d | %.0f | %.0f-%.0f %% | %.0f-%.0f %% | %.0f-%.0f %% | %.0f-%.0f %% | %.0f-%.0f %% | %d | %.0f M |" % (
         len(rz), sum(x["time_us"] for x in rz), min(x["issue_active_pct"] for x in rz), max(x["issue_active_pct"] for x in rz),
         min(x["warps_active_pct"] for x in rz), max(x["warps_active_pct"] for x in rz), min(x["alu_pipe_pct"] for x in rz), max(x["alu_pipe_pct"] for x in rz),
         min(x["fma_pipe_pct"] for x in rz), max(x["fma_pipe_pct"] for x in rz), min(x["lsu_data_pipe_pct"] for x in rz), max(x["lsu_data_pipe_pct"] for x in rz),
         int(rz[0]["regs"]), sum(x["inst_executed"] for x in rz) / 1e6))
 for x in d:
-    if x["kernel"] != "k_resize":
+    if not x["kernel"].startswith("k_resize"):
         w("| `%s` | %.0f | %.0f %% | %.0f %% | %.0f %% | %.0f %% | %.0f %% | %d | %.0f M |" % (x["kernel"], x["time_us"], x["issue_active_pct"], x["warps_active_pct"],
           x["alu_pipe_pct"], x.get("fma_pipe_pct", 0), x.get("lsu_data_pipe_pct", 0), int(x["regs"]), x["inst_executed"] / 1e6))
 
@@ -85,7 +85,7 @@ for n_ in (1, 2, 4, 8):
     x = J(f); m = x["matching"]
     w("| %d | %.0f | %.0f | %.0f | %.0f | %.0f | %.2f | %.2f |" % (n_, x["value"], x["e2e"]["value"], x["e2e"]["host_copy_ceiling"]["value"], x["hd"]["value"], x["hd"]["e2e"]["value"],
       m["search_for_initialization"]["distance_evals_per_s"] / 1e12, m["search_by_projection"]["map_points_per_s"] / 1e9))
-w("\nDevice-resident extraction scales with the GPU count (no data-path collective). End to end every configuration sits at 87-94 % of what")
+w("\nDevice-resident extraction scales with the GPU count (no data-path collective). End to end every configuration sits at 87-95 % of what")
 w("the host delivers when the same buffers are copied with no kernels at all (`r2_pcie_aggregate.json`: 54 GB/s up for one rank, 99 for two,")
 w("103 for four -- GPUs 0-3 share one path -- and 161 for eight, with the downloads running the other way). The matching configs are strong")
 w("scaling of millisecond-sized jobs: SearchByProjection's greedy pass is one dependent chain per frame and stops scaling first.\n")
