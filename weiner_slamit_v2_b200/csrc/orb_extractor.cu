@@ -1164,11 +1164,28 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
         atomicMax(&best[pslot[p]], key);
     }
     __syncthreads();
-    // list order = descending creation number
+    // list order = descending creation number: a node's position is the number of live nodes created after it.  Creation
+    // numbers are unique, so the live ones are marked in a bitmap (in ccnt, dead by now) and a position is a popcount over the
+    // words above the node's bit -- a dozen words instead of a pass over all node slots (which stays as the fallback for a
+    // tree that created more nodes than the bitmap holds)
+    const int nwords = (S.nextseq + 31) >> 5;
+    const bool bitmap = nwords <= 4 * NC;
+    unsigned* live = reinterpret_cast<unsigned*>(ccnt);
+    if (bitmap) {
+        for (int i = tid; i < nwords; i += QT_THREADS) live[i] = 0u;
+        __syncthreads();
+        for (int s = tid; s < nslots; s += QT_THREADS)
+            if (ncnt[s] > 0) atomicOr(&live[nseq[s] >> 5], 1u << (nseq[s] & 31));
+        __syncthreads();
+    }
     for (int s = tid; s < nslots; s += QT_THREADS) {
         if (ncnt[s] <= 0) continue;
         const int q = nseq[s];
         int pos = 0;
+        if (bitmap) {
+            pos = __popc(live[q >> 5] & ~(0xffffffffu >> (31 - (q & 31))));        // bits above q in its own word
+            for (int w = (q >> 5) + 1; w < nwords; w++) pos += __popc(live[w]);
+        } else
         for (int t = 0; t < nslots; t++) pos += (ncnt[t] > 0 && nseq[t] > q);
         const unsigned long long key = best[s];
         const unsigned long long ord = 0xffffffffffull - (key & 0xffffffffffull);
