@@ -935,10 +935,14 @@ constexpr int SIDE_MAX_BATCH = 8;      // up to this many frames per call the bl
 constexpr int QT_POINTS_ON_CHIP = 1536;   // candidates of one tree held in shared memory; larger trees run out of global memory (measured 1024 / 1536 / 2304 / 3072 / 4600: 0.125 / 0.118 / 0.118 / 0.124 / 0.140 ms per 256 VGA frames: the footprint decides how many trees share an SM)
 
 struct QtShared {
-    int size, nslots, nextseq, E, phase, finish, cut, rounds;
+    int size, E, cut;            // initial list (written once), position of the N-cut in a largest-first round
     int warpsum[40];
 };
 
+// Exclusive block scan of data[0 .. n) in place, returns the total.  Element i is read and written by thread i % QT_THREADS.
+// `closing` = barrier after the last chunk's write-back (needed when other threads read the result next, and never for
+// `warpsum`, which the callers touch again only behind later barriers).
+template <bool closing>
 __device__ __forceinline__ int qt_block_excl_scan(int* data, int n, int* warpsum)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -968,7 +972,7 @@ __device__ __forceinline__ int qt_block_excl_scan(int* data, int n, int* warpsum
         __syncthreads();
         if (i < n) data[i] = x - v + warpsum[warp] + carry;
         carry += warpsum[32];
-        __syncthreads();
+        if (closing || base + QT_THREADS < n) __syncthreads();
     }
     return carry;
 }
@@ -1039,12 +1043,15 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
             if (ncnt[i] > 0) size++;
             if (ncnt[i] > 1) elist[E++] = i;
         }
-        S.size = size; S.nslots = nIni; S.nextseq = nIni; S.E = E; S.phase = 1; S.finish = 0; S.rounds = 0;
+        S.size = size; S.E = E;
     }
     __syncthreads();
 
-    while (!S.finish) {
-        const int E = S.E, size = S.size, nslots = S.nslots, nextseq = S.nextseq, phase = S.phase;
+    // The state of the list (node count, slots in use, next creation number, nodes to split, phase) is carried in registers:
+    // every thread derives the same next state from the same scan totals, so a round needs no bookkeeping barrier.
+    int E = S.E, size = S.size, nslots = nIni, nextseq = nIni, phase = 1, rounds = 0;
+    bool finish = false;
+    while (!finish) {
         // A: rank the nodes to split, remember their split point
         for (int k = tid; k < E; k += QT_THREADS) {
             const int s = elist[k];
@@ -1062,24 +1069,20 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
         }
         __syncthreads();
         // C: children per node, prefix sums in processing order, N-cut
-        for (int k = tid; k < E; k += QT_THREADS) {
-            const int c = (ccnt[4 * k] > 0) + (ccnt[4 * k + 1] > 0) + (ccnt[4 * k + 2] > 0) + (ccnt[4 * k + 3] > 0);
-            scanC[k] = c;
-            scanG[k] = c - 1;
-        }
-        __syncthreads();
-        const int totalC = qt_block_excl_scan(scanC, E, S.warpsum);
-        const int totalG = qt_block_excl_scan(scanG, E, S.warpsum);
+        // (a split replaces one node by its c children: the list grows by c - 1, so the running growth before node k is
+        // scanC[k] - k and one scan serves both; the scan reads element k in the thread that wrote it: no barrier in between)
+        for (int k = tid; k < E; k += QT_THREADS)
+            scanC[k] = (ccnt[4 * k] > 0) + (ccnt[4 * k + 1] > 0) + (ccnt[4 * k + 2] > 0) + (ccnt[4 * k + 3] > 0);
+        const int totalC = qt_block_excl_scan<false>(scanC, E, S.warpsum);
         if (phase == 2) {
-            for (int k = tid; k < E; k += QT_THREADS) {
-                const int gk = (k + 1 < E ? scanG[k + 1] : totalG) - scanG[k];
-                if (size + scanG[k] + gk >= N) atomicMin(&S.cut, k);        // break at :743
-            }
+            __syncthreads();                                                 // the cut reads its neighbour's scan element
+            for (int k = tid; k < E; k += QT_THREADS)
+                if (size + (k + 1 < E ? scanC[k + 1] : totalC) - (k + 1) >= N) atomicMin(&S.cut, k);        // break at :743
             __syncthreads();
         }
         const int Ecut = S.cut < E ? S.cut + 1 : E;
-        const int grow = Ecut < E ? scanG[Ecut] : totalG;
         const int made = Ecut < E ? scanC[Ecut] : totalC;
+        const int grow = made - Ecut;
         // D: create the children (n1..n4 order = quadrant order)
         for (int k = tid; k < Ecut; k += QT_THREADS) {
             const int s = elist[k];
@@ -1091,7 +1094,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
                 const int cnt = ccnt[4 * k + q];
                 int slot = -1;
                 if (cnt > 0) {
-                    slot = j == 0 ? s : nslots + scanG[k] + j - 1;
+                    slot = j == 0 ? s : nslots + scanC[k] - k + j - 1;
                     nrect[slot] = make_short4((q & 1) ? (short)m.x : r.x, (q & 1) ? r.y : (short)m.x,
                                               (q & 2) ? (short)m.y : r.z, (q & 2) ? r.w : (short)m.y);
                     ncnt[slot] = cnt;
@@ -1107,31 +1110,32 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
             const int k = erank[pslot[p]];
             if (k >= 0 && k < Ecut) pslot[p] = (uint16_t)cslot[4 * k + qt_quadrant(pts[p], emid[k])];
         }
-        __syncthreads();
-        // F/G: clear ranks, collect the children that can still be split (creation order)
+        // F/G: collect the children that can still be split (creation order), clear the ranks.  One scan element per split
+        // node = its children with more than one point, so the scan is over Ecut elements, not 4 Ecut; nothing it writes is
+        // read by step E, whose readers of erank are all past the scan's first barrier before the ranks are cleared
+        for (int k = tid; k < Ecut; k += QT_THREADS)
+            scanG[k] = (ccnt[4 * k] > 1) + (ccnt[4 * k + 1] > 1) + (ccnt[4 * k + 2] > 1) + (ccnt[4 * k + 3] > 1);
+        const int newE = qt_block_excl_scan<false>(scanG, Ecut, S.warpsum);
         for (int k = tid; k < E; k += QT_THREADS) erank[elist[k]] = -1;
-        for (int i = tid; i < 4 * Ecut; i += QT_THREADS) ccnt[i] = ccnt[i] > 1 ? 1 : 0;
-        __syncthreads();
-        const int newE = qt_block_excl_scan(ccnt, 4 * Ecut, S.warpsum);
-        for (int i = tid; i < 4 * Ecut; i += QT_THREADS) {
-            const int s = cslot[i];
-            if (s >= 0 && ncnt[s] > 1) elist2[ccnt[i]] = s;
+        for (int k = tid; k < Ecut; k += QT_THREADS) {
+            int at = scanG[k];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (ccnt[4 * k + q] > 1) elist2[at++] = cslot[4 * k + q];
         }
         __syncthreads();
-        if (tid == 0) {
+        {
             const int nsize = size + grow;
-            int fin = 0, nphase = phase;
-            if (nsize >= N || nsize == size) fin = 1;                        // :682 / :747
-            else if (phase == 1 && nsize + 3 * newE > N) nphase = 2;         // :686
-            if (++S.rounds > 4096) { fin = 1; atomicOr(P.status, STATUS_QT_RUNAWAY); }
-            if (nslots + grow > NC) { fin = 1; atomicOr(P.status, STATUS_KP_OVERFLOW); }
-            S.size = nsize; S.nslots = nslots + grow; S.nextseq = nextseq + made; S.E = newE;
-            S.phase = nphase; S.finish = fin;
+            if (nsize >= N || nsize == size) finish = true;                              // :682 / :747
+            else if (phase == 1 && nsize + 3 * newE > N) phase = 2;                      // :686
+            if (++rounds > 4096) { finish = true; if (tid == 0) atomicOr(P.status, STATUS_QT_RUNAWAY); }
+            if (nslots + grow > NC) { finish = true; if (tid == 0) atomicOr(P.status, STATUS_KP_OVERFLOW); }
+            size = nsize; nslots += grow; nextseq += made; E = newE;
         }
-        __syncthreads();
-        if (!S.finish) {
-            if (S.phase == 1) {
-                // next breadth pass walks the list front to back = newest child first
+        if (!finish) {
+            if (phase == 1) {
+                // next breadth pass walks the list front to back = newest child first (every thread writes the entry it
+                // reads in the next round's step A: no barrier)
                 for (int k = tid; k < newE; k += QT_THREADS) elist[k] = elist2[newE - 1 - k];
             } else {
                 // largest first; equal counts: later-created node first
@@ -1145,14 +1149,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
                     }
                     elist[pos] = s;
                 }
+                __syncthreads();
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // best response per leaf; ties go to the earlier candidate in the reference's order
     // (cells row-major, row-major inside a cell), recovered from the coordinates (:755-773)
-    const int nslots = S.nslots;
     for (int s = tid; s < nslots; s += QT_THREADS) best[s] = 0ull;
     __syncthreads();
     for (int p = tid; p < n; p += QT_THREADS) {
@@ -1168,7 +1172,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
     // numbers are unique, so the live ones are marked in a bitmap (in ccnt, dead by now) and a position is a popcount over the
     // words above the node's bit -- a dozen words instead of a pass over all node slots (which stays as the fallback for a
     // tree that created more nodes than the bitmap holds)
-    const int nwords = (S.nextseq + 31) >> 5;
+    const int nwords = (nextseq + 31) >> 5;
     const bool bitmap = nwords <= 4 * NC;
     unsigned* live = reinterpret_cast<unsigned*>(ccnt);
     if (bitmap) {
@@ -1192,7 +1196,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const ExtractParams P)
         if (pos < g.kpCap) lkp[pos] = (uint32_t)(ord & 0xffffff) | ((uint32_t)(key >> 40) << 24);
         else atomicOr(P.status, STATUS_KP_OVERFLOW);
     }
-    if (tid == 0) P.lkpCount[frame * P.nlevels + l] = min(S.size, g.kpCap);
+    if (tid == 0) P.lkpCount[frame * P.nlevels + l] = min(size, g.kpCap);
 }
 
 // ======================================================================================
