@@ -85,10 +85,11 @@ for n_ in (1, 2, 4, 8):
     x = J(f); m = x["matching"]
     w("| %d | %.0f | %.0f | %.0f | %.0f | %.0f | %.2f | %.2f |" % (n_, x["value"], x["e2e"]["value"], x["e2e"]["host_copy_ceiling"]["value"], x["hd"]["value"], x["hd"]["e2e"]["value"],
       m["search_for_initialization"]["distance_evals_per_s"] / 1e12, m["search_by_projection"]["map_points_per_s"] / 1e9))
-w("\nDevice-resident extraction scales with the GPU count (no data-path collective). End to end every configuration sits at 87-95 % of what")
-w("the host delivers when the same buffers are copied with no kernels at all (`r2_pcie_aggregate.json`: 54 GB/s up for one rank, 99 for two,")
-w("103 for four -- GPUs 0-3 share one path -- and 161 for eight, with the downloads running the other way). The matching configs are strong")
-w("scaling of millisecond-sized jobs: SearchByProjection's greedy pass is one dependent chain per frame and stops scaling first.\n")
+w("\nDevice-resident extraction scales with the GPU count (no data-path collective). End to end every configuration sits at 87-100 % of what")
+w("the host delivers when the same buffers are copied with no kernels at all -- the `copy ceiling` column, measured inside each run, because it")
+w("depends on the box the run landed on (`r2_pcie_aggregate.json` is one such box: 54 GB/s up for one rank, 99 for two, 103 for four -- its GPUs")
+w("0-3 share one path -- and 161 for eight; the 4-GPU box of this table delivered 540 k frames/s, the 8-GPU box 515 k). The matching configs are")
+w("strong scaling of millisecond-sized jobs.\n")
 
 m = l["matching"]
 w("## matching rows (%s_bench.json, one GPU)\n" % btag)
