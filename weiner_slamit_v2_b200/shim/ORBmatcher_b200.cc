@@ -18,6 +18,7 @@
 // The pointer graph is flattened to structure-of-arrays on the host, the search runs in CUDA
 // through include/orb_b200.h, and the results are written back into the fields the reference
 // mutates.  No CPU search path exists here; on a device error the call logs and reports 0 matches.
+#include <atomic>
 #include "ORBmatcher.h"
 
 #include <cstdio>
@@ -36,17 +37,24 @@ namespace
 {
 // One device scratch handle per host thread: ORBmatcher is stateless and is used concurrently from
 // the Tracking, LocalMapping and LoopClosing threads (S/System.cc:156,160).
+// The CUDA device the matcher handles of this process live on (orbb200_shim_set_matcher_device; default 0).  A thread's
+// handle follows the setting the next time it is used.
+std::atomic<int> gMatcherDevice(0);
+
 struct ThreadMatcher {
-    orbb200_matcher* h; int items, points;
-    ThreadMatcher() : h(0), items(0), points(0) {}
+    orbb200_matcher* h; int items, points, device;
+    ThreadMatcher() : h(0), items(0), points(0), device(0) {}
     ~ThreadMatcher() { if (h) orbb200_matcher_destroy(h); }
     orbb200_matcher* get(int needPoints)
     {
-        if (h && needPoints <= points) return h;
+        const int want = gMatcherDevice.load();
+        if (h && needPoints <= points && device == want) return h;
         if (h) orbb200_matcher_destroy(h);
         h = 0;
+        if (needPoints < points) needPoints = points;
         points = needPoints < 4096 ? 4096 : needPoints;
-        if (orbb200_matcher_create(1, points, 0, &h) != ORBB200_OK) {
+        device = want;
+        if (orbb200_matcher_create(1, points, device, &h) != ORBB200_OK) {
             std::fprintf(stderr, "ORBmatcher(B200): %s\n", orbb200_last_error());
             h = 0; points = 0;
         }
@@ -81,6 +89,11 @@ void FrameBounds(float b[4])
     b[0] = Frame::mnMinX; b[1] = Frame::mnMinY; b[2] = Frame::mnMaxX; b[3] = Frame::mnMaxY;
 }
 }  // namespace
+
+// Selects the CUDA device of the matcher handles (one per host thread); call it before the threads that match start, e.g.
+// next to the ORBextractor's device argument.  Declared in the integrator's code as
+//     namespace ORB_SLAM2 { void orbb200_shim_set_matcher_device(int device); }
+void orbb200_shim_set_matcher_device(int device) { gMatcherDevice.store(device < 0 ? 0 : device); }
 
 int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b)
 {
