@@ -436,10 +436,12 @@ def test_handles_on_two_devices_interleaved():
 @pytest.mark.parametrize("fast,describe,resize", [("1", "1", "1"), ("1", "3", "3"), ("2", "1", "3"), ("2", "3", "1")])
 def test_first_generation_kernels_stay_bit_exact(fast, describe, resize, monkeypatch):
     """Round 1's k_fast / k_describe / k_resize stay selectable for A/B runs (ORBB200_FAST_VARIANT / ORBB200_DESCRIBE_VARIANT /
-    ORBB200_RESIZE_VARIANT, read when a handle is created): every combination gives the oracle's result."""
+    ORBB200_RESIZE_VARIANT, ORBB200_FAST_TILE, read when a handle is created): every combination gives the oracle's result."""
     monkeypatch.setenv("ORBB200_FAST_VARIANT", fast)
     monkeypatch.setenv("ORBB200_DESCRIBE_VARIANT", describe)
     monkeypatch.setenv("ORBB200_RESIZE_VARIANT", resize)
+    if resize == "1":
+        monkeypatch.setenv("ORBB200_FAST_TILE", "26")      # k_fast2's 26-word tile also where the 22-word one would do
     frames = np.stack([synthetic_frame(70 + i) for i in range(3)])
     ex = ORBextractor(*PARAMS, max_batch=3)
     orc = O.OracleExtractor(*PARAMS)

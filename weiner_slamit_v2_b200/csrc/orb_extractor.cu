@@ -639,7 +639,7 @@ struct FastMaps { CUtensorMap m[MAXL]; };
 template <int TPW, int TH>
 struct FastGeo2 {
     static constexpr int SP = TPW * 2 - 4;                    // score-map pitch in bytes (multiple of 4)
-    static constexpr int BW = TPW == 26 ? 64 : 96;            // TMA box: BW bytes x TH rows (15 alignment columns + window + 5)
+    static constexpr int BW = TPW <= 26 ? 64 : 96;            // TMA box: BW bytes x TH rows (15 alignment columns + window + 5)
     static constexpr int QCAP = (TPW - 2) * (TH - 6);
     static constexpr int QBYTES = 2 * QCAP + 64;
     static constexpr int RAW_BYTES = BW * TH;
@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(32) k_fast2(const __grid_constant__ ExtractPar
     uint32_t* klist = tw;
     const uint32_t bar = smem_u32(smem + G::BAR_OFF);
 
+    pdl_trigger();       // (lets the second of the two FAST launches start early; no effect otherwise)
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1898,6 +1899,8 @@ struct orbb200_extractor {
     ResizeMaps resizeMaps;     // k_resize3's source-window maps (m[1] is encoded per call: level 0 may be the caller's buffer)
     int resizeVariant;         // 3 = k_resize3 (source-row walk over TMA-staged windows, default), 1 = k_resize (ORBB200_RESIZE_VARIANT=1 at create, kept for A/B runs)
     BlurMaps blurMaps;         // k_blur's window maps (level 0 per call)
+    int fastSmallCells;        // k_fast2: the first fastSmallCells entries of the cell table are at most 33 wide and run in the <22,42> instantiation
+                               // (6.7 KB of shared memory per cell instead of 8.0: 29 cells per SM instead of 25), the rest in <26,42>
     FastMaps fastMaps;         // tensor maps of the pyramid levels (level 0 is encoded per call: it may be the caller's buffer)
     DescMaps descMaps;         // k_describe2's patch maps of the unblurred and the blurred levels (box 64 x 37)
     int descVariant, maxLevelKpCap;   // 3 = k_describe3 (default), 1 = k_describe (ORBB200_DESCRIBE_VARIANT=1 at create, kept for A/B runs)
@@ -1913,6 +1916,7 @@ struct orbb200_extractor {
     cudaStream_t side; cudaEvent_t evFork, evJoin;   // the blur runs beside the quadtree (it needs only the pyramid)
     bool pending;                        // an orbb200_extract_host_async call has not been waited for yet
     std::map<int, cudaGraphExec_t> graphs;   // host path, small batches: the kernel sequence of one call as a CUDA graph, by batch size
+    std::map<int, int> graphLaunches;                // kernels inside each of them
     std::vector<void*> allocs;
 };
 
@@ -2011,6 +2015,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     h->width = width; h->height = height; h->maxBatch = max_batch; h->device = device; h->blurTaps = blur_taps ? 1 : 0;
     h->pinned = nullptr; h->pinnedBytes = 0; h->lastLaunches = 0; h->lastBatch = 0; h->lastIn = nullptr;
     h->profiling = false;
+    h->fastSmallCells = 0;
     h->chunkOverride = 0;
     if (const char* e = getenv("ORBB200_CHUNKS")) h->chunkOverride = std::max(0, std::min(8, atoi(e)));
     for (int i = 0; i < 6; i++) h->ev[i] = nullptr;
@@ -2150,9 +2155,15 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
     } else
     h->fastSmem = (size_t)FAST_WARPS * (P.fastLarge ? FastGeo<38, 64>::WARP_BYTES : FastGeo<26, 42>::WARP_BYTES);
     // k_fast2's cell table: window origin and size, level, offset of the cell inside the level (:807-822, :840-841)
+    // (levels whose cells fit the 22-word tile come first: they run in their own launch, see launch_kernels)
+    bool smallTile = h->fastVariant == 2 && !P.fastLarge;
+    if (const char* e = getenv("ORBB200_FAST_TILE")) if (atoi(e) == 26) smallTile = false;      // A/B switch: the 26-word tile for every cell
     std::vector<int4> cellTab;
+    for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) h->fastSmallCells = (int)cellTab.size();
     for (int l = 0; l < nlevels; l++) {
         const LevelGeo& g = P.lv[l];
+        if ((smallTile && FastGeo2<22, 42>::fits(g.wCell, g.hCell)) != (pass == 0)) continue;
         for (int ci = 0; ci < g.nRows; ci++)
             for (int cj = 0; cj < g.nCols; cj++) {
                 const int iniY = BORDER + ci * g.hCell, iniX = BORDER + cj * g.wCell;
@@ -2161,6 +2172,7 @@ extern "C" int orbb200_extractor_create(int nfeatures, float scaleFactor, int nl
                 if (ww < 7 || wh < 7) continue;                                               // cv::FAST finds nothing in < 7 px
                 cellTab.push_back(make_int4(iniX | (iniY << 16), ww | (wh << 8) | (l << 16), (cj * g.wCell) | ((ci * g.hCell) << 16), 0));
             }
+    }
     }
     P.nCells = (int)cellTab.size();
     // k_quadtree shared memory: 88 bytes per node slot + 6 bytes per candidate held on chip
@@ -2363,9 +2375,23 @@ static int launch_kernels(orbb200_extractor* h, const ExtractParams& P, int batc
         int rc = encode_level_map(&h->fastMaps.m[0], P.in, h->width, h->height, batch, (size_t)P.inPitch, (size_t)P.inFrameStride,
                                   P.fastLarge ? FastGeo2<38, 64>::BW : FastGeo2<26, 42>::BW, P.fastLarge ? 64 : 42);
         if (rc != ORBB200_OK) return rc;
-        const dim3 grid(P.nCells, batch);
-        if (P.fastLarge) k_fast2<38, 64><<<grid, 32, h->fastSmem, st>>>(P, h->fastMaps);
-        else k_fast2<26, 42><<<grid, 32, h->fastSmem, st>>>(P, h->fastMaps);
+        const int nSmall = h->fastSmallCells;
+        if (P.fastLarge) k_fast2<38, 64><<<dim3(P.nCells, batch), 32, h->fastSmem, st>>>(P, h->fastMaps);
+        else {
+            // the few cells wider than 33 px first, in the 26-word tile; the others follow in the 22-word tile as a dependent launch
+            // that waits for nothing (the two grids touch different levels): its blocks fill the SMs as the first grid drains
+            if (nSmall < P.nCells) {
+                ExtractParams Pw = P;
+                Pw.cells += nSmall;
+                k_fast2<26, 42><<<dim3(P.nCells - nSmall, batch), 32, FastGeo2<26, 42>::SMEM_BYTES, st>>>(Pw, h->fastMaps);
+                ORB_CHECK_LAUNCH("k_fast"); launches++;
+            }
+            if (nSmall > 0 && nSmall < P.nCells) {
+                const cudaError_t le = launch_pdl(k_fast2<22, 42>, dim3(nSmall, batch), 32, FastGeo2<22, 42>::SMEM_BYTES, st, P, h->fastMaps);
+                if (le != cudaSuccess) { set_error("launch of k_fast failed: %s", cudaGetErrorString(le)); return ORBB200_ECUDA; }
+            } else if (nSmall > 0)      // (alone it must wait for the pyramid like any kernel: a plain launch)
+                k_fast2<22, 42><<<dim3(nSmall, batch), 32, FastGeo2<22, 42>::SMEM_BYTES, st>>>(P, h->fastMaps);
+        }
     } else {
         const dim3 grid((h->totalCells + FAST_WARPS - 1) / FAST_WARPS, batch);
         if (P.fastLarge) k_fast<38, 64><<<grid, FAST_WARPS * 32, h->fastSmem, st>>>(P);
@@ -2474,8 +2500,9 @@ static int enqueue(orbb200_extractor* h, const uint8_t* d_images, int batch, siz
             ORB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
             cudaGraphDestroy(graph);
             it = h->graphs.insert(std::make_pair(batch, exec)).first;
+            h->graphLaunches[batch] = launches;
         } else {
-            launches = P.nlevels - 1 + 4;
+            launches = h->graphLaunches[batch];
         }
         ORB_CUDA(cudaGraphLaunch(it->second, st));
     } else {
