@@ -1102,14 +1102,14 @@ def run_stereo(local, steps):
 def _issue_profile(kernel):
     """Issue-slot use and instruction count of `kernel` from the committed ncu --set full summary: the path is
     integer/byte work bound by instruction issue, so this is the number that explains the HBM fraction."""
-    for tag in ("r2c", "r2b", "r2a", "r1p", "r1o", "r1n", "r1m", "r1l", "r1k"):
-        p = os.path.join(ROOT, "profiles", tag + "_ncu_full_summary.json")
-        if os.path.exists(p):
-            with open(p) as f:
-                for e in json.load(f):
-                    if e["kernel"] in (kernel, kernel + "2", kernel + "3"):
-                        return {"issue_slots_busy_pct": e["issue_active_pct"], "warp_instructions_per_launch": e["inst_executed"],
-                                "dram_pct_of_peak": e["dram_pct"], "source": "profiles/%s_ncu_full_summary.json" % tag}
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.json")), reverse=True):      # newest round / step first
+        with open(p) as f:
+            rows = [e for e in json.load(f) if e["kernel"] in (kernel, kernel + "2", kernel + "3")]
+        if rows:
+            e = max(rows, key=lambda r: r["inst_executed"])       # (FAST is two launches: the one that holds nearly all cells)
+            return {"issue_slots_busy_pct": e["issue_active_pct"], "warp_instructions_per_launch": sum(r["inst_executed"] for r in rows),
+                    "dram_pct_of_peak": e["dram_pct"], "source": "profiles/" + os.path.basename(p)}
     return None
 
 

@@ -5,13 +5,14 @@
 //   IC_Angle :82-109, GaussianBlur call :1117, computeOrbDescriptor :113-152, operator() :1064-1136.
 // Everything here is integer / byte streaming work (HBM- and issue-bound): no tensor cores.
 //
-// Kernel map (one launch each per batch unless noted):
-//   k_resize     x (nlevels-1)  pyramid level l from level l-1, 11-bit fixed-point bilinear
-//   k_fast       one CTA per 30-px detection cell: FAST-9/16 score map in shared memory, 3x3 NMS,
-//                iniThFAST -> minThFAST retry decided per cell, candidates appended per (frame,level)
+// Kernel map (one launch each per batch unless noted; round 1's k_resize / k_fast / k_describe stay selectable for A/B runs):
+//   k_resize3    x (nlevels-1)  pyramid level l from level l-1, 11-bit fixed-point bilinear; a warp = 64 columns x 16 rows of two
+//                frames behind its own TMA window, one pass over the source rows; the launches are chained (griddepcontrol)
+//   k_fast2      one warp = one 30-px detection cell (TMA window, 16-bit tile): FAST-9/16 in three passes, 3x3 NMS, iniThFAST ->
+//                minThFAST retry decided per cell, candidates appended per (frame,level); two launches when some cells are wide
 //   k_quadtree   one CTA per (frame,level): DistributeOctTree as parallel rounds over a node table
-//   k_blur       7x7 fixed-point separable Gaussian, shared-memory tiles
-//   k_describe   one warp per keypoint: IC_Angle moments (warp reduction) + steered BRIEF + output
+//   k_blur       7x7 fixed-point separable Gaussian, persistent warps over 128 x 24 tiles (one TMA window per tile)
+//   k_describe3  persistent warps over groups of 8 keypoints: IC_Angle moments + steered BRIEF + output, TMA patches
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <algorithm>
 #include <cmath>
