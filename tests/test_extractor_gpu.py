@@ -256,6 +256,24 @@ def test_random_geometries_odd_batch(seed):
         assert np.array_equal(desc[f, :counts[f]], do)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(size=(1920, 1080), params=(3000, 1.2, 8, 20, 7)),     # full HD: 64 x 36 FAST cells on level 0, 8 levels
+    dict(size=(160, 120), params=(200, 1.2, 3, 20, 7)),        # a thumbnail: a handful of cells per level
+    dict(size=(96, 80), params=(50, 1.2, 1, 20, 7)),           # close to the smallest legal frame (one level, 2 x 1 cells)
+])
+def test_very_large_and_very_small_frames(cfg):
+    w, h = cfg["size"]
+    p = cfg["params"]
+    frames = np.stack([synthetic_frame(600 + i, w, h) for i in range(2)])
+    ex = ORBextractor(*p, width=w, height=h, max_batch=2)
+    orc = O.OracleExtractor(*p)
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(2):
+        ko, do = _compare_frame(ex, orc, frames, f)
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], do)
+
+
 def test_rejected_geometries():
     from weiner_slamit_v2_b200 import OrbB200Error
     with pytest.raises(OrbB200Error):
