@@ -1,3 +1,4 @@
+# developer tool (run on the GPU box): k_blur with other tile heights / blocks per SM, per-stage times of each build
 F=weiner_slamit_v2_b200/csrc/orb_extractor.cu
 cp $F /tmp/orig.cu
 run() { sh weiner_slamit_v2_b200/csrc/build.sh 2>&1 | grep -E " error" ; echo "$1: $(timeout 200 python tools/stage_times.py 256 2>&1 | tail -1)"; cp /tmp/orig.cu $F; }
