@@ -111,6 +111,22 @@ def test_other_parameters_1280x720_2000():
         assert np.array_equal(desc[f, :counts[f]], do)
 
 
+def test_full_batch_code_path_at_1280x720():
+    """More than 8 frames per call switch the launch shapes (the blur behind the quadtree, descriptors in groups of 8 keypoints):
+    a batch of 11 HD frames (an odd count: the pyramid pairs frames) through extract_device against the oracle."""
+    p = (2000, 1.2, 8, 20, 7)
+    distinct = [synthetic_frame(20 + i, 1280, 720) for i in range(3)]
+    frames = np.stack([distinct[i % 3] for i in range(11)])
+    ex = ORBextractor(*p, width=1280, height=720, max_batch=11)
+    orc = O.OracleExtractor(*p)
+    want = [orc(f) for f in distinct]
+    kps, desc, counts = ex.extract_batch(frames)
+    for f in range(11):
+        ko, do = want[f % 3]
+        assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes(), f
+        assert np.array_equal(desc[f, :counts[f]], do), f
+
+
 def test_tables_match_oracle():
     ex = ORBextractor(*PARAMS)
     orc = O.OracleExtractor(*PARAMS)
